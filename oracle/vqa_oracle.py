@@ -1,0 +1,399 @@
+"""CPU oracle for the VQA forward hot path of Jayie/vqa-collection.
+
+THIS FILE IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  It is a CPU restatement
+(torch-CPU tensor ops for the floating-point contractions, numpy for the box
+geometry) of the reference algorithm.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it, and only as the checker / the CPU baseline.
+Nothing under ``vqa_collection_b200/`` imports it.
+
+Parity status: PINNED.  ``tests/golden/*.npz`` hold outputs of the real
+reference (``/root/reference``, imported unmodified by
+``tests/golden/make_golden.py``) on seeded inputs; ``tests/test_oracle_golden.py``
+checks every function here against them.  The one exception is the float32
+``arctan2`` rounding inside ``spatial_relation`` (numpy SIMD path, host
+dependent): pinned only on integer-grid boxes and the known-answer
+table of SURVEY.md §8a-R.
+
+Every function cites the reference file:line it follows (paths relative to the
+reference repository root).  All functions compute in the dtype of their
+inputs, so feeding float64 weights/inputs yields a float64 "truth" run.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, asdict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------
+# configuration / synthetic data
+# ----------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Config:
+    """Hyper-parameters of the path (reference defaults: main.py:60-80)."""
+    ntoken: int = 20000
+    v_dim: int = 2048
+    embed_dim: int = 300
+    hidden_dim: int = 1024
+    ans_dim: int = 3129
+    num_objs: int = 36
+    q_len: int = 14
+    c_len: int = 20
+    num_labels: int = 12
+    conv_layer: int = 1
+    relation: bool = False          # encoder_type 'relation' vs 'base'
+
+    def as_dict(self):
+        return asdict(self)
+
+
+FULL = Config()
+FULL_REGAT = Config(relation=True)
+# small config: every dimension shrunk, same structure (fast CPU tests)
+SMALL = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200,
+               relation=False)
+SMALL_REGAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200,
+                     relation=True)
+
+
+def _uniform(gen, shape, bound):
+    return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2.0 - 1.0) * bound
+
+
+def make_weights(cfg: Config, seed: int = 1111, sharpen_att: float = 100.0,
+                 sharpen_cls: float = 4.0, sharpen_gcn: float = 4.0) -> dict:
+    """Seeded synthetic weights, keyed by the reference's parameter names
+    (probed listing of ``Wrapper.state_dict()``), plus the
+    unregistered GCN layer tensors (gcn.py:188-190) under ``gcn.{i}.*``.
+
+    Distributions follow the reference's default initialisers (nn.Linear /
+    nn.GRU / nn.Embedding defaults; gcn.py:69-76 for the label bias) but are
+    drawn by this function from ONE torch.Generator so that the same seed gives
+    the same weights on any host.  ``weight_g`` is ``‖v‖_F`` (weight_norm's
+    init) times an optional "trained-like" sharpening factor so
+    that attention and answer distributions are not flat.
+    """
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    H, V, E, A = cfg.hidden_dim, cfg.v_dim, cfg.embed_dim, cfg.ans_dim
+    w = {}
+
+    emb = torch.randn((cfg.ntoken + 1, E), generator=g, dtype=torch.float32)
+    emb[cfg.ntoken].zero_()                       # padding_idx row (encoder.py:128)
+    w["encoder.embedding.weight"] = emb
+    kb = 1.0 / math.sqrt(H)
+    w["encoder.q_rnn.rnn.weight_ih_l0"] = _uniform(g, (3 * H, E), kb)
+    w["encoder.q_rnn.rnn.weight_hh_l0"] = _uniform(g, (3 * H, H), kb)
+    w["encoder.q_rnn.rnn.bias_ih_l0"] = _uniform(g, (3 * H,), kb)
+    w["encoder.q_rnn.rnn.bias_hh_l0"] = _uniform(g, (3 * H,), kb)
+
+    def wn_linear(prefix, out_dim, in_dim, gscale=1.0):
+        b = 1.0 / math.sqrt(in_dim)
+        v = _uniform(g, (out_dim, in_dim), b)
+        w[prefix + ".bias"] = _uniform(g, (out_dim,), b)
+        w[prefix + ".weight_g"] = (torch.norm(v) * gscale).reshape(())
+        w[prefix + ".weight_v"] = v
+
+    wn_linear("encoder.attention.W_v.main.0", H, V)
+    wn_linear("encoder.attention.W_q.main.0", H, H)
+    wn_linear("encoder.attention.linear", 1, H, sharpen_att)
+    wn_linear("encoder.q_net.main.0", H, H)
+    wn_linear("predictor.v_net.main.0", H, V)
+    wn_linear("predictor.classifier.main.0", 2 * H, H)
+    wn_linear("predictor.classifier.main.3", A, 2 * H, sharpen_cls)
+
+    if cfg.relation:
+        for i in range(cfg.conv_layer):
+            p = f"gcn.{i}."
+            bv = 1.0 / math.sqrt(V)
+            w[p + "bias"] = _uniform(g, (cfg.num_labels, V), bv)
+            for d in range(3):
+                w[p + f"weight.{d}.weight"] = _uniform(g, (V, V), bv)
+            for nm in ("wa", "wb"):
+                w[p + f"dot_product.{nm}.weight"] = _uniform(g, (V, V), bv) * sharpen_gcn
+                w[p + f"dot_product.{nm}.bias"] = _uniform(g, (V,), bv)
+    return w
+
+
+def make_boxes(B: int, K: int, seed: int, W: int = 640, H: int = 480,
+               grid: bool = True) -> np.ndarray:
+    """Seeded synthetic boxes [B,K,4] float32 (x0,y0,x1,y1).  ``grid=True``:
+    integer-grid boxes on which label parity is bit-exact;
+    ``grid=False``: continuous-uniform boxes for the statistical gate."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    if grid:
+        x0 = torch.randint(0, W - 16, (B, K), generator=g).float()
+        y0 = torch.randint(0, H - 16, (B, K), generator=g).float()
+        bw = torch.randint(8, 201, (B, K), generator=g).float()
+        bh = torch.randint(8, 201, (B, K), generator=g).float()
+    else:
+        x0 = torch.rand((B, K), generator=g) * (W - 16)
+        y0 = torch.rand((B, K), generator=g) * (H - 16)
+        bw = 8 + torch.rand((B, K), generator=g) * 192
+        bh = 8 + torch.rand((B, K), generator=g) * 192
+    x1 = torch.minimum(x0 + bw, torch.tensor(float(W - 1)))
+    y1 = torch.minimum(y0 + bh, torch.tensor(float(H - 1)))
+    return torch.stack([x0, y0, x1, y1], dim=2).numpy().astype(np.float32)
+
+
+def make_batch(cfg: Config, B: int, seed: int, W: int = 640, H: int = 480) -> dict:
+    """Seeded synthetic batch in the reference's wire format (dataset.py:96-104):
+    img f32 [B,K,V] ~U[0,1); q int64 [B,T]; c int64 [B,c_len]; cap_len; a f64
+    sparse soft scores; bbox f32 [B,K,4] (integer grid) and graph f64 [B,K,K]
+    = relation_graph(bbox) when cfg.relation."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    batch = {
+        "img": torch.rand((B, cfg.num_objs, cfg.v_dim), generator=g, dtype=torch.float32),
+        "q": torch.randint(0, cfg.ntoken, (B, cfg.q_len), generator=g),
+        "c": torch.randint(0, cfg.ntoken, (B, cfg.c_len), generator=g),
+        "cap_len": torch.full((B,), cfg.c_len, dtype=torch.int64),
+    }
+    a = torch.zeros((B, cfg.ans_dim), dtype=torch.float64)
+    idx = torch.randint(0, cfg.ans_dim, (B, 3), generator=g)
+    val = torch.randint(1, 4, (B, 3), generator=g).double() / 3.0
+    a.scatter_(1, idx, val)
+    batch["a"] = a
+    if cfg.relation:
+        bbox = make_boxes(B, cfg.num_objs, seed + 7919, W, H, grid=True)
+        batch["bbox"] = torch.from_numpy(bbox)
+        batch["wh"] = (W, H)
+        graph = np.stack([relation_graph(bbox[i], W, H) for i in range(B)])
+        batch["graph"] = torch.from_numpy(graph)          # float64, like the loader
+    return batch
+
+
+# ----------------------------------------------------------------------------
+# building blocks
+# ----------------------------------------------------------------------------
+def weight_norm_scale(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """s = g / ‖v‖_F — the scalar of weight_norm(dim=None) (modules.py:38;
+    torch ``_weight_norm(v, g, -1)`` = ``v * (g / v.norm())``)."""
+    return g / torch.norm(v)
+
+
+def wn_weight(v, g):
+    return v * weight_norm_scale(v, g)
+
+
+def fcnet1(x, W, prefix):
+    """1-layer FCNet: ReLU(Linear_wn(x)) (modules.py:35-38,55)."""
+    wt = wn_weight(W[prefix + ".main.0.weight_v"], W[prefix + ".main.0.weight_g"])
+    return torch.relu(F.linear(x, wt, W[prefix + ".main.0.bias"]))
+
+
+def gru_last(x, W, prefix="encoder.q_rnn.rnn"):
+    """nn.GRU(1 layer, batch_first, h0=0), last time step (modules.py:139-159).
+    Gate order [r; z; n]; n uses r ⊙ (W_hn h + b_hn) (torch GRU semantics)."""
+    w_ih, w_hh = W[prefix + ".weight_ih_l0"], W[prefix + ".weight_hh_l0"]
+    b_ih, b_hh = W[prefix + ".bias_ih_l0"], W[prefix + ".bias_hh_l0"]
+    B, T, _ = x.shape
+    Hd = w_hh.shape[1]
+    h = torch.zeros((B, Hd), dtype=x.dtype)
+    gi_all = F.linear(x, w_ih, b_ih)                       # [B,T,3H]
+    for t in range(T):
+        gi = gi_all[:, t]
+        gh = F.linear(h, w_hh, b_hh)
+        r = torch.sigmoid(gi[:, :Hd] + gh[:, :Hd])
+        z = torch.sigmoid(gi[:, Hd:2 * Hd] + gh[:, Hd:2 * Hd])
+        n = torch.tanh(gi[:, 2 * Hd:] + r * gh[:, 2 * Hd:])
+        h = (1.0 - z) * n + z * h
+    return h
+
+
+def question_embedding(q_tokens, W):
+    """embedding → GRU last state (encoder.py:159-160)."""
+    emb = W["encoder.embedding.weight"][q_tokens]
+    return gru_last(emb, W)
+
+
+def multiply_attention_logits(v, q, W, prefix="encoder.attention"):
+    """MultiplyAttention.logits (attention.py:68-76), dropout = identity (eval)."""
+    vp = fcnet1(v, W, prefix + ".W_v")                       # [B,K,H]
+    qp = fcnet1(q, W, prefix + ".W_q").unsqueeze(1)          # [B,1,H]
+    joint = vp * qp
+    wl = wn_weight(W[prefix + ".linear.weight_v"], W[prefix + ".linear.weight_g"])
+    return F.linear(joint, wl, W[prefix + ".linear.bias"])   # [B,K,1]
+
+
+def multiply_attention(v, q, W, prefix="encoder.attention"):
+    """MultiplyAttention.forward: softmax over the K regions (attention.py:78-86)."""
+    return torch.softmax(multiply_attention_logits(v, q, W, prefix), dim=1)
+
+
+def base_encoder(batch, W):
+    """BaseEncoder.base_forward (encoder.py:146-181) minus the caption keys."""
+    v = batch["img"]
+    q = question_embedding(batch["q"], W)
+    v_att = multiply_attention(v, q, W)
+    v = v_att * v
+    qn = fcnet1(q, W, "encoder.q_net")
+    return {"v": v, "q": qn, "v_att": v_att, "q_emb": q}
+
+
+def directed_conv(feature, graph, W, p):
+    """DirectedGraphConv.conv (gcn.py:93-107): W2 f + adj·(W0 f) + adj·(W1 f)
+    + Σ_j bias[label_ij]  (label 0, incl. the diagonal, contributes bias[0])."""
+    adj = (graph != 0).to(feature.dtype)
+    out = F.linear(feature, W[p + "weight.2.weight"])
+    for d in range(2):
+        out = out + torch.bmm(adj, F.linear(feature, W[p + f"weight.{d}.weight"]))
+    labels = graph.long()
+    return out + W[p + "bias"][labels].sum(2)
+
+
+def relation_alpha(feature, adj, W, p):
+    """CorrelatedGraphConv.relation_alpha (gcn.py:119-128; DotProduct
+    modules.py:86-95): softmax over dim=1 (the ROW index i) of adj·ReLU(ABᵀ)."""
+    a = F.linear(feature, W[p + "dot_product.wa.weight"], W[p + "dot_product.wa.bias"])
+    b = F.linear(feature, W[p + "dot_product.wb.weight"], W[p + "dot_product.wb.bias"])
+    alpha = torch.relu(torch.bmm(a, b.transpose(1, 2)))
+    alpha = torch.bmm(adj, alpha)
+    return torch.softmax(alpha, dim=1)
+
+
+def corr_graph_conv(feature, graph, W, p):
+    """CorrelatedGraphConv.forward (gcn.py:152-168) → (output, alpha)."""
+    adj = (graph != 0).to(feature.dtype)
+    conv = directed_conv(feature, graph, W, p)
+    alpha = relation_alpha(feature, adj, W, p)
+    return torch.bmm(alpha, conv), alpha
+
+
+def gcn(feature, graph, W, n_layer=1):
+    """GCN.forward (gcn.py:199-215): per layer conv → dropout(identity) → ReLU."""
+    alphas = []
+    for i in range(n_layer):
+        feature, alpha = corr_graph_conv(feature, graph, W, f"gcn.{i}.")
+        alphas.append(alpha)
+        feature = torch.relu(feature)
+    return feature, alphas
+
+
+def relation_encoder(batch, W, n_layer=1):
+    """RelationEncoder.forward, spatial branch only (encoder.py:236-272)."""
+    out = base_encoder(batch, W)
+    graph = batch["graph"].to(out["v"].dtype)
+    new_v, alphas = gcn(out["v"], graph, W, n_layer)
+    out["v"] = torch.zeros_like(out["v"]) + new_v
+    out["alpha"] = alphas
+    return out
+
+
+def base_predictor(enc, W):
+    """BasePredictor.forward (predictor.py:81-93): Σ_K v → v_net → ⊙q →
+    classifier FCNet(H→2H→A, 2 layers, final ReLU modules.py:55)."""
+    v = enc["v"].sum(1)
+    v = fcnet1(v, W, "predictor.v_net")
+    joint = enc["q"] * v
+    p = "predictor.classifier.main"
+    w0 = wn_weight(W[p + ".0.weight_v"], W[p + ".0.weight_g"])
+    w3 = wn_weight(W[p + ".3.weight_v"], W[p + ".3.weight_g"])
+    h = torch.relu(F.linear(joint, w0, W[p + ".0.bias"]))
+    return torch.relu(F.linear(h, w3, W[p + ".3.bias"]))
+
+
+def compute_score(predict, target):
+    """compute_score (wrapper.py:8-22): lowest-index argmax → one-hot ⊙ target."""
+    label = torch.max(predict, 1)[1]
+    one_hot = torch.zeros_like(target)
+    one_hot.scatter_(1, label.view(-1, 1), 1)
+    return one_hot * target, label
+
+
+def forward(batch, W, cfg: Config):
+    """Wrapper.forward / get_att composition (wrapper.py:64-74,107-110)."""
+    enc = relation_encoder(batch, W, cfg.conv_layer) if cfg.relation else base_encoder(batch, W)
+    logits = base_predictor(enc, W)
+    return logits, enc
+
+
+def forward_vqa(batch, W, cfg: Config):
+    """Wrapper.forward_vqa (wrapper.py:113-118) → (score, label, target)."""
+    logits, _ = forward(batch, W, cfg)
+    target = batch["a"].to(logits.dtype)
+    score, label = compute_score(logits, target)
+    return score, label, target
+
+
+def to_dtype(W: dict, dtype):
+    return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in W.items()}
+
+
+# ----------------------------------------------------------------------------
+# spatial relation labels (util/relation.py)
+# ----------------------------------------------------------------------------
+def spatial_relation_pairs(a: np.ndarray, b: np.ndarray, w, h):
+    """Vectorised spatial_relation (relation.py:3-45) over N box pairs.
+    a, b: [N,4] float32.  Returns (label_ab, label_ba) uint8 [N].
+
+    dtype flow mirrors the reference with float32 boxes: intersection, areas,
+    IoU, centres, centre distance, arctan2/rad2deg/-90/%360//45 all float32;
+    ‖(w,h)‖ is float64 (python ints) so the ``dist <= 0.5`` compare is float64.
+    """
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    n = a.shape[0]
+    I = np.stack([np.maximum(a[:, 0], b[:, 0]), np.maximum(a[:, 1], b[:, 1]),
+                  np.minimum(a[:, 2], b[:, 2]), np.minimum(a[:, 3], b[:, 3])], axis=1)
+    lab_ab = np.zeros(n, dtype=np.uint8)
+    lab_ba = np.zeros(n, dtype=np.uint8)
+    done = np.zeros(n, dtype=bool)
+
+    inside = np.all(I == b, axis=1)                      # relation.py:24
+    lab_ab[inside], lab_ba[inside] = 1, 2
+    done |= inside
+    covered = np.all(I == a, axis=1) & ~done             # relation.py:25
+    lab_ab[covered], lab_ba[covered] = 2, 1
+    done |= covered
+
+    area = lambda x: (x[:, 3] - x[:, 1]) * (x[:, 2] - x[:, 0])   # unclamped (F6)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ai = area(I)
+        iou = ai / (area(a) + area(b) - ai)
+    overlap = (iou >= np.float32(0.5)) & ~done           # relation.py:30
+    lab_ab[overlap], lab_ba[overlap] = 3, 3
+    done |= overlap
+
+    two = np.float32(2)
+    ca = np.stack([a[:, 0] + (a[:, 2] - a[:, 0]) / two, a[:, 1] + (a[:, 3] - a[:, 1]) / two], 1)
+    cb = np.stack([b[:, 0] + (b[:, 2] - b[:, 0]) / two, b[:, 1] + (b[:, 3] - b[:, 1]) / two], 1)
+    d = ca - cb
+    nrm = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])       # float32 (np.linalg.norm)
+    dist = nrm.astype(np.float64) / np.linalg.norm([w, h])
+    near = (dist <= 0.5) & ~done                         # relation.py:37-38
+    e = cb - ca
+    delta = np.rad2deg(np.arctan2(e[:, 0], e[:, 1])) - np.float32(90)   # relation.py:40
+    idx = lambda x: (np.ceil((x % np.float32(360)) / np.float32(45)) + 3).astype(np.int64)
+    i1 = idx(delta)
+    i2 = idx(delta + np.float32(180))
+    lab_ab[near] = i1[near]
+    lab_ba[near] = i2[near]
+    return lab_ab, lab_ba
+
+
+def relation_graph(bbox: np.ndarray, w, h) -> np.ndarray:
+    """relation_graph (relation.py:65-80): float64 [K,K]; one evaluation per
+    unordered pair i<j writes [i,j] and [j,i]; the diagonal stays 0."""
+    K = bbox.shape[0]
+    iu, ju = np.triu_indices(K, 1)
+    lab_ab, lab_ba = spatial_relation_pairs(bbox[iu], bbox[ju], w, h)
+    out = np.zeros((K, K), dtype=np.float64)
+    out[iu, ju] = lab_ab
+    out[ju, iu] = lab_ba
+    return out
+
+
+def relation_graph_batch(bbox: np.ndarray, w, h) -> np.ndarray:
+    """[B,K,4] → uint8 [B,K,K] (the on-device wire format of the label kernel)."""
+    B, K, _ = bbox.shape
+    iu, ju = np.triu_indices(K, 1)
+    a = bbox[:, iu].reshape(-1, 4)
+    b = bbox[:, ju].reshape(-1, 4)
+    lab_ab, lab_ba = spatial_relation_pairs(a, b, w, h)
+    out = np.zeros((B, K, K), dtype=np.uint8)
+    out[:, iu, ju] = lab_ab.reshape(B, -1)
+    out[:, ju, iu] = lab_ba.reshape(B, -1)
+    return out

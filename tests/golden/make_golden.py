@@ -1,0 +1,111 @@
+"""Generate tests/golden/*.npz from the REAL reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports the unmodified reference from /root/reference (read-only; never copied
+into this repo), loads the seeded synthetic weights of
+``oracle.vqa_oracle.make_weights`` into the reference's own ``Wrapper`` (GCN
+layer tensors are assigned object-by-object because they are not registered
+parameters), runs the reference's own forward on the seeded
+batches of ``make_batch`` and stores ONLY outputs (inputs and weights are
+re-derivable from the seeds).  The reference cannot travel to the GPU box, the
+fixtures do.
+"""
+import os
+import sys
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+import numpy as np
+import torch
+
+from oracle import vqa_oracle as O
+
+from modules.wrapper import set_model          # noqa: E402  (the reference)
+from util.relation import relation_graph, spatial_relation   # noqa: E402
+
+
+def build_reference(cfg: O.Config, W: dict):
+    m = set_model(encoder_type="relation" if cfg.relation else "base",
+                  predictor_type="base", decoder_type="none", ntoken=cfg.ntoken,
+                  v_dim=cfg.v_dim, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim,
+                  decoder_hidden_dim=0, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2,
+                  c_len=cfg.c_len, device="cpu", dropout=0.2, rnn_type="GRU",
+                  att_type="new", conv_layer=cfg.conv_layer, conv_type="corr")
+    sd = {k: v for k, v in W.items() if not k.startswith("gcn.")}
+    m.load_state_dict(sd, strict=True)
+    if cfg.relation:
+        for i, layer in enumerate(m.encoder.spatial_encoder.gcn):
+            lsd = {k[len(f"gcn.{i}."):]: v for k, v in W.items() if k.startswith(f"gcn.{i}.")}
+            layer.load_state_dict(lsd, strict=True)
+    return m.eval()
+
+
+def run_model(name, cfg, B, wseed, bseed):
+    W = O.make_weights(cfg, wseed)
+    batch = O.make_batch(cfg, B, bseed)
+    m = build_reference(cfg, W)
+    ref_batch = {k: v for k, v in batch.items() if k not in ("bbox", "wh")}
+    with torch.no_grad():
+        enc = m.encoder(ref_batch)
+        logits = m.predictor(enc)
+        score, label, _ = m.forward_vqa(ref_batch)
+        out = {
+            "logits": logits.numpy(), "label": label.numpy(), "score_sum": score.sum(1).numpy(),
+            "v_att": enc["v_att"].numpy()[:, :, 0], "q": enc["q"].numpy(),
+            # encoder 'v' is [B,K,V]: keep every 16th channel + the K-sum
+            "v_sub": enc["v"].numpy()[:, :, ::16].copy(), "v_sum": enc["v"].sum(1).numpy(),
+        }
+        # the GRU state is not returned by the reference encoder: recompute it with the
+        # reference's own sub-modules
+        out["q_emb"] = m.encoder.q_rnn(m.encoder.embedding(batch["q"])).numpy()
+        out["att_logits"] = m.encoder.attention.logits(batch["img"], torch.from_numpy(out["q_emb"])).numpy()[:, :, 0]
+        if cfg.relation:
+            out["alpha"] = m.encoder(ref_batch, True)[0].numpy()
+            out["graph"] = batch["graph"].numpy().astype(np.uint8)
+    meta = dict(cfg=cfg.as_dict(), B=B, wseed=wseed, bseed=bseed)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array(repr(meta)), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
+def run_relation():
+    W_, H_ = 640, 480
+    boxes = O.make_boxes(48, 36, 4242, W_, H_, grid=True)
+    graphs = np.stack([relation_graph(boxes[i], W_, H_) for i in range(boxes.shape[0])]).astype(np.uint8)
+    cont = O.make_boxes(16, 36, 4243, W_, H_, grid=False)
+    cgraphs = np.stack([relation_graph(cont[i], W_, H_) for i in range(cont.shape[0])]).astype(np.uint8)
+    # known-answer table of SURVEY.md §8a-R evaluated through the reference itself
+    a = np.array([290, 190, 310, 210], dtype=np.float32)
+    shifts = [(50, 0), (50, 20), (50, 50), (20, 50), (0, 50), (-20, 50), (-50, 50), (-50, 20),
+              (-50, 0), (-50, -20), (-50, -50), (-20, -50), (0, -50), (20, -50), (50, -50), (50, -20)]
+    ka_a, ka_b, ka_l = [], [], []
+    for dx, dy in shifts:
+        b = a + np.array([dx, dy, dx, dy], dtype=np.float32)
+        ka_a.append(a); ka_b.append(b); ka_l.append(spatial_relation(a, b, W_, H_))
+    a2 = np.array([10, 10, 100, 100], dtype=np.float32)
+    for b in ([20, 20, 50, 50], [0, 0, 200, 200], [10, 10, 100, 100], [10, 10, 50, 50],
+              [20, 10, 110, 100], [50, 50, 50, 50], [600, 440, 630, 470], [120, 10, 200, 100]):
+        b = np.array(b, dtype=np.float32)
+        ka_a.append(a2); ka_b.append(b); ka_l.append(spatial_relation(a2, b, W_, H_))
+    a3 = np.array([0, 0, 10, 10], dtype=np.float32)
+    for b in ([20, 20, 30, 30], [20, 0, 30, 10], [0, 20, 10, 30], [200, 200, 203, 203]):
+        b = np.array(b, dtype=np.float32)
+        ka_a.append(a3); ka_b.append(b); ka_l.append(spatial_relation(a3, b, W_, H_))
+    np.savez_compressed(os.path.join(HERE, "relation.npz"),
+                        meta=np.array(repr(dict(W=W_, H=H_, grid_seed=4242, cont_seed=4243))),
+                        grid_graph=graphs, cont_graph=cgraphs,
+                        ka_a=np.stack(ka_a), ka_b=np.stack(ka_b), ka_labels=np.array(ka_l, dtype=np.uint8))
+    print("relation", graphs.shape, cgraphs.shape, np.array(ka_l).T)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    run_relation()
+    run_model("updown_small", O.SMALL, 8, 1111, 2001)
+    run_model("regat_small", O.SMALL_REGAT, 8, 1111, 3001)
+    run_model("updown_full", O.FULL, 4, 1111, 2002)
+    run_model("regat_full", O.FULL_REGAT, 4, 1111, 3002)

@@ -1,0 +1,98 @@
+"""Pin the CPU oracle against outputs of the REAL reference (tests/golden/*.npz,
+made by tests/golden/make_golden.py from /root/reference)."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vqa_oracle as O
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    return z, meta
+
+
+def _relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+@pytest.mark.parametrize("name", ["updown_small", "regat_small", "updown_full", "regat_full"])
+def test_forward_matches_reference(golden_dir, name):
+    z, meta = _load(golden_dir, name)
+    cfg = O.Config(**meta["cfg"])
+    W = O.make_weights(cfg, meta["wseed"])
+    batch = O.make_batch(cfg, meta["B"], meta["bseed"])
+    with torch.no_grad():
+        logits, enc = O.forward(batch, W, cfg)
+        score, label, _ = O.forward_vqa(batch, W, cfg)
+    # fp32 restatement vs the reference's fp32 library kernels: 1e-5 of max-norm
+    assert _relerr(enc["q_emb"].numpy(), z["q_emb"]) < 1e-5
+    assert _relerr(enc["v_att"].numpy()[:, :, 0], z["v_att"]) < 1e-5
+    assert _relerr(enc["q"].numpy(), z["q"]) < 1e-5
+    assert _relerr(enc["v"].numpy()[:, :, ::16], z["v_sub"]) < 1e-5
+    assert _relerr(enc["v"].sum(1).numpy(), z["v_sum"]) < 1e-5
+    assert _relerr(logits.numpy(), z["logits"]) < 1e-5
+    assert np.array_equal(label.numpy(), z["label"])
+    assert np.allclose(score.sum(1).numpy(), z["score_sum"])
+    if cfg.relation:
+        assert _relerr(enc["alpha"][0].numpy(), z["alpha"]) < 1e-5
+        assert np.array_equal(batch["graph"].numpy().astype(np.uint8), z["graph"])
+
+
+def test_attention_logits_match_reference(golden_dir):
+    z, meta = _load(golden_dir, "updown_full")
+    cfg = O.Config(**meta["cfg"])
+    W = O.make_weights(cfg, meta["wseed"])
+    batch = O.make_batch(cfg, meta["B"], meta["bseed"])
+    with torch.no_grad():
+        lg = O.multiply_attention_logits(batch["img"], torch.from_numpy(z["q_emb"]), W)
+    assert _relerr(lg.numpy()[:, :, 0], z["att_logits"]) < 1e-5
+
+
+def test_float64_truth_is_close(golden_dir):
+    """The float64 run of the oracle brackets the reference's own fp32 error."""
+    z, meta = _load(golden_dir, "updown_small")
+    cfg = O.Config(**meta["cfg"])
+    W = O.to_dtype(O.make_weights(cfg, meta["wseed"]), torch.float64)
+    batch = O.make_batch(cfg, meta["B"], meta["bseed"])
+    batch["img"] = batch["img"].double()
+    with torch.no_grad():
+        logits, _ = O.forward(batch, W, cfg)
+    assert _relerr(logits.numpy(), z["logits"]) < 1e-4
+
+
+def test_relation_grid_exact(golden_dir):
+    z, meta = _load(golden_dir, "relation")
+    boxes = O.make_boxes(48, 36, meta["grid_seed"], meta["W"], meta["H"], grid=True)
+    got = O.relation_graph_batch(boxes, meta["W"], meta["H"])
+    assert np.array_equal(got, z["grid_graph"])
+    one = O.relation_graph(boxes[0], meta["W"], meta["H"])
+    assert one.dtype == np.float64 and np.array_equal(one.astype(np.uint8), z["grid_graph"][0])
+    assert np.all(np.diagonal(got, axis1=1, axis2=2) == 0)
+
+
+def test_relation_continuous(golden_dir):
+    z, meta = _load(golden_dir, "relation")
+    boxes = O.make_boxes(16, 36, meta["cont_seed"], meta["W"], meta["H"], grid=False)
+    got = O.relation_graph_batch(boxes, meta["W"], meta["H"])
+    # same numpy float32 arctan2 on this host: expected exact; gate is statistical (H2)
+    assert (got != z["cont_graph"]).mean() < 1e-4
+
+
+def test_relation_known_answers(golden_dir):
+    z, meta = _load(golden_dir, "relation")
+    ab, ba = O.spatial_relation_pairs(z["ka_a"], z["ka_b"], meta["W"], meta["H"])
+    assert np.array_equal(np.stack([ab, ba], 1), z["ka_labels"])
+    # the table of SURVEY.md §8a-R, hand-pinned (first 16 = the compass, a→b / b→a)
+    compass = [(3, 7), (11, 7), (10, 6), (10, 6), (9, 5), (9, 5), (8, 4), (8, 4),
+               (7, 3), (7, 11), (6, 10), (6, 10), (5, 9), (5, 9), (4, 8), (4, 8)]
+    assert [tuple(x) for x in z["ka_labels"][:16].tolist()] == compass
+    rest = [(1, 2), (2, 1), (1, 2), (1, 2), (3, 3), (1, 2), (0, 0), (3, 7),
+            (3, 3), (3, 7), (9, 5), (10, 6)]
+    assert [tuple(x) for x in z["ka_labels"][16:].tolist()] == rest
