@@ -1,0 +1,234 @@
+/*
+ * vqa_b200.h — C ABI of the B200-native VQA forward hot path.
+ *
+ * Drop-in boundary for Jayie/vqa-collection's Up-Down / ReGAT forward path.
+ * The reference is pure Python/PyTorch (no FFI of its own); every entry point
+ * below names the reference symbol (file:line, relative to the reference
+ * repository root) whose arithmetic it replaces.  The Python host side in
+ * vqa_collection_b200/ binds these with ctypes (see INTEGRATION.md for the stub
+ * a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - pointers named d_* are DEVICE pointers (current device), h_* are HOST
+ *     pointers (pinned memory recommended); `stream` is a cudaStream_t passed
+ *     as void* (NULL = legacy default stream)
+ *   - every function returns 0 on success, a negative vqa_status on failure and
+ *     never falls back to a CPU path; vqa_last_error() returns the message of
+ *     the last failure on the calling thread
+ *   - all launches are asynchronous on `stream` unless the name ends in _host
+ *   - matrices are row-major; "ld" is the leading dimension in ELEMENTS
+ *   - sm_100a only: functions return VQA_ERR_UNSUPPORTED on other devices
+ */
+#ifndef VQA_B200_H_
+#define VQA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQA_B200_ABI_VERSION 1
+
+typedef enum {
+  VQA_OK = 0,
+  VQA_ERR_INVALID = -1,      /* bad argument (shape, alignment, NULL)       */
+  VQA_ERR_CUDA = -2,         /* CUDA runtime / driver error                 */
+  VQA_ERR_UNSUPPORTED = -3   /* not an sm_100 device / unsupported config   */
+} vqa_status;
+
+typedef enum {
+  VQA_F32 = 0,               /* fp32 operands, fp32 FFMA accumulate          */
+  VQA_BF16 = 1               /* bf16 operands, fp32 accumulate (tcgen05/TMEM)*/
+} vqa_dtype;
+
+int vqa_abi_version(void);
+const char* vqa_last_error(void);
+/* sm count / compute capability of the current device */
+int vqa_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------
+ * k7  spatial relation labels
+ * replaces util/relation.py:65-80 relation_graph (and :3-45 spatial_relation),
+ * batched: bbox [B,K,4] f32 (x0,y0,x1,y1) -> labels [B,K,K] u8 in {0..11}.
+ * One evaluation per unordered pair i<j writes [i,j] and [j,i]; diagonal 0.
+ * Image size: per image from d_wh [B,2] f32 (w,h) when non-NULL, else the
+ * uniform (img_w, img_h).  K <= 64.
+ * ---------------------------------------------------------------------- */
+int vqa_relation_labels(const float* d_bbox, const float* d_wh, int B, int K, float img_w,
+                        float img_h, uint8_t* d_labels, void* stream);
+/* host-buffer form (H2D + kernel + D2H + sync), the e2e path of the label op */
+int vqa_relation_labels_host(const float* h_bbox, int B, int K, float img_w, float img_h,
+                             uint8_t* h_labels);
+
+/* ------------------------------------------------------------------------
+ * element type conversion (wire format f32 -> resident bf16), n elements
+ * ---------------------------------------------------------------------- */
+int vqa_cast_f32_to_bf16(const float* d_src, void* d_dst, size_t n, void* stream);
+int vqa_cast_bf16_to_f32(const void* d_src, float* d_dst, size_t n, void* stream);
+
+/* ------------------------------------------------------------------------
+ * k4/k5/k8/k11  fused weight-normed linear layer
+ * replaces modules/modules.py:13-60 FCNet (one weight_norm(nn.Linear)+ReLU
+ * stage), attention.py:66,75 (the 1-wide logit layer, fused as a row
+ * reduction) and the plain nn.Linear maps of gcn.py:101-103 / modules.py:92-93.
+ *
+ *   y[m,n] = (sum_k A[m,k] * W[n,k]) * scale[n] + bias[n]
+ *   if relu:  y = max(y, 0)
+ *   if mul:   y *= mul[(m / mul_row_div), n]          (f32, ld_mul)
+ *   if logit_w == NULL:  out[m,n] = y                 (out_dtype, ldo)
+ *   else: out_f32[m * n_parts + p] = sum_{n in part p} y * logit_w[n]
+ *         with n_parts = ceil(N / vqa_linear_part_width(dtype))
+ *
+ * dtype VQA_BF16: A, W are bf16, K % 64 == 0, lda/ldw % 8 == 0, 16-byte aligned
+ * bases (TMA); tcgen05.mma 128xBN tiles with TMEM accumulators.
+ * dtype VQA_F32 : A, W are f32, K % 16 == 0; FFMA tiles.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const void* d_A;  int lda;
+  const void* d_W;  int ldw;
+  int M, N, K;
+  int dtype;                 /* vqa_dtype of A and W                         */
+  const float* d_scale;      /* [N] or NULL (=1)                             */
+  const float* d_bias;       /* [N] or NULL (=0)                             */
+  int relu;
+  const float* d_mul;        /* optional elementwise multiplier, or NULL     */
+  int ld_mul;
+  int mul_row_div;           /* row m reads mul row m / mul_row_div (>=1)    */
+  const float* d_logit_w;    /* [N] or NULL; selects the row-reduction form  */
+  void* d_out;               /* [M,ldo] out_dtype, or [M,n_parts] f32        */
+  int ldo;
+  int out_dtype;             /* vqa_dtype of out (ignored in logit form)     */
+} vqa_linear_args;
+
+int vqa_linear(const vqa_linear_args* args, void* stream);
+int vqa_linear_part_width(int dtype);
+
+/* ------------------------------------------------------------------------
+ * a6/a7  question encoder: embedding gather + 1-layer GRU, last state
+ * replaces encoder.py:159-160, modules.py:139-159 (nn.Embedding + nn.GRU,
+ * h0 = 0, output[:, -1], gate order [r;z;n]).
+ *   tokens int64 [B,T]; emb [ntoken+1, ld_emb] (dtype); w_ih [3H, ld_emb]
+ *   (zero padded to ld_emb), w_hh [3H,H] (dtype); biases f32 [3H].
+ *   workspace: vqa_gru_workspace_bytes(B,T,H,ld_emb,dtype) bytes.
+ *   out: h_last f32 [B,H]; if d_h_last_lp != NULL also written in `dtype`.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const int64_t* d_tokens;
+  int B, T, H, E_pad, ntoken_rows;
+  int dtype;
+  const void* d_emb;
+  const void* d_w_ih;  const float* d_b_ih;
+  const void* d_w_hh;  const float* d_b_hh;
+  void* d_workspace;   size_t workspace_bytes;
+  float* d_h_last;     void* d_h_last_lp;
+} vqa_gru_args;
+
+int vqa_gru_last_state(const vqa_gru_args* args, void* stream);
+size_t vqa_gru_workspace_bytes(int B, int T, int H, int E_pad, int dtype);
+
+/* ------------------------------------------------------------------------
+ * k6  top-down attention pooling
+ * replaces attention.py:86 (softmax over the K regions), encoder.py:166
+ * (v = v_att * v) and predictor.py:85 (v.sum(1)).
+ *   logit_parts f32 [B*K, n_parts] (from vqa_linear's reduction form),
+ *   logit_bias = attention.linear.bias; x [B,K,V] (dtype).
+ *   outputs (each optional, NULL = skip):
+ *     att   f32 [B,K]            softmax weights
+ *     vsum  [B,V] (dtype)        sum_k att_k x_k
+ *     vatt  [B,K,V] (dtype)      att_k x_k   (encoder output 'v')
+ * V % 8 == 0, K <= 64.
+ * ---------------------------------------------------------------------- */
+int vqa_attention_pool(const float* d_logit_parts, int n_parts, float logit_bias,
+                       const void* d_x, int B, int K, int V, int dtype,
+                       float* d_att, void* d_vsum, void* d_vatt, void* stream);
+
+/* ------------------------------------------------------------------------
+ * k9+k10  relation-masked graph attention (one CorrelatedGraphConv layer + the
+ * GCN's ReLU), after the wide projection Y = x * [W0+W1 ; W2 ; Wa ; Wb]^T.
+ * replaces gcn.py:93-107 (conv, label bias), gcn.py:119-128 (relation_alpha),
+ * gcn.py:152-168 (forward), gcn.py:211-212 (dropout=identity, ReLU) and
+ * predictor.py:85 (the K-sum) when vsum is requested.
+ *   Y [B*K, ldy] (dtype): columns [0,V) P=(W0+W1)x, [V,2V) S=W2 x,
+ *                         [2V,3V) Wa x, [3V,4V) Wb x   (x = RAW features)
+ *   att f32 [B,K]: the top-down attention (feature f_i = att_i * x_i; row
+ *                  scaling commutes with the bias-free maps), NULL = all ones
+ *   labels u8 [B,K,K]; label_bias f32 [L,V]; ba, bb f32 [V]
+ *   outputs (optional): out [B,K,V] (dtype) = ReLU(alpha . conv);
+ *                       vsum [B,V] (dtype) = sum_i out_i; alpha f32 [B,K,K]
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const void* d_Y; int ldy;
+  const float* d_att;
+  const uint8_t* d_labels;
+  const float* d_label_bias; int num_labels;
+  const float* d_ba; const float* d_bb;
+  int B, K, V, dtype;
+  void* d_out; void* d_vsum; float* d_alpha;
+} vqa_graph_attention_args;
+
+int vqa_graph_attention(const vqa_graph_attention_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
+ * a14  answer selection: lowest-index argmax over the A logits
+ * replaces wrapper.py:14 (torch.max(predict, 1)[1]).
+ * ---------------------------------------------------------------------- */
+int vqa_argmax_rows(const float* d_logits, int B, int A, int ld, int64_t* d_label,
+                    void* stream);
+
+/* ------------------------------------------------------------------------
+ * whole path: Wrapper.forward / forward_vqa (wrapper.py:64-74,113-118) for
+ * encoder_type in {base, relation}, att_type 'new', predictor 'base'.
+ * All weight pointers are "prepared" device tensors (see
+ * vqa_collection_b200/engine.py: bf16 or f32 copies, weight-norm scalars
+ * expanded to per-column scale vectors, concatenated where noted).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  /* dims */
+  int B, K, V, H, A, T, E_pad, ntoken_rows, num_labels;
+  int dtype;                 /* vqa_dtype of activations and weights         */
+  int relation;              /* 0 = Up-Down, 1 = Up-Down + ReGAT (1 layer)   */
+  /* inputs */
+  const void* d_img;         /* [B,K,V] dtype                                */
+  const int64_t* d_tokens;   /* [B,T]                                        */
+  const uint8_t* d_labels;   /* [B,K,K] (relation) or NULL                   */
+  const float* d_bbox;       /* [B,K,4]: if non-NULL and d_labels_out given,
+                                labels are computed on device first          */
+  float img_w, img_h;
+  /* question encoder */
+  const void* d_emb; const void* d_w_ih; const float* d_b_ih;
+  const void* d_w_hh; const float* d_b_hh;
+  /* attention (attention.py:61-66) */
+  const void* d_Wv;  const float* d_sv;  const float* d_bv;      /* [H,V]    */
+  const void* d_Wqq; const float* d_sqq; const float* d_bqq;     /* [2H,H]: W_q ; q_net */
+  const float* d_wlin;       /* [H] = linear.weight_v * g/||v||              */
+  float b_lin;
+  /* ReGAT layer (gcn.py), concatenated [4V,V] = [W0+W1; W2; Wa; Wb] */
+  const void* d_Wg; const float* d_label_bias; const float* d_ba; const float* d_bb;
+  /* predictor (predictor.py:58-79) */
+  const void* d_Wvn; const float* d_svn; const float* d_bvn;     /* [H,V]    */
+  const void* d_Wc0; const float* d_sc0; const float* d_bc0;     /* [2H,H]   */
+  const void* d_Wc1; const float* d_sc1; const float* d_bc1;     /* [A,2H], rows padded to mult of 8 */
+  /* workspace */
+  void* d_workspace; size_t workspace_bytes;
+  /* outputs (optional ones may be NULL) */
+  float* d_logits;           /* [B,A] f32                                    */
+  int64_t* d_label;          /* [B]   lowest-index argmax                    */
+  float* d_att;              /* [B,K] attention weights (v_att)              */
+  float* d_q;                /* [B,H] q_net output, optional                 */
+  void* d_v;                 /* [B,K,V] encoder output 'v', optional         */
+  float* d_alpha;            /* [B,K,K], optional (relation)                 */
+  uint8_t* d_labels_out;     /* [B,K,K], optional (relation + bbox)          */
+} vqa_forward_args;
+
+size_t vqa_forward_workspace_bytes(const vqa_forward_args* args);
+int vqa_forward(const vqa_forward_args* args, void* stream);
+/* number of kernels the last vqa_forward on this thread launched */
+int vqa_forward_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQA_B200_H_ */

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Staged GPU check (run under gpurun): safe kernels first, tcgen05 GEMM in its own
+# process so that a hang there does not lose the other results.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,driver_version,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+export PYTHONDONTWRITEBYTECODE=1
+T="timeout 600 python -m pytest -q --timeout=300 --timeout-method=thread -p no:cacheprovider"
+echo "== stage 1: fp32 / non-tensor kernels (VQA_B200_FORCE_SIMT=1)"
+VQA_B200_FORCE_SIMT=1 $T tests/test_gpu_ops.py tests/test_gpu_forward.py -m gpu 2>&1 | tail -40 | tee gpurun_out/stage1.log
+echo "== stage 2: tcgen05 GEMM"
+$T tests/test_gpu_ops.py -m gpu -k "linear" 2>&1 | tail -40 | tee gpurun_out/stage2.log
+echo "== stage 3: everything on the tensor-core path"
+$T tests -m gpu 2>&1 | tail -40 | tee gpurun_out/stage3.log

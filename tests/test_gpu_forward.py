@@ -1,0 +1,138 @@
+"""End-to-end GPU parity: VQAEngine (one C call per forward) against the CPU oracle and
+the committed golden outputs of the real reference."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vqa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine_mod():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from vqa_collection_b200 import engine
+    return engine
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def margin_ok_mask(ref_logits, err_abs):
+    """samples whose reference top-1/top-2 gap exceeds 4x the observed logit error (H1b)"""
+    s = np.sort(ref_logits, 1)
+    return (s[:, -1] - s[:, -2]) > 4.0 * err_abs
+
+
+GOLDEN = ["updown_small", "regat_small", "updown_full", "regat_full"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", GOLDEN)
+def test_engine_matches_reference_golden(engine_mod, golden_dir, name, precision):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    cfg = O.Config(**meta["cfg"])
+    W = O.make_weights(cfg, meta["wseed"])
+    batch = O.make_batch(cfg, meta["B"], meta["bseed"])
+    eng = engine_mod.VQAEngine(W, relation=cfg.relation, precision=precision)
+    kw = dict(labels=batch["graph"].cuda(), want_alpha=True) if cfg.relation else {}
+    out = eng.forward(batch["img"].cuda(), batch["q"].cuda(), want_v=True, want_q=True, **kw)
+    tol = 1e-5 if precision == "fp32" else 1e-2
+    assert relerr(out["att"], z["v_att"]) < tol
+    assert relerr(out["q"], z["q"]) < tol
+    assert relerr(out["v"].float()[:, :, ::16], z["v_sub"]) < tol
+    assert relerr(out["logits"], z["logits"]) < tol
+    if cfg.relation:
+        assert relerr(out["alpha"], z["alpha"]) < tol
+    label = out["label"].cpu().numpy()
+    if precision == "fp32":
+        assert np.array_equal(label, z["label"])                 # bit-exact answers
+    else:
+        err = np.abs(out["logits"].cpu().numpy() - z["logits"]).max()
+        ok = margin_ok_mask(z["logits"], err)
+        assert np.array_equal(label[ok], z["label"][ok])
+    # the kernel's own argmax rule: lowest index among its own maxima
+    assert torch.equal(out["label"].cpu(), torch.max(out["logits"].cpu(), 1)[1])
+    assert eng.last_launches > 0
+
+
+@pytest.mark.parametrize("precision,relation,B", [("fp32", False, 64), ("bf16", False, 256),
+                                                   ("fp32", True, 16), ("bf16", True, 64)])
+def test_engine_matches_oracle_full_dims(engine_mod, precision, relation, B):
+    cfg = O.FULL_REGAT if relation else O.FULL
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, B, 4321)
+    with torch.no_grad():
+        ref_logits, enc = O.forward(batch, W, cfg)
+        _, ref_label, _ = O.forward_vqa(batch, W, cfg)
+    eng = engine_mod.VQAEngine(W, relation=relation, precision=precision)
+    kw = {}
+    if relation:
+        # labels computed on device from the boxes (k7) inside the same forward
+        kw = dict(bbox=batch["bbox"].cuda(), wh=batch["wh"], want_alpha=True)
+    out = eng.forward(batch["img"].cuda(), batch["q"].cuda(), **kw)
+    tol = 1e-5 if precision == "fp32" else 1e-2
+    assert relerr(out["att"], enc["v_att"][:, :, 0]) < tol
+    assert relerr(out["logits"], ref_logits) < tol
+    if relation:
+        assert np.array_equal(out["labels"].cpu().numpy(), batch["graph"].numpy().astype(np.uint8))
+        assert relerr(out["alpha"], enc["alpha"][0]) < tol
+    label = out["label"].cpu().numpy()
+    ref_label = ref_label.numpy()
+    if precision == "fp32":
+        assert np.array_equal(label, ref_label)
+    else:
+        err = np.abs(out["logits"].cpu().numpy() - ref_logits.numpy()).max()
+        ok = margin_ok_mask(ref_logits.numpy(), err)
+        assert ok.mean() > 0.5
+        assert np.array_equal(label[ok], ref_label[ok])
+
+
+def test_engine_sharded_equals_unsharded(engine_mod):
+    """Data-parallel sharding is exact: rows [r*B/N, (r+1)*B/N) of the unsharded result."""
+    cfg = O.FULL
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, 256, 99)
+    eng = engine_mod.VQAEngine(W, relation=False, precision="bf16")
+    img, q = batch["img"].cuda(), batch["q"].cuda()
+    full = eng.forward(img, q)
+    full_logits = full["logits"].clone()
+    for r in range(2):
+        part = eng.forward(img[r * 128:(r + 1) * 128], q[r * 128:(r + 1) * 128])
+        assert torch.equal(part["logits"], full_logits[r * 128:(r + 1) * 128])
+
+
+def test_engine_host_path(engine_mod):
+    cfg = O.FULL
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, 300, 98)
+    eng = engine_mod.VQAEngine(W, relation=False, precision="bf16")
+    dev = eng.forward(batch["img"].cuda(), batch["q"].cuda())
+    label_h, h2d, d2h = eng.forward_host(batch["img"].pin_memory(), batch["q"].pin_memory(), chunk=128)
+    assert torch.equal(label_h, dev["label"].cpu())
+    assert h2d == batch["img"].numel() * 4 + batch["q"].numel() * 8 and d2h == 300 * 8
+
+
+def test_engine_full_batch_properties(engine_mod):
+    """BASELINE size (B=1024): determinism, non-negativity (final ReLU, F7), attention rows sum to 1."""
+    cfg = O.FULL
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, 1024, 7)
+    eng = engine_mod.VQAEngine(W, relation=False, precision="bf16")
+    img, q = eng.resident(batch["img"].cuda()), batch["q"].cuda()
+    a = eng.forward(img, q)
+    la, aa = a["logits"].clone(), a["att"].clone()
+    b = eng.forward(img, q)
+    assert torch.equal(la, b["logits"]) and torch.equal(aa, b["att"])
+    assert float(la.min()) >= 0.0
+    assert torch.allclose(aa.sum(1), torch.ones(1024, device="cuda"), atol=1e-5)
+    assert torch.equal(b["label"], torch.max(b["logits"], 1)[1])

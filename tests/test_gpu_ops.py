@@ -1,0 +1,259 @@
+"""GPU parity tests, op by op, through the C ABI (ctypes) against the CPU oracle.
+
+Bar: bit-exact for labels / indices; ‖Δ‖∞/‖ref‖∞ ≤ 1e-5 in fp32 mode and ≤ 1e-2 in
+bf16 mode (BASELINE.json north_star) for floating point.
+"""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vqa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.bfloat16: 1e-2}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from vqa_collection_b200 import ops as _ops
+    return _ops
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+# ---------------------------------------------------------------------------- relation labels
+def test_relation_labels_golden(ops, golden_dir):
+    z = np.load(os.path.join(golden_dir, "relation.npz"))
+    meta = ast.literal_eval(str(z["meta"]))
+    boxes = O.make_boxes(48, 36, meta["grid_seed"], meta["W"], meta["H"], grid=True)
+    got = ops.relation_labels(torch.from_numpy(boxes).cuda(), meta["W"], meta["H"]).cpu().numpy()
+    assert np.array_equal(got, z["grid_graph"])            # vs the REAL reference's output
+    # known-answer table: pair (a,b) as a 2-box image
+    pair = np.stack([z["ka_a"], z["ka_b"]], 1).astype(np.float32)         # [N,2,4]
+    lab = ops.relation_labels(torch.from_numpy(pair).cuda(), meta["W"], meta["H"]).cpu().numpy()
+    assert np.array_equal(np.stack([lab[:, 0, 1], lab[:, 1, 0]], 1), z["ka_labels"])
+    assert np.all(lab[:, 0, 0] == 0) and np.all(lab[:, 1, 1] == 0)
+
+
+@pytest.mark.parametrize("B,K", [(1, 36), (257, 36), (64, 1), (33, 64), (1024, 36)])
+def test_relation_labels_grid_exact(ops, B, K):
+    boxes = O.make_boxes(B, K, 77 + B + K, 640, 480, grid=True)
+    want = O.relation_graph_batch(boxes, 640, 480)
+    got = ops.relation_labels(torch.from_numpy(boxes).cuda(), 640, 480).cpu().numpy()
+    assert got.shape == (B, K, K) and got.dtype == np.uint8
+    assert np.array_equal(got, want)
+
+
+def test_relation_labels_edge_cases(ops):
+    # empty batch
+    got = ops.relation_labels(torch.zeros((0, 36, 4), device="cuda"), 640, 480)
+    assert got.shape == (0, 36, 36)
+    # identical boxes, zero-area boxes, diagonal-disjoint boxes (F6 quirks)
+    b = np.array([[[0, 0, 10, 10], [0, 0, 10, 10], [20, 20, 30, 30], [5, 5, 5, 5], [200, 200, 203, 203]]], np.float32)
+    want = O.relation_graph_batch(b, 640, 480)
+    got = ops.relation_labels(torch.from_numpy(b).cuda(), 640, 480).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert got[0, 0, 1] == 1 and got[0, 1, 0] == 2          # identical → (1,2)
+    assert got[0, 0, 2] == 3 and got[0, 2, 0] == 3          # diagonal-disjoint → (3,3)
+    # per-image (w,h)
+    boxes = O.make_boxes(8, 36, 5, 640, 480, grid=True)
+    wh = np.array([[640, 480], [320, 240], [1000, 50], [64, 48]] * 2, np.float32)
+    want = np.stack([O.relation_graph_batch(boxes[i:i + 1], wh[i, 0], wh[i, 1])[0] for i in range(8)])
+    got = ops.relation_labels(torch.from_numpy(boxes).cuda(), wh=torch.from_numpy(wh).cuda()).cpu().numpy()
+    assert np.array_equal(got, want)
+    # K out of range is an error, not a silent fallback
+    with pytest.raises(RuntimeError):
+        ops.relation_labels(torch.zeros((1, 65, 4), device="cuda"), 640, 480)
+    with pytest.raises(RuntimeError):
+        ops.relation_labels(torch.zeros((1, 36, 4)), 640, 480)          # CPU tensor
+
+
+def test_relation_labels_continuous_statistical(ops):
+    boxes = O.make_boxes(512, 36, 991, 640, 480, grid=False)
+    want = O.relation_graph_batch(boxes, 640, 480)
+    got = ops.relation_labels(torch.from_numpy(boxes).cuda(), 640, 480).cpu().numpy()
+    assert (got != want).mean() < 1e-5                       # near-boundary pairs only (H2)
+
+
+def test_relation_labels_host_form(ops):
+    boxes = O.make_boxes(100, 36, 12, 640, 480, grid=True)
+    got = ops.relation_labels_host(boxes, 640, 480)
+    assert np.array_equal(got, O.relation_graph_batch(boxes, 640, 480))
+
+
+def test_relation_full_size_properties(ops):
+    """BASELINE size and beyond: size-independent properties (zero diagonal, label range,
+    opposite-direction pairing, determinism)."""
+    boxes = torch.from_numpy(O.make_boxes(16384, 36, 3, 640, 480, grid=True)).cuda()
+    lab = ops.relation_labels(boxes, 640, 480)
+    lab2 = ops.relation_labels(boxes, 640, 480)
+    assert torch.equal(lab, lab2)
+    assert int(lab.max()) <= 11
+    assert int(torch.diagonal(lab, dim1=1, dim2=2).max()) == 0
+    lt = lab.transpose(1, 2)
+    d = (lab >= 4) & (lt >= 4)
+    opp = torch.where(lab <= 7, lab + 4, lab - 4)
+    assert torch.equal(lt[d], opp[d])                          # direction labels come in opposite pairs
+    assert torch.equal((lab == 1), (lt == 2)) and torch.equal((lab == 0), (lt == 0))
+
+
+# ---------------------------------------------------------------------------- linear
+def _lin_ref(A, W, scale, bias, relu, mul, div, logit_w):
+    y = A.double() @ W.double().t()
+    if scale is not None:
+        y = y * scale.double()
+    if bias is not None:
+        y = y + bias.double()
+    if relu:
+        y = torch.relu(y)
+    if mul is not None:
+        y = y * mul.double().repeat_interleave(div, 0)[: y.shape[0]]
+    if logit_w is not None:
+        return y * logit_w.double()
+    return y
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (72, 128, 128), (300, 200, 192), (1024, 3129, 2048),
+                                   (36 * 64, 1024, 2048), (8, 3072, 1024), (1, 64, 64)])
+def test_linear_store(ops, dtype, M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((M, K), generator=g).to(dtype)
+    W = (torch.randn((N, K), generator=g) / K ** 0.5).to(dtype)
+    scale = torch.rand((N,), generator=g) + 0.5
+    bias = torch.randn((N,), generator=g)
+    want = _lin_ref(A.float(), W.float(), scale, bias, True, None, 1, None)
+    for out_dtype in (torch.float32, dtype):
+        got = ops.linear(A.cuda(), W.cuda(), scale.cuda(), bias.cuda(), relu=True, out_dtype=out_dtype)
+        assert got.shape == (M, N) and got.dtype == out_dtype
+        # operands are exact in `dtype`, so only accumulation order / output rounding differ
+        tol = (1e-5 if dtype == torch.float32 else 1e-4) if out_dtype == torch.float32 else 1e-2
+        assert relerr(got, want) < tol, (dtype, out_dtype)
+    # no scale / bias / relu
+    got = ops.linear(A.cuda(), W.cuda(), out_dtype=torch.float32)
+    assert relerr(got, _lin_ref(A.float(), W.float(), None, None, False, None, 1, None)) < (
+        1e-5 if dtype == torch.float32 else 1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Bn,K36,N,K", [(4, 36, 1024, 2048), (7, 36, 128, 256), (3, 36, 300, 64)])
+def test_linear_mul_and_logit_reduction(ops, dtype, Bn, K36, N, K):
+    g = torch.Generator().manual_seed(Bn + N + K)
+    M = Bn * K36
+    A = torch.rand((M, K), generator=g).to(dtype)
+    W = (torch.randn((N, K), generator=g) / K ** 0.5).to(dtype)
+    scale = torch.full((N,), 0.9)
+    bias = torch.randn((N,), generator=g) * 0.1
+    mul_c = torch.rand((Bn, N), generator=g)
+    lw = torch.randn((N,), generator=g)
+    # elementwise multiplier, row-broadcast over the K36 regions
+    got = ops.linear(A.cuda(), W.cuda(), scale.cuda(), bias.cuda(), relu=True, mul=mul_c.cuda(),
+                     mul_row_div=K36, out_dtype=torch.float32)
+    want = _lin_ref(A.float(), W.float(), scale, bias, True, mul_c, K36, None)
+    tol = 1e-5 if dtype == torch.float32 else 1e-4
+    assert relerr(got, want) < tol
+    # row reduction with the logit vector
+    parts = ops.linear(A.cuda(), W.cuda(), scale.cuda(), bias.cuda(), relu=True, mul=mul_c.cuda(),
+                       mul_row_div=K36, logit_w=lw.cuda())
+    pw = ops.linear_part_width(dtype)
+    assert parts.shape == (M, (N + pw - 1) // pw)
+    full = _lin_ref(A.float(), W.float(), scale, bias, True, mul_c, K36, lw)
+    assert relerr(parts.sum(1), full.sum(1)) < tol
+    for p in range(parts.shape[1]):
+        assert relerr(parts[:, p], full[:, p * pw:(p + 1) * pw].sum(1)) < 2 * tol
+
+
+def test_linear_rejects_bad_arguments(ops):
+    A = torch.zeros((8, 60), device="cuda", dtype=torch.bfloat16)
+    W = torch.zeros((8, 60), device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.linear(A, W)                                      # K % 64 != 0
+    with pytest.raises(RuntimeError):
+        ops.linear(A.cpu(), W.cpu())                          # no CPU fallback
+    with pytest.raises(TypeError):
+        ops.linear(A.half(), W.half())
+
+
+# ---------------------------------------------------------------------------- GRU
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cfg,B", [(O.SMALL, 5), (O.FULL, 16)])
+def test_gru_last_state(ops, dtype, cfg, B):
+    from vqa_collection_b200.engine import prepare_weights
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, B, 5)
+    P = prepare_weights(W, dtype, "cuda", False)
+    h = ops.gru_last_state(batch["q"].cuda(), P["emb"], P["w_ih"], P["b_ih"], P["w_hh"], P["b_hh"])
+    with torch.no_grad():
+        want = O.question_embedding(batch["q"], W)
+    assert relerr(h, want) < TOL[dtype]
+
+
+# ---------------------------------------------------------------------------- attention pooling
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,K,V,P", [(3, 36, 2048, 4), (1, 36, 256, 1), (5, 10, 64, 2), (2, 64, 512, 8)])
+def test_attention_pool(ops, dtype, B, K, V, P):
+    g = torch.Generator().manual_seed(B * K + V)
+    parts = torch.randn((B * K, P), generator=g)
+    x = torch.rand((B, K, V), generator=g).to(dtype)
+    bias = 0.3
+    att, vsum, vatt = ops.attention_pool(parts.cuda(), bias, x.cuda(), True, True, True)
+    want_att = torch.softmax(parts.sum(1).view(B, K) + bias, 1)
+    want_v = want_att.unsqueeze(2).double() * x.double()
+    assert relerr(att, want_att) < 1e-5
+    assert relerr(vatt, want_v) < TOL[dtype]
+    assert relerr(vsum, want_v.sum(1)) < TOL[dtype]
+    att2, vsum2, none = ops.attention_pool(parts.cuda(), bias, x.cuda(), True, True, False)
+    assert none is None and relerr(vsum2, want_v.sum(1)) < TOL[dtype]
+
+
+# ---------------------------------------------------------------------------- argmax
+def test_argmax_lowest_index_on_ties(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.relu(torch.randn((257, 3129), generator=g))         # ~50 % exact zeros (F7)
+    x[0] = 0.0                                                    # all tied → index 0
+    x[1, 100] = x[1, 3000] = 9.0                                  # tie → 100
+    x[2, 3128] = 10.0
+    got = ops.argmax_rows(x.cuda()).cpu()
+    assert torch.equal(got, torch.max(x, 1)[1])
+    assert got[0] == 0 and got[1] == 100 and got[2] == 3128
+
+
+# ---------------------------------------------------------------------------- graph attention
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cfg,B", [(O.SMALL_REGAT, 6), (O.FULL_REGAT, 3)])
+def test_graph_attention_layer(ops, dtype, cfg, B):
+    from vqa_collection_b200.engine import prepare_gcn_layer
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, B, 9)
+    g = torch.Generator().manual_seed(4)
+    att = torch.softmax(torch.randn((B, cfg.num_objs), generator=g) * 2, 1)
+    x = batch["img"]
+    feature = att.unsqueeze(2) * x
+    with torch.no_grad():
+        want, alpha = O.corr_graph_conv(feature, batch["graph"].float(), W, "gcn.0.")
+        want = torch.relu(want)
+    Pl = prepare_gcn_layer({k[6:]: v for k, v in W.items() if k.startswith("gcn.0.")}, dtype, "cuda")
+    xd = x.to(dtype).cuda().view(B * cfg.num_objs, cfg.v_dim)
+    Y = ops.linear(xd, Pl["Wg"])
+    labels = batch["graph"].to(torch.uint8).cuda()
+    out, vsum, al = ops.graph_attention(Y, att.cuda(), labels, Pl["label_bias"], Pl["ba"], Pl["bb"],
+                                        cfg.num_objs, True, True, True)
+    tol = TOL[dtype]
+    assert relerr(al, alpha) < tol
+    assert relerr(out, want) < tol
+    assert relerr(vsum, want.sum(1)) < tol
+    # attention = None means the features are used as they are
+    with torch.no_grad():
+        want1, _ = O.corr_graph_conv(x, batch["graph"].float(), W, "gcn.0.")
+    out1, _, _ = ops.graph_attention(Y, None, labels, Pl["label_bias"], Pl["ba"], Pl["bb"], cfg.num_objs)
+    assert relerr(out1, torch.relu(want1)) < tol

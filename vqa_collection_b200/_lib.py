@@ -1,0 +1,132 @@
+"""ctypes binding of the C ABI in include/vqa_b200.h.
+
+The library is the product: there is NO Python/CPU fallback.  If
+``lib/libvqa_b200.so`` is missing, ``load()`` raises and tells the caller to
+build it (``python -m vqa_collection_b200.build`` or ``__graft_entry__.build()``).
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
+
+VQA_F32, VQA_BF16 = 0, 1
+ABI_VERSION = 1
+
+c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [
+        ("d_A", c_void_p), ("lda", c_int),
+        ("d_W", c_void_p), ("ldw", c_int),
+        ("M", c_int), ("N", c_int), ("K", c_int),
+        ("dtype", c_int),
+        ("d_scale", c_void_p), ("d_bias", c_void_p),
+        ("relu", c_int),
+        ("d_mul", c_void_p), ("ld_mul", c_int), ("mul_row_div", c_int),
+        ("d_logit_w", c_void_p),
+        ("d_out", c_void_p), ("ldo", c_int), ("out_dtype", c_int),
+    ]
+
+
+class GruArgs(C.Structure):
+    _fields_ = [
+        ("d_tokens", c_void_p),
+        ("B", c_int), ("T", c_int), ("H", c_int), ("E_pad", c_int), ("ntoken_rows", c_int),
+        ("dtype", c_int),
+        ("d_emb", c_void_p),
+        ("d_w_ih", c_void_p), ("d_b_ih", c_void_p),
+        ("d_w_hh", c_void_p), ("d_b_hh", c_void_p),
+        ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("d_h_last", c_void_p), ("d_h_last_lp", c_void_p),
+    ]
+
+
+class GraphAttentionArgs(C.Structure):
+    _fields_ = [
+        ("d_Y", c_void_p), ("ldy", c_int),
+        ("d_att", c_void_p),
+        ("d_labels", c_void_p),
+        ("d_label_bias", c_void_p), ("num_labels", c_int),
+        ("d_ba", c_void_p), ("d_bb", c_void_p),
+        ("B", c_int), ("K", c_int), ("V", c_int), ("dtype", c_int),
+        ("d_out", c_void_p), ("d_vsum", c_void_p), ("d_alpha", c_void_p),
+    ]
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("B", c_int), ("K", c_int), ("V", c_int), ("H", c_int), ("A", c_int), ("T", c_int),
+        ("E_pad", c_int), ("ntoken_rows", c_int), ("num_labels", c_int),
+        ("dtype", c_int), ("relation", c_int),
+        ("d_img", c_void_p), ("d_tokens", c_void_p), ("d_labels", c_void_p), ("d_bbox", c_void_p),
+        ("img_w", c_float), ("img_h", c_float),
+        ("d_emb", c_void_p), ("d_w_ih", c_void_p), ("d_b_ih", c_void_p),
+        ("d_w_hh", c_void_p), ("d_b_hh", c_void_p),
+        ("d_Wv", c_void_p), ("d_sv", c_void_p), ("d_bv", c_void_p),
+        ("d_Wqq", c_void_p), ("d_sqq", c_void_p), ("d_bqq", c_void_p),
+        ("d_wlin", c_void_p), ("b_lin", c_float),
+        ("d_Wg", c_void_p), ("d_label_bias", c_void_p), ("d_ba", c_void_p), ("d_bb", c_void_p),
+        ("d_Wvn", c_void_p), ("d_svn", c_void_p), ("d_bvn", c_void_p),
+        ("d_Wc0", c_void_p), ("d_sc0", c_void_p), ("d_bc0", c_void_p),
+        ("d_Wc1", c_void_p), ("d_sc1", c_void_p), ("d_bc1", c_void_p),
+        ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("d_logits", c_void_p), ("d_label", c_void_p), ("d_att", c_void_p), ("d_q", c_void_p),
+        ("d_v", c_void_p), ("d_alpha", c_void_p), ("d_labels_out", c_void_p),
+    ]
+
+
+# every symbol include/vqa_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "vqa_abi_version": (c_int, []),
+    "vqa_last_error": (C.c_char_p, []),
+    "vqa_device_info": (c_int, [C.POINTER(c_int)] * 3),
+    "vqa_relation_labels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "vqa_relation_labels_host": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
+    "vqa_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vqa_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vqa_linear": (c_int, [C.POINTER(LinearArgs), c_void_p]),
+    "vqa_linear_part_width": (c_int, [c_int]),
+    "vqa_gru_last_state": (c_int, [C.POINTER(GruArgs), c_void_p]),
+    "vqa_gru_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "vqa_attention_pool": (c_int, [c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vqa_graph_attention": (c_int, [C.POINTER(GraphAttentionArgs), c_void_p]),
+    "vqa_argmax_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vqa_forward_workspace_bytes": (c_size_t, [C.POINTER(ForwardArgs)]),
+    "vqa_forward": (c_int, [C.POINTER(ForwardArgs), c_void_p]),
+    "vqa_forward_last_launch_count": (c_int, []),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the C-ABI library and bind every declared symbol (raises if missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"vqa_collection_b200: CUDA library {LIB_PATH} is not built and there is no CPU fallback; "
+            "run `python -m vqa_collection_b200.build` (or __graft_entry__.build()) first")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.vqa_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"vqa_collection_b200: ABI version mismatch ({lib.vqa_abi_version()} != {ABI_VERSION})")
+    _lib = lib
+    return lib
+
+
+class VqaError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().vqa_last_error().decode("utf-8", "replace")
+        raise VqaError(f"vqa_b200 error {rc}: {msg}")

@@ -1,0 +1,350 @@
+// C-ABI entry points (include/vqa_b200.h) and the whole-path orchestration.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vqa {
+
+// ---- thread-local error / launch accounting --------------------------------
+static thread_local char g_error[512] = "";
+static thread_local int g_launches = 0;
+
+char* error_buffer() { return g_error; }
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches += n; }
+int launch_count() { return g_launches; }
+void reset_launch_count() { g_launches = 0; }
+
+struct DevInfo { int dev = -1, sms = 0, major = 0, minor = 0; };
+static DevInfo query_device() {
+  DevInfo d;
+  if (cudaGetDevice(&d.dev) != cudaSuccess) { d.dev = -1; return d; }
+  cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, d.dev);
+  cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, d.dev);
+  cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, d.dev);
+  return d;
+}
+static const DevInfo& device() {
+  static thread_local DevInfo cache;
+  int dev = -1;
+  cudaGetDevice(&dev);
+  if (cache.dev != dev || dev < 0) cache = query_device();
+  return cache;
+}
+int sm_count() { const int n = device().sms; return n > 0 ? n : 148; }
+int require_sm100() {
+  const DevInfo& d = device();
+  if (d.dev < 0) return fail(VQA_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(cudaGetLastError()));
+  if (d.major != 10)
+    return fail(VQA_ERR_UNSUPPORTED, "device compute capability %d.%d: this library is built for sm_100a only",
+                d.major, d.minor);
+  return VQA_OK;
+}
+
+// kernels implemented in the other translation units
+int relation_labels(const float*, const float*, int, int, float, float, uint8_t*, cudaStream_t);
+int attention_pool(const float*, int, float, const void*, int, int, int, int, float*, void*, void*, cudaStream_t);
+int argmax_rows(const float*, int, int, int, int64_t*, cudaStream_t);
+int embedding_gather(const int64_t*, int, int, int, int, const void*, void*, cudaStream_t);
+int gru_gate(const float*, const float*, int, int, int, int, const float*, float*, void*, int, cudaStream_t);
+int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
+int cast_bf16_to_f32(const void*, float*, size_t, cudaStream_t);
+int graph_attention(const vqa_graph_attention_args&, cudaStream_t);
+
+static bool force_simt() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VQA_B200_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+static int linear_dispatch(const vqa_linear_args& a, cudaStream_t s) {
+  VQA_REQUIRE(a.d_A && a.d_W && a.d_out, "vqa_linear: NULL pointer");
+  VQA_REQUIRE(a.M >= 0 && a.N >= 1 && a.K >= 1, "vqa_linear: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  VQA_REQUIRE(a.dtype == VQA_F32 || a.dtype == VQA_BF16, "vqa_linear: dtype=%d", a.dtype);
+  VQA_REQUIRE(a.d_mul == nullptr || a.mul_row_div >= 1, "vqa_linear: mul_row_div must be >= 1");
+  if (a.dtype == VQA_BF16 && !force_simt()) return linear_tc(a, s);
+  return linear_simt(a, s);
+}
+
+static int part_width(int dtype) {
+  return (dtype == VQA_BF16 && !force_simt()) ? linear_tc_part_width() : 128;
+}
+
+// ---- GRU --------------------------------------------------------------------
+struct GruWs { void* X; float* gi; float* gh; float* h; void* h_lp; size_t bytes; };
+static GruWs carve_gru(void* base, int B, int T, int H, int E_pad, int dtype) {
+  GruWs w;
+  size_t off = 0;
+  char* p = (char*)base;
+  auto take = [&](size_t n) { void* r = p ? p + off : nullptr; off += align_up(n, 256); return r; };
+  w.X = take((size_t)B * T * E_pad * elem_size(dtype));
+  w.gi = (float*)take((size_t)B * T * 3 * H * 4);
+  w.gh = (float*)take((size_t)B * 3 * H * 4);
+  w.h = (float*)take((size_t)B * H * 4);
+  w.h_lp = take((size_t)B * H * elem_size(dtype));
+  w.bytes = off;
+  return w;
+}
+
+static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
+  VQA_REQUIRE(a.d_tokens && a.d_emb && a.d_w_ih && a.d_w_hh && a.d_b_ih && a.d_b_hh && a.d_h_last,
+              "vqa_gru_last_state: NULL pointer");
+  VQA_REQUIRE(a.B >= 0 && a.T >= 1 && a.H >= 1 && a.E_pad >= 1, "vqa_gru_last_state: bad dims");
+  const GruWs need = carve_gru(nullptr, a.B, a.T, a.H, a.E_pad, a.dtype);
+  VQA_REQUIRE(a.d_workspace && a.workspace_bytes >= need.bytes,
+              "vqa_gru_last_state: workspace %zu < %zu bytes", a.workspace_bytes, need.bytes);
+  if (a.B == 0) return VQA_OK;
+  const GruWs w = carve_gru(a.d_workspace, a.B, a.T, a.H, a.E_pad, a.dtype);
+  int rc;
+  if ((rc = embedding_gather(a.d_tokens, a.B * a.T, a.E_pad, a.ntoken_rows, a.dtype, a.d_emb, w.X, s))) return rc;
+  // gi = X W_ihᵀ + b_ih for all T steps at once: [B*T, 3H] f32
+  vqa_linear_args gi{};
+  gi.d_A = w.X; gi.lda = a.E_pad; gi.d_W = a.d_w_ih; gi.ldw = a.E_pad;
+  gi.M = a.B * a.T; gi.N = 3 * a.H; gi.K = a.E_pad; gi.dtype = a.dtype;
+  gi.d_bias = a.d_b_ih; gi.d_out = w.gi; gi.ldo = 3 * a.H; gi.out_dtype = VQA_F32; gi.mul_row_div = 1;
+  if ((rc = linear_dispatch(gi, s))) return rc;
+  VQA_CUDA_CHECK(cudaMemsetAsync(w.h, 0, (size_t)a.B * a.H * 4, s));
+  VQA_CUDA_CHECK(cudaMemsetAsync(w.h_lp, 0, (size_t)a.B * a.H * elem_size(a.dtype), s));
+  for (int t = 0; t < a.T; ++t) {
+    vqa_linear_args gh{};
+    gh.d_A = w.h_lp; gh.lda = a.H; gh.d_W = a.d_w_hh; gh.ldw = a.H;
+    gh.M = a.B; gh.N = 3 * a.H; gh.K = a.H; gh.dtype = a.dtype;
+    gh.d_bias = a.d_b_hh; gh.d_out = w.gh; gh.ldo = 3 * a.H; gh.out_dtype = VQA_F32; gh.mul_row_div = 1;
+    if ((rc = linear_dispatch(gh, s))) return rc;
+    const bool last = (t == a.T - 1);
+    // state kept in f32 (w.h, updated in place) plus the low-precision copy that feeds the
+    // next step's GEMM; the last step writes the caller's buffers
+    if ((rc = gru_gate(w.gi, w.gh, a.B, a.H, a.T, t, w.h, last ? a.d_h_last : w.h,
+                       (last && a.d_h_last_lp) ? a.d_h_last_lp : w.h_lp, a.dtype, s))) return rc;
+  }
+  return VQA_OK;
+}
+
+}  // namespace vqa
+
+using namespace vqa;
+
+// =============================================================================
+extern "C" {
+
+int vqa_abi_version(void) { return VQA_B200_ABI_VERSION; }
+const char* vqa_last_error(void) { return error_buffer(); }
+
+int vqa_device_info(int* sms, int* major, int* minor) {
+  const DevInfo d = query_device();
+  if (d.dev < 0) return fail(VQA_ERR_CUDA, "no CUDA device available");
+  if (sms) *sms = d.sms;
+  if (major) *major = d.major;
+  if (minor) *minor = d.minor;
+  return VQA_OK;
+}
+
+int vqa_relation_labels(const float* d_bbox, const float* d_wh, int B, int K, float img_w, float img_h,
+                        uint8_t* d_labels, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return relation_labels(d_bbox, d_wh, B, K, img_w, img_h, d_labels, (cudaStream_t)stream);
+}
+
+int vqa_relation_labels_host(const float* h_bbox, int B, int K, float img_w, float img_h, uint8_t* h_labels) {
+  if (int rc = require_sm100()) return rc;
+  VQA_REQUIRE(h_bbox && h_labels && B >= 0 && K >= 1, "vqa_relation_labels_host: bad arguments");
+  if (B == 0) return VQA_OK;
+  float* d_bbox = nullptr;
+  uint8_t* d_lab = nullptr;
+  cudaStream_t s;
+  VQA_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  int rc = VQA_OK;
+  const size_t nb = (size_t)B * K * 4 * sizeof(float), nl = (size_t)B * K * K;
+  cudaError_t e;
+  if ((e = cudaMallocAsync((void**)&d_bbox, nb, s)) != cudaSuccess ||
+      (e = cudaMallocAsync((void**)&d_lab, nl, s)) != cudaSuccess ||
+      (e = cudaMemcpyAsync(d_bbox, h_bbox, nb, cudaMemcpyHostToDevice, s)) != cudaSuccess) {
+    rc = fail(VQA_ERR_CUDA, "vqa_relation_labels_host: %s", cudaGetErrorString(e));
+  }
+  if (rc == VQA_OK) rc = relation_labels(d_bbox, nullptr, B, K, img_w, img_h, d_lab, s);
+  if (rc == VQA_OK && (e = cudaMemcpyAsync(h_labels, d_lab, nl, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+    rc = fail(VQA_ERR_CUDA, "vqa_relation_labels_host: %s", cudaGetErrorString(e));
+  if (d_bbox) cudaFreeAsync(d_bbox, s);
+  if (d_lab) cudaFreeAsync(d_lab, s);
+  e = cudaStreamSynchronize(s);
+  if (rc == VQA_OK && e != cudaSuccess) rc = fail(VQA_ERR_CUDA, "vqa_relation_labels_host: %s", cudaGetErrorString(e));
+  cudaStreamDestroy(s);
+  return rc;
+}
+
+int vqa_cast_f32_to_bf16(const float* d_src, void* d_dst, size_t n, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return cast_f32_to_bf16(d_src, d_dst, n, (cudaStream_t)stream);
+}
+int vqa_cast_bf16_to_f32(const void* d_src, float* d_dst, size_t n, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return cast_bf16_to_f32(d_src, d_dst, n, (cudaStream_t)stream);
+}
+
+int vqa_linear(const vqa_linear_args* args, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  VQA_REQUIRE(args, "vqa_linear: NULL args");
+  return linear_dispatch(*args, (cudaStream_t)stream);
+}
+int vqa_linear_part_width(int dtype) { return part_width(dtype); }
+
+size_t vqa_gru_workspace_bytes(int B, int T, int H, int E_pad, int dtype) {
+  return carve_gru(nullptr, B, T, H, E_pad, dtype).bytes;
+}
+int vqa_gru_last_state(const vqa_gru_args* args, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  VQA_REQUIRE(args, "vqa_gru_last_state: NULL args");
+  return gru_last_state(*args, (cudaStream_t)stream);
+}
+
+int vqa_attention_pool(const float* d_logit_parts, int n_parts, float logit_bias, const void* d_x, int B,
+                       int K, int V, int dtype, float* d_att, void* d_vsum, void* d_vatt, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return attention_pool(d_logit_parts, n_parts, logit_bias, d_x, B, K, V, dtype, d_att, d_vsum, d_vatt,
+                        (cudaStream_t)stream);
+}
+
+int vqa_graph_attention(const vqa_graph_attention_args* args, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  VQA_REQUIRE(args, "vqa_graph_attention: NULL args");
+  return graph_attention(*args, (cudaStream_t)stream);
+}
+
+int vqa_argmax_rows(const float* d_logits, int B, int A, int ld, int64_t* d_label, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return argmax_rows(d_logits, B, A, ld, d_label, (cudaStream_t)stream);
+}
+
+// ---- whole path --------------------------------------------------------------
+struct FwdWs {
+  void* gru; size_t gru_bytes;
+  float* h; void* h_lp; float* qq; float* parts; void* vsum; void* Y; void* joint; void* hid;
+  size_t bytes;
+};
+static FwdWs carve_fwd(const vqa_forward_args& a, void* base) {
+  FwdWs w{};
+  size_t off = 0;
+  char* p = (char*)base;
+  auto take = [&](size_t n) { void* r = p ? p + off : nullptr; off += align_up(n, 256); return r; };
+  const size_t es = elem_size(a.dtype);
+  w.gru_bytes = carve_gru(nullptr, a.B, a.T, a.H, a.E_pad, a.dtype).bytes;
+  w.gru = take(w.gru_bytes);
+  w.h = (float*)take((size_t)a.B * a.H * 4);
+  w.h_lp = take((size_t)a.B * a.H * es);
+  w.qq = (float*)take((size_t)a.B * 2 * a.H * 4);
+  const int n_parts = (a.H + part_width(a.dtype) - 1) / part_width(a.dtype);
+  w.parts = (float*)take((size_t)a.B * a.K * n_parts * 4);
+  w.vsum = take((size_t)a.B * a.V * es);
+  w.Y = a.relation ? take((size_t)a.B * a.K * 4 * a.V * es) : nullptr;
+  w.joint = take((size_t)a.B * a.H * es);
+  w.hid = take((size_t)a.B * 2 * a.H * es);
+  w.bytes = off;
+  return w;
+}
+
+size_t vqa_forward_workspace_bytes(const vqa_forward_args* args) {
+  if (!args) return 0;
+  return carve_fwd(*args, nullptr).bytes;
+}
+
+static thread_local int g_last_forward_launches = 0;
+int vqa_forward_last_launch_count(void) { return g_last_forward_launches; }
+
+int vqa_forward(const vqa_forward_args* args, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  VQA_REQUIRE(args, "vqa_forward: NULL args");
+  const vqa_forward_args& a = *args;
+  cudaStream_t s = (cudaStream_t)stream;
+  VQA_REQUIRE(a.B >= 0 && a.K >= 1 && a.V >= 1 && a.H >= 1 && a.A >= 1 && a.T >= 1, "vqa_forward: bad dims");
+  VQA_REQUIRE(a.d_img && a.d_tokens && a.d_logits, "vqa_forward: NULL input/output");
+  VQA_REQUIRE(a.d_emb && a.d_w_ih && a.d_w_hh && a.d_Wv && a.d_Wqq && a.d_wlin && a.d_Wvn && a.d_Wc0 && a.d_Wc1,
+              "vqa_forward: NULL weight");
+  const FwdWs need = carve_fwd(a, nullptr);
+  VQA_REQUIRE(a.d_workspace && a.workspace_bytes >= need.bytes, "vqa_forward: workspace %zu < %zu bytes",
+              a.workspace_bytes, need.bytes);
+  if (a.B == 0) return VQA_OK;
+  const FwdWs w = carve_fwd(a, a.d_workspace);
+  const int before = launch_count();
+  int rc;
+  const uint8_t* labels = a.d_labels;
+  if (a.relation) {
+    VQA_REQUIRE(a.d_Wg && a.d_label_bias && a.d_ba && a.d_bb, "vqa_forward: NULL ReGAT weight");
+    if (a.d_bbox != nullptr) {
+      VQA_REQUIRE(a.d_labels_out, "vqa_forward: d_bbox given without d_labels_out");
+      if ((rc = relation_labels(a.d_bbox, nullptr, a.B, a.K, a.img_w, a.img_h, a.d_labels_out, s))) return rc;
+      labels = a.d_labels_out;
+    }
+    VQA_REQUIRE(labels, "vqa_forward: relation path needs d_labels or d_bbox");
+  }
+  // 1. question encoder (encoder.py:159-160)
+  vqa_gru_args g{};
+  g.d_tokens = a.d_tokens; g.B = a.B; g.T = a.T; g.H = a.H; g.E_pad = a.E_pad; g.ntoken_rows = a.ntoken_rows;
+  g.dtype = a.dtype; g.d_emb = a.d_emb; g.d_w_ih = a.d_w_ih; g.d_b_ih = a.d_b_ih; g.d_w_hh = a.d_w_hh;
+  g.d_b_hh = a.d_b_hh; g.d_workspace = w.gru; g.workspace_bytes = w.gru_bytes; g.d_h_last = w.h; g.d_h_last_lp = w.h_lp;
+  if ((rc = gru_last_state(g, s))) return rc;
+  // 2. [W_q ; q_net] (attention.py:71, encoder.py:169): qq = ReLU(h Wqqᵀ s + b) f32 [B,2H]
+  vqa_linear_args l{};
+  l.d_A = w.h_lp; l.lda = a.H; l.d_W = a.d_Wqq; l.ldw = a.H; l.M = a.B; l.N = 2 * a.H; l.K = a.H; l.dtype = a.dtype;
+  l.d_scale = a.d_sqq; l.d_bias = a.d_bqq; l.relu = 1; l.mul_row_div = 1;
+  l.d_out = w.qq; l.ldo = 2 * a.H; l.out_dtype = VQA_F32;
+  if ((rc = linear_dispatch(l, s))) return rc;
+  // 3. W_v projection fused with ⊙Qp and the 1-wide logit layer (attention.py:70-75)
+  const int pw = part_width(a.dtype);
+  const int n_parts = (a.H + pw - 1) / pw;
+  l = vqa_linear_args{};
+  l.d_A = a.d_img; l.lda = a.V; l.d_W = a.d_Wv; l.ldw = a.V; l.M = a.B * a.K; l.N = a.H; l.K = a.V; l.dtype = a.dtype;
+  l.d_scale = a.d_sv; l.d_bias = a.d_bv; l.relu = 1; l.d_mul = w.qq; l.ld_mul = 2 * a.H; l.mul_row_div = a.K;
+  l.d_logit_w = a.d_wlin; l.d_out = w.parts; l.ldo = n_parts; l.out_dtype = VQA_F32;
+  if ((rc = linear_dispatch(l, s))) return rc;
+  // 4. softmax over K + weighted sum (attention.py:86, encoder.py:166, predictor.py:85)
+  if (!a.relation) {
+    if ((rc = attention_pool(w.parts, n_parts, a.b_lin, a.d_img, a.B, a.K, a.V, a.dtype, a.d_att ? a.d_att : nullptr,
+                             w.vsum, a.d_v, s))) return rc;
+  } else {
+    float* att = a.d_att;
+    VQA_REQUIRE(att, "vqa_forward: relation path needs d_att");
+    if ((rc = attention_pool(w.parts, n_parts, a.b_lin, a.d_img, a.B, a.K, a.V, a.dtype, att, nullptr, nullptr, s))) return rc;
+    // 5. wide projection of the raw features + relation-masked graph attention (gcn.py)
+    l = vqa_linear_args{};
+    l.d_A = a.d_img; l.lda = a.V; l.d_W = a.d_Wg; l.ldw = a.V; l.M = a.B * a.K; l.N = 4 * a.V; l.K = a.V; l.dtype = a.dtype;
+    l.mul_row_div = 1; l.d_out = w.Y; l.ldo = 4 * a.V; l.out_dtype = a.dtype;
+    if ((rc = linear_dispatch(l, s))) return rc;
+    vqa_graph_attention_args ga{};
+    ga.d_Y = w.Y; ga.ldy = 4 * a.V; ga.d_att = att; ga.d_labels = labels; ga.d_label_bias = a.d_label_bias;
+    ga.num_labels = a.num_labels; ga.d_ba = a.d_ba; ga.d_bb = a.d_bb; ga.B = a.B; ga.K = a.K; ga.V = a.V; ga.dtype = a.dtype;
+    ga.d_out = a.d_v; ga.d_vsum = w.vsum; ga.d_alpha = a.d_alpha;
+    if ((rc = graph_attention(ga, s))) return rc;
+  }
+  // 6. v_net ⊙ q_net (predictor.py:88-91)
+  l = vqa_linear_args{};
+  l.d_A = w.vsum; l.lda = a.V; l.d_W = a.d_Wvn; l.ldw = a.V; l.M = a.B; l.N = a.H; l.K = a.V; l.dtype = a.dtype;
+  l.d_scale = a.d_svn; l.d_bias = a.d_bvn; l.relu = 1; l.d_mul = w.qq + a.H; l.ld_mul = 2 * a.H; l.mul_row_div = 1;
+  l.d_out = w.joint; l.ldo = a.H; l.out_dtype = a.dtype;
+  if ((rc = linear_dispatch(l, s))) return rc;
+  // 7. classifier (predictor.py:93; FCNet 2 layers, final ReLU modules.py:55)
+  l = vqa_linear_args{};
+  l.d_A = w.joint; l.lda = a.H; l.d_W = a.d_Wc0; l.ldw = a.H; l.M = a.B; l.N = 2 * a.H; l.K = a.H; l.dtype = a.dtype;
+  l.d_scale = a.d_sc0; l.d_bias = a.d_bc0; l.relu = 1; l.mul_row_div = 1;
+  l.d_out = w.hid; l.ldo = 2 * a.H; l.out_dtype = a.dtype;
+  if ((rc = linear_dispatch(l, s))) return rc;
+  l = vqa_linear_args{};
+  l.d_A = w.hid; l.lda = 2 * a.H; l.d_W = a.d_Wc1; l.ldw = 2 * a.H; l.M = a.B; l.N = a.A; l.K = 2 * a.H; l.dtype = a.dtype;
+  l.d_scale = a.d_sc1; l.d_bias = a.d_bc1; l.relu = 1; l.mul_row_div = 1;
+  l.d_out = a.d_logits; l.ldo = a.A; l.out_dtype = VQA_F32;
+  if ((rc = linear_dispatch(l, s))) return rc;
+  // 8. answers (wrapper.py:14)
+  if (a.d_label) if ((rc = argmax_rows(a.d_logits, a.B, a.A, a.A, a.d_label, s))) return rc;
+  if (a.d_q) VQA_CUDA_CHECK(cudaMemcpy2DAsync(a.d_q, (size_t)a.H * 4, w.qq + a.H, (size_t)2 * a.H * 4, (size_t)a.H * 4, a.B,
+                                              cudaMemcpyDeviceToDevice, s));
+  g_last_forward_launches = launch_count() - before;
+  return VQA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Shared host/device helpers for the vqa_b200 C-ABI library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/vqa_b200.h"
+
+namespace vqa {
+
+// ---- error reporting (thread local, returned through vqa_last_error) -------
+char* error_buffer();
+int fail(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+int launch_count();
+void reset_launch_count();
+
+#define VQA_CUDA_CHECK(expr)                                                         \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess)                                                           \
+      return ::vqa::fail(VQA_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,  \
+                         cudaGetErrorString(_e));                                    \
+  } while (0)
+
+#define VQA_LAUNCH_CHECK()                                                           \
+  do {                                                                               \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess)                                                           \
+      return ::vqa::fail(VQA_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__,        \
+                         __LINE__, cudaGetErrorString(_e));                          \
+    ::vqa::count_launch();                                                           \
+  } while (0)
+
+#define VQA_REQUIRE(cond, ...)                                                       \
+  do {                                                                               \
+    if (!(cond)) return ::vqa::fail(VQA_ERR_INVALID, __VA_ARGS__);                   \
+  } while (0)
+
+int require_sm100();          // VQA_OK or VQA_ERR_UNSUPPORTED
+int sm_count();
+
+inline size_t elem_size(int dtype) { return dtype == VQA_BF16 ? 2 : 4; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device-side element helpers -------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static __device__ __forceinline__ float to_f(float x) { return x; }
+  static __device__ __forceinline__ float from_f(float x) { return x; }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float x) { return __float2bfloat16_rn(x); }
+};
+
+// 8 consecutive elements <-> 8 floats (16 B for bf16, 32 B for f32)
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 r;
+  r.x = pack_bf16x2(v[0], v[1]); r.y = pack_bf16x2(v[2], v[3]);
+  r.z = pack_bf16x2(v[4], v[5]); r.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- internal launchers shared between api.cu and the kernels --------------
+int linear_simt(const vqa_linear_args& a, cudaStream_t s);
+int linear_tc(const vqa_linear_args& a, cudaStream_t s);
+int linear_tc_part_width();
+
+}  // namespace vqa

@@ -1,0 +1,407 @@
+// tcgen05 / TMEM / TMA implementation of vqa_linear for bf16 operands (sm_100a).
+//
+// Reference arithmetic: modules/modules.py:13-60 (FCNet = weight_norm(nn.Linear)
+// + ReLU), attention.py:70-75 (W_v projection ⊙ W_q projection → 1-wide logit
+// layer), gcn.py:101-103 and modules.py:92-93 (plain nn.Linear maps).
+//
+// Design (B200-first, not a translation of anything in the reference — it has no
+// kernels): persistent warp-specialised CTA per SM.
+//   warp 0    TMA producer: cp.async.bulk.tensor 2-D loads of a 128x64 A box and a
+//             BNx64 W box (bf16, 128-byte swizzle) into a STAGES-deep smem ring,
+//             completion on mbarriers (complete_tx)
+//   warp 1    MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//             (M=128, N=BN, K=16) with smem descriptors; fp32 accumulators live in
+//             TMEM, double buffered (2 x BN columns) so the epilogue of tile i
+//             overlaps the main loop of tile i+1; tcgen05.commit frees smem slots
+//   warp 2    TMEM allocator (tcgen05.alloc / dealloc)
+//   warps 4-7 epilogue: tcgen05.ld 32x32b (thread = accumulator row), fused
+//             scale·acc + bias → ReLU → ⊙mul → {store | row-reduction with logit_w}
+// A is [M,K] row-major, W is [N,K] row-major (nn.Linear layout): both operands are
+// K-major, so no transposes are ever materialised.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace vqa {
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int THREADS = 256;
+constexpr int EPI_WARP0 = 4;           // warps 4..7 (warp_id % 4 selects the TMEM lane quarter)
+
+__host__ __device__ constexpr int pow2_ge(int x) { int p = 32; while (p < x) p <<= 1; return p; }
+
+template <int BN> struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = pow2_ge(2 * BN);
+  static constexpr int ACC_STRIDE = TMEM_COLS / 2;
+  static constexpr int PARAM_FLOATS = 2 * 3 * BN;            // 2 acc stages x (scale,bias,logit_w)
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 256 /*barriers*/ +
+                                    PARAM_FLOATS * 4;
+};
+
+struct Params {
+  int M, N, K;
+  const float* scale; const float* bias; int relu;
+  const float* mul; int ld_mul; int mul_row_div;
+  const float* logit_w;
+  void* out; int ldo; int out_bf16; int n_parts;
+  int tiles_m, tiles_n;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] · B[smem]ᵀ, bf16 x bf16 → f32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive f32 columns: thread i of the warp gets row (lane base + i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 = 1024 B (8 rows x 128 B) | [46,48) version = 1
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=f32, A=B=bf16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- the kernel ----------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B needs 1024-byte alignment
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + C::STAGES * C::STAGE_BYTES;       // barrier block (256 B)
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
+  float* params_smem = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
+          tma_load_2d(sb, &tmW, full_bar(stage), kb * BK, n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          const uint64_t adesc = make_sw128_kmajor_desc(sa), bdesc = make_sw128_kmajor_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));                     // smem slot reusable when these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc)); // accumulator complete
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===== epilogue =====
+    const int q = warp - EPI_WARP0;                  // == warp % 4: TMEM lane quarter
+    const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      const int n0 = n_blk * BN;
+      // stage this tile's per-column parameters (double buffered with the accumulator)
+      float* ps = params_smem + acc * 3 * BN;
+      for (int c = et; c < BN; c += 128) {
+        const int n = n0 + c;
+        const bool ok = n < p.N;
+        ps[c] = (ok && p.scale) ? p.scale[n] : 1.f;
+        ps[BN + c] = (ok && p.bias) ? p.bias[n] : 0.f;
+        ps[2 * BN + c] = (ok && p.logit_w) ? p.logit_w[n] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float* mul_row = p.mul ? p.mul + (size_t)((row_ok ? row : 0) / p.mul_row_div) * p.ld_mul : nullptr;
+      const bool mul_vec = p.mul && ((p.ld_mul & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mul) & 15) == 0);
+      float part = 0.f;
+      const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c0, v);
+        tmem_ld_wait();
+        const int nbase = n0 + c0;
+        if (nbase >= p.N) continue;
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = fmaf(__uint_as_float(v[j]), ps[c0 + j], ps[BN + c0 + j]);
+          y[j] = p.relu ? fmaxf(t, 0.f) : t;
+        }
+        const bool full = nbase + 32 <= p.N;
+        if (mul_row) {
+          if (mul_vec && full) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 m4 = __ldg(reinterpret_cast<const float4*>(mul_row + nbase) + j4);
+              y[4 * j4] *= m4.x; y[4 * j4 + 1] *= m4.y; y[4 * j4 + 2] *= m4.z; y[4 * j4 + 3] *= m4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nbase + j < p.N) y[j] *= __ldg(mul_row + nbase + j);
+          }
+        }
+        if (p.logit_w) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) part = fmaf(y[j], ps[2 * BN + c0 + j], part);   // logit_w = 0 beyond N
+        } else if (row_ok) {
+          if (p.out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + nbase;
+            if (full && ((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                uint4 r;
+                r.x = pack_bf16x2(y[8 * j8], y[8 * j8 + 1]); r.y = pack_bf16x2(y[8 * j8 + 2], y[8 * j8 + 3]);
+                r.z = pack_bf16x2(y[8 * j8 + 4], y[8 * j8 + 5]); r.w = pack_bf16x2(y[8 * j8 + 6], y[8 * j8 + 7]);
+                reinterpret_cast<uint4*>(o)[j8] = r;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (nbase + j < p.N) o[j] = __float2bfloat16_rn(y[j]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + nbase;
+            if (full && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) {
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                reinterpret_cast<float4*>(o)[j4] = make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (nbase + j < p.N) o[j] = y[j];
+            }
+          }
+        }
+      }
+      if (p.logit_w && row_ok) reinterpret_cast<float*>(p.out)[(size_t)row * p.n_parts + n_blk] = part;
+      // release the accumulator stage
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ---- host side -------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+
+// row-major [rows, cols] bf16 matrix with leading dimension ld → 2-D map, box = [box_rows, 64 cols], SW128
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(VQA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VQA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%d cols=%d ld=%d)", (int)r, rows, cols, ld);
+  return VQA_OK;
+}
+
+template <int BN>
+static int launch(const vqa_linear_args& a, cudaStream_t s) {
+  using C = Cfg<BN>;
+  CUtensorMap tmA, tmW;
+  int rc;
+  if ((rc = make_map(&tmA, a.d_A, a.M, a.K, a.lda, BM))) return rc;
+  if ((rc = make_map(&tmW, a.d_W, a.N, a.K, a.ldw, BN))) return rc;
+  Params p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.scale = a.d_scale; p.bias = a.d_bias; p.relu = a.relu;
+  p.mul = a.d_mul; p.ld_mul = a.ld_mul; p.mul_row_div = a.mul_row_div > 0 ? a.mul_row_div : 1;
+  p.logit_w = a.d_logit_w; p.out = a.d_out; p.ldo = a.ldo; p.out_bf16 = (a.out_dtype == VQA_BF16);
+  p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
+  auto kern = linear_tc_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, THREADS, C::SMEM_BYTES, s>>>(tmA, tmW, p);
+  VQA_LAUNCH_CHECK();
+  return VQA_OK;
+}
+
+}  // namespace tc
+
+int linear_tc_part_width() { return 256; }
+
+int linear_tc(const vqa_linear_args& a, cudaStream_t s) {
+  VQA_REQUIRE(a.K % tc::BK == 0, "vqa_linear(bf16): K=%d must be a multiple of %d", a.K, tc::BK);
+  VQA_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0 && (uintptr_t)a.d_A % 16 == 0 && (uintptr_t)a.d_W % 16 == 0,
+              "vqa_linear(bf16): TMA needs 16-byte aligned rows (lda=%d ldw=%d)", a.lda, a.ldw);
+  if (a.M == 0) return VQA_OK;
+  if (a.d_logit_w) return tc::launch<256>(a, s);          // part width is fixed at 256 columns
+  // pick the widest N tile that still gives every SM a tile (small-M layers), else 256
+  const int tiles_m = (a.M + tc::BM - 1) / tc::BM;
+  const int sms = sm_count();
+  if (tiles_m * ((a.N + 255) / 256) >= sms) return tc::launch<256>(a, s);
+  if (tiles_m * ((a.N + 127) / 128) >= sms || a.N > 1024) return tc::launch<128>(a, s);
+  return tc::launch<64>(a, s);
+}
+
+}  // namespace vqa

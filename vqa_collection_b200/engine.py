@@ -1,0 +1,250 @@
+"""Whole-path engine: prepared weights + one C call per forward.
+
+``VQAEngine`` owns device copies of the weights in the layout the kernels want
+(bf16 or f32, weight-norm scalars expanded to per-column scale vectors, W_q and
+q_net concatenated, the four ReGAT maps concatenated) and a workspace, and runs
+``vqa_forward`` (include/vqa_b200.h) — the B200 replacement for
+``Wrapper.forward`` / ``forward_vqa`` (wrapper.py:64-74,113-118) with
+encoder_type in {base, relation}, att_type 'new', predictor 'base'.
+
+Weights arrive under the reference's parameter names, e.g. from
+``Wrapper.state_dict()`` plus the unregistered GCN tensors as ``gcn.{i}.*``.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def weight_norm_scale(v: torch.Tensor, g: torch.Tensor) -> float:
+    """s = g/‖v‖_F evaluated with the same torch CPU op as the reference's
+    weight_norm hook (modules.py:38; SURVEY.md F13/H9: the fp32 norm is only
+    1e-5..1e-4 accurate, so it must be THIS op, not a better one)."""
+    v = v.detach().to("cpu", torch.float32)
+    g = g.detach().to("cpu", torch.float32)
+    return float(g / torch.norm(v))
+
+
+def _pad_cols(t: torch.Tensor, cols: int) -> torch.Tensor:
+    if t.shape[1] == cols:
+        return t
+    out = torch.zeros((t.shape[0], cols), dtype=t.dtype)
+    out[:, : t.shape[1]] = t
+    return out
+
+
+def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_layer: int = 0) -> dict:
+    """Reference-named tensors → device tensors in kernel layout."""
+    f32 = lambda t: t.detach().to("cpu", torch.float32)
+    dev = lambda t, dt=torch.float32: t.to(dt).contiguous().to(device)
+    P = {}
+    emb = f32(W["encoder.embedding.weight"])
+    E = emb.shape[1]
+    E_pad = (E + 63) // 64 * 64
+    P["E"], P["E_pad"], P["ntoken_rows"] = E, E_pad, emb.shape[0]
+    P["emb"] = dev(_pad_cols(emb, E_pad), dtype)
+    r = "encoder.q_rnn.rnn."
+    P["w_ih"] = dev(_pad_cols(f32(W[r + "weight_ih_l0"]), E_pad), dtype)
+    P["w_hh"] = dev(f32(W[r + "weight_hh_l0"]), dtype)
+    P["b_ih"] = dev(f32(W[r + "bias_ih_l0"]))
+    P["b_hh"] = dev(f32(W[r + "bias_hh_l0"]))
+    H = P["w_hh"].shape[1]
+
+    def wn(prefix):
+        v, g, b = f32(W[prefix + ".weight_v"]), f32(W[prefix + ".weight_g"]), f32(W[prefix + ".bias"])
+        return v, weight_norm_scale(v, g), b
+
+    v, s, b = wn("encoder.attention.W_v.main.0")
+    P["Wv"], P["sv"], P["bv"] = dev(v, dtype), dev(torch.full((v.shape[0],), s)), dev(b)
+    vq, sq, bq = wn("encoder.attention.W_q.main.0")
+    vn, sn, bn = wn("encoder.q_net.main.0")
+    P["Wqq"] = dev(torch.cat([vq, vn], 0), dtype)
+    P["sqq"] = dev(torch.cat([torch.full((vq.shape[0],), sq), torch.full((vn.shape[0],), sn)]))
+    P["bqq"] = dev(torch.cat([bq, bn]))
+    vl, sl, bl = wn("encoder.attention.linear")
+    P["wlin"] = dev((vl * sl).reshape(-1))
+    P["b_lin"] = float(bl.reshape(-1)[0])
+    v, s, b = wn("predictor.v_net.main.0")
+    P["Wvn"], P["svn"], P["bvn"] = dev(v, dtype), dev(torch.full((v.shape[0],), s)), dev(b)
+    v, s, b = wn("predictor.classifier.main.0")
+    P["Wc0"], P["sc0"], P["bc0"] = dev(v, dtype), dev(torch.full((v.shape[0],), s)), dev(b)
+    v, s, b = wn("predictor.classifier.main.3")
+    P["Wc1"], P["sc1"], P["bc1"] = dev(v, dtype), dev(torch.full((v.shape[0],), s)), dev(b)
+    P["H"], P["V"], P["A"] = H, P["Wv"].shape[1], P["Wc1"].shape[0]
+    if relation:
+        p = f"gcn.{gcn_layer}."
+        P.update(prepare_gcn_layer({k[len(p):]: t for k, t in W.items() if k.startswith(p)}, dtype, device))
+    return P
+
+
+def prepare_gcn_layer(Wl: dict, dtype, device) -> dict:
+    """One CorrelatedGraphConv layer (gcn.py:55-67,113-117): concatenate
+    [W0+W1 ; W2 ; Wa ; Wb] so a single pass over x feeds all four maps."""
+    f32 = lambda t: t.detach().to("cpu", torch.float32)
+    dev = lambda t, dt=torch.float32: t.to(dt).contiguous().to(device)
+    w01 = f32(Wl["weight.0.weight"]) + f32(Wl["weight.1.weight"])
+    Wg = torch.cat([w01, f32(Wl["weight.2.weight"]), f32(Wl["dot_product.wa.weight"]),
+                    f32(Wl["dot_product.wb.weight"])], 0)
+    return {"Wg": dev(Wg, dtype), "label_bias": dev(f32(Wl["bias"])),
+            "ba": dev(f32(Wl["dot_product.wa.bias"])), "bb": dev(f32(Wl["dot_product.wb.bias"])),
+            "num_labels": Wl["bias"].shape[0]}
+
+
+class VQAEngine:
+    """B200 forward engine for the Up-Down (+ReGAT) VQA path."""
+
+    def __init__(self, weights: dict, relation: bool = False, precision: str = "bf16",
+                 device="cuda", num_objs: int = 36):
+        self.lib = L.load()
+        self.device = torch.device(device)
+        self.dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[precision]
+        self.precision = precision
+        self.relation = bool(relation)
+        self.K = num_objs
+        with torch.cuda.device(self.device):
+            self.P = prepare_weights(weights, self.dtype, self.device, self.relation)
+        self._ws = {}
+        self.last_launches = 0
+
+    # -- helpers ---------------------------------------------------------------
+    def _args(self, B, T):
+        P, a = self.P, L.ForwardArgs()
+        a.B, a.K, a.V, a.H, a.A, a.T = B, self.K, P["V"], P["H"], P["A"], T
+        a.E_pad, a.ntoken_rows = P["E_pad"], P["ntoken_rows"]
+        a.num_labels = P.get("num_labels", 0)
+        a.dtype, a.relation = ops.dtype_code(self.dtype), int(self.relation)
+        for name in ("emb", "w_ih", "b_ih", "w_hh", "b_hh", "Wv", "sv", "bv", "Wqq", "sqq", "bqq", "wlin",
+                     "Wvn", "svn", "bvn", "Wc0", "sc0", "bc0", "Wc1", "sc1", "bc1"):
+            setattr(a, "d_" + name, P[name].data_ptr())
+        a.b_lin = P["b_lin"]
+        if self.relation:
+            for name in ("Wg", "label_bias", "ba", "bb"):
+                setattr(a, "d_" + name, P[name].data_ptr())
+        return a
+
+    def _workspace(self, a):
+        need = self.lib.vqa_forward_workspace_bytes(C.byref(a))
+        key = (a.B, a.T)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty((max(need, 1),), dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws, need
+
+    def resident(self, img: torch.Tensor) -> torch.Tensor:
+        """Wire-format f32 features → the resident compute dtype (bf16 cast kernel)."""
+        if img.dtype == self.dtype:
+            return img
+        if img.dtype == torch.float32 and self.dtype == torch.bfloat16:
+            return ops.cast_to_bf16(img.contiguous())
+        raise TypeError(f"img dtype {img.dtype} cannot feed a {self.precision} engine")
+
+    # -- device-resident forward -------------------------------------------------
+    def forward(self, img, tokens, labels=None, bbox=None, wh=None, want_v=False, want_q=False,
+                want_alpha=False):
+        """img [B,K,V] (CUDA, f32 or the engine dtype), tokens int64 [B,T] (CUDA);
+        relation engines also need ``labels`` u8 [B,K,K] or ``bbox`` f32 [B,K,4] + ``wh``=(w,h).
+        Returns dict(logits f32 [B,A], label int64 [B], att f32 [B,K], ...)."""
+        if not (img.is_cuda and tokens.is_cuda):
+            raise RuntimeError("VQAEngine.forward needs CUDA tensors (use forward_host for host buffers)")
+        n_cast = int(img.dtype != self.dtype)
+        img = self.resident(img).contiguous()
+        tokens = tokens.contiguous()
+        B, K, V = img.shape
+        if K != self.K or V != self.P["V"]:
+            raise ValueError(f"img must be [B,{self.K},{self.P['V']}], got {tuple(img.shape)}")
+        a = self._args(B, tokens.shape[1])
+        ws, need = self._workspace(a)
+        dev = self.device
+        out = {
+            "logits": torch.empty((B, a.A), dtype=torch.float32, device=dev),
+            "label": torch.empty((B,), dtype=torch.int64, device=dev),
+            "att": torch.empty((B, K), dtype=torch.float32, device=dev),
+        }
+        a.d_img, a.d_tokens = img.data_ptr(), tokens.data_ptr()
+        a.d_workspace, a.workspace_bytes = ws.data_ptr(), need
+        a.d_logits, a.d_label, a.d_att = out["logits"].data_ptr(), out["label"].data_ptr(), out["att"].data_ptr()
+        if want_v:
+            out["v"] = torch.empty((B, K, V), dtype=self.dtype, device=dev)
+            a.d_v = out["v"].data_ptr()
+        if want_q:
+            out["q"] = torch.empty((B, a.H), dtype=torch.float32, device=dev)
+            a.d_q = out["q"].data_ptr()
+        if self.relation:
+            if labels is not None:
+                if labels.dtype != torch.uint8:
+                    labels = labels.to(torch.uint8)          # loader format is float64 (dataset.py:102)
+                labels = labels.contiguous()
+                a.d_labels = labels.data_ptr()
+                out["labels"] = labels
+            elif bbox is not None:
+                if wh is None:
+                    raise ValueError("bbox needs wh=(img_w, img_h)")
+                bbox = bbox.contiguous()
+                out["labels"] = torch.empty((B, K, K), dtype=torch.uint8, device=dev)
+                a.d_bbox, a.d_labels_out = bbox.data_ptr(), out["labels"].data_ptr()
+                a.img_w, a.img_h = float(wh[0]), float(wh[1])
+            else:
+                raise ValueError("relation engine needs labels or bbox")
+            if want_alpha:
+                out["alpha"] = torch.empty((B, K, K), dtype=torch.float32, device=dev)
+                a.d_alpha = out["alpha"].data_ptr()
+        L.check(self.lib.vqa_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.last_launches = self.lib.vqa_forward_last_launch_count() + n_cast
+        return out
+
+    # -- host-buffer forward (the e2e path) ----------------------------------------
+    def forward_host(self, img_h, tokens_h, labels_h=None, bbox_h=None, wh=None, chunk=128):
+        """Host (pinned) buffers in the reference wire format → host results.
+
+        img_h f32 [B,K,V], tokens_h int64 [B,T] (+ labels_h u8/f64 [B,K,K] or bbox_h f32).
+        The feature copy is chunked: chunk i+1's H2D overlaps chunk i's f32→bf16 cast; the
+        forward runs once on the resident batch; the answers come back with one D2H.
+        Returns (label int64 [B] on host, bytes_h2d, bytes_d2h)."""
+        B, K, V = img_h.shape
+        dev = self.device
+        copy_s = getattr(self, "_copy_stream", None)
+        if copy_s is None:
+            copy_s = self._copy_stream = torch.cuda.Stream(device=dev)
+        main_s = torch.cuda.current_stream()
+        res = torch.empty((B, K, V), dtype=self.dtype, device=dev)
+        stage = [torch.empty((chunk, K, V), dtype=torch.float32, device=dev) for _ in range(2)]
+        free_ev = [None, None]
+        h2d = 0
+        copy_s.wait_stream(main_s)
+        for i, b0 in enumerate(range(0, B, chunk)):
+            b1 = min(B, b0 + chunk)
+            buf = stage[i & 1][: b1 - b0]
+            with torch.cuda.stream(copy_s):
+                if free_ev[i & 1] is not None:
+                    copy_s.wait_event(free_ev[i & 1])
+                buf.copy_(img_h[b0:b1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+            main_s.wait_event(ev)
+            if self.dtype == torch.float32:
+                res[b0:b1].copy_(buf)
+            else:
+                L.check(self.lib.vqa_cast_f32_to_bf16(buf.data_ptr(), res[b0:b1].data_ptr(), buf.numel(),
+                                                      C.c_void_p(main_s.cuda_stream)))
+            free_ev[i & 1] = torch.cuda.Event()
+            free_ev[i & 1].record(main_s)
+            h2d += buf.numel() * 4
+        tokens = tokens_h.to(dev, non_blocking=True)
+        h2d += tokens_h.numel() * 8
+        labels = bbox = None
+        if self.relation:
+            if labels_h is not None:
+                labels = labels_h.to(dev, non_blocking=True)
+                h2d += labels_h.numel() * labels_h.element_size()
+            else:
+                bbox = bbox_h.to(dev, non_blocking=True)
+                h2d += bbox_h.numel() * 4
+        out = self.forward(res, tokens, labels=labels, bbox=bbox, wh=wh)
+        n_chunks = (B + chunk - 1) // chunk
+        self.last_launches += n_chunks if self.dtype == torch.bfloat16 else 0
+        label_h = out["label"].to("cpu")           # synchronising D2H of the answers
+        return label_h, h2d, label_h.numel() * 8

@@ -1,0 +1,235 @@
+"""Tensor-level wrappers over the C ABI (include/vqa_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every
+function passes raw device pointers + sizes to the library and returns torch
+tensors allocated with the caching allocator.  Inputs must already be CUDA
+tensors; there is no CPU path (non-CUDA input raises, like a device mismatch
+does in the reference).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_TORCH_DTYPE = {L.VQA_F32: torch.float32, L.VQA_BF16: torch.bfloat16}
+
+
+def dtype_code(t: torch.dtype) -> int:
+    if t == torch.float32:
+        return L.VQA_F32
+    if t == torch.bfloat16:
+        return L.VQA_BF16
+    raise TypeError(f"vqa_collection_b200: unsupported dtype {t} (float32 or bfloat16)")
+
+
+def torch_dtype(code: int) -> torch.dtype:
+    return _TORCH_DTYPE[code]
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _require(t, dtype=None, name="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"vqa_collection_b200: {name} must be a CUDA tensor (no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"vqa_collection_b200: {name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"vqa_collection_b200: {name} must be contiguous")
+    return t
+
+
+def device_info():
+    lib = L.load()
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    L.check(lib.vqa_device_info(C.byref(a), C.byref(b), C.byref(c)))
+    return {"sm_count": a.value, "cc": (b.value, c.value)}
+
+
+def relation_labels(bbox, img_w=None, img_h=None, wh=None):
+    """bbox f32 [B,K,4] (CUDA) → uint8 [B,K,K].  util/relation.py:65-80 batched."""
+    lib = L.load()
+    _require(bbox, torch.float32, "bbox")
+    if bbox.dim() != 3 or bbox.shape[2] != 4:
+        raise ValueError("bbox must be [B,K,4]")
+    B, K = bbox.shape[0], bbox.shape[1]
+    if wh is not None:
+        _require(wh, torch.float32, "wh")
+        if tuple(wh.shape) != (B, 2):
+            raise ValueError("wh must be [B,2]")
+    elif img_w is None or img_h is None:
+        raise ValueError("relation_labels needs (img_w, img_h) or a per-image wh tensor")
+    out = torch.empty((B, K, K), dtype=torch.uint8, device=bbox.device)
+    L.check(lib.vqa_relation_labels(_ptr(bbox), _ptr(wh), B, K, float(img_w or 0), float(img_h or 0),
+                                    _ptr(out), _stream()))
+    return out
+
+
+def relation_labels_host(bbox_np, img_w, img_h):
+    """Host-buffer form: numpy f32 [B,K,4] → numpy uint8 [B,K,K] (H2D + kernel + D2H)."""
+    import numpy as np
+    lib = L.load()
+    bbox_np = np.ascontiguousarray(bbox_np, dtype=np.float32)
+    B, K = bbox_np.shape[0], bbox_np.shape[1]
+    out = np.empty((B, K, K), dtype=np.uint8)
+    L.check(lib.vqa_relation_labels_host(bbox_np.ctypes.data_as(C.c_void_p), B, K, float(img_w), float(img_h),
+                                         out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def cast_to_bf16(x):
+    lib = L.load()
+    _require(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    L.check(lib.vqa_cast_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()))
+    return out
+
+
+def cast_to_f32(x):
+    lib = L.load()
+    _require(x, torch.bfloat16, "x")
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    L.check(lib.vqa_cast_bf16_to_f32(_ptr(x), _ptr(out), x.numel(), _stream()))
+    return out
+
+
+def linear_part_width(dtype: torch.dtype) -> int:
+    return L.load().vqa_linear_part_width(dtype_code(dtype))
+
+
+def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, logit_w=None,
+           out_dtype=None, N=None):
+    """Fused weight-normed linear layer (modules.py:13-60), see vqa_linear in the header.
+
+    A [M,K], W [N_rows,K] (same dtype); returns [M,N] (out_dtype) or, with ``logit_w``,
+    the f32 row-reduction parts [M, n_parts].  ``N`` < W.shape[0] uses only the first N
+    rows of W (row-padded weights).
+    """
+    lib = L.load()
+    _require(A, None, "A")
+    _require(W, A.dtype, "W")
+    if A.dim() != 2 or W.dim() != 2 or A.shape[1] != W.shape[1]:
+        raise ValueError(f"linear: shape mismatch A{tuple(A.shape)} W{tuple(W.shape)}")
+    M, K = A.shape
+    N = W.shape[0] if N is None else N
+    code = dtype_code(A.dtype)
+    for nm, t in (("scale", scale), ("bias", bias), ("logit_w", logit_w)):
+        if t is not None:
+            _require(t, torch.float32, nm)
+            if t.numel() < N:
+                raise ValueError(f"linear: {nm} has {t.numel()} < N={N} elements")
+    a = L.LinearArgs()
+    a.d_A, a.lda, a.d_W, a.ldw = A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0)
+    a.M, a.N, a.K, a.dtype = M, N, K, code
+    a.d_scale, a.d_bias, a.relu = _ptr(scale), _ptr(bias), int(bool(relu))
+    if mul is not None:
+        _require(mul, torch.float32, "mul")
+        a.d_mul, a.ld_mul, a.mul_row_div = mul.data_ptr(), mul.stride(0), int(mul_row_div)
+    else:
+        a.mul_row_div = 1
+    if logit_w is not None:
+        pw = lib.vqa_linear_part_width(code)
+        n_parts = (N + pw - 1) // pw
+        out = torch.empty((M, n_parts), dtype=torch.float32, device=A.device)
+        a.d_logit_w, a.ldo, a.out_dtype = logit_w.data_ptr(), n_parts, L.VQA_F32
+    else:
+        out_dtype = A.dtype if out_dtype is None else out_dtype
+        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+        a.ldo, a.out_dtype = N, dtype_code(out_dtype)
+    a.d_out = out.data_ptr()
+    L.check(lib.vqa_linear(C.byref(a), _stream()))
+    return out
+
+
+def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False):
+    """Embedding gather + GRU last state (encoder.py:159-160, modules.py:139-159).
+
+    tokens int64 [B,T]; emb [rows,E_pad]; w_ih [3H,E_pad]; w_hh [3H,H] (all one dtype);
+    biases f32.  Returns f32 [B,H] (and the low-precision copy when ``want_lp``).
+    """
+    lib = L.load()
+    _require(tokens, torch.int64, "tokens")
+    _require(emb, None, "emb")
+    _require(w_ih, emb.dtype, "w_ih")
+    _require(w_hh, emb.dtype, "w_hh")
+    _require(b_ih, torch.float32, "b_ih")
+    _require(b_hh, torch.float32, "b_hh")
+    B, T = tokens.shape
+    H = w_hh.shape[1]
+    E_pad = emb.shape[1]
+    if w_ih.shape != (3 * H, E_pad) or w_hh.shape != (3 * H, H):
+        raise ValueError("gru_last_state: weight shapes do not match")
+    code = dtype_code(emb.dtype)
+    ws_bytes = lib.vqa_gru_workspace_bytes(B, T, H, E_pad, code)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=tokens.device)
+    h = torch.empty((B, H), dtype=torch.float32, device=tokens.device)
+    h_lp = torch.empty((B, H), dtype=emb.dtype, device=tokens.device) if want_lp else None
+    a = L.GruArgs()
+    a.d_tokens, a.B, a.T, a.H, a.E_pad, a.ntoken_rows, a.dtype = tokens.data_ptr(), B, T, H, E_pad, emb.shape[0], code
+    a.d_emb, a.d_w_ih, a.d_b_ih, a.d_w_hh, a.d_b_hh = (emb.data_ptr(), w_ih.data_ptr(), b_ih.data_ptr(),
+                                                       w_hh.data_ptr(), b_hh.data_ptr())
+    a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+    a.d_h_last, a.d_h_last_lp = h.data_ptr(), (h_lp.data_ptr() if want_lp else None)
+    L.check(lib.vqa_gru_last_state(C.byref(a), _stream()))
+    return (h, h_lp) if want_lp else h
+
+
+def attention_pool(parts, logit_bias, x, want_att=True, want_vsum=True, want_vatt=False):
+    """softmax over K + weighted sums (attention.py:86, encoder.py:166, predictor.py:85).
+
+    parts f32 [B*K, n_parts]; x [B,K,V].  Returns (att f32 [B,K], vsum [B,V], vatt [B,K,V]),
+    None for outputs not requested."""
+    lib = L.load()
+    _require(parts, torch.float32, "parts")
+    _require(x, None, "x")
+    B, K, V = x.shape
+    if parts.shape[0] != B * K:
+        raise ValueError("attention_pool: parts rows != B*K")
+    att = torch.empty((B, K), dtype=torch.float32, device=x.device) if want_att else None
+    vsum = torch.empty((B, V), dtype=x.dtype, device=x.device) if want_vsum else None
+    vatt = torch.empty((B, K, V), dtype=x.dtype, device=x.device) if want_vatt else None
+    L.check(lib.vqa_attention_pool(_ptr(parts), parts.shape[1], float(logit_bias), _ptr(x), B, K, V,
+                                   dtype_code(x.dtype), _ptr(att), _ptr(vsum), _ptr(vatt), _stream()))
+    return att, vsum, vatt
+
+
+def graph_attention(Y, att, labels, label_bias, ba, bb, K, want_out=True, want_vsum=False, want_alpha=False):
+    """One CorrelatedGraphConv layer + ReLU after the wide projection (gcn.py:93-168,211-212).
+
+    Y [B*K, 4V] = x·[W0+W1; W2; Wa; Wb]ᵀ; att f32 [B,K] or None; labels u8 [B,K,K]."""
+    lib = L.load()
+    _require(Y, None, "Y")
+    _require(labels, torch.uint8, "labels")
+    _require(label_bias, torch.float32, "label_bias")
+    _require(ba, torch.float32, "ba")
+    _require(bb, torch.float32, "bb")
+    if att is not None:
+        _require(att, torch.float32, "att")
+    V = Y.shape[1] // 4
+    B = Y.shape[0] // K
+    out = torch.empty((B, K, V), dtype=Y.dtype, device=Y.device) if want_out else None
+    vsum = torch.empty((B, V), dtype=Y.dtype, device=Y.device) if want_vsum else None
+    alpha = torch.empty((B, K, K), dtype=torch.float32, device=Y.device) if want_alpha else None
+    a = L.GraphAttentionArgs()
+    a.d_Y, a.ldy, a.d_att, a.d_labels = Y.data_ptr(), Y.stride(0), _ptr(att), labels.data_ptr()
+    a.d_label_bias, a.num_labels, a.d_ba, a.d_bb = label_bias.data_ptr(), label_bias.shape[0], ba.data_ptr(), bb.data_ptr()
+    a.B, a.K, a.V, a.dtype = B, K, V, dtype_code(Y.dtype)
+    a.d_out, a.d_vsum, a.d_alpha = _ptr(out), _ptr(vsum), _ptr(alpha)
+    L.check(lib.vqa_graph_attention(C.byref(a), _stream()))
+    return out, vsum, alpha
+
+
+def argmax_rows(logits):
+    """Lowest-index argmax per row (wrapper.py:14)."""
+    lib = L.load()
+    _require(logits, torch.float32, "logits")
+    B, A = logits.shape
+    out = torch.empty((B,), dtype=torch.int64, device=logits.device)
+    L.check(lib.vqa_argmax_rows(_ptr(logits), B, A, logits.stride(0), _ptr(out), _stream()))
+    return out
