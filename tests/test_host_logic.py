@@ -1,0 +1,219 @@
+"""CPU tests of the host side: C-ABI surface, parameter names, weight preparation, the
+comparison-only octant rule, sharding (incl. a world_size-2 gloo run).  No compute calls
+into the library (there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vqa_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from vqa_collection_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    from vqa_collection_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "vqa_b200.h")).read()
+    declared = set(re.findall(r"\b(vqa_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(libpath)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.vqa_abi_version.restype = ctypes.c_int
+    assert lib.vqa_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors have one field per member of the C structs, in order"""
+    from vqa_collection_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "vqa_b200.h")).read()
+    for cname, cls in (("vqa_linear_args", _lib.LinearArgs), ("vqa_gru_args", _lib.GruArgs),
+                       ("vqa_graph_attention_args", _lib.GraphAttentionArgs), ("vqa_forward_args", _lib.ForwardArgs)):
+        body = re.search(r"typedef struct \{([^}]*)\}\s*" + cname + ";", header).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for stmt in body.split(";"):
+            stmt = stmt.strip()
+            if not stmt:
+                continue
+            for part in stmt.split(","):
+                names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", part.strip())[0])
+        assert names == [f[0] for f in cls._fields_], cname
+
+
+def test_library_fails_loudly_without_gpu(libpath):
+    from vqa_collection_b200 import _lib
+    lib = _lib.load()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    rc = lib.vqa_relation_labels(None, None, 1, 36, 640.0, 480.0, None, None)
+    assert rc != 0 and len(lib.vqa_last_error()) > 0           # an error code, never a CPU fallback
+    from vqa_collection_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.relation_labels(torch.zeros((1, 36, 4)), 640, 480)
+    with pytest.raises(RuntimeError):
+        ops.linear(torch.zeros((8, 64)), torch.zeros((8, 64)))
+
+
+REF_KEYS = [
+    "encoder.embedding.weight", "encoder.q_rnn.rnn.weight_ih_l0", "encoder.q_rnn.rnn.weight_hh_l0",
+    "encoder.q_rnn.rnn.bias_ih_l0", "encoder.q_rnn.rnn.bias_hh_l0",
+    "encoder.attention.W_v.main.0.bias", "encoder.attention.W_v.main.0.weight_g", "encoder.attention.W_v.main.0.weight_v",
+    "encoder.attention.W_q.main.0.bias", "encoder.attention.W_q.main.0.weight_g", "encoder.attention.W_q.main.0.weight_v",
+    "encoder.attention.linear.bias", "encoder.attention.linear.weight_g", "encoder.attention.linear.weight_v",
+    "encoder.q_net.main.0.bias", "encoder.q_net.main.0.weight_g", "encoder.q_net.main.0.weight_v",
+    "predictor.v_net.main.0.bias", "predictor.v_net.main.0.weight_g", "predictor.v_net.main.0.weight_v",
+    "predictor.classifier.main.0.bias", "predictor.classifier.main.0.weight_g", "predictor.classifier.main.0.weight_v",
+    "predictor.classifier.main.3.bias", "predictor.classifier.main.3.weight_g", "predictor.classifier.main.3.weight_v",
+]
+
+
+@pytest.mark.parametrize("enc", ["base", "relation"])
+def test_drop_in_parameter_names_and_checkpoint_loading(enc):
+    """state_dict keys are the reference's (SURVEY.md §8b probed listing) → old checkpoints load"""
+    from vqa_collection_b200.modules.wrapper import set_model
+    cfg = O.SMALL_REGAT if enc == "relation" else O.SMALL
+    m = set_model(encoder_type=enc, predictor_type="base", decoder_type="none", ntoken=cfg.ntoken, v_dim=cfg.v_dim,
+                  embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2,
+                  c_len=20, device="cpu", dropout=0.2, rnn_type="GRU", att_type="new", conv_layer=1, conv_type="corr")
+    assert list(m.state_dict().keys()) == REF_KEYS               # GCN tensors stay unregistered (F3)
+    W = O.make_weights(cfg, 1111)
+    m.load_state_dict({k: v for k, v in W.items() if not k.startswith("gcn.")}, strict=True)
+    if enc == "relation":
+        layer = m.encoder.spatial_encoder.gcn[0]                 # indexable plain list like the reference
+        assert sorted(layer.state_dict().keys()) == sorted(k[6:] for k in W if k.startswith("gcn.0."))
+        layer.load_state_dict({k[6:]: v for k, v in W.items() if k.startswith("gcn.0.")}, strict=True)
+        names = m.reference_named_weights()
+        assert set(names) == set(W)
+    with pytest.raises(NotImplementedError):
+        m.get_loss({})
+    m.train()
+    with pytest.raises(NotImplementedError):                     # training path must not silently run eval math
+        m.encoder.q_net(torch.zeros(2, cfg.hidden_dim))
+
+
+def test_unsupported_configurations_raise():
+    from vqa_collection_b200.modules.wrapper import set_model
+    from vqa_collection_b200.modules.attention import set_att, MultiplyAttention, ConcatAttention
+    from vqa_collection_b200.modules.gcn import get_graph_conv, CorrelatedGraphConv
+    assert set_att("new") is MultiplyAttention and set_att("base") is ConcatAttention
+    assert get_graph_conv("corr") is CorrelatedGraphConv
+    with pytest.raises(KeyError):
+        set_att("nope")
+    with pytest.raises(NotImplementedError):
+        set_model(decoder_type="base", device="cpu")
+
+
+def test_prepare_weights_layout():
+    from vqa_collection_b200.engine import prepare_weights, weight_norm_scale
+    cfg = O.SMALL_REGAT
+    W = O.make_weights(cfg, 7)
+    P = prepare_weights(W, torch.bfloat16, "cpu", True)
+    H, V = cfg.hidden_dim, cfg.v_dim
+    assert P["E_pad"] % 64 == 0 and P["emb"].shape == (cfg.ntoken + 1, P["E_pad"])
+    assert torch.all(P["emb"][:, cfg.embed_dim:] == 0) and torch.all(P["w_ih"][:, cfg.embed_dim:] == 0)
+    assert P["Wqq"].shape == (2 * H, H) and P["Wg"].shape == (4 * V, V)
+    s = weight_norm_scale(W["encoder.attention.W_v.main.0.weight_v"], W["encoder.attention.W_v.main.0.weight_g"])
+    assert torch.all(P["sv"] == s)
+    # weight_norm scale comes from the same torch CPU op as the reference hook (H9)
+    ref = (W["encoder.attention.W_v.main.0.weight_g"] / torch.norm(W["encoder.attention.W_v.main.0.weight_v"])).item()
+    assert s == ref
+    w01 = (W["gcn.0.weight.0.weight"] + W["gcn.0.weight.1.weight"]).to(torch.bfloat16)
+    assert torch.equal(P["Wg"][:V], w01)
+    wl = W["encoder.attention.linear.weight_v"] * O.weight_norm_scale(W["encoder.attention.linear.weight_v"],
+                                                                       W["encoder.attention.linear.weight_g"])
+    assert torch.allclose(P["wlin"], wl.reshape(-1))
+
+
+def _octant_rule(ex, ey):
+    """numpy mirror of the comparison-only octant rule in csrc/relation.cu"""
+    ab = np.zeros(ex.shape, np.uint8)
+    ba = np.zeros(ex.shape, np.uint8)
+
+    def put(m, a, b):
+        ab[m], ba[m] = a, b
+    pos, neg, zx = ex > 0, ex < 0, ex == 0
+    put(pos & (ey == 0), 3, 7)
+    put(pos & (ey < 0) & (-ey <= ex), 4, 8)
+    put(pos & (ey < 0) & (-ey > ex), 5, 9)
+    put(pos & (ey > 0) & (ex <= ey), 10, 6)
+    put(pos & (ey > 0) & (ex > ey), 11, 7)
+    put(neg & (ey == 0), 7, 3)
+    put(neg & (ey < 0) & (ex >= ey), 6, 10)
+    put(neg & (ey < 0) & (ex < ey), 7, 11)
+    put(neg & (ey > 0) & (ey <= -ex), 8, 4)
+    put(neg & (ey > 0) & (ey > -ex), 9, 5)
+    put(zx & (ey < 0), 5, 9)
+    put(zx & (ey >= 0), 9, 5)
+    return ab, ba
+
+
+def test_octant_rule_equals_arctan2_pipeline_on_grid():
+    """the rule the kernel uses == the reference's float32 arctan2 pipeline on half-integer offsets
+    (exact boundaries hit often, never merely approached: SURVEY.md H2)"""
+    r = np.arange(-200, 201, dtype=np.float32) * 0.5
+    ex, ey = [a.ravel() for a in np.meshgrid(r, r)]
+    delta = np.rad2deg(np.arctan2(ex, ey)) - np.float32(90)
+    idx = lambda x: (np.ceil((x % np.float32(360)) / np.float32(45)) + 3).astype(np.uint8)
+    ab, ba = _octant_rule(ex, ey)
+    assert np.array_equal(ab, idx(delta)) and np.array_equal(ba, idx(delta + np.float32(180)))
+
+
+def test_shard_bounds_cover_rows_exactly():
+    from vqa_collection_b200.parallel import shard_bounds, shard_batch
+    for n in (0, 1, 7, 1024, 1027):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(n, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+    batch = O.make_batch(O.SMALL_REGAT, 10, 3)
+    s = shard_batch(batch, 4, 1)
+    assert s["img"].shape[0] == 3 and s["graph"].shape[0] == 3 and s["wh"] == batch["wh"]
+    assert torch.equal(s["q"], batch["q"][3:6])
+
+
+GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import vqa_oracle as O
+from vqa_collection_b200.parallel import shard_batch, gather_rows, reduce_score
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+cfg = O.SMALL
+W = O.make_weights(cfg, 1111)
+batch = O.make_batch(cfg, 11, 5)                   # ragged: 6 + 5 rows
+with torch.no_grad():
+    full_score, full_label, _ = O.forward_vqa(batch, W, cfg)
+    local = shard_batch(batch, world, rank)
+    score, label, _ = O.forward_vqa(local, W, cfg)   # the CPU oracle stands in for the per-rank engine
+labels = gather_rows(label, 11)
+total = reduce_score(score.sum())
+assert torch.equal(labels, full_label), (labels, full_label)
+assert torch.allclose(total, full_score.sum())
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_sharded_forward_equals_unsharded(tmp_path):
+    """world_size-2 gloo run: sharded result == unsharded result, no data-path collective"""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29531", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

@@ -65,8 +65,9 @@ static bool force_simt() {
 }
 
 static int linear_dispatch(const vqa_linear_args& a, cudaStream_t s) {
-  VQA_REQUIRE(a.d_A && a.d_W && a.d_out, "vqa_linear: NULL pointer");
   VQA_REQUIRE(a.M >= 0 && a.N >= 1 && a.K >= 1, "vqa_linear: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  if (a.M == 0) return VQA_OK;
+  VQA_REQUIRE(a.d_A && a.d_W && a.d_out, "vqa_linear: NULL pointer");
   VQA_REQUIRE(a.dtype == VQA_F32 || a.dtype == VQA_BF16, "vqa_linear: dtype=%d", a.dtype);
   VQA_REQUIRE(a.d_mul == nullptr || a.mul_row_div >= 1, "vqa_linear: mul_row_div must be >= 1");
   if (a.dtype == VQA_BF16 && !force_simt()) return linear_tc(a, s);

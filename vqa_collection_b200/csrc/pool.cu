@@ -76,10 +76,10 @@ attention_pool_kernel(const float* __restrict__ parts, int n_parts, float bias,
 
 int attention_pool(const float* parts, int n_parts, float bias, const void* x, int B, int K, int V,
                    int dtype, float* att, void* vsum, void* vatt, cudaStream_t s) {
-  VQA_REQUIRE(parts && x, "attention_pool: NULL input");
   VQA_REQUIRE(K >= 1 && K <= kPoolMaxK, "attention_pool: K=%d out of range", K);
   VQA_REQUIRE(V % 8 == 0 && n_parts >= 1, "attention_pool: V=%d must be a multiple of 8", V);
   if (B == 0) return VQA_OK;
+  VQA_REQUIRE(parts && x, "attention_pool: NULL input");
   if (dtype == VQA_BF16) {
     attention_pool_kernel<__nv_bfloat16><<<B, kPoolThreads, 0, s>>>(
         parts, n_parts, bias, (const __nv_bfloat16*)x, B, K, V, att, (__nv_bfloat16*)vsum,
@@ -118,8 +118,8 @@ argmax_rows_kernel(const float* __restrict__ logits, int B, int A, int ld, int64
 }
 
 int argmax_rows(const float* logits, int B, int A, int ld, int64_t* out, cudaStream_t s) {
-  VQA_REQUIRE(logits && out && A >= 1 && ld >= A, "argmax_rows: bad arguments");
   if (B == 0) return VQA_OK;
+  VQA_REQUIRE(logits && out && A >= 1 && ld >= A, "argmax_rows: bad arguments");
   const int rows_per_cta = 8;
   argmax_rows_kernel<<<(B + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, s>>>(logits, B, A,
                                                                                         ld, out);

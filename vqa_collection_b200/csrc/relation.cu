@@ -95,10 +95,10 @@ relation_labels_kernel(const float4* __restrict__ bbox, const float2* __restrict
 
 int relation_labels(const float* d_bbox, const float* d_wh, int B, int K, float img_w, float img_h,
                     uint8_t* d_labels, cudaStream_t s) {
-  VQA_REQUIRE(d_bbox && d_labels, "relation_labels: NULL pointer");
   VQA_REQUIRE(K >= 1 && K <= kRelMaxK, "relation_labels: K=%d out of range [1,%d]", K, kRelMaxK);
   VQA_REQUIRE(B >= 0, "relation_labels: B=%d", B);
-  if (B == 0) return VQA_OK;
+  if (B == 0) return VQA_OK;                       // empty batch: nothing to do (pointers may be NULL)
+  VQA_REQUIRE(d_bbox && d_labels, "relation_labels: NULL pointer");
   const double half_diag = 0.5 * sqrt((double)img_w * (double)img_w + (double)img_h * (double)img_h);
   const int grid = B < sm_count() * 8 ? B : sm_count() * 8;
   relation_labels_kernel<<<grid, kRelThreads, 0, s>>>(reinterpret_cast<const float4*>(d_bbox),

@@ -1,0 +1,78 @@
+"""Attention blocks — mirror of modules/attention.py on the C-ABI kernels.
+
+MultiplyAttention ('new', attention.py:54-86): the W_v projection, the ⊙ with the W_q
+projection and the 1-wide logit layer run as ONE tcgen05 GEMM with a row-reduction
+epilogue (the [B,K,H] projection never reaches HBM); softmax over the K regions is the
+pooling kernel.
+"""
+import torch
+import torch.nn as nn
+
+from .. import compute_dtype, ops
+from .modules import FCNet, PreparedCache, as_compute, wn_linear, _no_training
+from ..engine import weight_norm_scale
+
+
+def set_att(att_type):
+    return {
+        'base': ConcatAttention,
+        'new': MultiplyAttention
+    }[att_type]
+
+
+class MultiplyAttention(nn.Module):
+    """softmax_K( w · (ReLU(W_v v) ⊙ ReLU(W_q q)) + b )   (attention.py:54-86)"""
+
+    def __init__(self, v_dim, q_dim, hidden_dim, dropout=0.2):
+        super().__init__()
+        self.W_v = FCNet(v_dim, hidden_dim)
+        self.W_q = FCNet(q_dim, hidden_dim)
+        self.dropout = nn.Dropout(dropout)              # identity in eval (attention.py:74)
+        self.linear = wn_linear(q_dim, 1)               # uses q_dim like the reference (:66)
+        self._cache = PreparedCache()
+
+    def _logit_vector(self):
+        lin = self.linear
+        return self._cache.get("wlin", (lin.weight_v, lin.weight_g), lambda: (
+            lin.weight_v.detach().float().reshape(-1) * weight_norm_scale(lin.weight_v, lin.weight_g)).contiguous())
+
+    def logit_parts(self, v, q):
+        """→ (parts f32 [B*K, n_parts], x in compute dtype [B,K,V])"""
+        _no_training(self)
+        dtype = compute_dtype()
+        B, K, V = v.shape
+        x = as_compute(v, dtype)
+        qp = self.W_q(q, out_dtype=torch.float32)                            # [B,H] f32
+        (W, s, b), = self.W_v.prepared(dtype)
+        parts = ops.linear(x.view(B * K, V), W, s, b, relu=True, mul=qp.contiguous(), mul_row_div=K,
+                           logit_w=self._logit_vector())
+        return parts, x
+
+    def logits(self, v, q):
+        parts, _ = self.logit_parts(v, q)
+        B, K = v.shape[0], v.shape[1]
+        return (parts.sum(1) + self.linear.bias.detach().float()).view(B, K, 1)
+
+    def forward(self, v, q):
+        """v [batch, num_objs, v_dim], q [batch, q_dim] → [batch, num_objs, 1] (f32)"""
+        parts, x = self.logit_parts(v, q)
+        att, _, _ = ops.attention_pool(parts, float(self.linear.bias.detach()), x, True, False, False)
+        return att.unsqueeze(2)
+
+
+class ConcatAttention(nn.Module):
+    """softmax_K( w2 · ReLU(W1 [v;q] + b1) + b2 )   (attention.py:18-51, att_type='base').
+
+    Parameters are kept under the reference's names; the kernel path needs an additive
+    row-broadcast epilogue operand (the q-half of W1) that vqa_linear does not have yet."""
+
+    def __init__(self, v_dim, q_dim, hidden_dim):
+        super().__init__()
+        self.sequence = nn.Sequential(wn_linear(v_dim + q_dim, hidden_dim), nn.ReLU(), wn_linear(hidden_dim, 1))
+
+    def logits(self, v, q):
+        raise NotImplementedError("att_type='base' (ConcatAttention) is not on the accelerated path yet; "
+                                  "use att_type='new' (the CLI default, main.py:67)")
+
+    def forward(self, v, q):
+        return self.logits(v, q)

@@ -1,0 +1,194 @@
+"""Building blocks — mirror of modules/modules.py (FCNet :13-60, DotProduct :80-95,
+SentenceEmbedding :98-163) on the C-ABI kernels.
+
+torch.nn containers are used ONLY to own parameters under the reference's names
+(``main.{i}.weight_g / weight_v / bias``, so old checkpoints load); their own
+forward is never called.
+"""
+import warnings
+
+import torch
+import torch.nn as nn
+
+from .. import compute_dtype, ops
+from ..engine import weight_norm_scale
+
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    from torch.nn.utils.weight_norm import weight_norm as _weight_norm
+
+
+def wn_linear(in_dim, out_dim):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return _weight_norm(nn.Linear(in_dim, out_dim), dim=None)
+
+
+def _key(*params):
+    return tuple((p._version, p.data_ptr(), p.device) for p in params)
+
+
+class PreparedCache:
+    """device copies of parameters in kernel layout, rebuilt when a parameter changes"""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, tag, params, build):
+        k = _key(*params)
+        hit = self._store.get(tag)
+        if hit is None or hit[0] != k:
+            hit = (k, build())
+            self._store[tag] = hit
+        return hit[1]
+
+
+def prep_wn_linear(cache, lin, dtype, tag="wn"):
+    """weight_norm(nn.Linear, dim=None) → (W [out,in] dtype, scale f32 [out], bias f32 [out])"""
+    def build():
+        dev = lin.weight_v.device
+        s = weight_norm_scale(lin.weight_v, lin.weight_g)
+        return (lin.weight_v.detach().to(dtype).contiguous(),
+                torch.full((lin.weight_v.shape[0],), s, dtype=torch.float32, device=dev),
+                lin.bias.detach().float().contiguous())
+    return cache.get((tag, dtype), (lin.weight_v, lin.weight_g, lin.bias), build)
+
+
+def as_compute(x, dtype):
+    """activation → the compute dtype with the library's cast kernels"""
+    x = x.contiguous()
+    if x.dtype == dtype:
+        return x
+    if x.dtype == torch.float32 and dtype == torch.bfloat16:
+        return ops.cast_to_bf16(x)
+    if x.dtype == torch.bfloat16 and dtype == torch.float32:
+        return ops.cast_to_f32(x)
+    return as_compute(x.float(), dtype)
+
+
+class FCNet(nn.Module):
+    """Non-linear fully-connected network (modules.py:13-60): weight-normed Linear + ReLU
+    stages, final ReLU always (modules.py:55)."""
+
+    def __init__(self, in_dim: int, out_dim: int, mid_dim: int = 0, layer: int = 1, dropout: float = 0):
+        super().__init__()
+        layers = []
+        if layer == 1 or mid_dim == 0:
+            layers.append(wn_linear(in_dim, out_dim))
+        else:
+            layers.append(wn_linear(in_dim, mid_dim))
+            layers.append(nn.ReLU())
+            layers.append(nn.Dropout(dropout, inplace=True))
+            for _ in range(layer - 2):
+                layers.append(wn_linear(mid_dim, mid_dim))
+                layers.append(nn.ReLU())
+                layers.append(nn.Dropout(dropout, inplace=True))
+            layers.append(wn_linear(mid_dim, out_dim))
+        layers.append(nn.ReLU())
+        self.main = nn.Sequential(*layers)
+        self._cache = PreparedCache()
+
+    def linears(self):
+        return [(i, m) for i, m in enumerate(self.main) if isinstance(m, nn.Linear)]
+
+    def prepared(self, dtype):
+        return [prep_wn_linear(self._cache, m, dtype, tag=("wn", i)) for i, m in self.linears()]
+
+    def forward(self, x, mul=None, out_dtype=None):
+        """x [..., in_dim] (CUDA).  ``mul`` (f32 [rows,out]) is an optional elementwise
+        multiplier fused into the LAST stage's epilogue (q ⊙ v of predictor.py:91)."""
+        _no_training(self)
+        dtype = compute_dtype()
+        lead = x.shape[:-1]
+        h = as_compute(x.reshape(-1, x.shape[-1]), dtype)
+        preps = self.prepared(dtype)
+        for j, (W, s, b) in enumerate(preps):
+            last = j == len(preps) - 1
+            h = ops.linear(h, W, s, b, relu=True, mul=mul if last else None,
+                           out_dtype=(out_dtype or dtype) if last else dtype)
+        return h.reshape(*lead, h.shape[-1])
+
+
+def _no_training(module):
+    if module.training and torch.is_grad_enabled():
+        raise NotImplementedError(
+            "vqa_collection_b200 builds the forward (eval / no_grad) path; the training step "
+            "(BASELINE config 4) is not built yet — call model.eval() and torch.no_grad()")
+
+
+class DotProduct(nn.Module):
+    """(Wa a + ba)(Wb b + bb)ᵀ (modules.py:80-95); parameters only — the contraction is
+    fused into vqa_graph_attention (see gcn.py)."""
+
+    def __init__(self, a_dim, b_dim, out_dim):
+        super().__init__()
+        self.wa = nn.Linear(a_dim, out_dim)
+        self.wb = nn.Linear(b_dim, out_dim)
+
+    def forward(self, a, b):
+        dtype = compute_dtype()
+        A = ops.linear(as_compute(a.reshape(-1, a.shape[-1]), dtype), self.wa.weight.detach().to(dtype).contiguous(),
+                       bias=self.wa.bias.detach().float().contiguous(), out_dtype=dtype)
+        Bm = ops.linear(as_compute(b.reshape(-1, b.shape[-1]), dtype), self.wb.weight.detach().to(dtype).contiguous(),
+                        bias=self.wb.bias.detach().float().contiguous(), out_dtype=dtype)
+        outs = []
+        for i in range(a.shape[0]):                       # per-image [a_len,out]x[out,b_len]
+            Ai = A[i * a.shape[1]:(i + 1) * a.shape[1]]
+            Bi = Bm[i * b.shape[1]:(i + 1) * b.shape[1]]
+            pad = (-Bi.shape[0]) % 8
+            outs.append(ops.linear(Ai, Bi, out_dtype=torch.float32))
+        return torch.stack(outs)
+
+
+class SentenceEmbedding(nn.Module):
+    """nn.GRU wrapper returning the last time step (modules.py:98-163).  Only the
+    configuration on the hot path is built: GRU, 1 layer, unidirectional."""
+
+    def __init__(self, in_dim: int, hidden_dim: int, device: str, rnn_layer: int = 1, dropout: float = 0.0,
+                 rnn_type: str = 'LSTM', bidirect: bool = False):
+        super().__init__()
+        assert rnn_type == 'LSTM' or rnn_type == 'GRU'
+        if rnn_type != 'GRU' or rnn_layer != 1 or bidirect:
+            raise NotImplementedError("vqa_collection_b200: only rnn_type='GRU', rnn_layer=1, unidirectional "
+                                      "is on the accelerated path (main.py:75-76 defaults)")
+        self.rnn = nn.GRU(input_size=in_dim, hidden_size=hidden_dim, num_layers=1, dropout=dropout,
+                          bidirectional=False, batch_first=True)
+        self.in_dim, self.hidden_dim, self.rnn_layer = in_dim, hidden_dim, rnn_layer
+        self.rnn_type, self.ndirections, self.device = rnn_type, 1, device
+        self._cache = PreparedCache()
+
+    def prepared(self, dtype):
+        r = self.rnn
+
+        def build():
+            E = r.weight_ih_l0.shape[1]
+            E_pad = (E + 63) // 64 * 64
+            w_ih = torch.zeros((r.weight_ih_l0.shape[0], E_pad), dtype=dtype, device=r.weight_ih_l0.device)
+            w_ih[:, :E] = r.weight_ih_l0.detach().to(dtype)
+            return (w_ih, r.bias_ih_l0.detach().float().contiguous(),
+                    r.weight_hh_l0.detach().to(dtype).contiguous(), r.bias_hh_l0.detach().float().contiguous(), E_pad)
+        return self._cache.get(("gru", dtype), (r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0), build)
+
+    def forward_tokens(self, tokens, embedding_weight):
+        """fused embedding gather + GRU (encoder.py:159-160) → f32 [B,H]"""
+        dtype = compute_dtype()
+        w_ih, b_ih, w_hh, b_hh, E_pad = self.prepared(dtype)
+        emb = self._cache.get(("emb", dtype), (embedding_weight,), lambda: _pad_emb(embedding_weight, E_pad, dtype))
+        return ops.gru_last_state(tokens.contiguous(), emb, w_ih, b_ih, w_hh, b_hh)
+
+    def forward(self, batch):
+        """batch: already-embedded [B,T,in_dim] (modules.py:155-159) → last step [B,H] f32"""
+        _no_training(self)
+        dtype = compute_dtype()
+        w_ih, b_ih, w_hh, b_hh, E_pad = self.prepared(dtype)
+        B, T, E = batch.shape
+        table = torch.zeros((B * T, E_pad), dtype=dtype, device=batch.device)
+        table[:, :E] = batch.reshape(B * T, E).to(dtype)
+        tokens = torch.arange(B * T, device=batch.device, dtype=torch.int64).view(B, T)
+        return ops.gru_last_state(tokens, table, w_ih, b_ih, w_hh, b_hh)
+
+
+def _pad_emb(weight, E_pad, dtype):
+    out = torch.zeros((weight.shape[0], E_pad), dtype=dtype, device=weight.device)
+    out[:, : weight.shape[1]] = weight.detach().to(dtype)
+    return out

@@ -1,0 +1,155 @@
+"""Model composition — mirror of modules/wrapper.py (Wrapper :39-123, set_model :125-191,
+compute_score :8-22, losses :25-36) for the VQA forward path.
+
+``Wrapper.forward`` / ``get_att`` compose the module-level kernels; ``forward_vqa`` (the
+call train.evaluate makes per batch, train.py:184) takes the fused single-C-call engine
+path.  The caption generator (generator.py) is out of scope: decoder_type must be 'none'.
+"""
+import torch
+import torch.nn as nn
+
+from .. import get_precision, ops
+from .encoder import set_encoder, RelationEncoder
+from .predictor import set_predictor, BasePredictor
+
+
+def compute_score(predict, target, device, get_label=False):
+    """VQA soft score of the lowest-index argmax answer (wrapper.py:8-22)."""
+    predict = predict.to(device)
+    target = target.to(device)
+    if predict.is_cuda:
+        logits = ops.argmax_rows(predict.float().contiguous())          # torch.max(predict, 1)[1] tie rule
+    else:
+        logits = torch.max(predict, 1)[1].data
+    one_hots = torch.zeros(*target.size()).to(device)
+    one_hots.scatter_(1, logits.view(-1, 1), 1)
+    scores = one_hots * target
+    if get_label:
+        return scores, logits
+    return scores
+
+
+def instance_bce_with_logits(predict, target):
+    """Loss function for VQA prediction (wrapper.py:25-29)"""
+    loss = nn.functional.binary_cross_entropy_with_logits(predict, target)
+    loss *= target.size(1)
+    return loss
+
+
+def ce_for_language_model(predict, target):
+    """Loss function for caption generation (wrapper.py:32-36)"""
+    assert predict.dim() == 2
+    return nn.functional.cross_entropy(predict, target)
+
+
+class Wrapper(nn.Module):
+    def __init__(self, encoder=None, predictor=None, generator=None, use_mtl=True):
+        super().__init__()
+        self.encoder = encoder
+        self.predictor = predictor
+        self.generator = generator
+        self.device = encoder.device
+        if self.predictor is None or self.generator is None:
+            use_mtl = False
+        if use_mtl:
+            self.log_vars = nn.Parameter(torch.zeros(2))
+        self.use_mtl = use_mtl
+        self.gradients = []
+        name = ''
+        for name, module in self.encoder.named_modules():
+            pass
+        self.encoder_last_layer = name
+        self._engine = None
+        self._engine_key = None
+
+    def save_grad(self, grad):
+        self.gradients.append(grad)
+
+    # -- fused engine over the CURRENT parameters ---------------------------------------
+    def reference_named_weights(self):
+        """state_dict + the unregistered GCN tensors as gcn.{i}.* """
+        W = {k: v for k, v in self.state_dict().items()}
+        if isinstance(self.encoder, RelationEncoder):
+            for i, layer in enumerate(self.encoder.spatial_encoder.gcn):
+                for k, v in layer.state_dict().items():
+                    W[f"gcn.{i}.{k}"] = v
+        return W
+
+    def engine(self):
+        from ..engine import VQAEngine
+        params = list(self.parameters())
+        if isinstance(self.encoder, RelationEncoder):
+            for layer in self.encoder.spatial_encoder.gcn:
+                params += list(layer.parameters())
+        key = (get_precision(),) + tuple((p._version, p.data_ptr()) for p in params)
+        if self._engine is None or self._engine_key != key:
+            relation = isinstance(self.encoder, RelationEncoder)
+            if relation and len(self.encoder.spatial_encoder.gcn) != 1:
+                return None                                  # multi-layer GCN: module-level path
+            self._engine = VQAEngine(self.reference_named_weights(), relation=relation,
+                                     precision=get_precision(), device=self.device)
+            self._engine_key = key
+        return self._engine
+
+    # -- reference API --------------------------------------------------------------------
+    def forward(self, batch):
+        self.gradients = []
+        batch = self.encoder(batch)
+        caption = self.generator(batch) if self.generator else None
+        predict = self.predictor(batch) if self.predictor else None
+        return predict, caption
+
+    def get_loss(self, batch):
+        raise NotImplementedError("vqa_collection_b200: the training step (BASELINE config 4: backward kernels + NCCL "
+                                  "gradient all-reduce) is not built yet; this round covers the forward path")
+
+    def get_att(self, batch):
+        batch = self.encoder(batch)
+        predict = self.predictor(batch)
+        return predict, batch['v_att']
+
+    def forward_vqa(self, batch):
+        target = batch['a'].float().to(self.device)
+        eng = self.engine() if isinstance(self.predictor, BasePredictor) else None
+        if eng is None or self.training:
+            enc = self.encoder(batch)
+            predict = self.predictor(enc)
+            score, label = compute_score(predict, target, self.device, True)
+            return score, label, target
+        img = batch['img'].to(self.device)
+        tokens = batch['q'].to(self.device)
+        kw = {}
+        if eng.relation:
+            if 'graph' in batch:
+                kw['labels'] = self.encoder.graph_labels(batch)
+            else:
+                kw['bbox'], kw['wh'] = batch['bbox'].to(self.device).float(), batch['wh']
+        out = eng.forward(img, tokens, **kw)
+        label = out['label']
+        one_hots = torch.zeros_like(target)
+        one_hots.scatter_(1, label.view(-1, 1), 1)
+        return one_hots * target, label, target
+
+    def forward_cap(self, batch):
+        batch = self.encoder(batch)
+        return self.generator(batch) if self.generator else None
+
+
+def set_model(encoder_type: str = 'base', predictor_type: str = 'base', decoder_type: str = 'base',
+              ntoken: int = 0, v_dim: int = 0, embed_dim: int = 0, hidden_dim: int = 0,
+              decoder_hidden_dim: int = 0, rnn_layer: int = 0, ans_dim: int = 0, cls_layer: int = 0,
+              c_len: int = 0, device: str = '', dropout: float = 0.5, neg_slope: float = 0.5,
+              rnn_type: str = 'GRU', att_type: str = 'base', conv_layer: int = 2, conv_type: str = 'corr',
+              decoder_device: str = '', pretrained_embed_path: str = '', use_mtl: bool = False):
+    if decoder_type != 'none':
+        raise NotImplementedError("caption decoders (generator.py) are outside the accelerated VQA forward path; "
+                                  "pass decoder_type='none'")
+    return Wrapper(
+        encoder=set_encoder(encoder_type=encoder_type, ntoken=ntoken, v_dim=v_dim, embed_dim=embed_dim,
+                            hidden_dim=hidden_dim, device=device, dropout=dropout, rnn_type=rnn_type,
+                            rnn_layer=rnn_layer, att_type=att_type, conv_type=conv_type, conv_layer=conv_layer,
+                            vocab_path=pretrained_embed_path),
+        predictor=set_predictor(predictor_type=predictor_type, v_dim=v_dim, embed_dim=embed_dim,
+                                hidden_dim=hidden_dim, ans_dim=ans_dim, device=device, cls_layer=cls_layer,
+                                dropout=dropout, c_len=c_len, neg_slope=neg_slope),
+        generator=None, use_mtl=use_mtl)
