@@ -122,6 +122,12 @@ typedef struct {
   const void* d_emb;
   const void* d_w_ih;  const float* d_b_ih;
   const void* d_w_hh;  const float* d_b_hh;
+  /* optional gate-interleaved copies (bf16, H % 64 == 0) that select the persistent fused
+   * tcgen05 kernel (one launch for all T steps); NULL = generic per-step path.
+   *   d_wx_packed [3H,E_pad], d_wh_packed [3H,H]: 192-row block j = rows of units
+   *   [64j,64j+64) in gate order [r(64) | z(64) | n(64)];
+   *   d_bias_packed f32 [4H] = b_ir+b_hr | b_iz+b_hz | b_in | b_hn            */
+  const void* d_wx_packed; const void* d_wh_packed; const float* d_bias_packed;
   void* d_workspace;   size_t workspace_bytes;
   float* d_h_last;     void* d_h_last_lp;
 } vqa_gru_args;
@@ -200,6 +206,7 @@ typedef struct {
   /* question encoder */
   const void* d_emb; const void* d_w_ih; const float* d_b_ih;
   const void* d_w_hh; const float* d_b_hh;
+  const void* d_wx_packed; const void* d_wh_packed; const float* d_bias_packed;  /* see vqa_gru_args */
   /* attention (attention.py:61-66) */
   const void* d_Wv;  const float* d_sv;  const float* d_bv;      /* [H,V]    */
   const void* d_Wqq; const float* d_sqq; const float* d_bqq;     /* [2H,H]: W_q ; q_net */

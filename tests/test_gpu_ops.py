@@ -196,6 +196,32 @@ def test_gru_last_state(ops, dtype, cfg, B):
     with torch.no_grad():
         want = O.question_embedding(batch["q"], W)
     assert relerr(h, want) < TOL[dtype]
+    if dtype == torch.bfloat16:
+        # persistent fused kernel (gate-interleaved weights): one launch for all T steps
+        packed = (P["wx_packed"], P["wh_packed"], P["bias_packed"])
+        h2, h2_lp = ops.gru_last_state(batch["q"].cuda(), P["emb"], P["w_ih"], P["b_ih"], P["w_hh"], P["b_hh"],
+                                       want_lp=True, packed=packed)
+        assert relerr(h2, want) < TOL[dtype]
+        assert relerr(h2_lp, want) < TOL[dtype]
+        h3 = ops.gru_last_state(batch["q"].cuda(), P["emb"], P["w_ih"], P["b_ih"], P["w_hh"], P["b_hh"], packed=packed)
+        assert torch.equal(h2, h3)                              # deterministic
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (130, 3), (1024, 14), (1300, 14)])
+def test_gru_persistent_shapes(ops, B, T):
+    """ragged batch, single step, and a batch larger than one co-resident grid (chunked)"""
+    from vqa_collection_b200.engine import prepare_weights
+    cfg = O.FULL
+    W = O.make_weights(cfg, 1111)
+    P = prepare_weights(W, torch.bfloat16, "cuda", False)
+    g = torch.Generator().manual_seed(B + T)
+    q = torch.randint(0, cfg.ntoken + 1, (B, T), generator=g)           # includes the padding row
+    packed = (P["wx_packed"], P["wh_packed"], P["bias_packed"])
+    h = ops.gru_last_state(q.cuda(), P["emb"], P["w_ih"], P["b_ih"], P["w_hh"], P["b_hh"], packed=packed)
+    idx = torch.arange(0, B, max(1, B // 64))
+    with torch.no_grad():
+        want = O.question_embedding(q[idx], W)
+    assert relerr(h[idx.cuda()], want) < 1e-2
 
 
 # ---------------------------------------------------------------------------- attention pooling

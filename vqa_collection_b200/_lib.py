@@ -38,6 +38,7 @@ class GruArgs(C.Structure):
         ("d_emb", c_void_p),
         ("d_w_ih", c_void_p), ("d_b_ih", c_void_p),
         ("d_w_hh", c_void_p), ("d_b_hh", c_void_p),
+        ("d_wx_packed", c_void_p), ("d_wh_packed", c_void_p), ("d_bias_packed", c_void_p),
         ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("d_h_last", c_void_p), ("d_h_last_lp", c_void_p),
     ]
@@ -64,6 +65,7 @@ class ForwardArgs(C.Structure):
         ("img_w", c_float), ("img_h", c_float),
         ("d_emb", c_void_p), ("d_w_ih", c_void_p), ("d_b_ih", c_void_p),
         ("d_w_hh", c_void_p), ("d_b_hh", c_void_p),
+        ("d_wx_packed", c_void_p), ("d_wh_packed", c_void_p), ("d_bias_packed", c_void_p),
         ("d_Wv", c_void_p), ("d_sv", c_void_p), ("d_bv", c_void_p),
         ("d_Wqq", c_void_p), ("d_sqq", c_void_p), ("d_bqq", c_void_p),
         ("d_wlin", c_void_p), ("b_lin", c_float),

@@ -57,6 +57,8 @@ int gru_gate(const float*, const float*, int, int, int, int, const float*, float
 int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
 int cast_bf16_to_f32(const void*, float*, size_t, cudaStream_t);
 int graph_attention(const vqa_graph_attention_args&, cudaStream_t);
+int gru_persistent(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
+                   cudaStream_t);
 
 static bool force_simt() {
   static int v = -1;
@@ -79,17 +81,19 @@ static int part_width(int dtype) {
 }
 
 // ---- GRU --------------------------------------------------------------------
-struct GruWs { void* X; float* gi; float* gh; float* h; void* h_lp; size_t bytes; };
+struct GruWs { void* X; float* gi; float* gh; float* h; void* h_lp; void* h_op; int* counter; size_t bytes; };
 static GruWs carve_gru(void* base, int B, int T, int H, int E_pad, int dtype) {
   GruWs w;
   size_t off = 0;
   char* p = (char*)base;
   auto take = [&](size_t n) { void* r = p ? p + off : nullptr; off += align_up(n, 256); return r; };
   w.X = take((size_t)B * T * E_pad * elem_size(dtype));
-  w.gi = (float*)take((size_t)B * T * 3 * H * 4);
+  w.gi = (float*)take((size_t)B * T * 3 * H * 4);          // generic per-step path only
   w.gh = (float*)take((size_t)B * 3 * H * 4);
   w.h = (float*)take((size_t)B * H * 4);
   w.h_lp = take((size_t)B * H * elem_size(dtype));
+  w.h_op = take((size_t)2 * B * H * 2);                    // persistent kernel: bf16 state x 2
+  w.counter = (int*)take(256);
   w.bytes = off;
   return w;
 }
@@ -105,6 +109,9 @@ static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
   const GruWs w = carve_gru(a.d_workspace, a.B, a.T, a.H, a.E_pad, a.dtype);
   int rc;
   if ((rc = embedding_gather(a.d_tokens, a.B * a.T, a.E_pad, a.ntoken_rows, a.dtype, a.d_emb, w.X, s))) return rc;
+  if (a.dtype == VQA_BF16 && a.d_wx_packed && a.d_wh_packed && a.d_bias_packed && !force_simt() && a.H % 64 == 0)
+    return gru_persistent(w.X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
+                          a.d_h_last, a.d_h_last_lp, s);
   // gi = X W_ihᵀ + b_ih for all T steps at once: [B*T, 3H] f32
   vqa_linear_args gi{};
   gi.d_A = w.X; gi.lda = a.E_pad; gi.d_W = a.d_w_ih; gi.ldw = a.E_pad;
@@ -288,7 +295,8 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
   vqa_gru_args g{};
   g.d_tokens = a.d_tokens; g.B = a.B; g.T = a.T; g.H = a.H; g.E_pad = a.E_pad; g.ntoken_rows = a.ntoken_rows;
   g.dtype = a.dtype; g.d_emb = a.d_emb; g.d_w_ih = a.d_w_ih; g.d_b_ih = a.d_b_ih; g.d_w_hh = a.d_w_hh;
-  g.d_b_hh = a.d_b_hh; g.d_workspace = w.gru; g.workspace_bytes = w.gru_bytes; g.d_h_last = w.h; g.d_h_last_lp = w.h_lp;
+  g.d_b_hh = a.d_b_hh; g.d_wx_packed = a.d_wx_packed; g.d_wh_packed = a.d_wh_packed; g.d_bias_packed = a.d_bias_packed;
+  g.d_workspace = w.gru; g.workspace_bytes = w.gru_bytes; g.d_h_last = w.h; g.d_h_last_lp = w.h_lp;
   if ((rc = gru_last_state(g, s))) return rc;
   // 2. [W_q ; q_net] (attention.py:71, encoder.py:169): qq = ReLU(h Wqqᵀ s + b) f32 [B,2H]
   vqa_linear_args l{};

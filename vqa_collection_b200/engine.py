@@ -36,6 +36,21 @@ def _pad_cols(t: torch.Tensor, cols: int) -> torch.Tensor:
     return out
 
 
+def pack_gru(w_ih, w_hh, b_ih, b_hh, units: int = 64):
+    """Gate-interleaved GRU weights for the persistent fused kernel (vqa_gru_args):
+    192-row block j = [r | z | n] rows of hidden units [64j, 64j+64); biases
+    [b_ir+b_hr | b_iz+b_hz | b_in | b_hn].  Inputs in torch layout [3H, ·] / [3H]."""
+    H = w_hh.shape[1]
+    if H % units:
+        return None
+    j = torch.arange(H // units).view(-1, 1, 1)
+    gate = torch.arange(3).view(1, -1, 1)
+    u = torch.arange(units).view(1, 1, -1)
+    perm = (gate * H + j * units + u).reshape(-1).to(w_ih.device)
+    bias = torch.cat([b_ih[:H] + b_hh[:H], b_ih[H:2 * H] + b_hh[H:2 * H], b_ih[2 * H:], b_hh[2 * H:]])
+    return w_ih[perm].contiguous(), w_hh[perm].contiguous(), bias.float().contiguous()
+
+
 def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_layer: int = 0) -> dict:
     """Reference-named tensors → device tensors in kernel layout."""
     f32 = lambda t: t.detach().to("cpu", torch.float32)
@@ -52,6 +67,10 @@ def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_lay
     P["b_ih"] = dev(f32(W[r + "bias_ih_l0"]))
     P["b_hh"] = dev(f32(W[r + "bias_hh_l0"]))
     H = P["w_hh"].shape[1]
+    if dtype == torch.bfloat16:
+        packed = pack_gru(P["w_ih"], P["w_hh"], P["b_ih"], P["b_hh"])
+        if packed is not None:
+            P["wx_packed"], P["wh_packed"], P["bias_packed"] = packed
 
     def wn(prefix):
         v, g, b = f32(W[prefix + ".weight_v"]), f32(W[prefix + ".weight_g"]), f32(W[prefix + ".bias"])
@@ -120,6 +139,9 @@ class VQAEngine:
                      "Wvn", "svn", "bvn", "Wc0", "sc0", "bc0", "Wc1", "sc1", "bc1"):
             setattr(a, "d_" + name, P[name].data_ptr())
         a.b_lin = P["b_lin"]
+        if "wx_packed" in P:
+            a.d_wx_packed, a.d_wh_packed, a.d_bias_packed = (P["wx_packed"].data_ptr(), P["wh_packed"].data_ptr(),
+                                                             P["bias_packed"].data_ptr())
         if self.relation:
             for name in ("Wg", "label_bias", "ba", "bb"):
                 setattr(a, "d_" + name, P[name].data_ptr())

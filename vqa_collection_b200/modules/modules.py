@@ -11,7 +11,7 @@ import torch
 import torch.nn as nn
 
 from .. import compute_dtype, ops
-from ..engine import weight_norm_scale
+from ..engine import weight_norm_scale, pack_gru
 
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
@@ -165,27 +165,29 @@ class SentenceEmbedding(nn.Module):
             E_pad = (E + 63) // 64 * 64
             w_ih = torch.zeros((r.weight_ih_l0.shape[0], E_pad), dtype=dtype, device=r.weight_ih_l0.device)
             w_ih[:, :E] = r.weight_ih_l0.detach().to(dtype)
-            return (w_ih, r.bias_ih_l0.detach().float().contiguous(),
-                    r.weight_hh_l0.detach().to(dtype).contiguous(), r.bias_hh_l0.detach().float().contiguous(), E_pad)
+            b_ih, b_hh = r.bias_ih_l0.detach().float().contiguous(), r.bias_hh_l0.detach().float().contiguous()
+            w_hh = r.weight_hh_l0.detach().to(dtype).contiguous()
+            packed = pack_gru(w_ih, w_hh, b_ih, b_hh) if dtype == torch.bfloat16 else None
+            return (w_ih, b_ih, w_hh, b_hh, E_pad, packed)
         return self._cache.get(("gru", dtype), (r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0), build)
 
     def forward_tokens(self, tokens, embedding_weight):
         """fused embedding gather + GRU (encoder.py:159-160) → f32 [B,H]"""
         dtype = compute_dtype()
-        w_ih, b_ih, w_hh, b_hh, E_pad = self.prepared(dtype)
+        w_ih, b_ih, w_hh, b_hh, E_pad, packed = self.prepared(dtype)
         emb = self._cache.get(("emb", dtype), (embedding_weight,), lambda: _pad_emb(embedding_weight, E_pad, dtype))
-        return ops.gru_last_state(tokens.contiguous(), emb, w_ih, b_ih, w_hh, b_hh)
+        return ops.gru_last_state(tokens.contiguous(), emb, w_ih, b_ih, w_hh, b_hh, packed=packed)
 
     def forward(self, batch):
         """batch: already-embedded [B,T,in_dim] (modules.py:155-159) → last step [B,H] f32"""
         _no_training(self)
         dtype = compute_dtype()
-        w_ih, b_ih, w_hh, b_hh, E_pad = self.prepared(dtype)
+        w_ih, b_ih, w_hh, b_hh, E_pad, packed = self.prepared(dtype)
         B, T, E = batch.shape
         table = torch.zeros((B * T, E_pad), dtype=dtype, device=batch.device)
         table[:, :E] = batch.reshape(B * T, E).to(dtype)
         tokens = torch.arange(B * T, device=batch.device, dtype=torch.int64).view(B, T)
-        return ops.gru_last_state(tokens, table, w_ih, b_ih, w_hh, b_hh)
+        return ops.gru_last_state(tokens, table, w_ih, b_ih, w_hh, b_hh, packed=packed)
 
 
 def _pad_emb(weight, E_pad, dtype):

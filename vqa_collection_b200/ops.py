@@ -147,7 +147,7 @@ def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, log
     return out
 
 
-def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False):
+def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False, packed=None):
     """Embedding gather + GRU last state (encoder.py:159-160, modules.py:139-159).
 
     tokens int64 [B,T]; emb [rows,E_pad]; w_ih [3H,E_pad]; w_hh [3H,H] (all one dtype);
@@ -174,6 +174,9 @@ def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False):
     a.d_tokens, a.B, a.T, a.H, a.E_pad, a.ntoken_rows, a.dtype = tokens.data_ptr(), B, T, H, E_pad, emb.shape[0], code
     a.d_emb, a.d_w_ih, a.d_b_ih, a.d_w_hh, a.d_b_hh = (emb.data_ptr(), w_ih.data_ptr(), b_ih.data_ptr(),
                                                        w_hh.data_ptr(), b_hh.data_ptr())
+    if packed is not None:                 # (wx_packed, wh_packed, bias_packed) from engine.pack_gru
+        a.d_wx_packed, a.d_wh_packed, a.d_bias_packed = (packed[0].data_ptr(), packed[1].data_ptr(),
+                                                         packed[2].data_ptr())
     a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
     a.d_h_last, a.d_h_last_lp = h.data_ptr(), (h_lp.data_ptr() if want_lp else None)
     L.check(lib.vqa_gru_last_state(C.byref(a), _stream()))
