@@ -8,19 +8,22 @@ namespace vqa {
 // ---------------------------------------------------------------------------
 // k6: att = softmax_K(sum_p parts + b); vsum = sum_k att_k x_k; vatt = att_k x_k
 // Reference: attention.py:86, encoder.py:166, predictor.py:85.
-// One CTA per image; thread t owns channels [8t, 8t+8) (+ stride) and streams
-// the K rows of x once (K x 16-byte loads in flight per thread).
 // ---------------------------------------------------------------------------
-constexpr int kPoolThreads = 256;
+constexpr int kPoolThreads = 64;           // 2 warps; one CTA = (image, 512-channel slice)
+constexpr int kPoolChan = kPoolThreads * 8;
 constexpr int kPoolMaxK = 64;
 
+// Work item = (image, 512-channel slice): B·V/512 small CTAs (4096 at B=1024) so that the
+// whole grid is resident in one wave (no wave tail) and every SM keeps ~1600 threads with
+// four 16-byte loads each in flight.  Every CTA recomputes the 36-way softmax (L2 hits).
 template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
 attention_pool_kernel(const float* __restrict__ parts, int n_parts, float bias,
-                      const T* __restrict__ x, int B, int K, int V,
+                      const T* __restrict__ x, int B, int K, int V, int slices,
                       float* __restrict__ att_out, T* __restrict__ vsum, T* __restrict__ vatt) {
   __shared__ float s_att[kPoolMaxK];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / slices;
+  const int slice = blockIdx.x - b * slices;
   const int tid = threadIdx.x;
   if (tid < 32) {
     // K <= 64: lane handles k = lane and k = lane + 32
@@ -28,13 +31,13 @@ attention_pool_kernel(const float* __restrict__ parts, int n_parts, float bias,
     if (tid < K) {
       const float* p = parts + (size_t)(b * K + tid) * n_parts;
       float s = 0.f;
-      for (int i = 0; i < n_parts; ++i) s += p[i];
+      for (int i = 0; i < n_parts; ++i) s += __ldg(p + i);
       l0 = s + bias;
     }
     if (tid + 32 < K) {
       const float* p = parts + (size_t)(b * K + tid + 32) * n_parts;
       float s = 0.f;
-      for (int i = 0; i < n_parts; ++i) s += p[i];
+      for (int i = 0; i < n_parts; ++i) s += __ldg(p + i);
       l1 = s + bias;
     }
     const float m = warp_max(fmaxf(l0, l1));
@@ -45,33 +48,33 @@ attention_pool_kernel(const float* __restrict__ parts, int n_parts, float bias,
     if (tid + 32 < K) s_att[tid + 32] = e1 * inv;
   }
   __syncthreads();
-  if (att_out != nullptr && tid < K) att_out[(size_t)b * K + tid] = s_att[tid];
+  if (att_out != nullptr && slice == 0 && tid < K) att_out[(size_t)b * K + tid] = s_att[tid];
   if (vsum == nullptr && vatt == nullptr) return;
 
-  const T* xb = x + (size_t)b * K * V;
-  for (int c = tid * 8; c < V; c += kPoolThreads * 8) {
-    float acc[8];
+  const int c = slice * kPoolChan + tid * 8;
+  if (c >= V) return;
+  const T* xb = x + (size_t)b * K * V + c;
+  float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-      float v[8];
-      load8(xb + (size_t)k * V + c, v);
-      const float a = s_att[k];
-      if (vatt != nullptr) {
-        float w[8];
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 6
+  for (int k = 0; k < K; ++k) {
+    float v[8];
+    load8(xb + (size_t)k * V, v);
+    const float a = s_att[k];
+    if (vatt != nullptr) {
+      float w[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = a * v[i];
-        store8(vatt + ((size_t)b * K + k) * V + c, w);
+      for (int i = 0; i < 8; ++i) w[i] = a * v[i];
+      store8(vatt + ((size_t)b * K + k) * V + c, w);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += w[i];
-      } else {
+      for (int i = 0; i < 8; ++i) acc[i] += w[i];
+    } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, v[i], acc[i]);
-      }
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, v[i], acc[i]);
     }
-    if (vsum != nullptr) store8(vsum + (size_t)b * V + c, acc);
   }
+  if (vsum != nullptr) store8(vsum + (size_t)b * V + c, acc);
 }
 
 int attention_pool(const float* parts, int n_parts, float bias, const void* x, int B, int K, int V,
@@ -80,13 +83,16 @@ int attention_pool(const float* parts, int n_parts, float bias, const void* x, i
   VQA_REQUIRE(V % 8 == 0 && n_parts >= 1, "attention_pool: V=%d must be a multiple of 8", V);
   if (B == 0) return VQA_OK;
   VQA_REQUIRE(parts && x, "attention_pool: NULL input");
+  const bool stream_x = vsum != nullptr || vatt != nullptr;
+  const int slices = stream_x ? (V + kPoolChan - 1) / kPoolChan : 1;
+  const unsigned grid = (unsigned)B * slices;
   if (dtype == VQA_BF16) {
-    attention_pool_kernel<__nv_bfloat16><<<B, kPoolThreads, 0, s>>>(
-        parts, n_parts, bias, (const __nv_bfloat16*)x, B, K, V, att, (__nv_bfloat16*)vsum,
+    attention_pool_kernel<__nv_bfloat16><<<grid, kPoolThreads, 0, s>>>(
+        parts, n_parts, bias, (const __nv_bfloat16*)x, B, K, V, slices, att, (__nv_bfloat16*)vsum,
         (__nv_bfloat16*)vatt);
   } else {
-    attention_pool_kernel<float><<<B, kPoolThreads, 0, s>>>(parts, n_parts, bias, (const float*)x, B,
-                                                           K, V, att, (float*)vsum, (float*)vatt);
+    attention_pool_kernel<float><<<grid, kPoolThreads, 0, s>>>(parts, n_parts, bias, (const float*)x, B,
+                                                               K, V, slices, att, (float*)vsum, (float*)vatt);
   }
   VQA_LAUNCH_CHECK();
   return VQA_OK;
