@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 1
+#define VQA_B200_ABI_VERSION 2
 
 typedef enum {
   VQA_OK = 0,
@@ -153,15 +153,24 @@ int vqa_attention_pool(const float* d_logit_parts, int n_parts, float logit_bias
 
 /* ------------------------------------------------------------------------
  * k9+k10  relation-masked graph attention (one CorrelatedGraphConv layer + the
- * GCN's ReLU), after the wide projection Y = x * [W0+W1 ; W2 ; Wa ; Wb]^T.
+ * GCN's ReLU), after the wide projection of the RAW region features x.
  * replaces gcn.py:93-107 (conv, label bias), gcn.py:119-128 (relation_alpha),
  * gcn.py:152-168 (forward), gcn.py:211-212 (dropout=identity, ReLU) and
  * predictor.py:85 (the K-sum) when vsum is requested.
+ *
+ * layout 0 (f32 FFMA kernel, also bf16):  Y = x * [W0+W1 ; W2 ; Wa ; Wb]^T
  *   Y [B*K, ldy] (dtype): columns [0,V) P=(W0+W1)x, [V,2V) S=W2 x,
- *                         [2V,3V) Wa x, [3V,4V) Wb x   (x = RAW features)
+ *                         [2V,3V) Wa x, [3V,4V) Wb x ; ba, bb f32 [V]
+ * layout 1 (bf16 only, tcgen05 kernel):   Y = x * [W0+W1 ; W2 ; Wb^T Wa]^T
+ *   Y [B*K, ldy] bf16: [0,V) P, [V,2V) S, [2V,3V) Q with Q_i . x_j = (Wa x_i).(Wb x_j)
+ *   x [B*K, ldx] bf16 (the raw features again: second operand of Q x^T)
+ *   wvec bf16 [16,V]: row 0 = Wa^T bb, row 1 = Wb^T ba, rows 2..15 zero
+ *   c0 = ba . bb ; label_bias_lp bf16 [16,V] (rows >= num_labels zero)
+ *   K == 36, V % 128 == 0.
+ * common:
  *   att f32 [B,K]: the top-down attention (feature f_i = att_i * x_i; row
  *                  scaling commutes with the bias-free maps), NULL = all ones
- *   labels u8 [B,K,K]; label_bias f32 [L,V]; ba, bb f32 [V]
+ *   labels u8 [B,K,K]; label_bias f32 [L,V] (layout 0)
  *   outputs (optional): out [B,K,V] (dtype) = ReLU(alpha . conv);
  *                       vsum [B,V] (dtype) = sum_i out_i; alpha f32 [B,K,K]
  * ---------------------------------------------------------------------- */
@@ -173,6 +182,12 @@ typedef struct {
   const float* d_ba; const float* d_bb;
   int B, K, V, dtype;
   void* d_out; void* d_vsum; float* d_alpha;
+  /* layout 1 (merged algebra) */
+  int layout;
+  const void* d_x; int ldx;
+  const void* d_wvec;
+  float c0;
+  const void* d_label_bias_lp;
 } vqa_graph_attention_args;
 
 int vqa_graph_attention(const vqa_graph_attention_args* args, void* stream);
@@ -214,6 +229,9 @@ typedef struct {
   float b_lin;
   /* ReGAT layer (gcn.py), concatenated [4V,V] = [W0+W1; W2; Wa; Wb] */
   const void* d_Wg; const float* d_label_bias; const float* d_ba; const float* d_bb;
+  /* bf16 merged form (vqa_graph_attention layout 1): [3V,V] = [W0+W1; W2; Wb^T Wa]; when
+   * d_Wg3 is non-NULL (bf16 only) it replaces d_Wg/d_ba/d_bb/d_label_bias */
+  const void* d_Wg3; const void* d_wvec; float gat_c0; const void* d_label_bias_lp;
   /* predictor (predictor.py:58-79) */
   const void* d_Wvn; const float* d_svn; const float* d_bvn;     /* [H,V]    */
   const void* d_Wc0; const float* d_sc0; const float* d_bc0;     /* [2H,H]   */

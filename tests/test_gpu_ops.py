@@ -255,9 +255,11 @@ def test_argmax_lowest_index_on_ties(ops):
 
 
 # ---------------------------------------------------------------------------- graph attention
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("cfg,B", [(O.SMALL_REGAT, 6), (O.FULL_REGAT, 3)])
-def test_graph_attention_layer(ops, dtype, cfg, B):
+@pytest.mark.parametrize("dtype,merged", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)])
+@pytest.mark.parametrize("cfg,B", [(O.SMALL_REGAT, 6), (O.FULL_REGAT, 3), (O.SMALL_REGAT, 301)])
+def test_graph_attention_layer(ops, dtype, merged, cfg, B):
+    """layout 0 = FFMA kernel on [P|S|A'|B'] (fp32 parity path), layout 1 = tcgen05 kernel on the merged
+    [P|S|Q] projection (bf16 product path); B=301 makes every persistent CTA loop over >1 image."""
     from vqa_collection_b200.engine import prepare_gcn_layer
     W = O.make_weights(cfg, 1111)
     batch = O.make_batch(cfg, B, 9)
@@ -268,19 +270,29 @@ def test_graph_attention_layer(ops, dtype, cfg, B):
     with torch.no_grad():
         want, alpha = O.corr_graph_conv(feature, batch["graph"].float(), W, "gcn.0.")
         want = torch.relu(want)
-    Pl = prepare_gcn_layer({k[6:]: v for k, v in W.items() if k.startswith("gcn.0.")}, dtype, "cuda")
+    Pl = prepare_gcn_layer({k[6:]: v for k, v in W.items() if k.startswith("gcn.0.")}, dtype, "cuda", merged=merged)
     xd = x.to(dtype).cuda().view(B * cfg.num_objs, cfg.v_dim)
-    Y = ops.linear(xd, Pl["Wg"])
     labels = batch["graph"].to(torch.uint8).cuda()
-    out, vsum, al = ops.graph_attention(Y, att.cuda(), labels, Pl["label_bias"], Pl["ba"], Pl["bb"],
-                                        cfg.num_objs, True, True, True)
+
+    def run(att_d, *want_flags):
+        if merged:
+            Y = ops.linear(xd, Pl["Wg3"])
+            return ops.graph_attention_merged(Y, xd, att_d, labels, Pl["wvec"], Pl["gat_c0"], Pl["label_bias_lp"],
+                                              Pl["num_labels"], cfg.num_objs, *want_flags)
+        Y = ops.linear(xd, Pl["Wg"])
+        return ops.graph_attention(Y, att_d, labels, Pl["label_bias"], Pl["ba"], Pl["bb"], cfg.num_objs, *want_flags)
+
+    out, vsum, al = run(att.cuda(), True, True, True)
     tol = TOL[dtype]
     assert relerr(al, alpha) < tol
     assert relerr(out, want) < tol
     assert relerr(vsum, want.sum(1)) < tol
+    # only the K-sum requested (the whole-path configuration)
+    none, vsum2, none2 = run(att.cuda(), False, True, False)
+    assert none is None and none2 is None and torch.equal(vsum2, vsum)
     # attention = None means the features are used as they are
     with torch.no_grad():
         want1, _ = O.corr_graph_conv(x, batch["graph"].float(), W, "gcn.0.")
-    out1, _, _ = ops.graph_attention(Y, None, labels, Pl["label_bias"], Pl["ba"], Pl["bb"], cfg.num_objs)
+    out1, _, _ = run(None, True, False, False)
     # (un-attended features are 36x larger: α is far more peaked, so bf16 gets 3x the slack)
     assert relerr(out1, torch.relu(want1)) < (tol if dtype == torch.float32 else 3 * tol)

@@ -123,14 +123,27 @@ def test_prepare_weights_layout():
     H, V = cfg.hidden_dim, cfg.v_dim
     assert P["E_pad"] % 64 == 0 and P["emb"].shape == (cfg.ntoken + 1, P["E_pad"])
     assert torch.all(P["emb"][:, cfg.embed_dim:] == 0) and torch.all(P["w_ih"][:, cfg.embed_dim:] == 0)
-    assert P["Wqq"].shape == (2 * H, H) and P["Wg"].shape == (4 * V, V)
+    # bf16 + K=36 + V%128==0: merged ReGAT algebra [W0+W1 ; W2 ; WbᵀWa] (vqa_graph_attention layout 1)
+    assert P["Wqq"].shape == (2 * H, H) and P["Wg3"].shape == (3 * V, V) and "Wg" not in P
+    wa, wb = W["gcn.0.dot_product.wa.weight"].double(), W["gcn.0.dot_product.wb.weight"].double()
+    ba, bb = W["gcn.0.dot_product.wa.bias"].double(), W["gcn.0.dot_product.wb.bias"].double()
+    x = torch.rand((5, V), dtype=torch.float64)
+    dot = (x @ wa.t() + ba) @ (x @ wb.t() + bb).t()                       # modules.py:92-95
+    q = x @ (wb.t() @ wa).t()
+    merged = q @ x.t() + (x @ (wa.t() @ bb))[:, None] + (x @ (wb.t() @ ba))[None, :] + ba.dot(bb)
+    assert torch.allclose(dot, merged, rtol=1e-10, atol=1e-10)
+    assert torch.equal(P["Wg3"][2 * V:], (wb.t() @ wa).float().to(torch.bfloat16))
+    assert torch.equal(P["wvec"][0], (wa.t() @ bb).float().to(torch.bfloat16)) and torch.all(P["wvec"][2:] == 0)
+    assert abs(P["gat_c0"] - float(ba.dot(bb))) < 1e-12 and P["label_bias_lp"].shape == (16, V)
+    P32 = prepare_weights(W, torch.float32, "cpu", True)
+    assert P32["Wg"].shape == (4 * V, V) and "Wg3" not in P32
     s = weight_norm_scale(W["encoder.attention.W_v.main.0.weight_v"], W["encoder.attention.W_v.main.0.weight_g"])
     assert torch.all(P["sv"] == s)
     # weight_norm scale comes from the same torch CPU op as the reference hook (H9)
     ref = (W["encoder.attention.W_v.main.0.weight_g"] / torch.norm(W["encoder.attention.W_v.main.0.weight_v"])).item()
     assert s == ref
     w01 = (W["gcn.0.weight.0.weight"] + W["gcn.0.weight.1.weight"]).to(torch.bfloat16)
-    assert torch.equal(P["Wg"][:V], w01)
+    assert torch.equal(P["Wg3"][:V], w01)
     wl = W["encoder.attention.linear.weight_v"] * O.weight_norm_scale(W["encoder.attention.linear.weight_v"],
                                                                        W["encoder.attention.linear.weight_g"])
     assert torch.allclose(P["wlin"], wl.reshape(-1))

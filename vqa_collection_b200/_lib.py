@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
 
 VQA_F32, VQA_BF16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -53,6 +53,8 @@ class GraphAttentionArgs(C.Structure):
         ("d_ba", c_void_p), ("d_bb", c_void_p),
         ("B", c_int), ("K", c_int), ("V", c_int), ("dtype", c_int),
         ("d_out", c_void_p), ("d_vsum", c_void_p), ("d_alpha", c_void_p),
+        ("layout", c_int), ("d_x", c_void_p), ("ldx", c_int), ("d_wvec", c_void_p), ("c0", c_float),
+        ("d_label_bias_lp", c_void_p),
     ]
 
 
@@ -70,6 +72,7 @@ class ForwardArgs(C.Structure):
         ("d_Wqq", c_void_p), ("d_sqq", c_void_p), ("d_bqq", c_void_p),
         ("d_wlin", c_void_p), ("b_lin", c_float),
         ("d_Wg", c_void_p), ("d_label_bias", c_void_p), ("d_ba", c_void_p), ("d_bb", c_void_p),
+        ("d_Wg3", c_void_p), ("d_wvec", c_void_p), ("gat_c0", c_float), ("d_label_bias_lp", c_void_p),
         ("d_Wvn", c_void_p), ("d_svn", c_void_p), ("d_bvn", c_void_p),
         ("d_Wc0", c_void_p), ("d_sc0", c_void_p), ("d_bc0", c_void_p),
         ("d_Wc1", c_void_p), ("d_sc1", c_void_p), ("d_bc1", c_void_p),

@@ -57,6 +57,7 @@ int gru_gate(const float*, const float*, int, int, int, int, const float*, float
 int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
 int cast_bf16_to_f32(const void*, float*, size_t, cudaStream_t);
 int graph_attention(const vqa_graph_attention_args&, cudaStream_t);
+int graph_attention_tc(const vqa_graph_attention_args&, cudaStream_t);
 int gru_persistent(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
                    cudaStream_t);
 
@@ -222,6 +223,8 @@ int vqa_attention_pool(const float* d_logit_parts, int n_parts, float logit_bias
 int vqa_graph_attention(const vqa_graph_attention_args* args, void* stream) {
   if (int rc = require_sm100()) return rc;
   VQA_REQUIRE(args, "vqa_graph_attention: NULL args");
+  VQA_REQUIRE(args->layout == 0 || args->layout == 1, "vqa_graph_attention: layout=%d", args->layout);
+  if (args->layout == 1) return graph_attention_tc(*args, (cudaStream_t)stream);
   return graph_attention(*args, (cudaStream_t)stream);
 }
 
@@ -250,7 +253,7 @@ static FwdWs carve_fwd(const vqa_forward_args& a, void* base) {
   const int n_parts = (a.H + part_width(a.dtype) - 1) / part_width(a.dtype);
   w.parts = (float*)take((size_t)a.B * a.K * n_parts * 4);
   w.vsum = take((size_t)a.B * a.V * es);
-  w.Y = a.relation ? take((size_t)a.B * a.K * 4 * a.V * es) : nullptr;
+  w.Y = a.relation ? take((size_t)a.B * a.K * (a.d_Wg3 ? 3 : 4) * a.V * es) : nullptr;
   w.joint = take((size_t)a.B * a.H * es);
   w.hid = take((size_t)a.B * 2 * a.H * es);
   w.bytes = off;
@@ -283,7 +286,11 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
   int rc;
   const uint8_t* labels = a.d_labels;
   if (a.relation) {
-    VQA_REQUIRE(a.d_Wg && a.d_label_bias && a.d_ba && a.d_bb, "vqa_forward: NULL ReGAT weight");
+    if (a.d_Wg3) {
+      VQA_REQUIRE(a.dtype == VQA_BF16 && a.d_wvec && a.d_label_bias_lp, "vqa_forward: merged ReGAT weights need bf16");
+    } else {
+      VQA_REQUIRE(a.d_Wg && a.d_label_bias && a.d_ba && a.d_bb, "vqa_forward: NULL ReGAT weight");
+    }
     if (a.d_bbox != nullptr) {
       VQA_REQUIRE(a.d_labels_out, "vqa_forward: d_bbox given without d_labels_out");
       if ((rc = relation_labels(a.d_bbox, nullptr, a.B, a.K, a.img_w, a.img_h, a.d_labels_out, s))) return rc;
@@ -321,15 +328,20 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
     VQA_REQUIRE(att, "vqa_forward: relation path needs d_att");
     if ((rc = attention_pool(w.parts, n_parts, a.b_lin, a.d_img, a.B, a.K, a.V, a.dtype, att, nullptr, nullptr, s))) return rc;
     // 5. wide projection of the raw features + relation-masked graph attention (gcn.py)
+    const int maps = a.d_Wg3 ? 3 : 4;
     l = vqa_linear_args{};
-    l.d_A = a.d_img; l.lda = a.V; l.d_W = a.d_Wg; l.ldw = a.V; l.M = a.B * a.K; l.N = 4 * a.V; l.K = a.V; l.dtype = a.dtype;
-    l.mul_row_div = 1; l.d_out = w.Y; l.ldo = 4 * a.V; l.out_dtype = a.dtype;
+    l.d_A = a.d_img; l.lda = a.V; l.d_W = a.d_Wg3 ? a.d_Wg3 : a.d_Wg; l.ldw = a.V; l.M = a.B * a.K; l.N = maps * a.V; l.K = a.V;
+    l.dtype = a.dtype; l.mul_row_div = 1; l.d_out = w.Y; l.ldo = maps * a.V; l.out_dtype = a.dtype;
     if ((rc = linear_dispatch(l, s))) return rc;
     vqa_graph_attention_args ga{};
-    ga.d_Y = w.Y; ga.ldy = 4 * a.V; ga.d_att = att; ga.d_labels = labels; ga.d_label_bias = a.d_label_bias;
+    ga.d_Y = w.Y; ga.ldy = maps * a.V; ga.d_att = att; ga.d_labels = labels; ga.d_label_bias = a.d_label_bias;
     ga.num_labels = a.num_labels; ga.d_ba = a.d_ba; ga.d_bb = a.d_bb; ga.B = a.B; ga.K = a.K; ga.V = a.V; ga.dtype = a.dtype;
     ga.d_out = a.d_v; ga.d_vsum = w.vsum; ga.d_alpha = a.d_alpha;
-    if ((rc = graph_attention(ga, s))) return rc;
+    if (a.d_Wg3) {
+      ga.layout = 1; ga.d_x = a.d_img; ga.ldx = a.V; ga.d_wvec = a.d_wvec; ga.c0 = a.gat_c0;
+      ga.d_label_bias_lp = a.d_label_bias_lp;
+      if ((rc = graph_attention_tc(ga, s))) return rc;
+    } else if ((rc = graph_attention(ga, s))) return rc;
   }
   // 6. v_net ⊙ q_net (predictor.py:88-91)
   l = vqa_linear_args{};

@@ -1,0 +1,394 @@
+// k9+k10 on tcgen05 — relation-masked K×K graph attention for one CorrelatedGraphConv
+// layer (bf16, sm_100a), consuming the merged wide projection Y = x·[W0+W1 ; W2 ; WbᵀWa]ᵀ.
+//
+// Reference: gcn.py:93-107 (DirectedGraphConv.conv incl. the label-bias gather),
+// modules.py:86-95 (DotProduct), gcn.py:119-128 (relation_alpha: ReLU, adj·α, softmax over
+// dim=1 = the ROW index), gcn.py:152-168 (forward), gcn.py:211-212 (ReLU after the layer),
+// predictor.py:85 (Σ_K) when vsum is requested.
+//
+// Algebra (f_i = a_i·x_i with a = top-down attention; P=(W0+W1)x, S=W2x, Q=(WbᵀWa)x):
+//   dot_ij = a_i a_j (Q_i·x_j) + a_i (x_i·Waᵀbb) + a_j (x_j·Wbᵀba) + ba·bb
+//   α      = softmax_i( Σ_k adj_ik · ReLU(dot_kj) )
+//   out_i  = ReLU( Σ_j α_ij conv_j ),  conv_j = a_j S_j + Σ_k adj_jk a_k P_k + Σ_l hist_jl bias_l
+//          = ReLU( C_i · [P ; S ; bias] )      with the 36×96 coefficient matrix
+//            C = [ (α·adj)·diag(a) | α·diag(a) | α·hist ]
+// so the layer is two tensor-core contractions per image with a tiny K×K stage between them:
+//   phase 1  D1[36,36] = Q·xᵀ (K = V) and D2[36,2] = x·[Waᵀbb, Wbᵀba]       tcgen05.mma, both K-major
+//   phase 2  α and C in shared memory (fp32), C written as the bf16 K-major B operand
+//   phase 3  outᵀ[128 ch, 36] = [P;S;bias]ᵀ·Cᵀ per 128-channel tile             tcgen05.mma, A is
+//            M-major (channels contiguous): the TMA box {64 ch, rows} of Y IS the operand tile
+// One persistent CTA per SM loops over images; warp 0 = TMA producer (one 24 KB slot ring for both
+// phases, so phase-3 tiles stream in while phase 2 computes), warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4..11 = phase 0/2 math and the phase-3 epilogue (thread = channel).
+// Per image HBM traffic = Q, x, P, S (4 × 147 KB) + out: the kernel is HBM-bound by design.
+#include "tc_common.cuh"
+
+namespace vqa {
+namespace gat {
+
+using namespace tc;
+
+constexpr int GK = 36;                       // regions per image
+constexpr int NPAD = 48;                     // regions padded to the MMA N granularity (16)
+constexpr int P_ROWS = 40, S_ROWS = 40, LB_ROWS = 16;
+constexpr int KROWS = P_ROWS + S_ROWS + LB_ROWS;          // 96 contraction rows of phase 3
+constexpr int S_OFF = P_ROWS, LB_OFF = P_ROWS + S_ROWS;    // k index of the S / bias blocks
+constexpr int CH = 128;                      // channels per phase-3 tile (MMA M)
+constexpr int MAXL = 16;
+constexpr int ATOM_BYTES = KROWS * 128;      // one 64-channel atom of the phase-3 A tile (12 KB)
+constexpr int SLOT_BYTES = 2 * ATOM_BYTES;   // 24 KB
+constexpr int G_Q_OFF = 0, G_X_OFF = NPAD * 128, G_W_OFF = 2 * NPAD * 128;
+constexpr int G_BYTES = 2 * NPAD * 128 + 16 * 128;        // Q 6 KB + x 6 KB + wvec 2 KB
+constexpr int STAGES = 7;
+constexpr int BT_CHUNK = NPAD * 128;         // one 64-k chunk of the coefficient tile (6 KB)
+constexpr int BT_BYTES = 2 * BT_CHUNK;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;      // 384
+constexpr int TMEM_COLS = 512;
+constexpr int COL_G = 0, COL_U = 48, COL_OUT = 64, OUT_STRIDE = 64, OUT_BUFS = 4;
+
+struct P2 {
+  float G[GK][GK + 1];                       // Q·xᵀ
+  float A0[GK][GK + 1];                      // ReLU(dot)
+  float Al[GK][GK + 1];                      // adj·A0 → α
+  float hist[GK][MAXL];
+  float a[GK], ua[GK], ub[GK];
+  unsigned long long adj[GK], adjT[GK];      // row masks (bit k: label_ik≠0), column masks (bit j: label_jk≠0)
+};
+
+constexpr int BAR_OFF = STAGES * SLOT_BYTES + BT_BYTES;
+constexpr int P2_OFF = BAR_OFF + 256;
+constexpr int SMEM_BYTES = 1024 + P2_OFF + (int)sizeof(P2);
+
+struct Params {
+  int B, V;
+  const float* att; const uint8_t* labels; int num_labels; float c0;
+  __nv_bfloat16* out; __nv_bfloat16* vsum; float* alpha;
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
+                          const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmPS,
+                          const __grid_constant__ CUtensorMap tmLB, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bt = base + STAGES * SLOT_BYTES;               // coefficient tile (B operand of phase 3)
+  uint8_t* bt_ptr = base_ptr + STAGES * SLOT_BYTES;
+  const uint32_t bars = base + BAR_OFF;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const uint32_t g_full = bars + 8u * (2 * STAGES), c_full = bars + 8u * (2 * STAGES + 1);
+  auto ofull_bar = [&](int b) { return bars + 8u * (2 * STAGES + 2 + b); };
+  auto oempty_bar = [&](int b) { return bars + 8u * (2 * STAGES + 2 + OUT_BUFS + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 + 2 * OUT_BUFS);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + BAR_OFF + 8 * (2 * STAGES + 2 + 2 * OUT_BUFS));
+  P2& sm = *reinterpret_cast<P2*>(base_ptr + P2_OFF);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int V = p.V;
+  const int kb_g = V / BK;                   // phase-1 k-blocks
+  const int n_cc = V / CH;                   // phase-3 channel tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmPS); tma_prefetch_desc(&tmLB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(g_full, 1); mbar_init(c_full, 1);
+    for (int b = 0; b < OUT_BUFS; ++b) { mbar_init(ofull_bar(b), 1); mbar_init(oempty_bar(b), 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp >= EPI_WARP0) {
+    // coefficient tile: rows 36..47 and the k padding stay zero for the whole kernel
+    for (int i = threadIdx.x - EPI_WARP0 * 32; i < BT_BYTES / 16; i += EPI_THREADS)
+      reinterpret_cast<uint4*>(bt_ptr)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+        const int row0 = img * GK;
+        for (int kb = 0; kb < kb_g; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t slot = base + stage * SLOT_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), G_BYTES);
+          tma_load_2d(slot + G_Q_OFF, &tmQ, full_bar(stage), 2 * V + kb * BK, row0);
+          tma_load_2d(slot + G_X_OFF, &tmX, full_bar(stage), kb * BK, row0);
+          tma_load_2d(slot + G_W_OFF, &tmW, full_bar(stage), kb * BK, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        for (int cc = 0; cc < n_cc; ++cc) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t slot = base + stage * SLOT_BYTES;
+          mbar_arrive_expect_tx(full_bar(stage), SLOT_BYTES);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = cc * CH + h * 64;
+            const uint32_t atom = slot + h * ATOM_BYTES;
+            tma_load_2d(atom, &tmPS, full_bar(stage), c, row0);                          // P rows (k 0..39)
+            tma_load_2d(atom + S_OFF * 128, &tmPS, full_bar(stage), V + c, row0);        // S rows (k 40..79)
+            tma_load_2d(atom + LB_OFF * 128, &tmLB, full_bar(stage), c, 0);              // bias rows (k 80..95)
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_g = make_idesc_bf16(128, NPAD);
+      constexpr uint32_t idesc_u = make_idesc_bf16(128, 16);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, NPAD) | IDESC_A_MN_MAJOR;
+      int stage = 0; uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++it) {
+        // phase 1 (D1/D2 are free: the epilogue read them before arriving on c_full of the previous image)
+        for (int kb = 0; kb < kb_g; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t slot = base + stage * SLOT_BYTES;
+          const uint64_t qd = make_sw128_kmajor_desc(slot + G_Q_OFF), xd = make_sw128_kmajor_desc(slot + G_X_OFF),
+                         wd = make_sw128_kmajor_desc(slot + G_W_OFF);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_bf16(tmem_base + COL_G, qd + 2 * k, xd + 2 * k, idesc_g, (kb | k) != 0);
+            umma_bf16(tmem_base + COL_U, xd + 2 * k, wd + 2 * k, idesc_u, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(g_full);
+        // phase 3 needs the coefficient tile of this image
+        mbar_wait(c_full, it & 1u);
+        tcgen05_fence_after();
+        for (int cc = 0; cc < n_cc; ++cc) {
+          const uint32_t tile = it * (uint32_t)n_cc + (uint32_t)cc;      // running tile index of this CTA
+          const int buf = tile & (OUT_BUFS - 1);
+          const uint32_t use = tile / OUT_BUFS;
+          mbar_wait(oempty_bar(buf), (use & 1u) ^ 1u);
+          tcgen05_fence_after();
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t slot = base + stage * SLOT_BYTES;
+          const uint32_t d = tmem_base + COL_OUT + buf * OUT_STRIDE;
+#pragma unroll
+          for (int ks = 0; ks < KROWS / UMMA_K; ++ks) {
+            const uint64_t ad = make_sw128_mnmajor_desc(slot + ks * 2048, ATOM_BYTES, 1024);
+            const uint64_t bd = make_sw128_kmajor_desc(bt + (ks >> 2) * BT_CHUNK) + (uint64_t)(2 * (ks & 3));
+            umma_bf16(d, ad, bd, idesc_o, ks != 0);
+          }
+          umma_commit(empty_bar(stage));
+          umma_commit(ofull_bar(buf));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    const int q = warp & 3;                          // TMEM lane quarter of this warp
+    const int hf = (warp - EPI_WARP0) >> 2;          // which half of the phase-3 tiles
+    const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..255
+    uint32_t it = 0;
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++it) {
+      // ---- phase 0: attention scalars, adjacency masks, label histogram (overlaps phase-1 loads)
+      if (et < GK) {
+        sm.a[et] = p.att ? __ldg(p.att + (size_t)img * GK + et) : 1.f;
+        const uint8_t* lr = p.labels + ((size_t)img * GK + et) * GK;
+        unsigned long long m = 0ull;
+        float h[MAXL];
+#pragma unroll
+        for (int l = 0; l < MAXL; ++l) h[l] = 0.f;
+        for (int k = 0; k < GK; ++k) {
+          const int l = __ldg(lr + k);
+          if (l != 0) m |= (1ull << k);
+#pragma unroll
+          for (int t = 0; t < MAXL; ++t) h[t] += (t == l) ? 1.f : 0.f;
+        }
+        sm.adj[et] = m;
+#pragma unroll
+        for (int l = 0; l < MAXL; ++l) sm.hist[et][l] = (l < p.num_labels) ? h[l] : 0.f;
+      } else if (et >= 64 && et < 64 + GK) {
+        const int k = et - 64;
+        const uint8_t* lc = p.labels + (size_t)img * GK * GK + k;
+        unsigned long long m = 0ull;
+        for (int j = 0; j < GK; ++j) if (__ldg(lc + j * GK) != 0) m |= (1ull << j);
+        sm.adjT[k] = m;
+      }
+      // ---- phase 2a: D1/D2 rows 0..35 → shared memory
+      mbar_wait(g_full, it & 1u);
+      tcgen05_fence_after();
+      if (hf == 0 && q < 2) {
+        uint32_t v[32], w16[16], u16[16];
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        tmem_ld_32x32(t_row + COL_G, v);
+        tmem_ld_32x16(t_row + COL_G + 32, w16);
+        tmem_ld_32x16(t_row + COL_U, u16);
+        tmem_ld_wait();
+        const int r = q * 32 + lane;
+        if (r < GK) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sm.G[r][j] = __uint_as_float(v[j]);
+#pragma unroll
+          for (int j = 0; j < GK - 32; ++j) sm.G[r][32 + j] = __uint_as_float(w16[j]);
+          sm.ua[r] = __uint_as_float(u16[0]);
+          sm.ub[r] = __uint_as_float(u16[1]);
+        }
+      }
+      tcgen05_fence_before();
+      epi_bar();
+      // ---- 2b: α0 = ReLU(dot)
+      for (int e = et; e < GK * GK; e += EPI_THREADS) {
+        const int i = e / GK, j = e - i * GK;
+        const float ai = sm.a[i], aj = sm.a[j];
+        const float dot = ai * aj * sm.G[i][j] + ai * sm.ua[i] + aj * sm.ub[j] + p.c0;
+        sm.A0[i][j] = fmaxf(dot, 0.f);
+      }
+      epi_bar();
+      // ---- 2c: α1 = adj·α0
+      for (int e = et; e < GK * GK; e += EPI_THREADS) {
+        const int i = e / GK, j = e - i * GK;
+        const unsigned long long m = sm.adj[i];
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < GK; ++k) s += ((m >> k) & 1ull) ? sm.A0[k][j] : 0.f;
+        sm.Al[i][j] = s;
+      }
+      epi_bar();
+      // ---- 2d: softmax over the row index i for every column j
+      if (et < GK) {
+        const int j = et;
+        float x[GK];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < GK; ++i) { x[i] = sm.Al[i][j]; mx = fmaxf(mx, x[i]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < GK; ++i) { x[i] = expf(x[i] - mx); sum += x[i]; }
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int i = 0; i < GK; ++i) sm.Al[i][j] = x[i] * inv;
+      }
+      epi_bar();
+      // ---- 2e: coefficient matrix C [36, 96] → bf16, K-major 128B-swizzled B operand
+      //      k 0..35: (α·adj)_ik a_k   |  k 40..75: α_ij a_j  |  k 80..91: (α·hist)_il
+      for (int e = et; e < GK * (KROWS / 2); e += EPI_THREADS) {
+        const int i = e / (KROWS / 2), kp = e - i * (KROWS / 2);
+        float c2[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int kk = 2 * kp + t;
+          float c = 0.f;
+          if (kk < GK) {
+            const unsigned long long m = sm.adjT[kk];
+#pragma unroll
+            for (int j = 0; j < GK; ++j) c += ((m >> j) & 1ull) ? sm.Al[i][j] : 0.f;
+            c *= sm.a[kk];
+          } else if (kk >= S_OFF && kk < S_OFF + GK) {
+            c = sm.Al[i][kk - S_OFF] * sm.a[kk - S_OFF];
+          } else if (kk >= LB_OFF && kk < LB_OFF + MAXL) {
+            const int l = kk - LB_OFF;
+#pragma unroll
+            for (int j = 0; j < GK; ++j) c = fmaf(sm.Al[i][j], sm.hist[j][l], c);
+          }
+          c2[t] = c;
+        }
+        const int k0 = 2 * kp;
+        const int chunk = k0 >> 6, kc = k0 & 63;
+        const uint32_t off = chunk * BT_CHUNK + i * 128 + ((((kc * 2) >> 4) ^ (i & 7)) << 4) + ((kc * 2) & 15);
+        *reinterpret_cast<uint32_t*>(bt_ptr + off) = pack_bf16x2(c2[0], c2[1]);
+      }
+      if (p.alpha != nullptr)
+        for (int e = et; e < GK * GK; e += EPI_THREADS)
+          p.alpha[(size_t)img * GK * GK + e] = sm.Al[e / GK][e % GK];
+      fence_proxy_async();
+      epi_bar();
+      if (et == 0) mbar_arrive(c_full);
+      // ---- phase 3 epilogue: thread = channel; ReLU, Σ_i, store
+      for (int cc = 0; cc < n_cc; ++cc) {
+        const uint32_t tile = it * (uint32_t)n_cc + (uint32_t)cc;
+        if ((int)(tile & 1u) != hf) continue;          // buffer parity selects the warp set
+        const int buf = tile & (OUT_BUFS - 1);
+        const uint32_t use = tile / OUT_BUFS;
+        mbar_wait(ofull_bar(buf), use & 1u);
+        tcgen05_fence_after();
+        uint32_t v[32], w16[16];
+        const uint32_t t_row = tmem_base + COL_OUT + buf * OUT_STRIDE + ((uint32_t)(q * 32) << 16);
+        tmem_ld_32x32(t_row, v);
+        tmem_ld_32x16(t_row + 32, w16);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(oempty_bar(buf));
+        const int c = cc * CH + q * 32 + lane;
+        float vs = 0.f;
+        __nv_bfloat16* o = p.out ? p.out + (size_t)img * GK * V + c : nullptr;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = fmaxf(__uint_as_float(v[i]), 0.f);
+          vs += s;
+          if (o) o[(size_t)i * V] = __float2bfloat16_rn(s);
+        }
+#pragma unroll
+        for (int i = 32; i < GK; ++i) {
+          const float s = fmaxf(__uint_as_float(w16[i - 32]), 0.f);
+          vs += s;
+          if (o) o[(size_t)i * V] = __float2bfloat16_rn(s);
+        }
+        if (p.vsum) p.vsum[(size_t)img * V + c] = __float2bfloat16_rn(vs);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace gat
+
+int graph_attention_tc(const vqa_graph_attention_args& a, cudaStream_t s) {
+  using namespace gat;
+  VQA_REQUIRE(a.d_Y && a.d_x && a.d_wvec && a.d_label_bias_lp && a.d_labels, "graph_attention(layout 1): NULL input");
+  if (a.K != GK) return fail(VQA_ERR_UNSUPPORTED, "graph_attention: K=%d (only K=%d is built)", a.K, GK);
+  VQA_REQUIRE(a.dtype == VQA_BF16, "graph_attention(layout 1): bf16 only");
+  VQA_REQUIRE(a.V % CH == 0, "graph_attention(layout 1): V=%d must be a multiple of %d", a.V, CH);
+  VQA_REQUIRE(a.num_labels >= 1 && a.num_labels <= MAXL, "graph_attention: num_labels=%d", a.num_labels);
+  VQA_REQUIRE(a.ldy >= 3 * a.V && a.ldy % 8 == 0 && a.ldx >= a.V && a.ldx % 8 == 0, "graph_attention(layout 1): ldy=%d ldx=%d",
+              a.ldy, a.ldx);
+  if (a.B == 0) return VQA_OK;
+  CUtensorMap tmQ, tmX, tmW, tmPS, tmLB;
+  int rc;
+  const long long rows = (long long)a.B * GK;
+  if ((rc = tc::make_tensor_map_bf16(&tmQ, a.d_Y, rows, a.ldy, a.ldy, NPAD))) return rc;
+  if ((rc = tc::make_tensor_map_bf16(&tmX, a.d_x, rows, a.V, a.ldx, NPAD))) return rc;
+  if ((rc = tc::make_tensor_map_bf16(&tmW, a.d_wvec, 16, a.V, a.V, 16))) return rc;
+  if ((rc = tc::make_tensor_map_bf16(&tmPS, a.d_Y, rows, a.ldy, a.ldy, P_ROWS))) return rc;
+  if ((rc = tc::make_tensor_map_bf16(&tmLB, a.d_label_bias_lp, LB_ROWS, a.V, a.V, LB_ROWS))) return rc;
+  Params p;
+  p.B = a.B; p.V = a.V; p.att = a.d_att; p.labels = a.d_labels; p.num_labels = a.num_labels; p.c0 = a.c0;
+  p.out = (__nv_bfloat16*)a.d_out; p.vsum = (__nv_bfloat16*)a.d_vsum; p.alpha = a.d_alpha;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQA_CUDA_CHECK(cudaFuncSetAttribute(graph_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = a.B < sm_count() ? a.B : sm_count();
+  graph_attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tmQ, tmX, tmW, tmPS, tmLB, p);
+  VQA_LAUNCH_CHECK();
+  return VQA_OK;
+}
+
+}  // namespace vqa

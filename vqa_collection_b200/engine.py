@@ -51,7 +51,7 @@ def pack_gru(w_ih, w_hh, b_ih, b_hh, units: int = 64):
     return w_ih[perm].contiguous(), w_hh[perm].contiguous(), bias.float().contiguous()
 
 
-def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_layer: int = 0) -> dict:
+def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_layer: int = 0, K: int = 36) -> dict:
     """Reference-named tensors → device tensors in kernel layout."""
     f32 = lambda t: t.detach().to("cpu", torch.float32)
     dev = lambda t, dt=torch.float32: t.to(dt).contiguous().to(device)
@@ -95,21 +95,44 @@ def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_lay
     P["H"], P["V"], P["A"] = H, P["Wv"].shape[1], P["Wc1"].shape[0]
     if relation:
         p = f"gcn.{gcn_layer}."
-        P.update(prepare_gcn_layer({k[len(p):]: t for k, t in W.items() if k.startswith(p)}, dtype, device))
+        P.update(prepare_gcn_layer({k[len(p):]: t for k, t in W.items() if k.startswith(p)}, dtype, device, K))
     return P
 
 
-def prepare_gcn_layer(Wl: dict, dtype, device) -> dict:
-    """One CorrelatedGraphConv layer (gcn.py:55-67,113-117): concatenate
-    [W0+W1 ; W2 ; Wa ; Wb] so a single pass over x feeds all four maps."""
+def gat_tc_supported(dtype, V: int, K: int = 36) -> bool:
+    """shapes the tcgen05 graph-attention kernel (vqa_graph_attention layout 1) is built for"""
+    return dtype == torch.bfloat16 and K == 36 and V % 128 == 0
+
+
+def prepare_gcn_layer(Wl: dict, dtype, device, K: int = 36, merged=None) -> dict:
+    """One CorrelatedGraphConv layer (gcn.py:55-67,113-117).
+
+    fp32 (layout 0): concatenate [W0+W1 ; W2 ; Wa ; Wb] so a single pass over x feeds all four maps.
+    bf16 (layout 1): the DotProduct maps are merged exactly, (Wa x_i + ba)·(Wb x_j + bb) =
+    (WbᵀWa x_i)·x_j + x_i·(Waᵀbb) + x_j·(Wbᵀba) + ba·bb, so the wide GEMM has 3 maps
+    [W0+W1 ; W2 ; WbᵀWa] and the rank-1 terms ride along as two extra MMA columns (`wvec`)."""
     f32 = lambda t: t.detach().to("cpu", torch.float32)
     dev = lambda t, dt=torch.float32: t.to(dt).contiguous().to(device)
     w01 = f32(Wl["weight.0.weight"]) + f32(Wl["weight.1.weight"])
-    Wg = torch.cat([w01, f32(Wl["weight.2.weight"]), f32(Wl["dot_product.wa.weight"]),
-                    f32(Wl["dot_product.wb.weight"])], 0)
-    return {"Wg": dev(Wg, dtype), "label_bias": dev(f32(Wl["bias"])),
-            "ba": dev(f32(Wl["dot_product.wa.bias"])), "bb": dev(f32(Wl["dot_product.wb.bias"])),
-            "num_labels": Wl["bias"].shape[0]}
+    w2, wa, wb = f32(Wl["weight.2.weight"]), f32(Wl["dot_product.wa.weight"]), f32(Wl["dot_product.wb.weight"])
+    ba, bb, lbias = f32(Wl["dot_product.wa.bias"]), f32(Wl["dot_product.wb.bias"]), f32(Wl["bias"])
+    V, L = w2.shape[1], lbias.shape[0]
+    P = {"num_labels": L}
+    if merged is None:
+        merged = gat_tc_supported(dtype, V, K) and w2.shape[0] == V and L <= 16
+    if merged:
+        wq = wb.double().t().matmul(wa.double()).float()
+        wvec = torch.zeros((16, V))
+        wvec[0] = wa.double().t().matmul(bb.double()).float()
+        wvec[1] = wb.double().t().matmul(ba.double()).float()
+        lb = torch.zeros((16, V))
+        lb[:L] = lbias
+        P.update({"Wg3": dev(torch.cat([w01, w2, wq], 0), dtype), "wvec": dev(wvec, dtype),
+                  "gat_c0": float(ba.double().dot(bb.double())), "label_bias_lp": dev(lb, dtype)})
+    else:
+        P.update({"Wg": dev(torch.cat([w01, w2, wa, wb], 0), dtype), "label_bias": dev(lbias),
+                  "ba": dev(ba), "bb": dev(bb)})
+    return P
 
 
 class VQAEngine:
@@ -124,7 +147,7 @@ class VQAEngine:
         self.relation = bool(relation)
         self.K = num_objs
         with torch.cuda.device(self.device):
-            self.P = prepare_weights(weights, self.dtype, self.device, self.relation)
+            self.P = prepare_weights(weights, self.dtype, self.device, self.relation, K=num_objs)
         self._ws = {}
         self.last_launches = 0
 
@@ -143,8 +166,13 @@ class VQAEngine:
             a.d_wx_packed, a.d_wh_packed, a.d_bias_packed = (P["wx_packed"].data_ptr(), P["wh_packed"].data_ptr(),
                                                              P["bias_packed"].data_ptr())
         if self.relation:
-            for name in ("Wg", "label_bias", "ba", "bb"):
-                setattr(a, "d_" + name, P[name].data_ptr())
+            if "Wg3" in P:
+                for name in ("Wg3", "wvec", "label_bias_lp"):
+                    setattr(a, "d_" + name, P[name].data_ptr())
+                a.gat_c0 = P["gat_c0"]
+            else:
+                for name in ("Wg", "label_bias", "ba", "bb"):
+                    setattr(a, "d_" + name, P[name].data_ptr())
         return a
 
     def _workspace(self, a):

@@ -56,21 +56,29 @@ class CorrelatedGraphConv(DirectedGraphConv):
         self.dot_product = DotProduct(in_dim, in_dim, out_dim)
         self.softmax = nn.Softmax(dim=1)
         self._cache = PreparedCache()
+        self._K = 36
 
     def prepared(self, dtype):
         params = list(self.parameters())
-        return self._cache.get(("gcn", dtype), params, lambda: prepare_gcn_layer(
-            {k: v for k, v in self.state_dict().items()}, dtype, self.bias.device))
+        return self._cache.get(("gcn", dtype, self._K), params, lambda: prepare_gcn_layer(
+            {k: v for k, v in self.state_dict().items()}, dtype, self.bias.device, self._K))
 
     def run(self, x, graph, att=None, want_out=True, want_vsum=False, want_alpha=False):
         """x: RAW features [B,K,V]; att f32 [B,K] or None (feature = att ⊙ x).
         Returns (ReLU(layer output) or None, Σ_K or None, α or None) — the ReLU of
         GCN.forward (gcn.py:212) is fused."""
         dtype = compute_dtype()
-        P = self.prepared(dtype)
         B, K, V = x.shape
-        Y = ops.linear(as_compute(x, dtype).view(B * K, V), P["Wg"])
+        if K != self._K:
+            self._K = K
+        P = self.prepared(dtype)
         labels = graph if graph.dtype == torch.uint8 else graph.to(torch.uint8)
+        xc = as_compute(x, dtype).view(B * K, V)
+        if "Wg3" in P:                                   # bf16: merged algebra + tcgen05 graph attention
+            Y = ops.linear(xc, P["Wg3"])
+            return ops.graph_attention_merged(Y, xc, att, labels.contiguous(), P["wvec"], P["gat_c0"],
+                                              P["label_bias_lp"], P["num_labels"], K, want_out, want_vsum, want_alpha)
+        Y = ops.linear(xc, P["Wg"])
         return ops.graph_attention(Y, att, labels.contiguous(), P["label_bias"], P["ba"], P["bb"], K,
                                    want_out, want_vsum, want_alpha)
 

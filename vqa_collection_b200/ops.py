@@ -203,7 +203,7 @@ def attention_pool(parts, logit_bias, x, want_att=True, want_vsum=True, want_vat
 
 
 def graph_attention(Y, att, labels, label_bias, ba, bb, K, want_out=True, want_vsum=False, want_alpha=False):
-    """One CorrelatedGraphConv layer + ReLU after the wide projection (gcn.py:93-168,211-212).
+    """One CorrelatedGraphConv layer + ReLU after the wide projection (gcn.py:93-168,211-212), layout 0.
 
     Y [B*K, 4V] = x·[W0+W1; W2; Wa; Wb]ᵀ; att f32 [B,K] or None; labels u8 [B,K,K]."""
     lib = L.load()
@@ -224,6 +224,34 @@ def graph_attention(Y, att, labels, label_bias, ba, bb, K, want_out=True, want_v
     a.d_label_bias, a.num_labels, a.d_ba, a.d_bb = label_bias.data_ptr(), label_bias.shape[0], ba.data_ptr(), bb.data_ptr()
     a.B, a.K, a.V, a.dtype = B, K, V, dtype_code(Y.dtype)
     a.d_out, a.d_vsum, a.d_alpha = _ptr(out), _ptr(vsum), _ptr(alpha)
+    L.check(lib.vqa_graph_attention(C.byref(a), _stream()))
+    return out, vsum, alpha
+
+
+def graph_attention_merged(Y, x, att, labels, wvec, c0, label_bias_lp, num_labels, K, want_out=True,
+                           want_vsum=False, want_alpha=False):
+    """Layout 1 (bf16, tcgen05): Y [B*K, 3V] = x·[W0+W1; W2; WbᵀWa]ᵀ, x [B*K, V] the raw features,
+    wvec bf16 [16,V] (rows Waᵀbb, Wbᵀba), c0 = ba·bb, label_bias_lp bf16 [16,V]."""
+    lib = L.load()
+    _require(Y, torch.bfloat16, "Y")
+    _require(x, torch.bfloat16, "x")
+    _require(wvec, torch.bfloat16, "wvec")
+    _require(label_bias_lp, torch.bfloat16, "label_bias_lp")
+    _require(labels, torch.uint8, "labels")
+    if att is not None:
+        _require(att, torch.float32, "att")
+    V = Y.shape[1] // 3
+    B = Y.shape[0] // K
+    out = torch.empty((B, K, V), dtype=Y.dtype, device=Y.device) if want_out else None
+    vsum = torch.empty((B, V), dtype=Y.dtype, device=Y.device) if want_vsum else None
+    alpha = torch.empty((B, K, K), dtype=torch.float32, device=Y.device) if want_alpha else None
+    a = L.GraphAttentionArgs()
+    a.d_Y, a.ldy, a.d_att, a.d_labels = Y.data_ptr(), Y.stride(0), _ptr(att), labels.data_ptr()
+    a.num_labels = int(num_labels)
+    a.B, a.K, a.V, a.dtype = B, K, V, L.VQA_BF16
+    a.d_out, a.d_vsum, a.d_alpha = _ptr(out), _ptr(vsum), _ptr(alpha)
+    a.layout, a.d_x, a.ldx, a.d_wvec, a.c0 = 1, x.data_ptr(), x.stride(0), wvec.data_ptr(), float(c0)
+    a.d_label_bias_lp = label_bias_lp.data_ptr()
     L.check(lib.vqa_graph_attention(C.byref(a), _stream()))
     return out, vsum, alpha
 
