@@ -62,11 +62,17 @@ hid = torch.rand((B, 2048), device=dev).to(torch.bfloat16)
 timeit("cls1 gemm [B,2048]x[3129,2048] f32 out", lambda: ops.linear(hid, P["Wc1"], P["sc1"], P["bc1"], relu=True, out_dtype=torch.float32), flops=2.0 * B * 3129 * 2048)
 logits = torch.rand((B, 3129), device=dev)
 timeit("argmax", lambda: ops.argmax_rows(logits))
-timeit("wide ReGAT gemm [B*36,2048]x[8192,2048]", lambda: ops.linear(x2, P["Wg"]), reps=10, flops=2.0 * B * 36 * 8192 * 2048)
-Y = ops.linear(x2, P["Wg"])
+timeit("wide ReGAT gemm [B*36,2048]x[6144,2048]", lambda: ops.linear(x2, P["Wg3"]), reps=10, flops=2.0 * B * 36 * 6144 * 2048)
+Y = ops.linear(x2, P["Wg3"])
 att = torch.softmax(torch.randn((B, 36), device=dev), 1)
 labels = ops.relation_labels(torch.from_numpy(O.make_boxes(B, 36, 3)).to(dev), 640, 480)
-timeit("graph_attention (vsum only)", lambda: ops.graph_attention(Y, att, labels, P["label_bias"], P["ba"], P["bb"], 36, False, True, False), reps=10)
+gat_bytes = B * 36 * 2048 * 2 * 4 + B * 2048 * 2        # Q, x, P, S in; vsum out
+timeit("graph_attention tcgen05 (vsum only)", lambda: ops.graph_attention_merged(
+    Y, x2, att, labels, P["wvec"], P["gat_c0"], P["label_bias_lp"], P["num_labels"], 36, False, True, False),
+    reps=20, bytes_=gat_bytes)
+timeit("graph_attention tcgen05 (out+vsum+alpha)", lambda: ops.graph_attention_merged(
+    Y, x2, att, labels, P["wvec"], P["gat_c0"], P["label_bias_lp"], P["num_labels"], 36, True, True, True),
+    reps=20, bytes_=gat_bytes + B * 36 * 2048 * 2)
 boxes = torch.from_numpy(O.make_boxes(B, 36, 3)).to(dev)
 timeit("relation_labels B=1024", lambda: ops.relation_labels(boxes, 640, 480), bytes_=B * 1872)
 big = torch.from_numpy(O.make_boxes(1 << 18, 36, 4)).to(dev)

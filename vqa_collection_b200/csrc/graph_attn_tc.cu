@@ -18,8 +18,10 @@
 //   phase 3  outᵀ[128 ch, 36] = [P;S;bias]ᵀ·Cᵀ per 128-channel tile             tcgen05.mma, A is
 //            M-major (channels contiguous): the TMA box {64 ch, rows} of Y IS the operand tile
 // One persistent CTA per SM loops over images; warp 0 = TMA producer (one 24 KB slot ring for both
-// phases, so phase-3 tiles stream in while phase 2 computes), warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4..11 = phase 0/2 math and the phase-3 epilogue (thread = channel).
+// phases), warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = phase 0/2 math and the
+// phase-3 epilogue (thread = channel).  The image loop is software pipelined: phase 1 of image n+1
+// (loads + MMAs into the second D1/D2 buffer) runs while the epilogue warps do phase 2 of image n,
+// so the K×K stage never stalls the load stream.
 // Per image HBM traffic = Q, x, P, S (4 × 147 KB) + out: the kernel is HBM-bound by design.
 #include "tc_common.cuh"
 
@@ -45,7 +47,7 @@ constexpr int BT_BYTES = 2 * BT_CHUNK;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;      // 384
 constexpr int TMEM_COLS = 512;
-constexpr int COL_G = 0, COL_U = 48, COL_OUT = 64, OUT_STRIDE = 64, OUT_BUFS = 4;
+constexpr int COL_G = 0, COL_U = 48, G_STRIDE = 64, COL_OUT = 128, OUT_STRIDE = 64, OUT_BUFS = 4;
 
 struct P2 {
   float G[GK][GK + 1];                       // Q·xᵀ
@@ -81,12 +83,13 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   const uint32_t bars = base + BAR_OFF;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  const uint32_t g_full = bars + 8u * (2 * STAGES), c_full = bars + 8u * (2 * STAGES + 1);
-  auto ofull_bar = [&](int b) { return bars + 8u * (2 * STAGES + 2 + b); };
-  auto oempty_bar = [&](int b) { return bars + 8u * (2 * STAGES + 2 + OUT_BUFS + b); };
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 + 2 * OUT_BUFS);
+  auto gfull_bar = [&](int b) { return bars + 8u * (2 * STAGES + b); };
+  const uint32_t c_full = bars + 8u * (2 * STAGES + 2);
+  auto ofull_bar = [&](int b) { return bars + 8u * (2 * STAGES + 3 + b); };
+  auto oempty_bar = [&](int b) { return bars + 8u * (2 * STAGES + 3 + OUT_BUFS + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 3 + 2 * OUT_BUFS);
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + BAR_OFF + 8 * (2 * STAGES + 2 + 2 * OUT_BUFS));
+      reinterpret_cast<volatile uint32_t*>(base_ptr + BAR_OFF + 8 * (2 * STAGES + 3 + 2 * OUT_BUFS));
   P2& sm = *reinterpret_cast<P2*>(base_ptr + P2_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,7 +103,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(g_full, 1); mbar_init(c_full, 1);
+    mbar_init(gfull_bar(0), 1); mbar_init(gfull_bar(1), 1); mbar_init(c_full, 1);
     for (int b = 0; b < OUT_BUFS; ++b) { mbar_init(ofull_bar(b), 1); mbar_init(oempty_bar(b), 128); }
     fence_barrier_init();
   }
@@ -120,7 +123,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+      auto load_g = [&](int img) {                   // phase-1 operands of one image
         const int row0 = img * GK;
         for (int kb = 0; kb < kb_g; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -131,6 +134,11 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           tma_load_2d(slot + G_W_OFF, &tmW, full_bar(stage), kb * BK, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+      };
+      if ((int)blockIdx.x < p.B) load_g(blockIdx.x);
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
+        if (img + (int)gridDim.x < p.B) load_g(img + gridDim.x);
+        const int row0 = img * GK;
         for (int cc = 0; cc < n_cc; ++cc) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t slot = base + stage * SLOT_BYTES;
@@ -154,9 +162,9 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       constexpr uint32_t idesc_u = make_idesc_bf16(128, 16);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, NPAD) | IDESC_A_MN_MAJOR;
       int stage = 0; uint32_t phase = 0;
-      uint32_t it = 0;
-      for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++it) {
-        // phase 1 (D1/D2 are free: the epilogue read them before arriving on c_full of the previous image)
+      auto mma_g = [&](uint32_t gbuf) {
+        // phase 1 into D1/D2 buffer gbuf (free: its previous image's phase 2a finished before that image's c_full)
+        const uint32_t dg = tmem_base + gbuf * G_STRIDE;
         for (int kb = 0; kb < kb_g; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
@@ -165,13 +173,18 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
                          wd = make_sw128_kmajor_desc(slot + G_W_OFF);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(tmem_base + COL_G, qd + 2 * k, xd + 2 * k, idesc_g, (kb | k) != 0);
-            umma_bf16(tmem_base + COL_U, xd + 2 * k, wd + 2 * k, idesc_u, (kb | k) != 0);
+            umma_bf16(dg + COL_G, qd + 2 * k, xd + 2 * k, idesc_g, (kb | k) != 0);
+            umma_bf16(dg + COL_U, xd + 2 * k, wd + 2 * k, idesc_u, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(g_full);
+        umma_commit(gfull_bar(gbuf));
+      };
+      uint32_t it = 0;
+      if ((int)blockIdx.x < p.B) mma_g(0);
+      for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++it) {
+        if (img + (int)gridDim.x < p.B) mma_g((it + 1) & 1u);
         // phase 3 needs the coefficient tile of this image
         mbar_wait(c_full, it & 1u);
         tcgen05_fence_after();
@@ -201,18 +214,21 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const int q = warp & 3;                          // TMEM lane quarter of this warp
     const int hf = (warp - EPI_WARP0) >> 2;          // which half of the phase-3 tiles
     const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..255
-    uint32_t it = 0;
-    for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++it) {
-      // ---- phase 0: attention scalars, adjacency masks, label histogram (overlaps phase-1 loads)
+    // ---- phase 0: attention scalars, row adjacency masks, label histogram of one image
+    auto phase0 = [&](int img) {
       if (et < GK) {
         sm.a[et] = p.att ? __ldg(p.att + (size_t)img * GK + et) : 1.f;
-        const uint8_t* lr = p.labels + ((size_t)img * GK + et) * GK;
+        const uint32_t* lr = reinterpret_cast<const uint32_t*>(p.labels + ((size_t)img * GK + et) * GK);
+        uint32_t w[GK / 4];
+#pragma unroll
+        for (int k4 = 0; k4 < GK / 4; ++k4) w[k4] = __ldg(lr + k4);
         unsigned long long m = 0ull;
         float h[MAXL];
 #pragma unroll
         for (int l = 0; l < MAXL; ++l) h[l] = 0.f;
+#pragma unroll
         for (int k = 0; k < GK; ++k) {
-          const int l = __ldg(lr + k);
+          const int l = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
           if (l != 0) m |= (1ull << k);
 #pragma unroll
           for (int t = 0; t < MAXL; ++t) h[t] += (t == l) ? 1.f : 0.f;
@@ -220,19 +236,18 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         sm.adj[et] = m;
 #pragma unroll
         for (int l = 0; l < MAXL; ++l) sm.hist[et][l] = (l < p.num_labels) ? h[l] : 0.f;
-      } else if (et >= 64 && et < 64 + GK) {
-        const int k = et - 64;
-        const uint8_t* lc = p.labels + (size_t)img * GK * GK + k;
-        unsigned long long m = 0ull;
-        for (int j = 0; j < GK; ++j) if (__ldg(lc + j * GK) != 0) m |= (1ull << j);
-        sm.adjT[k] = m;
       }
+    };
+    uint32_t it = 0;
+    if ((int)blockIdx.x < p.B) phase0(blockIdx.x);
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++it) {
       // ---- phase 2a: D1/D2 rows 0..35 → shared memory
-      mbar_wait(g_full, it & 1u);
+      const uint32_t gbuf = it & 1u;
+      mbar_wait(gfull_bar(gbuf), (it >> 1) & 1u);
       tcgen05_fence_after();
       if (hf == 0 && q < 2) {
         uint32_t v[32], w16[16], u16[16];
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t t_row = tmem_base + gbuf * G_STRIDE + ((uint32_t)(q * 32) << 16);
         tmem_ld_32x32(t_row + COL_G, v);
         tmem_ld_32x16(t_row + COL_G + 32, w16);
         tmem_ld_32x16(t_row + COL_U, u16);
@@ -249,12 +264,19 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
       tcgen05_fence_before();
       epi_bar();
-      // ---- 2b: α0 = ReLU(dot)
+      // ---- 2b: α0 = ReLU(dot); column masks adjT from the row masks
       for (int e = et; e < GK * GK; e += EPI_THREADS) {
         const int i = e / GK, j = e - i * GK;
         const float ai = sm.a[i], aj = sm.a[j];
         const float dot = ai * aj * sm.G[i][j] + ai * sm.ua[i] + aj * sm.ub[j] + p.c0;
         sm.A0[i][j] = fmaxf(dot, 0.f);
+      }
+      if (et >= EPI_THREADS - GK) {
+        const int k = et - (EPI_THREADS - GK);
+        unsigned long long m = 0ull;
+#pragma unroll
+        for (int j = 0; j < GK; ++j) m |= ((sm.adj[j] >> k) & 1ull) << j;
+        sm.adjT[k] = m;
       }
       epi_bar();
       // ---- 2c: α1 = adj·α0
@@ -267,48 +289,62 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         sm.Al[i][j] = s;
       }
       epi_bar();
-      // ---- 2d: softmax over the row index i for every column j
-      if (et < GK) {
-        const int j = et;
-        float x[GK];
+      // ---- 2d: softmax over the row index i for every column j (4 threads per column, 9 rows each)
+      {
+        const bool valid = et < 4 * GK;                  // whole warps run the shuffles; the tail lanes idle along
+        const int j = valid ? (et >> 2) : 0, part = et & 3;
+        float x[GK / 4];
         float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < GK; ++i) { x[i] = sm.Al[i][j]; mx = fmaxf(mx, x[i]); }
+        for (int r = 0; r < GK / 4; ++r) { x[r] = valid ? sm.Al[part * (GK / 4) + r][j] : 0.f; mx = fmaxf(mx, x[r]); }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
         float sum = 0.f;
 #pragma unroll
-        for (int i = 0; i < GK; ++i) { x[i] = expf(x[i] - mx); sum += x[i]; }
+        for (int r = 0; r < GK / 4; ++r) { x[r] = expf(x[r] - mx); sum += x[r]; }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         const float inv = 1.f / sum;
+        __syncwarp();                                    // all reads of column j done before it is overwritten
+        if (valid) {
 #pragma unroll
-        for (int i = 0; i < GK; ++i) sm.Al[i][j] = x[i] * inv;
+          for (int r = 0; r < GK / 4; ++r) sm.Al[part * (GK / 4) + r][j] = x[r] * inv;
+        }
       }
       epi_bar();
       // ---- 2e: coefficient matrix C [36, 96] → bf16, K-major 128B-swizzled B operand
       //      k 0..35: (α·adj)_ik a_k   |  k 40..75: α_ij a_j  |  k 80..91: (α·hist)_il
-      for (int e = et; e < GK * (KROWS / 2); e += EPI_THREADS) {
-        const int i = e / (KROWS / 2), kp = e - i * (KROWS / 2);
-        float c2[2];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int kk = 2 * kp + t;
-          float c = 0.f;
-          if (kk < GK) {
-            const unsigned long long m = sm.adjT[kk];
-#pragma unroll
-            for (int j = 0; j < GK; ++j) c += ((m >> j) & 1ull) ? sm.Al[i][j] : 0.f;
-            c *= sm.a[kk];
-          } else if (kk >= S_OFF && kk < S_OFF + GK) {
-            c = sm.Al[i][kk - S_OFF] * sm.a[kk - S_OFF];
-          } else if (kk >= LB_OFF && kk < LB_OFF + MAXL) {
-            const int l = kk - LB_OFF;
-#pragma unroll
-            for (int j = 0; j < GK; ++j) c = fmaf(sm.Al[i][j], sm.hist[j][l], c);
-          }
-          c2[t] = c;
-        }
-        const int k0 = 2 * kp;
+      auto put2 = [&](int i, int k0, float c0v, float c1v) {
         const int chunk = k0 >> 6, kc = k0 & 63;
         const uint32_t off = chunk * BT_CHUNK + i * 128 + ((((kc * 2) >> 4) ^ (i & 7)) << 4) + ((kc * 2) & 15);
-        *reinterpret_cast<uint32_t*>(bt_ptr + off) = pack_bf16x2(c2[0], c2[1]);
+        *reinterpret_cast<uint32_t*>(bt_ptr + off) = pack_bf16x2(c0v, c1v);
+      };
+      for (int e = et; e < GK * (GK / 2); e += EPI_THREADS) {          // P block
+        const int i = e / (GK / 2), kp = e - i * (GK / 2);
+        const unsigned long long m0 = sm.adjT[2 * kp], m1 = sm.adjT[2 * kp + 1];
+        float c0v = 0.f, c1v = 0.f;
+#pragma unroll
+        for (int j = 0; j < GK; ++j) {
+          const float al = sm.Al[i][j];
+          c0v += ((m0 >> j) & 1ull) ? al : 0.f;
+          c1v += ((m1 >> j) & 1ull) ? al : 0.f;
+        }
+        put2(i, 2 * kp, c0v * sm.a[2 * kp], c1v * sm.a[2 * kp + 1]);
+      }
+      for (int e = et; e < GK * (GK / 2); e += EPI_THREADS) {          // S block
+        const int i = e / (GK / 2), kp = e - i * (GK / 2);
+        put2(i, S_OFF + 2 * kp, sm.Al[i][2 * kp] * sm.a[2 * kp], sm.Al[i][2 * kp + 1] * sm.a[2 * kp + 1]);
+      }
+      for (int e = et; e < GK * (MAXL / 2); e += EPI_THREADS) {        // label-bias block
+        const int i = e / (MAXL / 2), lp = e - i * (MAXL / 2);
+        float c0v = 0.f, c1v = 0.f;
+#pragma unroll
+        for (int j = 0; j < GK; ++j) {
+          const float al = sm.Al[i][j];
+          c0v = fmaf(al, sm.hist[j][2 * lp], c0v);
+          c1v = fmaf(al, sm.hist[j][2 * lp + 1], c1v);
+        }
+        put2(i, LB_OFF + 2 * lp, c0v, c1v);
       }
       if (p.alpha != nullptr)
         for (int e = et; e < GK * GK; e += EPI_THREADS)
@@ -316,6 +352,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       fence_proxy_async();
       epi_bar();
       if (et == 0) mbar_arrive(c_full);
+      if (img + (int)gridDim.x < p.B) phase0(img + gridDim.x);       // consumed after the next 2a barrier
       // ---- phase 3 epilogue: thread = channel; ReLU, Σ_i, store
       for (int cc = 0; cc < n_cc; ++cc) {
         const uint32_t tile = it * (uint32_t)n_cc + (uint32_t)cc;
