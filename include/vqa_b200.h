@@ -76,6 +76,8 @@ int vqa_cast_bf16_to_f32(const void* d_src, float* d_dst, size_t n, void* stream
  * reduction) and the plain nn.Linear maps of gcn.py:101-103 / modules.py:92-93.
  *
  *   y[m,n] = (sum_k A[m,k] * W[n,k]) * scale[n] + bias[n]
+ *   if add:   y += add[(m / add_row_div), n]          (f32, ld_add; the q-half of
+ *             ConcatAttention's first layer, attention.py:38-42, broadcast over K)
  *   if relu:  y = max(y, 0)
  *   if mul:   y *= mul[(m / mul_row_div), n]          (f32, ld_mul)
  *   if logit_w == NULL:  out[m,n] = y                 (out_dtype, ldo)
@@ -101,6 +103,9 @@ typedef struct {
   void* d_out;               /* [M,ldo] out_dtype, or [M,n_parts] f32        */
   int ldo;
   int out_dtype;             /* vqa_dtype of out (ignored in logit form)     */
+  const float* d_add;        /* optional additive row-broadcast operand      */
+  int ld_add;
+  int add_row_div;           /* row m reads add row m / add_row_div (>=1)    */
 } vqa_linear_args;
 
 int vqa_linear(const vqa_linear_args* args, void* stream);
@@ -201,7 +206,7 @@ int vqa_argmax_rows(const float* d_logits, int B, int A, int ld, int64_t* d_labe
 
 /* ------------------------------------------------------------------------
  * whole path: Wrapper.forward / forward_vqa (wrapper.py:64-74,113-118) for
- * encoder_type in {base, relation}, att_type 'new', predictor 'base'.
+ * encoder_type in {base, relation}, att_type in {'new', 'base'}, predictor 'base'.
  * All weight pointers are "prepared" device tensors (see
  * vqa_collection_b200/engine.py: bf16 or f32 copies, weight-norm scalars
  * expanded to per-column scale vectors, concatenated where noted).
@@ -227,6 +232,11 @@ typedef struct {
   const void* d_Wqq; const float* d_sqq; const float* d_bqq;     /* [2H,H]: W_q ; q_net */
   const float* d_wlin;       /* [H] = linear.weight_v * g/||v||              */
   float b_lin;
+  /* att_type 'base' (ConcatAttention, attention.py:18-51): att_concat = 1, then
+   *   d_Wv/d_sv = the v-half W1[:, :V] of sequence.0 and its scale (d_bv unused),
+   *   d_W1q [H,H] = the q-half W1[:, V:], d_b1 = sequence.0.bias (scale = d_sv),
+   *   d_Wqq/d_sqq/d_bqq = q_net alone [H,H], d_wlin/b_lin = sequence.2           */
+  int att_concat; const void* d_W1q; const float* d_b1;
   /* ReGAT layer (gcn.py), concatenated [4V,V] = [W0+W1; W2; Wa; Wb] */
   const void* d_Wg; const float* d_label_bias; const float* d_ba; const float* d_bb;
   /* bf16 merged form (vqa_graph_attention layout 1): [3V,V] = [W0+W1; W2; Wb^T Wa]; when

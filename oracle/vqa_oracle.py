@@ -46,6 +46,7 @@ class Config:
     num_labels: int = 12
     conv_layer: int = 1
     relation: bool = False          # encoder_type 'relation' vs 'base'
+    att_type: str = "new"           # 'new' = MultiplyAttention (CLI default main.py:67), 'base' = ConcatAttention
 
     def as_dict(self):
         return asdict(self)
@@ -58,6 +59,8 @@ SMALL = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200,
                relation=False)
 SMALL_REGAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200,
                      relation=True)
+SMALL_CONCAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, att_type="base")
+FULL_CONCAT = Config(att_type="base")
 
 
 def _uniform(gen, shape, bound):
@@ -97,9 +100,15 @@ def make_weights(cfg: Config, seed: int = 1111, sharpen_att: float = 100.0,
         w[prefix + ".weight_g"] = (torch.norm(v) * gscale).reshape(())
         w[prefix + ".weight_v"] = v
 
-    wn_linear("encoder.attention.W_v.main.0", H, V)
-    wn_linear("encoder.attention.W_q.main.0", H, H)
-    wn_linear("encoder.attention.linear", 1, H, sharpen_att)
+    if cfg.att_type == "new":
+        wn_linear("encoder.attention.W_v.main.0", H, V)
+        wn_linear("encoder.attention.W_q.main.0", H, H)
+        wn_linear("encoder.attention.linear", 1, H, sharpen_att)
+    else:                                          # ConcatAttention (attention.py:27-31)
+        wn_linear("encoder.attention.sequence.0", H, V + H)
+        # the concat logit layer sees un-gated ReLU features (much larger than the ⊙ product): a tenth
+        # of the sharpening gives a comparably peaked softmax
+        wn_linear("encoder.attention.sequence.2", 1, H, 0.1 * sharpen_att)
     wn_linear("encoder.q_net.main.0", H, H)
     wn_linear("predictor.v_net.main.0", H, V)
     wn_linear("predictor.classifier.main.0", 2 * H, H)
@@ -223,11 +232,27 @@ def multiply_attention(v, q, W, prefix="encoder.attention"):
     return torch.softmax(multiply_attention_logits(v, q, W, prefix), dim=1)
 
 
+def concat_attention_logits(v, q, W, prefix="encoder.attention"):
+    """ConcatAttention.logits (attention.py:33-40): w2·ReLU(W1 [v;q] + b1) + b2."""
+    vq = torch.cat((v, q.unsqueeze(1).repeat(1, v.size(1), 1)), 2)
+    w1 = wn_weight(W[prefix + ".sequence.0.weight_v"], W[prefix + ".sequence.0.weight_g"])
+    w2 = wn_weight(W[prefix + ".sequence.2.weight_v"], W[prefix + ".sequence.2.weight_g"])
+    hid = torch.relu(F.linear(vq, w1, W[prefix + ".sequence.0.bias"]))
+    return F.linear(hid, w2, W[prefix + ".sequence.2.bias"])          # [B,K,1]
+
+
+def attention_logits(v, q, W, prefix="encoder.attention"):
+    """set_att dispatch (attention.py:11-15) by the parameter names present"""
+    if prefix + ".sequence.0.weight_v" in W:
+        return concat_attention_logits(v, q, W, prefix)
+    return multiply_attention_logits(v, q, W, prefix)
+
+
 def base_encoder(batch, W):
     """BaseEncoder.base_forward (encoder.py:146-181) minus the caption keys."""
     v = batch["img"]
     q = question_embedding(batch["q"], W)
-    v_att = multiply_attention(v, q, W)
+    v_att = torch.softmax(attention_logits(v, q, W), dim=1)           # attention.py:51,86
     v = v_att * v
     qn = fcnet1(q, W, "encoder.q_net")
     return {"v": v, "q": qn, "v_att": v_att, "q_emb": q}

@@ -35,7 +35,7 @@ def build_reference(cfg: O.Config, W: dict):
                   v_dim=cfg.v_dim, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim,
                   decoder_hidden_dim=0, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2,
                   c_len=cfg.c_len, device="cpu", dropout=0.2, rnn_type="GRU",
-                  att_type="new", conv_layer=cfg.conv_layer, conv_type="corr")
+                  att_type=cfg.att_type, conv_layer=cfg.conv_layer, conv_type="corr")
     sd = {k: v for k, v in W.items() if not k.startswith("gcn.")}
     m.load_state_dict(sd, strict=True)
     if cfg.relation:
@@ -109,3 +109,5 @@ if __name__ == "__main__":
     run_model("regat_small", O.SMALL_REGAT, 8, 1111, 3001)
     run_model("updown_full", O.FULL, 4, 1111, 2002)
     run_model("regat_full", O.FULL_REGAT, 4, 1111, 3002)
+    run_model("concat_small", O.SMALL_CONCAT, 8, 1111, 4001)
+    run_model("concat_full", O.FULL_CONCAT, 4, 1111, 4002)

@@ -32,7 +32,7 @@ def margin_ok_mask(ref_logits, err_abs):
     return (s[:, -1] - s[:, -2]) > 4.0 * err_abs
 
 
-GOLDEN = ["updown_small", "regat_small", "updown_full", "regat_full"]
+GOLDEN = ["updown_small", "regat_small", "updown_full", "regat_full", "concat_small", "concat_full"]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

@@ -115,6 +115,23 @@ def test_unsupported_configurations_raise():
         set_model(decoder_type="base", device="cpu")
 
 
+def test_concat_attention_parameter_names():
+    """att_type='base' keeps the reference's names (encoder.attention.sequence.{0,2}.*)"""
+    from vqa_collection_b200.modules.wrapper import set_model
+    from vqa_collection_b200.engine import prepare_weights
+    cfg = O.SMALL_CONCAT
+    m = set_model(encoder_type="base", predictor_type="base", decoder_type="none", ntoken=cfg.ntoken, v_dim=cfg.v_dim,
+                  embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2,
+                  c_len=20, device="cpu", dropout=0.2, rnn_type="GRU", att_type="base", conv_layer=1, conv_type="corr")
+    W = O.make_weights(cfg, 1111)
+    assert set(m.state_dict().keys()) == set(W.keys())
+    m.load_state_dict(W, strict=True)
+    assert m.state_dict()["encoder.attention.sequence.0.weight_v"].shape == (cfg.hidden_dim, cfg.v_dim + cfg.hidden_dim)
+    P = prepare_weights(W, torch.float32, "cpu", False)
+    assert P["att_concat"] and P["Wv"].shape == (cfg.hidden_dim, cfg.v_dim) and P["W1q"].shape == (cfg.hidden_dim,) * 2
+    assert torch.equal(torch.cat([P["Wv"], P["W1q"]], 1), W["encoder.attention.sequence.0.weight_v"])
+
+
 def test_prepare_weights_layout():
     from vqa_collection_b200.engine import prepare_weights, weight_norm_scale
     cfg = O.SMALL_REGAT

@@ -22,7 +22,8 @@ def _relerr(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 
-@pytest.mark.parametrize("name", ["updown_small", "regat_small", "updown_full", "regat_full"])
+@pytest.mark.parametrize("name", ["updown_small", "regat_small", "updown_full", "regat_full", "concat_small",
+                                  "concat_full"])
 def test_forward_matches_reference(golden_dir, name):
     z, meta = _load(golden_dir, name)
     cfg = O.Config(**meta["cfg"])
@@ -45,13 +46,14 @@ def test_forward_matches_reference(golden_dir, name):
         assert np.array_equal(batch["graph"].numpy().astype(np.uint8), z["graph"])
 
 
-def test_attention_logits_match_reference(golden_dir):
-    z, meta = _load(golden_dir, "updown_full")
+@pytest.mark.parametrize("name", ["updown_full", "concat_full"])
+def test_attention_logits_match_reference(golden_dir, name):
+    z, meta = _load(golden_dir, name)
     cfg = O.Config(**meta["cfg"])
     W = O.make_weights(cfg, meta["wseed"])
     batch = O.make_batch(cfg, meta["B"], meta["bseed"])
     with torch.no_grad():
-        lg = O.multiply_attention_logits(batch["img"], torch.from_numpy(z["q_emb"]), W)
+        lg = O.attention_logits(batch["img"], torch.from_numpy(z["q_emb"]), W)
     assert _relerr(lg.numpy()[:, :, 0], z["att_logits"]) < 1e-5
 
 

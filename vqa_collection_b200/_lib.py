@@ -27,6 +27,7 @@ class LinearArgs(C.Structure):
         ("d_mul", c_void_p), ("ld_mul", c_int), ("mul_row_div", c_int),
         ("d_logit_w", c_void_p),
         ("d_out", c_void_p), ("ldo", c_int), ("out_dtype", c_int),
+        ("d_add", c_void_p), ("ld_add", c_int), ("add_row_div", c_int),
     ]
 
 
@@ -71,6 +72,7 @@ class ForwardArgs(C.Structure):
         ("d_Wv", c_void_p), ("d_sv", c_void_p), ("d_bv", c_void_p),
         ("d_Wqq", c_void_p), ("d_sqq", c_void_p), ("d_bqq", c_void_p),
         ("d_wlin", c_void_p), ("b_lin", c_float),
+        ("att_concat", c_int), ("d_W1q", c_void_p), ("d_b1", c_void_p),
         ("d_Wg", c_void_p), ("d_label_bias", c_void_p), ("d_ba", c_void_p), ("d_bb", c_void_p),
         ("d_Wg3", c_void_p), ("d_wvec", c_void_p), ("gat_c0", c_float), ("d_label_bias_lp", c_void_p),
         ("d_Wvn", c_void_p), ("d_svn", c_void_p), ("d_bvn", c_void_p),

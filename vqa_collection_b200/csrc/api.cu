@@ -73,6 +73,7 @@ static int linear_dispatch(const vqa_linear_args& a, cudaStream_t s) {
   VQA_REQUIRE(a.d_A && a.d_W && a.d_out, "vqa_linear: NULL pointer");
   VQA_REQUIRE(a.dtype == VQA_F32 || a.dtype == VQA_BF16, "vqa_linear: dtype=%d", a.dtype);
   VQA_REQUIRE(a.d_mul == nullptr || a.mul_row_div >= 1, "vqa_linear: mul_row_div must be >= 1");
+  VQA_REQUIRE(a.d_add == nullptr || a.add_row_div >= 1, "vqa_linear: add_row_div must be >= 1");
   if (a.dtype == VQA_BF16 && !force_simt()) return linear_tc(a, s);
   return linear_simt(a, s);
 }
@@ -307,16 +308,33 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
   if ((rc = gru_last_state(g, s))) return rc;
   // 2. [W_q ; q_net] (attention.py:71, encoder.py:169): qq = ReLU(h Wqqᵀ s + b) f32 [B,2H]
   vqa_linear_args l{};
-  l.d_A = w.h_lp; l.lda = a.H; l.d_W = a.d_Wqq; l.ldw = a.H; l.M = a.B; l.N = 2 * a.H; l.K = a.H; l.dtype = a.dtype;
-  l.d_scale = a.d_sqq; l.d_bias = a.d_bqq; l.relu = 1; l.mul_row_div = 1;
-  l.d_out = w.qq; l.ldo = 2 * a.H; l.out_dtype = VQA_F32;
-  if ((rc = linear_dispatch(l, s))) return rc;
-  // 3. W_v projection fused with ⊙Qp and the 1-wide logit layer (attention.py:70-75)
+  if (!a.att_concat) {
+    l.d_A = w.h_lp; l.lda = a.H; l.d_W = a.d_Wqq; l.ldw = a.H; l.M = a.B; l.N = 2 * a.H; l.K = a.H; l.dtype = a.dtype;
+    l.d_scale = a.d_sqq; l.d_bias = a.d_bqq; l.relu = 1; l.mul_row_div = 1;
+    l.d_out = w.qq; l.ldo = 2 * a.H; l.out_dtype = VQA_F32;
+    if ((rc = linear_dispatch(l, s))) return rc;
+  } else {
+    // ConcatAttention (attention.py:38-42): W1[v;q] = W1v v + W1q q, so the q-half is one [B,H] GEMM
+    // (no ReLU) that enters the W_v GEMM as an additive row-broadcast operand; q_net separately.
+    VQA_REQUIRE(a.d_W1q && a.d_b1, "vqa_forward: att_concat needs d_W1q and d_b1");
+    l.d_A = w.h_lp; l.lda = a.H; l.d_W = a.d_W1q; l.ldw = a.H; l.M = a.B; l.N = a.H; l.K = a.H; l.dtype = a.dtype;
+    l.d_scale = a.d_sv; l.d_bias = a.d_b1; l.relu = 0; l.mul_row_div = 1;
+    l.d_out = w.qq; l.ldo = 2 * a.H; l.out_dtype = VQA_F32;
+    if ((rc = linear_dispatch(l, s))) return rc;
+    l = vqa_linear_args{};
+    l.d_A = w.h_lp; l.lda = a.H; l.d_W = a.d_Wqq; l.ldw = a.H; l.M = a.B; l.N = a.H; l.K = a.H; l.dtype = a.dtype;
+    l.d_scale = a.d_sqq; l.d_bias = a.d_bqq; l.relu = 1; l.mul_row_div = 1;
+    l.d_out = w.qq + a.H; l.ldo = 2 * a.H; l.out_dtype = VQA_F32;
+    if ((rc = linear_dispatch(l, s))) return rc;
+  }
+  // 3. W_v projection fused with ⊙Qp (or + the q-half) and the 1-wide logit layer (attention.py:70-75 / :38-42)
   const int pw = part_width(a.dtype);
   const int n_parts = (a.H + pw - 1) / pw;
   l = vqa_linear_args{};
   l.d_A = a.d_img; l.lda = a.V; l.d_W = a.d_Wv; l.ldw = a.V; l.M = a.B * a.K; l.N = a.H; l.K = a.V; l.dtype = a.dtype;
-  l.d_scale = a.d_sv; l.d_bias = a.d_bv; l.relu = 1; l.d_mul = w.qq; l.ld_mul = 2 * a.H; l.mul_row_div = a.K;
+  l.d_scale = a.d_sv; l.relu = 1; l.mul_row_div = 1;
+  if (!a.att_concat) { l.d_bias = a.d_bv; l.d_mul = w.qq; l.ld_mul = 2 * a.H; l.mul_row_div = a.K; }
+  else { l.d_add = w.qq; l.ld_add = 2 * a.H; l.add_row_div = a.K; }
   l.d_logit_w = a.d_wlin; l.d_out = w.parts; l.ldo = n_parts; l.out_dtype = VQA_F32;
   if ((rc = linear_dispatch(l, s))) return rc;
   // 4. softmax over K + weighted sum (attention.py:86, encoder.py:166, predictor.py:85)

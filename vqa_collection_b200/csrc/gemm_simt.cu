@@ -12,6 +12,7 @@ constexpr int SBM = 128, SBN = 128, SBK = 16, STHREADS = 256;
 struct Epilogue {
   const float* scale; const float* bias; int relu;
   const float* mul; int ld_mul; int mul_row_div;
+  const float* add; int ld_add; int add_row_div;
   const float* logit_w;
   void* out; int ldo; int out_dtype; int n_parts;
 };
@@ -75,6 +76,7 @@ linear_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, in
         float y = acc[i][j];
         if (ep.scale) y *= ep.scale[n];
         if (ep.bias) y += ep.bias[n];
+        if (ep.add) y += ep.add[(size_t)(m / ep.add_row_div) * ep.ld_add + n];
         if (ep.relu) y = fmaxf(y, 0.f);
         if (ep.mul) y *= ep.mul[(size_t)(m / ep.mul_row_div) * ep.ld_mul + n];
         if (ep.logit_w) {
@@ -103,7 +105,7 @@ int linear_simt(const vqa_linear_args& a, cudaStream_t s) {
               "vqa_linear(simt): A/W rows must be 16-byte aligned (lda=%d ldw=%d)", a.lda, a.ldw);
   if (a.M == 0 || a.N == 0) return VQA_OK;
   Epilogue ep{a.d_scale, a.d_bias, a.relu, a.d_mul, a.ld_mul, a.mul_row_div > 0 ? a.mul_row_div : 1,
-              a.d_logit_w, a.d_out, a.ldo, a.out_dtype, (a.N + SBN - 1) / SBN};
+              a.d_add, a.ld_add, a.add_row_div > 0 ? a.add_row_div : 1, a.d_logit_w, a.d_out, a.ldo, a.out_dtype, (a.N + SBN - 1) / SBN};
   dim3 grid((a.N + SBN - 1) / SBN, (a.M + SBM - 1) / SBM);
   if (a.dtype == VQA_BF16)
     linear_simt_kernel<__nv_bfloat16><<<grid, STHREADS, 0, s>>>(

@@ -43,6 +43,7 @@ struct Params {
   int M, N, K;
   const float* scale; const float* bias; int relu;
   const float* mul; int ld_mul; int mul_row_div;
+  const float* add; int ld_add; int add_row_div;
   const float* logit_w;
   void* out; int ldo; int out_bf16; int n_parts;
   int tiles_m, tiles_n;
@@ -153,6 +154,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row < p.M;
       const float* mul_row = p.mul ? p.mul + (size_t)((row_ok ? row : 0) / p.mul_row_div) * p.ld_mul : nullptr;
       const bool mul_vec = p.mul && ((p.ld_mul & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mul) & 15) == 0);
+      const float* add_row = p.add ? p.add + (size_t)((row_ok ? row : 0) / p.add_row_div) * p.ld_add : nullptr;
+      const bool add_vec = p.add && ((p.ld_add & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.add) & 15) == 0);
       float part = 0.f;
       const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -163,12 +166,25 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int nbase = n0 + c0;
         if (nbase >= p.N) continue;
         float y[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = fmaf(__uint_as_float(v[j]), ps[c0 + j], ps[BN + c0 + j]);
-          y[j] = p.relu ? fmaxf(t, 0.f) : t;
-        }
         const bool full = nbase + 32 <= p.N;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), ps[c0 + j], ps[BN + c0 + j]);
+        if (add_row) {
+          if (add_vec && full) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(add_row + nbase) + j4);
+              y[4 * j4] += a4.x; y[4 * j4 + 1] += a4.y; y[4 * j4 + 2] += a4.z; y[4 * j4 + 3] += a4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nbase + j < p.N) y[j] += __ldg(add_row + nbase + j);
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+        }
         if (mul_row) {
           if (mul_vec && full) {
 #pragma unroll
@@ -273,6 +289,7 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.scale = a.d_scale; p.bias = a.d_bias; p.relu = a.relu;
   p.mul = a.d_mul; p.ld_mul = a.ld_mul; p.mul_row_div = a.mul_row_div > 0 ? a.mul_row_div : 1;
+  p.add = a.d_add; p.ld_add = a.ld_add; p.add_row_div = a.add_row_div > 0 ? a.add_row_div : 1;
   p.logit_w = a.d_logit_w; p.out = a.d_out; p.ldo = a.ldo; p.out_bf16 = (a.out_dtype == VQA_BF16);
   p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
   auto kern = linear_tc_kernel<BN>;

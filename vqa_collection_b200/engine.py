@@ -5,7 +5,7 @@
 q_net concatenated, the four ReGAT maps concatenated) and a workspace, and runs
 ``vqa_forward`` (include/vqa_b200.h) — the B200 replacement for
 ``Wrapper.forward`` / ``forward_vqa`` (wrapper.py:64-74,113-118) with
-encoder_type in {base, relation}, att_type 'new', predictor 'base'.
+encoder_type in {base, relation}, att_type in {'new', 'base'}, predictor 'base'.
 
 Weights arrive under the reference's parameter names, e.g. from
 ``Wrapper.state_dict()`` plus the unregistered GCN tensors as ``gcn.{i}.*``.
@@ -76,14 +76,23 @@ def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_lay
         v, g, b = f32(W[prefix + ".weight_v"]), f32(W[prefix + ".weight_g"]), f32(W[prefix + ".bias"])
         return v, weight_norm_scale(v, g), b
 
-    v, s, b = wn("encoder.attention.W_v.main.0")
-    P["Wv"], P["sv"], P["bv"] = dev(v, dtype), dev(torch.full((v.shape[0],), s)), dev(b)
-    vq, sq, bq = wn("encoder.attention.W_q.main.0")
     vn, sn, bn = wn("encoder.q_net.main.0")
-    P["Wqq"] = dev(torch.cat([vq, vn], 0), dtype)
-    P["sqq"] = dev(torch.cat([torch.full((vq.shape[0],), sq), torch.full((vn.shape[0],), sn)]))
-    P["bqq"] = dev(torch.cat([bq, bn]))
-    vl, sl, bl = wn("encoder.attention.linear")
+    P["att_concat"] = "encoder.attention.sequence.0.weight_v" in W
+    if not P["att_concat"]:                      # MultiplyAttention (attention.py:54-86)
+        v, s, b = wn("encoder.attention.W_v.main.0")
+        P["Wv"], P["sv"], P["bv"] = dev(v, dtype), dev(torch.full((v.shape[0],), s)), dev(b)
+        vq, sq, bq = wn("encoder.attention.W_q.main.0")
+        P["Wqq"] = dev(torch.cat([vq, vn], 0), dtype)
+        P["sqq"] = dev(torch.cat([torch.full((vq.shape[0],), sq), torch.full((vn.shape[0],), sn)]))
+        P["bqq"] = dev(torch.cat([bq, bn]))
+        vl, sl, bl = wn("encoder.attention.linear")
+    else:                                        # ConcatAttention (attention.py:18-51): split W1 = [W1v | W1q]
+        v, s, b = wn("encoder.attention.sequence.0")
+        Vd = v.shape[1] - H
+        P["Wv"], P["sv"], P["bv"] = dev(v[:, :Vd], dtype), dev(torch.full((v.shape[0],), s)), dev(torch.zeros(v.shape[0]))
+        P["W1q"], P["b1"] = dev(v[:, Vd:], dtype), dev(b)
+        P["Wqq"], P["sqq"], P["bqq"] = dev(vn, dtype), dev(torch.full((vn.shape[0],), sn)), dev(bn)
+        vl, sl, bl = wn("encoder.attention.sequence.2")
     P["wlin"] = dev((vl * sl).reshape(-1))
     P["b_lin"] = float(bl.reshape(-1)[0])
     v, s, b = wn("predictor.v_net.main.0")
@@ -162,6 +171,8 @@ class VQAEngine:
                      "Wvn", "svn", "bvn", "Wc0", "sc0", "bc0", "Wc1", "sc1", "bc1"):
             setattr(a, "d_" + name, P[name].data_ptr())
         a.b_lin = P["b_lin"]
+        if P["att_concat"]:
+            a.att_concat, a.d_W1q, a.d_b1 = 1, P["W1q"].data_ptr(), P["b1"].data_ptr()
         if "wx_packed" in P:
             a.d_wx_packed, a.d_wh_packed, a.d_bias_packed = (P["wx_packed"].data_ptr(), P["wh_packed"].data_ptr(),
                                                              P["bias_packed"].data_ptr())

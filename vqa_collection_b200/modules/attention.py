@@ -63,16 +63,53 @@ class MultiplyAttention(nn.Module):
 class ConcatAttention(nn.Module):
     """softmax_K( w2 · ReLU(W1 [v;q] + b1) + b2 )   (attention.py:18-51, att_type='base').
 
-    Parameters are kept under the reference's names; the kernel path needs an additive
-    row-broadcast epilogue operand (the q-half of W1) that vqa_linear does not have yet."""
+    W1 [v;q] = W1[:, :V] v + W1[:, V:] q: the q-half is ONE [B,H] GEMM (not K copies of q);
+    it enters the v-half GEMM as an additive row-broadcast epilogue operand, and the 1-wide
+    second layer is that GEMM's row-reduction epilogue — like MultiplyAttention, the
+    [B,K,H] hidden layer never reaches HBM.  Parameters keep the reference's names."""
 
     def __init__(self, v_dim, q_dim, hidden_dim):
         super().__init__()
         self.sequence = nn.Sequential(wn_linear(v_dim + q_dim, hidden_dim), nn.ReLU(), wn_linear(hidden_dim, 1))
+        self.v_dim = v_dim
+        self._cache = PreparedCache()
+
+    @property
+    def linear(self):                                   # the logit layer, same role as MultiplyAttention.linear
+        return self.sequence[2]
+
+    def _prepared(self, dtype):
+        l0, l2 = self.sequence[0], self.sequence[2]
+
+        def build():
+            V = self.v_dim
+            v = l0.weight_v.detach()
+            s1 = weight_norm_scale(l0.weight_v, l0.weight_g)
+            H = v.shape[0]
+            sv = torch.full((H,), s1, dtype=torch.float32, device=v.device)
+            wlin = (l2.weight_v.detach().float().reshape(-1) * weight_norm_scale(l2.weight_v, l2.weight_g)).contiguous()
+            return (v[:, :V].to(dtype).contiguous(), v[:, V:].to(dtype).contiguous(), sv,
+                    l0.bias.detach().float().contiguous(), wlin)
+        return self._cache.get(("concat", dtype), (l0.weight_v, l0.weight_g, l0.bias, l2.weight_v, l2.weight_g), build)
+
+    def logit_parts(self, v, q):
+        """→ (parts f32 [B*K, n_parts], x in compute dtype [B,K,V])"""
+        _no_training(self)
+        dtype = compute_dtype()
+        B, K, V = v.shape
+        x = as_compute(v, dtype)
+        W1v, W1q, sv, b1, wlin = self._prepared(dtype)
+        qadd = ops.linear(as_compute(q, dtype), W1q, sv, b1, relu=False, out_dtype=torch.float32)     # [B,H]
+        parts = ops.linear(x.view(B * K, V), W1v, sv, None, relu=True, add=qadd, add_row_div=K, logit_w=wlin)
+        return parts, x
 
     def logits(self, v, q):
-        raise NotImplementedError("att_type='base' (ConcatAttention) is not on the accelerated path yet; "
-                                  "use att_type='new' (the CLI default, main.py:67)")
+        parts, _ = self.logit_parts(v, q)
+        B, K = v.shape[0], v.shape[1]
+        return (parts.sum(1) + self.linear.bias.detach().float()).view(B, K, 1)
 
     def forward(self, v, q):
-        return self.logits(v, q)
+        """v [batch, num_objs, v_dim], q [batch, q_dim] → [batch, num_objs, 1] (f32)"""
+        parts, x = self.logit_parts(v, q)
+        att, _, _ = ops.attention_pool(parts, float(self.linear.bias.detach()), x, True, False, False)
+        return att.unsqueeze(2)

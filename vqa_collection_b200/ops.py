@@ -104,7 +104,7 @@ def linear_part_width(dtype: torch.dtype) -> int:
 
 
 def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, logit_w=None,
-           out_dtype=None, N=None):
+           out_dtype=None, N=None, add=None, add_row_div=1):
     """Fused weight-normed linear layer (modules.py:13-60), see vqa_linear in the header.
 
     A [M,K], W [N_rows,K] (same dtype); returns [M,N] (out_dtype) or, with ``logit_w``,
@@ -133,6 +133,11 @@ def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, log
         a.d_mul, a.ld_mul, a.mul_row_div = mul.data_ptr(), mul.stride(0), int(mul_row_div)
     else:
         a.mul_row_div = 1
+    if add is not None:
+        _require(add, torch.float32, "add")
+        a.d_add, a.ld_add, a.add_row_div = add.data_ptr(), add.stride(0), int(add_row_div)
+    else:
+        a.add_row_div = 1
     if logit_w is not None:
         pw = lib.vqa_linear_part_width(code)
         n_parts = (N + pw - 1) // pw
