@@ -84,8 +84,8 @@ int vqa_cast_bf16_to_f32(const void* d_src, float* d_dst, size_t n, void* stream
  *   else: out_f32[m * n_parts + p] = sum_{n in part p} y * logit_w[n]
  *         with n_parts = ceil(N / vqa_linear_part_width(dtype))
  *
- * dtype VQA_BF16: A, W are bf16, K % 64 == 0, lda/ldw % 8 == 0, 16-byte aligned
- * bases (TMA); tcgen05.mma 128xBN tiles with TMEM accumulators.
+ * dtype VQA_BF16: A, W are bf16, lda/ldw % 8 == 0, 16-byte aligned bases (TMA; a K
+ * tail is zero-filled); tcgen05.mma 128xBN tiles with TMEM accumulators.
  * dtype VQA_F32 : A, W are f32, K % 16 == 0; FFMA tiles.
  * ---------------------------------------------------------------------- */
 typedef struct {
@@ -106,6 +106,14 @@ typedef struct {
   const float* d_add;        /* optional additive row-broadcast operand      */
   int ld_add;
   int add_row_div;           /* row m reads add row m / add_row_div (>=1)    */
+  /* training-step forms (backward GEMMs on the same row-major tensors, no transposes):
+   *   trans_w: W is given as [K, N] row-major (ldw): y = A * W        e.g. dX = dY * W_fwd
+   *   trans_a: A is given as [K, M] row-major (lda): y = A^T * W      e.g. dW = dY^T * X
+   *            (trans_a needs trans_w).  bf16: K need not be a multiple of 64 (TMA zero fill).
+   *   mask:    y = (mask[m,n] > 0) ? y : 0, applied last (after relu and mul): the backward
+   *            of a ReLU whose saved OUTPUT is `mask` (mask_dtype, ld_mask)               */
+  int trans_a, trans_w;
+  const void* d_mask; int ld_mask; int mask_dtype;
 } vqa_linear_args;
 
 int vqa_linear(const vqa_linear_args* args, void* stream);

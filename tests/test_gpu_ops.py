@@ -242,6 +242,45 @@ def test_attention_pool(ops, dtype, B, K, V, P):
     assert none is None and relerr(vsum2, want_v.sum(1)) < TOL[dtype]
 
 
+# ---------------------------------------------------------------------------- backward GEMM forms
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(512, 2048, 3129), (1000, 304, 520), (36 * 64, 1024, 2048)])
+def test_linear_trans_w_is_dX(ops, dtype, M, N, K):
+    """dX[m,n] = Σ_k dY[m,k]·W[k,n]: W read as stored by the forward ([out=K, in=N] row-major), K tail zero-filled"""
+    g = torch.Generator().manual_seed(M + N + K)
+    ld = (K + 7) // 8 * 8
+    dY = torch.zeros((M, ld))
+    dY[:, :K] = torch.randn((M, K), generator=g)
+    dY[:, K:] = 7.0                                            # padding must never be read
+    W = torch.randn((K, N), generator=g) / K ** 0.5
+    saved = torch.relu(torch.randn((M, N), generator=g))       # ReLU output of the previous layer
+    acc = torch.randn((M, N), generator=g)
+    dYd, Wd = dY.to(dtype).cuda(), W.to(dtype).cuda()
+    want = (dYd[:, :K].float().cpu().double() @ Wd.float().cpu().double()) * 0.37 + acc.double()
+    want = torch.where(saved > 0, want, torch.zeros_like(want))
+    scale = torch.full((N,), 0.37).cuda()
+    got = ops.linear(dYd[:, :K], Wd, scale, None, trans_w=True, add=acc.cuda(), mask=saved.to(dtype).cuda(),
+                     out_dtype=torch.float32)
+    assert got.shape == (M, N)
+    assert relerr(got, want) < (1e-5 if dtype == torch.float32 else 2e-3)   # operands already rounded: only accumulation differs
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(3129, 2048, 512), (1024, 2048, 36 * 100), (200, 136, 77 * 8)])
+def test_linear_trans_a_is_dW(ops, dtype, M, N, K):
+    """dW[m,n] = Σ_k dY[k,m]·X[k,n]: both operands read row-major with the contraction as the row index"""
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    ldm = (M + 7) // 8 * 8
+    dY = torch.zeros((K, ldm))
+    dY[:, :M] = torch.randn((K, M), generator=g)
+    X = torch.randn((K, N), generator=g)
+    dYd, Xd = dY.to(dtype).cuda(), X.to(dtype).cuda()
+    want = dYd[:, :M].float().cpu().double().t() @ Xd.float().cpu().double()
+    got = ops.linear(dYd[:, :M], Xd, trans_a=True, trans_w=True, out_dtype=torch.float32)
+    assert got.shape == (M, N)
+    assert relerr(got, want) < (1e-5 if dtype == torch.float32 else 2e-3)
+
+
 # ---------------------------------------------------------------------------- argmax
 def test_argmax_lowest_index_on_ties(ops):
     g = torch.Generator().manual_seed(0)

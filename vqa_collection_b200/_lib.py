@@ -28,6 +28,8 @@ class LinearArgs(C.Structure):
         ("d_logit_w", c_void_p),
         ("d_out", c_void_p), ("ldo", c_int), ("out_dtype", c_int),
         ("d_add", c_void_p), ("ld_add", c_int), ("add_row_div", c_int),
+        ("trans_a", c_int), ("trans_w", c_int),
+        ("d_mask", c_void_p), ("ld_mask", c_int), ("mask_dtype", c_int),
     ]
 
 

@@ -13,11 +13,14 @@ struct Epilogue {
   const float* scale; const float* bias; int relu;
   const float* mul; int ld_mul; int mul_row_div;
   const float* add; int ld_add; int add_row_div;
+  const void* mask; int ld_mask; int mask_bf16;
   const float* logit_w;
   void* out; int ldo; int out_dtype; int n_parts;
 };
 
-template <typename T>
+// TA / TW: the operand is given with the contraction index as the ROW index ([K,M] / [K,N]
+// row-major) — the backward GEMMs of the training step; guarded scalar loads (parity path only).
+template <typename T, bool TA, bool TW>
 __global__ void __launch_bounds__(STHREADS)
 linear_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, int ldw, int M, int N,
                    int K, Epilogue ep) {
@@ -39,14 +42,37 @@ linear_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, in
   const T* ap = A + (size_t)(a_ok ? arow : 0) * lda + lk;
   const T* wp = W + (size_t)(w_ok ? wrow : 0) * ldw + lk;
 
+  const int tk = tid / 16, tc8 = (tid % 16) * 8;  // transposed loader: 16 k-rows x 16 chunks of 8 columns
   for (int k0 = 0; k0 < K; k0 += SBK) {
-    float av[8], wv[8];
-    load8(ap + k0, av);
-    load8(wp + k0, wv);
+    if constexpr (!TA) {
+      float av[8];
+      if (k0 + lk + 8 <= K) load8(ap + k0, av);
+      else
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      As[lk + i][lrow] = a_ok ? av[i] : 0.f;
-      Ws[lk + i][lrow] = w_ok ? wv[i] : 0.f;
+        for (int i = 0; i < 8; ++i) av[i] = (k0 + lk + i < K) ? Elem<T>::to_f(ap[k0 + i]) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) As[lk + i][lrow] = a_ok ? av[i] : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + tc8 + i, k = k0 + tk;
+        As[tk][tc8 + i] = (m < M && k < K) ? Elem<T>::to_f(A[(size_t)k * lda + m]) : 0.f;
+      }
+    }
+    if constexpr (!TW) {
+      float wv[8];
+      if (k0 + lk + 8 <= K) load8(wp + k0, wv);
+      else
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wv[i] = (k0 + lk + i < K) ? Elem<T>::to_f(wp[k0 + i]) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) Ws[lk + i][lrow] = w_ok ? wv[i] : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int n = n0 + tc8 + i, k = k0 + tk;
+        Ws[tk][tc8 + i] = (n < N && k < K) ? Elem<T>::to_f(W[(size_t)k * ldw + n]) : 0.f;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -79,6 +105,11 @@ linear_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, in
         if (ep.add) y += ep.add[(size_t)(m / ep.add_row_div) * ep.ld_add + n];
         if (ep.relu) y = fmaxf(y, 0.f);
         if (ep.mul) y *= ep.mul[(size_t)(m / ep.mul_row_div) * ep.ld_mul + n];
+        if (ep.mask) {
+          const float mk = ep.mask_bf16 ? __bfloat162float(((const __nv_bfloat16*)ep.mask)[(size_t)m * ep.ld_mask + n])
+                                        : ((const float*)ep.mask)[(size_t)m * ep.ld_mask + n];
+          if (!(mk > 0.f)) y = 0.f;
+        }
         if (ep.logit_w) {
           part = fmaf(y, ep.logit_w[n], part);
         } else if (ep.out_dtype == VQA_BF16) {
@@ -97,22 +128,29 @@ linear_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, in
   }
 }
 
+template <typename T>
+static void launch_simt(const vqa_linear_args& a, const Epilogue& ep, dim3 grid, cudaStream_t s) {
+  const T* A = (const T*)a.d_A;
+  const T* W = (const T*)a.d_W;
+  if (a.trans_a && a.trans_w) linear_simt_kernel<T, true, true><<<grid, STHREADS, 0, s>>>(A, a.lda, W, a.ldw, a.M, a.N, a.K, ep);
+  else if (a.trans_w) linear_simt_kernel<T, false, true><<<grid, STHREADS, 0, s>>>(A, a.lda, W, a.ldw, a.M, a.N, a.K, ep);
+  else linear_simt_kernel<T, false, false><<<grid, STHREADS, 0, s>>>(A, a.lda, W, a.ldw, a.M, a.N, a.K, ep);
+}
+
 int linear_simt(const vqa_linear_args& a, cudaStream_t s) {
-  VQA_REQUIRE(a.K % SBK == 0, "vqa_linear(simt): K=%d must be a multiple of %d", a.K, SBK);
   const int esz = (int)elem_size(a.dtype);
   VQA_REQUIRE((a.lda * esz) % 16 == 0 && (a.ldw * esz) % 16 == 0 &&
                   (uintptr_t)a.d_A % 16 == 0 && (uintptr_t)a.d_W % 16 == 0,
               "vqa_linear(simt): A/W rows must be 16-byte aligned (lda=%d ldw=%d)", a.lda, a.ldw);
+  VQA_REQUIRE(!(a.trans_a && !a.trans_w), "vqa_linear(simt): trans_a without trans_w is not built");
   if (a.M == 0 || a.N == 0) return VQA_OK;
   Epilogue ep{a.d_scale, a.d_bias, a.relu, a.d_mul, a.ld_mul, a.mul_row_div > 0 ? a.mul_row_div : 1,
-              a.d_add, a.ld_add, a.add_row_div > 0 ? a.add_row_div : 1, a.d_logit_w, a.d_out, a.ldo, a.out_dtype, (a.N + SBN - 1) / SBN};
+              a.d_add, a.ld_add, a.add_row_div > 0 ? a.add_row_div : 1,
+              a.d_mask, a.ld_mask, a.mask_dtype == VQA_BF16, a.d_logit_w, a.d_out, a.ldo, a.out_dtype,
+              (a.N + SBN - 1) / SBN};
   dim3 grid((a.N + SBN - 1) / SBN, (a.M + SBM - 1) / SBM);
-  if (a.dtype == VQA_BF16)
-    linear_simt_kernel<__nv_bfloat16><<<grid, STHREADS, 0, s>>>(
-        (const __nv_bfloat16*)a.d_A, a.lda, (const __nv_bfloat16*)a.d_W, a.ldw, a.M, a.N, a.K, ep);
-  else
-    linear_simt_kernel<float><<<grid, STHREADS, 0, s>>>((const float*)a.d_A, a.lda, (const float*)a.d_W,
-                                                        a.ldw, a.M, a.N, a.K, ep);
+  if (a.dtype == VQA_BF16) launch_simt<__nv_bfloat16>(a, ep, grid, s);
+  else launch_simt<float>(a, ep, grid, s);
   VQA_LAUNCH_CHECK();
   return VQA_OK;
 }

@@ -17,7 +17,10 @@
 //   warps 4-7 epilogue: tcgen05.ld 32x32b (thread = accumulator row), fused
 //             scale·acc + bias → ReLU → ⊙mul → {store | row-reduction with logit_w}
 // A is [M,K] row-major, W is [N,K] row-major (nn.Linear layout): both operands are
-// K-major, so no transposes are ever materialised.
+// K-major, so no transposes are ever materialised.  The backward GEMMs of the training step
+// (dX = dY·W, dW = dYᵀ·X) read the SAME row-major tensors with the contraction index as the
+// row index: `trans_a` / `trans_w` select MN-major operand tiles (TMA boxes {64 mn, 64 k-rows},
+// UMMA descriptors with the M/N-major bit) — again no transpose kernels.
 #include "tc_common.cuh"
 
 namespace vqa {
@@ -44,13 +47,14 @@ struct Params {
   const float* scale; const float* bias; int relu;
   const float* mul; int ld_mul; int mul_row_div;
   const float* add; int ld_add; int add_row_div;
+  const void* mask; int ld_mask; int mask_bf16;
   const float* logit_w;
   void* out; int ldo; int out_bf16; int n_parts;
   int tiles_m, tiles_n;
 };
 
 // ---- the kernel ----------------------------------------------------------------
-template <int BN>
+template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Params p) {
   using C = Cfg<BN>;
@@ -69,7 +73,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
-  const int num_kb = p.K / BK;
+  const int num_kb = (p.K + BK - 1) / BK;      // K tail: TMA zero-fills both operands
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -96,8 +100,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
           mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
-          tma_load_2d(sb, &tmW, full_bar(stage), kb * BK, n_blk * BN);
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
+          } else {                                   // tensor [K rows, M cols]: 64-wide atoms of 64 k-rows
+#pragma unroll
+            for (int h = 0; h < BM / 64; ++h)
+              tma_load_2d(sa + h * (BK * 128), &tmA, full_bar(stage), m_blk * BM + h * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmW, full_bar(stage), kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int h = 0; h < BN / 64; ++h)
+              tma_load_2d(sb + h * (BK * 128), &tmW, full_bar(stage), n_blk * BN + h * 64, kb * BK);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -105,7 +121,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN) | (A_MN ? IDESC_A_MN_MAJOR : 0u) | (B_MN ? IDESC_B_MN_MAJOR : 0u);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -116,11 +132,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
-          const uint64_t adesc = make_sw128_kmajor_desc(sa), bdesc = make_sw128_kmajor_desc(sb);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            // K-major: advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom (+2 in the addr>>4 field);
+            // MN-major: advance 16 k-rows = 2048 bytes, atoms BK*128 bytes apart
+            const uint64_t adesc = A_MN ? make_sw128_mnmajor_desc(sa + k * 2048, BK * 128, 1024)
+                                        : make_sw128_kmajor_desc(sa) + (uint64_t)(2 * k);
+            const uint64_t bdesc = B_MN ? make_sw128_mnmajor_desc(sb + k * 2048, BK * 128, 1024)
+                                        : make_sw128_kmajor_desc(sb) + (uint64_t)(2 * k);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));                     // smem slot reusable when these MMAs retire
           if (kb == num_kb - 1) umma_commit(tfull_bar(acc)); // accumulator complete
@@ -195,6 +215,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (nbase + j < p.N) y[j] *= __ldg(mul_row + nbase + j);
+          }
+        }
+        if (p.mask && row_ok) {                                    // backward of a ReLU: pass where the saved output > 0
+          if (p.mask_bf16) {
+            const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(p.mask) + (size_t)row * p.ld_mask + nbase;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nbase + j < p.N && !(__bfloat162float(mk[j]) > 0.f)) y[j] = 0.f;
+          } else {
+            const float* mk = reinterpret_cast<const float*>(p.mask) + (size_t)row * p.ld_mask + nbase;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nbase + j < p.N && !(__ldg(mk + j) > 0.f)) y[j] = 0.f;
           }
         }
         if (p.logit_w) {
@@ -278,21 +309,29 @@ int make_tensor_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long
   return VQA_OK;
 }
 
-template <int BN>
+// MN-major operand: the tensor is [K rows, MN cols] row-major; box = {64 mn, 64 k-rows}
+static int make_tensor_map_mn(CUtensorMap* map, const void* ptr, long long k_rows, long long mn_cols, long long ld) {
+  return make_tensor_map_bf16(map, ptr, k_rows, mn_cols, ld, BK);
+}
+
+template <int BN, bool A_MN, bool B_MN>
 static int launch(const vqa_linear_args& a, cudaStream_t s) {
   using C = Cfg<BN>;
   CUtensorMap tmA, tmW;
   int rc;
-  if ((rc = make_tensor_map_bf16(&tmA, a.d_A, a.M, a.K, a.lda, BM))) return rc;
-  if ((rc = make_tensor_map_bf16(&tmW, a.d_W, a.N, a.K, a.ldw, BN))) return rc;
+  if (A_MN) { if ((rc = make_tensor_map_mn(&tmA, a.d_A, a.K, a.M, a.lda))) return rc; }
+  else if ((rc = make_tensor_map_bf16(&tmA, a.d_A, a.M, a.K, a.lda, BM))) return rc;
+  if (B_MN) { if ((rc = make_tensor_map_mn(&tmW, a.d_W, a.K, a.N, a.ldw))) return rc; }
+  else if ((rc = make_tensor_map_bf16(&tmW, a.d_W, a.N, a.K, a.ldw, BN))) return rc;
   Params p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.scale = a.d_scale; p.bias = a.d_bias; p.relu = a.relu;
   p.mul = a.d_mul; p.ld_mul = a.ld_mul; p.mul_row_div = a.mul_row_div > 0 ? a.mul_row_div : 1;
   p.add = a.d_add; p.ld_add = a.ld_add; p.add_row_div = a.add_row_div > 0 ? a.add_row_div : 1;
+  p.mask = a.d_mask; p.ld_mask = a.ld_mask; p.mask_bf16 = (a.mask_dtype == VQA_BF16);
   p.logit_w = a.d_logit_w; p.out = a.d_out; p.ldo = a.ldo; p.out_bf16 = (a.out_dtype == VQA_BF16);
   p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
-  auto kern = linear_tc_kernel<BN>;
+  auto kern = linear_tc_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
     VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -305,22 +344,32 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
   return VQA_OK;
 }
 
+template <bool A_MN, bool B_MN>
+static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
+  // pick the widest N tile that still gives every SM a tile (small-M layers), else 256
+  const int tiles_m = (a.M + BM - 1) / BM;
+  const int sms = sm_count();
+  if (a.d_logit_w || tiles_m * ((a.N + 255) / 256) >= sms) return launch<256, A_MN, B_MN>(a, s);
+  if constexpr (!A_MN && !B_MN) {
+    if (tiles_m * ((a.N + 127) / 128) >= sms || a.N > 1024) return launch<128, A_MN, B_MN>(a, s);
+    return launch<64, A_MN, B_MN>(a, s);
+  } else {
+    return launch<128, A_MN, B_MN>(a, s);
+  }
+}
+
 }  // namespace tc
 
 int linear_tc_part_width() { return 256; }
 
 int linear_tc(const vqa_linear_args& a, cudaStream_t s) {
-  VQA_REQUIRE(a.K % tc::BK == 0, "vqa_linear(bf16): K=%d must be a multiple of %d", a.K, tc::BK);
   VQA_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0 && (uintptr_t)a.d_A % 16 == 0 && (uintptr_t)a.d_W % 16 == 0,
               "vqa_linear(bf16): TMA needs 16-byte aligned rows (lda=%d ldw=%d)", a.lda, a.ldw);
+  VQA_REQUIRE(!(a.trans_a && !a.trans_w), "vqa_linear(bf16): trans_a without trans_w is not built");
   if (a.M == 0) return VQA_OK;
-  if (a.d_logit_w) return tc::launch<256>(a, s);          // part width is fixed at 256 columns
-  // pick the widest N tile that still gives every SM a tile (small-M layers), else 256
-  const int tiles_m = (a.M + tc::BM - 1) / tc::BM;
-  const int sms = sm_count();
-  if (tiles_m * ((a.N + 255) / 256) >= sms) return tc::launch<256>(a, s);
-  if (tiles_m * ((a.N + 127) / 128) >= sms || a.N > 1024) return tc::launch<128>(a, s);
-  return tc::launch<64>(a, s);
+  if (a.trans_a) return tc::launch_bn<true, true>(a, s);       // dW = dYᵀ·X
+  if (a.trans_w) return tc::launch_bn<false, true>(a, s);      // dX = dY·W
+  return tc::launch_bn<false, false>(a, s);
 }
 
 }  // namespace vqa

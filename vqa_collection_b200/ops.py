@@ -40,7 +40,7 @@ def _require(t, dtype=None, name="tensor"):
         raise RuntimeError(f"vqa_collection_b200: {name} must be a CUDA tensor (no CPU fallback)")
     if dtype is not None and t.dtype != dtype:
         raise TypeError(f"vqa_collection_b200: {name} must be {dtype}, got {t.dtype}")
-    if not t.is_contiguous():
+    if not t.is_contiguous() and not (t.dim() == 2 and t.stride(1) == 1):      # row-strided 2-D views are fine
         raise RuntimeError(f"vqa_collection_b200: {name} must be contiguous")
     return t
 
@@ -104,20 +104,26 @@ def linear_part_width(dtype: torch.dtype) -> int:
 
 
 def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, logit_w=None,
-           out_dtype=None, N=None, add=None, add_row_div=1):
+           out_dtype=None, N=None, add=None, add_row_div=1, trans_a=False, trans_w=False, mask=None, out=None):
     """Fused weight-normed linear layer (modules.py:13-60), see vqa_linear in the header.
 
     A [M,K], W [N_rows,K] (same dtype); returns [M,N] (out_dtype) or, with ``logit_w``,
     the f32 row-reduction parts [M, n_parts].  ``N`` < W.shape[0] uses only the first N
-    rows of W (row-padded weights).
+    rows of W (row-padded weights).  Backward forms: ``trans_w`` → W is [K,N] (y = A·W),
+    ``trans_a`` (with trans_w) → A is [K,M] (y = Aᵀ·W); ``mask`` [M,N] zeroes y where mask ≤ 0.
     """
     lib = L.load()
     _require(A, None, "A")
     _require(W, A.dtype, "W")
-    if A.dim() != 2 or W.dim() != 2 or A.shape[1] != W.shape[1]:
+    if A.dim() != 2 or W.dim() != 2:
         raise ValueError(f"linear: shape mismatch A{tuple(A.shape)} W{tuple(W.shape)}")
-    M, K = A.shape
-    N = W.shape[0] if N is None else N
+    if trans_a and not trans_w:
+        raise ValueError("linear: trans_a needs trans_w")
+    M, K = (A.shape[1], A.shape[0]) if trans_a else A.shape
+    Kw, Nw = (W.shape[0], W.shape[1]) if trans_w else (W.shape[1], W.shape[0])
+    if K != Kw:
+        raise ValueError(f"linear: shape mismatch A{tuple(A.shape)} W{tuple(W.shape)} (trans_a={trans_a}, trans_w={trans_w})")
+    N = Nw if N is None else N
     code = dtype_code(A.dtype)
     for nm, t in (("scale", scale), ("bias", bias), ("logit_w", logit_w)):
         if t is not None:
@@ -127,6 +133,7 @@ def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, log
     a = L.LinearArgs()
     a.d_A, a.lda, a.d_W, a.ldw = A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0)
     a.M, a.N, a.K, a.dtype = M, N, K, code
+    a.trans_a, a.trans_w = int(bool(trans_a)), int(bool(trans_w))
     a.d_scale, a.d_bias, a.relu = _ptr(scale), _ptr(bias), int(bool(relu))
     if mul is not None:
         _require(mul, torch.float32, "mul")
@@ -138,15 +145,19 @@ def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, log
         a.d_add, a.ld_add, a.add_row_div = add.data_ptr(), add.stride(0), int(add_row_div)
     else:
         a.add_row_div = 1
+    if mask is not None:
+        _require(mask, None, "mask")
+        a.d_mask, a.ld_mask, a.mask_dtype = mask.data_ptr(), mask.stride(0), dtype_code(mask.dtype)
     if logit_w is not None:
         pw = lib.vqa_linear_part_width(code)
         n_parts = (N + pw - 1) // pw
         out = torch.empty((M, n_parts), dtype=torch.float32, device=A.device)
         a.d_logit_w, a.ldo, a.out_dtype = logit_w.data_ptr(), n_parts, L.VQA_F32
     else:
-        out_dtype = A.dtype if out_dtype is None else out_dtype
-        out = torch.empty((M, N), dtype=out_dtype, device=A.device)
-        a.ldo, a.out_dtype = N, dtype_code(out_dtype)
+        if out is None:
+            out_dtype = A.dtype if out_dtype is None else out_dtype
+            out = torch.empty((M, N), dtype=out_dtype, device=A.device)
+        a.ldo, a.out_dtype = out.stride(0), dtype_code(out.dtype)
     a.d_out = out.data_ptr()
     L.check(lib.vqa_linear(C.byref(a), _stream()))
     return out
