@@ -271,6 +271,49 @@ int vqa_forward(const vqa_forward_args* args, void* stream);
 /* number of kernels the last vqa_forward on this thread launched */
 int vqa_forward_last_launch_count(void);
 
+/* ------------------------------------------------------------------------
+ * training step of the Up-Down path (BASELINE config 4): forward with saved
+ * activations + BCE loss + full backward in one call.
+ * replaces Wrapper.get_loss (wrapper.py:76-105: forward, instance_bce_with_logits
+ * :25-29) followed by loss.backward() (train.py:108) for encoder 'base',
+ * att_type 'new', predictor 'base'.  The caller (train.py:109-111, unchanged)
+ * still owns gradient clipping and the Adamax step; with several GPUs the
+ * gradients are all-reduced between this call and the clip
+ * (vqa_collection_b200/parallel.py).
+ *
+ * Parameters are the f32 MASTER tensors under the reference's names and layouts;
+ * gradients are written (not accumulated) as f32 tensors of the same shapes.
+ * Layer order of p_v/p_g/p_b/g_v/g_g/g_b (weight_v, weight_g, bias):
+ *   0 encoder.attention.W_v.main.0 [H,V]   1 encoder.attention.W_q.main.0 [H,H]
+ *   2 encoder.attention.linear [1,H]       3 encoder.q_net.main.0 [H,H]
+ *   4 predictor.v_net.main.0 [H,V]         5 predictor.classifier.main.0 [2H,H]
+ *   6 predictor.classifier.main.3 [A,2H]
+ * dropout_att (attention.py:74) and dropout_cls (modules.py:45) are the train-
+ * mode dropout probabilities; masks come from a counter-based hash of `seed`.
+ * loss = mean(BCEWithLogits(logits, target)) * A, logits = the ReLU'd answers.
+ * ---------------------------------------------------------------------- */
+#define VQA_TRAIN_LAYERS 7
+typedef struct {
+  int B, K, V, H, A, T, E, ntoken_rows;
+  int dtype;                          /* compute dtype of operands/activations */
+  float dropout_att, dropout_cls;
+  unsigned long long seed;
+  const void* d_img;                  /* [B,K,V] dtype                         */
+  const int64_t* d_tokens;            /* [B,T]                                 */
+  const float* d_target;              /* [B,A] soft scores                     */
+  const float* p_emb;                 /* [ntoken_rows,E]; last row = padding   */
+  const float* p_w_ih; const float* p_w_hh; const float* p_b_ih; const float* p_b_hh;
+  const float* p_v[VQA_TRAIN_LAYERS]; const float* p_g[VQA_TRAIN_LAYERS]; const float* p_b[VQA_TRAIN_LAYERS];
+  float* g_emb; float* g_w_ih; float* g_w_hh; float* g_b_ih; float* g_b_hh;
+  float* g_v[VQA_TRAIN_LAYERS]; float* g_g[VQA_TRAIN_LAYERS]; float* g_b[VQA_TRAIN_LAYERS];
+  float* d_loss;                      /* [1]                                   */
+  float* d_logits;                    /* [B,A] f32 predictions                 */
+  void* d_workspace; size_t workspace_bytes;
+} vqa_train_args;
+
+size_t vqa_train_workspace_bytes(const vqa_train_args* args);
+int vqa_updown_train_step(const vqa_train_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -343,6 +343,25 @@ def forward_vqa(batch, W, cfg: Config):
     return score, label, target
 
 
+def get_loss(batch, W, cfg: Config):
+    """Wrapper.get_loss (wrapper.py:76-105) for the VQA head with dropout = identity:
+    instance_bce_with_logits (wrapper.py:25-29) = mean BCE-with-logits × number of answers."""
+    logits, _ = forward(batch, W, cfg)
+    target = batch["a"].to(logits.dtype)
+    loss = F.binary_cross_entropy_with_logits(logits, target) * target.size(1)
+    return loss, logits
+
+
+def loss_and_grads(batch, W, cfg: Config):
+    """What train.py:103,108 leave in ``.grad`` after get_loss + backward (torch autograd over the
+    restated forward; GCN tensors are not trainable in the reference)."""
+    Wg = {k: (v.detach().clone().requires_grad_(True) if not k.startswith("gcn.") else v) for k, v in W.items()}
+    loss, logits = get_loss(batch, Wg, cfg)
+    loss.backward()
+    grads = {k: v.grad for k, v in Wg.items() if not k.startswith("gcn.")}
+    return loss.detach(), logits.detach(), grads
+
+
 def to_dtype(W: dict, dtype):
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in W.items()}
 

@@ -72,6 +72,28 @@ def run_model(name, cfg, B, wseed, bseed):
     print(name, {k: v.shape for k, v in out.items()})
 
 
+def run_train(name, cfg, B, wseed, bseed, full_grads):
+    """Wrapper.get_loss + loss.backward() of the REAL reference in train mode with every nn.Dropout
+    set to p=0 / not in-place (the in-place dropout after ReLU breaks autograd in torch 2.x)."""
+    W = O.make_weights(cfg, wseed)
+    batch = O.make_batch(cfg, B, bseed)
+    m = build_reference(cfg, W).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p, mod.inplace = 0.0, False
+    ref_batch = {k: v for k, v in batch.items() if k not in ("bbox", "wh")}
+    loss, writes = m.get_loss(ref_batch)
+    loss.backward()
+    out = {"loss": np.array(loss.item(), dtype=np.float64), "score": np.array(writes["train/score"], dtype=np.float64)}
+    for k, p in m.named_parameters():
+        g = p.grad.detach().numpy().astype(np.float32)
+        out["norm:" + k] = np.array(np.linalg.norm(g.astype(np.float64)))
+        out["grad:" + k] = g if full_grads else g.reshape(-1)[::97].copy()
+    meta = dict(cfg=cfg.as_dict(), B=B, wseed=wseed, bseed=bseed, full_grads=full_grads, stride=1 if full_grads else 97)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array(repr(meta)), **out)
+    print(name, "loss", loss.item(), "params", len(out) // 2 - 1)
+
+
 def run_relation():
     W_, H_ = 640, 480
     boxes = O.make_boxes(48, 36, 4242, W_, H_, grid=True)
@@ -111,3 +133,5 @@ if __name__ == "__main__":
     run_model("regat_full", O.FULL_REGAT, 4, 1111, 3002)
     run_model("concat_small", O.SMALL_CONCAT, 8, 1111, 4001)
     run_model("concat_full", O.FULL_CONCAT, 4, 1111, 4002)
+    run_train("train_small", O.SMALL, 16, 1111, 5001, True)
+    run_train("train_full", O.FULL, 8, 1111, 5002, False)

@@ -39,7 +39,8 @@ def test_struct_layouts_match_header():
     from vqa_collection_b200 import _lib
     header = open(os.path.join(ROOT, "include", "vqa_b200.h")).read()
     for cname, cls in (("vqa_linear_args", _lib.LinearArgs), ("vqa_gru_args", _lib.GruArgs),
-                       ("vqa_graph_attention_args", _lib.GraphAttentionArgs), ("vqa_forward_args", _lib.ForwardArgs)):
+                       ("vqa_graph_attention_args", _lib.GraphAttentionArgs), ("vqa_forward_args", _lib.ForwardArgs),
+                       ("vqa_train_args", _lib.TrainArgs)):
         body = re.search(r"typedef struct \{([^}]*)\}\s*" + cname + ";", header).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
@@ -48,6 +49,7 @@ def test_struct_layouts_match_header():
             if not stmt:
                 continue
             for part in stmt.split(","):
+                part = re.sub(r"\[[^\]]*\]", "", part)                # array members: p_v[VQA_TRAIN_LAYERS]
                 names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", part.strip())[0])
         assert names == [f[0] for f in cls._fields_], cname
 
@@ -96,8 +98,10 @@ def test_drop_in_parameter_names_and_checkpoint_loading(enc):
         layer.load_state_dict({k[6:]: v for k, v in W.items() if k.startswith("gcn.0.")}, strict=True)
         names = m.reference_named_weights()
         assert set(names) == set(W)
-    with pytest.raises(NotImplementedError):
-        m.get_loss({})
+    assert m.train_step_supported() == (enc == "base")
+    if enc == "relation":
+        with pytest.raises(NotImplementedError):
+            m.get_loss({})
     m.train()
     with pytest.raises(NotImplementedError):                     # training path must not silently run eval math
         m.encoder.q_net(torch.zeros(2, cfg.hidden_dim))
@@ -247,3 +251,54 @@ def test_two_rank_sharded_forward_equals_unsharded(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+GLOO_TRAIN_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from oracle import vqa_oracle as O
+from vqa_collection_b200.parallel import shard_batch, FlatGradients, average_gradients_
+from vqa_collection_b200.training import param_names
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+cfg = O.SMALL
+W = O.make_weights(cfg, 1111)
+batch = O.make_batch(cfg, 12, 5)                    # equal shards: 6 + 6 rows
+_, _, full = O.loss_and_grads(batch, W, cfg)        # single-process gradients on the whole batch
+_, _, local = O.loss_and_grads(shard_batch(batch, world, rank), W, cfg)   # the CPU oracle stands in for the per-rank step
+names = param_names()
+fg = FlatGradients([tuple(W[n].shape) for n in names], "cpu")
+for v, n in zip(fg.views, names):
+    v.copy_(local[n])
+average_gradients_(fg.flat)                         # the exchange step (SUM + divide under gloo, AVG under NCCL)
+gmax = max(float(full[n].abs().max()) for n in names)
+for v, n in zip(fg.views, names):
+    ref = full[n]
+    if n == "encoder.attention.linear.bias":       # identically 0 up to rounding: the softmax is shift invariant
+        assert float(v.abs().max()) < 1e-5 * gmax and float(ref.abs().max()) < 1e-5 * gmax
+        continue
+    assert torch.allclose(v, ref, rtol=1e-4, atol=1e-6 * float(ref.abs().max()) + 1e-12), (n, float((v - ref).abs().max()))
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_rank_gradient_average_equals_single_process(tmp_path):
+    """config 4 exchange step on CPU: averaged shard gradients == gradients of the concatenated batch"""
+    script = tmp_path / "worker_train.py"
+    script.write_text(GLOO_TRAIN_WORKER)
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", OMP_NUM_THREADS="2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29532", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
+
+
+def test_flat_gradient_views():
+    from vqa_collection_b200.parallel import FlatGradients
+    shapes = [(3, 5), (), (7,), (2, 2, 2)]
+    fg = FlatGradients(shapes, "cpu")
+    assert [tuple(v.shape) for v in fg.views] == shapes and fg.matches(shapes, "cpu") and not fg.matches(shapes[:2], "cpu")
+    fg.views[2].fill_(3.0)
+    assert fg.flat.sum() == 21.0 and all(v.data_ptr() % 256 == fg.flat.data_ptr() % 256 for v in fg.views)

@@ -86,6 +86,25 @@ class ForwardArgs(C.Structure):
     ]
 
 
+TRAIN_LAYERS = 7
+_fp = C.c_void_p * TRAIN_LAYERS
+
+
+class TrainArgs(C.Structure):
+    _fields_ = [
+        ("B", c_int), ("K", c_int), ("V", c_int), ("H", c_int), ("A", c_int), ("T", c_int), ("E", c_int),
+        ("ntoken_rows", c_int), ("dtype", c_int),
+        ("dropout_att", c_float), ("dropout_cls", c_float), ("seed", C.c_ulonglong),
+        ("d_img", c_void_p), ("d_tokens", c_void_p), ("d_target", c_void_p),
+        ("p_emb", c_void_p), ("p_w_ih", c_void_p), ("p_w_hh", c_void_p), ("p_b_ih", c_void_p), ("p_b_hh", c_void_p),
+        ("p_v", _fp), ("p_g", _fp), ("p_b", _fp),
+        ("g_emb", c_void_p), ("g_w_ih", c_void_p), ("g_w_hh", c_void_p), ("g_b_ih", c_void_p), ("g_b_hh", c_void_p),
+        ("g_v", _fp), ("g_g", _fp), ("g_b", _fp),
+        ("d_loss", c_void_p), ("d_logits", c_void_p),
+        ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
 # every symbol include/vqa_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vqa_abi_version": (c_int, []),
@@ -106,6 +125,8 @@ SYMBOLS = {
     "vqa_forward_workspace_bytes": (c_size_t, [C.POINTER(ForwardArgs)]),
     "vqa_forward": (c_int, [C.POINTER(ForwardArgs), c_void_p]),
     "vqa_forward_last_launch_count": (c_int, []),
+    "vqa_train_workspace_bytes": (c_size_t, [C.POINTER(TrainArgs)]),
+    "vqa_updown_train_step": (c_int, [C.POINTER(TrainArgs), c_void_p]),
 }
 
 _lib = None

@@ -58,6 +58,8 @@ int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
 int cast_bf16_to_f32(const void*, float*, size_t, cudaStream_t);
 int graph_attention(const vqa_graph_attention_args&, cudaStream_t);
 int graph_attention_tc(const vqa_graph_attention_args&, cudaStream_t);
+size_t train_workspace_bytes(const vqa_train_args&);
+int updown_train_step(const vqa_train_args&, cudaStream_t);
 int gru_persistent(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
                    cudaStream_t);
 
@@ -384,6 +386,13 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
                                               cudaMemcpyDeviceToDevice, s));
   g_last_forward_launches = launch_count() - before;
   return VQA_OK;
+}
+
+size_t vqa_train_workspace_bytes(const vqa_train_args* args) { return args ? train_workspace_bytes(*args) : 0; }
+int vqa_updown_train_step(const vqa_train_args* args, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  VQA_REQUIRE(args, "vqa_updown_train_step: NULL args");
+  return updown_train_step(*args, (cudaStream_t)stream);
 }
 
 }  // extern "C"

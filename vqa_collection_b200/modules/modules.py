@@ -91,6 +91,12 @@ class FCNet(nn.Module):
     def linears(self):
         return [(i, m) for i, m in enumerate(self.main) if isinstance(m, nn.Linear)]
 
+    @property
+    def dropout_p(self):
+        """p of the nn.Dropout stages between the linears (modules.py:45,51); 0 without one"""
+        ps = [m.p for m in self.main if isinstance(m, nn.Dropout)]
+        return float(ps[0]) if ps else 0.0
+
     def prepared(self, dtype):
         return [prep_wn_linear(self._cache, m, dtype, tag=("wn", i)) for i, m in self.linears()]
 
@@ -112,8 +118,8 @@ class FCNet(nn.Module):
 def _no_training(module):
     if module.training and torch.is_grad_enabled():
         raise NotImplementedError(
-            "vqa_collection_b200 builds the forward (eval / no_grad) path; the training step "
-            "(BASELINE config 4) is not built yet — call model.eval() and torch.no_grad()")
+            "vqa_collection_b200: module-level forwards are the eval / no_grad path; gradients come from the fused "
+            "training step (Wrapper.get_loss → vqa_updown_train_step) — call model.eval() and torch.no_grad() here")
 
 
 class DotProduct(nn.Module):

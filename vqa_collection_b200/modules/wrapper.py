@@ -99,9 +99,34 @@ class Wrapper(nn.Module):
         predict = self.predictor(batch) if self.predictor else None
         return predict, caption
 
+    def train_step_supported(self):
+        """the fused training step covers encoder 'base' + att_type 'new' + predictor 'base' (BASELINE config 4)"""
+        from .attention import MultiplyAttention
+        from .encoder import BaseEncoder
+        return (type(self.encoder) is BaseEncoder and isinstance(self.encoder.attention, MultiplyAttention)
+                and isinstance(self.predictor, BasePredictor) and len(self.predictor.classifier.linears()) == 2
+                and self.generator is None)
+
     def get_loss(self, batch):
-        raise NotImplementedError("vqa_collection_b200: the training step (BASELINE config 4: backward kernels + NCCL "
-                                  "gradient all-reduce) is not built yet; this round covers the forward path")
+        """wrapper.py:76-105.  One C call runs forward + loss + backward (vqa_updown_train_step); the returned
+        loss carries the parameter gradients into ``loss.backward()`` (train.py:108).  With an initialised
+        torch.distributed group of > 1 ranks the gradients are averaged across ranks (NCCL all-reduce) before
+        ``backward`` returns, i.e. before the caller's clip_grad_norm_ (train.py:109) sees them."""
+        self.gradients = []
+        if not self.train_step_supported():
+            raise NotImplementedError("vqa_collection_b200: the training step is built for encoder_type='base', "
+                                      "att_type='new', predictor_type='base', cls_layer=2 (BASELINE config 4)")
+        from .. import compute_dtype, training
+        from .modules import as_compute
+        target = batch['a'].float().to(self.device)
+        img = as_compute(batch['img'].to(self.device), compute_dtype())
+        tokens = batch['q'].to(self.device)
+        loss_vqa, predict = training.updown_loss(self, img, tokens, target)
+        writes = {'train/loss': loss_vqa.item(),
+                  'train/score': compute_score(predict, target, self.device).sum().item()}
+        loss = torch.tensor(0, dtype=torch.float).to(self.device)
+        loss = loss + loss_vqa                       # use_mtl needs a generator too (wrapper.py:50)
+        return torch.mean(loss), writes
 
     def get_att(self, batch):
         batch = self.encoder(batch)
