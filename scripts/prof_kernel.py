@@ -1,4 +1,4 @@
-"""Launch one hot kernel a few times (for `ncu --set full`): python scripts/prof_kernel.py wv|pool|relation"""
+"""Launch one hot kernel a few times (for `ncu --set full`): python scripts/prof_kernel.py wv|pool|relation|gat|wide|gru|cls1"""
 import os
 import sys
 
@@ -28,5 +28,30 @@ elif which == "relation":
     boxes = torch.from_numpy(O.make_boxes(1 << 18, 36, 1)).to(dev)
     for _ in range(5):
         ops.relation_labels(boxes, 640, 480)
+elif which in ("gat", "wide", "gru", "cls1"):
+    from oracle import vqa_oracle as O
+    from vqa_collection_b200.engine import prepare_weights
+    cfg = O.FULL_REGAT
+    P = prepare_weights(O.make_weights(cfg, 1111), torch.bfloat16, dev, True)
+    x2 = torch.rand((B * K, V), generator=g).to(torch.bfloat16).to(dev)
+    if which == "wide":
+        for _ in range(4):
+            ops.linear(x2, P["Wg3"])
+    elif which == "gat":
+        Y = ops.linear(x2, P["Wg3"])
+        att = torch.softmax(torch.randn((B, K), device=dev), 1)
+        labels = ops.relation_labels(torch.from_numpy(O.make_boxes(B, K, 3)).to(dev), 640, 480)
+        for _ in range(4):
+            ops.graph_attention_merged(Y, x2, att, labels, P["wvec"], P["gat_c0"], P["label_bias_lp"], P["num_labels"], K,
+                                       False, True, False)
+    elif which == "gru":
+        q = torch.randint(0, cfg.ntoken, (B, 14), generator=g).to(dev)
+        packed = (P["wx_packed"], P["wh_packed"], P["bias_packed"])
+        for _ in range(4):
+            ops.gru_last_state(q, P["emb"], P["w_ih"], P["b_ih"], P["w_hh"], P["b_hh"], packed=packed)
+    else:
+        hid = torch.rand((B, 2 * H), generator=g).to(torch.bfloat16).to(dev)
+        for _ in range(4):
+            ops.linear(hid, P["Wc1"], P["sc1"], P["bc1"], relu=True, out_dtype=torch.float32)
 torch.cuda.synchronize()
 print("done", which)

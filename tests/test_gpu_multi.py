@@ -1,0 +1,76 @@
+"""Multi-GPU (one process per GPU, NCCL over NVLink) checks of the data-parallel paths.  Needs >= 2 GPUs
+(`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`); skipped on a single-GPU box."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+import vqa_collection_b200 as pkg
+from oracle import vqa_oracle as O
+from vqa_collection_b200.engine import VQAEngine
+from vqa_collection_b200.parallel import shard_batch, gather_rows
+from vqa_collection_b200 import training
+
+# ---- forward: sharded == unsharded, no data-path collective (SURVEY.md 8e)
+cfg = O.FULL
+W = O.make_weights(cfg, 1111)
+batch = O.make_batch(cfg, 256, 99)
+eng = VQAEngine(W, relation=False, precision="bf16", device=dev)
+full = eng.forward(batch["img"].to(dev), batch["q"].to(dev))
+loc = shard_batch(batch, world, rank)
+part = eng.forward(loc["img"].to(dev), loc["q"].to(dev))
+labels = gather_rows(part["label"], 256)
+assert torch.equal(labels, full["label"]), "sharded labels differ"
+logits = gather_rows(part["logits"], 256)
+assert torch.equal(logits, full["logits"]), "sharded logits differ"
+
+# ---- training: all-reduced shard gradients == single-process gradients of the concatenated batch
+names = training.param_names()
+tb = O.make_batch(cfg, 64 * world, 5)
+
+
+def grads_of(b, dp):
+    params = [W[n].to(dev).requires_grad_(True) for n in names]
+    training.set_process_group(None)
+    training._dp_disabled = not dp
+    loss, _ = training.UpDownTrainStep.apply(b["img"].float().to(dev), b["q"].to(dev), b["a"].float().to(dev), 0.0, 0.0, 1, *params)
+    loss.backward()
+    return [p.grad.clone() for p in params]
+
+
+single = grads_of(tb, False)                       # whole batch on every rank, no exchange
+dp = grads_of(shard_batch(tb, world, rank), True)  # shard per rank + NCCL average
+gmax = max(float(g.abs().max()) for g in single)
+for n, a, b in zip(names, dp, single):
+    err = float((a - b).abs().max())
+    assert err <= 2e-4 * max(float(b.abs().max()), 1e-3 * gmax), (n, err, float(b.abs().max()))
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_two_gpu_sharded_forward_and_gradient_allreduce(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = min(torch.cuda.device_count(), 8)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29541", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == n

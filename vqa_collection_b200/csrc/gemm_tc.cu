@@ -38,8 +38,9 @@ template <int BN> struct Cfg {
   static constexpr int TMEM_COLS = pow2_ge(2 * BN);
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
   static constexpr int PARAM_FLOATS = 2 * 3 * BN;            // 2 acc stages x (scale,bias,logit_w)
+  static constexpr int STAGE_OUT_FLOATS = 4 * 32 * 33;       // per epilogue warp: 32 rows x 32 cols (+1 pad) f32
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 256 /*barriers*/ +
-                                    PARAM_FLOATS * 4;
+                                    PARAM_FLOATS * 4 + STAGE_OUT_FLOATS * 4;
 };
 
 struct Params {
@@ -70,6 +71,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(base_ptr + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 4));
   float* params_smem = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE_BYTES + 256);
+  float* stage_out = params_smem + C::PARAM_FLOATS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.tiles_m * p.tiles_n;
@@ -246,17 +248,24 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) if (nbase + j < p.N) o[j] = __float2bfloat16_rn(y[j]);
             }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + nbase;
-            if (full && ((p.ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4)
-                reinterpret_cast<float4*>(o)[j4] = make_float4(y[4 * j4], y[4 * j4 + 1], y[4 * j4 + 2], y[4 * j4 + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (nbase + j < p.N) o[j] = y[j];
-            }
           }
+        }
+        if (!p.logit_w && !p.out_bf16) {
+          // f32 output: thread = row would scatter 4-byte stores over 32 rows per instruction; transpose the
+          // 32x32 chunk through shared memory so that every store instruction writes one 128-byte row segment
+          float* st = stage_out + q * (32 * 33);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) st[lane * 33 + j] = y[j];
+          __syncwarp();
+          const int row0 = m_blk * BM + q * 32;
+          const int n = nbase + lane;
+          float* o = reinterpret_cast<float*>(p.out) + (size_t)row0 * p.ldo + n;
+          if (n < p.N) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+              if (row0 + r < p.M) o[(size_t)r * p.ldo] = st[r * 33 + lane];
+          }
+          __syncwarp();
         }
       }
       if (p.logit_w && row_ok) reinterpret_cast<float*>(p.out)[(size_t)row * p.n_parts + n_blk] = part;

@@ -34,6 +34,7 @@ def param_names():
 _WS = {}
 _FLAT = {}
 _GROUP = None
+_dp_disabled = False          # tests: run a step without the exchange inside an initialised process group
 
 
 def set_process_group(group):
@@ -45,7 +46,7 @@ def set_process_group(group):
 
 def _dp_active():
     import torch.distributed as dist
-    return dist.is_available() and dist.is_initialized() and dist.get_world_size(_GROUP) > 1
+    return (not _dp_disabled) and dist.is_available() and dist.is_initialized() and dist.get_world_size(_GROUP) > 1
 
 
 def _workspace(lib, a, device):
