@@ -220,22 +220,42 @@ def main():
         ms_total = float(t.item())
     value = B * world * args.steps / (ms_total / 1e3)
 
-    # ---- e2e: host buffers in the reference wire format (f32 features), H2D + forward + D2H
+    # ---- e2e: host buffers in the reference wire format (pinned f32 features) through the C-ABI host entry
+    # point vqa_forward_host: host cores pack f32→bf16 chunk by chunk while the previous chunk's DMA is in
+    # flight → H2D → forward → answers D2H, all inside the timed region
     e2e_steps = max(3, min(args.steps, 20))
-    for _ in range(2):
-        eng.forward_host(host_img, host_tok, labels_h=host_lab)
-    barrier()
-    e0.record()
-    for _ in range(e2e_steps):
-        _, h2d, d2h = eng.forward_host(host_img, host_tok, labels_h=host_lab)
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+
+    RAW_PERIOD = 4      # hybrid staging: 3 of 4 chunks packed to bf16 by the host cores, 1 of 4 raw f32 + device cast
+
+    def time_host(pack):
+        for _ in range(2):
+            eng.forward_host(host_img, host_tok, labels_h=host_lab, pack_on_host=pack, raw_chunk_period=RAW_PERIOD)
+        barrier()
+        e0.record()
+        pending = None
+        for _ in range(e2e_steps):                    # two batches in flight: stage n+1 while n computes
+            nxt = eng.forward_host_async(host_img, host_tok, labels_h=host_lab, pack_on_host=pack,
+                                         raw_chunk_period=RAW_PERIOD)
+            if pending is not None:
+                pending.result()
+            pending = nxt
+        _, h2d_, d2h_ = pending.result()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, h2d_, d2h_
+
+    ms_e2e, h2d, d2h = time_host(args.precision == "bf16")
     e2e_value = B * world * e2e_steps / (ms_e2e / 1e3)
+    e2e_alt = None
+    if args.precision == "bf16":
+        ms_alt, h2d_alt, _ = time_host(False)
+        e2e_alt = {"value": B * world * e2e_steps / (ms_alt / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_alt,
+                   "ms_per_step": ms_alt / e2e_steps, "note": "f32 features over PCIe + device cast (no host packing)"}
 
     # ---- roofline of the dominant kernel (W_v projection fused with the attention logits),
     # timed alone with CUDA events on its launch stream
@@ -286,7 +306,11 @@ def main():
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                "note": "host f32 features (reference wire format) -> pinned H2D -> bf16 cast -> forward -> answers D2H"},
+                "host_pack_threads": os.cpu_count(), "raw_chunk_period": RAW_PERIOD, "batches_in_flight": 2,
+                "note": "vqa_forward_host_submit/_wait: pinned f32 host features (reference wire format) -> 3 of 4 "
+                        "64-image chunks packed to bf16 by the host cores, 1 of 4 sent as f32 and cast on the device, "
+                        "all pipelined with H2D -> forward -> answers D2H; batch n+1 is staged while batch n computes"},
+        "e2e_f32_over_pcie": e2e_alt,
         "gpu_launches": launches,
         "roofline": roof,
         "path_tflops_per_gpu": path_tflops,

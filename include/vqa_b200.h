@@ -272,6 +272,49 @@ int vqa_forward(const vqa_forward_args* args, void* stream);
 int vqa_forward_last_launch_count(void);
 
 /* ------------------------------------------------------------------------
+ * whole path from HOST buffers in the reference's wire format (the e2e leg).
+ * replaces the `.to(self.device)` copies inside the reference's forwards
+ * (encoder.py:153-156,265; predictor.py:82-83) + Wrapper.forward_vqa.
+ *   h_img    f32 [B,K,V] (dataset.py:96-104; pinned memory recommended)
+ *   h_tokens int64 [B,T];  h_labels u8 [B,K,K] or h_bbox f32 [B,K,4] (relation)
+ *   h_label  int64 [B] out (the answers); synchronises `stream` before returning
+ * `fwd` carries dims, weights, workspace and optional DEVICE outputs exactly as
+ * for vqa_forward; its d_img / d_tokens / d_labels / d_bbox / d_label members are
+ * ignored (the context owns those buffers).
+ * pack_on_host (bf16 engines): 1 = the host cores convert f32 -> bf16 (round to
+ * nearest even, bit-identical to vqa_cast_f32_to_bf16) into pinned staging slots
+ * while the previous chunk is in flight, so PCIe carries 2 bytes per feature;
+ * 0 = f32 over PCIe + device cast.  chunk_rows = images per staged chunk (0 = 64).
+ * raw_chunk_period = n mixes the two so that neither the host memory system (packing)
+ * nor PCIe (raw f32) is the lone bottleneck.
+ * h2d_bytes / d2h_bytes report what crossed PCIe.
+ * ---------------------------------------------------------------------- */
+typedef struct vqa_host_ctx vqa_host_ctx;
+int vqa_host_ctx_create(vqa_host_ctx** ctx, int pack_threads /* 0 = all host cores */);
+void vqa_host_ctx_destroy(vqa_host_ctx* ctx);
+int vqa_host_ctx_threads(vqa_host_ctx* ctx);
+
+typedef struct {
+  vqa_forward_args fwd;
+  const float* h_img;
+  const int64_t* h_tokens;
+  const uint8_t* h_labels;
+  const float* h_bbox;
+  int64_t* h_label;
+  int chunk_rows;
+  int pack_on_host;
+  int raw_chunk_period;      /* with pack_on_host: every n-th chunk (n >= 2) goes as f32 + device cast, 0 = none */
+  size_t h2d_bytes, d2h_bytes;
+} vqa_forward_host_args;
+
+int vqa_forward_host(vqa_host_ctx* ctx, vqa_forward_host_args* args, void* stream);
+/* split form for pipelining batches over two contexts: submit stages + enqueues everything and returns
+ * without synchronising; wait blocks until the answers of the submitted batch are in h_label.  While batch
+ * n computes, the host cores can already pack batch n+1 of the other context.                           */
+int vqa_forward_host_submit(vqa_host_ctx* ctx, vqa_forward_host_args* args, void* stream);
+int vqa_forward_host_wait(vqa_host_ctx* ctx);
+
+/* ------------------------------------------------------------------------
  * training step of the Up-Down path (BASELINE config 4): forward with saved
  * activations + BCE loss + full backward in one call.
  * replaces Wrapper.get_loss (wrapper.py:76-105: forward, instance_bce_with_logits

@@ -111,15 +111,46 @@ def test_engine_sharded_equals_unsharded(engine_mod):
         assert torch.equal(part["logits"], full_logits[r * 128:(r + 1) * 128])
 
 
-def test_engine_host_path(engine_mod):
-    cfg = O.FULL
+@pytest.mark.parametrize("pack_on_host", [True, False])
+@pytest.mark.parametrize("relation", [False, True])
+def test_engine_host_path(engine_mod, relation, pack_on_host):
+    """vqa_forward_host: wire-format host buffers → answers; host bf16 packing is bit-identical to the device cast"""
+    cfg = O.FULL_REGAT if relation else O.FULL
     W = O.make_weights(cfg, 1111)
-    batch = O.make_batch(cfg, 300, 98)
-    eng = engine_mod.VQAEngine(W, relation=False, precision="bf16")
+    B = 300 if not relation else 70                       # ragged last chunk
+    batch = O.make_batch(cfg, B, 98)
+    eng = engine_mod.VQAEngine(W, relation=relation, precision="bf16")
+    kw = dict(labels=batch["graph"].cuda()) if relation else {}
+    dev = eng.forward(batch["img"].cuda(), batch["q"].cuda(), **kw)
+    hkw = dict(labels_h=batch["graph"].to(torch.uint8)) if relation else {}
+    for _ in range(2):                                    # second call reuses the context's buffers
+        label_h, h2d, d2h = eng.forward_host(batch["img"].pin_memory(), batch["q"].pin_memory(), chunk=64,
+                                             pack_on_host=pack_on_host, **hkw)
+        assert torch.equal(label_h, dev["label"].cpu())
+        assert torch.equal(eng.last_host_outputs["logits"], dev["logits"])
+    if pack_on_host:                                      # hybrid staging: every 3rd chunk raw f32 + device cast
+        label_x, h2d_x, _ = eng.forward_host(batch["img"].pin_memory(), batch["q"].pin_memory(), chunk=32,
+                                             raw_chunk_period=3, **hkw)
+        assert torch.equal(label_x, dev["label"].cpu()) and torch.equal(eng.last_host_outputs["logits"], dev["logits"])
+        assert h2d_x > h2d
+        a1 = eng.forward_host_async(batch["img"], batch["q"], **hkw)          # two batches in flight
+        a2 = eng.forward_host_async(batch["img"], batch["q"], **hkw)
+        assert torch.equal(a1.result()[0], dev["label"].cpu()) and torch.equal(a2.result()[0], dev["label"].cpu())
+    per = 2 if pack_on_host else 4
+    assert h2d == batch["img"].numel() * per + batch["q"].numel() * 8 + (B * 36 * 36 if relation else 0) and d2h == B * 8
+    if relation:                                          # boxes instead of precomputed labels
+        label_b, _, _ = eng.forward_host(batch["img"], batch["q"], bbox_h=batch["bbox"], wh=batch["wh"], pack_on_host=pack_on_host)
+        assert torch.equal(label_b, dev["label"].cpu())
+
+
+def test_engine_host_path_fp32(engine_mod):
+    cfg = O.SMALL
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, 33, 98)
+    eng = engine_mod.VQAEngine(W, relation=False, precision="fp32")
     dev = eng.forward(batch["img"].cuda(), batch["q"].cuda())
-    label_h, h2d, d2h = eng.forward_host(batch["img"].pin_memory(), batch["q"].pin_memory(), chunk=128)
-    assert torch.equal(label_h, dev["label"].cpu())
-    assert h2d == batch["img"].numel() * 4 + batch["q"].numel() * 8 and d2h == 300 * 8
+    label_h, h2d, _ = eng.forward_host(batch["img"], batch["q"], chunk=8)
+    assert torch.equal(label_h, dev["label"].cpu()) and h2d == batch["img"].numel() * 4 + batch["q"].numel() * 8
 
 
 def test_engine_full_batch_properties(engine_mod):

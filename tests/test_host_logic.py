@@ -40,7 +40,7 @@ def test_struct_layouts_match_header():
     header = open(os.path.join(ROOT, "include", "vqa_b200.h")).read()
     for cname, cls in (("vqa_linear_args", _lib.LinearArgs), ("vqa_gru_args", _lib.GruArgs),
                        ("vqa_graph_attention_args", _lib.GraphAttentionArgs), ("vqa_forward_args", _lib.ForwardArgs),
-                       ("vqa_train_args", _lib.TrainArgs)):
+                       ("vqa_train_args", _lib.TrainArgs), ("vqa_forward_host_args", _lib.ForwardHostArgs)):
         body = re.search(r"typedef struct \{([^}]*)\}\s*" + cname + ";", header).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []
@@ -293,6 +293,24 @@ def test_two_rank_gradient_average_equals_single_process(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_host_pack_is_round_to_nearest_even(libpath):
+    """the e2e path's host-side f32→bf16 packing (host_pack.cpp) == torch's RNE cast, bit for bit"""
+    lib = ctypes.CDLL(libpath)
+    lib.vqa_packpool_create.restype = ctypes.c_void_p
+    lib.vqa_packpool_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    pool = ctypes.c_void_p(lib.vqa_packpool_create(3))
+    g = np.random.default_rng(0)
+    x = (g.standard_normal(1 << 18) * 10.0 ** g.integers(-30, 30, 1 << 18)).astype(np.float32)
+    x = np.concatenate([x, np.array([0, -0.0, np.inf, -np.inf, 1e-45, 3.4e38, 1.00390625, 1.01171875, 1.005859375], np.float32),
+                        g.random(77).astype(np.float32)])
+    y = np.empty(x.shape, np.uint16)
+    lib.vqa_packpool_run(pool, x.ctypes.data, y.ctypes.data, x.size)
+    ref = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    assert np.array_equal(y, ref)
+    lib.vqa_packpool_destroy.argtypes = [ctypes.c_void_p]
+    lib.vqa_packpool_destroy(pool)
 
 
 def test_flat_gradient_views():

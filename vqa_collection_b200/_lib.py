@@ -86,6 +86,16 @@ class ForwardArgs(C.Structure):
     ]
 
 
+class ForwardHostArgs(C.Structure):
+    _fields_ = [
+        ("fwd", ForwardArgs),
+        ("h_img", c_void_p), ("h_tokens", c_void_p), ("h_labels", c_void_p), ("h_bbox", c_void_p),
+        ("h_label", c_void_p),
+        ("chunk_rows", c_int), ("pack_on_host", c_int), ("raw_chunk_period", c_int),
+        ("h2d_bytes", c_size_t), ("d2h_bytes", c_size_t),
+    ]
+
+
 TRAIN_LAYERS = 7
 _fp = C.c_void_p * TRAIN_LAYERS
 
@@ -125,6 +135,12 @@ SYMBOLS = {
     "vqa_forward_workspace_bytes": (c_size_t, [C.POINTER(ForwardArgs)]),
     "vqa_forward": (c_int, [C.POINTER(ForwardArgs), c_void_p]),
     "vqa_forward_last_launch_count": (c_int, []),
+    "vqa_host_ctx_create": (c_int, [C.POINTER(c_void_p), c_int]),
+    "vqa_host_ctx_destroy": (None, [c_void_p]),
+    "vqa_host_ctx_threads": (c_int, [c_void_p]),
+    "vqa_forward_host": (c_int, [c_void_p, C.POINTER(ForwardHostArgs), c_void_p]),
+    "vqa_forward_host_submit": (c_int, [c_void_p, C.POINTER(ForwardHostArgs), c_void_p]),
+    "vqa_forward_host_wait": (c_int, [c_void_p]),
     "vqa_train_workspace_bytes": (c_size_t, [C.POINTER(TrainArgs)]),
     "vqa_updown_train_step": (c_int, [C.POINTER(TrainArgs), c_void_p]),
 }

@@ -16,7 +16,8 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvqa_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "relation.cu", "pool.cu", "gemm_simt.cu", "gemm_tc.cu", "gru_tc.cu", "graph_attn.cu", "graph_attn_tc.cu", "train.cu"]
+SOURCES = ["api.cu", "relation.cu", "pool.cu", "gemm_simt.cu", "gemm_tc.cu", "gru_tc.cu", "graph_attn.cu", "graph_attn_tc.cu", "train.cu", "host.cu"]
+HOST_SOURCES = ["host_pack.cpp"]          # plain C++ (g++): SIMD pack loop + thread pool of the e2e path
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v", "-I", INCLUDE,
@@ -49,13 +50,18 @@ def build(force=False, verbose=False):
         cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
+    for src in HOST_SOURCES:
+        obj = os.path.join(LIB_DIR, src.replace(".cpp", ".o"))
+        cmd = ["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
     log = []
     for src, p in procs:
         out, _ = p.communicate()
         log.append(f"==== {src}\n{out}")
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+            raise RuntimeError(f"compiler failed on {src}:\n{out}")
+    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread"]
     subprocess.run(cmd, check=True)
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
         f.write("\n".join(log))

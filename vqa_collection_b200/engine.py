@@ -258,54 +258,96 @@ class VQAEngine:
         return out
 
     # -- host-buffer forward (the e2e path) ----------------------------------------
-    def forward_host(self, img_h, tokens_h, labels_h=None, bbox_h=None, wh=None, chunk=128):
-        """Host (pinned) buffers in the reference wire format → host results.
+    def _next_host_ctx(self):
+        """two host contexts, used alternately, so that batch n+1 can be staged while batch n computes"""
+        import os
+        ctxs = getattr(self, "_host_ctxs", None)
+        if ctxs is None:
+            ctxs = self._host_ctxs = []
+            self._host_turn = 0
+        if len(ctxs) < 2:
+            ctx = C.c_void_p()
+            with torch.cuda.device(self.device):
+                L.check(self.lib.vqa_host_ctx_create(C.byref(ctx), int(os.environ.get("VQA_B200_PACK_THREADS", "0"))))
+            ctxs.append(ctx)
+            return ctx
+        self._host_turn ^= 1
+        return ctxs[self._host_turn]
 
-        img_h f32 [B,K,V], tokens_h int64 [B,T] (+ labels_h u8/f64 [B,K,K] or bbox_h f32).
-        The feature copy is chunked: chunk i+1's H2D overlaps chunk i's f32→bf16 cast; the
-        forward runs once on the resident batch; the answers come back with one D2H.
-        Returns (label int64 [B] on host, bytes_h2d, bytes_d2h)."""
+    def forward_host(self, img_h, tokens_h, labels_h=None, bbox_h=None, wh=None, chunk=64, pack_on_host=True,
+                     raw_chunk_period=0):
+        """synchronous form of forward_host_async: returns (label int64 [B] on host, bytes_h2d, bytes_d2h)"""
+        return self.forward_host_async(img_h, tokens_h, labels_h, bbox_h, wh, chunk, pack_on_host, raw_chunk_period).result()
+
+    def forward_host_async(self, img_h, tokens_h, labels_h=None, bbox_h=None, wh=None, chunk=64, pack_on_host=True,
+                           raw_chunk_period=0):
+        """Host buffers in the reference wire format → a handle whose ``result()`` gives the host answers
+        (vqa_forward_host_submit / _wait).
+
+        img_h f32 [B,K,V] (pinned recommended), tokens_h int64 [B,T] (+ labels_h u8 [B,K,K] or bbox_h f32
+        [B,K,4] with wh).  bf16 engines: ``pack_on_host`` lets the host cores convert the features to bf16
+        (bit-identical to the device cast) while the previous chunk is in flight, so PCIe carries 2 bytes per
+        feature; otherwise f32 crosses PCIe and is cast on the device.  Up to two batches may be in flight
+        (two staging contexts): submit batch n+1 before asking for batch n's result to overlap staging with
+        compute."""
+        for name, t, dt in (("img_h", img_h, torch.float32), ("tokens_h", tokens_h, torch.int64)):
+            if t.is_cuda or t.dtype != dt or not t.is_contiguous():
+                raise TypeError(f"forward_host: {name} must be a contiguous CPU {dt} tensor")
         B, K, V = img_h.shape
+        if K != self.K or V != self.P["V"]:
+            raise ValueError(f"img must be [B,{self.K},{self.P['V']}], got {tuple(img_h.shape)}")
+        ctx = self._next_host_ctx()
+        a = self._args(B, tokens_h.shape[1])
+        ws, need = self._workspace(a)
         dev = self.device
-        copy_s = getattr(self, "_copy_stream", None)
-        if copy_s is None:
-            copy_s = self._copy_stream = torch.cuda.Stream(device=dev)
-        main_s = torch.cuda.current_stream()
-        res = torch.empty((B, K, V), dtype=self.dtype, device=dev)
-        stage = [torch.empty((chunk, K, V), dtype=torch.float32, device=dev) for _ in range(2)]
-        free_ev = [None, None]
-        h2d = 0
-        copy_s.wait_stream(main_s)
-        for i, b0 in enumerate(range(0, B, chunk)):
-            b1 = min(B, b0 + chunk)
-            buf = stage[i & 1][: b1 - b0]
-            with torch.cuda.stream(copy_s):
-                if free_ev[i & 1] is not None:
-                    copy_s.wait_event(free_ev[i & 1])
-                buf.copy_(img_h[b0:b1], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_s)
-            main_s.wait_event(ev)
-            if self.dtype == torch.float32:
-                res[b0:b1].copy_(buf)
-            else:
-                L.check(self.lib.vqa_cast_f32_to_bf16(buf.data_ptr(), res[b0:b1].data_ptr(), buf.numel(),
-                                                      C.c_void_p(main_s.cuda_stream)))
-            free_ev[i & 1] = torch.cuda.Event()
-            free_ev[i & 1].record(main_s)
-            h2d += buf.numel() * 4
-        tokens = tokens_h.to(dev, non_blocking=True)
-        h2d += tokens_h.numel() * 8
-        labels = bbox = None
+        logits = torch.empty((B, a.A), dtype=torch.float32, device=dev)
+        att = torch.empty((B, K), dtype=torch.float32, device=dev)
+        a.d_workspace, a.workspace_bytes = ws.data_ptr(), need
+        a.d_logits, a.d_att = logits.data_ptr(), att.data_ptr()
+        ha = L.ForwardHostArgs()
+        ha.h_img, ha.h_tokens = img_h.data_ptr(), tokens_h.data_ptr()
+        keep = []
         if self.relation:
             if labels_h is not None:
-                labels = labels_h.to(dev, non_blocking=True)
-                h2d += labels_h.numel() * labels_h.element_size()
+                if labels_h.dtype != torch.uint8:
+                    labels_h = labels_h.to(torch.uint8)      # loader format is float64 (dataset.py:102)
+                labels_h = labels_h.contiguous()
+                keep.append(labels_h)
+                ha.h_labels = labels_h.data_ptr()
+            elif bbox_h is not None:
+                if wh is None:
+                    raise ValueError("bbox needs wh=(img_w, img_h)")
+                bbox_h = bbox_h.float().contiguous()
+                keep.append(bbox_h)
+                ha.h_bbox = bbox_h.data_ptr()
+                a.img_w, a.img_h = float(wh[0]), float(wh[1])
             else:
-                bbox = bbox_h.to(dev, non_blocking=True)
-                h2d += bbox_h.numel() * 4
-        out = self.forward(res, tokens, labels=labels, bbox=bbox, wh=wh)
+                raise ValueError("relation engine needs labels_h or bbox_h")
+        label_h = torch.empty((B,), dtype=torch.int64)
+        ha.fwd, ha.h_label = a, label_h.data_ptr()
+        ha.chunk_rows, ha.pack_on_host = int(chunk), int(bool(pack_on_host) and self.dtype == torch.bfloat16)
+        ha.raw_chunk_period = int(raw_chunk_period) if ha.pack_on_host else 0
+        L.check(self.lib.vqa_forward_host_wait(ctx))             # a context carries one batch at a time
+        with torch.cuda.device(self.device):
+            L.check(self.lib.vqa_forward_host_submit(ctx, C.byref(ha), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         n_chunks = (B + chunk - 1) // chunk
-        self.last_launches += n_chunks if self.dtype == torch.bfloat16 else 0
-        label_h = out["label"].to("cpu")           # synchronising D2H of the answers
-        return label_h, h2d, label_h.numel() * 8
+        self.last_launches = self.lib.vqa_forward_last_launch_count() + (
+            (n_chunks if not ha.pack_on_host else (n_chunks // ha.raw_chunk_period if ha.raw_chunk_period else 0))
+            if self.dtype == torch.bfloat16 else 0)
+        self.last_host_outputs = {"logits": logits, "att": att}
+        eng = self
+
+        class _Pending:
+            def result(self_inner):
+                L.check(eng.lib.vqa_forward_host_wait(ctx))
+                _ = keep, img_h, tokens_h                    # host buffers must outlive the transfer
+                return label_h, int(ha.h2d_bytes), int(ha.d2h_bytes)
+        return _Pending()
+
+    def __del__(self):
+        for ctx in getattr(self, "_host_ctxs", None) or []:
+            try:
+                self.lib.vqa_host_ctx_destroy(ctx)
+            except Exception:
+                pass
+        self._host_ctxs = None
