@@ -18,6 +18,12 @@
 //     to global memory (double buffered), followed by a grid-wide arrive/wait on a
 //     global counter (release/acquire + async-proxy fence, since TMA reads it)
 //   * no gi/gh round trip, no per-step launches: 1 launch instead of 2T+1.
+//   * the CTAs of one row block all read the same x_t / h_{t-1} tiles; h is freshly written every
+//     step (its L2 lines cannot be served from a read-only replica); measured, those reads cost
+//     more than the larger W tiles.  Optionally (VQA_B200_GRU_CLUSTER=2|4|8) the CTAs form
+//     thread-block clusters along the unit dimension: each CTA loads a 1/cs slice of the x / h
+//     tile and TMA-multicasts it to its cluster, and a stage is recycled only when every CTA of
+//     the cluster has consumed it (tcgen05.commit multicast onto all the empty barriers).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -46,12 +52,13 @@ constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + 4 * UNITS * 4;
 
 struct Params {
   int B, T, H, E_pad, tiles_n, num_ctas;
+  int cs;                       // cluster size along the unit dimension (1, 2, 4 or 8)
   const float* bias;            // packed [4H]: b_ir+b_hr | b_iz+b_hz | b_in | b_hn
   __nv_bfloat16* h_op[2];       // bf16 state, double buffered over steps
   float* h_last;                // [B,H] f32
   __nv_bfloat16* h_last_lp;     // [B,H] bf16 or NULL
   int* counter;                 // per-row-block arrival counters [tiles_m], zero on entry
-  int debug;                    // timing experiments only (VQA_B200_GRU_DEBUG): 1 no barrier wait, 2 no gate math, 4 no fence
+  int debug;                    // timing experiments only (VQA_B200_GRU_DEBUG): 1 no barrier wait, 2 no gate math, 4 no fence, 8 no h-tile loads, 16 no W_h-tile loads
 };
 
 // ex2.approx + rcp.approx: ~1e-6 relative, 2 MUFU each
@@ -85,8 +92,12 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmH0); tma_prefetch_desc(&tmH1);
     tma_prefetch_desc(&tmWx); tma_prefetch_desc(&tmWh);
   }
+  const int cs = p.cs;
+  const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  const int slice_rows = BM / cs;                      // rows of the x / h tile this CTA loads for its cluster
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), cs); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_THREADS); }
     fence_barrier_init();
   }
@@ -96,8 +107,14 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();                      // peers multicast into / arrive on these barriers
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // A-operand tile: this CTA's row slice, delivered to every CTA of the cluster
+  auto load_a = [&](uint32_t sa, const CUtensorMap* map, uint32_t bar, int col) {
+    if (cs > 1) tma_load_2d_multicast(sa + crank * (slice_rows * 128), map, bar, col, m0 + (int)crank * slice_rows, cmask);
+    else tma_load_2d(sa, map, bar, col, m0);
+  };
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -108,7 +125,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
           mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-          tma_load_2d(sa, &tmX, full_bar(stage), t * p.E_pad + kb * BK, m0);
+          load_a(sa, &tmX, full_bar(stage), t * p.E_pad + kb * BK);
           tma_load_2d(sw, &tmWx, full_bar(stage), kb * BK, n_blk * WROWS);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -118,8 +135,8 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           int pre_stage[W_PREFETCH];
           for (int kb = 0; kb < npre; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(base + stage * STAGE_BYTES + A_BYTES, &tmWh, full_bar(stage), kb * BK, n_blk * WROWS);
+            mbar_arrive_expect_tx(full_bar(stage), ((p.debug & 8) ? 0 : A_BYTES) + ((p.debug & 16) ? 0 : W_BYTES));
+            if (!(p.debug & 16)) tma_load_2d(base + stage * STAGE_BYTES + A_BYTES, &tmWh, full_bar(stage), kb * BK, n_blk * WROWS);
             pre_stage[kb] = stage;
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -129,13 +146,13 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           fence_proxy_async_all();
           const CUtensorMap* tmH = ((t - 1) & 1) ? &tmH1 : &tmH0;
           for (int kb = 0; kb < npre; ++kb)
-            tma_load_2d(base + pre_stage[kb] * STAGE_BYTES, tmH, full_bar(pre_stage[kb]), kb * BK, m0);
+            if (!(p.debug & 8)) load_a(base + pre_stage[kb] * STAGE_BYTES, tmH, full_bar(pre_stage[kb]), kb * BK);
           for (int kb = npre; kb < kb_h; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
-            mbar_arrive_expect_tx(full_bar(stage), STAGE_BYTES);
-            tma_load_2d(sa, tmH, full_bar(stage), kb * BK, m0);
-            tma_load_2d(sw, &tmWh, full_bar(stage), kb * BK, n_blk * WROWS);
+            mbar_arrive_expect_tx(full_bar(stage), ((p.debug & 8) ? 0 : A_BYTES) + ((p.debug & 16) ? 0 : W_BYTES));
+            if (!(p.debug & 8)) load_a(sa, tmH, full_bar(stage), kb * BK);
+            if (!(p.debug & 16)) tma_load_2d(sw, &tmWh, full_bar(stage), kb * BK, n_blk * WROWS);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -164,7 +181,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             umma_bf16(d + COL_R, adesc + 2 * k, wdesc + 2 * k, idesc_rz, (kb | k) != 0);
             umma_bf16(d + COL_NI, adesc + 2 * k, wdesc + N_ROW_OFF + 2 * k, idesc_n, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));
+          if (cs > 1) umma_commit_multicast(empty_bar(stage), cmask); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (t > 0) {
@@ -178,7 +195,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
               umma_bf16(d + COL_R, adesc + 2 * k, wdesc + 2 * k, idesc_rz, 1u);
               umma_bf16(d + COL_NH, adesc + 2 * k, wdesc + N_ROW_OFF + 2 * k, idesc_n, (kb | k) != 0);
             }
-            umma_commit(empty_bar(stage));
+            if (cs > 1) umma_commit_multicast(empty_bar(stage), cmask); else umma_commit(empty_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -256,6 +273,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
   tcgen05_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();                      // no CTA leaves while a peer may still signal its barriers
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
@@ -280,6 +298,14 @@ int gru_persistent(const void* X, int B, int T, int H, int E_pad, const void* wx
   }
   CUtensorMap tmWx, tmWh;
   int rc;
+  static int max_cs = 8;                               // halved whenever a cluster launch of that size is refused
+  int cs = 1;
+  // Measured at B=1024: with the grid barrier disabled multicast saves 21 us of operand traffic
+  // (172 -> 151 us), but the real step is bound by the publish -> acquire -> load latency chain and comes out the
+  // same (212 us at cluster sizes 1, 2, 4 and 8).  Default = plain launch; VQA_B200_GRU_CLUSTER=N turns it on.
+  int want = 1;
+  if (const char* e = getenv("VQA_B200_GRU_CLUSTER")) { const int v = atoi(e); if (v >= 1) want = v < max_cs ? v : max_cs; }
+  while (cs < want && tiles_n % (cs * 2) == 0) cs *= 2;
   if ((rc = tc::make_tensor_map_bf16(&tmWx, wx_p, 3LL * H, E_pad, E_pad, WROWS))) return rc;
   if ((rc = tc::make_tensor_map_bf16(&tmWh, wh_p, 3LL * H, H, H, WROWS))) return rc;
   // batch chunks so that every chunk's CTAs are co-resident (grid barrier)
@@ -290,20 +316,37 @@ int gru_persistent(const void* X, int B, int T, int H, int E_pad, const void* wx
     __nv_bfloat16* h0 = (__nv_bfloat16*)h_op + (size_t)b0 * H;
     __nv_bfloat16* h1 = (__nv_bfloat16*)h_op + (size_t)B * H + (size_t)b0 * H;
     CUtensorMap tmX, tmH0, tmH1;
-    if ((rc = tc::make_tensor_map_bf16(&tmX, Xc, Bc, (long long)T * E_pad, (long long)T * E_pad, tc::BM))) return rc;
-    if ((rc = tc::make_tensor_map_bf16(&tmH0, h0, Bc, H, H, tc::BM))) return rc;
-    if ((rc = tc::make_tensor_map_bf16(&tmH1, h1, Bc, H, H, tc::BM))) return rc;
+    if ((rc = tc::make_tensor_map_bf16(&tmX, Xc, Bc, (long long)T * E_pad, (long long)T * E_pad, tc::BM / cs))) return rc;
+    if ((rc = tc::make_tensor_map_bf16(&tmH0, h0, Bc, H, H, tc::BM / cs))) return rc;
+    if ((rc = tc::make_tensor_map_bf16(&tmH1, h1, Bc, H, H, tc::BM / cs))) return rc;
     Params p;
     p.B = Bc; p.T = T; p.H = H; p.E_pad = E_pad; p.tiles_n = tiles_n; p.num_ctas = tiles_m * tiles_n;
     p.bias = bias_p; p.h_op[0] = h0; p.h_op[1] = h1;
     p.h_last = h_last + (size_t)b0 * H;
     p.h_last_lp = h_last_lp ? (__nv_bfloat16*)h_last_lp + (size_t)b0 * H : nullptr;
     p.counter = counter;
+    p.cs = cs;
     { const char* e = getenv("VQA_B200_GRU_DEBUG"); p.debug = e ? atoi(e) : 0; }
     VQA_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int) * tiles_m, s));
     void* args[] = {&tmX, &tmH0, &tmH1, &tmWx, &tmWh, &p};
-    VQA_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persistent_kernel, dim3(p.num_ctas), dim3(THREADS), args,
-                                               (size_t)SMEM_BYTES, s));
+    if (cs > 1) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(p.num_ctas); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
+      cudaLaunchAttribute at[2];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+      cfg.attrs = at; cfg.numAttrs = 2;
+      cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)gru_persistent_kernel, args);
+      if (e != cudaSuccess) {
+        // clusters of this size cannot all be co-resident on this device: remember, retry the whole call smaller
+        (void)cudaGetLastError();
+        max_cs = cs / 2;
+        return gru_persistent(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, s);
+      }
+    } else {
+      VQA_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persistent_kernel, dim3(p.num_ctas), dim3(THREADS), args,
+                                                 (size_t)SMEM_BYTES, s));
+    }
     count_launch();
   }
   return VQA_OK;
