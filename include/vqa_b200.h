@@ -59,6 +59,11 @@ int vqa_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * ---------------------------------------------------------------------- */
 int vqa_relation_labels(const float* d_bbox, const float* d_wh, int B, int K, float img_w,
                         float img_h, uint8_t* d_labels, void* stream);
+/* Host-only helper (no GPU needed): the float32 threshold s_max the kernel compares the SQUARED
+ * centre distance against — the largest float32 s whose correctly rounded sqrt, widened to
+ * double, is <= ||(img_w,img_h)||/2, i.e. exactly relation.py:37-38's `dist <= 0.5`.  Exposed so
+ * the sqrt/divide-free form can be pinned against numpy on the CPU. */
+float vqa_relation_near_threshold(float img_w, float img_h);
 /* host-buffer form (H2D + kernel + D2H + sync), the e2e path of the label op */
 int vqa_relation_labels_host(const float* h_bbox, int B, int K, float img_w, float img_h,
                              uint8_t* h_labels);

@@ -204,6 +204,55 @@ def test_octant_rule_equals_arctan2_pipeline_on_grid():
     assert np.array_equal(ab, idx(delta)) and np.array_equal(ba, idx(delta + np.float32(180)))
 
 
+def _iou_rule(ai, d):
+    """the division-free form of `fl32(ai/d) >= 0.5` that csrc/relation.cu evaluates (float32 ops only)"""
+    ai, d = ai.astype(np.float32), d.astype(np.float32)
+    x = ai - np.float32(0.5) * d
+    t = d * np.float32(-2.0 ** -26)
+    return np.where(d > 0, x >= t, np.where(d < 0, x <= t, (d == 0) & (ai > 0)))
+
+
+def test_division_free_iou_rule_equals_float32_division():
+    """relation.py:28-30 compares the float32 quotient with 0.5; the kernel never divides"""
+    rng = np.random.default_rng(5)
+    n = 2_000_000
+    # d of either sign over many binades, ai clustered within a few ulp of d/2 plus a broad spread
+    d = (rng.standard_normal(n) * np.exp2(rng.integers(-8, 24, n))).astype(np.float32)
+    half = (np.float32(0.5) * d).astype(np.float32)
+    near = half.copy()
+    for _ in range(4):                                   # walk up to +-4 ulp away from d/2
+        step = rng.integers(-1, 2, n)
+        near = np.where(step > 0, np.nextafter(near, np.float32(np.inf)),
+                        np.where(step < 0, np.nextafter(near, np.float32(-np.inf)), near)).astype(np.float32)
+    broad = (d * rng.uniform(-2, 2, n).astype(np.float32)).astype(np.float32)
+    ai = np.where(rng.random(n) < 0.7, near, broad).astype(np.float32)
+    d[:1000] = 0.0                                       # +-inf / NaN quotients
+    ai[:300] = 0.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ref = (ai / d) >= np.float32(0.5)
+    got = _iou_rule(ai, d)
+    assert np.array_equal(ref, got), int((ref != got).sum())
+    assert 0.05 < ref.mean() < 0.95                      # the sample straddles the threshold
+
+
+def test_near_threshold_equals_sqrt_divide_compare(libpath):
+    """relation.py:37-38: float32 norm, float64 divide, `<= 0.5`; the kernel compares the squared distance
+    with one precomputed float32 (vqa_relation_near_threshold)"""
+    lib = ctypes.CDLL(libpath)
+    lib.vqa_relation_near_threshold.restype = ctypes.c_float
+    lib.vqa_relation_near_threshold.argtypes = [ctypes.c_float, ctypes.c_float]
+    for w, h in [(640, 480), (500, 375), (1, 1), (7, 3), (1920, 1080), (333.5, 250.25), (3, 4), (1e-3, 2e-3)]:
+        s_max = np.float32(lib.vqa_relation_near_threshold(w, h))
+        diag = np.linalg.norm([float(np.float32(w)), float(np.float32(h))])
+        s = np.full(65, s_max, dtype=np.float32)
+        for k in range(32):                              # 32 floats either side of the threshold
+            s[33 + k:] = np.nextafter(s[33 + k:], np.float32(np.inf))
+            s[:32 - k] = np.nextafter(s[:32 - k], np.float32(-np.inf))
+        ref = (np.sqrt(s).astype(np.float64) / diag) <= 0.5
+        assert np.array_equal(ref, s <= s_max), (w, h)
+        assert ref[32] and not ref[33]
+
+
 def test_shard_bounds_cover_rows_exactly():
     from vqa_collection_b200.parallel import shard_bounds, shard_batch
     for n in (0, 1, 7, 1024, 1027):

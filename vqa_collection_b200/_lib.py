@@ -122,6 +122,7 @@ SYMBOLS = {
     "vqa_device_info": (c_int, [C.POINTER(c_int)] * 3),
     "vqa_relation_labels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "vqa_relation_labels_host": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
+    "vqa_relation_near_threshold": (c_float, [c_float, c_float]),
     "vqa_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vqa_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vqa_linear": (c_int, [C.POINTER(LinearArgs), c_void_p]),

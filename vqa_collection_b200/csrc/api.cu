@@ -50,6 +50,7 @@ int require_sm100() {
 
 // kernels implemented in the other translation units
 int relation_labels(const float*, const float*, int, int, float, float, uint8_t*, cudaStream_t);
+float relation_near_threshold(float, float);
 int attention_pool(const float*, int, float, const void*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int argmax_rows(const float*, int, int, int, int64_t*, cudaStream_t);
 int embedding_gather(const int64_t*, int, int, int, int, const void*, void*, cudaStream_t);
@@ -163,6 +164,8 @@ int vqa_relation_labels(const float* d_bbox, const float* d_wh, int B, int K, fl
   if (int rc = require_sm100()) return rc;
   return relation_labels(d_bbox, d_wh, B, K, img_w, img_h, d_labels, (cudaStream_t)stream);
 }
+
+float vqa_relation_near_threshold(float img_w, float img_h) { return relation_near_threshold(img_w, img_h); }
 
 int vqa_relation_labels_host(const float* h_bbox, int B, int K, float img_w, float img_h, uint8_t* h_labels) {
   if (int rc = require_sm100()) return rc;

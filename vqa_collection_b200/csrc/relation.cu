@@ -1,96 +1,171 @@
 // k7 — spatial relation labels on device.
 //
 // Reference: util/relation.py:3-45 (spatial_relation) and :65-80
-// (relation_graph).  One CTA per image; every unordered pair i<j is evaluated
-// ONCE and writes both [i,j] (first return value) and [j,i] (second return
-// value) into a shared-memory K×K byte tile that is then stored with coalesced
-// 16-byte writes.  float32 geometry is mirrored with IEEE round-to-nearest
-// intrinsics (no FMA contraction); the direction octant is decided by exact
-// sign/magnitude comparisons of the centre offset instead of atan2f (SURVEY.md
-// H2): away from and exactly on the 8 angular boundaries this equals the
-// reference's float32 arctan2 → rad2deg → -90 → %360 → /45 → ceil pipeline.
+// (relation_graph).  Every unordered pair i<j is evaluated ONCE and yields both
+// [i,j] (first return value) and [j,i] (second return value).
+//
+// Layout of the work: a persistent CTA walks over images; thread p of the CTA
+// owns pair p = (i,j) for the whole kernel (K=36: 630 pairs -> 640 threads, the
+// (i,j) decode happens once).  Per image the K boxes and their per-box terms
+// (area, centre) go to shared memory once, each thread evaluates its pair with
+// ~45 fp32 instructions and drops the two label bytes into a K×K shared tile
+// that leaves with 16-byte coalesced stores.  Box tile and label tile are double
+// buffered, so there is ONE __syncthreads per image and the box load of image
+// n+1 is in flight under the pair evaluation of image n.
+//
+// Exactness (labels are bit-exact against the reference on the same float32 boxes):
+//  * float32 geometry uses IEEE round-to-nearest intrinsics (no FMA contraction);
+//  * `I == b` (relation.py:24) is four ordered compares: max(a,b)==b ⇔ a<=b;
+//  * `iou >= 0.5` with iou = fl(ai/d) (relation.py:28-30) is decided without the
+//    division: fl(ai/d) >= 0.5 ⇔ ai/d >= 0.5-2^-26 (ties-to-even lands on 0.5), i.e.
+//    for d>0  ai - d/2 >= -d·2^-26.  ai - d/2 is exact when ai ∈ [d/4, d] (Sterbenz) and
+//    otherwise so far from the threshold that its rounding cannot cross it; d<0 mirrors,
+//    d==0 gives ±inf/NaN -> ai>0;
+//  * `‖c_a-c_b‖/‖(w,h)‖ <= 0.5` (relation.py:37-38; float32 norm, float64 divide):
+//    (double)nrm/D <= 0.5 ⇔ (double)nrm <= D/2 (exact: x > D/2 implies x/D >= 0.5+2^-53),
+//    and since fl(sqrt(s)) is monotone in s the test is `s <= s_max` with s_max the
+//    largest float32 whose correctly rounded root is <= D/2 (found once per image size);
+//  * the direction octant is decided by exact sign/magnitude comparisons of the centre
+//    offset instead of atan2f: away from and exactly on the 8 angular
+//    boundaries this equals the reference's float32 arctan2 → rad2deg → -90 → %360 → /45
+//    → ceil pipeline.
+// Inputs are assumed finite (pixel coordinates).
+#include <math.h>
+
 #include "common.cuh"
 
 namespace vqa {
 
-struct LabelPair { uint8_t ab, ba; };
+constexpr int kRelMaxK = 64;
+constexpr int kRelMaxThreads = 1024;
+// pairs per thread: 1 up to K = 45 (990 pairs), 2 up to K = 64 (2016 pairs)
 
-__device__ __forceinline__ LabelPair relation_pair(const float4 a, const float4 b,
-                                                   const double half_diag) {
-  // intersection box (relation.py:19-22); float4 = (x0,y0,x1,y1)
-  const float i0 = fmaxf(a.x, b.x), i1 = fmaxf(a.y, b.y);
-  const float i2 = fminf(a.z, b.z), i3 = fminf(a.w, b.w);
-  if (i0 == b.x && i1 == b.y && i2 == b.z && i3 == b.w) return {1, 2};   // :24
-  if (i0 == a.x && i1 == a.y && i2 == a.z && i3 == a.w) return {2, 1};   // :25
-  // IoU with UNCLAMPED areas (:28-30) — negative×negative is positive (F6)
-  const float ai = __fmul_rn(__fsub_rn(i3, i1), __fsub_rn(i2, i0));
-  const float aa = __fmul_rn(__fsub_rn(a.w, a.y), __fsub_rn(a.z, a.x));
-  const float ab = __fmul_rn(__fsub_rn(b.w, b.y), __fsub_rn(b.z, b.x));
-  const float iou = __fdiv_rn(ai, __fsub_rn(__fadd_rn(aa, ab), ai));
-  if (iou >= 0.5f) return {3, 3};
-  // centres (:33-35): x0 + (x1-x0)/2
-  const float cax = __fadd_rn(a.x, __fmul_rn(__fsub_rn(a.z, a.x), 0.5f));
-  const float cay = __fadd_rn(a.y, __fmul_rn(__fsub_rn(a.w, a.y), 0.5f));
-  const float cbx = __fadd_rn(b.x, __fmul_rn(__fsub_rn(b.z, b.x), 0.5f));
-  const float cby = __fadd_rn(b.y, __fmul_rn(__fsub_rn(b.w, b.y), 0.5f));
-  const float dx = __fsub_rn(cax, cbx), dy = __fsub_rn(cay, cby);
-  const float nrm = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-  // (double)nrm / ‖(w,h)‖ <= 0.5  ⇔  (double)nrm <= ‖(w,h)‖/2  (exact)
-  if (!((double)nrm <= half_diag)) return {0, 0};                        // :37-38,45
-  // direction of b seen from a (:39-42): θ = atan2(ex, ey), δ = θ-90,
-  // label = ceil((δ mod 360)/45)+3 and the same for δ+180.
-  const float ex = __fsub_rn(cbx, cax), ey = __fsub_rn(cby, cay);
-  if (ex > 0.f) {
-    if (ey == 0.f) return {3, 7};                       // θ = 90  → m = 0  (label-3 quirk)
-    if (ey < 0.f) return (-ey <= ex) ? LabelPair{4, 8} : LabelPair{5, 9};   // (90,135] | (135,180)
-    return (ex <= ey) ? LabelPair{10, 6} : LabelPair{11, 7};                // (0,45] | (45,90)
+// largest float32 s with (double)fl(sqrt(s)) <= half_diag; -1 if there is none
+__host__ __device__ __noinline__ float near_threshold_sq(double half_diag) {
+  if (!(half_diag >= 0.0)) return -1.f;
+  if (half_diag > 1.8e19) return 3.4028234663852886e38f;       // sqrt(FLT_MAX): everything finite is near
+  float hf = (float)half_diag;                                 // round to nearest, then step down if above
+  if ((double)hf > half_diag) hf = nextafterf(hf, -1.f);
+  float s = hf * hf;
+  for (int it = 0; it < 64 && (double)sqrtf(s) > (double)hf; ++it) s = nextafterf(s, -1.f);
+  for (int it = 0; it < 64; ++it) {
+    const float up = nextafterf(s, 3.4028234663852886e38f);
+    if (up == s || (double)sqrtf(up) > (double)hf) break;
+    s = up;
   }
-  if (ex < 0.f) {
-    if (ey == 0.f) return {7, 3};                       // θ = -90 → δ+180 = 0 → 3
-    if (ey < 0.f) return (ex >= ey) ? LabelPair{6, 10} : LabelPair{7, 11};  // (-180,-135] | (-135,-90)
-    return (ey <= -ex) ? LabelPair{8, 4} : LabelPair{9, 5};                 // (-90,-45] | (-45,0)
-  }
-  // ex == 0: straight up/down, or coincident centres (atan2(0,0) = 0 → 9,5)
-  return (ey < 0.f) ? LabelPair{5, 9} : LabelPair{9, 5};
+  return s;
 }
 
-constexpr int kRelThreads = 256;
-constexpr int kRelMaxK = 64;
+// both labels of one unordered pair, packed as ab | ba << 8
+__device__ __forceinline__ uint32_t relation_pair(const float4 a, const float4 b, const float4 ea,
+                                                  const float4 eb, const float s_max) {
+  // e = (area, cx, cy, -)
+  const bool inside = (a.x <= b.x) & (a.y <= b.y) & (b.z <= a.z) & (b.w <= a.w);    // I == b   (:24)
+  const bool covered = (b.x <= a.x) & (b.y <= a.y) & (a.z <= b.z) & (a.w <= b.w);   // I == a   (:25)
+  // IoU with UNCLAMPED areas (:28-30) — negative×negative is positive (F6)
+  const float i0 = fmaxf(a.x, b.x), i1 = fmaxf(a.y, b.y);
+  const float i2 = fminf(a.z, b.z), i3 = fminf(a.w, b.w);
+  const float ai = __fmul_rn(__fsub_rn(i3, i1), __fsub_rn(i2, i0));
+  const float d = __fsub_rn(__fadd_rn(ea.x, eb.x), ai);
+  const float x = __fsub_rn(ai, __fmul_rn(0.5f, d));
+  const float t = __fmul_rn(d, -0x1p-26f);
+  const bool overlap = (d > 0.f) ? (x >= t) : ((d < 0.f) ? (x <= t) : (d == 0.f && ai > 0.f));
+  // centre distance (:33-38)
+  const float dx = __fsub_rn(ea.y, eb.y), dy = __fsub_rn(ea.z, eb.z);
+  const float s = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+  const bool near = s <= s_max;
+  // direction of b seen from a (:39-42): θ = atan2(ex, ey), δ = θ-90, label = ceil((δ mod 360)/45)+3
+  // and the same for δ+180.  e = c_b - c_a = -(c_a - c_b) exactly.
+  const float ex = -dx, ey = -dy;
+  // Branch-free octant: quadrant qn (counted from the first octant of label 4) and which half of it.
+  //   q0: ex>=0, ey<0  -> 4 | 5      q1: ex<0, ey<=0 -> 6 | 7      q2: ex<=0, ey>0 -> 8 | 9      q3: ex>0, ey>=0 -> 10 | 11
+  // second half of q0/q2 when !(|ey|<=|ex|), of q1/q3 when !(|ex|<=|ey|); the opposite direction is the quadrant
+  // two further on.  Three exceptions: θ=90 (ex>0, ey==0) is m=0 -> label 3, θ=-90 likewise for the way back,
+  // and coincident centres give atan2(0,0)=0 -> (9,5).
+  const bool xp = ex > 0.f, xn = ex < 0.f, yp = ey > 0.f, yn = ey < 0.f;
+  const bool yx = fabsf(ey) <= fabsf(ex), xy = fabsf(ex) <= fabsf(ey);
+  const uint32_t qn = (!xn & yn) ? 0u : (xn & !yp) ? 1u : (!xp & yp) ? 2u : 3u;
+  const uint32_t sec = (qn & 1u) ? (uint32_t)!xy : (uint32_t)!yx;
+  uint32_t lab_ab = 4u + 2u * qn + sec, lab_ba = 4u + 2u * ((qn + 2u) & 3u) + sec;
+  const bool y0 = !yp & !yn;
+  lab_ab = (y0 & xp) ? 3u : lab_ab;
+  lab_ba = (y0 & xn) ? 3u : lab_ba;
+  const bool both0 = y0 & !xp & !xn;
+  lab_ab = both0 ? 9u : lab_ab;
+  lab_ba = both0 ? 5u : lab_ba;
+  const uint32_t dir = lab_ab | (lab_ba << 8);
+  return inside ? (1u | (2u << 8)) : covered ? (2u | (1u << 8)) : overlap ? (3u | (3u << 8)) : near ? dir : 0u;
+}
 
-__global__ void __launch_bounds__(kRelThreads)
-relation_labels_kernel(const float4* __restrict__ bbox, const float2* __restrict__ wh,
-                       int B, int K, double half_diag_uniform, uint8_t* __restrict__ labels) {
-  __shared__ float4 s_box[kRelMaxK];
-  __shared__ __align__(16) uint8_t s_lab[kRelMaxK * kRelMaxK];
-  const int KK = K * K;
-  for (int img = blockIdx.x; img < B; img += gridDim.x) {
-    if (threadIdx.x < K) s_box[threadIdx.x] = __ldg(bbox + (size_t)img * K + threadIdx.x);
-    double half_diag = half_diag_uniform;
-    if (wh != nullptr) {
-      const float2 d = __ldg(wh + img);
-      half_diag = 0.5 * sqrt((double)d.x * (double)d.x + (double)d.y * (double)d.y);
+template <int kRelPairsPerThread>
+__global__ void __launch_bounds__(kRelMaxThreads, kRelPairsPerThread == 1 ? 2 : 1)
+relation_labels_kernel(const float4* __restrict__ bbox, const float2* __restrict__ wh, int B, int K,
+                       float s_max_uniform, uint8_t* __restrict__ labels) {
+  __shared__ float4 s_box[2][kRelMaxK];
+  __shared__ float4 s_ext[2][kRelMaxK];
+  __shared__ float s_thr[2];
+  __shared__ __align__(16) uint8_t s_lab[2][kRelMaxK * kRelMaxK];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int KK = K * K, npairs = K * (K - 1) / 2;
+  // this thread's pairs, decoded once: p -> (i,j), i<j, row-major over the upper triangle
+  int pi[kRelPairsPerThread], pj[kRelPairsPerThread];
+#pragma unroll
+  for (int u = 0; u < kRelPairsPerThread; ++u) {
+    int p = tid + u * nthr, i = 0;
+    pi[u] = -1; pj[u] = 0;
+    if (p < npairs) {
+      while (p >= K - 1 - i) { p -= K - 1 - i; ++i; }
+      pi[u] = i; pj[u] = i + 1 + p;
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < KK; t += kRelThreads) {
-      const int i = t / K, j = t - i * K;
-      if (i == j) s_lab[t] = 0;
-      if (i < j) {
-        const LabelPair l = relation_pair(s_box[i], s_box[j], half_diag);
-        s_lab[t] = l.ab;
-        s_lab[j * K + i] = l.ba;
+  }
+  for (int t = tid; t < 2 * kRelMaxK * kRelMaxK; t += nthr) (&s_lab[0][0])[t] = 0;    // the diagonal stays 0
+
+  auto stage_boxes = [&](int img, int buf, float4 bx) {
+    // per-box terms (:28-29,:33-35): area = (y1-y0)(x1-x0), centre = x0 + (x1-x0)/2
+    const float w = __fsub_rn(bx.z, bx.x), h = __fsub_rn(bx.w, bx.y);
+    s_box[buf][tid] = bx;
+    s_ext[buf][tid] = make_float4(__fmul_rn(h, w), __fadd_rn(bx.x, __fmul_rn(w, 0.5f)),
+                                  __fadd_rn(bx.y, __fmul_rn(h, 0.5f)), 0.f);
+    if (tid == 0 && wh != nullptr) {
+      const float2 dd = __ldg(wh + img);
+      s_thr[buf] = near_threshold_sq(0.5 * sqrt((double)dd.x * (double)dd.x + (double)dd.y * (double)dd.y));
+    }
+  };
+
+  int img = blockIdx.x, buf = 0;
+  if (img < B && tid < K) stage_boxes(img, 0, __ldg(bbox + (size_t)img * K + tid));
+  __syncthreads();
+  for (; img < B; img += gridDim.x, buf ^= 1) {
+    const int nxt = img + gridDim.x;
+    float4 nbx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nxt < B && tid < K) nbx = __ldg(bbox + (size_t)nxt * K + tid);     // in flight under the pair math
+    const float s_max = wh != nullptr ? s_thr[buf] : s_max_uniform;
+#pragma unroll
+    for (int u = 0; u < kRelPairsPerThread; ++u) {
+      if (pi[u] >= 0) {
+        const int i = pi[u], j = pj[u];
+        const uint32_t l = relation_pair(s_box[buf][i], s_box[buf][j], s_ext[buf][i], s_ext[buf][j], s_max);
+        s_lab[buf][i * K + j] = (uint8_t)(l & 0xffu);
+        s_lab[buf][j * K + i] = (uint8_t)(l >> 8);
       }
     }
+    if (nxt < B && tid < K) stage_boxes(nxt, buf ^ 1, nbx);
     __syncthreads();
+    // tile of image n leaves while the CTA already works on image n+1 (no second barrier: the tile
+    // is rewritten two images later, after the next barrier)
     uint8_t* out = labels + (size_t)img * KK;
     if ((KK & 15) == 0) {           // 36*36 = 1296 = 81 * 16: vector stores
-      const uint4* src = reinterpret_cast<const uint4*>(s_lab);
+      const uint4* src = reinterpret_cast<const uint4*>(s_lab[buf]);
       uint4* dst = reinterpret_cast<uint4*>(out);
-      for (int t = threadIdx.x; t < KK / 16; t += kRelThreads) dst[t] = src[t];
+      for (int t = tid; t < KK / 16; t += nthr) __stcs(dst + t, src[t]);
     } else {
-      for (int t = threadIdx.x; t < KK; t += kRelThreads) out[t] = s_lab[t];
+      for (int t = tid; t < KK; t += nthr) out[t] = s_lab[buf][t];
     }
-    __syncthreads();
   }
+}
+
+float relation_near_threshold(float img_w, float img_h) {
+  return near_threshold_sq(0.5 * sqrt((double)img_w * (double)img_w + (double)img_h * (double)img_h));
 }
 
 int relation_labels(const float* d_bbox, const float* d_wh, int B, int K, float img_w, float img_h,
@@ -100,10 +175,22 @@ int relation_labels(const float* d_bbox, const float* d_wh, int B, int K, float 
   if (B == 0) return VQA_OK;                       // empty batch: nothing to do (pointers may be NULL)
   VQA_REQUIRE(d_bbox && d_labels, "relation_labels: NULL pointer");
   const double half_diag = 0.5 * sqrt((double)img_w * (double)img_w + (double)img_h * (double)img_h);
-  const int grid = B < sm_count() * 8 ? B : sm_count() * 8;
-  relation_labels_kernel<<<grid, kRelThreads, 0, s>>>(reinterpret_cast<const float4*>(d_bbox),
-                                                      reinterpret_cast<const float2*>(d_wh), B, K,
-                                                      half_diag, d_labels);
+  const int npairs = K * (K - 1) / 2;
+  int threads = (npairs + 31) / 32 * 32;
+  if (threads < 96) threads = 96;                  // >= K box loaders and >= K*K/16 store lanes for small K
+  if (threads < (K + 31) / 32 * 32) threads = (K + 31) / 32 * 32;
+  if (threads > kRelMaxThreads) threads = kRelMaxThreads;
+  auto kernel = npairs <= kRelMaxThreads ? relation_labels_kernel<1> : relation_labels_kernel<2>;
+  static int ctas_per_sm[kRelMaxThreads / 32 + 1] = {0};
+  int& occ = ctas_per_sm[threads / 32];
+  if (occ == 0) {
+    VQA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0));
+    if (occ < 1) occ = 1;
+  }
+  const long long resident = (long long)sm_count() * occ;
+  const int grid = (int)(B < resident ? B : resident);
+  kernel<<<grid, threads, 0, s>>>(reinterpret_cast<const float4*>(d_bbox), reinterpret_cast<const float2*>(d_wh), B, K,
+                                  near_threshold_sq(half_diag), d_labels);
   VQA_LAUNCH_CHECK();
   return VQA_OK;
 }
