@@ -10,10 +10,13 @@
 //   * weights are pre-packed so that the j-th 192-row block of Wx/Wh holds [r | z | n]
 //     rows of units [64j, 64j+64): the three gates of a unit land in the same CTA
 //   * TMEM accumulators (256 fp32 columns, double buffered over time steps):
-//       [0,64) r   [64,128) z   [128,192) W_hn h   [192,256) W_in x
+//       [0,64) r   [64,128) z   [128,192) W_in x + W_hn h   [192,256) W_in x
 //     the x-part of step t+1 (independent of h) is issued while step t's epilogue and
-//     the grid barrier are still in flight
-//   * epilogue threads (one accumulator row each) keep their 64 fp32 state values in
+//     the grid barrier are still in flight.  The h-part is ONE N=192 MMA per k-step on top of
+//     the x-part's [r|z|n] tile (the A tile is read from shared memory once — the kernel is
+//     shared-memory-bandwidth bound: TMA fills + MMA operand reads ≈ 2 MB per step per SM);
+//     the epilogue recovers W_hn h as column [128,192) minus the separately kept W_in x
+//   * epilogue threads (one accumulator row, 16 units each) keep their fp32 state values in
 //     REGISTERS across all steps; only the bf16 copy that feeds the next step's MMA goes
 //     to global memory (double buffered), followed by a grid-wide arrive/wait on a
 //     global counter (release/acquire + async-proxy fence, since TMA reads it)
@@ -165,7 +168,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc_rz = make_idesc_bf16(BM, 2 * UNITS);     // N = 128: r,z rows
+      constexpr uint32_t idesc_rzn = make_idesc_bf16(BM, 3 * UNITS);    // N = 192: r,z,n rows
       constexpr uint32_t idesc_n = make_idesc_bf16(BM, UNITS);          // N = 64 : n rows
       constexpr uint32_t N_ROW_OFF = (2 * UNITS * BK * 2) >> 4;         // rows 128.. of the W tile (16 KB)
       int stage = 0; uint32_t phase = 0;
@@ -182,8 +185,8 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           const uint64_t adesc = make_sw128_kmajor_desc(sa), wdesc = make_sw128_kmajor_desc(sw);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(d + COL_R, adesc + 2 * k, wdesc + 2 * k, idesc_rz, (kb | k) != 0);
-            umma_bf16(d + COL_NI, adesc + 2 * k, wdesc + N_ROW_OFF + 2 * k, idesc_n, (kb | k) != 0);
+            umma_bf16(d + COL_R, adesc + 2 * k, wdesc + 2 * k, idesc_rzn, (kb | k) != 0);       // [r_x | z_x | n_x]
+            umma_bf16(d + COL_NI, adesc + 2 * k, wdesc + N_ROW_OFF + 2 * k, idesc_n, (kb | k) != 0);   // n_x again, kept apart
           }
           if (cs > 1) umma_commit_multicast(empty_bar(stage), cmask); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -196,8 +199,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             const uint64_t adesc = make_sw128_kmajor_desc(sa), wdesc = make_sw128_kmajor_desc(sw);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              umma_bf16(d + COL_R, adesc + 2 * k, wdesc + 2 * k, idesc_rz, 1u);
-              umma_bf16(d + COL_NH, adesc + 2 * k, wdesc + N_ROW_OFF + 2 * k, idesc_n, (kb | k) != 0);
+              umma_bf16(d + COL_R, adesc + 2 * k, wdesc + 2 * k, idesc_rzn, 1u);                  // one MMA, A tile read once
             }
             if (cs > 1) umma_commit_multicast(empty_bar(stage), cmask); else umma_commit(empty_bar(stage));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -231,7 +233,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         tmem_ld_32x8(trow + COL_R + c, vr);
         tmem_ld_32x8(trow + COL_Z + c, vz);
         tmem_ld_32x8(trow + COL_NI + c, vni);
-        if (t > 0) tmem_ld_32x8(trow + COL_NH + c, vnh);
+        tmem_ld_32x8(trow + COL_NH + c, vnh);
         tmem_ld_wait();
         float o[8];
 #pragma unroll
@@ -239,7 +241,8 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           if (p.debug & 2) { o[j] = __uint_as_float(vr[j]) + __uint_as_float(vz[j]) + __uint_as_float(vni[j]); h[c + j] = o[j]; continue; }
           const float pr = __uint_as_float(vr[j]) + bias_s[ub + c + j], pz = __uint_as_float(vz[j]) + bias_s[UNITS + ub + c + j];
           const float r = sigmoid_fast(pr), z = sigmoid_fast(pz);
-          const float nh = (t > 0 ? __uint_as_float(vnh[j]) : 0.f) + bias_s[3 * UNITS + ub + c + j];
+          // columns COL_NH hold n_x + W_hn·h (x-part and h-part accumulate into one N=192 tile); n_x alone is in COL_NI
+          const float nh = (__uint_as_float(vnh[j]) - __uint_as_float(vni[j])) + bias_s[3 * UNITS + ub + c + j];
           const float pn = __uint_as_float(vni[j]) + bias_s[2 * UNITS + ub + c + j] + r * nh;
           const float n = tanh_fast(pn);
           const float hn = (1.f - z) * n + z * h[c + j];
