@@ -15,6 +15,12 @@ checks every function here against them.  The one exception is the float32
 dependent): pinned only on integer-grid boxes and the known-answer
 table of SURVEY.md §8a-R.
 
+Config 5 (predictor 'q-cap', ``qcap_predictor`` below) is PINNED ONLY TO A REPAIRED REFERENCE: the
+reference's ``CaptionEmbedding.forward_all`` (modules.py:291-297) raises as written (SURVEY.md F8);
+``tests/golden/make_golden.py`` swaps in the minimal repair documented there for that ONE method and
+runs everything else (LReLUNet, CaptionAttention, both GRUs, PredictorwithCaption) unmodified.
+Parity for that method itself is therefore unpinned; every other op of config 5 is pinned.
+
 Every function cites the reference file:line it follows (paths relative to the
 reference repository root).  All functions compute in the dtype of their
 inputs, so feeding float64 weights/inputs yields a float64 "truth" run.
@@ -47,6 +53,8 @@ class Config:
     conv_layer: int = 1
     relation: bool = False          # encoder_type 'relation' vs 'base'
     att_type: str = "new"           # 'new' = MultiplyAttention (CLI default main.py:67), 'base' = ConcatAttention
+    predictor: str = "base"         # 'base' = BasePredictor, 'q-cap' = PredictorwithCaption (config 5)
+    neg_slope: float = 0.01         # LeakyReLU slope of the q-cap predictor's own LReLUNets (predictor.py:159)
 
     def as_dict(self):
         return asdict(self)
@@ -61,6 +69,8 @@ SMALL_REGAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_di
                      relation=True)
 SMALL_CONCAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, att_type="base")
 FULL_CONCAT = Config(att_type="base")
+SMALL_QCAP = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, predictor="q-cap")
+FULL_QCAP = Config(predictor="q-cap")
 
 
 def _uniform(gen, shape, bound):
@@ -110,9 +120,34 @@ def make_weights(cfg: Config, seed: int = 1111, sharpen_att: float = 100.0,
         # of the sharpening gives a comparably peaked softmax
         wn_linear("encoder.attention.sequence.2", 1, H, 0.1 * sharpen_att)
     wn_linear("encoder.q_net.main.0", H, H)
-    wn_linear("predictor.v_net.main.0", H, V)
-    wn_linear("predictor.classifier.main.0", 2 * H, H)
-    wn_linear("predictor.classifier.main.3", A, 2 * H, sharpen_cls)
+    if cfg.predictor == "q-cap":
+        # PredictorwithCaption (predictor.py:148-184): bias-free nn.Linear + LeakyReLU stages and two GRUs
+        def lrelu_linear(prefix, out_dim, in_dim, gain=1.0):
+            w[prefix + ".main.0.weight"] = _uniform(g, (out_dim, in_dim), gain / math.sqrt(in_dim))
+
+        def gru(prefix, in_dim):
+            w[prefix + ".weight_ih_l0"] = _uniform(g, (3 * H, in_dim), kb)
+            w[prefix + ".weight_hh_l0"] = _uniform(g, (3 * H, H), kb)
+            w[prefix + ".bias_ih_l0"] = _uniform(g, (3 * H,), kb)
+            w[prefix + ".bias_hh_l0"] = _uniform(g, (3 * H,), kb)
+
+        # "trained-like" gains: the default init shrinks activations ~3x per bias-free layer and the softmax over
+        # H divides by H again, which would leave every gate at its constant mid value (σ≈0.5, softmax≈uniform)
+        lrelu_linear("predictor.v_net", H, V, 4.0)
+        gru("predictor.caption_embedding.word_rnn.rnn", E)
+        gru("predictor.caption_embedding.caption_rnn.rnn", H)
+        lrelu_linear("predictor.caption_embedding.attention.W_v", H, H, 20.0)
+        lrelu_linear("predictor.caption_embedding.attention.W_q", H, H, 100.0)
+        lrelu_linear("predictor.caption_embedding.fcnet", H, H, 3.0)
+        lrelu_linear("predictor.c_net", H, H, 3.0)
+        lrelu_linear("predictor.vq_net", H, H, 2.0)
+        lrelu_linear("predictor.joint_net", H, H, 60.0)
+        lrelu_linear("predictor.vqc_net", H, H, 60.0)
+        w["predictor.classifier.0.main.0.weight"] = _uniform(g, (A, H), 6.0 * sharpen_cls / math.sqrt(H))
+    else:
+        wn_linear("predictor.v_net.main.0", H, V)
+        wn_linear("predictor.classifier.main.0", 2 * H, H)
+        wn_linear("predictor.classifier.main.3", A, 2 * H, sharpen_cls)
 
     if cfg.relation:
         for i in range(cfg.conv_layer):
@@ -193,6 +228,27 @@ def fcnet1(x, W, prefix):
     return torch.relu(F.linear(x, wt, W[prefix + ".main.0.bias"]))
 
 
+def gru_all(x, W, prefix):
+    """nn.GRU(1 layer, batch_first, h0=0), every time step: ``output`` [B,T,H] of
+    SentenceEmbedding.forward_all (modules.py:147-152); the final hidden state is output[:, -1]."""
+    w_ih, w_hh = W[prefix + ".weight_ih_l0"], W[prefix + ".weight_hh_l0"]
+    b_ih, b_hh = W[prefix + ".bias_ih_l0"], W[prefix + ".bias_hh_l0"]
+    B, T, _ = x.shape
+    Hd = w_hh.shape[1]
+    h = torch.zeros((B, Hd), dtype=x.dtype)
+    gi_all = F.linear(x, w_ih, b_ih)
+    outs = []
+    for t in range(T):
+        gi = gi_all[:, t]
+        gh = F.linear(h, w_hh, b_hh)
+        r = torch.sigmoid(gi[:, :Hd] + gh[:, :Hd])
+        z = torch.sigmoid(gi[:, Hd:2 * Hd] + gh[:, Hd:2 * Hd])
+        n = torch.tanh(gi[:, 2 * Hd:] + r * gh[:, 2 * Hd:])
+        h = (1.0 - z) * n + z * h
+        outs.append(h)
+    return torch.stack(outs, 1)
+
+
 def gru_last(x, W, prefix="encoder.q_rnn.rnn"):
     """nn.GRU(1 layer, batch_first, h0=0), last time step (modules.py:139-159).
     Gate order [r; z; n]; n uses r ⊙ (W_hn h + b_hn) (torch GRU semantics)."""
@@ -255,7 +311,10 @@ def base_encoder(batch, W):
     v_att = torch.softmax(attention_logits(v, q, W), dim=1)           # attention.py:51,86
     v = v_att * v
     qn = fcnet1(q, W, "encoder.q_net")
-    return {"v": v, "q": qn, "v_att": v_att, "q_emb": q}
+    out = {"v": v, "q": qn, "v_att": v_att, "q_emb": q}
+    if "c" in batch:
+        out["c"] = W["encoder.embedding.weight"][batch["c"]]          # encoder.py:172 (embedded caption tokens)
+    return out
 
 
 def directed_conv(feature, graph, W, p):
@@ -320,6 +379,41 @@ def base_predictor(enc, W):
     return torch.relu(F.linear(h, w3, W[p + ".3.bias"]))
 
 
+def lrelu_net(x, W, prefix, slope):
+    """LReLUNet (modules.py:62-78): LeakyReLU(Linear(x)), no bias."""
+    return F.leaky_relu(F.linear(x, W[prefix + ".main.0.weight"]), slope)
+
+
+def caption_embedding(v, q, c, W, prefix="predictor.caption_embedding"):
+    """CaptionEmbedding.forward (modules.py:291-306) with the minimal repair of forward_all (SURVEY.md F8 /
+    §8c): the word GRU's final state (not an undefined variable) gates its own outputs.
+        out_w = GRU_word(c)                  [B,T,H]   (modules.py:292; all steps)
+        a     = σ(h_w ⊙ LReLU(W_v v) + h_w ⊙ LReLU(W_q q)),  h_w = out_w[:, -1]   (CaptionAttention, modules.py:225-243;
+                its LReLUNets use the default slope 0.01, dropout = identity in eval)
+        out_c = GRU_cap(a[:,None,:] ⊙ out_w) [B,T,H]   (modules.py:294-295)
+        c_emb = max_t LReLU(W_f out_c)       [B,H]     (modules.py:296,306)"""
+    out_w = gru_all(c, W, prefix + ".word_rnn.rnn")
+    h_w = out_w[:, -1]
+    a = torch.sigmoid(h_w * lrelu_net(v, W, prefix + ".attention.W_v", 0.01)
+                      + h_w * lrelu_net(q, W, prefix + ".attention.W_q", 0.01))
+    out_c = gru_all(a.unsqueeze(1) * out_w, W, prefix + ".caption_rnn.rnn")
+    return lrelu_net(out_c, W, prefix + ".fcnet", 0.01).max(dim=1)[0]
+
+
+def qcap_predictor(enc, W, slope):
+    """PredictorwithCaption.forward (predictor.py:186-213); returns the sigmoid outputs [B,A]."""
+    V = lrelu_net(enc["v"], W, "predictor.v_net", slope)              # [B,K,H]   :188
+    v = V.sum(1)                                                      # :191
+    c = caption_embedding(v, enc["q"], enc["c"], W)                   # :192
+    vq = lrelu_net(v, W, "predictor.vq_net", slope)                   # :196
+    c = lrelu_net(c, W, "predictor.c_net", slope)                     # :197
+    joint = torch.softmax(lrelu_net(c * vq, W, "predictor.joint_net", slope), 1)          # :201-202
+    v = (joint.unsqueeze(1) * V).sum(1)                               # :203  (= joint ⊙ Σ_K V)
+    v = lrelu_net(v, W, "predictor.vqc_net", slope)                   # :208
+    joint = enc["q"] * (v + c)                                        # :209
+    return torch.sigmoid(F.leaky_relu(F.linear(joint, W["predictor.classifier.0.main.0.weight"]), slope))   # :213
+
+
 def compute_score(predict, target):
     """compute_score (wrapper.py:8-22): lowest-index argmax → one-hot ⊙ target."""
     label = torch.max(predict, 1)[1]
@@ -331,7 +425,7 @@ def compute_score(predict, target):
 def forward(batch, W, cfg: Config):
     """Wrapper.forward / get_att composition (wrapper.py:64-74,107-110)."""
     enc = relation_encoder(batch, W, cfg.conv_layer) if cfg.relation else base_encoder(batch, W)
-    logits = base_predictor(enc, W)
+    logits = qcap_predictor(enc, W, cfg.neg_slope) if cfg.predictor == "q-cap" else base_predictor(enc, W)
     return logits, enc
 
 

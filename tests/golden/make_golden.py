@@ -31,10 +31,10 @@ from util.relation import relation_graph, spatial_relation   # noqa: E402
 
 def build_reference(cfg: O.Config, W: dict):
     m = set_model(encoder_type="relation" if cfg.relation else "base",
-                  predictor_type="base", decoder_type="none", ntoken=cfg.ntoken,
+                  predictor_type=cfg.predictor, decoder_type="none", ntoken=cfg.ntoken,
                   v_dim=cfg.v_dim, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim,
                   decoder_hidden_dim=0, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2,
-                  c_len=cfg.c_len, device="cpu", dropout=0.2, rnn_type="GRU",
+                  c_len=cfg.c_len, device="cpu", dropout=0.2, neg_slope=cfg.neg_slope, rnn_type="GRU",
                   att_type=cfg.att_type, conv_layer=cfg.conv_layer, conv_type="corr")
     sd = {k: v for k, v in W.items() if not k.startswith("gcn.")}
     m.load_state_dict(sd, strict=True)
@@ -68,6 +68,50 @@ def run_model(name, cfg, B, wseed, bseed):
             out["alpha"] = m.encoder(ref_batch, True)[0].numpy()
             out["graph"] = batch["graph"].numpy().astype(np.uint8)
     meta = dict(cfg=cfg.as_dict(), B=B, wseed=wseed, bseed=bseed)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array(repr(meta)), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
+def repaired_forward_all(self, v, q, c):
+    """Minimal repair of CaptionEmbedding.forward_all (modules.py:291-297), which raises UnboundLocalError as
+    written: `word_hidden` / `cap_hidden` are read before assignment and
+    SentenceEmbedding.forward_all takes one argument and returns only `output`.  The repair keeps every live
+    line and supplies the one missing value — the word GRU's final hidden state, taken from the same nn.GRU
+    call forward_all makes (modules.py:149-151)."""
+    self.word_rnn.rnn.flatten_parameters()
+    output, word_hidden = self.word_rnn.rnn(c, self.word_rnn.init_hidden(c.size(0)))   # [B,T,H], [1,B,H]
+    word_hidden = self.attention(word_hidden, v, q)                                    # modules.py:293
+    word_hidden = word_hidden.repeat(20, 1, 1).transpose(0, 1)                         # modules.py:294
+    output = self.caption_rnn.forward_all(word_hidden * output)                        # modules.py:295
+    output = self.fcnet(output)                                                        # modules.py:296
+    return output
+
+
+def run_qcap(name, cfg, B, wseed, bseed):
+    """Config 5: the REAL reference (encoder, LReLUNet, CaptionAttention, both GRUs, PredictorwithCaption.forward)
+    with the one broken method replaced by `repaired_forward_all`.  Grad mode stays on: predictor.py:199,211 call
+    retain_grad(), which raises under no_grad."""
+    from modules.modules import CaptionEmbedding
+    assert cfg.c_len == 20                           # modules.py:294 hard-codes repeat(20, ...)
+    W = O.make_weights(cfg, wseed)
+    batch = O.make_batch(cfg, B, bseed)
+    m = build_reference(cfg, W)
+    CaptionEmbedding.forward_all = repaired_forward_all
+    ref_batch = {k: v for k, v in batch.items() if k not in ("bbox", "wh")}
+    enc = m.encoder(ref_batch)
+    enc_q, v_att = enc["q"].detach().clone(), enc["v_att"].detach().clone()
+    # sub-module outputs through the reference's own modules, for stage-wise pinning
+    pr = m.predictor
+    V = pr.v_net(enc["v"])
+    vsum = V.sum(1)
+    c_emb = pr.caption_embedding(vsum, enc["q"], enc["c"])
+    predict = pr(enc)                                # mutates enc['v'] in place (predictor.py:188)
+    score, label, _ = m.forward_vqa(ref_batch)
+    out = {"predict": predict.detach().numpy(), "label": label.numpy(), "score_sum": score.sum(1).detach().numpy(),
+           "v_att": v_att.numpy()[:, :, 0], "q": enc_q.numpy(), "vsum": vsum.detach().numpy(),
+           "c_emb": c_emb.detach().numpy(), "c_grad": pr.c_grad.detach().numpy(),
+           "joint": pr.logit_grad.detach().numpy()}
+    meta = dict(cfg=cfg.as_dict(), B=B, wseed=wseed, bseed=bseed, repaired="CaptionEmbedding.forward_all")
     np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array(repr(meta)), **out)
     print(name, {k: v.shape for k, v in out.items()})
 
@@ -126,6 +170,10 @@ def run_relation():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--qcap-only" in sys.argv:
+        run_qcap("qcap_small", O.SMALL_QCAP, 8, 1111, 6001)
+        run_qcap("qcap_full", O.FULL_QCAP, 4, 1111, 6002)
+        sys.exit(0)
     run_relation()
     run_model("updown_small", O.SMALL, 8, 1111, 2001)
     run_model("regat_small", O.SMALL_REGAT, 8, 1111, 3001)
@@ -135,3 +183,5 @@ if __name__ == "__main__":
     run_model("concat_full", O.FULL_CONCAT, 4, 1111, 4002)
     run_train("train_small", O.SMALL, 16, 1111, 5001, True)
     run_train("train_full", O.FULL, 8, 1111, 5002, False)
+    run_qcap("qcap_small", O.SMALL_QCAP, 8, 1111, 6001)
+    run_qcap("qcap_full", O.FULL_QCAP, 4, 1111, 6002)

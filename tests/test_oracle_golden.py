@@ -46,6 +46,31 @@ def test_forward_matches_reference(golden_dir, name):
         assert np.array_equal(batch["graph"].numpy().astype(np.uint8), z["graph"])
 
 
+@pytest.mark.parametrize("name", ["qcap_small", "qcap_full"])
+def test_qcap_forward_matches_repaired_reference(golden_dir, name):
+    """config 5: the real reference with ONE method repaired (CaptionEmbedding.forward_all, see make_golden.py)"""
+    z, meta = _load(golden_dir, name)
+    assert meta["repaired"] == "CaptionEmbedding.forward_all"
+    cfg = O.Config(**meta["cfg"])
+    W = O.make_weights(cfg, meta["wseed"])
+    batch = O.make_batch(cfg, meta["B"], meta["bseed"])
+    with torch.no_grad():
+        enc = O.base_encoder(batch, W)
+        V = O.lrelu_net(enc["v"], W, "predictor.v_net", cfg.neg_slope)
+        vsum = V.sum(1)
+        c_emb = O.caption_embedding(vsum, enc["q"], enc["c"], W)
+        predict, _ = O.forward(batch, W, cfg)
+        score, label, _ = O.forward_vqa(batch, W, cfg)
+    assert _relerr(enc["v_att"].numpy()[:, :, 0], z["v_att"]) < 1e-5
+    assert _relerr(enc["q"].numpy(), z["q"]) < 1e-5
+    assert _relerr(vsum.numpy(), z["vsum"]) < 1e-5
+    assert _relerr(c_emb.numpy(), z["c_emb"]) < 1e-5
+    assert _relerr(O.lrelu_net(c_emb, W, "predictor.c_net", cfg.neg_slope).numpy(), z["c_grad"]) < 1e-5
+    assert _relerr(predict.numpy(), z["predict"]) < 1e-5
+    assert np.array_equal(label.numpy(), z["label"])
+    assert np.allclose(score.sum(1).numpy(), z["score_sum"])
+
+
 @pytest.mark.parametrize("name", ["updown_full", "concat_full"])
 def test_attention_logits_match_reference(golden_dir, name):
     z, meta = _load(golden_dir, name)
