@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 2
+#define VQA_B200_ABI_VERSION 3
 
 typedef enum {
   VQA_OK = 0,
@@ -81,10 +81,13 @@ int vqa_cast_bf16_to_f32(const void* d_src, float* d_dst, size_t n, void* stream
  * reduction) and the plain nn.Linear maps of gcn.py:101-103 / modules.py:92-93.
  *
  *   y[m,n] = (sum_k A[m,k] * W[n,k]) * scale[n] + bias[n]
- *   if add:   y += add[(m / add_row_div), n]          (f32, ld_add; the q-half of
+ *   if add && !add_after_act:  y += add[(m / add_row_div), n]   (f32, ld_add; the q-half of
  *             ConcatAttention's first layer, attention.py:38-42, broadcast over K)
- *   if relu:  y = max(y, 0)
+ *   if relu:  y = y > 0 ? y : leaky_slope * y         (leaky_slope = 0: ReLU; != 0: the LeakyReLU of
+ *             modules.py:62-78 LReLUNet)
+ *   if add && add_after_act:  y += add[...]           (predictor.py:209  LReLU(W v) + c)
  *   if mul:   y *= mul[(m / mul_row_div), n]          (f32, ld_mul)
+ *   if sigmoid: y = 1 / (1 + exp(-y))                 (predictor.py:181-184 classifier)
  *   if logit_w == NULL:  out[m,n] = y                 (out_dtype, ldo)
  *   else: out_f32[m * n_parts + p] = sum_{n in part p} y * logit_w[n]
  *         with n_parts = ceil(N / vqa_linear_part_width(dtype))
@@ -119,6 +122,10 @@ typedef struct {
    *            of a ReLU whose saved OUTPUT is `mask` (mask_dtype, ld_mask)               */
   int trans_a, trans_w;
   const void* d_mask; int ld_mask; int mask_dtype;
+  /* config-5 epilogue forms (all 0 = the behaviour above) */
+  float leaky_slope;         /* negative-side slope of the activation when relu != 0 */
+  int add_after_act;         /* apply `add` after the activation instead of before   */
+  int sigmoid;               /* logistic function applied last                       */
 } vqa_linear_args;
 
 int vqa_linear(const vqa_linear_args* args, void* stream);
@@ -132,6 +139,10 @@ int vqa_linear_part_width(int dtype);
  *   (zero padded to ld_emb), w_hh [3H,H] (dtype); biases f32 [3H].
  *   workspace: vqa_gru_workspace_bytes(B,T,H,ld_emb,dtype) bytes.
  *   out: h_last f32 [B,H]; if d_h_last_lp != NULL also written in `dtype`.
+ * Sequence form (config 5, replaces modules.py:147-152 SentenceEmbedding.forward_all):
+ *   d_x != NULL      : dense inputs [B*T, E_pad] (dtype) instead of tokens + embedding gather
+ *   d_out_all != NULL: every hidden state, [B,T,H] in `dtype` (d_h_last may then be NULL;
+ *                      d_h_last_lp is ignored).
  * ---------------------------------------------------------------------- */
 typedef struct {
   const int64_t* d_tokens;
@@ -148,6 +159,7 @@ typedef struct {
   const void* d_wx_packed; const void* d_wh_packed; const float* d_bias_packed;
   void* d_workspace;   size_t workspace_bytes;
   float* d_h_last;     void* d_h_last_lp;
+  const void* d_x;     void* d_out_all;
 } vqa_gru_args;
 
 int vqa_gru_last_state(const vqa_gru_args* args, void* stream);
@@ -216,6 +228,22 @@ int vqa_graph_attention(const vqa_graph_attention_args* args, void* stream);
  * ---------------------------------------------------------------------- */
 int vqa_argmax_rows(const float* d_logits, int B, int A, int ld, int64_t* d_label,
                     void* stream);
+
+/* ------------------------------------------------------------------------
+ * config 5 (predictor_type 'q-cap') glue between the GEMMs and the two caption GRUs
+ * (all tensors contiguous, H % 8 == 0, 16-byte aligned; `dtype` = element type of the
+ * non-f32 tensors):
+ *  vqa_caption_gate_scale  replaces modules.py:225-243 (CaptionAttention) + :294-295:
+ *      a = sigmoid(h_w*p + h_w*r), h_w = out_w[:, T-1, :];  in2[b,t,:] = a[b,:] * out_w[b,t,:]
+ *      out_w, in2 [B,T,H] (dtype); p, r f32 [B,H] = LReLU(W_v v), LReLU(W_q q); d_a f32 [B,H] optional
+ *  vqa_seq_max             replaces modules.py:306 (output.max(dim=1)[0]): [B,T,H] -> [B,H] (dtype)
+ *  vqa_softmax_mul         replaces predictor.py:202-203: out = softmax_H(z) * v, z f32 [B,H],
+ *      v, out [B,H] (dtype)   (sum_K (joint*V_k) == joint * sum_K V_k, so v is the pooled feature)
+ * ---------------------------------------------------------------------- */
+int vqa_caption_gate_scale(const void* d_out_w, const float* d_p, const float* d_r, int B, int T, int H,
+                           int dtype, void* d_in2, float* d_a, void* stream);
+int vqa_seq_max(const void* d_e, int B, int T, int H, int dtype, void* d_out, void* stream);
+int vqa_softmax_mul(const float* d_z, const void* d_v, int B, int H, int dtype, void* d_out, void* stream);
 
 /* ------------------------------------------------------------------------
  * whole path: Wrapper.forward / forward_vqa (wrapper.py:64-74,113-118) for

@@ -142,8 +142,8 @@ def make_weights(cfg: Config, seed: int = 1111, sharpen_att: float = 100.0,
         lrelu_linear("predictor.c_net", H, H, 3.0)
         lrelu_linear("predictor.vq_net", H, H, 2.0)
         lrelu_linear("predictor.joint_net", H, H, 60.0)
-        lrelu_linear("predictor.vqc_net", H, H, 60.0)
-        w["predictor.classifier.0.main.0.weight"] = _uniform(g, (A, H), 6.0 * sharpen_cls / math.sqrt(H))
+        lrelu_linear("predictor.vqc_net", H, H, 40.0)
+        w["predictor.classifier.0.main.0.weight"] = _uniform(g, (A, H), 4.0 * sharpen_cls / math.sqrt(H))
     else:
         wn_linear("predictor.v_net.main.0", H, V)
         wn_linear("predictor.classifier.main.0", 2 * H, H)

@@ -1,0 +1,162 @@
+"""GPU parity of BASELINE config 5 (predictor_type 'q-cap': question-relevant caption embedding + Up-Down
+attention) — the ops it adds (sequence GRU, LeakyReLU / add-after-activation / sigmoid GEMM epilogues, the three
+caption glue kernels) against torch-CPU restatements, and the whole Wrapper API against the goldens of the
+reference with its one broken method repaired (tests/golden/make_golden.py::run_qcap)."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import vqa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vqa_collection_b200 import ops as o
+    return o
+
+
+def build_model(cfg, W, device="cuda"):
+    from vqa_collection_b200.modules.wrapper import set_model
+    m = set_model(encoder_type="base", predictor_type=cfg.predictor, decoder_type="none", ntoken=cfg.ntoken,
+                  v_dim=cfg.v_dim, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim, decoder_hidden_dim=0,
+                  rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2, c_len=cfg.c_len, device=device, dropout=0.2,
+                  neg_slope=cfg.neg_slope, rnn_type="GRU", att_type=cfg.att_type)
+    m.load_state_dict(W, strict=True)
+    return m.eval()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(64, 128, 128), (300, 200, 192), (1024, 3129, 1024)])
+def test_linear_leaky_add_after_sigmoid(ops, dtype, M, N, K):
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn((M, K), generator=g).to(dtype)
+    Wt = (torch.randn((N, K), generator=g) / K ** 0.5).to(dtype)
+    add, mul = torch.randn((M, N), generator=g), torch.randn((M, N), generator=g)
+    acc = A.double() @ Wt.double().T
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    y = ops.linear(A.cuda(), Wt.cuda(), relu=True, leaky_slope=0.01, out_dtype=torch.float32)
+    assert relerr(y, F.leaky_relu(acc, 0.01)) < tol
+    y = ops.linear(A.cuda(), Wt.cuda(), relu=True, leaky_slope=0.3, add=add.cuda(), add_after_act=True, mul=mul.cuda(),
+                   out_dtype=torch.float32)
+    assert relerr(y, (F.leaky_relu(acc, 0.3) + add.double()) * mul.double()) < tol
+    y = ops.linear(A.cuda(), Wt.cuda(), relu=True, leaky_slope=0.01, sigmoid=True, out_dtype=torch.float32)
+    assert relerr(y, torch.sigmoid(F.leaky_relu(acc, 0.01))) < tol
+    # slope 0 stays the plain ReLU, add-before-activation stays the default
+    y = ops.linear(A.cuda(), Wt.cuda(), relu=True, add=add.cuda(), out_dtype=torch.float32)
+    assert relerr(y, torch.relu(acc + add.double())) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,E,H", [(5, 20, 64, 128), (3, 20, 300, 1024), (130, 7, 128, 128), (64, 20, 1024, 1024)])
+def test_gru_sequence_all_states(ops, dtype, B, T, E, H):
+    from vqa_collection_b200.engine import pack_gru
+    g = torch.Generator().manual_seed(B * T)
+    kb = 1.0 / H ** 0.5
+    W = {"r.weight_ih_l0": (torch.rand((3 * H, E), generator=g) * 2 - 1) * kb,
+         "r.weight_hh_l0": (torch.rand((3 * H, H), generator=g) * 2 - 1) * kb,
+         "r.bias_ih_l0": (torch.rand((3 * H,), generator=g) * 2 - 1) * kb,
+         "r.bias_hh_l0": (torch.rand((3 * H,), generator=g) * 2 - 1) * kb}
+    x = torch.randn((B, T, E), generator=g)
+    ref = O.gru_all(x, W, "r")
+    E_pad = (E + 63) // 64 * 64
+    xp = torch.zeros((B, T, E_pad), dtype=dtype)
+    xp[:, :, :E] = x.to(dtype)
+    w_ih = torch.zeros((3 * H, E_pad), dtype=dtype)
+    w_ih[:, :E] = W["r.weight_ih_l0"].to(dtype)
+    w_ih, w_hh = w_ih.cuda(), W["r.weight_hh_l0"].to(dtype).cuda()
+    b_ih, b_hh = W["r.bias_ih_l0"].cuda(), W["r.bias_hh_l0"].cuda()
+    packed = pack_gru(w_ih, w_hh, b_ih, b_hh) if dtype == torch.bfloat16 else None
+    out, last = ops.gru_sequence(xp.cuda(), w_ih, b_ih, w_hh, b_hh, packed=packed, want_last=True)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert out.shape == (B, T, H) and out.dtype == dtype
+    assert relerr(out, ref) < tol
+    assert relerr(last, ref[:, -1]) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_caption_glue_kernels(ops, dtype):
+    g = torch.Generator().manual_seed(9)
+    B, T, H = 7, 20, 256
+    out_w = torch.randn((B, T, H), generator=g).to(dtype)
+    p, r = torch.randn((B, H), generator=g), torch.randn((B, H), generator=g)
+    hw = out_w[:, -1].float()
+    a_ref = torch.sigmoid(hw * p + hw * r)
+    in2, a = ops.caption_gate_scale(out_w.cuda(), p.cuda(), r.cuda(), want_a=True)
+    tol = 1e-6 if dtype == torch.float32 else 4e-3           # one bf16 rounding of the product
+    assert relerr(a, a_ref) < 1e-6
+    assert relerr(in2, a_ref[:, None, :] * out_w.float()) < tol
+    assert torch.equal(ops.seq_max(out_w.cuda()).cpu(), out_w.max(dim=1)[0])        # exact: a max of inputs
+    z = torch.randn((B, H), generator=g) * 3
+    v = torch.randn((B, H), generator=g).to(dtype)
+    sm = ops.softmax_mul(z.cuda(), v.cuda())
+    assert relerr(sm, torch.softmax(z.double(), 1) * v.double()) < (1e-6 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["qcap_small", "qcap_full"])
+def test_qcap_wrapper_matches_repaired_reference(golden_dir, name, precision):
+    import vqa_collection_b200 as pkg
+    pkg.set_precision(precision)
+    try:
+        z = np.load(os.path.join(golden_dir, name + ".npz"))
+        meta = ast.literal_eval(str(z["meta"]))
+        cfg = O.Config(**meta["cfg"])
+        W = O.make_weights(cfg, meta["wseed"])
+        batch = O.make_batch(cfg, meta["B"], meta["bseed"])
+        m = build_model(cfg, W)
+        tol = 1e-5 if precision == "fp32" else 1e-2
+        with torch.no_grad():
+            predict, att = m.get_att(dict(batch))
+            score, label, target = m.forward_vqa(dict(batch))
+        assert relerr(att[:, :, 0], z["v_att"]) < tol
+        assert relerr(m.predictor.c_grad, z["c_grad"]) < tol
+        assert relerr(m.predictor.logit_grad, z["joint"]) < (tol if precision == "fp32" else 3e-2)
+        assert relerr(predict, z["predict"]) < tol
+        if precision == "fp32":
+            assert np.array_equal(label.cpu().numpy(), z["label"])
+            assert np.allclose(score.sum(1).cpu().numpy(), z["score_sum"])
+    finally:
+        pkg.set_precision("bf16")
+
+
+@pytest.mark.parametrize("precision,B", [("fp32", 16), ("bf16", 96)])
+def test_qcap_full_dims_matches_oracle(precision, B):
+    import vqa_collection_b200 as pkg
+    pkg.set_precision(precision)
+    try:
+        cfg = O.FULL_QCAP
+        W = O.make_weights(cfg, 1111)
+        batch = O.make_batch(cfg, B, 6100)
+        with torch.no_grad():
+            ref, enc = O.forward(batch, W, cfg)
+        m = build_model(cfg, W)
+        with torch.no_grad():
+            predict, _ = m(dict(batch))
+        tol = 1e-5 if precision == "fp32" else 1e-2
+        assert relerr(predict, ref) < tol
+        # answers agree wherever the reference's top-2 margin exceeds 4x the error observed on that question
+        err = (predict.cpu() - ref).abs().max(dim=1).values
+        top2 = torch.topk(ref, 2, dim=1).values
+        safe = (top2[:, 0] - top2[:, 1]) > 4 * err
+        assert safe.float().mean() > (0.99 if precision == "fp32" else 0.25)
+        assert torch.equal(predict.cpu().argmax(1)[safe], ref.argmax(1)[safe])
+    finally:
+        pkg.set_precision("bf16")

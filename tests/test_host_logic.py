@@ -119,6 +119,26 @@ def test_unsupported_configurations_raise():
         set_model(decoder_type="base", device="cpu")
 
 
+def test_qcap_parameter_names_and_checkpoint_loading():
+    """predictor_type='q-cap' (BASELINE config 5) keeps the reference's parameter names: the oracle's weight dict
+    (keyed like the reference's state_dict, pinned by tests/golden/qcap_*.npz) loads strictly"""
+    from vqa_collection_b200.modules.wrapper import set_model
+    cfg = O.SMALL_QCAP
+    W = O.make_weights(cfg, 1111)
+    m = set_model(encoder_type="base", predictor_type="q-cap", decoder_type="none", ntoken=cfg.ntoken, v_dim=cfg.v_dim,
+                  embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim, decoder_hidden_dim=0, rnn_layer=1,
+                  ans_dim=cfg.ans_dim, cls_layer=2, c_len=cfg.c_len, device="cpu", dropout=0.2,
+                  neg_slope=cfg.neg_slope, rnn_type="GRU", att_type="new")
+    sd = m.state_dict()
+    assert set(sd) == set(W), set(sd) ^ set(W)
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(W[k].shape), k
+    m.load_state_dict(W, strict=True)
+    with pytest.raises(NotImplementedError):
+        set_model(predictor_type="base-cap", decoder_type="none", device="cpu", ntoken=10, v_dim=8, embed_dim=8,
+                  hidden_dim=8, ans_dim=4, cls_layer=2, rnn_layer=1, att_type="new")
+
+
 def test_concat_attention_parameter_names():
     """att_type='base' keeps the reference's names (encoder.attention.sequence.{0,2}.*)"""
     from vqa_collection_b200.modules.wrapper import set_model

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
 
 VQA_F32, VQA_BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -30,6 +30,7 @@ class LinearArgs(C.Structure):
         ("d_add", c_void_p), ("ld_add", c_int), ("add_row_div", c_int),
         ("trans_a", c_int), ("trans_w", c_int),
         ("d_mask", c_void_p), ("ld_mask", c_int), ("mask_dtype", c_int),
+        ("leaky_slope", c_float), ("add_after_act", c_int), ("sigmoid", c_int),
     ]
 
 
@@ -44,6 +45,7 @@ class GruArgs(C.Structure):
         ("d_wx_packed", c_void_p), ("d_wh_packed", c_void_p), ("d_bias_packed", c_void_p),
         ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("d_h_last", c_void_p), ("d_h_last_lp", c_void_p),
+        ("d_x", c_void_p), ("d_out_all", c_void_p),
     ]
 
 
@@ -132,6 +134,10 @@ SYMBOLS = {
     "vqa_attention_pool": (c_int, [c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "vqa_graph_attention": (c_int, [C.POINTER(GraphAttentionArgs), c_void_p]),
+    "vqa_caption_gate_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                       c_void_p]),
+    "vqa_seq_max": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vqa_softmax_mul": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vqa_argmax_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vqa_forward_workspace_bytes": (c_size_t, [C.POINTER(ForwardArgs)]),
     "vqa_forward": (c_int, [C.POINTER(ForwardArgs), c_void_p]),

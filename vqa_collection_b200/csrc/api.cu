@@ -51,10 +51,13 @@ int require_sm100() {
 // kernels implemented in the other translation units
 int relation_labels(const float*, const float*, int, int, float, float, uint8_t*, cudaStream_t);
 float relation_near_threshold(float, float);
+int caption_gate_scale(const void*, const float*, const float*, int, int, int, int, void*, float*, cudaStream_t);
+int seq_max(const void*, int, int, int, int, void*, cudaStream_t);
+int softmax_mul(const float*, const void*, int, int, int, void*, cudaStream_t);
 int attention_pool(const float*, int, float, const void*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int argmax_rows(const float*, int, int, int, int64_t*, cudaStream_t);
 int embedding_gather(const int64_t*, int, int, int, int, const void*, void*, cudaStream_t);
-int gru_gate(const float*, const float*, int, int, int, int, const float*, float*, void*, int, cudaStream_t);
+int gru_gate(const float*, const float*, int, int, int, int, const float*, float*, void*, int, int, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
 int cast_bf16_to_f32(const void*, float*, size_t, cudaStream_t);
 int graph_attention(const vqa_graph_attention_args&, cudaStream_t);
@@ -62,7 +65,7 @@ int graph_attention_tc(const vqa_graph_attention_args&, cudaStream_t);
 size_t train_workspace_bytes(const vqa_train_args&);
 int updown_train_step(const vqa_train_args&, cudaStream_t);
 int gru_persistent(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
-                   cudaStream_t);
+                   void*, cudaStream_t);
 
 static bool force_simt() {
   static int v = -1;
@@ -104,8 +107,8 @@ static GruWs carve_gru(void* base, int B, int T, int H, int E_pad, int dtype) {
 }
 
 static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
-  VQA_REQUIRE(a.d_tokens && a.d_emb && a.d_w_ih && a.d_w_hh && a.d_b_ih && a.d_b_hh && a.d_h_last,
-              "vqa_gru_last_state: NULL pointer");
+  VQA_REQUIRE(((a.d_tokens && a.d_emb) || a.d_x) && a.d_w_ih && a.d_w_hh && a.d_b_ih && a.d_b_hh &&
+              (a.d_h_last || a.d_out_all), "vqa_gru_last_state: NULL pointer");
   VQA_REQUIRE(a.B >= 0 && a.T >= 1 && a.H >= 1 && a.E_pad >= 1, "vqa_gru_last_state: bad dims");
   const GruWs need = carve_gru(nullptr, a.B, a.T, a.H, a.E_pad, a.dtype);
   VQA_REQUIRE(a.d_workspace && a.workspace_bytes >= need.bytes,
@@ -113,29 +116,41 @@ static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
   if (a.B == 0) return VQA_OK;
   const GruWs w = carve_gru(a.d_workspace, a.B, a.T, a.H, a.E_pad, a.dtype);
   int rc;
-  if ((rc = embedding_gather(a.d_tokens, a.B * a.T, a.E_pad, a.ntoken_rows, a.dtype, a.d_emb, w.X, s))) return rc;
-  if (a.dtype == VQA_BF16 && a.d_wx_packed && a.d_wh_packed && a.d_bias_packed && !force_simt() && a.H % 64 == 0)
-    return gru_persistent(w.X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
-                          a.d_h_last, a.d_h_last_lp, s);
+  const void* X = a.d_x;
+  if (!X) {
+    if ((rc = embedding_gather(a.d_tokens, a.B * a.T, a.E_pad, a.ntoken_rows, a.dtype, a.d_emb, w.X, s))) return rc;
+    X = w.X;
+  }
+  if (a.dtype == VQA_BF16 && a.d_wx_packed && a.d_wh_packed && a.d_bias_packed && !force_simt() && a.H % 64 == 0 &&
+      a.E_pad % 64 == 0)
+    return gru_persistent(X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
+                          a.d_h_last, a.d_h_last_lp, a.d_out_all, s);
   // gi = X W_ihᵀ + b_ih for all T steps at once: [B*T, 3H] f32
   vqa_linear_args gi{};
-  gi.d_A = w.X; gi.lda = a.E_pad; gi.d_W = a.d_w_ih; gi.ldw = a.E_pad;
+  gi.d_A = X; gi.lda = a.E_pad; gi.d_W = a.d_w_ih; gi.ldw = a.E_pad;
   gi.M = a.B * a.T; gi.N = 3 * a.H; gi.K = a.E_pad; gi.dtype = a.dtype;
   gi.d_bias = a.d_b_ih; gi.d_out = w.gi; gi.ldo = 3 * a.H; gi.out_dtype = VQA_F32; gi.mul_row_div = 1;
   if ((rc = linear_dispatch(gi, s))) return rc;
   VQA_CUDA_CHECK(cudaMemsetAsync(w.h, 0, (size_t)a.B * a.H * 4, s));
   VQA_CUDA_CHECK(cudaMemsetAsync(w.h_lp, 0, (size_t)a.B * a.H * elem_size(a.dtype), s));
+  const size_t es = elem_size(a.dtype);
   for (int t = 0; t < a.T; ++t) {
+    // operand of this step's recurrent GEMM: the [B,H] copy, or (sequence form) the previous slice of [B,T,H]
+    const bool from_all = a.d_out_all && t > 0;
     vqa_linear_args gh{};
-    gh.d_A = w.h_lp; gh.lda = a.H; gh.d_W = a.d_w_hh; gh.ldw = a.H;
+    gh.d_A = from_all ? (const void*)((const char*)a.d_out_all + (size_t)(t - 1) * a.H * es) : w.h_lp;
+    gh.lda = from_all ? a.T * a.H : a.H;
+    gh.d_W = a.d_w_hh; gh.ldw = a.H;
     gh.M = a.B; gh.N = 3 * a.H; gh.K = a.H; gh.dtype = a.dtype;
     gh.d_bias = a.d_b_hh; gh.d_out = w.gh; gh.ldo = 3 * a.H; gh.out_dtype = VQA_F32; gh.mul_row_div = 1;
     if ((rc = linear_dispatch(gh, s))) return rc;
     const bool last = (t == a.T - 1);
     // state kept in f32 (w.h, updated in place) plus the low-precision copy that feeds the
     // next step's GEMM; the last step writes the caller's buffers
-    if ((rc = gru_gate(w.gi, w.gh, a.B, a.H, a.T, t, w.h, last ? a.d_h_last : w.h,
-                       (last && a.d_h_last_lp) ? a.d_h_last_lp : w.h_lp, a.dtype, s))) return rc;
+    void* lp = a.d_out_all ? (void*)((char*)a.d_out_all + (size_t)t * a.H * es)
+                           : ((last && a.d_h_last_lp) ? a.d_h_last_lp : w.h_lp);
+    if ((rc = gru_gate(w.gi, w.gh, a.B, a.H, a.T, t, w.h, (last && a.d_h_last) ? a.d_h_last : w.h, lp,
+                       a.d_out_all ? a.T * a.H : a.H, a.dtype, s))) return rc;
   }
   return VQA_OK;
 }
@@ -237,6 +252,20 @@ int vqa_graph_attention(const vqa_graph_attention_args* args, void* stream) {
 int vqa_argmax_rows(const float* d_logits, int B, int A, int ld, int64_t* d_label, void* stream) {
   if (int rc = require_sm100()) return rc;
   return argmax_rows(d_logits, B, A, ld, d_label, (cudaStream_t)stream);
+}
+
+int vqa_caption_gate_scale(const void* d_out_w, const float* d_p, const float* d_r, int B, int T, int H, int dtype,
+                           void* d_in2, float* d_a, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return caption_gate_scale(d_out_w, d_p, d_r, B, T, H, dtype, d_in2, d_a, (cudaStream_t)stream);
+}
+int vqa_seq_max(const void* d_e, int B, int T, int H, int dtype, void* d_out, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return seq_max(d_e, B, T, H, dtype, d_out, (cudaStream_t)stream);
+}
+int vqa_softmax_mul(const float* d_z, const void* d_v, int B, int H, int dtype, void* d_out, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return softmax_mul(d_z, d_v, B, H, dtype, d_out, (cudaStream_t)stream);
 }
 
 // ---- whole path --------------------------------------------------------------

@@ -16,6 +16,7 @@ struct Epilogue {
   const void* mask; int ld_mask; int mask_bf16;
   const float* logit_w;
   void* out; int ldo; int out_dtype; int n_parts;
+  float leaky_slope; int add_after_act; int sigmoid;
 };
 
 // TA / TW: the operand is given with the contraction index as the ROW index ([K,M] / [K,N]
@@ -102,14 +103,16 @@ linear_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ W, in
         float y = acc[i][j];
         if (ep.scale) y *= ep.scale[n];
         if (ep.bias) y += ep.bias[n];
-        if (ep.add) y += ep.add[(size_t)(m / ep.add_row_div) * ep.ld_add + n];
-        if (ep.relu) y = fmaxf(y, 0.f);
+        if (ep.add && !ep.add_after_act) y += ep.add[(size_t)(m / ep.add_row_div) * ep.ld_add + n];
+        if (ep.relu) y = ep.leaky_slope == 0.f ? fmaxf(y, 0.f) : (y > 0.f ? y : ep.leaky_slope * y);
+        if (ep.add && ep.add_after_act) y += ep.add[(size_t)(m / ep.add_row_div) * ep.ld_add + n];
         if (ep.mul) y *= ep.mul[(size_t)(m / ep.mul_row_div) * ep.ld_mul + n];
         if (ep.mask) {
           const float mk = ep.mask_bf16 ? __bfloat162float(((const __nv_bfloat16*)ep.mask)[(size_t)m * ep.ld_mask + n])
                                         : ((const float*)ep.mask)[(size_t)m * ep.ld_mask + n];
           if (!(mk > 0.f)) y = 0.f;
         }
+        if (ep.sigmoid) y = 1.f / (1.f + expf(-y));
         if (ep.logit_w) {
           part = fmaf(y, ep.logit_w[n], part);
         } else if (ep.out_dtype == VQA_BF16) {
@@ -147,7 +150,7 @@ int linear_simt(const vqa_linear_args& a, cudaStream_t s) {
   Epilogue ep{a.d_scale, a.d_bias, a.relu, a.d_mul, a.ld_mul, a.mul_row_div > 0 ? a.mul_row_div : 1,
               a.d_add, a.ld_add, a.add_row_div > 0 ? a.add_row_div : 1,
               a.d_mask, a.ld_mask, a.mask_dtype == VQA_BF16, a.d_logit_w, a.d_out, a.ldo, a.out_dtype,
-              (a.N + SBN - 1) / SBN};
+              (a.N + SBN - 1) / SBN, a.leaky_slope, a.add_after_act, a.sigmoid};
   dim3 grid((a.N + SBN - 1) / SBN, (a.M + SBM - 1) / SBM);
   if (a.dtype == VQA_BF16) launch_simt<__nv_bfloat16>(a, ep, grid, s);
   else launch_simt<float>(a, ep, grid, s);

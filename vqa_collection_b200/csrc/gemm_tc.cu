@@ -52,6 +52,7 @@ struct Params {
   const float* logit_w;
   void* out; int ldo; int out_bf16; int n_parts;
   int tiles_m, tiles_n;
+  float leaky_slope; int add_after_act; int sigmoid;
 };
 
 // ---- the kernel ----------------------------------------------------------------
@@ -191,7 +192,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool full = nbase + 32 <= p.N;
 #pragma unroll
         for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), ps[c0 + j], ps[BN + c0 + j]);
-        if (add_row) {
+        if (add_row && !p.add_after_act) {
           if (add_vec && full) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
@@ -204,9 +205,27 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (p.relu) {
+          if (p.leaky_slope == 0.f) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = y[j] > 0.f ? y[j] : p.leaky_slope * y[j];
+          }
         }
+        if (add_row && p.add_after_act) {
+          if (add_vec && full) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(add_row + nbase) + j4);
+              y[4 * j4] += a4.x; y[4 * j4 + 1] += a4.y; y[4 * j4 + 2] += a4.z; y[4 * j4 + 3] += a4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nbase + j < p.N) y[j] += __ldg(add_row + nbase + j);
+          }
+        }
+
         if (mul_row) {
           if (mul_vec && full) {
 #pragma unroll
@@ -229,6 +248,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (nbase + j < p.N && !(__ldg(mk + j) > 0.f)) y[j] = 0.f;
           }
+        }
+        if (p.sigmoid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = __fdividef(1.f, 1.f + __expf(-y[j]));
         }
         if (p.logit_w) {
 #pragma unroll
@@ -340,6 +363,7 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
   p.mask = a.d_mask; p.ld_mask = a.ld_mask; p.mask_bf16 = (a.mask_dtype == VQA_BF16);
   p.logit_w = a.d_logit_w; p.out = a.d_out; p.ldo = a.ldo; p.out_bf16 = (a.out_dtype == VQA_BF16);
   p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
+  p.leaky_slope = a.leaky_slope; p.add_after_act = a.add_after_act; p.sigmoid = a.sigmoid;
   auto kern = linear_tc_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {

@@ -59,8 +59,10 @@ struct Params {
   int cs;                       // cluster size along the unit dimension (1, 2, 4 or 8)
   const float* bias;            // packed [4H]: b_ir+b_hr | b_iz+b_hz | b_in | b_hn
   __nv_bfloat16* h_op[2];       // bf16 state, double buffered over steps
-  float* h_last;                // [B,H] f32
+  float* h_last;                // [B,H] f32 or NULL
   __nv_bfloat16* h_last_lp;     // [B,H] bf16 or NULL
+  __nv_bfloat16* h_all;         // [B,T,H] bf16 or NULL: every state; then it also IS the operand buffer
+                                // (both tensor maps view it as [B, T*H], step t reads columns (t-1)*H..)
   int* counter;                 // per-row-block arrival counters [tiles_m], zero on entry
   int debug;                    // timing experiments only (VQA_B200_GRU_DEBUG): 1 no barrier wait, 2 no gate math, 4 no fence, 8 no h-tile loads, 16 no W_h-tile loads
 };
@@ -152,13 +154,14 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           if (!(p.debug & 1)) while (ld_acquire_gpu(p.counter + m_blk) < target) { }
           fence_proxy_async_all();
           const CUtensorMap* tmH = ((t - 1) & 1) ? &tmH1 : &tmH0;
+          const int hcol = p.h_all ? (t - 1) * p.H : 0;
           for (int kb = 0; kb < npre; ++kb)
-            if (!(p.debug & 8)) load_a(base + pre_stage[kb] * STAGE_BYTES, tmH, full_bar(pre_stage[kb]), kb * BK);
+            if (!(p.debug & 8)) load_a(base + pre_stage[kb] * STAGE_BYTES, tmH, full_bar(pre_stage[kb]), hcol + kb * BK);
           for (int kb = npre; kb < kb_h; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
             mbar_arrive_expect_tx(full_bar(stage), ((p.debug & 8) ? 0 : A_BYTES) + ((p.debug & 16) ? 0 : W_BYTES));
-            if (!(p.debug & 8)) load_a(sa, tmH, full_bar(stage), kb * BK);
+            if (!(p.debug & 8)) load_a(sa, tmH, full_bar(stage), hcol + kb * BK);
             if (!(p.debug & 16)) tma_load_2d(sw, &tmWh, full_bar(stage), kb * BK, n_blk * WROWS);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -226,7 +229,8 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16) + ub;
       const bool last = (t == p.T - 1);
-      __nv_bfloat16* hdst = (last && p.h_last_lp) ? p.h_last_lp : p.h_op[t & 1];
+      __nv_bfloat16* hdst = p.h_all ? p.h_all + (size_t)t * p.H : ((last && p.h_last_lp) ? p.h_last_lp : p.h_op[t & 1]);
+      const size_t h_ld = p.h_all ? (size_t)p.T * p.H : (size_t)p.H;
 #pragma unroll
       for (int c = 0; c < UPT; c += 8) {
         uint32_t vr[8], vz[8], vni[8], vnh[8];
@@ -253,7 +257,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           uint4 w0;
           w0.x = pack_bf16x2(o[0], o[1]); w0.y = pack_bf16x2(o[2], o[3]);
           w0.z = pack_bf16x2(o[4], o[5]); w0.w = pack_bf16x2(o[6], o[7]);
-          *reinterpret_cast<uint4*>(hdst + (size_t)row * p.H + u0 + ub + c) = w0;
+          *reinterpret_cast<uint4*>(hdst + (size_t)row * h_ld + u0 + ub + c) = w0;
         }
       }
       tcgen05_fence_before();
@@ -269,7 +273,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
       }
     }
-    if (row_ok) {
+    if (row_ok && p.h_last) {
       float* dst = p.h_last + (size_t)row * p.H + u0 + ub;
 #pragma unroll
       for (int j = 0; j < UPT; j += 4)
@@ -289,7 +293,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 // X [B*T, E_pad] bf16 (row b*T+t); wx_p [3H,E_pad], wh_p [3H,H] packed; bias_p [4H];
 // h_op: 2*B*H bf16 scratch; counter: >= 64 ints (zeroed here).
 int gru_persistent(const void* X, int B, int T, int H, int E_pad, const void* wx_p, const void* wh_p,
-                   const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp,
+                   const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
                    cudaStream_t s) {
   using namespace gru;
   VQA_REQUIRE(H % UNITS == 0 && E_pad % tc::BK == 0, "gru(bf16): H=%d must be a multiple of 64 and E_pad=%d of 64", H, E_pad);
@@ -323,12 +327,19 @@ int gru_persistent(const void* X, int B, int T, int H, int E_pad, const void* wx
     __nv_bfloat16* h1 = (__nv_bfloat16*)h_op + (size_t)B * H + (size_t)b0 * H;
     CUtensorMap tmX, tmH0, tmH1;
     if ((rc = tc::make_tensor_map_bf16(&tmX, Xc, Bc, (long long)T * E_pad, (long long)T * E_pad, tc::BM / cs))) return rc;
-    if ((rc = tc::make_tensor_map_bf16(&tmH0, h0, Bc, H, H, tc::BM / cs))) return rc;
-    if ((rc = tc::make_tensor_map_bf16(&tmH1, h1, Bc, H, H, tc::BM / cs))) return rc;
+    __nv_bfloat16* hall = h_all ? (__nv_bfloat16*)h_all + (size_t)b0 * T * H : nullptr;
+    if (hall) {
+      if ((rc = tc::make_tensor_map_bf16(&tmH0, hall, Bc, (long long)T * H, (long long)T * H, tc::BM / cs))) return rc;
+      tmH1 = tmH0;
+    } else {
+      if ((rc = tc::make_tensor_map_bf16(&tmH0, h0, Bc, H, H, tc::BM / cs))) return rc;
+      if ((rc = tc::make_tensor_map_bf16(&tmH1, h1, Bc, H, H, tc::BM / cs))) return rc;
+    }
     Params p;
     p.B = Bc; p.T = T; p.H = H; p.E_pad = E_pad; p.tiles_n = tiles_n; p.num_ctas = tiles_m * tiles_n;
     p.bias = bias_p; p.h_op[0] = h0; p.h_op[1] = h1;
-    p.h_last = h_last + (size_t)b0 * H;
+    p.h_last = h_last ? h_last + (size_t)b0 * H : nullptr;
+    p.h_all = hall;
     p.h_last_lp = h_last_lp ? (__nv_bfloat16*)h_last_lp + (size_t)b0 * H : nullptr;
     p.counter = counter;
     p.cs = cs;
@@ -347,7 +358,7 @@ int gru_persistent(const void* X, int B, int T, int H, int E_pad, const void* wx
         // clusters of this size cannot all be co-resident on this device: remember, retry the whole call smaller
         (void)cudaGetLastError();
         max_cs = cs / 2;
-        return gru_persistent(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, s);
+        return gru_persistent(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, s);
       }
     } else {
       VQA_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)gru_persistent_kernel, dim3(p.num_ctas), dim3(THREADS), args,

@@ -175,7 +175,7 @@ int embedding_gather(const int64_t* tokens, int n_rows, int E_pad, int ntoken_ro
 template <typename T>
 __global__ void __launch_bounds__(256)
 gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh, int B, int H, int Tlen,
-                int t, const float* h_prev, float* h_out, T* __restrict__ h_lp) {
+                int t, const float* h_prev, float* h_out, T* __restrict__ h_lp, int ld_lp) {
   const int total = B * H;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int b = i / H, j = i - b * H;
@@ -186,20 +186,21 @@ gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh, int 
     const float n = tanhf(gir[2 * H + j] + r * ghr[2 * H + j]);
     const float hn = (1.f - z) * n + z * h_prev[i];
     h_out[i] = hn;
-    h_lp[i] = Elem<T>::from_f(hn);
+    h_lp[(size_t)b * ld_lp + j] = Elem<T>::from_f(hn);
   }
 }
 
+// h_lp row stride ld_lp: H for the [B,H] operand copy, T*H when the states go straight into [B,T,H]
 int gru_gate(const float* gi, const float* gh, int B, int H, int T, int t, const float* h_prev,
-             float* h_out, void* h_lp, int dtype, cudaStream_t s) {
+             float* h_out, void* h_lp, int ld_lp, int dtype, cudaStream_t s) {
   const int total = B * H;
   int grid = (total + 255) / 256;
   if (grid > sm_count() * 8) grid = sm_count() * 8;
   if (dtype == VQA_BF16)
     gru_gate_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(gi, gh, B, H, T, t, h_prev, h_out,
-                                                        (__nv_bfloat16*)h_lp);
+                                                        (__nv_bfloat16*)h_lp, ld_lp);
   else
-    gru_gate_kernel<float><<<grid, 256, 0, s>>>(gi, gh, B, H, T, t, h_prev, h_out, (float*)h_lp);
+    gru_gate_kernel<float><<<grid, 256, 0, s>>>(gi, gh, B, H, T, t, h_prev, h_out, (float*)h_lp, ld_lp);
   VQA_LAUNCH_CHECK();
   return VQA_OK;
 }

@@ -1,5 +1,5 @@
-"""Building blocks — mirror of modules/modules.py (FCNet :13-60, DotProduct :80-95,
-SentenceEmbedding :98-163) on the C-ABI kernels.
+"""Building blocks — mirror of modules/modules.py (FCNet :13-60, LReLUNet :62-78, DotProduct :80-95,
+SentenceEmbedding :98-163, CaptionAttention :202-243, CaptionEmbedding :246-306) on the C-ABI kernels.
 
 torch.nn containers are used ONLY to own parameters under the reference's names
 (``main.{i}.weight_g / weight_v / bias``, so old checkpoints load); their own
@@ -115,6 +115,29 @@ class FCNet(nn.Module):
         return h.reshape(*lead, h.shape[-1])
 
 
+class LReLUNet(nn.Module):
+    """f(x) = LeakyReLU(W x), no bias (modules.py:62-78)."""
+
+    def __init__(self, in_dim: int, out_dim: int, neg_slope: float = 0.01):
+        super().__init__()
+        self.main = nn.Sequential(nn.Linear(in_dim, out_dim, bias=False), nn.LeakyReLU(neg_slope))
+        self.neg_slope = neg_slope
+        self._cache = PreparedCache()
+
+    def prepared(self, dtype):
+        w = self.main[0].weight
+        return self._cache.get(("w", dtype), (w,), lambda: w.detach().to(dtype).contiguous())
+
+    def forward(self, x, out_dtype=None, **epilogue):
+        """``epilogue``: extra vqa_linear epilogue operands (mul=, add=, add_after_act=, sigmoid=)"""
+        _no_training(self)
+        dtype = compute_dtype()
+        lead = x.shape[:-1]
+        h = ops.linear(as_compute(x.reshape(-1, x.shape[-1]), dtype), self.prepared(dtype), relu=True,
+                       leaky_slope=self.neg_slope, out_dtype=out_dtype or dtype, **epilogue)
+        return h.reshape(*lead, h.shape[-1])
+
+
 def _no_training(module):
     if module.training and torch.is_grad_enabled():
         raise NotImplementedError(
@@ -184,6 +207,19 @@ class SentenceEmbedding(nn.Module):
         emb = self._cache.get(("emb", dtype), (embedding_weight,), lambda: _pad_emb(embedding_weight, E_pad, dtype))
         return ops.gru_last_state(tokens.contiguous(), emb, w_ih, b_ih, w_hh, b_hh, packed=packed)
 
+    def forward_all(self, batch):
+        """batch: [B,T,in_dim] → every hidden state [B,T,H] in the compute dtype (modules.py:147-152)"""
+        _no_training(self)
+        dtype = compute_dtype()
+        w_ih, b_ih, w_hh, b_hh, E_pad, packed = self.prepared(dtype)
+        B, T, E = batch.shape
+        if E == E_pad and batch.dtype == dtype and batch.is_contiguous():
+            x = batch
+        else:
+            x = torch.zeros((B, T, E_pad), dtype=dtype, device=batch.device)
+            x[:, :, :E] = batch.to(dtype)
+        return ops.gru_sequence(x, w_ih, b_ih, w_hh, b_hh, packed=packed)
+
     def forward(self, batch):
         """batch: already-embedded [B,T,in_dim] (modules.py:155-159) → last step [B,H] f32"""
         _no_training(self)
@@ -194,6 +230,56 @@ class SentenceEmbedding(nn.Module):
         table[:, :E] = batch.reshape(B * T, E).to(dtype)
         tokens = torch.arange(B * T, device=batch.device, dtype=torch.int64).view(B, T)
         return ops.gru_last_state(tokens, table, w_ih, b_ih, w_hh, b_hh, packed=packed)
+
+
+class CaptionAttention(nn.Module):
+    """a = sigmoid(h * f(v) + h * f(q)) (modules.py:202-243); parameters + the two f(.) projections — the gate
+    itself is fused with the sequence scaling in vqa_caption_gate_scale (see CaptionEmbedding)."""
+
+    def __init__(self, v_dim: int, q_dim: int, hidden_dim: int, neg_slope: float = 0.01, dropout: float = 0.2):
+        super().__init__()
+        self.W_v = LReLUNet(v_dim, hidden_dim, neg_slope)
+        self.W_q = LReLUNet(q_dim, hidden_dim, neg_slope)
+        self.dropout = nn.Dropout(dropout)
+        self.sigmoid = nn.Sigmoid()
+
+    def projections(self, v, q):
+        return self.W_v(v, out_dtype=torch.float32), self.W_q(q, out_dtype=torch.float32)
+
+    def forward(self, h, v, q):
+        """h [B,H] (or [1,B,H]) → sigmoid(h*W_v(v) + h*W_q(q)), f32"""
+        p, r = self.projections(v, q)
+        lead = h.shape
+        hw = as_compute(h.reshape(-1, 1, h.shape[-1]), compute_dtype())          # a T=1 sequence
+        _, a = ops.caption_gate_scale(hw, p.contiguous(), r.contiguous(), want_a=True)
+        return a.reshape(lead)
+
+
+class CaptionEmbedding(nn.Module):
+    """Question-relevant caption embedding (modules.py:246-306).  ``forward_all`` follows the minimal repair of
+    the reference's broken method (tests/golden/make_golden.py::repaired_forward_all): the word GRU's
+    final state gates its own outputs, the gated sequence feeds the caption GRU, LeakyReLU FC on every step."""
+
+    def __init__(self, v_dim: int, q_dim: int, c_dim: int, hidden_dim: int, max_len: int, device: str,
+                 dropout: float = 0.2, neg_slope: float = 0.01, rnn_type: str = 'GRU'):
+        super().__init__()
+        self.c_dim, self.hidden_dim, self.max_len, self.rnn_type, self.device = c_dim, hidden_dim, max_len, rnn_type, device
+        assert rnn_type == 'LSTM' or rnn_type == 'GRU'
+        self.word_rnn = SentenceEmbedding(in_dim=c_dim, hidden_dim=hidden_dim, device=device, rnn_type=rnn_type)
+        self.caption_rnn = SentenceEmbedding(in_dim=hidden_dim, hidden_dim=hidden_dim, device=device, rnn_type=rnn_type)
+        self.attention = CaptionAttention(v_dim=v_dim, q_dim=q_dim, hidden_dim=hidden_dim, dropout=dropout)
+        self.fcnet = LReLUNet(hidden_dim, hidden_dim, neg_slope)
+
+    def forward_all(self, v, q, c):
+        out_w = self.word_rnn.forward_all(c)                                   # [B,T,H]
+        p, r = self.attention.projections(v, q)                                # f32 [B,H] each
+        gated = ops.caption_gate_scale(out_w, p.contiguous(), r.contiguous())  # σ(h_w p + h_w r) ⊙ out_w
+        out_c = self.caption_rnn.forward_all(gated)
+        return self.fcnet(out_c)                                               # [B,T,H]
+
+    def forward(self, v, q, c):
+        """v [B,v_dim], q [B,q_dim], c [B,c_len,c_dim] → [B,hidden_dim] (compute dtype)"""
+        return ops.seq_max(self.forward_all(v, q, c).contiguous())
 
 
 def _pad_emb(weight, E_pad, dtype):

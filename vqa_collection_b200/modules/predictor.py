@@ -1,9 +1,10 @@
-"""Predictors — mirror of modules/predictor.py (BasePredictor :54-93) on the C-ABI kernels."""
+"""Predictors — mirror of modules/predictor.py (BasePredictor :54-93, PredictorwithCaption :144-213) on the
+C-ABI kernels."""
 import torch
 import torch.nn as nn
 
 from .. import compute_dtype, ops
-from .modules import FCNet, as_compute, _no_training
+from .modules import FCNet, LReLUNet, CaptionEmbedding, as_compute, _no_training
 
 
 def set_predictor(predictor_type: str, v_dim: int, embed_dim: int, hidden_dim: int, ans_dim: int, device: str,
@@ -11,9 +12,12 @@ def set_predictor(predictor_type: str, v_dim: int, embed_dim: int, hidden_dim: i
     if predictor_type == 'base':
         return BasePredictor(v_dim=v_dim, hidden_dim=hidden_dim, ans_dim=ans_dim, device=device,
                              cls_layer=cls_layer, dropout=dropout).to(device)
-    if predictor_type in ('base-cap', 'q-cap'):
-        raise NotImplementedError(f"predictor_type='{predictor_type}' is outside the accelerated VQA forward path "
-                                  "(q-cap is broken in the reference, SURVEY.md F8)")
+    if predictor_type == 'q-cap':
+        return PredictorwithCaption(embed_dim=embed_dim, c_len=c_len, v_dim=v_dim, hidden_dim=hidden_dim,
+                                    ans_dim=ans_dim, device=device, cls_layer=cls_layer, dropout=dropout,
+                                    neg_slope=neg_slope).to(device)
+    if predictor_type == 'base-cap':
+        raise NotImplementedError("predictor_type='base-cap' is outside the accelerated VQA forward path")
     return None            # like the reference: unknown types (e.g. 'none') give no predictor
 
 
@@ -43,3 +47,48 @@ class BasePredictor(nn.Module):
             v = vs.float() * K
         joint = self.v_net(v, mul=q.float().contiguous())        # ReLU(W v) ⊙ q   (predictor.py:88-91)
         return self.classifier(joint, out_dtype=torch.float32)
+
+
+class PredictorwithCaption(nn.Module):
+    """'Generating Question Relevant Captions to Aid VQA' predictor (predictor.py:144-213, BASELINE config 5).
+
+    Every stage is a bias-free Linear + LeakyReLU (LReLUNet) on the tcgen05 GEMM with the element-wise neighbours
+    folded into its epilogue: ``c ⊙ vq`` is the ``mul`` operand of vq_net, ``q ⊙ (v + c)`` the ``add``-after-
+    activation + ``mul`` operands of vqc_net, the final Sigmoid the classifier's epilogue.  Line 203's
+    ``(joint.repeat ⊙ V).sum(1)`` equals ``joint ⊙ Σ_K V`` and is computed on the pooled vector."""
+
+    def __init__(self, embed_dim: int, c_len: int, v_dim: int, hidden_dim: int, ans_dim: int, device: str,
+                 cls_layer: int = 2, dropout: float = 0.5, neg_slope: float = 0.01):
+        super().__init__()
+        self.device = device
+        self.v_net = LReLUNet(v_dim, hidden_dim, neg_slope)
+        self.caption_embedding = CaptionEmbedding(v_dim=hidden_dim, q_dim=hidden_dim, c_dim=embed_dim,
+                                                  hidden_dim=hidden_dim, max_len=c_len, device=device, dropout=dropout)
+        self.c_net = LReLUNet(hidden_dim, hidden_dim, neg_slope)
+        self.vq_net = LReLUNet(hidden_dim, hidden_dim, neg_slope)
+        self.joint_net = LReLUNet(hidden_dim, hidden_dim, neg_slope)
+        self.vqc_net = LReLUNet(hidden_dim, hidden_dim, neg_slope)
+        self.classifier = nn.Sequential(LReLUNet(hidden_dim, ans_dim, neg_slope), nn.Sigmoid())
+
+    def forward(self, batch):
+        _no_training(self)
+        for i in batch:
+            if torch.is_tensor(batch[i]):
+                batch[i] = batch[i].to(self.device)
+        dtype = compute_dtype()
+        q = batch['q'].float().contiguous()
+        batch['v'] = self.v_net(batch['v'])                                   # [B,K,H]  (predictor.py:188)
+        V = batch['v']
+        B, K, H = V.shape
+        zeros = torch.zeros((B * K, 1), dtype=torch.float32, device=V.device)       # softmax(0) = 1/K
+        _, vmean, _ = ops.attention_pool(zeros, 0.0, V.contiguous(), False, True, False)
+        v = as_compute((vmean.float() * K).contiguous(), dtype)               # Σ_K V  (:191)
+        c = self.caption_embedding(v, q, batch['c'])                          # [B,H]  (:192)
+        c = self.c_net(c, out_dtype=torch.float32)                            # (:197)
+        self.c_grad = c
+        cv = self.vq_net(v, mul=c)                                            # LReLU(W_vq v) ⊙ c  (:196,201)
+        z = self.joint_net(cv, out_dtype=torch.float32)                       # (:201)
+        v2 = ops.softmax_mul(z.contiguous(), v)                               # softmax_H ⊙ Σ_K V  (:202-203)
+        joint = self.vqc_net(v2, add=c, add_after_act=True, mul=q)            # q ⊙ (LReLU(W v) + c)  (:208-209)
+        self.logit_grad = joint
+        return self.classifier[0](joint, out_dtype=torch.float32, sigmoid=True)      # (:213)

@@ -104,13 +104,16 @@ def linear_part_width(dtype: torch.dtype) -> int:
 
 
 def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, logit_w=None,
-           out_dtype=None, N=None, add=None, add_row_div=1, trans_a=False, trans_w=False, mask=None, out=None):
+           out_dtype=None, N=None, add=None, add_row_div=1, trans_a=False, trans_w=False, mask=None, out=None,
+           leaky_slope=0.0, add_after_act=False, sigmoid=False):
     """Fused weight-normed linear layer (modules.py:13-60), see vqa_linear in the header.
 
     A [M,K], W [N_rows,K] (same dtype); returns [M,N] (out_dtype) or, with ``logit_w``,
     the f32 row-reduction parts [M, n_parts].  ``N`` < W.shape[0] uses only the first N
     rows of W (row-padded weights).  Backward forms: ``trans_w`` → W is [K,N] (y = A·W),
     ``trans_a`` (with trans_w) → A is [K,M] (y = Aᵀ·W); ``mask`` [M,N] zeroes y where mask ≤ 0.
+    ``leaky_slope`` turns the ReLU into LeakyReLU (LReLUNet, modules.py:62-78); ``add_after_act`` applies ``add``
+    after the activation; ``sigmoid`` applies the logistic function last.
     """
     lib = L.load()
     _require(A, None, "A")
@@ -135,6 +138,7 @@ def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, log
     a.M, a.N, a.K, a.dtype = M, N, K, code
     a.trans_a, a.trans_w = int(bool(trans_a)), int(bool(trans_w))
     a.d_scale, a.d_bias, a.relu = _ptr(scale), _ptr(bias), int(bool(relu))
+    a.leaky_slope, a.add_after_act, a.sigmoid = float(leaky_slope), int(bool(add_after_act)), int(bool(sigmoid))
     if mul is not None:
         _require(mul, torch.float32, "mul")
         a.d_mul, a.ld_mul, a.mul_row_div = mul.data_ptr(), mul.stride(0), int(mul_row_div)
@@ -197,6 +201,74 @@ def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False, packed=No
     a.d_h_last, a.d_h_last_lp = h.data_ptr(), (h_lp.data_ptr() if want_lp else None)
     L.check(lib.vqa_gru_last_state(C.byref(a), _stream()))
     return (h, h_lp) if want_lp else h
+
+
+def gru_sequence(x, w_ih, b_ih, w_hh, b_hh, packed=None, want_last=False):
+    """1-layer GRU over dense inputs, every hidden state (SentenceEmbedding.forward_all, modules.py:147-152).
+
+    x [B,T,E_pad] (E_pad = w_ih.shape[1], zero padded); returns out [B,T,H] in x.dtype
+    (and the f32 last state [B,H] when ``want_last``)."""
+    lib = L.load()
+    _require(x, None, "x")
+    _require(w_ih, x.dtype, "w_ih")
+    _require(w_hh, x.dtype, "w_hh")
+    _require(b_ih, torch.float32, "b_ih")
+    _require(b_hh, torch.float32, "b_hh")
+    B, T, E_pad = x.shape
+    H = w_hh.shape[1]
+    if w_ih.shape != (3 * H, E_pad) or w_hh.shape != (3 * H, H):
+        raise ValueError("gru_sequence: weight shapes do not match")
+    code = dtype_code(x.dtype)
+    ws_bytes = lib.vqa_gru_workspace_bytes(B, T, H, E_pad, code)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=x.device)
+    out = torch.empty((B, T, H), dtype=x.dtype, device=x.device)
+    h = torch.empty((B, H), dtype=torch.float32, device=x.device) if want_last else None
+    a = L.GruArgs()
+    a.B, a.T, a.H, a.E_pad, a.dtype = B, T, H, E_pad, code
+    a.d_x, a.d_out_all = x.data_ptr(), out.data_ptr()
+    a.d_w_ih, a.d_b_ih, a.d_w_hh, a.d_b_hh = w_ih.data_ptr(), b_ih.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr()
+    if packed is not None:
+        a.d_wx_packed, a.d_wh_packed, a.d_bias_packed = (packed[0].data_ptr(), packed[1].data_ptr(),
+                                                         packed[2].data_ptr())
+    a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+    a.d_h_last = _ptr(h)
+    L.check(lib.vqa_gru_last_state(C.byref(a), _stream()))
+    return (out, h) if want_last else out
+
+
+def caption_gate_scale(out_w, p, r, want_a=False):
+    """a = σ(h_w⊙p + h_w⊙r), h_w = out_w[:, -1]; returns a[:, None, :] ⊙ out_w (modules.py:225-243,294-295)."""
+    lib = L.load()
+    _require(out_w, None, "out_w")
+    _require(p, torch.float32, "p")
+    _require(r, torch.float32, "r")
+    B, T, H = out_w.shape
+    in2 = torch.empty_like(out_w)
+    a = torch.empty((B, H), dtype=torch.float32, device=out_w.device) if want_a else None
+    L.check(lib.vqa_caption_gate_scale(out_w.data_ptr(), p.data_ptr(), r.data_ptr(), B, T, H, dtype_code(out_w.dtype),
+                                       in2.data_ptr(), _ptr(a), _stream()))
+    return (in2, a) if want_a else in2
+
+
+def seq_max(e):
+    """max over the time axis of [B,T,H] (modules.py:306)."""
+    lib = L.load()
+    _require(e, None, "e")
+    B, T, H = e.shape
+    out = torch.empty((B, H), dtype=e.dtype, device=e.device)
+    L.check(lib.vqa_seq_max(e.data_ptr(), B, T, H, dtype_code(e.dtype), out.data_ptr(), _stream()))
+    return out
+
+
+def softmax_mul(z, v):
+    """softmax over the last axis of z (f32 [B,H]) times v [B,H] (predictor.py:202-203)."""
+    lib = L.load()
+    _require(z, torch.float32, "z")
+    _require(v, None, "v")
+    B, H = z.shape
+    out = torch.empty_like(v)
+    L.check(lib.vqa_softmax_mul(z.data_ptr(), v.data_ptr(), B, H, dtype_code(v.dtype), out.data_ptr(), _stream()))
+    return out
 
 
 def attention_pool(parts, logit_bias, x, want_att=True, want_vsum=True, want_vatt=False):
