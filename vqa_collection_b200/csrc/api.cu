@@ -67,6 +67,12 @@ int updown_train_step(const vqa_train_args&, cudaStream_t);
 int gru_persistent(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
                    void*, cudaStream_t);
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VQA_B200_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 static bool force_simt() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("VQA_B200_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }

@@ -46,6 +46,29 @@ int sm_count();
 inline size_t elem_size(int dtype) { return dtype == VQA_BF16 ? 2 : 4; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------
+// The forward path is a chain of short kernels on one stream.  Each kernel calls griddep_launch()
+// once its CTA is set up (the NEXT kernel's CTAs may then be scheduled as SMs free up and run their
+// own prologue: barrier init, TMEM allocation, tensor-map prefetch) and griddep_wait() before it
+// touches global memory (returns when the PREVIOUS kernel has completed and its writes are
+// visible).  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();            // VQA_B200_NO_PDL=1 turns the launch attribute off (A/B timing)
+
+// launch `kernel` so that it may start while the previous kernel of the stream is still draining
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- device-side element helpers -------------------------------------------
 template <typename T> struct Elem;
 template <> struct Elem<float> {

@@ -34,7 +34,7 @@ template <int BN> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8));
   static constexpr int TMEM_COLS = pow2_ge(2 * BN);
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
   static constexpr int PARAM_FLOATS = 2 * 3 * BN;            // 2 acc stages x (scale,bias,logit_w)
@@ -92,6 +92,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_launch();              // PDL: the next kernel may set itself up behind us ...
+  griddep_wait();                // ... and we touch global memory only after our predecessor is complete
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -372,20 +374,34 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, THREADS, C::SMEM_BYTES, s>>>(tmA, tmW, p);
+  VQA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)C::SMEM_BYTES, s, tmA, tmW, p));
   VQA_LAUNCH_CHECK();
   return VQA_OK;
 }
 
 template <bool A_MN, bool B_MN>
 static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
-  // pick the widest N tile that still gives every SM a tile (small-M layers), else 256
+  // Large GEMMs (a tile for every SM at BN = 256) are tensor-bound: widest tile.  Small-M layers are bound by
+  // what one SM can pull in per tile — (BM + BN)·K operand bytes — times the number of waves, so pick the BN
+  // that minimises waves x (BM + BN); ties go to the wider tile (fewer operand bytes in total).
+  // Measured on the 3129-way classifier (M = 1024, K = 2048): BN = 128 -> 200 tiles = 2 waves, 30 us;
+  // BN = 192 -> 136 tiles = 1 wave.
   const int tiles_m = (a.M + BM - 1) / BM;
   const int sms = sm_count();
   if (a.d_logit_w || tiles_m * ((a.N + 255) / 256) >= sms) return launch<256, A_MN, B_MN>(a, s);
   if constexpr (!A_MN && !B_MN) {
-    if (tiles_m * ((a.N + 127) / 128) >= sms || a.N > 1024) return launch<128, A_MN, B_MN>(a, s);
-    return launch<64, A_MN, B_MN>(a, s);
+    int best_bn = 256, best_cost = 1 << 30;
+    for (int bn : {256, 192, 128, 64}) {
+      const int tiles = tiles_m * ((a.N + bn - 1) / bn);
+      const int cost = ((tiles + sms - 1) / sms) * (BM + bn);
+      if (cost < best_cost) { best_cost = cost; best_bn = bn; }
+    }
+    switch (best_bn) {
+      case 256: return launch<256, A_MN, B_MN>(a, s);
+      case 192: return launch<192, A_MN, B_MN>(a, s);
+      case 128: return launch<128, A_MN, B_MN>(a, s);
+      default: return launch<64, A_MN, B_MN>(a, s);
+    }
   } else {
     return launch<128, A_MN, B_MN>(a, s);
   }

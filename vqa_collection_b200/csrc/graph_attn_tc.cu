@@ -118,6 +118,8 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_launch();              // PDL (common.cuh): next kernel sets up behind us; global memory only after the wait
+  griddep_wait();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -423,7 +425,8 @@ int graph_attention_tc(const vqa_graph_attention_args& a, cudaStream_t s) {
     attr_set = true;
   }
   const int grid = a.B < sm_count() ? a.B : sm_count();
-  graph_attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tmQ, tmX, tmW, tmPS, tmLB, p);
+  VQA_CUDA_CHECK(launch_pdl(graph_attention_tc_kernel, dim3(grid), dim3(THREADS), (size_t)SMEM_BYTES, s, tmQ, tmX, tmW, tmPS,
+                            tmLB, p));
   VQA_LAUNCH_CHECK();
   return VQA_OK;
 }

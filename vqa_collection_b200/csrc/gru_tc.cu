@@ -119,6 +119,7 @@ gru_persistent_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (cs > 1) cluster_sync_all();                      // peers multicast into / arrive on these barriers
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_launch();              // PDL primary only (cooperative launches are not made dependents)
   // A-operand tile: this CTA's row slice, delivered to every CTA of the cluster
   auto load_a = [&](uint32_t sa, const CUtensorMap* map, uint32_t bar, int col) {
     if (cs > 1) tma_load_2d_multicast(sa + crank * (slice_rows * 128), map, bar, col, m0 + (int)crank * slice_rows, cmask);

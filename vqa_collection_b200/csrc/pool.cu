@@ -22,6 +22,8 @@ attention_pool_kernel(const float* __restrict__ parts, int n_parts, float bias,
                       const T* __restrict__ x, int B, int K, int V, int slices,
                       float* __restrict__ att_out, T* __restrict__ vsum, T* __restrict__ vatt) {
   __shared__ float s_att[kPoolMaxK];
+  griddep_launch();
+  griddep_wait();
   const int b = blockIdx.x / slices;
   const int slice = blockIdx.x - b * slices;
   const int tid = threadIdx.x;
@@ -87,12 +89,12 @@ int attention_pool(const float* parts, int n_parts, float bias, const void* x, i
   const int slices = stream_x ? (V + kPoolChan - 1) / kPoolChan : 1;
   const unsigned grid = (unsigned)B * slices;
   if (dtype == VQA_BF16) {
-    attention_pool_kernel<__nv_bfloat16><<<grid, kPoolThreads, 0, s>>>(
-        parts, n_parts, bias, (const __nv_bfloat16*)x, B, K, V, slices, att, (__nv_bfloat16*)vsum,
-        (__nv_bfloat16*)vatt);
+    VQA_CUDA_CHECK(launch_pdl(attention_pool_kernel<__nv_bfloat16>, dim3(grid), dim3(kPoolThreads), 0, s,
+                              parts, n_parts, bias, (const __nv_bfloat16*)x, B, K, V, slices, att, (__nv_bfloat16*)vsum,
+                              (__nv_bfloat16*)vatt));
   } else {
-    attention_pool_kernel<float><<<grid, kPoolThreads, 0, s>>>(parts, n_parts, bias, (const float*)x, B,
-                                                               K, V, slices, att, (float*)vsum, (float*)vatt);
+    VQA_CUDA_CHECK(launch_pdl(attention_pool_kernel<float>, dim3(grid), dim3(kPoolThreads), 0, s, parts, n_parts, bias,
+                              (const float*)x, B, K, V, slices, att, (float*)vsum, (float*)vatt));
   }
   VQA_LAUNCH_CHECK();
   return VQA_OK;
@@ -106,6 +108,8 @@ __global__ void __launch_bounds__(256)
 argmax_rows_kernel(const float* __restrict__ logits, int B, int A, int ld, int64_t* __restrict__ out) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  griddep_launch();
+  griddep_wait();
   if (row >= B) return;
   const float* p = logits + (size_t)row * ld;
   float best = -INFINITY;
@@ -127,8 +131,8 @@ int argmax_rows(const float* logits, int B, int A, int ld, int64_t* out, cudaStr
   if (B == 0) return VQA_OK;
   VQA_REQUIRE(logits && out && A >= 1 && ld >= A, "argmax_rows: bad arguments");
   const int rows_per_cta = 8;
-  argmax_rows_kernel<<<(B + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, s>>>(logits, B, A,
-                                                                                        ld, out);
+  VQA_CUDA_CHECK(launch_pdl(argmax_rows_kernel, dim3((B + rows_per_cta - 1) / rows_per_cta), dim3(rows_per_cta * 32), 0, s,
+                            logits, B, A, ld, out));
   VQA_LAUNCH_CHECK();
   return VQA_OK;
 }

@@ -21,7 +21,7 @@ def compute_score(predict, target, device, get_label=False):
         logits = ops.argmax_rows(predict.float().contiguous())          # torch.max(predict, 1)[1] tie rule
     else:
         logits = torch.max(predict, 1)[1].data
-    one_hots = torch.zeros(*target.size()).to(device)
+    one_hots = torch.zeros(*target.size(), device=target.device)      # (the reference fills it on the host and copies)
     one_hots.scatter_(1, logits.view(-1, 1), 1)
     scores = one_hots * target
     if get_label:
