@@ -283,8 +283,8 @@ def main():
         roof = {"kernel": "linear_tc_kernel<256> (W_v projection + logit reduction)", "bound": "tensor",
                 "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch, `ncu --set full`
-                # (profiles/r01a_ncu_wv_gemm.md; algorithmic bytes = 159.0 MB at B=1024)
-                "traffic": (163.2e6 * B / 1024), "traffic_source": "profiles/r01a_ncu_wv_gemm.md", "peak_source": pk["src"] + " burst (kernel timed alone)", "launch_ms": k_ms,
+                # (profiles/r01d_ncu_wv.md: 159.47 MB read + 5.43 MB written; algorithmic bytes = 159.0 MB at B=1024)
+                "traffic": (164.9e6 * B / 1024), "traffic_source": "profiles/r01d_ncu_wv.md", "peak_source": pk["src"] + " burst (kernel timed alone)", "launch_ms": k_ms,
                 "flops_per_launch": flops}
     path_tflops = value / world * FLOPS_PER_Q[args.workload] / 1e12
 

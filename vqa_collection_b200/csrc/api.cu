@@ -66,6 +66,8 @@ size_t train_workspace_bytes(const vqa_train_args&);
 int updown_train_step(const vqa_train_args&, cudaStream_t);
 int gru_persistent(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
                    void*, cudaStream_t);
+int gru_pair(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
+             void*, cudaStream_t);
 
 bool pdl_enabled() {
   static int v = -1;
@@ -128,9 +130,18 @@ static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
     X = w.X;
   }
   if (a.dtype == VQA_BF16 && a.d_wx_packed && a.d_wh_packed && a.d_bias_packed && !force_simt() && a.H % 64 == 0 &&
-      a.E_pad % 64 == 0)
+      a.E_pad % 64 == 0) {
+    // CTA pairs (tcgen05 cta_group::2) when VQA_B200_GRU_PAIR=1 and the device can hold the pairs; else one CTA per tile
+    static int pair = -1;
+    if (pair < 0) { const char* e = getenv("VQA_B200_GRU_PAIR"); pair = (e && e[0] == '1') ? 1 : 0; }
+    if (pair) {
+      rc = gru_pair(X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
+                    a.d_h_last, a.d_h_last_lp, a.d_out_all, s);
+      if (rc != VQA_ERR_UNSUPPORTED) return rc;
+    }
     return gru_persistent(X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
                           a.d_h_last, a.d_h_last_lp, a.d_out_all, s);
+  }
   // gi = X W_ihᵀ + b_ih for all T steps at once: [B*T, 3H] f32
   vqa_linear_args gi{};
   gi.d_A = X; gi.lda = a.E_pad; gi.d_W = a.d_w_ih; gi.ldw = a.E_pad;

@@ -1,0 +1,344 @@
+// Persistent fused GRU on CTA PAIRS (tcgen05 cta_group::2) — same algorithm, outputs and packed
+// weights as gru_tc.cu (read that header first); what changes is who holds which operand.
+//
+// gru_tc.cu is bound by shared-memory bandwidth per SM: every step each CTA fills 855 KB through
+// TMA and the MMAs read 0.96 MB of operands back out.  Here two CTAs on one TPC form a pair that
+// owns 256 batch rows × 64 hidden units:
+//   * each CTA still owns (loads, gates, publishes) its own 128 rows — the epilogue, the fp32 state
+//     in registers and the per-row-block publish/acquire protocol are unchanged;
+//   * the 192-row W tile of a k-block is SPLIT: CTA r loads rows [r|z|n] of units [32r, 32r+32)
+//     (three 32-row TMA boxes out of the same gate-interleaved packing) — half the W fill per SM;
+//   * ONE thread of the pair's leader CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 192): each
+//     SM's tensor core reads its own A tile and both B halves, so the B operand reads per SM halve too.
+// Accumulator columns (per CTA, N = 192 ordered as the two B halves):
+//   unit u = 32·hf + uu:  r at 96·hf + uu,  z at 96·hf + 32 + uu,  n_x + W_hn·h at 96·hf + 64 + uu;
+//   n_x alone (second x-part MMA, N = 64) at 192 + u.   Double buffered over steps (2 × 256 columns).
+// Barriers: TMA of both CTAs counts bytes on the LEADER's full barrier (cp.async.bulk.tensor
+// .cta_group::2); tcgen05.commit multicasts the stage release and "accumulator ready" to both CTAs;
+// the epilogue warps of both CTAs release the accumulator on the leader's barrier (mapa + remote arrive).
+#include <stdlib.h>
+
+#include "tc_common.cuh"
+
+namespace vqa {
+namespace grup {
+
+using namespace tc;
+
+constexpr int UNITS = 64;                         // hidden units per CTA pair
+constexpr int WROWS = 3 * UNITS;                  // 192 rows of the packed W block
+constexpr int HALF_UNITS = UNITS / 2;             // units whose W rows one CTA holds
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;   // 640
+constexpr int UPT = UNITS / (EPI_WARPS / 4);      // 16 units per epilogue thread
+constexpr int W_PREFETCH = 4;
+constexpr int A_BYTES = BM * BK * 2;              // 16 KB
+constexpr int W_BYTES = 3 * HALF_UNITS * BK * 2;  // 12 KB: this CTA's half of the W tile
+constexpr int STAGE_BYTES = A_BYTES + W_BYTES;    // 28 KB
+constexpr int STAGES = 7;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;
+constexpr int COL_NI = 192;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + 4 * UNITS * 4;
+
+struct Params {
+  int B, T, H, E_pad, tiles_n, num_ctas;
+  const float* bias;            // packed [4H]: b_ir+b_hr | b_iz+b_hz | b_in | b_hn
+  __nv_bfloat16* h_op[2];       // bf16 state, double buffered over steps
+  float* h_last;                // [B,H] f32 or NULL
+  __nv_bfloat16* h_last_lp;     // [B,H] bf16 or NULL
+  __nv_bfloat16* h_all;         // [B,T,H] bf16 or NULL (sequence form, see gru_tc.cu)
+  int* counter;                 // per-row-block arrival counters, zero on entry
+};
+
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH0,
+                const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmWx,
+                const __grid_constant__ CUtensorMap tmWh, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bars = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  float* bias_s = reinterpret_cast<float*>(base_ptr + STAGES * STAGE_BYTES + 256);   // [4][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();          // 0 = leader of the pair
+  const bool lead = crank == 0;
+  const int pid = blockIdx.x >> 1;
+  const int m_blk = 2 * (pid / p.tiles_n) + (int)crank, n_blk = pid % p.tiles_n;
+  const int m0 = m_blk * BM, u0 = n_blk * UNITS;
+  const int kb_x = p.E_pad / BK, kb_h = p.H / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmH0); tma_prefetch_desc(&tmH1);
+    tma_prefetch_desc(&tmWx); tma_prefetch_desc(&tmWh);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+  if (warp == 3) {
+    for (int i = lane; i < 4 * UNITS; i += 32) bias_s[i] = p.bias[(i / UNITS) * p.H + u0 + (i % UNITS)];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // the peer signals / fills through these barriers
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  griddep_launch();
+
+  // this CTA's half of the 192-row W tile: rows [r | z | n] of units [32·crank, 32·crank + 32)
+  auto load_w = [&](uint32_t sw, const CUtensorMap* map, uint32_t bar, int col) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+      tma_load_2d_2cta(sw + g * (HALF_UNITS * 128), map, bar, col, n_blk * WROWS + g * UNITS + (int)crank * HALF_UNITS);
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; bytes are counted on the leader's full barrier) =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < p.T; ++t) {
+        for (int kb = 0; kb < kb_x; ++kb) {                       // x-part: no dependence on h
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
+          if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+          tma_load_2d_2cta(sa, &tmX, full_bar(stage), t * p.E_pad + kb * BK, m0);
+          load_w(sw, &tmWx, full_bar(stage), kb * BK);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (t > 0) {
+          const int npre = kb_h < W_PREFETCH ? kb_h : W_PREFETCH;
+          int pre_stage[W_PREFETCH];
+          for (int kb = 0; kb < npre; ++kb) {                     // W_h tiles do not depend on h: start them early
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            load_w(base + stage * STAGE_BYTES + A_BYTES, &tmWh, full_bar(stage), kb * BK);
+            pre_stage[kb] = stage;
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          // h_{t-1}[rows of this CTA, :] is published by the tiles_n CTAs that own these rows
+          const int target = t * p.tiles_n;
+          while (ld_acquire_gpu(p.counter + m_blk) < target) { }
+          fence_proxy_async_all();
+          const CUtensorMap* tmH = ((t - 1) & 1) ? &tmH1 : &tmH0;
+          const int hcol = p.h_all ? (t - 1) * p.H : 0;
+          for (int kb = 0; kb < npre; ++kb)
+            tma_load_2d_2cta(base + pre_stage[kb] * STAGE_BYTES, tmH, full_bar(pre_stage[kb]), hcol + kb * BK, m0);
+          for (int kb = npre; kb < kb_h; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
+            if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            tma_load_2d_2cta(sa, tmH, full_bar(stage), hcol + kb * BK, m0);
+            load_w(sw, &tmWh, full_bar(stage), kb * BK);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the LEADER CTA drives both tensor cores =====
+    if (lane == 0 && lead) {
+      constexpr uint32_t idesc_rzn = make_idesc_bf16(2 * BM, 3 * UNITS);   // M = 256, N = 192
+      constexpr uint32_t idesc_n = make_idesc_bf16(2 * BM, UNITS);         // M = 256, N = 64: n rows of both halves
+      constexpr uint32_t N_ROW_OFF = (2 * HALF_UNITS * BK * 2) >> 4;       // rows 64.. of a half tile (8 KB)
+      int stage = 0; uint32_t phase = 0;
+      for (int t = 0; t < p.T; ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_phase = (uint32_t)(t >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + acc * ACC_STRIDE;
+        for (int kb = 0; kb < kb_x; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
+          const uint64_t adesc = make_sw128_kmajor_desc(sa), wdesc = make_sw128_kmajor_desc(sw);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_bf16_2cta(d, adesc + 2 * k, wdesc + 2 * k, idesc_rzn, (kb | k) != 0);                      // [r|z|n_x] x 2 halves
+            umma_bf16_2cta(d + COL_NI, adesc + 2 * k, wdesc + N_ROW_OFF + 2 * k, idesc_n, (kb | k) != 0);   // n_x kept apart
+          }
+          umma_commit_2cta(empty_bar(stage), 0b11);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (t > 0) {
+          for (int kb = 0; kb < kb_h; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
+            const uint64_t adesc = make_sw128_kmajor_desc(sa), wdesc = make_sw128_kmajor_desc(sw);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_2cta(d, adesc + 2 * k, wdesc + 2 * k, idesc_rzn, 1u);
+            umma_commit_2cta(empty_bar(stage), 0b11);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit_2cta(tfull_bar(acc), 0b11);
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===== gate epilogue (both CTAs, own 128 rows): thread = (batch row, 16 units), fp32 state in registers =====
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int uh = (warp - EPI_WARP0) >> 2;          // which 16-unit slice of the 64 units
+    const int et = threadIdx.x - EPI_WARP0 * 32;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.B;
+    const int ub = uh * UPT;                         // first unit (within the tile) of this thread
+    const int colb = (ub / HALF_UNITS) * (3 * HALF_UNITS) + (ub % HALF_UNITS);   // column of r for unit ub
+    float h[UPT];
+#pragma unroll
+    for (int j = 0; j < UPT; ++j) h[j] = 0.f;
+    for (int t = 0; t < p.T; ++t) {
+      const int acc = t & 1;
+      const uint32_t acc_phase = (uint32_t)(t >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t trow = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+      const bool last = (t == p.T - 1);
+      __nv_bfloat16* hdst = p.h_all ? p.h_all + (size_t)t * p.H : ((last && p.h_last_lp) ? p.h_last_lp : p.h_op[t & 1]);
+      const size_t h_ld = p.h_all ? (size_t)p.T * p.H : (size_t)p.H;
+#pragma unroll
+      for (int c = 0; c < UPT; c += 8) {
+        uint32_t vr[8], vz[8], vni[8], vnh[8];
+        tmem_ld_32x8(trow + colb + c, vr);
+        tmem_ld_32x8(trow + colb + HALF_UNITS + c, vz);
+        tmem_ld_32x8(trow + colb + 2 * HALF_UNITS + c, vnh);
+        tmem_ld_32x8(trow + COL_NI + ub + c, vni);
+        tmem_ld_wait();
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pr = __uint_as_float(vr[j]) + bias_s[ub + c + j], pz = __uint_as_float(vz[j]) + bias_s[UNITS + ub + c + j];
+          const float r = sigmoid_fast(pr), z = sigmoid_fast(pz);
+          const float nh = (__uint_as_float(vnh[j]) - __uint_as_float(vni[j])) + bias_s[3 * UNITS + ub + c + j];
+          const float pn = __uint_as_float(vni[j]) + bias_s[2 * UNITS + ub + c + j] + r * nh;
+          const float n = tanh_fast(pn);
+          const float hn = (1.f - z) * n + z * h[c + j];
+          h[c + j] = hn;
+          o[j] = hn;
+        }
+        if (row_ok) {
+          uint4 w0;
+          w0.x = pack_bf16x2(o[0], o[1]); w0.y = pack_bf16x2(o[2], o[3]);
+          w0.z = pack_bf16x2(o[4], o[5]); w0.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(hdst + (size_t)row * h_ld + u0 + ub + c) = w0;
+        }
+      }
+      // accumulator buffer drained: one arrive per warp on the LEADER's barrier (2 CTAs x 16 warps)
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+      if (!last) {
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        if (et == 0) {
+          fence_proxy_async_all();
+          red_release_gpu_add(p.counter + m_blk, 1);
+        }
+      }
+    }
+    if (row_ok && p.h_last) {
+      float* dst = p.h_last + (size_t)row * p.H + u0 + ub;
+#pragma unroll
+      for (int j = 0; j < UPT; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // no CTA leaves while its peer may still use its memory / barriers
+  tcgen05_fence_after();
+  if (warp == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+}
+
+}  // namespace grup
+
+// Same contract as gru_persistent (gru_tc.cu).  Returns VQA_ERR_UNSUPPORTED (without setting the error text as a
+// failure of the call) when the pair launch is not possible; the caller then uses the single-CTA kernel.
+int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, const void* wh_p,
+             const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
+             cudaStream_t s) {
+  using namespace grup;
+  if (H % UNITS != 0 || E_pad % tc::BK != 0) return VQA_ERR_UNSUPPORTED;
+  const int tiles_n = H / UNITS;
+  const int sms = sm_count();
+  int max_tiles_m = (sms / tiles_n) & ~1;            // pairs: an even number of 128-row blocks per launch
+  if (max_tiles_m < 2) return VQA_ERR_UNSUPPORTED;
+  static int usable = -1;                            // can max_tiles_m * tiles_n CTAs run as co-resident pairs?
+  if (usable < 0) {
+    if (cudaFuncSetAttribute(gru_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+      (void)cudaGetLastError();
+      usable = 0;
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(max_tiles_m * tiles_n); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&clusters, (const void*)gru_pair_kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); clusters = 0; }
+      usable = clusters > 0 ? clusters : 0;          // number of pairs the device can hold at once
+    }
+  }
+  if (usable <= 0) return VQA_ERR_UNSUPPORTED;
+  while (max_tiles_m >= 2 && (max_tiles_m * tiles_n) / 2 > usable) max_tiles_m -= 2;
+  if (max_tiles_m < 2) return VQA_ERR_UNSUPPORTED;
+  CUtensorMap tmWx, tmWh;
+  int rc;
+  if ((rc = tc::make_tensor_map_bf16(&tmWx, wx_p, 3LL * H, E_pad, E_pad, HALF_UNITS))) return rc;
+  if ((rc = tc::make_tensor_map_bf16(&tmWh, wh_p, 3LL * H, H, H, HALF_UNITS))) return rc;
+  for (int b0 = 0; b0 < B; b0 += max_tiles_m * tc::BM) {
+    const int Bc = (B - b0 < max_tiles_m * tc::BM) ? B - b0 : max_tiles_m * tc::BM;
+    const int tiles_m = ((Bc + tc::BM - 1) / tc::BM + 1) & ~1;      // padded to whole pairs; extra rows are masked
+    const __nv_bfloat16* Xc = (const __nv_bfloat16*)X + (size_t)b0 * T * E_pad;
+    __nv_bfloat16* h0 = (__nv_bfloat16*)h_op + (size_t)b0 * H;
+    __nv_bfloat16* h1 = (__nv_bfloat16*)h_op + (size_t)B * H + (size_t)b0 * H;
+    CUtensorMap tmX, tmH0, tmH1;
+    if ((rc = tc::make_tensor_map_bf16(&tmX, Xc, Bc, (long long)T * E_pad, (long long)T * E_pad, tc::BM))) return rc;
+    __nv_bfloat16* hall = h_all ? (__nv_bfloat16*)h_all + (size_t)b0 * T * H : nullptr;
+    if (hall) {
+      if ((rc = tc::make_tensor_map_bf16(&tmH0, hall, Bc, (long long)T * H, (long long)T * H, tc::BM))) return rc;
+      tmH1 = tmH0;
+    } else {
+      if ((rc = tc::make_tensor_map_bf16(&tmH0, h0, Bc, H, H, tc::BM))) return rc;
+      if ((rc = tc::make_tensor_map_bf16(&tmH1, h1, Bc, H, H, tc::BM))) return rc;
+    }
+    Params p;
+    p.B = Bc; p.T = T; p.H = H; p.E_pad = E_pad; p.tiles_n = tiles_n; p.num_ctas = tiles_m * tiles_n;
+    p.bias = bias_p; p.h_op[0] = h0; p.h_op[1] = h1;
+    p.h_last = h_last ? h_last + (size_t)b0 * H : nullptr;
+    p.h_all = hall;
+    p.h_last_lp = h_last_lp ? (__nv_bfloat16*)h_last_lp + (size_t)b0 * H : nullptr;
+    p.counter = counter;
+    VQA_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int) * tiles_m, s));
+    void* args[] = {(void*)&tmX, (void*)&tmH0, (void*)&tmH1, (void*)&tmWx, (void*)&tmWh, (void*)&p};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.num_ctas); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    VQA_CUDA_CHECK(cudaLaunchKernelExC(&cfg, (const void*)gru_pair_kernel, args));
+    count_launch();
+  }
+  return VQA_OK;
+}
+
+}  // namespace vqa
