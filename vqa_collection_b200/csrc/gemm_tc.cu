@@ -389,21 +389,20 @@ static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
   const int tiles_m = (a.M + BM - 1) / BM;
   const int sms = sm_count();
   if (a.d_logit_w || tiles_m * ((a.N + 255) / 256) >= sms) return launch<256, A_MN, B_MN>(a, s);
-  if constexpr (!A_MN && !B_MN) {
-    int best_bn = 256, best_cost = 1 << 30;
-    for (int bn : {256, 192, 128, 64}) {
-      const int tiles = tiles_m * ((a.N + bn - 1) / bn);
-      const int cost = ((tiles + sms - 1) / sms) * (BM + bn);
-      if (cost < best_cost) { best_cost = cost; best_bn = bn; }
-    }
-    switch (best_bn) {
-      case 256: return launch<256, A_MN, B_MN>(a, s);
-      case 192: return launch<192, A_MN, B_MN>(a, s);
-      case 128: return launch<128, A_MN, B_MN>(a, s);
-      default: return launch<64, A_MN, B_MN>(a, s);
-    }
-  } else {
-    return launch<128, A_MN, B_MN>(a, s);
+  int best_bn = 256, best_cost = 1 << 30;
+  for (int bn : {256, 192, 128, 64}) {
+    if (bn == 192 && (A_MN || B_MN)) continue;       // MN-major operand tiles come in 64-wide atoms: 256 / 128 / 64 only
+    const int tiles = tiles_m * ((a.N + bn - 1) / bn);
+    const int cost = ((tiles + sms - 1) / sms) * (BM + bn);
+    if (cost < best_cost) { best_cost = cost; best_bn = bn; }
+  }
+  switch (best_bn) {
+    case 256: return launch<256, A_MN, B_MN>(a, s);
+    case 192:
+      if constexpr (!A_MN && !B_MN) return launch<192, A_MN, B_MN>(a, s);
+      else return launch<128, A_MN, B_MN>(a, s);
+    case 128: return launch<128, A_MN, B_MN>(a, s);
+    default: return launch<64, A_MN, B_MN>(a, s);
   }
 }
 

@@ -27,7 +27,7 @@ namespace train {
 
 enum { L_WV = 0, L_WQ, L_LIN, L_QNET, L_VNET, L_C0, L_C1, NL };
 constexpr int SVEC = 4096;                 // length of the per-layer uniform scale vectors
-constexpr int PARTS = 64;                  // partial sums per layer in the norm / dot reductions
+constexpr int PARTS = 256;                 // partial sums per layer in the norm / dot reductions (fixed order: deterministic)
 
 struct WnTable {
   const float* v[NL]; const float* g[NL]; float* dW[NL]; float* dg[NL];
@@ -63,7 +63,26 @@ __global__ void __launch_bounds__(256) wn_dot_partials_kernel(WnTable t, int use
   const float* b = t.v[l];
   const unsigned long long n = t.n[l];
   float s = 0.f;
-  for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n; i += 256ull * gridDim.x) s = fmaf(a[i], b[i], s);
+  if ((n & 3ull) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+    // streaming form: 16-byte loads, four independent chains per thread (the scalar loop ran at 0.6 TB/s)
+    const unsigned long long n4 = n >> 2, stride = 256ull * gridDim.x;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n4; i += 4 * stride) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned long long j = i + u * stride;
+        if (j < n4) {
+          const float4 x = __ldg(a4 + j), y = __ldg(b4 + j);
+          acc[u] = fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, acc[u]))));
+        }
+      }
+    }
+    s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  } else {
+    for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n; i += 256ull * gridDim.x) s = fmaf(a[i], b[i], s);
+  }
   s = block_sum_256(s, red);
   if (threadIdx.x == 0) part[l * PARTS + blockIdx.x] = s;
 }
@@ -109,6 +128,17 @@ __global__ void __launch_bounds__(256) wn_backward_apply_kernel(WnTable t, const
   float* dW = t.dW[l];
   const float* v = t.v[l];
   const unsigned long long n = t.n[l];
+  if ((n & 3ull) == 0 && ((reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+    float4* d4 = reinterpret_cast<float4*>(dW);
+    const float4* v4 = reinterpret_cast<const float4*>(v);
+    for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < (n >> 2); i += 256ull * gridDim.x) {
+      float4 d = d4[i];
+      const float4 x = __ldg(v4 + i);
+      d.x = s * (d.x - c * x.x); d.y = s * (d.y - c * x.y); d.z = s * (d.z - c * x.z); d.w = s * (d.w - c * x.w);
+      d4[i] = d;
+    }
+    return;
+  }
   for (unsigned long long i = blockIdx.x * 256ull + threadIdx.x; i < n; i += 256ull * gridDim.x) dW[i] = s * (dW[i] - c * v[i]);
 }
 
@@ -118,6 +148,15 @@ template <typename T>
 __global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__ src, int rows, int cols_in, int cols_out,
                                                        T* __restrict__ dst) {
   const size_t total = (size_t)rows * cols_out;
+  if (cols_in == cols_out && (total & 7) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < (total >> 3); i += 256ull * gridDim.x) {
+      float v[8];
+      load8(src + i * 8, v);
+      store8(dst + i * 8, v);
+    }
+    return;
+  }
   for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < total; i += 256ull * gridDim.x) {
     const int r = (int)(i / cols_out), c = (int)(i - (size_t)r * cols_out);
     dst[i] = Elem<T>::from_f(c < cols_in ? src[(size_t)r * cols_in + c] : 0.f);
@@ -339,11 +378,11 @@ __global__ void __launch_bounds__(256) bce_loss_grad_kernel(const float* __restr
   if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
 __global__ void __launch_bounds__(32) loss_finalize_kernel(const float* __restrict__ part, int n, int B, float* __restrict__ loss) {
-  if (threadIdx.x == 0) {
-    double acc = 0.0;
-    for (int i = 0; i < n; ++i) acc += (double)part[i];
-    loss[0] = (float)(acc / (double)B);
-  }
+  double acc = 0.0;                                   // lane-strided partial sums, then a fixed-order tree: deterministic
+  for (int i = threadIdx.x; i < n; i += 32) acc += (double)part[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x == 0) loss[0] = (float)(acc / (double)B);
 }
 
 // ---- column sums (bias gradients): out[n] = Σ_m x[m,n], deterministic two-pass in one launch ----
