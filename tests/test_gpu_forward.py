@@ -167,3 +167,25 @@ def test_engine_full_batch_properties(engine_mod):
     assert float(la.min()) >= 0.0
     assert torch.allclose(aa.sum(1), torch.ones(1024, device="cuda"), atol=1e-5)
     assert torch.equal(b["label"], torch.max(b["logits"], 1)[1])
+
+
+@pytest.mark.parametrize("relation", [False, True])
+@pytest.mark.parametrize("B", [0, 1, 37, 129])
+def test_engine_empty_single_and_ragged_batches(engine_mod, relation, B):
+    """edge cases of the data-parallel split: an empty shard, one question, sizes that are not tile multiples"""
+    cfg = O.SMALL_REGAT if relation else O.SMALL
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, max(B, 1), 77 + B)
+    batch = {k: (v[:B] if torch.is_tensor(v) else v) for k, v in batch.items()}
+    eng = engine_mod.VQAEngine(W, relation=relation, precision="fp32")
+    kw = dict(bbox=batch["bbox"].cuda(), wh=batch["wh"]) if relation else {}
+    out = eng.forward(batch["img"].cuda(), batch["q"].cuda(), **kw)
+    assert out["logits"].shape == (B, cfg.ans_dim) and out["label"].shape == (B,) and out["att"].shape == (B, cfg.num_objs)
+    if B == 0:
+        assert eng.last_launches == 0
+        return
+    with torch.no_grad():
+        ref, enc = O.forward(batch, W, cfg)
+    assert relerr(out["logits"], ref) < 1e-5
+    assert relerr(out["att"], enc["v_att"][:, :, 0]) < 1e-5
+    assert torch.equal(out["label"].cpu(), ref.argmax(1))

@@ -67,7 +67,7 @@ int updown_train_step(const vqa_train_args&, cudaStream_t);
 int gru_persistent(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
                    void*, cudaStream_t);
 int gru_pair(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
-             void*, cudaStream_t);
+             void*, const GruTrainSave*, cudaStream_t);
 
 bool pdl_enabled() {
   static int v = -1;
@@ -137,7 +137,7 @@ static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
     if (pair < 0) { const char* e = getenv("VQA_B200_GRU_PAIR"); pair = (e && e[0] == '0') ? 0 : 1; }
     if (pair) {
       rc = gru_pair(X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
-                    a.d_h_last, a.d_h_last_lp, a.d_out_all, s);
+                    a.d_h_last, a.d_h_last_lp, a.d_out_all, nullptr, s);
       if (rc != VQA_ERR_UNSUPPORTED) return rc;
     }
     return gru_persistent(X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,

@@ -122,6 +122,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---- internal launchers shared between api.cu and the kernels --------------
+struct GruTrainSave { float *R, *Z, *N, *HN, *Hs; };      // f32 [T,B,H] each; Hs slot t = state after step t
 int linear_simt(const vqa_linear_args& a, cudaStream_t s);
 int linear_tc(const vqa_linear_args& a, cudaStream_t s);
 int linear_tc_part_width();

@@ -49,8 +49,11 @@ struct Params {
   __nv_bfloat16* h_op[2];       // bf16 state, double buffered over steps
   float* h_last;                // [B,H] f32 or NULL
   __nv_bfloat16* h_last_lp;     // [B,H] bf16 or NULL
-  __nv_bfloat16* h_all;         // [B,T,H] bf16 or NULL (sequence form, see gru_tc.cu)
+  __nv_bfloat16* h_all;         // every state, or NULL: [B,T,H] (sequence form, see gru_tc.cu) or, time-major, [T,Bfull,H]
   int* counter;                 // per-row-block arrival counters, zero on entry
+  // training form (train.cu): states time-major, gates saved for the backward pass (f32 [T,Bfull,H] each, chunk offset applied)
+  int time_major, Bfull, b0;
+  float *save_r, *save_z, *save_n, *save_hn, *save_h;   // save_h: slot t = state AFTER step t
 };
 
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -137,14 +140,15 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           while (ld_acquire_gpu(p.counter + m_blk) < target) { }
           fence_proxy_async_all();
           const CUtensorMap* tmH = ((t - 1) & 1) ? &tmH1 : &tmH0;
-          const int hcol = p.h_all ? (t - 1) * p.H : 0;
+          const int hcol = (p.h_all && !p.time_major) ? (t - 1) * p.H : 0;
+          const int hrow = p.time_major ? (t - 1) * p.Bfull + p.b0 + m0 : m0;
           for (int kb = 0; kb < npre; ++kb)
-            tma_load_2d_2cta(base + pre_stage[kb] * STAGE_BYTES, tmH, full_bar(pre_stage[kb]), hcol + kb * BK, m0);
+            tma_load_2d_2cta(base + pre_stage[kb] * STAGE_BYTES, tmH, full_bar(pre_stage[kb]), hcol + kb * BK, hrow);
           for (int kb = npre; kb < kb_h; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
             if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
-            tma_load_2d_2cta(sa, tmH, full_bar(stage), hcol + kb * BK, m0);
+            tma_load_2d_2cta(sa, tmH, full_bar(stage), hcol + kb * BK, hrow);
             load_w(sw, &tmWh, full_bar(stage), kb * BK);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -211,8 +215,10 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       tcgen05_fence_after();
       const uint32_t trow = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
       const bool last = (t == p.T - 1);
-      __nv_bfloat16* hdst = p.h_all ? p.h_all + (size_t)t * p.H : ((last && p.h_last_lp) ? p.h_last_lp : p.h_op[t & 1]);
-      const size_t h_ld = p.h_all ? (size_t)p.T * p.H : (size_t)p.H;
+      const size_t slot = (size_t)t * p.Bfull * p.H;             // time-major slot of this step
+      __nv_bfloat16* hdst = p.h_all ? p.h_all + (p.time_major ? slot : (size_t)t * p.H)
+                                    : ((last && p.h_last_lp) ? p.h_last_lp : p.h_op[t & 1]);
+      const size_t h_ld = (p.h_all && !p.time_major) ? (size_t)p.T * p.H : (size_t)p.H;
 #pragma unroll
       for (int c = 0; c < UPT; c += 8) {
         uint32_t vr[8], vz[8], vni[8], vnh[8];
@@ -240,10 +246,13 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           *reinterpret_cast<uint4*>(hdst + (size_t)row * h_ld + u0 + ub + c) = w0;
         }
       }
-      // accumulator buffer drained: one arrive per warp on the LEADER's barrier (2 CTAs x 16 warps)
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+      const bool saving = p.save_r != nullptr;
+      if (!saving) {
+        // accumulator buffer drained: one arrive per warp on the LEADER's barrier (2 CTAs x 16 warps)
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+      }
       if (!last) {
         __threadfence();
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
@@ -251,6 +260,37 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           fence_proxy_async_all();
           red_release_gpu_add(p.counter + m_blk, 1);
         }
+      }
+      if (saving) {
+        // Training form: what the backward pass needs (train.cu) is written AFTER h_t has been published, so the
+        // 20 extra 16-byte stores per thread stay out of the step-to-step dependency chain; the gates are
+        // recomputed from the accumulators, which are released only now (the next step uses the other buffer).
+#pragma unroll
+        for (int c = 0; c < UPT; c += 8) {
+          uint32_t vr[8], vz[8], vni[8], vnh[8];
+          tmem_ld_32x8(trow + colb + c, vr);
+          tmem_ld_32x8(trow + colb + HALF_UNITS + c, vz);
+          tmem_ld_32x8(trow + colb + 2 * HALF_UNITS + c, vnh);
+          tmem_ld_32x8(trow + COL_NI + ub + c, vni);
+          tmem_ld_wait();
+          float gr[8], gz[8], gn[8], ghn[8], hs[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            gr[j] = sigmoid_fast(__uint_as_float(vr[j]) + bias_s[ub + c + j]);
+            gz[j] = sigmoid_fast(__uint_as_float(vz[j]) + bias_s[UNITS + ub + c + j]);
+            ghn[j] = (__uint_as_float(vnh[j]) - __uint_as_float(vni[j])) + bias_s[3 * UNITS + ub + c + j];
+            gn[j] = tanh_fast(__uint_as_float(vni[j]) + bias_s[2 * UNITS + ub + c + j] + gr[j] * ghn[j]);
+            hs[j] = h[c + j];
+          }
+          if (row_ok) {
+            const size_t off = slot + (size_t)row * p.H + u0 + ub + c;
+            store8(p.save_r + off, gr); store8(p.save_z + off, gz); store8(p.save_n + off, gn); store8(p.save_hn + off, ghn);
+            store8(p.save_h + off, hs);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
       }
     }
     if (row_ok && p.h_last) {
@@ -270,11 +310,12 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
 }  // namespace grup
 
-// Same contract as gru_persistent (gru_tc.cu).  Returns VQA_ERR_UNSUPPORTED (without setting the error text as a
+// Same contract as gru_persistent (gru_tc.cu).  With `save` (training form): h_all is time-major [T,B,H] (slot t = state
+// after step t) and the gates r, z, n, W_hn·h + b_hn and the f32 states are stored per step for the backward pass.  Returns VQA_ERR_UNSUPPORTED (without setting the error text as a
 // failure of the call) when the pair launch is not possible; the caller then uses the single-CTA kernel.
 int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, const void* wh_p,
              const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
-             cudaStream_t s) {
+             const GruTrainSave* save, cudaStream_t s) {
   using namespace grup;
   if (H % UNITS != 0 || E_pad % tc::BK != 0) return VQA_ERR_UNSUPPORTED;
   const int tiles_n = H / UNITS;
@@ -312,8 +353,12 @@ int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, co
     __nv_bfloat16* h1 = (__nv_bfloat16*)h_op + (size_t)B * H + (size_t)b0 * H;
     CUtensorMap tmX, tmH0, tmH1;
     if ((rc = tc::make_tensor_map_bf16(&tmX, Xc, Bc, (long long)T * E_pad, (long long)T * E_pad, tc::BM))) return rc;
-    __nv_bfloat16* hall = h_all ? (__nv_bfloat16*)h_all + (size_t)b0 * T * H : nullptr;
-    if (hall) {
+    const bool tmajor = save != nullptr;
+    __nv_bfloat16* hall = h_all ? (__nv_bfloat16*)h_all + (tmajor ? (size_t)b0 * H : (size_t)b0 * T * H) : nullptr;
+    if (hall && tmajor) {                               // [T*B rows, H]: step t reads rows (t-1)*B + b0 + m0 ..
+      if ((rc = tc::make_tensor_map_bf16(&tmH0, h_all, (long long)T * B, H, H, tc::BM))) return rc;
+      tmH1 = tmH0;
+    } else if (hall) {
       if ((rc = tc::make_tensor_map_bf16(&tmH0, hall, Bc, (long long)T * H, (long long)T * H, tc::BM))) return rc;
       tmH1 = tmH0;
     } else {
@@ -327,6 +372,11 @@ int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, co
     p.h_all = hall;
     p.h_last_lp = h_last_lp ? (__nv_bfloat16*)h_last_lp + (size_t)b0 * H : nullptr;
     p.counter = counter;
+    p.time_major = tmajor ? 1 : 0; p.Bfull = B; p.b0 = b0;
+    const size_t so = (size_t)b0 * H;
+    p.save_r = tmajor ? save->R + so : nullptr; p.save_z = tmajor ? save->Z + so : nullptr;
+    p.save_n = tmajor ? save->N + so : nullptr; p.save_hn = tmajor ? save->HN + so : nullptr;
+    p.save_h = tmajor ? save->Hs + so : nullptr;
     VQA_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int) * tiles_m, s));
     void* args[] = {(void*)&tmX, (void*)&tmH0, (void*)&tmH1, (void*)&tmWx, (void*)&tmWh, (void*)&p};
     cudaLaunchConfig_t cfg = {};

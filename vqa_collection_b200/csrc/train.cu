@@ -16,9 +16,14 @@
 // Master parameters and gradients are f32 under the reference's names; operands are re-cast to
 // the compute dtype every step (the optimiser changed them) and s = g/‖v‖ is re-evaluated on the
 // device.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vqa {
+
+int gru_pair(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
+             void*, const GruTrainSave*, cudaStream_t);
 
 int attention_pool(const float*, int, float, const void*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
@@ -160,6 +165,27 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const float* __restrict__
   for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < total; i += 256ull * gridDim.x) {
     const int r = (int)(i / cols_out), c = (int)(i - (size_t)r * cols_out);
     dst[i] = Elem<T>::from_f(c < cols_in ? src[(size_t)r * cols_in + c] : 0.f);
+  }
+}
+
+// gate-interleaved packing of the GRU weights for the persistent kernel (same layout as engine.pack_gru):
+// dst row j*192 + g*64 + u  <-  src row g*H + 64*j + u (zero padded to cols_out); bias [b_ir+b_hr | b_iz+b_hz | b_in | b_hn]
+template <typename T>
+__global__ void __launch_bounds__(256) pack_gru_kernel(const float* __restrict__ src, int H, int cols_in, int cols_out,
+                                                       T* __restrict__ dst) {
+  const size_t total = (size_t)3 * H * cols_out;
+  for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < total; i += 256ull * gridDim.x) {
+    const int p = (int)(i / cols_out), c = (int)(i - (size_t)p * cols_out);
+    const int j = p / 192, g = (p - j * 192) / 64, u = p - j * 192 - g * 64;
+    const int r = g * H + j * 64 + u;
+    dst[i] = Elem<T>::from_f(c < cols_in ? src[(size_t)r * cols_in + c] : 0.f);
+  }
+}
+__global__ void __launch_bounds__(256) pack_gru_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh, int H,
+                                                            float* __restrict__ out) {
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < 4 * H; i += 256 * gridDim.x) {
+    const int g = i / H, j = i - g * H;
+    out[i] = g < 2 ? b_ih[g * H + j] + b_hh[g * H + j] : (g == 2 ? b_ih[2 * H + j] : b_hh[2 * H + j]);
   }
 }
 
@@ -435,6 +461,7 @@ struct TrainWs {
   void *Wv, *Wqq, *Wvn, *Wc0, *Wc1, *w_ih, *w_hh;
   float *scal, *svec, *wlin, *bqq, *part, *coef;
   void* X; float* GI; float* GH; float* Hs; void* Hlp; float *R, *Z, *N, *HN;
+  void *wx_packed, *wh_packed; float* bias_packed; int* gru_counter;       // persistent forward GRU (bf16)
   float* qq; void* Vp; float* logit; float* att; void* vsum; void* vn; void* joint; void* hid;
   void* dlogits; void* dhid; float* djoint; void* dvn; void* dqq; float* dvsum; float* dlogit;
   float* dwl_part; float* dbl_part; float* dh0; float* dh1; float* dh_part; void* dGI; void* dGH; float* dX; float* dwih_pad;
@@ -459,6 +486,8 @@ static TrainWs carve_train(const vqa_train_args& a, void* base) {
   w.X = take(B * T * Ep * es); w.GI = (float*)take(B * T * 3 * H * 4); w.GH = (float*)take(B * 3 * H * 4);
   w.Hs = (float*)take((T + 1) * B * H * 4); w.Hlp = take((T + 1) * B * H * es);
   w.R = (float*)take(T * B * H * 4); w.Z = (float*)take(T * B * H * 4); w.N = (float*)take(T * B * H * 4); w.HN = (float*)take(T * B * H * 4);
+  w.wx_packed = take(3 * H * Ep * es); w.wh_packed = take(3 * H * H * es); w.bias_packed = (float*)take(4 * H * 4);
+  w.gru_counter = (int*)take(256);
   w.qq = (float*)take(B * 2 * H * 4); w.Vp = take(B * K * H * es); w.logit = (float*)take(B * K * 4); w.att = (float*)take(B * K * 4);
   w.vsum = take(B * V * es); w.vn = take(B * H * es); w.joint = take(B * H * es); w.hid = take(B * 2 * H * es);
   w.dlogits = take(B * ldA * es); w.dhid = take(B * 2 * H * es); w.djoint = (float*)take(B * H * 4); w.dvn = take(B * H * es);
@@ -530,23 +559,41 @@ static int train_step_t(const vqa_train_args& a, const TrainWs& w, cudaStream_t 
   // ---------------- forward ----------------
   gather_f32_kernel<T><<<grid_for((size_t)B * Tn * Ep), 256, 0, s>>>(a.d_tokens, B * Tn, E, Ep, a.ntoken_rows, a.p_emb, (T*)w.X);
   VQA_LAUNCH_CHECK();
-  {
-    vqa_linear_args l{};
-    l.d_A = w.X; l.lda = Ep; l.d_W = w.w_ih; l.ldw = Ep; l.M = B * Tn; l.N = 3 * H; l.K = Ep; l.d_bias = a.p_b_ih;
-    l.d_out = w.GI; l.ldo = 3 * H; l.out_dtype = VQA_F32;
-    if ((rc = lin(l))) return rc;
-  }
   VQA_CUDA_CHECK(cudaMemsetAsync(w.Hs, 0, (size_t)B * H * 4, s));
   VQA_CUDA_CHECK(cudaMemsetAsync(w.Hlp, 0, (size_t)B * H * sizeof(T), s));
   const size_t BH = (size_t)B * H;
-  for (int t = 0; t < Tn; ++t) {
-    vqa_linear_args l{};
-    l.d_A = (T*)w.Hlp + t * BH; l.lda = H; l.d_W = w.w_hh; l.ldw = H; l.M = B; l.N = 3 * H; l.K = H; l.d_bias = a.p_b_hh;
-    l.d_out = w.GH; l.ldo = 3 * H; l.out_dtype = VQA_F32;
-    if ((rc = lin(l))) return rc;
-    gru_gate_train_kernel<T><<<grid_for(BH), 256, 0, s>>>(w.GI, w.GH, B, H, Tn, t, w.Hs + t * BH, w.Hs + (t + 1) * BH,
-                                                         (T*)w.Hlp + (t + 1) * BH, w.R + t * BH, w.Z + t * BH, w.N + t * BH, w.HN + t * BH);
+  // Forward GRU.  bf16: ONE launch of the persistent pair kernel (gru_pair.cu) in its training form — states written
+  // time-major into Hs / Hlp, gates r, z, n and W_hn·h + b_hn saved per step; the input projection is fused, so the
+  // [B*T,3H] gi GEMM and the 2T per-step launches disappear.  fp32 (and devices that cannot hold the pairs): per step.
+  int gru_rc = VQA_ERR_UNSUPPORTED;
+  if (bf16 && H % 64 == 0 && !getenv("VQA_B200_TRAIN_GRU_STEPWISE")) {
+    pack_gru_kernel<T><<<grid_for((size_t)3 * H * Ep), 256, 0, s>>>(a.p_w_ih, H, E, Ep, (T*)w.wx_packed);
     VQA_LAUNCH_CHECK();
+    pack_gru_kernel<T><<<grid_for((size_t)3 * H * H), 256, 0, s>>>(a.p_w_hh, H, H, H, (T*)w.wh_packed);
+    VQA_LAUNCH_CHECK();
+    pack_gru_bias_kernel<<<(4 * H + 255) / 256, 256, 0, s>>>(a.p_b_ih, a.p_b_hh, H, w.bias_packed);
+    VQA_LAUNCH_CHECK();
+    const GruTrainSave save{w.R, w.Z, w.N, w.HN, w.Hs + BH};
+    gru_rc = gru_pair(w.X, B, Tn, H, Ep, w.wx_packed, w.wh_packed, w.bias_packed, nullptr, w.gru_counter, nullptr, nullptr,
+                      (T*)w.Hlp + BH, &save, s);
+    if (gru_rc != VQA_OK && gru_rc != VQA_ERR_UNSUPPORTED) return gru_rc;
+  }
+  if (gru_rc == VQA_ERR_UNSUPPORTED) {
+    {
+      vqa_linear_args l{};
+      l.d_A = w.X; l.lda = Ep; l.d_W = w.w_ih; l.ldw = Ep; l.M = B * Tn; l.N = 3 * H; l.K = Ep; l.d_bias = a.p_b_ih;
+      l.d_out = w.GI; l.ldo = 3 * H; l.out_dtype = VQA_F32;
+      if ((rc = lin(l))) return rc;
+    }
+    for (int t = 0; t < Tn; ++t) {
+      vqa_linear_args l{};
+      l.d_A = (T*)w.Hlp + t * BH; l.lda = H; l.d_W = w.w_hh; l.ldw = H; l.M = B; l.N = 3 * H; l.K = H; l.d_bias = a.p_b_hh;
+      l.d_out = w.GH; l.ldo = 3 * H; l.out_dtype = VQA_F32;
+      if ((rc = lin(l))) return rc;
+      gru_gate_train_kernel<T><<<grid_for(BH), 256, 0, s>>>(w.GI, w.GH, B, H, Tn, t, w.Hs + t * BH, w.Hs + (t + 1) * BH,
+                                                           (T*)w.Hlp + (t + 1) * BH, w.R + t * BH, w.Z + t * BH, w.N + t * BH, w.HN + t * BH);
+      VQA_LAUNCH_CHECK();
+    }
   }
   const T* hT = (T*)w.Hlp + (size_t)Tn * BH;
   {  // qq = ReLU([W_q;q_net] h) f32 [B,2H]

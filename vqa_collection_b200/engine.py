@@ -253,6 +253,9 @@ class VQAEngine:
             if want_alpha:
                 out["alpha"] = torch.empty((B, K, K), dtype=torch.float32, device=dev)
                 a.d_alpha = out["alpha"].data_ptr()
+        if B == 0:                                   # empty shard: nothing to launch, empty outputs
+            self.last_launches = 0
+            return out
         L.check(self.lib.vqa_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         self.last_launches = self.lib.vqa_forward_last_launch_count() + n_cast
         return out
