@@ -21,6 +21,8 @@
 // (dX = dY·W, dW = dYᵀ·X) read the SAME row-major tensors with the contraction index as the
 // row index: `trans_a` / `trans_w` select MN-major operand tiles (TMA boxes {64 mn, 64 k-rows},
 // UMMA descriptors with the M/N-major bit) — again no transpose kernels.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace vqa {
@@ -30,11 +32,14 @@ namespace tc {
 constexpr int THREADS = 256;
 constexpr int EPI_WARP0 = 4;           // warps 4..7 (warp_id % 4 selects the TMEM lane quarter)
 
-template <int BN> struct Cfg {
+// PAIR: two CTAs on one TPC work on a 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA loads its own 128 rows of A
+// and HALF of the W tile (the tensor cores of both SMs read both halves), so the shared-memory fill and the B-operand
+// reads per SM shrink by a third / a half; one thread of the leader CTA issues the MMAs (see gru_pair.cu for the protocol).
+template <int BN, bool PAIR = false> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8));
+  static constexpr int STAGES = PAIR ? 6 : (BN >= 256 ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8)));
   static constexpr int TMEM_COLS = pow2_ge(2 * BN);
   static constexpr int ACC_STRIDE = TMEM_COLS / 2;
   static constexpr int PARAM_FLOATS = 2 * 3 * BN;            // 2 acc stages x (scale,bias,logit_w)
@@ -56,10 +61,11 @@ struct Params {
 };
 
 // ---- the kernel ----------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool PAIR = false>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Params p) {
-  using C = Cfg<BN>;
+  static_assert(!PAIR || (!A_MN && !B_MN), "CTA pairs are built for the K-major forward form");
+  using C = Cfg<BN, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B needs 1024-byte alignment
@@ -75,7 +81,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   float* stage_out = params_smem + C::PARAM_FLOATS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  // PAIR: the pair walks over (row-block pair, n_blk) tiles; this CTA owns row block 2*mp + rank of each
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const bool lead = crank == 0;
+  const int num_tiles = PAIR ? ((p.tiles_m + 1) / 2) * p.tiles_n : p.tiles_m * p.tiles_n;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_m = [&](int tile) { return PAIR ? 2 * (tile / p.tiles_n) + (int)crank : tile / p.tiles_n; };
   const int num_kb = (p.K + BK - 1) / BK;      // K tail: TMA zero-fills both operands
 
   if (warp == 0 && lane == 0) {
@@ -84,12 +96,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    // accumulator release: 128 epilogue threads, or (PAIR) one arrive per epilogue warp of both CTAs on the leader's barrier
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 8 : 128); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 2) { if constexpr (PAIR) tmem_alloc_2cta(tmem_slot, C::TMEM_COLS); else tmem_alloc(tmem_slot, C::TMEM_COLS); }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   griddep_launch();              // PDL: the next kernel may set itself up behind us ...
@@ -99,11 +113,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = tile_m(tile), n_blk = tile % p.tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          if constexpr (PAIR) {                      // both CTAs fill their own slots; bytes are counted on the leader's barrier
+            if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+            tma_load_2d_2cta(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
+            tma_load_2d_2cta(sb, &tmW, full_bar(stage), kb * BK, n_blk * BN + (int)crank * (BN / 2));
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
           if constexpr (!A_MN) {
             tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
@@ -125,11 +146,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN) | (A_MN ? IDESC_A_MN_MAJOR : 0u) | (B_MN ? IDESC_B_MN_MAJOR : 0u);
+    if (lane == 0 && lead) {
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN) | (A_MN ? IDESC_A_MN_MAJOR : 0u) | (B_MN ? IDESC_B_MN_MAJOR : 0u);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
@@ -145,10 +166,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                         : make_sw128_kmajor_desc(sa) + (uint64_t)(2 * k);
             const uint64_t bdesc = B_MN ? make_sw128_mnmajor_desc(sb + k * 2048, BK * 128, 1024)
                                         : make_sw128_kmajor_desc(sb) + (uint64_t)(2 * k);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            if constexpr (PAIR) umma_bf16_2cta(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));                     // smem slot reusable when these MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc)); // accumulator complete
+          if constexpr (PAIR) {                              // both CTAs' slots / accumulators
+            umma_commit_2cta(empty_bar(stage), 0b11);
+            if (kb == num_kb - 1) umma_commit_2cta(tfull_bar(acc), 0b11);
+          } else {
+            umma_commit(empty_bar(stage));                     // smem slot reusable when these MMAs retire
+            if (kb == num_kb - 1) umma_commit(tfull_bar(acc)); // accumulator complete
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -159,8 +186,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp - EPI_WARP0;                  // == warp % 4: TMEM lane quarter
     const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / p.tiles_n, n_blk = tile % p.tiles_n;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_blk = tile_m(tile), n_blk = tile % p.tiles_n;
       const int n0 = n_blk * BN;
       // stage this tile's per-column parameters (double buffered with the accumulator)
       float* ps = params_smem + acc * 3 * BN;
@@ -296,15 +323,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.logit_w && row_ok) reinterpret_cast<float*>(p.out)[(size_t)row * p.n_parts + n_blk] = part;
       // release the accumulator stage
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      if constexpr (PAIR) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+      } else {
+        mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();              // the peer may still read our slots / signal our barriers
   tcgen05_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (warp == 2) { if constexpr (PAIR) tmem_dealloc_2cta(tmem_base, C::TMEM_COLS); else tmem_dealloc(tmem_base, C::TMEM_COLS); }
 }
 
 // ---- host side -------------------------------------------------------------------
@@ -379,6 +412,55 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
   return VQA_OK;
 }
 
+// 256 x 256 tiles on CTA pairs (tcgen05 cta_group::2) for the large K-major GEMMs.  VQA_ERR_UNSUPPORTED = the device cannot
+// hold the pairs (or VQA_B200_GEMM_PAIR=0): the caller falls back to one CTA per tile.
+static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
+  constexpr int BN = 256;
+  using C = Cfg<BN, true>;
+  auto kern = linear_tc_kernel<BN, false, false, true>;
+  static int pairs_resident = -1;
+  if (pairs_resident < 0) {
+    const char* e = getenv("VQA_B200_GEMM_PAIR");
+    pairs_resident = 0;
+    if (!(e && e[0] == '0') &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * (sm_count() / 2)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, (const void*)kern, &cfg) == cudaSuccess) pairs_resident = n;
+    }
+    (void)cudaGetLastError();
+  }
+  if (pairs_resident <= 0) return VQA_ERR_UNSUPPORTED;
+  CUtensorMap tmA, tmW;
+  int rc;
+  if ((rc = make_tensor_map_bf16(&tmA, a.d_A, a.M, a.K, a.lda, BM))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmW, a.d_W, a.N, a.K, a.ldw, BN / 2))) return rc;
+  Params p;
+  p.M = a.M; p.N = a.N; p.K = a.K;
+  p.scale = a.d_scale; p.bias = a.d_bias; p.relu = a.relu;
+  p.mul = a.d_mul; p.ld_mul = a.ld_mul; p.mul_row_div = a.mul_row_div > 0 ? a.mul_row_div : 1;
+  p.add = a.d_add; p.ld_add = a.ld_add; p.add_row_div = a.add_row_div > 0 ? a.add_row_div : 1;
+  p.mask = a.d_mask; p.ld_mask = a.ld_mask; p.mask_bf16 = (a.mask_dtype == VQA_BF16);
+  p.logit_w = a.d_logit_w; p.out = a.d_out; p.ldo = a.ldo; p.out_bf16 = (a.out_dtype == VQA_BF16);
+  p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
+  p.leaky_slope = a.leaky_slope; p.add_after_act = a.add_after_act; p.sigmoid = a.sigmoid;
+  const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
+  const int pairs = pair_tiles < pairs_resident ? pair_tiles : pairs_resident;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  VQA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, p));
+  VQA_LAUNCH_CHECK();
+  return VQA_OK;
+}
+
 template <bool A_MN, bool B_MN>
 static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
   // Large GEMMs (a tile for every SM at BN = 256) are tensor-bound: widest tile.  Small-M layers are bound by
@@ -388,7 +470,15 @@ static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
   // BN = 192 -> 136 tiles = 1 wave.
   const int tiles_m = (a.M + BM - 1) / BM;
   const int sms = sm_count();
-  if (a.d_logit_w || tiles_m * ((a.N + 255) / 256) >= sms) return launch<256, A_MN, B_MN>(a, s);
+  if (a.d_logit_w || tiles_m * ((a.N + 255) / 256) >= sms) {
+    if constexpr (!A_MN && !B_MN) {
+      if (tiles_m * ((a.N + 255) / 256) >= 2 * sms) {          // many tiles per SM: CTA pairs pay
+        const int rc = launch_pair(a, s);
+        if (rc != VQA_ERR_UNSUPPORTED) return rc;
+      }
+    }
+    return launch<256, A_MN, B_MN>(a, s);
+  }
   int best_bn = 256, best_cost = 1 << 30;
   for (int bn : {256, 192, 128, 64}) {
     if (bn == 192 && (A_MN || B_MN)) continue;       // MN-major operand tiles come in 64-wide atoms: 256 / 128 / 64 only
