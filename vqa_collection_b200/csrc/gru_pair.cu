@@ -25,23 +25,27 @@ namespace grup {
 
 using namespace tc;
 
-constexpr int UNITS = 64;                         // hidden units per CTA pair
-constexpr int WROWS = 3 * UNITS;                  // 192 rows of the packed W block
-constexpr int HALF_UNITS = UNITS / 2;             // units whose W rows one CTA holds
+constexpr int PACK_UNITS = 64;                    // the packed weights come in 192-row blocks of 64 units ([r|z|n])
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_WARPS = 16;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;   // 640
-constexpr int UPT = UNITS / (EPI_WARPS / 4);      // 16 units per epilogue thread
 constexpr int W_PREFETCH = 4;
 constexpr int A_BYTES = BM * BK * 2;              // 16 KB
-constexpr int W_BYTES = 3 * HALF_UNITS * BK * 2;  // 12 KB: this CTA's half of the W tile
-constexpr int STAGE_BYTES = A_BYTES + W_BYTES;    // 28 KB
-constexpr int STAGES = 7;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;
-constexpr int COL_NI = 192;
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + 4 * UNITS * 4;
+
+// UNITS = hidden units per CTA pair: 64 normally; 32 when the batch is so small that 64-unit tiles would leave
+// half of the SMs idle (B <= 512 at H = 1024) — twice the CTAs, half the W tile and half the gate math per CTA.
+template <int UNITS> struct Cfg {
+  static constexpr int HALF_UNITS = UNITS / 2;             // units whose W rows one CTA holds
+  static constexpr int UPT = UNITS / (EPI_WARPS / 4);      // units per epilogue thread (16 / 8)
+  static constexpr int W_BYTES = 3 * HALF_UNITS * BK * 2;  // this CTA's half of the W tile (12 KB / 6 KB)
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;    // 28 KB / 22 KB
+  static constexpr int STAGES = UNITS == 64 ? 7 : 9;
+  static constexpr int COL_NI = 3 * UNITS;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + 4 * UNITS * 4;
+};
 
 struct Params {
   int B, T, H, E_pad, tiles_n, num_ctas;
@@ -59,10 +63,13 @@ struct Params {
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
+template <int UNITS>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH0,
                 const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmWx,
                 const __grid_constant__ CUtensorMap tmWh, const Params p) {
+  using C = Cfg<UNITS>;
+  constexpr int HALF_UNITS = C::HALF_UNITS, UPT = C::UPT, STAGE_BYTES = C::STAGE_BYTES, STAGES = C::STAGES, COL_NI = C::COL_NI;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -105,11 +112,12 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_ptr;
   griddep_launch();
 
-  // this CTA's half of the 192-row W tile: rows [r | z | n] of units [32·crank, 32·crank + 32)
+  // this CTA's half of the pair's W rows: [r | z | n] rows of units [u0 + HALF·crank, u0 + HALF·crank + HALF)
   auto load_w = [&](uint32_t sw, const CUtensorMap* map, uint32_t bar, int col) {
 #pragma unroll
     for (int g = 0; g < 3; ++g)
-      tma_load_2d_2cta(sw + g * (HALF_UNITS * 128), map, bar, col, n_blk * WROWS + g * UNITS + (int)crank * HALF_UNITS);
+      tma_load_2d_2cta(sw + g * (HALF_UNITS * 128), map, bar, col,
+                       (u0 / PACK_UNITS) * (3 * PACK_UNITS) + g * PACK_UNITS + (u0 % PACK_UNITS) + (int)crank * HALF_UNITS);
   };
 
   if (warp == 0) {
@@ -158,9 +166,9 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the LEADER CTA drives both tensor cores =====
     if (lane == 0 && lead) {
-      constexpr uint32_t idesc_rzn = make_idesc_bf16(2 * BM, 3 * UNITS);   // M = 256, N = 192
-      constexpr uint32_t idesc_n = make_idesc_bf16(2 * BM, UNITS);         // M = 256, N = 64: n rows of both halves
-      constexpr uint32_t N_ROW_OFF = (2 * HALF_UNITS * BK * 2) >> 4;       // rows 64.. of a half tile (8 KB)
+      constexpr uint32_t idesc_rzn = make_idesc_bf16(2 * BM, 3 * UNITS);   // M = 256, N = 192 (96)
+      constexpr uint32_t idesc_n = make_idesc_bf16(2 * BM, UNITS);         // M = 256, N = 64 (32): n rows of both halves
+      constexpr uint32_t N_ROW_OFF = (2 * HALF_UNITS * BK * 2) >> 4;       // the n rows of a half tile
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < p.T; ++t) {
         const int acc = t & 1;
@@ -313,18 +321,22 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // Same contract as gru_persistent (gru_tc.cu).  With `save` (training form): h_all is time-major [T,B,H] (slot t = state
 // after step t) and the gates r, z, n, W_hn·h + b_hn and the f32 states are stored per step for the backward pass.  Returns VQA_ERR_UNSUPPORTED (without setting the error text as a
 // failure of the call) when the pair launch is not possible; the caller then uses the single-CTA kernel.
-int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, const void* wh_p,
-             const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
-             const GruTrainSave* save, cudaStream_t s) {
+template <int UNITS>
+static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void* wx_p, const void* wh_p,
+                      const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
+                      const GruTrainSave* save, cudaStream_t s) {
   using namespace grup;
-  if (H % UNITS != 0 || E_pad % tc::BK != 0) return VQA_ERR_UNSUPPORTED;
+  using C = Cfg<UNITS>;
+  constexpr int HALF_UNITS = C::HALF_UNITS, SMEM_BYTES = C::SMEM_BYTES;
+  auto kernel = gru_pair_kernel<UNITS>;
+  if (H % PACK_UNITS != 0 || E_pad % tc::BK != 0) return VQA_ERR_UNSUPPORTED;
   const int tiles_n = H / UNITS;
   const int sms = sm_count();
   int max_tiles_m = (sms / tiles_n) & ~1;            // pairs: an even number of 128-row blocks per launch
   if (max_tiles_m < 2) return VQA_ERR_UNSUPPORTED;
   static int usable = -1;                            // can max_tiles_m * tiles_n CTAs run as co-resident pairs?
   if (usable < 0) {
-    if (cudaFuncSetAttribute(gru_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
       (void)cudaGetLastError();
       usable = 0;
     } else {
@@ -334,7 +346,7 @@ int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, co
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int clusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&clusters, (const void*)gru_pair_kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); clusters = 0; }
+      if (cudaOccupancyMaxActiveClusters(&clusters, (const void*)kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); clusters = 0; }
       usable = clusters > 0 ? clusters : 0;          // number of pairs the device can hold at once
     }
   }
@@ -385,10 +397,23 @@ int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, co
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 2;
-    VQA_CUDA_CHECK(cudaLaunchKernelExC(&cfg, (const void*)gru_pair_kernel, args));
+    VQA_CUDA_CHECK(cudaLaunchKernelExC(&cfg, (const void*)kernel, args));
     count_launch();
   }
   return VQA_OK;
+}
+
+int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, const void* wh_p,
+             const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
+             const GruTrainSave* save, cudaStream_t s) {
+  // 32-unit tiles when 64-unit tiles would use at most half of the SMs (VQA_B200_GRU_UNITS=64 forces the wide tile)
+  static int force64 = -1;
+  if (force64 < 0) { const char* e = getenv("VQA_B200_GRU_UNITS"); force64 = (e && atoi(e) == 64) ? 1 : 0; }
+  const int row_pairs = (B + 2 * tc::BM - 1) / (2 * tc::BM);
+  const int ctas64 = 2 * row_pairs * (H / grup::PACK_UNITS);
+  if (!force64 && H % grup::PACK_UNITS == 0 && 2 * ctas64 <= sm_count())
+    return gru_pair_t<32>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, s);
+  return gru_pair_t<64>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, s);
 }
 
 }  // namespace vqa
