@@ -39,6 +39,11 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 print(f"q-cap forward_vqa B={B}: {ms*1e3:.1f} us/step = {B/ms*1e3:.0f} questions/s", flush=True)
+import json
+print(json.dumps({"metric": "Q-Relevant caption-embedding + Up-Down joint forward questions/sec (BASELINE config 5)",
+                  "value": B / ms * 1e3, "unit": "questions/s", "n_gpus": 1, "ms_per_step": ms, "dtype": "bf16",
+                  "data": "synthetic", "config": {"workload": "q-cap predictor, 20-token captions, module-level API "
+                  "(Wrapper.forward_vqa), bf16 features resident", "batch": B}}), flush=True)
 if os.environ.get("PROFILE"):
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:

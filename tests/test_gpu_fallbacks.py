@@ -1,0 +1,56 @@
+"""The single-CTA kernels behind the CTA-pair paths (taken when a device cannot hold the pairs) and the launch
+without programmatic dependent launch must give the same answers: each switch is read once per process, so every
+variant runs in its own subprocess and is compared with the default path and the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r"""
+import sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch
+from oracle import vqa_oracle as O
+from vqa_collection_b200.engine import VQAEngine
+cfg = O.FULL_REGAT
+W = O.make_weights(cfg, 1111)
+batch = O.make_batch(cfg, 300, 910)           # 300 rows: ragged pair tiles, wide GEMM large enough for CTA pairs
+eng = VQAEngine(W, relation=True, precision="bf16")
+out = eng.forward(batch["img"].cuda(), batch["q"].cuda(), bbox=batch["bbox"].cuda(), wh=batch["wh"])
+np.savez(sys.argv[2], logits=out["logits"].cpu().numpy(), att=out["att"].cpu().numpy(), label=out["label"].cpu().numpy())
+"""
+
+
+def _run(tmp_path, name, env):
+    out = str(tmp_path / (name + ".npz"))
+    e = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", **env)
+    r = subprocess.run([sys.executable, "-c", SCRIPT, ROOT, out], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return np.load(out)
+
+
+def test_single_cta_and_no_pdl_paths_match_default(tmp_path):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from oracle import vqa_oracle as O
+    ref = _run(tmp_path, "default", {})
+    cfg = O.FULL_REGAT
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, 300, 910)
+    with torch.no_grad():
+        oracle_logits, enc = O.forward(batch, W, cfg)
+    scale = float(oracle_logits.abs().max())
+    assert np.abs(ref["logits"] - oracle_logits.numpy()).max() / scale < 1e-2
+    for name, env in (("gru_single", {"VQA_B200_GRU_PAIR": "0"}), ("gemm_single", {"VQA_B200_GEMM_PAIR": "0"}),
+                      ("no_pdl", {"VQA_B200_NO_PDL": "1"}), ("gru_units64", {"VQA_B200_GRU_UNITS": "64"})):
+        got = _run(tmp_path, name, env)
+        # same arithmetic in the same order: the variants differ in who loads what, not in what is summed
+        assert np.abs(got["logits"] - ref["logits"]).max() / scale < 1e-3, name
+        assert np.abs(got["att"] - ref["att"]).max() < 1e-3, name
+        assert (got["label"] == ref["label"]).mean() > 0.99, name

@@ -75,6 +75,12 @@ bool pdl_enabled() {
   return v == 1;
 }
 
+bool l2_order_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VQA_B200_NO_L2_ORDER"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 static bool force_simt() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("VQA_B200_FORCE_SIMT"); v = (e && e[0] == '1') ? 1 : 0; }

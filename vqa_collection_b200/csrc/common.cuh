@@ -56,6 +56,9 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 bool pdl_enabled();            // VQA_B200_NO_PDL=1 turns the launch attribute off (A/B timing)
+// Consumers of a tensor that the previous kernel swept in ascending order walk it in DESCENDING order, so that they
+// start on the part that is still in the 126 MB L2 (VQA_B200_NO_L2_ORDER=1 restores ascending order for A/B timing).
+bool l2_order_enabled();
 
 // launch `kernel` so that it may start while the previous kernel of the stream is still draining
 template <typename... KArgs, typename... Args>

@@ -23,6 +23,8 @@
 // (loads + MMAs into the second D1/D2 buffer) runs while the epilogue warps do phase 2 of image n,
 // so the K×K stage never stalls the load stream.
 // Per image HBM traffic = Q, x, P, S (4 × 147 KB) + out: the kernel is HBM-bound by design.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace vqa {
@@ -64,6 +66,7 @@ constexpr int SMEM_BYTES = 1024 + P2_OFF + (int)sizeof(P2);
 
 struct Params {
   int B, V;
+  int rev;                     // walk the images in descending order (the tail of Y is what the GEMM left in L2)
   const float* att; const uint8_t* labels; int num_labels; float c0;
   __nv_bfloat16* out; __nv_bfloat16* vsum; float* alpha;
 };
@@ -126,7 +129,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       auto load_g = [&](int img) {                   // phase-1 operands of one image
-        const int row0 = img * GK;
+        const int row0 = (p.rev ? p.B - 1 - img : img) * GK;
         for (int kb = 0; kb < kb_g; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t slot = base + stage * SLOT_BYTES;
@@ -140,7 +143,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       if ((int)blockIdx.x < p.B) load_g(blockIdx.x);
       for (int img = blockIdx.x; img < p.B; img += gridDim.x) {
         if (img + (int)gridDim.x < p.B) load_g(img + gridDim.x);
-        const int row0 = img * GK;
+        const int row0 = (p.rev ? p.B - 1 - img : img) * GK;
         for (int cc = 0; cc < n_cc; ++cc) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t slot = base + stage * SLOT_BYTES;
@@ -217,7 +220,8 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const int hf = (warp - EPI_WARP0) >> 2;          // which half of the phase-3 tiles
     const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..255
     // ---- phase 0: attention scalars, row adjacency masks, label histogram of one image
-    auto phase0 = [&](int img) {
+    auto phase0 = [&](int img_it) {
+      const int img = p.rev ? p.B - 1 - img_it : img_it;
       if (et < GK) {
         sm.a[et] = p.att ? __ldg(p.att + (size_t)img * GK + et) : 1.f;
         const uint32_t* lr = reinterpret_cast<const uint32_t*>(p.labels + ((size_t)img * GK + et) * GK);
@@ -350,7 +354,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
       if (p.alpha != nullptr)
         for (int e = et; e < GK * GK; e += EPI_THREADS)
-          p.alpha[(size_t)img * GK * GK + e] = sm.Al[e / GK][e % GK];
+          p.alpha[(size_t)(p.rev ? p.B - 1 - img : img) * GK * GK + e] = sm.Al[e / GK][e % GK];
       fence_proxy_async();
       epi_bar();
       if (et == 0) mbar_arrive(c_full);
@@ -372,7 +376,8 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         mbar_arrive(oempty_bar(buf));
         const int c = cc * CH + q * 32 + lane;
         float vs = 0.f;
-        __nv_bfloat16* o = p.out ? p.out + (size_t)img * GK * V + c : nullptr;
+        const int oimg = p.rev ? p.B - 1 - img : img;
+        __nv_bfloat16* o = p.out ? p.out + (size_t)oimg * GK * V + c : nullptr;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float s = fmaxf(__uint_as_float(v[i]), 0.f);
@@ -385,7 +390,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           vs += s;
           if (o) o[(size_t)i * V] = __float2bfloat16_rn(s);
         }
-        if (p.vsum) p.vsum[(size_t)img * V + c] = __float2bfloat16_rn(vs);
+        if (p.vsum) p.vsum[(size_t)oimg * V + c] = __float2bfloat16_rn(vs);
       }
     }
   }
@@ -419,6 +424,10 @@ int graph_attention_tc(const vqa_graph_attention_args& a, cudaStream_t s) {
   Params p;
   p.B = a.B; p.V = a.V; p.att = a.d_att; p.labels = a.d_labels; p.num_labels = a.num_labels; p.c0 = a.c0;
   p.out = (__nv_bfloat16*)a.d_out; p.vsum = (__nv_bfloat16*)a.d_vsum; p.alpha = a.d_alpha;
+  // measured: no gain here (1089 vs 1085 us per ReGAT step) — Y is 3.6x the L2, the tail that survives is small
+  static int rev = -1;
+  if (rev < 0) { const char* e = getenv("VQA_B200_GAT_REVERSE"); rev = (e && e[0] == '1') ? 1 : 0; }
+  p.rev = rev;
   static bool attr_set = false;
   if (!attr_set) {
     VQA_CUDA_CHECK(cudaFuncSetAttribute(graph_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -19,13 +19,15 @@ constexpr int kPoolMaxK = 64;
 template <typename T>
 __global__ void __launch_bounds__(kPoolThreads)
 attention_pool_kernel(const float* __restrict__ parts, int n_parts, float bias,
-                      const T* __restrict__ x, int B, int K, int V, int slices,
+                      const T* __restrict__ x, int B, int K, int V, int slices, int rev,
                       float* __restrict__ att_out, T* __restrict__ vsum, T* __restrict__ vatt) {
   __shared__ float s_att[kPoolMaxK];
   griddep_launch();
   griddep_wait();
-  const int b = blockIdx.x / slices;
-  const int slice = blockIdx.x - b * slices;
+  // images in DESCENDING order: the projection GEMM that ran just before swept the same features in ascending row
+  // order, so its last ~100 MB are still in the 126 MB L2 when the first CTAs of this kernel ask for them
+  const int b = rev ? B - 1 - (int)(blockIdx.x / slices) : (int)(blockIdx.x / slices);
+  const int slice = blockIdx.x % slices;
   const int tid = threadIdx.x;
   if (tid < 32) {
     // K <= 64: lane handles k = lane and k = lane + 32
@@ -88,13 +90,14 @@ int attention_pool(const float* parts, int n_parts, float bias, const void* x, i
   const bool stream_x = vsum != nullptr || vatt != nullptr;
   const int slices = stream_x ? (V + kPoolChan - 1) / kPoolChan : 1;
   const unsigned grid = (unsigned)B * slices;
+  const int rev = l2_order_enabled() ? 1 : 0;
   if (dtype == VQA_BF16) {
     VQA_CUDA_CHECK(launch_pdl(attention_pool_kernel<__nv_bfloat16>, dim3(grid), dim3(kPoolThreads), 0, s,
-                              parts, n_parts, bias, (const __nv_bfloat16*)x, B, K, V, slices, att, (__nv_bfloat16*)vsum,
+                              parts, n_parts, bias, (const __nv_bfloat16*)x, B, K, V, slices, rev, att, (__nv_bfloat16*)vsum,
                               (__nv_bfloat16*)vatt));
   } else {
     VQA_CUDA_CHECK(launch_pdl(attention_pool_kernel<float>, dim3(grid), dim3(kPoolThreads), 0, s, parts, n_parts, bias,
-                              (const float*)x, B, K, V, slices, att, (float*)vsum, (float*)vatt));
+                              (const float*)x, B, K, V, slices, rev, att, (float*)vsum, (float*)vatt));
   }
   VQA_LAUNCH_CHECK();
   return VQA_OK;
