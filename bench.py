@@ -290,11 +290,11 @@ def main():
         k_ms = e0.elapsed_time(e1) / reps
         flops = 2.0 * B * 36 * P["H"] * P["V"]
         achieved = flops / (k_ms / 1e3) / 1e12
-        roof = {"kernel": "linear_tc_kernel<256> (W_v projection + logit reduction)", "bound": "tensor",
+        roof = {"kernel": "linear_tc_kernel<256,pair> (W_v projection + logit reduction, tcgen05 cta_group::2)", "bound": "tensor",
                 "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch, `ncu --set full`
-                # (profiles/r01d_ncu_wv.md: 159.47 MB read + 5.43 MB written; algorithmic bytes = 159.0 MB at B=1024)
-                "traffic": (164.9e6 * B / 1024), "traffic_source": "profiles/r01d_ncu_wv.md", "peak_source": pk["src"] + " burst (kernel timed alone)", "launch_ms": k_ms,
+                # (profiles/r01e_ncu_wv.md: 159.48 MB read + 6.71 MB written; algorithmic bytes = 159.0 MB at B=1024)
+                "traffic": (166.2e6 * B / 1024), "traffic_source": "profiles/r01e_ncu_wv.md", "peak_source": pk["src"] + " burst (kernel timed alone)", "launch_ms": k_ms,
                 "flops_per_launch": flops}
     path_tflops = value / world * FLOPS_PER_Q[args.workload] / 1e12
 

@@ -228,6 +228,12 @@ int vqa_graph_attention(const vqa_graph_attention_args* args, void* stream);
  * ---------------------------------------------------------------------- */
 int vqa_argmax_rows(const float* d_logits, int B, int A, int ld, int64_t* d_label,
                     void* stream);
+/* VQA soft score of the chosen answers, replaces wrapper.py:16-22 (one_hot(label) * target) and the
+ * `.sum()` the evaluation loop takes of it (train.py:186-189), with no host round trip:
+ *   d_scores_dense [B,A] f32 or NULL;  d_score_row [B] f32 = target[b, label[b]] or NULL;
+ *   d_score_sum [1] f32 = sum_b score_row[b] (fixed summation order) or NULL (needs d_score_row). */
+int vqa_answer_scores(const int64_t* d_label, const float* d_target, int B, int A, int ld_target,
+                      float* d_scores_dense, float* d_score_row, float* d_score_sum, void* stream);
 
 /* ------------------------------------------------------------------------
  * config 5 (predictor_type 'q-cap') glue between the GEMMs and the two caption GRUs

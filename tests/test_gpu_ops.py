@@ -335,3 +335,21 @@ def test_graph_attention_layer(ops, dtype, merged, cfg, B):
     out1, _, _ = run(None, True, False, False)
     # (un-attended features are 36x larger: α is far more peaked, so bf16 gets 3x the slack)
     assert relerr(out1, torch.relu(want1)) < (tol if dtype == torch.float32 else 3 * tol)
+
+
+def test_answer_scores(ops):
+    g = torch.Generator().manual_seed(4)
+    B, A = 67, 3129
+    target = torch.zeros((B, A))
+    idx = torch.randint(0, A, (B, 3), generator=g)
+    target.scatter_(1, idx, torch.randint(1, 4, (B, 3), generator=g).float() / 3.0)
+    logits = torch.randn((B, A), generator=g)
+    logits[:, 7] = logits.max() + 1.0                  # a tie between two answers: the lowest index wins
+    logits[:, 3000] = logits[:, 7]
+    ref_score, ref_label = O.compute_score(logits, target)
+    label = ops.argmax_rows(logits.cuda())
+    dense, row, total = ops.answer_scores(label, target.cuda(), want_dense=True, want_sum=True)
+    assert torch.equal(label.cpu(), ref_label) and torch.equal(dense.cpu(), ref_score)
+    assert torch.equal(row.cpu(), ref_score.sum(1)) and abs(float(total) - float(ref_score.sum())) < 1e-4
+    _, row2, _ = ops.answer_scores(label, target.cuda(), want_dense=False)
+    assert torch.equal(row2, row)

@@ -134,6 +134,7 @@ SYMBOLS = {
     "vqa_attention_pool": (c_int, [c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "vqa_graph_attention": (c_int, [C.POINTER(GraphAttentionArgs), c_void_p]),
+    "vqa_answer_scores": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vqa_caption_gate_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p]),
     "vqa_seq_max": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -51,6 +51,7 @@ int require_sm100() {
 // kernels implemented in the other translation units
 int relation_labels(const float*, const float*, int, int, float, float, uint8_t*, cudaStream_t);
 float relation_near_threshold(float, float);
+int answer_scores(const int64_t*, const float*, int, int, int, float*, float*, float*, cudaStream_t);
 int caption_gate_scale(const void*, const float*, const float*, int, int, int, int, void*, float*, cudaStream_t);
 int seq_max(const void*, int, int, int, int, void*, cudaStream_t);
 int softmax_mul(const float*, const void*, int, int, int, void*, cudaStream_t);
@@ -276,6 +277,12 @@ int vqa_graph_attention(const vqa_graph_attention_args* args, void* stream) {
 int vqa_argmax_rows(const float* d_logits, int B, int A, int ld, int64_t* d_label, void* stream) {
   if (int rc = require_sm100()) return rc;
   return argmax_rows(d_logits, B, A, ld, d_label, (cudaStream_t)stream);
+}
+
+int vqa_answer_scores(const int64_t* d_label, const float* d_target, int B, int A, int ld_target, float* d_scores_dense,
+                      float* d_score_row, float* d_score_sum, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return answer_scores(d_label, d_target, B, A, ld_target, d_scores_dense, d_score_row, d_score_sum, (cudaStream_t)stream);
 }
 
 int vqa_caption_gate_scale(const void* d_out_w, const float* d_p, const float* d_r, int B, int T, int H, int dtype,

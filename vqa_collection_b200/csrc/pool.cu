@@ -213,6 +213,49 @@ int gru_gate(const float* gi, const float* gh, int B, int H, int T, int t, const
 }
 
 // ---------------------------------------------------------------------------
+// a14 / f4: VQA soft score of the chosen answers (wrapper.py:16-22: one_hot(label) ⊙ target) without the
+// zeros → scatter → multiply round trips: one block per question writes its dense row (optional) and
+// score_row[b] = target[b, label[b]]; a single warp then sums the rows in a fixed order (deterministic).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+answer_scores_kernel(const int64_t* __restrict__ label, const float* __restrict__ target, int A, int ld,
+                     float* __restrict__ dense, float* __restrict__ score_row) {
+  const int b = blockIdx.x;
+  const long long l = label[b];
+  const float v = (l >= 0 && l < A) ? target[(size_t)b * ld + l] : 0.f;
+  if (dense != nullptr) {
+    float* row = dense + (size_t)b * A;
+    for (int n = threadIdx.x; n < A; n += 256) row[n] = (n == l) ? v : 0.f;
+  }
+  if (score_row != nullptr && threadIdx.x == 0) score_row[b] = v;
+}
+__global__ void __launch_bounds__(32) score_sum_kernel(const float* __restrict__ score_row, int B, float* __restrict__ out) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < B; i += 32) acc += (double)score_row[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (threadIdx.x == 0) out[0] = (float)acc;
+}
+
+int answer_scores(const int64_t* label, const float* target, int B, int A, int ld, float* dense, float* score_row,
+                  float* score_sum, cudaStream_t s) {
+  VQA_REQUIRE(B >= 0 && A >= 1 && ld >= A, "answer_scores: bad dims B=%d A=%d ld=%d", B, A, ld);
+  VQA_REQUIRE(score_sum == nullptr || score_row != nullptr, "answer_scores: d_score_sum needs d_score_row");
+  if (B == 0) {
+    if (score_sum) VQA_CUDA_CHECK(cudaMemsetAsync(score_sum, 0, sizeof(float), s));
+    return VQA_OK;
+  }
+  VQA_REQUIRE(label && target, "answer_scores: NULL input");
+  answer_scores_kernel<<<B, 256, 0, s>>>(label, target, A, ld, dense, score_row);
+  VQA_LAUNCH_CHECK();
+  if (score_sum) {
+    score_sum_kernel<<<1, 32, 0, s>>>(score_row, B, score_sum);
+    VQA_LAUNCH_CHECK();
+  }
+  return VQA_OK;
+}
+
+// ---------------------------------------------------------------------------
 // casts (wire format f32 -> resident bf16 and back)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

@@ -17,13 +17,14 @@ def compute_score(predict, target, device, get_label=False):
     """VQA soft score of the lowest-index argmax answer (wrapper.py:8-22)."""
     predict = predict.to(device)
     target = target.to(device)
-    if predict.is_cuda:
+    if predict.is_cuda and target.is_cuda:
         logits = ops.argmax_rows(predict.float().contiguous())          # torch.max(predict, 1)[1] tie rule
+        scores, _, _ = ops.answer_scores(logits, target.float().contiguous())     # one_hot ⊙ target in one kernel
     else:
         logits = torch.max(predict, 1)[1].data
-    one_hots = torch.zeros(*target.size(), device=target.device)      # (the reference fills it on the host and copies)
-    one_hots.scatter_(1, logits.view(-1, 1), 1)
-    scores = one_hots * target
+        one_hots = torch.zeros(*target.size(), device=target.device)
+        one_hots.scatter_(1, logits.view(-1, 1), 1)
+        scores = one_hots * target
     if get_label:
         return scores, logits
     return scores
@@ -151,9 +152,8 @@ class Wrapper(nn.Module):
                 kw['bbox'], kw['wh'] = batch['bbox'].to(self.device).float(), batch['wh']
         out = eng.forward(img, tokens, **kw)
         label = out['label']
-        one_hots = torch.zeros_like(target)
-        one_hots.scatter_(1, label.view(-1, 1), 1)
-        return one_hots * target, label, target
+        score, _, _ = ops.answer_scores(label, target.contiguous())
+        return score, label, target
 
     def forward_cap(self, batch):
         batch = self.encoder(batch)

@@ -344,6 +344,20 @@ def graph_attention_merged(Y, x, att, labels, wvec, c0, label_bias_lp, num_label
     return out, vsum, alpha
 
 
+def answer_scores(label, target, want_dense=True, want_sum=False):
+    """one_hot(label) ⊙ target (wrapper.py:16-22) → (dense [B,A] or None, per-question score [B], sum [1] or None)."""
+    lib = L.load()
+    _require(label, torch.int64, "label")
+    _require(target, torch.float32, "target")
+    B, A = target.shape
+    dense = torch.empty((B, A), dtype=torch.float32, device=target.device) if want_dense else None
+    row = torch.empty((B,), dtype=torch.float32, device=target.device)
+    total = torch.empty((1,), dtype=torch.float32, device=target.device) if want_sum else None
+    L.check(lib.vqa_answer_scores(label.data_ptr(), target.data_ptr(), B, A, target.stride(0), _ptr(dense), row.data_ptr(),
+                                  _ptr(total), _stream()))
+    return dense, row, total
+
+
 def argmax_rows(logits):
     """Lowest-index argmax per row (wrapper.py:14)."""
     lib = L.load()
