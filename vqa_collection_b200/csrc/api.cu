@@ -140,8 +140,15 @@ static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
       a.E_pad % 64 == 0) {
     // CTA pairs (tcgen05 cta_group::2, gru_pair.cu: 138 vs 144 us at B=1024, T=14) when the device can hold the pairs,
     // else one CTA per tile; VQA_B200_GRU_PAIR=0 forces the single-CTA kernel
+    // Nsight Compute cannot launch a cooperative CLUSTER kernel ("LaunchFailed" under the profiler and the target process is
+    // torn down): when its injection environment is present the single-CTA kernel runs instead, so `ncu python bench.py` works
+    // (VQA_B200_GRU_PAIR=1 overrides).
     static int pair = -1;
-    if (pair < 0) { const char* e = getenv("VQA_B200_GRU_PAIR"); pair = (e && e[0] == '0') ? 0 : 1; }
+    if (pair < 0) {
+      const char* e = getenv("VQA_B200_GRU_PAIR");
+      if (e) pair = (e[0] == '0') ? 0 : 1;
+      else pair = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ? 0 : 1;
+    }
     if (pair) {
       rc = gru_pair(X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
                     a.d_h_last, a.d_h_last_lp, a.d_out_all, nullptr, s);

@@ -566,7 +566,7 @@ static int train_step_t(const vqa_train_args& a, const TrainWs& w, cudaStream_t 
   // time-major into Hs / Hlp, gates r, z, n and W_hn·h + b_hn saved per step; the input projection is fused, so the
   // [B*T,3H] gi GEMM and the 2T per-step launches disappear.  fp32 (and devices that cannot hold the pairs): per step.
   int gru_rc = VQA_ERR_UNSUPPORTED;
-  if (bf16 && H % 64 == 0 && !getenv("VQA_B200_TRAIN_GRU_STEPWISE")) {
+  if (bf16 && H % 64 == 0 && !getenv("VQA_B200_TRAIN_GRU_STEPWISE") && !getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR")) {   // (ncu: see api.cu)
     pack_gru_kernel<T><<<grid_for((size_t)3 * H * Ep), 256, 0, s>>>(a.p_w_ih, H, E, Ep, (T*)w.wx_packed);
     VQA_LAUNCH_CHECK();
     pack_gru_kernel<T><<<grid_for((size_t)3 * H * H), 256, 0, s>>>(a.p_w_hh, H, H, H, (T*)w.wh_packed);
