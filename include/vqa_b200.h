@@ -344,6 +344,8 @@ typedef struct {
   int pack_on_host;
   int raw_chunk_period;      /* with pack_on_host: every n-th chunk (n >= 2) goes as f32 + device cast, 0 = none */
   size_t h2d_bytes, d2h_bytes;
+  int img_is_bf16;           /* h_img holds bf16 [B,K,V] (a feature cache kept in the resident format):
+                                chunks go straight into HBM, no host pack and no device cast (dtype must be VQA_BF16) */
 } vqa_forward_host_args;
 
 int vqa_forward_host(vqa_host_ctx* ctx, vqa_forward_host_args* args, void* stream);

@@ -189,3 +189,19 @@ def test_engine_empty_single_and_ragged_batches(engine_mod, relation, B):
     assert relerr(out["logits"], ref) < 1e-5
     assert relerr(out["att"], enc["v_att"][:, :, 0]) < 1e-5
     assert torch.equal(out["label"].cpu(), ref.argmax(1))
+
+
+def test_engine_host_path_bf16_feature_cache(engine_mod):
+    """a host feature cache kept in the resident bf16 format goes straight to HBM: same answers as the device path"""
+    cfg = O.SMALL
+    W = O.make_weights(cfg, 1111)
+    batch = O.make_batch(cfg, 150, 41)
+    eng = engine_mod.VQAEngine(W, relation=False, precision="bf16")
+    img_lp = batch["img"].to(torch.bfloat16)
+    ref = eng.forward(img_lp.cuda(), batch["q"].cuda())
+    label_h, h2d, d2h = eng.forward_host(img_lp.pin_memory(), batch["q"].pin_memory(), chunk=64)
+    assert torch.equal(label_h, ref["label"].cpu())
+    assert torch.equal(eng.last_host_outputs["logits"], ref["logits"])
+    assert h2d == img_lp.numel() * 2 + batch["q"].numel() * 8 and d2h == 150 * 8
+    with pytest.raises(TypeError):
+        engine_mod.VQAEngine(W, relation=False, precision="fp32").forward_host(img_lp, batch["q"])

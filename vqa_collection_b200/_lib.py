@@ -95,6 +95,7 @@ class ForwardHostArgs(C.Structure):
         ("h_label", c_void_p),
         ("chunk_rows", c_int), ("pack_on_host", c_int), ("raw_chunk_period", c_int),
         ("h2d_bytes", c_size_t), ("d2h_bytes", c_size_t),
+        ("img_is_bf16", c_int),
     ]
 
 

@@ -139,7 +139,9 @@ int vqa_forward_host_submit(vqa_host_ctx* c, vqa_forward_host_args* ha, void* st
   const size_t es = elem_size(a.dtype);
   const size_t row_elems = (size_t)a.K * a.V;
   const int chunk = ha->chunk_rows > 0 ? ha->chunk_rows : 64;
-  const bool pack = a.dtype == VQA_BF16 && ha->pack_on_host;
+  const bool wire_bf16 = ha->img_is_bf16 != 0;
+  VQA_REQUIRE(!wire_bf16 || a.dtype == VQA_BF16, "vqa_forward_host: img_is_bf16 needs a bf16 engine");
+  const bool pack = a.dtype == VQA_BF16 && ha->pack_on_host && !wire_bf16;
   // hybrid staging: every `raw_chunk_period`-th chunk crosses PCIe as f32 and is cast on the device, the others
   // are packed by the host cores — balances host memory bandwidth (pack) against PCIe bandwidth (raw)
   const int period = pack ? ha->raw_chunk_period : 0;
@@ -169,7 +171,7 @@ int vqa_forward_host_submit(vqa_host_ctx* c, vqa_forward_host_args* ha, void* st
       c->slot_bytes = need;
     }
   }
-  if (a.dtype == VQA_BF16 && (!pack || period > 0)) {
+  if (a.dtype == VQA_BF16 && !wire_bf16 && (!pack || period > 0)) {
     const size_t need = (size_t)chunk * row_elems * 4;
     if (c->stage_bytes < need) {
       for (int i = 0; i < 2; ++i) {
@@ -191,7 +193,10 @@ int vqa_forward_host_submit(vqa_host_ctx* c, vqa_forward_host_args* ha, void* st
     const float* src = ha->h_img + (size_t)b0 * row_elems;
     char* dst = (char*)c->d_img + (size_t)b0 * row_elems * es;
     const bool raw = period > 0 && (i % period == period - 1);
-    if (pack && !raw) {
+    if (wire_bf16) {                                   // already in the resident format: one DMA per chunk
+      VQA_CUDA_CHECK(cudaMemcpyAsync(dst, (const char*)ha->h_img + (size_t)b0 * row_elems * 2, n * 2, cudaMemcpyHostToDevice, c->copy));
+      ha->h2d_bytes += n * 2;
+    } else if (pack && !raw) {
       const int slot = i % NS;
       if (c->slot_used[slot]) VQA_CUDA_CHECK(cudaEventSynchronize(c->slot_done[slot]));      // its previous DMA has drained
       vqa_packpool_run(c->pool, src, (uint16_t*)c->pinned[slot], n);

@@ -322,13 +322,17 @@ class VQAEngine:
         """Host buffers in the reference wire format → a handle whose ``result()`` gives the host answers
         (vqa_forward_host_submit / _wait).
 
-        img_h f32 [B,K,V] (pinned recommended), tokens_h int64 [B,T] (+ labels_h u8 [B,K,K] or bbox_h f32
+        img_h f32 [B,K,V] (pinned recommended; or bf16 [B,K,V] when the caller keeps its feature cache in the
+        resident format — then chunks go straight to HBM), tokens_h int64 [B,T] (+ labels_h u8 [B,K,K] or bbox_h f32
         [B,K,4] with wh).  bf16 engines: ``pack_on_host`` lets the host cores convert the features to bf16
         (bit-identical to the device cast) while the previous chunk is in flight, so PCIe carries 2 bytes per
         feature; otherwise f32 crosses PCIe and is cast on the device.  Up to two batches may be in flight
         (two staging contexts): submit batch n+1 before asking for batch n's result to overlap staging with
         compute."""
-        for name, t, dt in (("img_h", img_h, torch.float32), ("tokens_h", tokens_h, torch.int64)):
+        wire_bf16 = img_h.dtype == torch.bfloat16          # a host-side feature cache already in the resident format
+        if wire_bf16 and self.dtype != torch.bfloat16:
+            raise TypeError("forward_host: bf16 host features need a bf16 engine")
+        for name, t, dt in (("img_h", img_h, img_h.dtype if wire_bf16 else torch.float32), ("tokens_h", tokens_h, torch.int64)):
             if t.is_cuda or t.dtype != dt or not t.is_contiguous():
                 raise TypeError(f"forward_host: {name} must be a contiguous CPU {dt} tensor")
         B, K, V = img_h.shape
@@ -365,13 +369,14 @@ class VQAEngine:
         ha.fwd, ha.h_label = a, label_h.data_ptr()
         ha.chunk_rows, ha.pack_on_host = int(chunk), int(bool(pack_on_host) and self.dtype == torch.bfloat16)
         ha.raw_chunk_period = int(raw_chunk_period) if ha.pack_on_host else 0
+        ha.img_is_bf16 = int(wire_bf16)
         L.check(self.lib.vqa_forward_host_wait(ctx))             # a context carries one batch at a time
         with torch.cuda.device(self.device):
             L.check(self.lib.vqa_forward_host_submit(ctx, C.byref(ha), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         n_chunks = (B + chunk - 1) // chunk
         self.last_launches = self.lib.vqa_forward_last_launch_count() + (
             (n_chunks if not ha.pack_on_host else (n_chunks // ha.raw_chunk_period if ha.raw_chunk_period else 0))
-            if self.dtype == torch.bfloat16 else 0)
+            if (self.dtype == torch.bfloat16 and not wire_bf16) else 0)
         self.last_host_outputs = {"logits": logits, "att": att}
         eng = self
 
