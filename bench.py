@@ -297,25 +297,41 @@ def main():
     def wv(i):
         return ops.linear(imgs[i % NB].view(B * 36, 2048), P["Wv"], P["sv"], P["bv"], relu=True, mul=qq,
                           mul_row_div=36, logit_w=P["wlin"])
-    roof = None
-    if args.precision == "bf16":
+
+    def wide(i):
+        return ops.linear(imgs[i % NB].view(B * 36, 2048), P["Wg3"])
+
+    def time_kernel(fn, n):
         for i in range(3):
-            wv(i)
+            fn(i)
         torch.cuda.synchronize()
         e0.record()
-        for i in range(reps):
-            wv(i)
+        for i in range(n):
+            fn(i)
         e1.record()
         torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / reps
-        flops = 2.0 * B * 36 * P["H"] * P["V"]
+        return e0.elapsed_time(e1) / n
+
+    roof = None
+    if args.precision == "bf16":
+        # dominant kernel of the workload: Up-Down = the W_v projection fused with the attention logits; ReGAT = the wide
+        # projection x·[W0+W1; W2; WbᵀWa]ᵀ (55 % of the step).  traffic = dram__bytes_read.sum + dram__bytes_write.sum per
+        # launch from `ncu --set full` (profiles/r01e_ncu_wv.md: 159.48 + 6.71 MB, algorithmic 159.0 MB;
+        # profiles/r01e_ncu_wide.md: 181.17 + 412.90 MB, algorithmic 151 + 25 + 453 MB — part of Y is still in L2 at kernel end)
+        if relation and "Wg3" in P:
+            k_ms = time_kernel(wide, max(5, reps // 5))
+            flops = 2.0 * B * 36 * P["V"] * P["Wg3"].shape[0]
+            name, traffic, src = ("linear_tc_kernel<256,pair> (wide ReGAT projection [B*36,2048]x[6144,2048]^T, tcgen05 cta_group::2)",
+                                  594.07e6, "profiles/r01e_ncu_wide.md")
+        else:
+            k_ms = time_kernel(wv, reps)
+            flops = 2.0 * B * 36 * P["H"] * P["V"]
+            name, traffic, src = ("linear_tc_kernel<256,pair> (W_v projection + logit reduction, tcgen05 cta_group::2)",
+                                  166.2e6, "profiles/r01e_ncu_wv.md")
         achieved = flops / (k_ms / 1e3) / 1e12
-        roof = {"kernel": "linear_tc_kernel<256,pair> (W_v projection + logit reduction, tcgen05 cta_group::2)", "bound": "tensor",
-                "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch, `ncu --set full`
-                # (profiles/r01e_ncu_wv.md: 159.48 MB read + 6.71 MB written; algorithmic bytes = 159.0 MB at B=1024)
-                "traffic": (166.2e6 * B / 1024), "traffic_source": "profiles/r01e_ncu_wv.md", "peak_source": pk["src"] + " burst (kernel timed alone)", "launch_ms": k_ms,
-                "flops_per_launch": flops}
+        roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops"], "traffic": traffic * B / 1024, "traffic_source": src,
+                "peak_source": pk["src"] + " burst (kernel timed alone)", "launch_ms": k_ms, "flops_per_launch": flops}
     path_tflops = value / world * FLOPS_PER_Q[args.workload] / 1e12
 
     if rank != 0:

@@ -389,3 +389,16 @@ def test_flat_gradient_views():
     assert [tuple(v.shape) for v in fg.views] == shapes and fg.matches(shapes, "cpu") and not fg.matches(shapes[:2], "cpu")
     fg.views[2].fill_(3.0)
     assert fg.flat.sum() == 21.0 and all(v.data_ptr() % 256 == fg.flat.data_ptr() % 256 for v in fg.views)
+
+
+def test_host_path_tuning_scales_with_cores_per_rank(monkeypatch):
+    """the packing pool and the packed/raw split of the host path follow this rank's share of the host cores"""
+    from vqa_collection_b200 import engine
+    assert [engine.host_raw_chunk_period(c) for c in (32, 16, 8, 4, 2, 1)] == [0, 4, 3, 2, 1, 1]
+    n = engine.host_cores_per_rank()
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert engine.host_cores_per_rank() == max(1, n // 8)
+    monkeypatch.setenv("VQA_B200_PACK_THREADS", "3")
+    assert engine.host_pack_threads() == 3
+    monkeypatch.delenv("VQA_B200_PACK_THREADS")
+    assert engine.host_pack_threads() == max(1, n // 8)
