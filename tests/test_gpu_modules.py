@@ -121,3 +121,35 @@ def test_util_relation_drop_in():
     assert g.dtype == np.float64 and g.shape == (36, 36)
     assert np.array_equal(g, O.relation_graph(boxes, 640, 480))
     assert spatial_relation(np.float32([290, 190, 310, 210]), np.float32([340, 190, 360, 210]), 640, 480) == (3, 7)
+
+
+@pytest.mark.parametrize("cls_layer", [1, 3])
+def test_other_classifier_depths_take_the_module_path(cls_layer):
+    """the fused engine is built for the 2-layer classifier (main.py default); other depths must not reach it"""
+    import vqa_collection_b200 as pkg
+    from vqa_collection_b200.modules.wrapper import set_model
+    pkg.set_precision("fp32")
+    try:
+        cfg = O.SMALL
+        torch.manual_seed(3)
+        m = set_model(encoder_type="base", predictor_type="base", decoder_type="none", ntoken=cfg.ntoken, v_dim=cfg.v_dim,
+                      embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim, decoder_hidden_dim=0, rnn_layer=1,
+                      ans_dim=cfg.ans_dim, cls_layer=cls_layer, c_len=cfg.c_len, device="cuda", dropout=0.2, rnn_type="GRU",
+                      att_type="new").eval()
+        assert m.engine() is None
+        batch = O.make_batch(cfg, 5, 12)
+        with torch.no_grad():
+            score, label, target = m.forward_vqa({k: v for k, v in batch.items() if torch.is_tensor(v)})
+            predict, _ = m({k: v for k, v in batch.items() if torch.is_tensor(v)})
+        # the same stack in plain torch on the module's own parameters
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        enc = O.base_encoder(batch, sd)
+        x = O.fcnet1(enc["v"].sum(1), sd, "predictor.v_net") * enc["q"]
+        lin = [i for i, mod in enumerate(m.predictor.classifier.main) if isinstance(mod, torch.nn.Linear)]
+        for i in lin:
+            p = f"predictor.classifier.main.{i}"
+            x = torch.relu(torch.nn.functional.linear(x, O.wn_weight(sd[p + ".weight_v"], sd[p + ".weight_g"]), sd[p + ".bias"]))
+        assert relerr(predict, x) < 1e-5
+        assert torch.equal(label.cpu(), x.argmax(1))
+    finally:
+        pkg.set_precision("bf16")

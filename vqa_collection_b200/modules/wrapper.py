@@ -87,6 +87,8 @@ class Wrapper(nn.Module):
             relation = isinstance(self.encoder, RelationEncoder)
             if relation and len(self.encoder.spatial_encoder.gcn) != 1:
                 return None                                  # multi-layer GCN: module-level path
+            if len(self.predictor.classifier.linears()) != 2:
+                return None                                  # cls_layer != 2: module-level path (FCNet handles any depth)
             self._engine = VQAEngine(self.reference_named_weights(), relation=relation,
                                      precision=get_precision(), device=self.device)
             self._engine_key = key
