@@ -18,10 +18,12 @@
 //   phase 3  outᵀ[128 ch, 36] = [P;S;bias]ᵀ·Cᵀ per 128-channel tile             tcgen05.mma, A is
 //            M-major (channels contiguous): the TMA box {64 ch, rows} of Y IS the operand tile
 // One persistent CTA per SM loops over images; warp 0 = TMA producer (one 24 KB slot ring for both
-// phases), warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..11 = phase 0/2 math and the
-// phase-3 epilogue (thread = channel).  The image loop is software pipelined: phase 1 of image n+1
-// (loads + MMAs into the second D1/D2 buffer) runs while the epilogue warps do phase 2 of image n,
-// so the K×K stage never stalls the load stream.
+// phases), warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 = phase 0/2 math (the K×K stage),
+// warps 8..11 = phase-3 epilogue (thread = channel).  The image loop is software pipelined two deep:
+// phase 1 of image n+1 (loads + MMAs into the second D1/D2 buffer) and phase 2 of image n+1 (into the
+// second coefficient tile) run while the tensor core and the phase-3 warps work on image n, so neither
+// the K×K stage nor the epilogue stalls the load stream (with one warp set doing phase 2 and phase 3 in
+// turn the kernel ran at 0.68 of HBM with nothing saturated).
 // Per image HBM traffic = Q, x, P, S (4 × 147 KB) + out: the kernel is HBM-bound by design.
 #include <stdlib.h>
 
@@ -41,11 +43,19 @@ constexpr int CH = 128;                      // channels per phase-3 tile (MMA M
 constexpr int MAXL = 16;
 constexpr int ATOM_BYTES = KROWS * 128;      // one 64-channel atom of the phase-3 A tile (12 KB)
 constexpr int SLOT_BYTES = 2 * ATOM_BYTES;   // 24 KB
-constexpr int G_Q_OFF = 0, G_X_OFF = NPAD * 128, G_W_OFF = 2 * NPAD * 128;
-constexpr int G_BYTES = 2 * NPAD * 128 + 16 * 128;        // Q 6 KB + x 6 KB + wvec 2 KB
+// phase-1 operands of one 64-channel k-block: Q 40 rows (5 KB) + x 40 rows (5 KB) + wvec 16 rows (2 KB) = 12 KB, TWO k-blocks
+// per 24 KB ring slot.  (With one k-block per slot the ring carried 17 KB per slot on average and the kernel was bound by
+// bytes in flight / HBM latency: 7 slots x 17 KB / 2.8 us = 43 GB/s per SM, 0.68 of HBM.)  The MMAs read 48 x-rows (N = 48):
+// rows 40..47 are the first rows of the wvec tile — finite garbage that only reaches the unused columns 40..47 of D1.
+constexpr int GROWS = 40;
+constexpr int G_Q_OFF = 0, G_X_OFF = GROWS * 128, G_W_OFF = 2 * GROWS * 128;
+constexpr int G_BYTES = 2 * GROWS * 128 + 16 * 128;       // 12 KB per k-block
+static_assert(2 * G_BYTES == 2 * 12 * 1024, "two phase-1 k-blocks fill one ring slot");
 constexpr int STAGES = 7;
 constexpr int BT_CHUNK = NPAD * 128;         // one 64-k chunk of the coefficient tile (6 KB)
 constexpr int BT_BYTES = 2 * BT_CHUNK;
+constexpr int BT_BUFS = 2;                   // coefficient tile double buffered over images
+constexpr int P2_THREADS = 128;              // warps 4..7: phase 0/2;  warps 8..11: phase-3 epilogue
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;      // 384
 constexpr int TMEM_COLS = 512;
@@ -60,7 +70,7 @@ struct P2 {
   unsigned long long adj[GK], adjT[GK];      // row masks (bit k: label_ik≠0), column masks (bit j: label_jk≠0)
 };
 
-constexpr int BAR_OFF = STAGES * SLOT_BYTES + BT_BYTES;
+constexpr int BAR_OFF = STAGES * SLOT_BYTES + BT_BUFS * BT_BYTES;
 constexpr int P2_OFF = BAR_OFF + 256;
 constexpr int SMEM_BYTES = 1024 + P2_OFF + (int)sizeof(P2);
 
@@ -71,7 +81,7 @@ struct Params {
   __nv_bfloat16* out; __nv_bfloat16* vsum; float* alpha;
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(P2_THREADS) : "memory"); }
 
 __global__ void __launch_bounds__(THREADS, 1)
 graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmX,
@@ -87,12 +97,13 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto gfull_bar = [&](int b) { return bars + 8u * (2 * STAGES + b); };
-  const uint32_t c_full = bars + 8u * (2 * STAGES + 2);
-  auto ofull_bar = [&](int b) { return bars + 8u * (2 * STAGES + 3 + b); };
-  auto oempty_bar = [&](int b) { return bars + 8u * (2 * STAGES + 3 + OUT_BUFS + b); };
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 3 + 2 * OUT_BUFS);
+  auto cfull_bar = [&](int b) { return bars + 8u * (2 * STAGES + 2 + b); };          // coefficient tile b written
+  auto cempty_bar = [&](int b) { return bars + 8u * (2 * STAGES + 4 + b); };         // ... and consumed by phase 3
+  auto ofull_bar = [&](int b) { return bars + 8u * (2 * STAGES + 6 + b); };
+  auto oempty_bar = [&](int b) { return bars + 8u * (2 * STAGES + 6 + OUT_BUFS + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 6 + 2 * OUT_BUFS);
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + BAR_OFF + 8 * (2 * STAGES + 3 + 2 * OUT_BUFS));
+      reinterpret_cast<volatile uint32_t*>(base_ptr + BAR_OFF + 8 * (2 * STAGES + 6 + 2 * OUT_BUFS));
   P2& sm = *reinterpret_cast<P2*>(base_ptr + P2_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -106,14 +117,15 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(gfull_bar(0), 1); mbar_init(gfull_bar(1), 1); mbar_init(c_full, 1);
+    mbar_init(gfull_bar(0), 1); mbar_init(gfull_bar(1), 1);
+    for (int b = 0; b < BT_BUFS; ++b) { mbar_init(cfull_bar(b), 1); mbar_init(cempty_bar(b), 1); }
     for (int b = 0; b < OUT_BUFS; ++b) { mbar_init(ofull_bar(b), 1); mbar_init(oempty_bar(b), 128); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TMEM_COLS);
   if (warp >= EPI_WARP0) {
     // coefficient tile: rows 36..47 and the k padding stay zero for the whole kernel
-    for (int i = threadIdx.x - EPI_WARP0 * 32; i < BT_BYTES / 16; i += EPI_THREADS)
+    for (int i = threadIdx.x - EPI_WARP0 * 32; i < BT_BUFS * BT_BYTES / 16; i += EPI_THREADS)
       reinterpret_cast<uint4*>(bt_ptr)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
   }
@@ -130,13 +142,17 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       int stage = 0; uint32_t phase = 0;
       auto load_g = [&](int img) {                   // phase-1 operands of one image
         const int row0 = (p.rev ? p.B - 1 - img : img) * GK;
-        for (int kb = 0; kb < kb_g; ++kb) {
+        for (int kb = 0; kb < kb_g; kb += 2) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t slot = base + stage * SLOT_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), G_BYTES);
-          tma_load_2d(slot + G_Q_OFF, &tmQ, full_bar(stage), 2 * V + kb * BK, row0);
-          tma_load_2d(slot + G_X_OFF, &tmX, full_bar(stage), kb * BK, row0);
-          tma_load_2d(slot + G_W_OFF, &tmW, full_bar(stage), kb * BK, 0);
+          mbar_arrive_expect_tx(full_bar(stage), 2 * G_BYTES);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t sk = slot + h * G_BYTES;
+            tma_load_2d(sk + G_Q_OFF, &tmQ, full_bar(stage), 2 * V + (kb + h) * BK, row0);
+            tma_load_2d(sk + G_X_OFF, &tmX, full_bar(stage), (kb + h) * BK, row0);
+            tma_load_2d(sk + G_W_OFF, &tmW, full_bar(stage), (kb + h) * BK, 0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       };
@@ -170,16 +186,20 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       auto mma_g = [&](uint32_t gbuf) {
         // phase 1 into D1/D2 buffer gbuf (free: its previous image's phase 2a finished before that image's c_full)
         const uint32_t dg = tmem_base + gbuf * G_STRIDE;
-        for (int kb = 0; kb < kb_g; ++kb) {
+        for (int kb = 0; kb < kb_g; kb += 2) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t slot = base + stage * SLOT_BYTES;
-          const uint64_t qd = make_sw128_kmajor_desc(slot + G_Q_OFF), xd = make_sw128_kmajor_desc(slot + G_X_OFF),
-                         wd = make_sw128_kmajor_desc(slot + G_W_OFF);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(dg + COL_G, qd + 2 * k, xd + 2 * k, idesc_g, (kb | k) != 0);
-            umma_bf16(dg + COL_U, xd + 2 * k, wd + 2 * k, idesc_u, (kb | k) != 0);
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t sk = slot + h * G_BYTES;
+            const uint64_t qd = make_sw128_kmajor_desc(sk + G_Q_OFF), xd = make_sw128_kmajor_desc(sk + G_X_OFF),
+                           wd = make_sw128_kmajor_desc(sk + G_W_OFF);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_bf16(dg + COL_G, qd + 2 * k, xd + 2 * k, idesc_g, (kb | h | k) != 0);
+              umma_bf16(dg + COL_U, xd + 2 * k, wd + 2 * k, idesc_u, (kb | h | k) != 0);
+            }
           }
           umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -191,8 +211,10 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++it) {
         if (img + (int)gridDim.x < p.B) mma_g((it + 1) & 1u);
         // phase 3 needs the coefficient tile of this image
-        mbar_wait(c_full, it & 1u);
+        const uint32_t cb = it & 1u;
+        mbar_wait(cfull_bar(cb), (it >> 1) & 1u);
         tcgen05_fence_after();
+        const uint32_t btb = bt + cb * BT_BYTES;
         for (int cc = 0; cc < n_cc; ++cc) {
           const uint32_t tile = it * (uint32_t)n_cc + (uint32_t)cc;      // running tile index of this CTA
           const int buf = tile & (OUT_BUFS - 1);
@@ -206,19 +228,20 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 #pragma unroll
           for (int ks = 0; ks < KROWS / UMMA_K; ++ks) {
             const uint64_t ad = make_sw128_mnmajor_desc(slot + ks * 2048, ATOM_BYTES, 1024);
-            const uint64_t bd = make_sw128_kmajor_desc(bt + (ks >> 2) * BT_CHUNK) + (uint64_t)(2 * (ks & 3));
+            const uint64_t bd = make_sw128_kmajor_desc(btb + (ks >> 2) * BT_CHUNK) + (uint64_t)(2 * (ks & 3));
             umma_bf16(d, ad, bd, idesc_o, ks != 0);
           }
           umma_commit(empty_bar(stage));
           umma_commit(ofull_bar(buf));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        umma_commit(cempty_bar(cb));                   // the phase-2 warps may rewrite this coefficient tile
       }
     }
   } else if (warp >= EPI_WARP0) {
     const int q = warp & 3;                          // TMEM lane quarter of this warp
-    const int hf = (warp - EPI_WARP0) >> 2;          // which half of the phase-3 tiles
-    const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..255
+    const int hf = (warp - EPI_WARP0) >> 2;          // 0: phase 0/2 warps (4..7), 1: phase-3 epilogue warps (8..11)
+    const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127 within the phase-2 group
     // ---- phase 0: attention scalars, row adjacency masks, label histogram of one image
     auto phase0 = [&](int img_it) {
       const int img = p.rev ? p.B - 1 - img_it : img_it;
@@ -245,13 +268,15 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
     };
     uint32_t it = 0;
+    if (hf == 0) {
+    // ================= phase 0/2 warps =================
     if ((int)blockIdx.x < p.B) phase0(blockIdx.x);
     for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++it) {
       // ---- phase 2a: D1/D2 rows 0..35 → shared memory
       const uint32_t gbuf = it & 1u;
       mbar_wait(gfull_bar(gbuf), (it >> 1) & 1u);
       tcgen05_fence_after();
-      if (hf == 0 && q < 2) {
+      if (q < 2) {
         uint32_t v[32], w16[16], u16[16];
         const uint32_t t_row = tmem_base + gbuf * G_STRIDE + ((uint32_t)(q * 32) << 16);
         tmem_ld_32x32(t_row + COL_G, v);
@@ -271,14 +296,14 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       tcgen05_fence_before();
       epi_bar();
       // ---- 2b: α0 = ReLU(dot); column masks adjT from the row masks
-      for (int e = et; e < GK * GK; e += EPI_THREADS) {
+      for (int e = et; e < GK * GK; e += P2_THREADS) {
         const int i = e / GK, j = e - i * GK;
         const float ai = sm.a[i], aj = sm.a[j];
         const float dot = ai * aj * sm.G[i][j] + ai * sm.ua[i] + aj * sm.ub[j] + p.c0;
         sm.A0[i][j] = fmaxf(dot, 0.f);
       }
-      if (et >= EPI_THREADS - GK) {
-        const int k = et - (EPI_THREADS - GK);
+      if (et >= P2_THREADS - GK) {
+        const int k = et - (P2_THREADS - GK);
         unsigned long long m = 0ull;
 #pragma unroll
         for (int j = 0; j < GK; ++j) m |= ((sm.adj[j] >> k) & 1ull) << j;
@@ -286,7 +311,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
       epi_bar();
       // ---- 2c: α1 = adj·α0
-      for (int e = et; e < GK * GK; e += EPI_THREADS) {
+      for (int e = et; e < GK * GK; e += P2_THREADS) {
         const int i = e / GK, j = e - i * GK;
         const unsigned long long m = sm.adj[i];
         float s = 0.f;
@@ -297,35 +322,36 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       epi_bar();
       // ---- 2d: softmax over the row index i for every column j (4 threads per column, 9 rows each)
       {
-        const bool valid = et < 4 * GK;                  // whole warps run the shuffles; the tail lanes idle along
-        const int j = valid ? (et >> 2) : 0, part = et & 3;
-        float x[GK / 4];
+        const bool valid = et < 2 * GK;                  // whole warps run the shuffles; the tail lanes idle along
+        const int j = valid ? (et >> 1) : 0, part = et & 1;
+        float x[GK / 2];
         float mx = -INFINITY;
 #pragma unroll
-        for (int r = 0; r < GK / 4; ++r) { x[r] = valid ? sm.Al[part * (GK / 4) + r][j] : 0.f; mx = fmaxf(mx, x[r]); }
+        for (int r = 0; r < GK / 2; ++r) { x[r] = valid ? sm.Al[part * (GK / 2) + r][j] : 0.f; mx = fmaxf(mx, x[r]); }
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
         float sum = 0.f;
 #pragma unroll
-        for (int r = 0; r < GK / 4; ++r) { x[r] = expf(x[r] - mx); sum += x[r]; }
+        for (int r = 0; r < GK / 2; ++r) { x[r] = expf(x[r] - mx); sum += x[r]; }
         sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
         const float inv = 1.f / sum;
         __syncwarp();                                    // all reads of column j done before it is overwritten
         if (valid) {
 #pragma unroll
-          for (int r = 0; r < GK / 4; ++r) sm.Al[part * (GK / 4) + r][j] = x[r] * inv;
+          for (int r = 0; r < GK / 2; ++r) sm.Al[part * (GK / 2) + r][j] = x[r] * inv;
         }
       }
       epi_bar();
       // ---- 2e: coefficient matrix C [36, 96] → bf16, K-major 128B-swizzled B operand
       //      k 0..35: (α·adj)_ik a_k   |  k 40..75: α_ij a_j  |  k 80..91: (α·hist)_il
+      const uint32_t cb = it & 1u;
+      if (it >= 2) mbar_wait(cempty_bar(cb), ((it >> 1) - 1u) & 1u);     // phase 3 of image it-2 has read this tile
+      uint8_t* btw = bt_ptr + cb * BT_BYTES;
       auto put2 = [&](int i, int k0, float c0v, float c1v) {
         const int chunk = k0 >> 6, kc = k0 & 63;
         const uint32_t off = chunk * BT_CHUNK + i * 128 + ((((kc * 2) >> 4) ^ (i & 7)) << 4) + ((kc * 2) & 15);
-        *reinterpret_cast<uint32_t*>(bt_ptr + off) = pack_bf16x2(c0v, c1v);
+        *reinterpret_cast<uint32_t*>(btw + off) = pack_bf16x2(c0v, c1v);
       };
-      for (int e = et; e < GK * (GK / 2); e += EPI_THREADS) {          // P block
+      for (int e = et; e < GK * (GK / 2); e += P2_THREADS) {          // P block
         const int i = e / (GK / 2), kp = e - i * (GK / 2);
         const unsigned long long m0 = sm.adjT[2 * kp], m1 = sm.adjT[2 * kp + 1];
         float c0v = 0.f, c1v = 0.f;
@@ -337,11 +363,11 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         }
         put2(i, 2 * kp, c0v * sm.a[2 * kp], c1v * sm.a[2 * kp + 1]);
       }
-      for (int e = et; e < GK * (GK / 2); e += EPI_THREADS) {          // S block
+      for (int e = et; e < GK * (GK / 2); e += P2_THREADS) {          // S block
         const int i = e / (GK / 2), kp = e - i * (GK / 2);
         put2(i, S_OFF + 2 * kp, sm.Al[i][2 * kp] * sm.a[2 * kp], sm.Al[i][2 * kp + 1] * sm.a[2 * kp + 1]);
       }
-      for (int e = et; e < GK * (MAXL / 2); e += EPI_THREADS) {        // label-bias block
+      for (int e = et; e < GK * (MAXL / 2); e += P2_THREADS) {        // label-bias block
         const int i = e / (MAXL / 2), lp = e - i * (MAXL / 2);
         float c0v = 0.f, c1v = 0.f;
 #pragma unroll
@@ -353,16 +379,18 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         put2(i, LB_OFF + 2 * lp, c0v, c1v);
       }
       if (p.alpha != nullptr)
-        for (int e = et; e < GK * GK; e += EPI_THREADS)
+        for (int e = et; e < GK * GK; e += P2_THREADS)
           p.alpha[(size_t)(p.rev ? p.B - 1 - img : img) * GK * GK + e] = sm.Al[e / GK][e % GK];
       fence_proxy_async();
       epi_bar();
-      if (et == 0) mbar_arrive(c_full);
+      if (et == 0) mbar_arrive(cfull_bar(cb));
       if (img + (int)gridDim.x < p.B) phase0(img + gridDim.x);       // consumed after the next 2a barrier
-      // ---- phase 3 epilogue: thread = channel; ReLU, Σ_i, store
+    }
+    } else {
+    // ================= phase-3 epilogue warps: thread = channel; ReLU, Σ_i, store =================
+    for (int img = blockIdx.x; img < p.B; img += gridDim.x, ++it) {
       for (int cc = 0; cc < n_cc; ++cc) {
         const uint32_t tile = it * (uint32_t)n_cc + (uint32_t)cc;
-        if ((int)(tile & 1u) != hf) continue;          // buffer parity selects the warp set
         const int buf = tile & (OUT_BUFS - 1);
         const uint32_t use = tile / OUT_BUFS;
         mbar_wait(ofull_bar(buf), use & 1u);
@@ -393,6 +421,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         if (p.vsum) p.vsum[(size_t)oimg * V + c] = __float2bfloat16_rn(vs);
       }
     }
+    }
   }
 
   tcgen05_fence_before();
@@ -416,8 +445,8 @@ int graph_attention_tc(const vqa_graph_attention_args& a, cudaStream_t s) {
   CUtensorMap tmQ, tmX, tmW, tmPS, tmLB;
   int rc;
   const long long rows = (long long)a.B * GK;
-  if ((rc = tc::make_tensor_map_bf16(&tmQ, a.d_Y, rows, a.ldy, a.ldy, NPAD))) return rc;
-  if ((rc = tc::make_tensor_map_bf16(&tmX, a.d_x, rows, a.V, a.ldx, NPAD))) return rc;
+  if ((rc = tc::make_tensor_map_bf16(&tmQ, a.d_Y, rows, a.ldy, a.ldy, GROWS))) return rc;
+  if ((rc = tc::make_tensor_map_bf16(&tmX, a.d_x, rows, a.V, a.ldx, GROWS))) return rc;
   if ((rc = tc::make_tensor_map_bf16(&tmW, a.d_wvec, 16, a.V, a.V, 16))) return rc;
   if ((rc = tc::make_tensor_map_bf16(&tmPS, a.d_Y, rows, a.ldy, a.ldy, P_ROWS))) return rc;
   if ((rc = tc::make_tensor_map_bf16(&tmLB, a.d_label_bias_lp, LB_ROWS, a.V, a.V, LB_ROWS))) return rc;
