@@ -205,14 +205,12 @@ int vqa_forward_host_submit(vqa_host_ctx* c, vqa_forward_host_args* ha, void* st
       c->slot_used[slot] = true;
       ha->h2d_bytes += n * 2;
     } else if (a.dtype == VQA_BF16) {
+      // raw chunk: f32 over PCIe, cast on the device.  The cast runs on the COPY stream right behind its DMA (in-order, so
+      // the two staging buffers need no events) — on the main stream it would queue behind the forward of the batch that
+      // is still computing and stall this batch's DMA stream after two chunks.
       const int sl = (period > 0 ? i / period : i) & 1;
-      if (c->stage_used[sl]) VQA_CUDA_CHECK(cudaStreamWaitEvent(c->copy, c->stage_free[sl], 0));
       VQA_CUDA_CHECK(cudaMemcpyAsync(c->d_stage[sl], src, n * 4, cudaMemcpyHostToDevice, c->copy));
-      VQA_CUDA_CHECK(cudaEventRecord(c->ev_copies, c->copy));
-      VQA_CUDA_CHECK(cudaStreamWaitEvent(main_s, c->ev_copies, 0));
-      if ((rc = cast_f32_to_bf16((const float*)c->d_stage[sl], dst, n, main_s))) return rc;
-      VQA_CUDA_CHECK(cudaEventRecord(c->stage_free[sl], main_s));
-      c->stage_used[sl] = true;
+      if ((rc = cast_f32_to_bf16((const float*)c->d_stage[sl], dst, n, c->copy))) return rc;
       ha->h2d_bytes += n * 4;
     } else {
       VQA_CUDA_CHECK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyHostToDevice, c->copy));
