@@ -55,6 +55,8 @@ class Config:
     att_type: str = "new"           # 'new' = MultiplyAttention (CLI default main.py:67), 'base' = ConcatAttention
     predictor: str = "base"         # 'base' = BasePredictor, 'q-cap' = PredictorwithCaption (config 5)
     neg_slope: float = 0.01         # LeakyReLU slope of the q-cap predictor's own LReLUNets (predictor.py:159)
+    decoder: str = "none"           # 'base' = BaseDecoder caption head (generator.py:123-181; main.py:87 default)
+    decoder_hidden_dim: int = 512   # main.py:88
 
     def as_dict(self):
         return asdict(self)
@@ -71,6 +73,9 @@ SMALL_CONCAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_d
 FULL_CONCAT = Config(att_type="base")
 SMALL_QCAP = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, predictor="q-cap")
 FULL_QCAP = Config(predictor="q-cap")
+SMALL_DECODER = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, decoder="base",
+                       decoder_hidden_dim=64)
+FULL_DECODER = Config(decoder="base")
 
 
 def _uniform(gen, shape, bound):
@@ -159,6 +164,25 @@ def make_weights(cfg: Config, seed: int = 1111, sharpen_att: float = 100.0,
             for nm in ("wa", "wb"):
                 w[p + f"dot_product.{nm}.weight"] = _uniform(g, (V, V), bv) * sharpen_gcn
                 w[p + f"dot_product.{nm}.bias"] = _uniform(g, (V,), bv)
+
+    if cfg.decoder == "base":
+        # BaseDecoder (generator.py:155-166): nn.GRUCell(E+V -> Hd), its own attention over (v, h), nn.Linear(Hd, ntoken).
+        # Drawn last so that every earlier tensor is the same with and without the caption head.
+        Hd = cfg.decoder_hidden_dim
+        kd = 1.0 / math.sqrt(Hd)
+        w["generator.rnn.weight_ih"] = _uniform(g, (3 * Hd, E + V), kd)
+        w["generator.rnn.weight_hh"] = _uniform(g, (3 * Hd, Hd), kd)
+        w["generator.rnn.bias_ih"] = _uniform(g, (3 * Hd,), kd)
+        w["generator.rnn.bias_hh"] = _uniform(g, (3 * Hd,), kd)
+        if cfg.att_type == "new":
+            wn_linear("generator.attention.W_v.main.0", Hd, V)
+            wn_linear("generator.attention.W_q.main.0", Hd, Hd)
+            wn_linear("generator.attention.linear", 1, Hd, sharpen_att)
+        else:
+            wn_linear("generator.attention.sequence.0", Hd, V + Hd)
+            wn_linear("generator.attention.sequence.2", 1, Hd, 0.1 * sharpen_att)
+        w["generator.fcnet.weight"] = _uniform(g, (cfg.ntoken, Hd), 0.1 * sharpen_cls)     # generator.py:165 (±0.1)
+        w["generator.fcnet.bias"] = _uniform(g, (cfg.ntoken,), 0.1)
     return w
 
 
@@ -206,6 +230,19 @@ def make_batch(cfg: Config, B: int, seed: int, W: int = 640, H: int = 480) -> di
         batch["wh"] = (W, H)
         graph = np.stack([relation_graph(bbox[i], W, H) for i in range(B)])
         batch["graph"] = torch.from_numpy(graph)          # float64, like the loader
+    return batch
+
+
+def make_decoder_batch(cfg: Config, B: int, seed: int) -> dict:
+    """make_batch with ragged caption lengths in [2, c_len] (the decoder stops one step before each
+    caption's <end>, generator.py:93).  Distinct lengths while B < c_len, so that the descending sort
+    of generator.py:76 has no ties to order; beyond that ties occur (stable order, see base_decoder_forward)."""
+    batch = make_batch(cfg, B, seed)
+    g = torch.Generator(device="cpu").manual_seed(seed + 104729)
+    if B < cfg.c_len:
+        batch["cap_len"] = (torch.randperm(cfg.c_len - 1, generator=g)[:B] + 2).to(torch.int64)
+    else:
+        batch["cap_len"] = torch.randint(2, cfg.c_len + 1, (B,), generator=g)
     return batch
 
 
@@ -314,6 +351,9 @@ def base_encoder(batch, W):
     out = {"v": v, "q": qn, "v_att": v_att, "q_emb": q}
     if "c" in batch:
         out["c"] = W["encoder.embedding.weight"][batch["c"]]          # encoder.py:172 (embedded caption tokens)
+        out["c_target"] = batch["c"]                                  # encoder.py:155,178
+    if "cap_len" in batch:
+        out["cap_len"] = batch["cap_len"]
     return out
 
 
@@ -412,6 +452,46 @@ def qcap_predictor(enc, W, slope):
     v = lrelu_net(v, W, "predictor.vqc_net", slope)                   # :208
     joint = enc["q"] * (v + c)                                        # :209
     return torch.sigmoid(F.leaky_relu(F.linear(joint, W["predictor.classifier.0.main.0.weight"]), slope))   # :213
+
+
+def gru_cell(x, h, W, prefix):
+    """nn.GRUCell (generator.py:158-159): gate order [r; z; n], n = tanh(W_in x + b_in + r ⊙ (W_hn h + b_hn))."""
+    Hd = h.shape[1]
+    gi = F.linear(x, W[prefix + ".weight_ih"], W[prefix + ".bias_ih"])
+    gh = F.linear(h, W[prefix + ".weight_hh"], W[prefix + ".bias_hh"])
+    r = torch.sigmoid(gi[:, :Hd] + gh[:, :Hd])
+    z = torch.sigmoid(gi[:, Hd:2 * Hd] + gh[:, Hd:2 * Hd])
+    n = torch.tanh(gi[:, 2 * Hd:] + r * gh[:, 2 * Hd:])
+    return (1.0 - z) * n + z * h
+
+
+def base_decoder_step(v, prev, h, W, prefix="generator"):
+    """BaseDecoder.decode (generator.py:168-181), rnn_type='GRU', dropout = identity (eval):
+    att = attention(v, h); att_v = Σ_K att·v; h' = GRUCell([prev; att_v], h); word = Linear(h')."""
+    att = torch.softmax(attention_logits(v, h, W, prefix + ".attention"), dim=1)
+    att_v = (att * v).sum(1)
+    h = gru_cell(torch.cat([prev, att_v], dim=1), h, W, prefix + ".rnn")
+    return h, F.linear(h, W[prefix + ".fcnet.weight"], W[prefix + ".fcnet.bias"]), att
+
+
+def base_decoder_forward(enc, W, cfg: Config, prefix="generator"):
+    """DecoderModule.forward (generator.py:66-120), teacher forced: captions sorted by decreasing length
+    (generator.py:76-79; ties keep their batch order — torch's CPU sort is stable), step t runs on the
+    ``batch_t`` captions longer than t+1, and the per-step word logits / targets come back in
+    pack_padded_sequence order (time-major, generator.py:117-118) without building the padded
+    [B, max_len, ntoken] tensor.  ``enc``: encoder output with 'v', 'c' (embedded caption), 'c_target', 'cap_len'."""
+    cap_len, sort_id = torch.sort(enc["cap_len"], dim=0, descending=True, stable=True)
+    v, caption, target = enc["v"][sort_id], enc["c"][sort_id], enc["c_target"][sort_id]
+    decode_len = (cap_len - 1).tolist()
+    h = torch.zeros((v.shape[0], cfg.decoder_hidden_dim), dtype=v.dtype)
+    predict, tgt, atts = [], [], []
+    for t in range(max(decode_len)):
+        bt = sum(l > t for l in decode_len)
+        h, word, att = base_decoder_step(v[:bt], caption[:bt, t], h[:bt], W, prefix)
+        predict.append(word)
+        tgt.append(target[:bt, t + 1])                     # targets are the words after <start> (generator.py:115)
+        atts.append(att)
+    return {"predict": torch.cat(predict, 0), "target": torch.cat(tgt, 0), "att": atts}
 
 
 def compute_score(predict, target):

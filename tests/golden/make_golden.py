@@ -31,9 +31,9 @@ from util.relation import relation_graph, spatial_relation   # noqa: E402
 
 def build_reference(cfg: O.Config, W: dict):
     m = set_model(encoder_type="relation" if cfg.relation else "base",
-                  predictor_type=cfg.predictor, decoder_type="none", ntoken=cfg.ntoken,
+                  predictor_type=cfg.predictor, decoder_type=cfg.decoder, ntoken=cfg.ntoken,
                   v_dim=cfg.v_dim, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim,
-                  decoder_hidden_dim=0, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2,
+                  decoder_hidden_dim=cfg.decoder_hidden_dim, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2,
                   c_len=cfg.c_len, device="cpu", dropout=0.2, neg_slope=cfg.neg_slope, rnn_type="GRU",
                   att_type=cfg.att_type, conv_layer=cfg.conv_layer, conv_type="corr")
     sd = {k: v for k, v in W.items() if not k.startswith("gcn.")}
@@ -138,6 +138,34 @@ def run_train(name, cfg, B, wseed, bseed, full_grads):
     print(name, "loss", loss.item(), "params", len(out) // 2 - 1)
 
 
+def run_decoder(name, cfg, B, wseed, bseed, col_stride):
+    """Wrapper.forward with the default caption head (decoder_type='base', main.py:87): VQA logits + the
+    teacher-forced word logits of DecoderModule.forward in pack_padded_sequence order, and one decode() step
+    (the call tools/caption.py:93 makes).  Word logits: every ``col_stride``-th column + row argmax + row
+    logsumexp + the cross-entropy of wrapper.py:32-36 (keeps the fixture small at ntoken=20000)."""
+    W = O.make_weights(cfg, wseed)
+    batch = O.make_decoder_batch(cfg, B, bseed)
+    m = build_reference(cfg, W)
+    ref_batch = {k: v for k, v in batch.items() if k not in ("bbox", "wh")}
+    with torch.no_grad():
+        predict, cap = m(ref_batch)
+        cap2 = m.forward_cap(ref_batch)
+        assert torch.equal(cap["predict"], cap2["predict"])
+        loss_cap = torch.nn.functional.cross_entropy(cap["predict"], cap["target"])
+        enc = m.encoder(ref_batch)
+        h0 = [torch.rand((B, cfg.decoder_hidden_dim), generator=torch.Generator().manual_seed(bseed)) - 0.5]
+        h1, word, att = m.generator.decode(v=enc["v"], v_mean=enc["v"].mean(1), prev=enc["c"][:, 3], h=h0)
+    out = {"logits": predict.numpy(), "cap_predict_sub": cap["predict"].numpy()[:, ::col_stride].copy(),
+           "cap_argmax": cap["predict"].argmax(1).numpy(), "cap_lse": torch.logsumexp(cap["predict"], 1).numpy(),
+           "cap_target": cap["target"].numpy(), "cap_loss": np.array(loss_cap.item(), dtype=np.float64),
+           "cap_len": batch["cap_len"].numpy(),
+           "step_h": h1[0].numpy(), "step_word_sub": word.numpy()[:, ::col_stride].copy(),
+           "step_word_argmax": word.argmax(1).numpy(), "step_att": att.numpy()[:, :, 0]}
+    meta = dict(cfg=cfg.as_dict(), B=B, wseed=wseed, bseed=bseed, col_stride=col_stride)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array(repr(meta)), **out)
+    print(name, {k: v.shape for k, v in out.items()}, float(loss_cap))
+
+
 def run_relation():
     W_, H_ = 640, 480
     boxes = O.make_boxes(48, 36, 4242, W_, H_, grid=True)
@@ -170,6 +198,10 @@ def run_relation():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--decoder-only" in sys.argv:
+        run_decoder("decoder_small", O.SMALL_DECODER, 8, 1111, 7001, 1)
+        run_decoder("decoder_full", O.FULL_DECODER, 5, 1111, 7002, 16)
+        sys.exit(0)
     if "--qcap-only" in sys.argv:
         run_qcap("qcap_small", O.SMALL_QCAP, 8, 1111, 6001)
         run_qcap("qcap_full", O.FULL_QCAP, 4, 1111, 6002)
@@ -185,3 +217,5 @@ if __name__ == "__main__":
     run_train("train_full", O.FULL, 8, 1111, 5002, False)
     run_qcap("qcap_small", O.SMALL_QCAP, 8, 1111, 6001)
     run_qcap("qcap_full", O.FULL_QCAP, 4, 1111, 6002)
+    run_decoder("decoder_small", O.SMALL_DECODER, 8, 1111, 7001, 1)
+    run_decoder("decoder_full", O.FULL_DECODER, 5, 1111, 7002, 16)

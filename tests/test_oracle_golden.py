@@ -148,3 +148,32 @@ def test_relation_known_answers(golden_dir):
     rest = [(1, 2), (2, 1), (1, 2), (1, 2), (3, 3), (1, 2), (0, 0), (3, 7),
             (3, 3), (3, 7), (9, 5), (10, 6)]
     assert [tuple(x) for x in z["ka_labels"][16:].tolist()] == rest
+
+
+@pytest.mark.parametrize("name", ["decoder_small", "decoder_full"])
+def test_caption_decoder_matches_reference(golden_dir, name):
+    """SURVEY §8f f3 (second half): the teacher-forced BaseDecoder forward and one decode() step of the real
+    reference (decoder_type='base', the main.py default) — ragged caption lengths, packed output order."""
+    z, meta = _load(golden_dir, name)
+    cfg = O.Config(**meta["cfg"])
+    W = O.make_weights(cfg, meta["wseed"])
+    batch = O.make_decoder_batch(cfg, meta["B"], meta["bseed"])
+    assert np.array_equal(batch["cap_len"].numpy(), z["cap_len"])
+    cs = meta["col_stride"]
+    with torch.no_grad():
+        logits, enc = O.forward(batch, W, cfg)
+        cap = O.base_decoder_forward(enc, W, cfg)
+        h0 = torch.rand((meta["B"], cfg.decoder_hidden_dim), generator=torch.Generator().manual_seed(meta["bseed"])) - 0.5
+        h1, word, att = O.base_decoder_step(enc["v"], enc["c"][:, 3], h0, W)
+    assert _relerr(logits.numpy(), z["logits"]) < 1e-5                       # the VQA head is unchanged by the caption head
+    assert cap["predict"].shape[0] == int((z["cap_len"] - 1).sum())
+    assert np.array_equal(cap["target"].numpy(), z["cap_target"])
+    assert _relerr(cap["predict"].numpy()[:, ::cs], z["cap_predict_sub"]) < 1e-5
+    assert _relerr(torch.logsumexp(cap["predict"], 1).numpy(), z["cap_lse"]) < 1e-5
+    assert np.array_equal(cap["predict"].argmax(1).numpy(), z["cap_argmax"])
+    loss = torch.nn.functional.cross_entropy(cap["predict"], cap["target"])   # wrapper.py:32-36
+    assert abs(loss.item() - float(z["cap_loss"])) < 1e-5 * abs(float(z["cap_loss"]))
+    assert _relerr(h1.numpy(), z["step_h"]) < 1e-5
+    assert _relerr(word.numpy()[:, ::cs], z["step_word_sub"]) < 1e-5
+    assert np.array_equal(word.argmax(1).numpy(), z["step_word_argmax"])
+    assert _relerr(att.numpy()[:, :, 0], z["step_att"]) < 1e-5
