@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 3
+#define VQA_B200_ABI_VERSION 4
 
 typedef enum {
   VQA_OK = 0,
@@ -250,6 +250,27 @@ int vqa_caption_gate_scale(const void* d_out_w, const float* d_p, const float* d
                            int dtype, void* d_in2, float* d_a, void* stream);
 int vqa_seq_max(const void* d_e, int B, int T, int H, int dtype, void* d_out, void* stream);
 int vqa_softmax_mul(const float* d_z, const void* d_v, int B, int H, int dtype, void* d_out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * caption head (decoder_type 'base'): per-step pieces of BaseDecoder.decode
+ * (generator.py:168-181); the GEMMs are vqa_linear, the softmax + weighted sum is
+ * vqa_attention_pool.
+ *  vqa_attention_logits  replaces attention.py:70-76 / :33-40 evaluated at every decoding step: the region
+ *      half of the attention is projected ONCE per caption batch (it does not depend on the hidden state),
+ *      each step reduces it against the hidden-state half.
+ *      proj [B*K, ldp] (dtype), q f32 [B, ldq], w f32 [Hd] (the weight-normed 1-wide logit layer),
+ *      logits f32 [B*K] (bias not added: it is vqa_attention_pool's logit_bias; n_parts = 1)
+ *        mode 0 ('new'):  proj = ReLU(W_v v + b), q = ReLU(W_q h + b):  sum_h proj*q*w
+ *        mode 1 ('base'): proj = W1[:, :V] v,     q = W1[:, V:] h + b1: sum_h ReLU(proj + q)*w
+ *      Hd, ldp, ldq % 8 == 0, 16-byte aligned bases.
+ *  vqa_gru_cell          replaces nn.GRUCell's gate update (generator.py:158-159,178), gate order [r;z;n]:
+ *      gi = W_ih x + b_ih, gh = W_hh h + b_hh  f32 [B,3H] (from vqa_linear);  h' = (1-z)*n + z*h
+ *      h_prev, h_out f32 [B,H] (may alias); h_lp [B, ld_lp] (dtype): the copy the next GEMMs read.
+ * ---------------------------------------------------------------------- */
+int vqa_attention_logits(const void* d_proj, int ldp, const float* d_q, int ldq, const float* d_w, int B, int K,
+                         int Hd, int mode, int dtype, float* d_logits, void* stream);
+int vqa_gru_cell(const float* d_gi, const float* d_gh, const float* d_h_prev, int B, int H, int dtype,
+                 float* d_h_out, void* d_h_lp, int ld_lp, void* stream);
 
 /* ------------------------------------------------------------------------
  * whole path: Wrapper.forward / forward_vqa (wrapper.py:64-74,113-118) for

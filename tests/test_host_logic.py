@@ -115,8 +115,33 @@ def test_unsupported_configurations_raise():
     assert get_graph_conv("corr") is CorrelatedGraphConv
     with pytest.raises(KeyError):
         set_att("nope")
+    kw = dict(encoder_type="base", predictor_type="base", ntoken=10, v_dim=8, embed_dim=8, hidden_dim=8,
+              decoder_hidden_dim=8, rnn_layer=1, ans_dim=4, cls_layer=2, c_len=5, device="cpu", att_type="new")
+    with pytest.raises(NotImplementedError):                     # BUTDDecoder.decode returns None in the reference
+        set_model(decoder_type="butd", **kw)
     with pytest.raises(NotImplementedError):
-        set_model(decoder_type="base", device="cpu")
+        set_model(decoder_type="base", rnn_type="LSTM", **kw)
+
+
+def test_caption_head_parameter_names_and_checkpoint_loading():
+    """decoder_type='base' (main.py:87 default): the generator's state_dict keys are the reference's (the oracle's
+    weight dict, pinned by tests/golden/decoder_*.npz, loads strictly); use_mtl adds log_vars (wrapper.py:50)"""
+    from vqa_collection_b200.modules.wrapper import set_model
+    cfg = O.SMALL_DECODER
+    kw = dict(encoder_type="base", predictor_type="base", decoder_type="base", ntoken=cfg.ntoken, v_dim=cfg.v_dim,
+              embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim, decoder_hidden_dim=cfg.decoder_hidden_dim, rnn_layer=1,
+              ans_dim=cfg.ans_dim, cls_layer=2, c_len=cfg.c_len, device="cpu", dropout=0.2, rnn_type="GRU", att_type="new")
+    m = set_model(**kw)
+    W = O.make_weights(cfg, 1111)
+    assert sorted(m.state_dict().keys()) == sorted(W.keys())
+    m.load_state_dict(W, strict=True)
+    assert not m.use_mtl and not m.train_step_supported()
+    assert [h.shape for h in m.generator.init_hidden(3)] == [(3, cfg.decoder_hidden_dim)]
+    m2 = set_model(use_mtl=True, **kw)
+    assert "log_vars" in m2.state_dict() and m2.use_mtl
+    with pytest.raises(RuntimeError):                            # no CPU fallback behind the caption head either
+        m.eval().generator.decode(torch.zeros(2, 36, cfg.v_dim), None, torch.zeros(2, cfg.embed_dim),
+                                  m.generator.init_hidden(2))
 
 
 def test_qcap_parameter_names_and_checkpoint_loading():

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
 
 VQA_F32, VQA_BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -140,6 +140,9 @@ SYMBOLS = {
                                        c_void_p]),
     "vqa_seq_max": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vqa_softmax_mul": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vqa_attention_logits": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p]),
+    "vqa_gru_cell": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "vqa_argmax_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vqa_forward_workspace_bytes": (c_size_t, [C.POINTER(ForwardArgs)]),
     "vqa_forward": (c_int, [C.POINTER(ForwardArgs), c_void_p]),

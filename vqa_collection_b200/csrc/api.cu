@@ -55,6 +55,7 @@ int answer_scores(const int64_t*, const float*, int, int, int, float*, float*, f
 int caption_gate_scale(const void*, const float*, const float*, int, int, int, int, void*, float*, cudaStream_t);
 int seq_max(const void*, int, int, int, int, void*, cudaStream_t);
 int softmax_mul(const float*, const void*, int, int, int, void*, cudaStream_t);
+int attention_logits(const void*, int, const float*, int, const float*, int, int, int, int, int, float*, cudaStream_t);
 int attention_pool(const float*, int, float, const void*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int argmax_rows(const float*, int, int, int, int64_t*, cudaStream_t);
 int embedding_gather(const int64_t*, int, int, int, int, const void*, void*, cudaStream_t);
@@ -304,6 +305,20 @@ int vqa_seq_max(const void* d_e, int B, int T, int H, int dtype, void* d_out, vo
 int vqa_softmax_mul(const float* d_z, const void* d_v, int B, int H, int dtype, void* d_out, void* stream) {
   if (int rc = require_sm100()) return rc;
   return softmax_mul(d_z, d_v, B, H, dtype, d_out, (cudaStream_t)stream);
+}
+
+int vqa_attention_logits(const void* d_proj, int ldp, const float* d_q, int ldq, const float* d_w, int B, int K, int Hd,
+                         int mode, int dtype, float* d_logits, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return attention_logits(d_proj, ldp, d_q, ldq, d_w, B, K, Hd, mode, dtype, d_logits, (cudaStream_t)stream);
+}
+int vqa_gru_cell(const float* d_gi, const float* d_gh, const float* d_h_prev, int B, int H, int dtype, float* d_h_out,
+                 void* d_h_lp, int ld_lp, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  VQA_REQUIRE(B >= 0 && H >= 1 && ld_lp >= H, "gru_cell: bad dims B=%d H=%d ld_lp=%d", B, H, ld_lp);
+  if (B == 0) return VQA_OK;
+  VQA_REQUIRE(d_gi && d_gh && d_h_prev && d_h_out && d_h_lp, "gru_cell: NULL pointer");
+  return gru_gate(d_gi, d_gh, B, H, 1, 0, d_h_prev, d_h_out, d_h_lp, ld_lp, dtype, (cudaStream_t)stream);
 }
 
 // ---- whole path --------------------------------------------------------------

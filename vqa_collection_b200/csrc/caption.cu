@@ -9,9 +9,46 @@
 //   seq_max            : out[b,:] = max_t e[b,t,:]                               (modules.py:306)
 //   softmax_mul        : out[b,:] = softmax_H(z[b,:]) ⊙ v[b,:]                   (predictor.py:202-203;
 //                        Σ_K (joint ⊙ V_k) = joint ⊙ Σ_K V_k, so only the pooled v is needed)
+//
+// Caption decoder (BaseDecoder.decode, generator.py:168-181) per-step glue:
+//   attention_logits   : the decoder attends over the SAME regions at every step, so the region half of its
+//                        attention (ReLU(W_v v), or W1_v v for att_type='base') is projected once per caption batch
+//                        and each step only reduces it against that step's hidden-state half:
+//                          mode 0: logit[b,k] = Σ_h proj[b,k,h] · q[b,h] · w[h]            (attention.py:70-76)
+//                          mode 1: logit[b,k] = Σ_h ReLU(proj[b,k,h] + q[b,h]) · w[h]      (attention.py:33-40)
+//                        one warp per (b,k) row, 16-byte loads; HBM/L2-streaming over proj.
+//   (the GRUCell gate update is gru_gate of pool.cu with T = 1)
 #include "common.cuh"
 
 namespace vqa {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+attention_logits_kernel(const T* __restrict__ proj, int ldp, const float* __restrict__ q, int ldq,
+                        const float* __restrict__ w, int rows, int K, int Hd, int mode, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+    const T* pr = proj + (size_t)row * ldp;
+    const float* qr = q + (size_t)(row / K) * ldq;
+    float acc = 0.f;
+    for (int h0 = lane * 8; h0 < Hd; h0 += 256) {
+      float pv[8], qv[8], wv[8];
+      load8(pr + h0, pv);
+      load8(qr + h0, qv);
+      load8(w + h0, wv);
+      if (mode == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += pv[j] * qv[j] * wv[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += fmaxf(pv[j] + qv[j], 0.f) * wv[j];
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = acc;
+  }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -92,6 +129,23 @@ static int grid_for(size_t total) {
   size_t g = (total + 255) / 256;
   const size_t cap = (size_t)sm_count() * 8;
   return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+int attention_logits(const void* proj, int ldp, const float* q, int ldq, const float* w, int B, int K, int Hd, int mode,
+                     int dtype, float* out, cudaStream_t s) {
+  VQA_REQUIRE(B >= 0 && K >= 1 && Hd >= 8 && Hd % 8 == 0 && ldp % 8 == 0 && ldq % 8 == 0 && (mode == 0 || mode == 1),
+              "attention_logits: bad dims B=%d K=%d Hd=%d ldp=%d ldq=%d mode=%d", B, K, Hd, ldp, ldq, mode);
+  if (B == 0) return VQA_OK;
+  VQA_REQUIRE(proj && q && w && out, "attention_logits: NULL pointer");
+  const int rows = B * K;
+  const int grid = grid_for((size_t)rows * 32);
+  if (dtype == VQA_BF16)
+    attention_logits_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)proj, ldp, q, ldq, w, rows, K, Hd,
+                                                                mode, out);
+  else
+    attention_logits_kernel<float><<<grid, 256, 0, s>>>((const float*)proj, ldp, q, ldq, w, rows, K, Hd, mode, out);
+  VQA_LAUNCH_CHECK();
+  return VQA_OK;
 }
 
 int caption_gate_scale(const void* out_w, const float* p, const float* r, int B, int T, int H, int dtype,

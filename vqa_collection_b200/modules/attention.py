@@ -53,6 +53,21 @@ class MultiplyAttention(nn.Module):
         B, K = v.shape[0], v.shape[1]
         return (parts.sum(1) + self.linear.bias.detach().float()).view(B, K, 1)
 
+    # -- caption decoder: many queries against the SAME regions (generator.py:172 inside the time loop) --------
+    def project(self, v):
+        """region half of the logits, once per caption batch: ReLU(W_v v + b) → ([B*K,H] compute dtype, x)"""
+        _no_training(self)
+        dtype = compute_dtype()
+        B, K, V = v.shape
+        x = as_compute(v, dtype)
+        (W, s, b), = self.W_v.prepared(dtype)
+        return ops.linear(x.view(B * K, V), W, s, b, relu=True, out_dtype=dtype), x
+
+    def step_parts(self, proj, q, K):
+        """logit parts [b*K,1] of one step for the first b = q.shape[0] samples of ``proj``"""
+        qp = self.W_q(q, out_dtype=torch.float32)
+        return ops.attention_logits(proj, qp.contiguous(), self._logit_vector(), K, mode=0)
+
     def forward(self, v, q):
         """v [batch, num_objs, v_dim], q [batch, q_dim] → [batch, num_objs, 1] (f32)"""
         parts, x = self.logit_parts(v, q)
@@ -107,6 +122,23 @@ class ConcatAttention(nn.Module):
         parts, _ = self.logit_parts(v, q)
         B, K = v.shape[0], v.shape[1]
         return (parts.sum(1) + self.linear.bias.detach().float()).view(B, K, 1)
+
+    # -- caption decoder: many queries against the SAME regions (generator.py:172 inside the time loop) --------
+    def project(self, v):
+        """region half of the hidden layer, once per caption batch: W1[:, :V] v (pre-activation) → ([B*K,H], x)"""
+        _no_training(self)
+        dtype = compute_dtype()
+        B, K, V = v.shape
+        x = as_compute(v, dtype)
+        W1v, _, sv, _, _ = self._prepared(dtype)
+        return ops.linear(x.view(B * K, V), W1v, sv, None, relu=False, out_dtype=dtype), x
+
+    def step_parts(self, proj, q, K):
+        """logit parts [b*K,1] of one step for the first b = q.shape[0] samples of ``proj``"""
+        dtype = compute_dtype()
+        _, W1q, sv, b1, wlin = self._prepared(dtype)
+        qadd = ops.linear(as_compute(q, dtype), W1q, sv, b1, relu=False, out_dtype=torch.float32)
+        return ops.attention_logits(proj, qadd, wlin, K, mode=1)
 
     def forward(self, v, q):
         """v [batch, num_objs, v_dim], q [batch, q_dim] → [batch, num_objs, 1] (f32)"""

@@ -3,13 +3,15 @@ compute_score :8-22, losses :25-36) for the VQA forward path.
 
 ``Wrapper.forward`` / ``get_att`` compose the module-level kernels; ``forward_vqa`` (the
 call train.evaluate makes per batch, train.py:184) takes the fused single-C-call engine
-path.  The caption generator (generator.py) is out of scope: decoder_type must be 'none'.
+path.  The caption head (generator.py) is the teacher-forced BaseDecoder forward and its decode()
+step (decoder_type 'base', the main.py default, or 'none'); its training step is not built.
 """
 import torch
 import torch.nn as nn
 
 from .. import get_precision, ops
 from .encoder import set_encoder, RelationEncoder
+from .generator import set_decoder
 from .predictor import set_predictor, BasePredictor
 
 
@@ -168,9 +170,8 @@ def set_model(encoder_type: str = 'base', predictor_type: str = 'base', decoder_
               c_len: int = 0, device: str = '', dropout: float = 0.5, neg_slope: float = 0.5,
               rnn_type: str = 'GRU', att_type: str = 'base', conv_layer: int = 2, conv_type: str = 'corr',
               decoder_device: str = '', pretrained_embed_path: str = '', use_mtl: bool = False):
-    if decoder_type != 'none':
-        raise NotImplementedError("caption decoders (generator.py) are outside the accelerated VQA forward path; "
-                                  "pass decoder_type='none'")
+    if decoder_device == '':
+        decoder_device = device
     return Wrapper(
         encoder=set_encoder(encoder_type=encoder_type, ntoken=ntoken, v_dim=v_dim, embed_dim=embed_dim,
                             hidden_dim=hidden_dim, device=device, dropout=dropout, rnn_type=rnn_type,
@@ -179,4 +180,7 @@ def set_model(encoder_type: str = 'base', predictor_type: str = 'base', decoder_
         predictor=set_predictor(predictor_type=predictor_type, v_dim=v_dim, embed_dim=embed_dim,
                                 hidden_dim=hidden_dim, ans_dim=ans_dim, device=device, cls_layer=cls_layer,
                                 dropout=dropout, c_len=c_len, neg_slope=neg_slope),
-        generator=None, use_mtl=use_mtl)
+        generator=set_decoder(decoder_type=decoder_type, ntoken=ntoken, embed_dim=embed_dim,
+                              hidden_dim=decoder_hidden_dim, v_dim=v_dim, max_len=c_len, device=decoder_device,
+                              dropout=dropout, rnn_type=rnn_type, att_type=att_type),
+        use_mtl=use_mtl)

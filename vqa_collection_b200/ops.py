@@ -271,6 +271,44 @@ def softmax_mul(z, v):
     return out
 
 
+def attention_logits(proj, q, w, K, mode=0):
+    """Attention logits of one decoding step from the region projection made once per caption batch
+    (BaseDecoder.decode → attention.py:70-76 / :33-40, see vqa_attention_logits).
+
+    proj [B*K, Hd] (compute dtype; may hold MORE rows than B*K — only the first q.shape[0]*K are read),
+    q f32 [B,Hd], w f32 [Hd]; mode 0 = MultiplyAttention, 1 = ConcatAttention.  Returns f32 [B*K, 1]
+    (the ``parts`` operand of attention_pool; the logit layer's bias is added there)."""
+    lib = L.load()
+    _require(proj, None, "proj")
+    _require(q, torch.float32, "q")
+    _require(w, torch.float32, "w")
+    B, Hd = q.shape
+    if proj.dim() != 2 or proj.shape[1] != Hd or proj.shape[0] < B * K or w.numel() != Hd:
+        raise ValueError(f"attention_logits: shape mismatch proj{tuple(proj.shape)} q{tuple(q.shape)} w{tuple(w.shape)}")
+    out = torch.empty((B * K, 1), dtype=torch.float32, device=q.device)
+    L.check(lib.vqa_attention_logits(proj.data_ptr(), proj.stride(0), q.data_ptr(), q.stride(0), w.data_ptr(), B, K, Hd,
+                                     int(mode), dtype_code(proj.dtype), out.data_ptr(), _stream()))
+    return out
+
+
+def gru_cell(gi, gh, h, h_lp):
+    """nn.GRUCell gate update (generator.py:158-159,178): gi = W_ih x + b_ih, gh = W_hh h + b_hh (f32 [B,3H]);
+    ``h`` f32 [B,H] is updated IN PLACE, ``h_lp`` [B,H] (compute dtype, row-strided view allowed) receives the copy
+    the next GEMMs read."""
+    lib = L.load()
+    _require(gi, torch.float32, "gi")
+    _require(gh, torch.float32, "gh")
+    _require(h, torch.float32, "h")
+    _require(h_lp, None, "h_lp")
+    B, H = h.shape
+    if gi.shape != (B, 3 * H) or gh.shape != (B, 3 * H) or h_lp.shape != (B, H) or not (gi.is_contiguous() and
+                                                                                        gh.is_contiguous() and h.is_contiguous()):
+        raise ValueError("gru_cell: shape mismatch")
+    L.check(lib.vqa_gru_cell(gi.data_ptr(), gh.data_ptr(), h.data_ptr(), B, H, dtype_code(h_lp.dtype), h.data_ptr(),
+                             h_lp.data_ptr(), h_lp.stride(0), _stream()))
+    return h
+
+
 def attention_pool(parts, logit_bias, x, want_att=True, want_vsum=True, want_vatt=False):
     """softmax over K + weighted sums (attention.py:86, encoder.py:166, predictor.py:85).
 
