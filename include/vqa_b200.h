@@ -272,6 +272,32 @@ int vqa_attention_logits(const void* d_proj, int ldp, const float* d_q, int ldq,
 int vqa_gru_cell(const float* d_gi, const float* d_gh, const float* d_h_prev, int B, int H, int dtype,
                  float* d_h_out, void* d_h_lp, int ld_lp, void* stream);
 
+/*  vqa_caption_decode_steps  replaces the time loop of DecoderModule.forward (generator.py:99-111) around
+ *      BaseDecoder.decode (:168-181) in ONE call: T teacher-forced steps, step t on the first h_batches[t]
+ *      samples (captions sorted by decreasing length, so h_batches is non-increasing).  Per step:
+ *      q = act(W_q h) -> vqa_attention_logits -> vqa_attention_pool -> gi = W_att att_v + gi_prev[:, t]
+ *      -> gh = W_hh h + b_hh -> GRUCell gate update.  Hoisted by the caller (they do not depend on h):
+ *      proj (region half of the attention), gi_prev (previous-word half of the GRUCell input GEMM, all steps);
+ *      the word logits Linear(h_t) of all steps are one vqa_linear over h_all afterwards.
+ *        x [B,K,V], proj [B*K,Hd], w_q [Hd,Hd] (+ scale/bias f32 [Hd]), w_att [3Hd,V], w_hh [3Hd,Hd] (dtype);
+ *        gi_prev f32 [B, T*3Hd]; h f32 [B,Hd] in: initial state, out: final states; h0_lp [B,Hd] (dtype) = h;
+ *        h_all out [sum_t h_batches[t], Hd] (dtype): every new state, time-major = pack_padded_sequence order.
+ *      h_batches is a HOST array.  Hd % 8 == 0, V % 8 == 0. */
+typedef struct {
+  int B, K, V, Hd, T, dtype;
+  const int* h_batches;
+  const void* d_x; const void* d_proj;
+  int att_mode;                       /* 0 = MultiplyAttention, 1 = ConcatAttention (see vqa_attention_logits) */
+  const void* d_wq; const float* d_wq_scale; const float* d_wq_bias;
+  const float* d_logit_w; float logit_bias;
+  const float* d_gi_prev;
+  const void* d_w_att; const void* d_w_hh; const float* d_b_hh;
+  void* d_h_all; float* d_h; const void* d_h0_lp;
+  void* d_workspace; size_t workspace_bytes;
+} vqa_caption_decode_args;
+size_t vqa_caption_decode_workspace_bytes(int B, int K, int V, int Hd, int dtype);
+int vqa_caption_decode_steps(const vqa_caption_decode_args* args, void* stream);
+
 /* ------------------------------------------------------------------------
  * whole path: Wrapper.forward / forward_vqa (wrapper.py:64-74,113-118) for
  * encoder_type in {base, relation}, att_type in {'new', 'base'}, predictor 'base'.

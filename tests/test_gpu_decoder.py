@@ -93,6 +93,12 @@ def test_caption_head_ties_and_concat_attention_vs_oracle(att_type):
         assert relerr(predict, want_logits) < 1e-5
         assert torch.equal(cap["target"].cpu(), want["target"])
         assert relerr(cap["predict"], want["predict"]) < 1e-5
+        # the per-step ops composed from Python launch the same kernels in the same order as vqa_caption_decode_steps
+        m.generator.step_loop_in_python = True
+        with torch.no_grad():
+            cap_py = m.forward_cap(batch)
+        m.generator.step_loop_in_python = False
+        assert torch.equal(cap_py["predict"], cap["predict"]) and torch.equal(cap_py["target"], cap["target"])
         # one caption only (the tools/caption.py beam-search shape): batch of 1, a single step
         one = {k: (v[:1] if torch.is_tensor(v) else v) for k, v in batch.items()}
         one["cap_len"] = torch.tensor([2])

@@ -118,6 +118,21 @@ class TrainArgs(C.Structure):
     ]
 
 
+class CaptionDecodeArgs(C.Structure):
+    _fields_ = [
+        ("B", c_int), ("K", c_int), ("V", c_int), ("Hd", c_int), ("T", c_int), ("dtype", c_int),
+        ("h_batches", C.POINTER(c_int)),
+        ("d_x", c_void_p), ("d_proj", c_void_p),
+        ("att_mode", c_int),
+        ("d_wq", c_void_p), ("d_wq_scale", c_void_p), ("d_wq_bias", c_void_p),
+        ("d_logit_w", c_void_p), ("logit_bias", c_float),
+        ("d_gi_prev", c_void_p),
+        ("d_w_att", c_void_p), ("d_w_hh", c_void_p), ("d_b_hh", c_void_p),
+        ("d_h_all", c_void_p), ("d_h", c_void_p), ("d_h0_lp", c_void_p),
+        ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
+    ]
+
+
 # every symbol include/vqa_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "vqa_abi_version": (c_int, []),
@@ -143,6 +158,8 @@ SYMBOLS = {
     "vqa_attention_logits": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p]),
     "vqa_gru_cell": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "vqa_caption_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "vqa_caption_decode_steps": (c_int, [C.POINTER(CaptionDecodeArgs), c_void_p]),
     "vqa_argmax_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vqa_forward_workspace_bytes": (c_size_t, [C.POINTER(ForwardArgs)]),
     "vqa_forward": (c_int, [C.POINTER(ForwardArgs), c_void_p]),

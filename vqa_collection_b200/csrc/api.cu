@@ -321,6 +321,68 @@ int vqa_gru_cell(const float* d_gi, const float* d_gh, const float* d_h_prev, in
   return gru_gate(d_gi, d_gh, B, H, 1, 0, d_h_prev, d_h_out, d_h_lp, ld_lp, dtype, (cudaStream_t)stream);
 }
 
+// Teacher-forced time loop of the caption head in one call (generator.py:99-111 around BaseDecoder.decode :168-181):
+// per step W_q GEMM -> attention_logits -> attention_pool -> W_ih[:, E:] GEMM (+ the hoisted previous-word half) ->
+// W_hh GEMM -> gate update; step t runs on the first batch_t samples (captions sorted by decreasing length).
+struct DecWs { float* q; float* parts; void* att_v; float* gi; float* gh; size_t bytes; };
+static DecWs carve_dec(char* base, int B, int K, int V, int Hd, int dtype) {
+  DecWs w{}; size_t off = 0;
+  auto take = [&](size_t n) { char* p = base ? base + off : nullptr; off += align_up(n, 256); return p; };
+  w.q = (float*)take((size_t)B * Hd * 4);
+  w.parts = (float*)take((size_t)B * K * 4);
+  w.att_v = take((size_t)B * V * elem_size(dtype));
+  w.gi = (float*)take((size_t)B * 3 * Hd * 4);
+  w.gh = (float*)take((size_t)B * 3 * Hd * 4);
+  w.bytes = off;
+  return w;
+}
+size_t vqa_caption_decode_workspace_bytes(int B, int K, int V, int Hd, int dtype) {
+  return carve_dec(nullptr, B, K, V, Hd, dtype).bytes;
+}
+int vqa_caption_decode_steps(const vqa_caption_decode_args* args, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  VQA_REQUIRE(args, "vqa_caption_decode_steps: NULL args");
+  const vqa_caption_decode_args& a = *args;
+  cudaStream_t s = (cudaStream_t)stream;
+  VQA_REQUIRE(a.B >= 0 && a.T >= 0 && a.K >= 1 && a.V >= 8 && a.Hd >= 8 && a.Hd % 8 == 0,
+              "caption_decode: bad dims B=%d T=%d K=%d V=%d Hd=%d", a.B, a.T, a.K, a.V, a.Hd);
+  if (a.B == 0 || a.T == 0) return VQA_OK;
+  VQA_REQUIRE(a.h_batches && a.d_x && a.d_proj && a.d_wq && a.d_logit_w && a.d_gi_prev && a.d_w_att && a.d_w_hh &&
+              a.d_b_hh && a.d_h_all && a.d_h && a.d_h0_lp && a.d_workspace, "caption_decode: NULL pointer");
+  const DecWs w = carve_dec((char*)a.d_workspace, a.B, a.K, a.V, a.Hd, a.dtype);
+  VQA_REQUIRE(a.workspace_bytes >= w.bytes, "caption_decode: workspace %zu < %zu bytes", a.workspace_bytes, w.bytes);
+  const size_t es = elem_size(a.dtype);
+  const void* h_in = a.d_h0_lp;
+  size_t row = 0;
+  int prev_bt = a.B, rc;
+  for (int t = 0; t < a.T; ++t) {
+    const int bt = a.h_batches[t];
+    VQA_REQUIRE(bt >= 1 && bt <= prev_bt, "caption_decode: batch schedule must be non-increasing in [1,B] (step %d: %d)", t, bt);
+    prev_bt = bt;
+    vqa_linear_args q{};                       // hidden-state half of the attention
+    q.d_A = h_in; q.lda = a.Hd; q.d_W = a.d_wq; q.ldw = a.Hd; q.M = bt; q.N = a.Hd; q.K = a.Hd; q.dtype = a.dtype;
+    q.d_scale = a.d_wq_scale; q.d_bias = a.d_wq_bias; q.relu = a.att_mode == 0;
+    q.d_out = w.q; q.ldo = a.Hd; q.out_dtype = VQA_F32; q.mul_row_div = 1; q.add_row_div = 1;
+    if ((rc = linear_dispatch(q, s))) return rc;
+    if ((rc = attention_logits(a.d_proj, a.Hd, w.q, a.Hd, a.d_logit_w, bt, a.K, a.Hd, a.att_mode, a.dtype, w.parts, s))) return rc;
+    if ((rc = attention_pool(w.parts, 1, a.logit_bias, a.d_x, bt, a.K, a.V, a.dtype, nullptr, w.att_v, nullptr, s))) return rc;
+    vqa_linear_args gi{};                      // W_ih[:, E:] att_v + (W_ih[:, :E] prev + b_ih)
+    gi.d_A = w.att_v; gi.lda = a.V; gi.d_W = a.d_w_att; gi.ldw = a.V; gi.M = bt; gi.N = 3 * a.Hd; gi.K = a.V; gi.dtype = a.dtype;
+    gi.d_add = a.d_gi_prev + (size_t)t * 3 * a.Hd; gi.ld_add = a.T * 3 * a.Hd; gi.add_row_div = 1;
+    gi.d_out = w.gi; gi.ldo = 3 * a.Hd; gi.out_dtype = VQA_F32; gi.mul_row_div = 1;
+    if ((rc = linear_dispatch(gi, s))) return rc;
+    vqa_linear_args gh{};
+    gh.d_A = h_in; gh.lda = a.Hd; gh.d_W = a.d_w_hh; gh.ldw = a.Hd; gh.M = bt; gh.N = 3 * a.Hd; gh.K = a.Hd; gh.dtype = a.dtype;
+    gh.d_bias = a.d_b_hh; gh.d_out = w.gh; gh.ldo = 3 * a.Hd; gh.out_dtype = VQA_F32; gh.mul_row_div = 1; gh.add_row_div = 1;
+    if ((rc = linear_dispatch(gh, s))) return rc;
+    void* h_out_lp = (char*)a.d_h_all + row * a.Hd * es;
+    if ((rc = gru_gate(w.gi, w.gh, bt, a.Hd, 1, 0, a.d_h, a.d_h, h_out_lp, a.Hd, a.dtype, s))) return rc;
+    h_in = h_out_lp;
+    row += (size_t)bt;
+  }
+  return VQA_OK;
+}
+
 // ---- whole path --------------------------------------------------------------
 struct FwdWs {
   void* gru; size_t gru_bytes;

@@ -68,6 +68,11 @@ class MultiplyAttention(nn.Module):
         qp = self.W_q(q, out_dtype=torch.float32)
         return ops.attention_logits(proj, qp.contiguous(), self._logit_vector(), K, mode=0)
 
+    def step_weights(self, dtype):
+        """(mode, W_q, scale, bias, logit vector) of the hidden-state half, for vqa_caption_decode_steps"""
+        (W, s, b), = self.W_q.prepared(dtype)
+        return 0, W, s, b, self._logit_vector()
+
     def forward(self, v, q):
         """v [batch, num_objs, v_dim], q [batch, q_dim] → [batch, num_objs, 1] (f32)"""
         parts, x = self.logit_parts(v, q)
@@ -139,6 +144,11 @@ class ConcatAttention(nn.Module):
         _, W1q, sv, b1, wlin = self._prepared(dtype)
         qadd = ops.linear(as_compute(q, dtype), W1q, sv, b1, relu=False, out_dtype=torch.float32)
         return ops.attention_logits(proj, qadd, wlin, K, mode=1)
+
+    def step_weights(self, dtype):
+        """(mode, W1[:, V:], scale, bias, logit vector) of the hidden-state half, for vqa_caption_decode_steps"""
+        _, W1q, sv, b1, wlin = self._prepared(dtype)
+        return 1, W1q, sv, b1, wlin
 
     def forward(self, v, q):
         """v [batch, num_objs, v_dim], q [batch, q_dim] → [batch, num_objs, 1] (f32)"""

@@ -56,6 +56,8 @@ class DecoderModule(nn.Module):
 class BaseDecoder(DecoderModule):
     """Base generator based on "Show, Attend and Tell" (generator.py:123-181), rnn_type='GRU'."""
 
+    step_loop_in_python = False          # True: compose the per-step ops from Python (same kernels; tests run both)
+
     def __init__(self, ntoken: int, embed_dim: int, hidden_dim: int, v_dim: int, max_len: int, device: str,
                  dropout: float = 0.5, rnn_type: str = 'GRU', att_type: str = 'base'):
         super().__init__()
@@ -150,15 +152,20 @@ class BaseDecoder(DecoderModule):
 
         h = torch.zeros((B, Hd), dtype=torch.float32, device=dev)
         h_in = torch.zeros((B, Hd), dtype=dtype, device=dev)
-        h_all = torch.empty((offs[-1], Hd), dtype=dtype, device=dev)                     # every h_t, packed order
-        for t, bt in enumerate(batches):
-            h_in = h_in[:bt]
-            parts = self.attention.step_parts(proj, h_in, K)
-            _, att_v, _ = ops.attention_pool(parts, att_bias, x[:bt], False, True, False)
-            gi = ops.linear(att_v, P["w_att"], add=gi_prev[:bt, t * 3 * Hd:(t + 1) * 3 * Hd], out_dtype=torch.float32)
-            gh = ops.linear(h_in, P["w_hh"], bias=P["b_hh"], out_dtype=torch.float32)
-            h_in = h_all[offs[t]:offs[t + 1]]
-            ops.gru_cell(gi, gh, h[:bt], h_in)
+        if self.step_loop_in_python:
+            h_all = torch.empty((offs[-1], Hd), dtype=dtype, device=dev)                 # every h_t, packed order
+            for t, bt in enumerate(batches):
+                h_in = h_in[:bt]
+                parts = self.attention.step_parts(proj, h_in, K)
+                _, att_v, _ = ops.attention_pool(parts, att_bias, x[:bt], False, True, False)
+                gi = ops.linear(att_v, P["w_att"], add=gi_prev[:bt, t * 3 * Hd:(t + 1) * 3 * Hd], out_dtype=torch.float32)
+                gh = ops.linear(h_in, P["w_hh"], bias=P["b_hh"], out_dtype=torch.float32)
+                h_in = h_all[offs[t]:offs[t + 1]]
+                ops.gru_cell(gi, gh, h[:bt], h_in)
+        else:                                                                            # the same steps in one C call
+            mode, w_q, q_scale, q_bias, logit_w = self.attention.step_weights(dtype)
+            h_all = ops.caption_decode_steps(x, proj, batches, mode, w_q, q_scale, q_bias, logit_w, att_bias, gi_prev,
+                                             P["w_att"], P["w_hh"], P["b_hh"], h, h_in)
         predict = ops.linear(h_all, P["w_fc"], bias=P["b_fc"], out_dtype=torch.float32)
         # the targets are the words after <start> (generator.py:115), packed like the predictions
         tgt = torch.cat([target[:bt, t + 1] for t, bt in enumerate(batches)])

@@ -309,6 +309,45 @@ def gru_cell(gi, gh, h, h_lp):
     return h
 
 
+def caption_decode_steps(x, proj, batches, att_mode, w_q, q_scale, q_bias, logit_w, logit_bias, gi_prev, w_att, w_hh, b_hh,
+                         h, h0_lp):
+    """The teacher-forced time loop of the caption head in one C call (vqa_caption_decode_steps;
+    generator.py:99-111 + :168-181).  ``batches``: python list, batch_t per step (non-increasing).
+    x [B,K,V], proj [B*K,Hd], gi_prev f32 [B, T*3Hd], h f32 [B,Hd] (updated in place), h0_lp [B,Hd].
+    Returns h_all [Σ batch_t, Hd] in the compute dtype (every new state, pack_padded_sequence order)."""
+    lib = L.load()
+    _require(x, None, "x")
+    dt = x.dtype
+    for nm, t in (("proj", proj), ("w_q", w_q), ("w_att", w_att), ("w_hh", w_hh), ("h0_lp", h0_lp)):
+        _require(t, dt, nm)
+    for nm, t in (("q_scale", q_scale), ("q_bias", q_bias), ("logit_w", logit_w), ("gi_prev", gi_prev), ("b_hh", b_hh),
+                  ("h", h)):
+        if t is not None:
+            _require(t, torch.float32, nm)
+    B, K, V = x.shape
+    Hd, T = h.shape[1], len(batches)
+    if (proj.shape != (B * K, Hd) or gi_prev.shape != (B, T * 3 * Hd) or w_att.shape != (3 * Hd, V) or
+            w_hh.shape != (3 * Hd, Hd) or w_q.shape != (Hd, Hd) or h.shape != (B, Hd) or h0_lp.shape != (B, Hd) or
+            not all(t.is_contiguous() for t in (x, proj, gi_prev, w_att, w_hh, w_q, h, h0_lp))):
+        raise ValueError("caption_decode_steps: shape mismatch")
+    code = dtype_code(dt)
+    h_all = torch.empty((sum(batches), Hd), dtype=dt, device=x.device)
+    ws_bytes = lib.vqa_caption_decode_workspace_bytes(B, K, V, Hd, code)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=x.device)
+    a = L.CaptionDecodeArgs()
+    a.B, a.K, a.V, a.Hd, a.T, a.dtype = B, K, V, Hd, T, code
+    sched = (C.c_int * max(T, 1))(*batches)
+    a.h_batches = sched
+    a.d_x, a.d_proj, a.att_mode = x.data_ptr(), proj.data_ptr(), int(att_mode)
+    a.d_wq, a.d_wq_scale, a.d_wq_bias = w_q.data_ptr(), _ptr(q_scale), _ptr(q_bias)
+    a.d_logit_w, a.logit_bias, a.d_gi_prev = logit_w.data_ptr(), float(logit_bias), gi_prev.data_ptr()
+    a.d_w_att, a.d_w_hh, a.d_b_hh = w_att.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr()
+    a.d_h_all, a.d_h, a.d_h0_lp = h_all.data_ptr(), h.data_ptr(), h0_lp.data_ptr()
+    a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+    L.check(lib.vqa_caption_decode_steps(C.byref(a), _stream()))
+    return h_all
+
+
 def attention_pool(parts, logit_bias, x, want_att=True, want_vsum=True, want_vatt=False):
     """softmax over K + weighted sums (attention.py:86, encoder.py:166, predictor.py:85).
 
