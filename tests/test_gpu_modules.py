@@ -153,3 +153,40 @@ def test_other_classifier_depths_take_the_module_path(cls_layer):
         assert torch.equal(label.cpu(), x.argmax(1))
     finally:
         pkg.set_precision("bf16")
+
+
+def test_pretrained_word_embedding_matches_embedding_layer(tmp_path):
+    """set_model(pretrained_embed_path=...) (main.py:83 default): same answers as an nn.Embedding holding the same table,
+    through the fused engine and through the module-level path"""
+    import vqa_collection_b200 as pkg
+    from vqa_collection_b200.modules.wrapper import set_model
+    pkg.set_precision("fp32")
+    try:
+        cfg = O.SMALL
+        n_words = cfg.ntoken - 3                                     # + <oov>,<start>,<end>,<pad> = ntoken + 1 rows
+        table = torch.randn((n_words, cfg.embed_dim), generator=torch.Generator().manual_seed(9))
+        path = str(tmp_path / "glove.txt")
+        with open(path, "w") as f:
+            for i in range(n_words):
+                f.write(f"w{i} " + " ".join(f"{x:.6f}" for x in table[i].tolist()) + "\n")
+        kw = dict(encoder_type="base", predictor_type="base", decoder_type="none", ntoken=cfg.ntoken, v_dim=cfg.v_dim,
+                  embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim, decoder_hidden_dim=0, rnn_layer=1, ans_dim=cfg.ans_dim,
+                  cls_layer=2, c_len=cfg.c_len, device="cuda", dropout=0.2, rnn_type="GRU", att_type="new")
+        W = O.make_weights(cfg, 1111)
+        m_glove = set_model(pretrained_embed_path=path, **kw)
+        m_glove.load_state_dict({k: v for k, v in W.items() if k != "encoder.embedding.weight"}, strict=True)
+        W2 = dict(W)
+        W2["encoder.embedding.weight"] = m_glove.encoder.embedding.vocab.clone()
+        m_plain = set_model(**kw)
+        m_plain.load_state_dict(W2, strict=True)
+        batch = {k: v for k, v in O.make_batch(cfg, 6, 31).items() if torch.is_tensor(v)}
+        with torch.no_grad():
+            s1, l1, _ = m_glove.eval().forward_vqa(batch)
+            s2, l2, _ = m_plain.eval().forward_vqa(batch)
+            p1, _ = m_glove(batch)
+            p2, _ = m_plain(batch)
+            want, _ = O.forward(batch, W2, cfg)
+        assert torch.equal(l1, l2) and torch.equal(s1, s2) and torch.equal(p1, p2)
+        assert relerr(p1, want) < 1e-5
+    finally:
+        pkg.set_precision("bf16")

@@ -427,3 +427,32 @@ def test_host_path_tuning_scales_with_cores_per_rank(monkeypatch):
     assert engine.host_pack_threads() == 3
     monkeypatch.delenv("VQA_B200_PACK_THREADS")
     assert engine.host_pack_threads() == max(1, n // 8)
+
+
+def _write_glove(path, n_words, dim, seed=3):
+    g = torch.Generator().manual_seed(seed)
+    table = torch.randn((n_words, dim), generator=g)
+    with open(path, "w") as f:
+        for i in range(n_words):
+            f.write(f"w{i} " + " ".join(f"{x:.6f}" for x in table[i].tolist()) + "\n")
+    return table
+
+
+def test_pretrained_word_embedding_drop_in(tmp_path):
+    """main.py:83 default: a GloVe text file replaces encoder.embedding (encoder.py:56-57, modules.py:166-199) — rows in
+    file order + 4 zero rows, frozen, NOT in the state_dict"""
+    from vqa_collection_b200.modules.wrapper import set_model
+    from vqa_collection_b200.modules.modules import PretrainedWordEmbedding
+    path = str(tmp_path / "glove.txt")
+    table = _write_glove(path, 12, 8)
+    m = set_model(encoder_type="base", predictor_type="base", decoder_type="none", ntoken=15, v_dim=16, embed_dim=8,
+                  hidden_dim=8, rnn_layer=1, ans_dim=4, cls_layer=2, c_len=5, device="cpu", att_type="new",
+                  pretrained_embed_path=path)
+    emb = m.encoder.embedding
+    assert isinstance(emb, PretrainedWordEmbedding) and (emb.vocab_len, emb.vocab_dim) == (16, 8)
+    assert "encoder.embedding.weight" not in m.state_dict() and not list(emb.parameters())
+    assert torch.allclose(emb.vocab[:12], table, atol=1e-6) and float(emb.vocab[12:].abs().max()) == 0.0
+    s = torch.tensor([[0, 11, 15], [3, 3, 12]])
+    out = emb(s)
+    assert out.shape == (2, 3, 8) and torch.equal(out, emb.vocab[s])
+    assert "encoder.embedding.weight" in m.reference_named_weights()          # the fused engine still gets the table

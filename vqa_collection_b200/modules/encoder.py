@@ -5,7 +5,7 @@ import torch.nn as nn
 from .. import compute_dtype, ops
 from .attention import set_att
 from .gcn import GCN
-from .modules import FCNet, SentenceEmbedding, PreparedCache, as_compute, _no_training
+from .modules import FCNet, SentenceEmbedding, PretrainedWordEmbedding, PreparedCache, as_compute, _no_training
 
 
 def set_encoder(encoder_type: str, ntoken: int, v_dim: int, embed_dim: int, hidden_dim: int, device: str,
@@ -21,8 +21,7 @@ def set_encoder(encoder_type: str, ntoken: int, v_dim: int, embed_dim: int, hidd
     else:
         raise NotImplementedError(f"encoder_type='{encoder_type}' is outside the accelerated VQA forward path")
     if vocab_path != '':
-        raise NotImplementedError("PretrainedWordEmbedding (GloVe file loader) is outside the accelerated path; "
-                                  "load the vectors into encoder.embedding.weight instead")
+        model.embedding = PretrainedWordEmbedding(vocab_path=vocab_path, device=device)      # encoder.py:56-57
     return model.to(device)
 
 

@@ -232,6 +232,36 @@ class SentenceEmbedding(nn.Module):
         return ops.gru_last_state(tokens, table, w_ih, b_ih, w_hh, b_hh, packed=packed)
 
 
+class PretrainedWordEmbedding(nn.Module):
+    """Pre-trained (GloVe text file) word vectors + 4 zero rows for <oov>/<start>/<end>/<pad>, frozen
+    (modules.py:166-199).  Like the reference, ``vocab`` is a plain tensor attribute — it is NOT in the
+    state_dict (a checkpoint trained with GloVe has no ``encoder.embedding.weight`` key) and never receives
+    a gradient.  ``weight`` is the device copy the fused embedding-gather + GRU kernel reads."""
+
+    def __init__(self, vocab_path: str, device: str):
+        super().__init__()
+        import numpy as np
+        with open(vocab_path) as f:
+            rows = [line.split()[1:] for line in f]
+        self.device = device
+        self.vocab_dim = len(rows[0])
+        self.vocab_len = len(rows) + 4
+        vocab = np.zeros((self.vocab_len, self.vocab_dim), dtype=np.float32)
+        vocab[: len(rows)] = np.asarray(rows, dtype=np.float32)
+        self.vocab = torch.from_numpy(vocab)
+        self._weight = None
+
+    @property
+    def weight(self):
+        if self._weight is None or str(self._weight.device) != str(torch.device(self.device)):
+            self._weight = self.vocab.to(self.device)
+        return self._weight
+
+    def forward(self, s):
+        """s int64 [batch, s_len] → [batch, s_len, vocab_dim] on ``device`` (a row gather; the reference loops over the batch)"""
+        return torch.nn.functional.embedding(s.to(self.device), self.weight)
+
+
 class CaptionAttention(nn.Module):
     """a = sigmoid(h * f(v) + h * f(q)) (modules.py:202-243); parameters + the two f(.) projections — the gate
     itself is fused with the sequence scaling in vqa_caption_gate_scale (see CaptionEmbedding)."""

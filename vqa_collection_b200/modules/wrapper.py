@@ -72,6 +72,7 @@ class Wrapper(nn.Module):
     def reference_named_weights(self):
         """state_dict + the unregistered GCN tensors as gcn.{i}.* """
         W = {k: v for k, v in self.state_dict().items()}
+        W.setdefault("encoder.embedding.weight", self.encoder.embedding.weight)      # PretrainedWordEmbedding: not a parameter
         if isinstance(self.encoder, RelationEncoder):
             for i, layer in enumerate(self.encoder.spatial_encoder.gcn):
                 for k, v in layer.state_dict().items():

@@ -120,6 +120,8 @@ def updown_loss(model, img, tokens, target, seed=None):
     """loss (autograd-attached) and the detached predictions for a vqa_collection_b200 Wrapper with a
     BaseEncoder / MultiplyAttention / BasePredictor; dropout follows model.training."""
     named = dict(model.named_parameters())
+    # a PretrainedWordEmbedding table is frozen and not a parameter (modules.py:166-199): its gradient is dropped by autograd
+    named.setdefault("encoder.embedding.weight", model.encoder.embedding.weight)
     params = [named[n] for n in param_names()]
     enc, pred = model.encoder, model.predictor
     training = model.training
