@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 4
+#define VQA_B200_ABI_VERSION 5
 
 typedef enum {
   VQA_OK = 0,
@@ -297,6 +297,35 @@ typedef struct {
 } vqa_caption_decode_args;
 size_t vqa_caption_decode_workspace_bytes(int B, int K, int V, int Hd, int dtype);
 int vqa_caption_decode_steps(const vqa_caption_decode_args* args, void* stream);
+
+/* ------------------------------------------------------------------------
+ * optimizer side of the training step (BASELINE config 4; the step after the path):
+ * one launch per operation over ALL parameter tensors (pointer table by value).
+ *  vqa_grad_clip     replaces nn.utils.clip_grad_norm_(model.parameters(), max_norm) (train.py:109):
+ *      total_norm = ||all grads||_2, scale = min(1, max_norm / (total_norm + 1e-6)), both written to DEVICE
+ *      scalars (no host sync); scale_in_place != 0 also multiplies every gradient by scale (what the
+ *      reference leaves in .grad), 0 leaves the gradients alone (hand d_scale to vqa_adamax_step instead).
+ *      workspace: vqa_grad_clip_workspace_bytes() bytes.
+ *  vqa_adamax_step   replaces torch.optim.Adamax(...).step() (train.py:57,110), maximize=False:
+ *      g = grad * (*d_grad_scale) + weight_decay * p;  m += (1-beta1)(g-m);  u = max(beta2*u, |g|+eps);
+ *      p -= lr / (1 - beta1^step) * m / u.     lr is per tensor (the param groups of train.py:54-56).
+ *      All tensors f32, contiguous; d_m / d_u are the optimizer state (exp_avg / exp_inf).
+ * h_tensors is a HOST array; at most 8 * VQA_OPTIM_MAX_TENSORS entries.
+ * ---------------------------------------------------------------------- */
+#define VQA_OPTIM_MAX_TENSORS 64
+typedef struct {
+  float* d_p;          /* parameter (NULL for vqa_grad_clip)  */
+  const float* d_g;    /* gradient                            */
+  float* d_m;          /* exp_avg  (NULL for vqa_grad_clip)   */
+  float* d_u;          /* exp_inf  (NULL for vqa_grad_clip)   */
+  size_t n;            /* elements                            */
+  float lr;            /* learning rate of this tensor's group */
+} vqa_optim_tensor;
+size_t vqa_grad_clip_workspace_bytes(void);
+int vqa_grad_clip(const vqa_optim_tensor* h_tensors, int n_tensors, float max_norm, int scale_in_place,
+                  void* d_workspace, float* d_total_norm, float* d_scale, void* stream);
+int vqa_adamax_step(const vqa_optim_tensor* h_tensors, int n_tensors, float beta1, float beta2, float eps,
+                    float weight_decay, int step, const float* d_grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------
  * whole path: Wrapper.forward / forward_vqa (wrapper.py:64-74,113-118) for

@@ -456,3 +456,24 @@ def test_pretrained_word_embedding_drop_in(tmp_path):
     out = emb(s)
     assert out.shape == (2, 3, 8) and torch.equal(out, emb.vocab[s])
     assert "encoder.embedding.weight" in m.reference_named_weights()          # the fused engine still gets the table
+
+
+def test_fused_optimizer_host_side():
+    """constructor checks mirror torch.optim.Adamax; CPU tensors raise (no CPU fallback); nothing to do without grads"""
+    from vqa_collection_b200 import optim
+    p = torch.nn.Parameter(torch.zeros(4))
+    with pytest.raises(ValueError):
+        optim.Adamax([p], lr=-1.0)
+    with pytest.raises(ValueError):
+        optim.Adamax([p], betas=(1.0, 0.999))
+    o = optim.Adamax([{"params": [p]}], lr=0.002)
+    assert o.defaults == dict(lr=0.002, betas=(0.9, 0.999), eps=1e-8, weight_decay=0)
+    o.step()                                                            # no gradients: no library call
+    assert float(optim.clip_grad_norm_([p], 0.25)) == 0.0
+    p.grad = torch.ones(4)
+    with pytest.raises(RuntimeError):
+        o.step()
+    with pytest.raises(RuntimeError):
+        optim.clip_grad_norm_([p], 0.25)
+    with pytest.raises(NotImplementedError):
+        optim.clip_grad_norm_([p], 0.25, norm_type=1)

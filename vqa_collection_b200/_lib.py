@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
 
 VQA_F32, VQA_BF16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -118,6 +118,13 @@ class TrainArgs(C.Structure):
     ]
 
 
+OPTIM_MAX_TENSORS = 64
+
+
+class OptimTensor(C.Structure):
+    _fields_ = [("d_p", c_void_p), ("d_g", c_void_p), ("d_m", c_void_p), ("d_u", c_void_p), ("n", c_size_t), ("lr", c_float)]
+
+
 class CaptionDecodeArgs(C.Structure):
     _fields_ = [
         ("B", c_int), ("K", c_int), ("V", c_int), ("Hd", c_int), ("T", c_int), ("dtype", c_int),
@@ -160,6 +167,10 @@ SYMBOLS = {
     "vqa_gru_cell": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "vqa_caption_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vqa_caption_decode_steps": (c_int, [C.POINTER(CaptionDecodeArgs), c_void_p]),
+    "vqa_grad_clip_workspace_bytes": (c_size_t, []),
+    "vqa_grad_clip": (c_int, [C.POINTER(OptimTensor), c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vqa_adamax_step": (c_int, [C.POINTER(OptimTensor), c_int, c_float, c_float, c_float, c_float, c_int, c_void_p,
+                                c_void_p]),
     "vqa_argmax_rows": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vqa_forward_workspace_bytes": (c_size_t, [C.POINTER(ForwardArgs)]),
     "vqa_forward": (c_int, [C.POINTER(ForwardArgs), c_void_p]),

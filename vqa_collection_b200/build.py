@@ -16,7 +16,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libvqa_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["api.cu", "relation.cu", "pool.cu", "gemm_simt.cu", "gemm_tc.cu", "gru_tc.cu", "gru_pair.cu", "graph_attn.cu", "graph_attn_tc.cu", "train.cu", "host.cu", "caption.cu"]
+SOURCES = ["api.cu", "relation.cu", "pool.cu", "gemm_simt.cu", "gemm_tc.cu", "gru_tc.cu", "gru_pair.cu", "graph_attn.cu", "graph_attn_tc.cu", "train.cu", "host.cu", "caption.cu", "optim.cu"]
 HOST_SOURCES = ["host_pack.cpp"]          # plain C++ (g++): SIMD pack loop + thread pool of the e2e path
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -64,6 +64,9 @@ int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
 int cast_bf16_to_f32(const void*, float*, size_t, cudaStream_t);
 int graph_attention(const vqa_graph_attention_args&, cudaStream_t);
 int graph_attention_tc(const vqa_graph_attention_args&, cudaStream_t);
+size_t optim_norm_workspace_bytes();
+int grad_clip(const vqa_optim_tensor*, int, float, int, float*, float*, float*, cudaStream_t);
+int adamax_step(const vqa_optim_tensor*, int, float, float, float, float, int, const float*, cudaStream_t);
 size_t train_workspace_bytes(const vqa_train_args&);
 int updown_train_step(const vqa_train_args&, cudaStream_t);
 int gru_persistent(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
@@ -381,6 +384,19 @@ int vqa_caption_decode_steps(const vqa_caption_decode_args* args, void* stream) 
     row += (size_t)bt;
   }
   return VQA_OK;
+}
+
+size_t vqa_grad_clip_workspace_bytes(void) { return optim_norm_workspace_bytes(); }
+int vqa_grad_clip(const vqa_optim_tensor* h_tensors, int n_tensors, float max_norm, int scale_in_place, void* d_workspace,
+                  float* d_total_norm, float* d_scale, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return grad_clip(h_tensors, n_tensors, max_norm, scale_in_place, (float*)d_workspace, d_total_norm, d_scale,
+                   (cudaStream_t)stream);
+}
+int vqa_adamax_step(const vqa_optim_tensor* h_tensors, int n_tensors, float beta1, float beta2, float eps, float weight_decay,
+                    int step, const float* d_grad_scale, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return adamax_step(h_tensors, n_tensors, beta1, beta2, eps, weight_decay, step, d_grad_scale, (cudaStream_t)stream);
 }
 
 // ---- whole path --------------------------------------------------------------

@@ -128,11 +128,12 @@ class Wrapper(nn.Module):
         img = as_compute(batch['img'].to(self.device), compute_dtype())
         tokens = batch['q'].to(self.device)
         loss_vqa, predict = training.updown_loss(self, img, tokens, target)
-        writes = {'train/loss': loss_vqa.item(),
-                  'train/score': compute_score(predict, target, self.device).sum().item()}
-        loss = torch.tensor(0, dtype=torch.float).to(self.device)
-        loss = loss + loss_vqa                       # use_mtl needs a generator too (wrapper.py:50)
-        return torch.mean(loss), writes
+        # the two logged scalars (wrapper.py:86-87) leave the device in ONE copy: lowest-index argmax → Σ one_hot ⊙ target
+        _, _, score_sum = ops.answer_scores(ops.argmax_rows(predict), target.contiguous(), want_dense=False, want_sum=True)
+        loss_val, score_val = torch.stack((loss_vqa.detach(), score_sum[0])).tolist()
+        writes = {'train/loss': loss_val, 'train/score': score_val}
+        # use_mtl needs a generator too (wrapper.py:50): loss = mean(0 + loss_vqa) = loss_vqa
+        return loss_vqa, writes
 
     def get_att(self, batch):
         batch = self.encoder(batch)

@@ -75,7 +75,12 @@ class FlatGradients:
             offs.append(off)
             off += (n + 63) // 64 * 64                       # 256-byte aligned views
         self.flat = torch.zeros((off,), dtype=torch.float32, device=device)
-        self.views = [self.flat[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
+        self._layout = list(zip(offs, sizes, shapes))
+        self.views = [self.flat[o:o + n].view(s) for o, n, s in self._layout]
+
+    def fresh_views(self):
+        """new tensor objects over the same memory (nobody else holds them, so autograd may adopt them as .grad)"""
+        return [self.flat[o:o + n].view(s) for o, n, s in self._layout]
 
     def matches(self, shapes, device):
         return (len(shapes) == len(self.views) and self.flat.device == torch.device(device)
