@@ -242,6 +242,27 @@ def test_attention_pool(ops, dtype, B, K, V, P):
     assert none is None and relerr(vsum2, want_v.sum(1)) < TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,K,V,P", [(1, 36, 2048, 4), (37, 36, 2048, 4), (300, 36, 2048, 1), (9, 64, 1024, 2), (11, 7, 512, 3),
+                                     (1024, 36, 2048, 4)])
+def test_attention_pool_stream_kernel(ops, dtype, B, K, V, P):
+    """att + vsum (the Up-Down forward's form) takes the persistent bulk-copy streaming kernel (V <= 2048): fewer images
+    than SMs, many ring wrap-arounds per CTA, a short last chunk (K = 64), one chunk per image (K = 7), idle consumer warps"""
+    g = torch.Generator().manual_seed(B * K + V + P)
+    parts = torch.randn((B * K, P), generator=g) * 2
+    x = torch.rand((B, K, V), generator=g).to(dtype)
+    att, vsum, none = ops.attention_pool(parts.cuda(), -0.2, x.cuda(), True, True, False)
+    want_att = torch.softmax(parts.sum(1).view(B, K) - 0.2, 1)
+    want = (want_att.unsqueeze(2).double() * x.double()).sum(1)
+    assert none is None and relerr(att, want_att) < 1e-5
+    assert relerr(vsum, want) < TOL[dtype]
+    # per-row check (a max-norm over the whole batch would hide a wrong image): every image on its own
+    err = ((vsum.double().cpu() - want).abs().amax(1) / want.abs().amax(1))
+    assert float(err.max()) < TOL[dtype] * 2
+    _, vsum2, _ = ops.attention_pool(parts.cuda(), -0.2, x.cuda(), False, True, False)
+    assert torch.equal(vsum2, vsum)                                        # deterministic, att output optional
+
+
 # ---------------------------------------------------------------------------- backward GEMM forms
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,N,K", [(512, 2048, 3129), (1000, 304, 520), (36 * 64, 1024, 2048)])

@@ -1,7 +1,9 @@
 // k6 top-down attention pooling, a14 lowest-index argmax, GRU gate update,
 // embedding gather and f32<->bf16 casts.  All HBM-bound streaming kernels:
 // 16-byte vector accesses, one CTA per image / row group, no tensor cores.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "tc_common.cuh"
 
 namespace vqa {
 
@@ -81,12 +83,177 @@ attention_pool_kernel(const float* __restrict__ parts, int n_parts, float bias,
   if (vsum != nullptr) store8(vsum + (size_t)b * V + c, acc);
 }
 
+// ---------------------------------------------------------------------------
+// k6, streaming form (att + vsum, the Up-Down forward): persistent CTAs; one image's [K,V] block is CONTIGUOUS in
+// memory (147 KB at K=36, V=2048 bf16), so it is streamed as a few large sequential bulk async copies
+// (cp.async.bulk, mbarrier complete_tx) through a shared-memory ring instead of as K strided 1 KB pieces per CTA
+// through registers (the kernel above; ncu cold: 41 % of DRAM peak, 3.4 TB/s).
+//   warps 0..7  consumers: thread t owns channels [8t, 8t+8) for the whole image (V <= 2048)
+//   warp 8      producer: one lane issues one bulk copy per ring stage (R whole rows, <= 36 KB)
+//   warp 0 also computes the image's softmax (double-buffered in shared memory) before the first chunk is consumed
+// ---------------------------------------------------------------------------
+constexpr int kStreamMaxStages = 6;
+constexpr int kStreamChunkBytes = 36 * 1024;
+constexpr int kStreamConsumers = 256;
+constexpr int kStreamThreads = kStreamConsumers + 32;
+
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void lds8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+attention_pool_stream_kernel(const float* __restrict__ parts, int n_parts, float bias, const T* __restrict__ x, int B, int K,
+                             int V, int rev, int S, int R, float* __restrict__ att_out, T* __restrict__ vsum) {
+  using namespace tc;
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const uint32_t row_bytes = (uint32_t)V * sizeof(T);
+  const uint32_t chunk_bytes = (uint32_t)R * row_bytes;
+  const int chunks = (K + R - 1) / R;
+  const uint32_t ring = smem_u32(ring_smem);
+  const uint32_t bars = ring + (uint32_t)S * chunk_bytes;                   // full[0..S), empty[0..S)
+  float* s_att = reinterpret_cast<float*>(ring_smem + (size_t)S * chunk_bytes + 128);   // [2][kPoolMaxK]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < S; ++st) { mbar_init(bars + 8u * st, 1); mbar_init(bars + 8u * (S + st), kStreamConsumers / 32); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  griddep_launch();
+  griddep_wait();
+  if (warp == kStreamConsumers / 32) {
+    // ===== producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int img = blockIdx.x; img < B; img += gridDim.x) {
+        const int b = rev ? B - 1 - img : img;                    // descending image order, see attention_pool_kernel
+        const T* src = x + (size_t)b * K * V;
+        for (int c = 0; c < chunks; ++c, ++it) {
+          const int st = it % S;
+          mbar_wait(bars + 8u * (S + st), (((uint32_t)(it / S)) & 1u) ^ 1u);
+          const int rows = (K - c * R) < R ? (K - c * R) : R;
+          const uint32_t bytes = (uint32_t)rows * row_bytes;
+          mbar_arrive_expect_tx(bars + 8u * st, bytes);
+          bulk_copy_g2s(ring + (uint32_t)st * chunk_bytes, src + (size_t)c * R * V, bytes, bars + 8u * st);
+        }
+      }
+    }
+  } else {
+    // ===== consumers =====
+    const int ch = threadIdx.x * 8;
+    const bool active = ch < V;
+    int it = 0, n = 0;
+    for (int img = blockIdx.x; img < B; img += gridDim.x, ++n) {
+      const int b = rev ? B - 1 - img : img;
+      float* att = s_att + (n & 1) * kPoolMaxK;
+      if (warp == 0) {
+        // softmax over the K regions (lane handles k = lane and lane + 32) while the copies land
+        float l0 = -INFINITY, l1 = -INFINITY;
+        if (lane < K) {
+          const float* p = parts + (size_t)(b * K + lane) * n_parts;
+          float sacc = 0.f;
+          for (int i = 0; i < n_parts; ++i) sacc += __ldg(p + i);
+          l0 = sacc + bias;
+        }
+        if (lane + 32 < K) {
+          const float* p = parts + (size_t)(b * K + lane + 32) * n_parts;
+          float sacc = 0.f;
+          for (int i = 0; i < n_parts; ++i) sacc += __ldg(p + i);
+          l1 = sacc + bias;
+        }
+        const float m = warp_max(fmaxf(l0, l1));
+        const float e0 = (lane < K) ? expf(l0 - m) : 0.f;
+        const float e1 = (lane + 32 < K) ? expf(l1 - m) : 0.f;
+        const float inv = 1.f / warp_sum(e0 + e1);
+        if (lane < K) { att[lane] = e0 * inv; if (att_out) att_out[(size_t)b * K + lane] = e0 * inv; }
+        if (lane + 32 < K) { att[lane + 32] = e1 * inv; if (att_out) att_out[(size_t)b * K + lane + 32] = e1 * inv; }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kStreamConsumers) : "memory");
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int c = 0; c < chunks; ++c, ++it) {
+        const int st = it % S;
+        mbar_wait(bars + 8u * st, ((uint32_t)(it / S)) & 1u);
+        const int rows = (K - c * R) < R ? (K - c * R) : R;
+        if (active) {
+          const T* base = reinterpret_cast<const T*>(ring_smem + (size_t)st * chunk_bytes) + ch;
+#pragma unroll 3
+          for (int r = 0; r < rows; ++r) {
+            float v[8];
+            lds8(base + (size_t)r * V, v);
+            const float a = att[c * R + r];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(a, v[i], acc[i]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8u * (S + st));          // this warp is done with the stage
+      }
+      if (active) store8(vsum + (size_t)b * V + ch, acc);
+    }
+  }
+}
+
+static bool pool_stream_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VQA_B200_POOL_STREAM"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+template <typename T>
+static int launch_pool_stream(const float* parts, int n_parts, float bias, const T* x, int B, int K, int V, int rev, float* att,
+                              T* vsum, cudaStream_t s) {
+  const int row_bytes = V * (int)sizeof(T);
+  int R = kStreamChunkBytes / row_bytes;
+  if (R < 1) R = 1;
+  if (R > K) R = K;
+  const int chunks = (K + R - 1) / R;
+  int S = kStreamMaxStages;
+  const size_t smem = (size_t)S * R * row_bytes + 128 + 2 * kPoolMaxK * sizeof(float);
+  const int grid = B < sm_count() ? B : sm_count();
+  (void)chunks;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[sizeof(T) == 2]) {
+    VQA_CUDA_CHECK(cudaFuncSetAttribute(attention_pool_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kStreamMaxStages * kStreamChunkBytes + 1024));
+    attr_done[sizeof(T) == 2] = true;
+  }
+  VQA_CUDA_CHECK(launch_pdl(attention_pool_stream_kernel<T>, dim3(grid), dim3(kStreamThreads), smem, s, parts, n_parts, bias,
+                            x, B, K, V, rev, S, R, att, vsum));
+  VQA_LAUNCH_CHECK();
+  return VQA_OK;
+}
+
 int attention_pool(const float* parts, int n_parts, float bias, const void* x, int B, int K, int V,
                    int dtype, float* att, void* vsum, void* vatt, cudaStream_t s) {
   VQA_REQUIRE(K >= 1 && K <= kPoolMaxK, "attention_pool: K=%d out of range", K);
   VQA_REQUIRE(V % 8 == 0 && n_parts >= 1, "attention_pool: V=%d must be a multiple of 8", V);
   if (B == 0) return VQA_OK;
   VQA_REQUIRE(parts && x, "attention_pool: NULL input");
+  if (vsum != nullptr && vatt == nullptr && pool_stream_enabled() && V <= kStreamConsumers * 8 &&
+      V * (int)elem_size(dtype) <= kStreamChunkBytes && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(vsum) & 15) == 0) {
+    const int rev = l2_order_enabled() ? 1 : 0;
+    if (dtype == VQA_BF16)
+      return launch_pool_stream<__nv_bfloat16>(parts, n_parts, bias, (const __nv_bfloat16*)x, B, K, V, rev, att,
+                                               (__nv_bfloat16*)vsum, s);
+    return launch_pool_stream<float>(parts, n_parts, bias, (const float*)x, B, K, V, rev, att, (float*)vsum, s);
+  }
   const bool stream_x = vsum != nullptr || vatt != nullptr;
   const int slices = stream_x ? (V + kPoolChan - 1) / kPoolChan : 1;
   const unsigned grid = (unsigned)B * slices;
