@@ -19,14 +19,9 @@ def compute_score(predict, target, device, get_label=False):
     """VQA soft score of the lowest-index argmax answer (wrapper.py:8-22)."""
     predict = predict.to(device)
     target = target.to(device)
-    if predict.is_cuda and target.is_cuda:
-        logits = ops.argmax_rows(predict.float().contiguous())          # torch.max(predict, 1)[1] tie rule
-        scores, _, _ = ops.answer_scores(logits, target.float().contiguous())     # one_hot ⊙ target in one kernel
-    else:
-        logits = torch.max(predict, 1)[1].data
-        one_hots = torch.zeros(*target.size(), device=target.device)
-        one_hots.scatter_(1, logits.view(-1, 1), 1)
-        scores = one_hots * target
+    # no CPU path: ops raises on non-CUDA tensors
+    logits = ops.argmax_rows(predict.float().contiguous())              # torch.max(predict, 1)[1] tie rule
+    scores, _, _ = ops.answer_scores(logits, target.float().contiguous())         # one_hot ⊙ target in one kernel
     if get_label:
         return scores, logits
     return scores

@@ -131,46 +131,3 @@ class Adamax(torch.optim.Optimizer):
                 a.d_p, a.d_g, a.d_m, a.d_u, a.n, a.lr = e
             L.check(lib.vqa_adamax_step(arr, len(entries), b1, b2, eps, wd, step, gs, _stream()))
         return loss
-        key = tuple(id(p) for _, p in live)
-        plan = self._plan if getattr(self, "_plan", None) is not None and self._plan[0] == key else None
-        if plan is None:
-            # first step (or the set of parameters with gradients changed): state + one pointer table per distinct
-            # (betas, eps, weight_decay, step) — a single table for the reference's param groups, which differ in lr only
-            buckets = {}
-            for gi, p in live:
-                group = self.param_groups[gi]
-                _check_grad(p, p.grad)
-                if not p.is_contiguous():
-                    raise RuntimeError("vqa_collection_b200.optim.Adamax: parameters must be contiguous")
-                st = self.state[p]
-                if len(st) == 0:
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_inf"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                b1, b2 = group["betas"]
-                hk = (float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), int(st["step"]))
-                buckets.setdefault(hk, []).append((gi, p, st))
-            tables = []
-            for hk, items in buckets.items():
-                arr = _table([(p.data_ptr(), None, st["exp_avg"].data_ptr(), st["exp_inf"].data_ptr(), p.numel(), 0.0)
-                              for _, p, st in items])
-                tables.append((hk[:4], items, arr))
-            plan = self._plan = (key, tables)
-        gs = None
-        if grad_scale is not None:
-            if not (grad_scale.is_cuda and grad_scale.dtype == torch.float32 and grad_scale.numel() == 1):
-                raise TypeError("Adamax.step: grad_scale must be a 1-element float32 CUDA tensor")
-            gs = grad_scale.data_ptr()
-        for (b1, b2, eps, wd), items, arr in plan[1]:
-            step = None
-            for i, (gi, p, st) in enumerate(items):
-                g = p.grad
-                if g.dtype != torch.float32 or not g.is_cuda or not g.is_contiguous():
-                    _check_grad(p, g)
-                    raise RuntimeError("vqa_collection_b200.optim.Adamax: gradients must be contiguous")
-                st["step"] += 1
-                arr[i].d_g, arr[i].lr = g.data_ptr(), float(self.param_groups[gi]["lr"])
-                if step is None:
-                    step = int(st["step"])
-            L.check(lib.vqa_adamax_step(arr, len(items), b1, b2, eps, wd, step, gs, _stream()))
-        return loss
