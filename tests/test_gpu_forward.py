@@ -169,6 +169,33 @@ def test_engine_full_batch_properties(engine_mod):
     assert torch.equal(b["label"], torch.max(b["logits"], 1)[1])
 
 
+def test_regat_full_batch_properties(engine_mod):
+    """BASELINE config 3 size (ReGAT, B=1024), size-independent properties: on-device labels == the oracle's relation graphs
+    for every image, determinism, alpha columns sum to 1 (softmax over the ROW index, gcn.py:125), and the 8-way
+    data-parallel split (128 questions per GPU) reproduces its rows of the unsharded result bit for bit."""
+    cfg = O.FULL_REGAT
+    W = O.make_weights(cfg, 1111)
+    B = 1024
+    g = torch.Generator().manual_seed(77)
+    img = torch.rand((B, cfg.num_objs, cfg.v_dim), generator=g).to(torch.bfloat16).cuda()
+    q = torch.randint(0, cfg.ntoken, (B, cfg.q_len), generator=g).cuda()
+    boxes = O.make_boxes(B, cfg.num_objs, 78, 640, 480, grid=True)
+    bbox = torch.from_numpy(boxes).cuda()
+    eng = engine_mod.VQAEngine(W, relation=True, precision="bf16")
+    a = eng.forward(img, q, bbox=bbox, wh=(640, 480), want_alpha=True)
+    logits, alpha, labels, answers = a["logits"].clone(), a["alpha"].clone(), a["labels"].clone(), a["label"].clone()
+    assert np.array_equal(labels.cpu().numpy(), O.relation_graph_batch(boxes, 640, 480).astype(np.uint8))
+    b = eng.forward(img, q, bbox=bbox, wh=(640, 480), want_alpha=True)
+    assert torch.equal(b["logits"], logits) and torch.equal(b["alpha"], alpha) and torch.equal(b["label"], answers)
+    assert float(logits.min()) >= 0.0
+    assert torch.allclose(alpha.sum(1), torch.ones((B, cfg.num_objs), device="cuda"), atol=1e-4)
+    assert torch.equal(answers, torch.max(logits, 1)[1])
+    for r in (0, 3, 7):                                                   # ranks of an 8-GPU job
+        lo, hi = r * 128, (r + 1) * 128
+        part = eng.forward(img[lo:hi], q[lo:hi], bbox=bbox[lo:hi], wh=(640, 480))
+        assert torch.equal(part["logits"], logits[lo:hi]) and torch.equal(part["label"], answers[lo:hi])
+
+
 @pytest.mark.parametrize("relation", [False, True])
 @pytest.mark.parametrize("B", [0, 1, 37, 129])
 def test_engine_empty_single_and_ragged_batches(engine_mod, relation, B):
