@@ -73,6 +73,8 @@ SMALL_CONCAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_d
 FULL_CONCAT = Config(att_type="base")
 SMALL_QCAP = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, predictor="q-cap")
 FULL_QCAP = Config(predictor="q-cap")
+SMALL_BASECAP = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, predictor="base-cap")
+FULL_BASECAP = Config(predictor="base-cap")
 SMALL_DECODER = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, decoder="base",
                        decoder_hidden_dim=64)
 FULL_DECODER = Config(decoder="base")
@@ -153,6 +155,14 @@ def make_weights(cfg: Config, seed: int = 1111, sharpen_att: float = 100.0,
         wn_linear("predictor.v_net.main.0", H, V)
         wn_linear("predictor.classifier.main.0", 2 * H, H)
         wn_linear("predictor.classifier.main.3", A, 2 * H, sharpen_cls)
+        if cfg.predictor == "base-cap":
+            # BaseCaptionPredictor (predictor.py:95-140): + a caption GRU (last state) and FCNet(H, H)
+            p = "predictor.c_rnn.rnn"
+            w[p + ".weight_ih_l0"] = _uniform(g, (3 * H, E), kb)
+            w[p + ".weight_hh_l0"] = _uniform(g, (3 * H, H), kb)
+            w[p + ".bias_ih_l0"] = _uniform(g, (3 * H,), kb)
+            w[p + ".bias_hh_l0"] = _uniform(g, (3 * H,), kb)
+            wn_linear("predictor.c_net.main.0", H, H)
 
     if cfg.relation:
         for i in range(cfg.conv_layer):
@@ -419,6 +429,19 @@ def base_predictor(enc, W):
     return torch.relu(F.linear(h, w3, W[p + ".3.bias"]))
 
 
+def base_caption_predictor(enc, W):
+    """BaseCaptionPredictor.forward (predictor.py:116-140): c = FCNet(GRU_last(embedded caption));
+    joint = q ⊙ (c + v_net(Σ_K v)); same classifier as BasePredictor."""
+    v = fcnet1(enc["v"].sum(1), W, "predictor.v_net")
+    c = fcnet1(gru_last(enc["c"], W, "predictor.c_rnn.rnn"), W, "predictor.c_net")
+    joint = enc["q"] * (c + v)
+    p = "predictor.classifier.main"
+    w0 = wn_weight(W[p + ".0.weight_v"], W[p + ".0.weight_g"])
+    w3 = wn_weight(W[p + ".3.weight_v"], W[p + ".3.weight_g"])
+    h = torch.relu(F.linear(joint, w0, W[p + ".0.bias"]))
+    return torch.relu(F.linear(h, w3, W[p + ".3.bias"]))
+
+
 def lrelu_net(x, W, prefix, slope):
     """LReLUNet (modules.py:62-78): LeakyReLU(Linear(x)), no bias."""
     return F.leaky_relu(F.linear(x, W[prefix + ".main.0.weight"]), slope)
@@ -505,7 +528,12 @@ def compute_score(predict, target):
 def forward(batch, W, cfg: Config):
     """Wrapper.forward / get_att composition (wrapper.py:64-74,107-110)."""
     enc = relation_encoder(batch, W, cfg.conv_layer) if cfg.relation else base_encoder(batch, W)
-    logits = qcap_predictor(enc, W, cfg.neg_slope) if cfg.predictor == "q-cap" else base_predictor(enc, W)
+    if cfg.predictor == "q-cap":
+        logits = qcap_predictor(enc, W, cfg.neg_slope)
+    elif cfg.predictor == "base-cap":
+        logits = base_caption_predictor(enc, W)
+    else:
+        logits = base_predictor(enc, W)
     return logits, enc
 
 

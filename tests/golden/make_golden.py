@@ -198,6 +198,10 @@ def run_relation():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--basecap-only" in sys.argv:
+        run_model("basecap_small", O.SMALL_BASECAP, 8, 1111, 8001)
+        run_model("basecap_full", O.FULL_BASECAP, 4, 1111, 8002)
+        sys.exit(0)
     if "--decoder-only" in sys.argv:
         run_decoder("decoder_small", O.SMALL_DECODER, 8, 1111, 7001, 1)
         run_decoder("decoder_full", O.FULL_DECODER, 5, 1111, 7002, 16)
@@ -219,3 +223,5 @@ if __name__ == "__main__":
     run_qcap("qcap_full", O.FULL_QCAP, 4, 1111, 6002)
     run_decoder("decoder_small", O.SMALL_DECODER, 8, 1111, 7001, 1)
     run_decoder("decoder_full", O.FULL_DECODER, 5, 1111, 7002, 16)
+    run_model("basecap_small", O.SMALL_BASECAP, 8, 1111, 8001)
+    run_model("basecap_full", O.FULL_BASECAP, 4, 1111, 8002)

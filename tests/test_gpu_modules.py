@@ -21,7 +21,7 @@ def relerr(a, b):
 
 def build_model(cfg, W, device="cuda"):
     from vqa_collection_b200.modules.wrapper import set_model
-    m = set_model(encoder_type="relation" if cfg.relation else "base", predictor_type="base", decoder_type="none",
+    m = set_model(encoder_type="relation" if cfg.relation else "base", predictor_type=cfg.predictor, decoder_type="none",
                   ntoken=cfg.ntoken, v_dim=cfg.v_dim, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim,
                   decoder_hidden_dim=0, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2, c_len=cfg.c_len, device=device,
                   dropout=0.2, rnn_type="GRU", att_type=cfg.att_type, conv_layer=cfg.conv_layer, conv_type="corr")
@@ -40,7 +40,7 @@ def _need_gpu():
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["updown_small", "regat_small", "updown_full", "regat_full", "concat_small",
-                                  "concat_full"])
+                                  "concat_full", "basecap_small", "basecap_full"])
 def test_wrapper_api_matches_reference(golden_dir, name, precision):
     import vqa_collection_b200 as pkg
     pkg.set_precision(precision)
@@ -55,7 +55,7 @@ def test_wrapper_api_matches_reference(golden_dir, name, precision):
         tol = 1e-5 if precision == "fp32" else 1e-2
         with torch.no_grad():
             predict, att = m.get_att(ref_batch)                      # module-level kernels
-            score, label, target = m.forward_vqa(ref_batch)         # fused engine
+            score, label, target = m.forward_vqa(ref_batch)         # fused engine (module-level path for 'base-cap')
             p2, cap = m(ref_batch)
         assert cap is None and att.shape == (meta["B"], 36, 1)
         assert relerr(att[:, :, 0], z["v_att"]) < tol

@@ -159,9 +159,15 @@ def test_qcap_parameter_names_and_checkpoint_loading():
     for k in sd:
         assert tuple(sd[k].shape) == tuple(W[k].shape), k
     m.load_state_dict(W, strict=True)
-    with pytest.raises(NotImplementedError):
-        set_model(predictor_type="base-cap", decoder_type="none", device="cpu", ntoken=10, v_dim=8, embed_dim=8,
-                  hidden_dim=8, ans_dim=4, cls_layer=2, rnn_layer=1, att_type="new")
+    # predictor_type='base-cap' (predictor.py:95-140): the reference's names again; never on the fused Up-Down engine / train step
+    cfg2 = O.SMALL_BASECAP
+    m2 = set_model(encoder_type="base", predictor_type="base-cap", decoder_type="none", ntoken=cfg2.ntoken, v_dim=cfg2.v_dim,
+                   embed_dim=cfg2.embed_dim, hidden_dim=cfg2.hidden_dim, decoder_hidden_dim=0, rnn_layer=1,
+                   ans_dim=cfg2.ans_dim, cls_layer=2, c_len=cfg2.c_len, device="cpu", dropout=0.2, rnn_type="GRU", att_type="new")
+    W2 = O.make_weights(cfg2, 1111)
+    assert sorted(m2.state_dict().keys()) == sorted(W2.keys())
+    m2.load_state_dict(W2, strict=True)
+    assert not m2.train_step_supported()
 
 
 def test_concat_attention_parameter_names():

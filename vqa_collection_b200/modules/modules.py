@@ -100,9 +100,11 @@ class FCNet(nn.Module):
     def prepared(self, dtype):
         return [prep_wn_linear(self._cache, m, dtype, tag=("wn", i)) for i, m in self.linears()]
 
-    def forward(self, x, mul=None, out_dtype=None):
+    def forward(self, x, mul=None, out_dtype=None, add=None, add_after_act=False):
         """x [..., in_dim] (CUDA).  ``mul`` (f32 [rows,out]) is an optional elementwise
-        multiplier fused into the LAST stage's epilogue (q ⊙ v of predictor.py:91)."""
+        multiplier fused into the LAST stage's epilogue (q ⊙ v of predictor.py:91); ``add`` (f32 [rows,out]) an
+        additive operand of that epilogue, before the multiplier and (``add_after_act``) after the ReLU
+        (q ⊙ (v + c) of predictor.py:131-134)."""
         _no_training(self)
         dtype = compute_dtype()
         lead = x.shape[:-1]
@@ -110,8 +112,8 @@ class FCNet(nn.Module):
         preps = self.prepared(dtype)
         for j, (W, s, b) in enumerate(preps):
             last = j == len(preps) - 1
-            h = ops.linear(h, W, s, b, relu=True, mul=mul if last else None,
-                           out_dtype=(out_dtype or dtype) if last else dtype)
+            h = ops.linear(h, W, s, b, relu=True, mul=mul if last else None, add=add if last else None,
+                           add_after_act=add_after_act and last, out_dtype=(out_dtype or dtype) if last else dtype)
         return h.reshape(*lead, h.shape[-1])
 
 

@@ -1,10 +1,10 @@
-"""Predictors — mirror of modules/predictor.py (BasePredictor :54-93, PredictorwithCaption :144-213) on the
-C-ABI kernels."""
+"""Predictors — mirror of modules/predictor.py (BasePredictor :54-93, BaseCaptionPredictor :95-140,
+PredictorwithCaption :144-213) on the C-ABI kernels."""
 import torch
 import torch.nn as nn
 
 from .. import compute_dtype, ops
-from .modules import FCNet, LReLUNet, CaptionEmbedding, as_compute, _no_training
+from .modules import FCNet, LReLUNet, CaptionEmbedding, SentenceEmbedding, as_compute, _no_training
 
 
 def set_predictor(predictor_type: str, v_dim: int, embed_dim: int, hidden_dim: int, ans_dim: int, device: str,
@@ -17,7 +17,8 @@ def set_predictor(predictor_type: str, v_dim: int, embed_dim: int, hidden_dim: i
                                     ans_dim=ans_dim, device=device, cls_layer=cls_layer, dropout=dropout,
                                     neg_slope=neg_slope).to(device)
     if predictor_type == 'base-cap':
-        raise NotImplementedError("predictor_type='base-cap' is outside the accelerated VQA forward path")
+        return BaseCaptionPredictor(v_dim=v_dim, embed_dim=embed_dim, hidden_dim=hidden_dim, ans_dim=ans_dim,
+                                    device=device, cls_layer=cls_layer, dropout=dropout).to(device)
     return None            # like the reference: unknown types (e.g. 'none') give no predictor
 
 
@@ -32,20 +33,41 @@ class BasePredictor(nn.Module):
         self.classifier = FCNet(in_dim=hidden_dim, mid_dim=2 * hidden_dim, out_dim=ans_dim, layer=cls_layer,
                                 dropout=dropout)
 
+    def _pooled(self, batch):
+        """Σ_K v (predictor.py:85)"""
+        if 'v_sum' in batch:                       # encoder already produced Σ_K (fused pooling kernels)
+            return batch['v_sum'].to(self.device)
+        v = batch['v'].to(self.device)
+        dtype = compute_dtype()
+        v = as_compute(v, dtype)
+        B, K, V = v.shape
+        ones = torch.zeros((B * K, 1), dtype=torch.float32, device=v.device)   # softmax(0)·K = 1
+        _, vs, _ = ops.attention_pool(ones, 0.0, v, False, True, False)         # (1/K) Σ_K v
+        return vs.float() * K
+
     def forward(self, batch):
         _no_training(self)
         q = batch['q'].to(self.device)
-        if 'v_sum' in batch:                       # encoder already produced Σ_K (fused pooling kernels)
-            v = batch['v_sum'].to(self.device)
-        else:
-            v = batch['v'].to(self.device)
-            dtype = compute_dtype()
-            v = as_compute(v, dtype)
-            B, K, V = v.shape
-            ones = torch.zeros((B * K, 1), dtype=torch.float32, device=v.device)   # softmax(0)·K = 1
-            _, vs, _ = ops.attention_pool(ones, 0.0, v, False, True, False)         # (1/K) Σ_K v
-            v = vs.float() * K
-        joint = self.v_net(v, mul=q.float().contiguous())        # ReLU(W v) ⊙ q   (predictor.py:88-91)
+        joint = self.v_net(self._pooled(batch), mul=q.float().contiguous())        # ReLU(W v) ⊙ q   (predictor.py:88-91)
+        return self.classifier(joint, out_dtype=torch.float32)
+
+
+class BaseCaptionPredictor(BasePredictor):
+    """BasePredictor + a caption embedding added to the visual one: joint = q ⊙ (c_net(GRU_last(c)) + v_net(Σ_K v))
+    (predictor.py:95-140).  The add and the ⊙ q are v_net's epilogue (add-after-activation, then mul)."""
+
+    def __init__(self, v_dim: int, embed_dim: int, hidden_dim: int, ans_dim: int, device: str, cls_layer: int = 2,
+                 dropout: float = 0.5):
+        super().__init__(v_dim, hidden_dim, ans_dim, device, cls_layer, dropout)
+        self.c_rnn = SentenceEmbedding(in_dim=embed_dim, hidden_dim=hidden_dim, rnn_layer=1, device=device, rnn_type='GRU')
+        self.c_net = FCNet(hidden_dim, hidden_dim, dropout=dropout)
+
+    def forward(self, batch):
+        _no_training(self)
+        q = batch['q'].to(self.device)
+        c = self.c_net(self.c_rnn(batch['c'].to(self.device)), out_dtype=torch.float32)       # [B,H] f32
+        v = self._pooled(batch)
+        joint = self.v_net(v, mul=q.float().contiguous(), add=c.contiguous(), add_after_act=True)   # q ⊙ (ReLU(W v) + c)
         return self.classifier(joint, out_dtype=torch.float32)
 
 

@@ -105,7 +105,7 @@ class Wrapper(nn.Module):
         from .attention import MultiplyAttention
         from .encoder import BaseEncoder
         return (type(self.encoder) is BaseEncoder and isinstance(self.encoder.attention, MultiplyAttention)
-                and isinstance(self.predictor, BasePredictor) and len(self.predictor.classifier.linears()) == 2
+                and type(self.predictor) is BasePredictor and len(self.predictor.classifier.linears()) == 2
                 and self.generator is None)
 
     def get_loss(self, batch):
@@ -137,7 +137,7 @@ class Wrapper(nn.Module):
 
     def forward_vqa(self, batch):
         target = batch['a'].float().to(self.device)
-        eng = self.engine() if isinstance(self.predictor, BasePredictor) else None
+        eng = self.engine() if type(self.predictor) is BasePredictor else None      # caption predictors: module-level path
         if eng is None or self.training:
             enc = self.encoder(batch)
             predict = self.predictor(enc)
