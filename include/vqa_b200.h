@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 5
+#define VQA_B200_ABI_VERSION 6
 
 typedef enum {
   VQA_OK = 0,
@@ -164,6 +164,26 @@ typedef struct {
 
 int vqa_gru_last_state(const vqa_gru_args* args, void* stream);
 size_t vqa_gru_workspace_bytes(int B, int T, int H, int E_pad, int dtype);
+
+/* ------------------------------------------------------------------------
+ * a7 (rnn_type='LSTM')  1-layer LSTM over dense inputs, h0 = c0 = 0
+ * replaces modules.py:121-130,139-159 (nn.LSTM, gate order [i;f;g;o]; SentenceEmbedding.forward_all /
+ * forward = output[:, -1]).  Per-step path: one GEMM for the input half of all steps, then per step one
+ * GEMM (recurrent half + the input half as its additive epilogue operand) and the gate kernel.
+ *   x [B*T, E_pad] (dtype, zero padded); w_ih [4H, E_pad], w_hh [4H, H] (dtype); biases f32 [4H]
+ *   outputs (at least one): out_all [B,T,H] (dtype) every hidden state; h_last f32 [B,H]
+ *   workspace: vqa_lstm_workspace_bytes(B,T,H,dtype) bytes.
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  int B, T, H, E_pad, dtype;
+  const void* d_x;
+  const void* d_w_ih;  const float* d_b_ih;
+  const void* d_w_hh;  const float* d_b_hh;
+  void* d_workspace;   size_t workspace_bytes;
+  float* d_h_last;     void* d_out_all;
+} vqa_lstm_args;
+int vqa_lstm_sequence(const vqa_lstm_args* args, void* stream);
+size_t vqa_lstm_workspace_bytes(int B, int T, int H, int dtype);
 
 /* ------------------------------------------------------------------------
  * k6  top-down attention pooling

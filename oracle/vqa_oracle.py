@@ -55,6 +55,8 @@ class Config:
     att_type: str = "new"           # 'new' = MultiplyAttention (CLI default main.py:67), 'base' = ConcatAttention
     predictor: str = "base"         # 'base' = BasePredictor, 'q-cap' = PredictorwithCaption (config 5)
     neg_slope: float = 0.01         # LeakyReLU slope of the q-cap predictor's own LReLUNets (predictor.py:159)
+    rnn_type: str = "GRU"           # question encoder cell (main.py:66): 'GRU' or 'LSTM'
+    rnn_layer: int = 1              # stacked layers of the question encoder (main.py:72)
     decoder: str = "none"           # 'base' = BaseDecoder caption head (generator.py:123-181; main.py:87 default)
     decoder_hidden_dim: int = 512   # main.py:88
 
@@ -73,6 +75,9 @@ SMALL_CONCAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_d
 FULL_CONCAT = Config(att_type="base")
 SMALL_QCAP = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, predictor="q-cap")
 FULL_QCAP = Config(predictor="q-cap")
+SMALL_GRU2 = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, rnn_layer=2)
+SMALL_LSTM2 = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, rnn_type="LSTM", rnn_layer=2)
+FULL_LSTM = Config(rnn_type="LSTM")
 SMALL_BASECAP = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, predictor="base-cap")
 FULL_BASECAP = Config(predictor="base-cap")
 SMALL_DECODER = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, decoder="base",
@@ -105,10 +110,12 @@ def make_weights(cfg: Config, seed: int = 1111, sharpen_att: float = 100.0,
     emb[cfg.ntoken].zero_()                       # padding_idx row (encoder.py:128)
     w["encoder.embedding.weight"] = emb
     kb = 1.0 / math.sqrt(H)
-    w["encoder.q_rnn.rnn.weight_ih_l0"] = _uniform(g, (3 * H, E), kb)
-    w["encoder.q_rnn.rnn.weight_hh_l0"] = _uniform(g, (3 * H, H), kb)
-    w["encoder.q_rnn.rnn.bias_ih_l0"] = _uniform(g, (3 * H,), kb)
-    w["encoder.q_rnn.rnn.bias_hh_l0"] = _uniform(g, (3 * H,), kb)
+    ng = 4 if cfg.rnn_type == "LSTM" else 3                 # gates per cell (nn.LSTM [i;f;g;o] / nn.GRU [r;z;n])
+    for l in range(cfg.rnn_layer):
+        w[f"encoder.q_rnn.rnn.weight_ih_l{l}"] = _uniform(g, (ng * H, E if l == 0 else H), kb)
+        w[f"encoder.q_rnn.rnn.weight_hh_l{l}"] = _uniform(g, (ng * H, H), kb)
+        w[f"encoder.q_rnn.rnn.bias_ih_l{l}"] = _uniform(g, (ng * H,), kb)
+        w[f"encoder.q_rnn.rnn.bias_hh_l{l}"] = _uniform(g, (ng * H,), kb)
 
     def wn_linear(prefix, out_dim, in_dim, gscale=1.0):
         b = 1.0 / math.sqrt(in_dim)
@@ -275,11 +282,39 @@ def fcnet1(x, W, prefix):
     return torch.relu(F.linear(x, wt, W[prefix + ".main.0.bias"]))
 
 
-def gru_all(x, W, prefix):
-    """nn.GRU(1 layer, batch_first, h0=0), every time step: ``output`` [B,T,H] of
+def lstm_all(x, W, prefix, layer=0):
+    """one nn.LSTM layer (batch_first, h0 = c0 = 0, modules.py:121-130,139-146), every time step.
+    Gate order [i; f; g; o]; c' = σ(f)c + σ(i)tanh(g); h' = σ(o)tanh(c')."""
+    w_ih, w_hh = W[prefix + f".weight_ih_l{layer}"], W[prefix + f".weight_hh_l{layer}"]
+    b_ih, b_hh = W[prefix + f".bias_ih_l{layer}"], W[prefix + f".bias_hh_l{layer}"]
+    B, T, _ = x.shape
+    Hd = w_hh.shape[1]
+    h = torch.zeros((B, Hd), dtype=x.dtype)
+    c = torch.zeros((B, Hd), dtype=x.dtype)
+    gi_all = F.linear(x, w_ih, b_ih)
+    outs = []
+    for t in range(T):
+        gates = gi_all[:, t] + F.linear(h, w_hh, b_hh)
+        i, f, g, o = gates[:, :Hd], gates[:, Hd:2 * Hd], gates[:, 2 * Hd:3 * Hd], gates[:, 3 * Hd:]
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        outs.append(h)
+    return torch.stack(outs, 1)
+
+
+def rnn_stack_last(x, W, prefix, rnn_type="GRU", n_layer=1):
+    """SentenceEmbedding.forward (modules.py:155-159): stacked nn.GRU / nn.LSTM layers (each layer reads the full
+    output sequence of the one below; inter-layer dropout is training-only), last time step of the top layer."""
+    for l in range(n_layer):
+        x = lstm_all(x, W, prefix, l) if rnn_type == "LSTM" else gru_all(x, W, prefix, l)
+    return x[:, -1]
+
+
+def gru_all(x, W, prefix, layer=0):
+    """one nn.GRU layer (batch_first, h0=0), every time step: ``output`` [B,T,H] of
     SentenceEmbedding.forward_all (modules.py:147-152); the final hidden state is output[:, -1]."""
-    w_ih, w_hh = W[prefix + ".weight_ih_l0"], W[prefix + ".weight_hh_l0"]
-    b_ih, b_hh = W[prefix + ".bias_ih_l0"], W[prefix + ".bias_hh_l0"]
+    w_ih, w_hh = W[prefix + f".weight_ih_l{layer}"], W[prefix + f".weight_hh_l{layer}"]
+    b_ih, b_hh = W[prefix + f".bias_ih_l{layer}"], W[prefix + f".bias_hh_l{layer}"]
     B, T, _ = x.shape
     Hd = w_hh.shape[1]
     h = torch.zeros((B, Hd), dtype=x.dtype)
@@ -316,9 +351,14 @@ def gru_last(x, W, prefix="encoder.q_rnn.rnn"):
 
 
 def question_embedding(q_tokens, W):
-    """embedding → GRU last state (encoder.py:159-160)."""
+    """embedding → RNN last state (encoder.py:159-160); cell type and depth are read off the parameter names/shapes."""
     emb = W["encoder.embedding.weight"][q_tokens]
-    return gru_last(emb, W)
+    p = "encoder.q_rnn.rnn"
+    n_layer = sum(1 for k in W if k.startswith(p + ".weight_hh_l"))
+    lstm = W[p + ".weight_hh_l0"].shape[0] == 4 * W[p + ".weight_hh_l0"].shape[1]
+    if n_layer == 1 and not lstm:
+        return gru_last(emb, W)
+    return rnn_stack_last(emb, W, p, "LSTM" if lstm else "GRU", n_layer)
 
 
 def multiply_attention_logits(v, q, W, prefix="encoder.attention"):

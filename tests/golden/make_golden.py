@@ -33,8 +33,8 @@ def build_reference(cfg: O.Config, W: dict):
     m = set_model(encoder_type="relation" if cfg.relation else "base",
                   predictor_type=cfg.predictor, decoder_type=cfg.decoder, ntoken=cfg.ntoken,
                   v_dim=cfg.v_dim, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim,
-                  decoder_hidden_dim=cfg.decoder_hidden_dim, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2,
-                  c_len=cfg.c_len, device="cpu", dropout=0.2, neg_slope=cfg.neg_slope, rnn_type="GRU",
+                  decoder_hidden_dim=cfg.decoder_hidden_dim, rnn_layer=cfg.rnn_layer, ans_dim=cfg.ans_dim, cls_layer=2,
+                  c_len=cfg.c_len, device="cpu", dropout=0.2, neg_slope=cfg.neg_slope, rnn_type=cfg.rnn_type,
                   att_type=cfg.att_type, conv_layer=cfg.conv_layer, conv_type="corr")
     sd = {k: v for k, v in W.items() if not k.startswith("gcn.")}
     m.load_state_dict(sd, strict=True)
@@ -198,6 +198,11 @@ def run_relation():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--rnn-only" in sys.argv:
+        run_model("gru2_small", O.SMALL_GRU2, 8, 1111, 9001)
+        run_model("lstm2_small", O.SMALL_LSTM2, 8, 1111, 9002)
+        run_model("lstm_full", O.FULL_LSTM, 4, 1111, 9003)
+        sys.exit(0)
     if "--basecap-only" in sys.argv:
         run_model("basecap_small", O.SMALL_BASECAP, 8, 1111, 8001)
         run_model("basecap_full", O.FULL_BASECAP, 4, 1111, 8002)
@@ -225,3 +230,6 @@ if __name__ == "__main__":
     run_decoder("decoder_full", O.FULL_DECODER, 5, 1111, 7002, 16)
     run_model("basecap_small", O.SMALL_BASECAP, 8, 1111, 8001)
     run_model("basecap_full", O.FULL_BASECAP, 4, 1111, 8002)
+    run_model("gru2_small", O.SMALL_GRU2, 8, 1111, 9001)
+    run_model("lstm2_small", O.SMALL_LSTM2, 8, 1111, 9002)
+    run_model("lstm_full", O.FULL_LSTM, 4, 1111, 9003)

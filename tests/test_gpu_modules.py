@@ -23,8 +23,8 @@ def build_model(cfg, W, device="cuda"):
     from vqa_collection_b200.modules.wrapper import set_model
     m = set_model(encoder_type="relation" if cfg.relation else "base", predictor_type=cfg.predictor, decoder_type="none",
                   ntoken=cfg.ntoken, v_dim=cfg.v_dim, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim,
-                  decoder_hidden_dim=0, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2, c_len=cfg.c_len, device=device,
-                  dropout=0.2, rnn_type="GRU", att_type=cfg.att_type, conv_layer=cfg.conv_layer, conv_type="corr")
+                  decoder_hidden_dim=0, rnn_layer=cfg.rnn_layer, ans_dim=cfg.ans_dim, cls_layer=2, c_len=cfg.c_len, device=device,
+                  dropout=0.2, rnn_type=cfg.rnn_type, att_type=cfg.att_type, conv_layer=cfg.conv_layer, conv_type="corr")
     m.load_state_dict({k: v for k, v in W.items() if not k.startswith("gcn.")}, strict=True)
     if cfg.relation:
         for i, layer in enumerate(m.encoder.spatial_encoder.gcn):
@@ -40,7 +40,7 @@ def _need_gpu():
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["updown_small", "regat_small", "updown_full", "regat_full", "concat_small",
-                                  "concat_full", "basecap_small", "basecap_full"])
+                                  "concat_full", "basecap_small", "basecap_full", "gru2_small", "lstm2_small", "lstm_full"])
 def test_wrapper_api_matches_reference(golden_dir, name, precision):
     import vqa_collection_b200 as pkg
     pkg.set_precision(precision)

@@ -160,3 +160,25 @@ def test_qcap_full_dims_matches_oracle(precision, B):
         assert torch.equal(predict.cpu().argmax(1)[safe], ref.argmax(1)[safe])
     finally:
         pkg.set_precision("bf16")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,E,H", [(5, 7, 64, 128), (33, 14, 320, 1024), (1, 1, 64, 64)])
+def test_lstm_sequence_matches_torch(ops, dtype, B, T, E, H):
+    """vqa_lstm_sequence (SentenceEmbedding with rnn_type='LSTM', modules.py:121-159) against torch.nn.LSTM on the CPU"""
+    torch.manual_seed(B * T + H)
+    ref = torch.nn.LSTM(E, H, num_layers=1, batch_first=True)
+    x = torch.rand((B, T, E)) - 0.5
+    wd = lambda t: t.detach().to(dtype)
+    with torch.no_grad():
+        ref.weight_ih_l0.copy_(wd(ref.weight_ih_l0).float())
+        ref.weight_hh_l0.copy_(wd(ref.weight_hh_l0).float())
+        want, _ = ref(wd(x).float())
+    out, h = ops.lstm_sequence(wd(x).cuda(), wd(ref.weight_ih_l0).cuda(), ref.bias_ih_l0.detach().cuda(),
+                               wd(ref.weight_hh_l0).cuda(), ref.bias_hh_l0.detach().cuda(), want_all=True, want_last=True)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert out.shape == (B, T, H) and relerr(out, want) < tol
+    assert relerr(h, want[:, -1]) < tol
+    _, h2 = ops.lstm_sequence(wd(x).cuda(), wd(ref.weight_ih_l0).cuda(), ref.bias_ih_l0.detach().cuda(),
+                              wd(ref.weight_hh_l0).cuda(), ref.bias_hh_l0.detach().cuda(), want_all=False, want_last=True)
+    assert relerr(h2, want[:, -1]) < tol

@@ -119,8 +119,14 @@ def test_unsupported_configurations_raise():
               decoder_hidden_dim=8, rnn_layer=1, ans_dim=4, cls_layer=2, c_len=5, device="cpu", att_type="new")
     with pytest.raises(NotImplementedError):                     # BUTDDecoder.decode returns None in the reference
         set_model(decoder_type="butd", **kw)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):                     # the caption head's cell is the GRUCell only
         set_model(decoder_type="base", rnn_type="LSTM", **kw)
+    # LSTM / stacked question encoders (main.py:66,72): the reference's parameter names, never on the fused engine / train step
+    m = set_model(decoder_type="none", rnn_type="LSTM", **{**kw, "rnn_layer": 2})
+    names = [k for k in m.state_dict() if k.startswith("encoder.q_rnn.rnn.")]
+    assert sorted(names) == sorted(f"encoder.q_rnn.rnn.{w}_l{l}" for l in (0, 1) for w in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+    assert m.state_dict()["encoder.q_rnn.rnn.weight_ih_l1"].shape == (32, 8) and m.engine() is None
+    assert not m.train_step_supported()
 
 
 def test_caption_head_parameter_names_and_checkpoint_loading():

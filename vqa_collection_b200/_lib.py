@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
 
 VQA_F32, VQA_BF16 = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -118,6 +118,15 @@ class TrainArgs(C.Structure):
     ]
 
 
+class LstmArgs(C.Structure):
+    _fields_ = [
+        ("B", c_int), ("T", c_int), ("H", c_int), ("E_pad", c_int), ("dtype", c_int),
+        ("d_x", c_void_p), ("d_w_ih", c_void_p), ("d_b_ih", c_void_p), ("d_w_hh", c_void_p), ("d_b_hh", c_void_p),
+        ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("d_h_last", c_void_p), ("d_out_all", c_void_p),
+    ]
+
+
 OPTIM_MAX_TENSORS = 64
 
 
@@ -154,6 +163,8 @@ SYMBOLS = {
     "vqa_linear_part_width": (c_int, [c_int]),
     "vqa_gru_last_state": (c_int, [C.POINTER(GruArgs), c_void_p]),
     "vqa_gru_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "vqa_lstm_sequence": (c_int, [C.POINTER(LstmArgs), c_void_p]),
+    "vqa_lstm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "vqa_attention_pool": (c_int, [c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "vqa_graph_attention": (c_int, [C.POINTER(GraphAttentionArgs), c_void_p]),

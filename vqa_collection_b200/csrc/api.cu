@@ -60,6 +60,7 @@ int attention_pool(const float*, int, float, const void*, int, int, int, int, fl
 int argmax_rows(const float*, int, int, int, int64_t*, cudaStream_t);
 int embedding_gather(const int64_t*, int, int, int, int, const void*, void*, cudaStream_t);
 int gru_gate(const float*, const float*, int, int, int, int, const float*, float*, void*, int, int, cudaStream_t);
+int lstm_gate(const float*, int, int, float*, float*, void*, int, int, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
 int cast_bf16_to_f32(const void*, float*, size_t, cudaStream_t);
 int graph_attention(const vqa_graph_attention_args&, cudaStream_t);
@@ -191,6 +192,55 @@ static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
   return VQA_OK;
 }
 
+// ---- LSTM (rnn_type='LSTM' of SentenceEmbedding, modules.py:121-130): generic per-step path -----------------
+// gi = X W_ihᵀ + b_ih for all T steps in one GEMM; per step ONE GEMM (h W_hhᵀ + b_hh + gi[:, t] as the additive
+// epilogue operand) and the gate kernel.  h0 = c0 = 0 (modules.py:139-146).
+struct LstmWs { float* gi; float* gates; float* c; void* h_lp; size_t bytes; };
+static LstmWs carve_lstm(void* base, int B, int T, int H, int dtype) {
+  LstmWs w; size_t off = 0; char* p = (char*)base;
+  auto take = [&](size_t n) { void* r = p ? p + off : nullptr; off += align_up(n, 256); return r; };
+  w.gi = (float*)take((size_t)B * T * 4 * H * 4);
+  w.gates = (float*)take((size_t)B * 4 * H * 4);
+  w.c = (float*)take((size_t)B * H * 4);
+  w.h_lp = take((size_t)B * H * elem_size(dtype));
+  w.bytes = off;
+  return w;
+}
+static int lstm_sequence(const vqa_lstm_args& a, cudaStream_t s) {
+  VQA_REQUIRE(a.d_x && a.d_w_ih && a.d_w_hh && a.d_b_ih && a.d_b_hh && (a.d_h_last || a.d_out_all),
+              "vqa_lstm_sequence: NULL pointer");
+  VQA_REQUIRE(a.B >= 0 && a.T >= 1 && a.H >= 1 && a.E_pad >= 1, "vqa_lstm_sequence: bad dims");
+  const LstmWs need = carve_lstm(nullptr, a.B, a.T, a.H, a.dtype);
+  VQA_REQUIRE(a.d_workspace && a.workspace_bytes >= need.bytes, "vqa_lstm_sequence: workspace %zu < %zu bytes",
+              a.workspace_bytes, need.bytes);
+  if (a.B == 0) return VQA_OK;
+  const LstmWs w = carve_lstm(a.d_workspace, a.B, a.T, a.H, a.dtype);
+  const size_t es = elem_size(a.dtype);
+  int rc;
+  vqa_linear_args gi{};
+  gi.d_A = a.d_x; gi.lda = a.E_pad; gi.d_W = a.d_w_ih; gi.ldw = a.E_pad;
+  gi.M = a.B * a.T; gi.N = 4 * a.H; gi.K = a.E_pad; gi.dtype = a.dtype;
+  gi.d_bias = a.d_b_ih; gi.d_out = w.gi; gi.ldo = 4 * a.H; gi.out_dtype = VQA_F32; gi.mul_row_div = 1; gi.add_row_div = 1;
+  if ((rc = linear_dispatch(gi, s))) return rc;
+  VQA_CUDA_CHECK(cudaMemsetAsync(w.c, 0, (size_t)a.B * a.H * 4, s));
+  VQA_CUDA_CHECK(cudaMemsetAsync(w.h_lp, 0, (size_t)a.B * a.H * es, s));
+  for (int t = 0; t < a.T; ++t) {
+    const bool from_all = a.d_out_all && t > 0;
+    vqa_linear_args gh{};
+    gh.d_A = from_all ? (const void*)((const char*)a.d_out_all + (size_t)(t - 1) * a.H * es) : w.h_lp;
+    gh.lda = from_all ? a.T * a.H : a.H;
+    gh.d_W = a.d_w_hh; gh.ldw = a.H; gh.M = a.B; gh.N = 4 * a.H; gh.K = a.H; gh.dtype = a.dtype;
+    gh.d_bias = a.d_b_hh; gh.d_add = w.gi + (size_t)t * 4 * a.H; gh.ld_add = a.T * 4 * a.H; gh.add_row_div = 1;
+    gh.d_out = w.gates; gh.ldo = 4 * a.H; gh.out_dtype = VQA_F32; gh.mul_row_div = 1;
+    if ((rc = linear_dispatch(gh, s))) return rc;
+    const bool last = (t == a.T - 1);
+    void* lp = a.d_out_all ? (void*)((char*)a.d_out_all + (size_t)t * a.H * es) : w.h_lp;
+    if ((rc = lstm_gate(w.gates, a.B, a.H, w.c, last ? a.d_h_last : nullptr, lp, a.d_out_all ? a.T * a.H : a.H, a.dtype, s)))
+      return rc;
+  }
+  return VQA_OK;
+}
+
 }  // namespace vqa
 
 using namespace vqa;
@@ -268,6 +318,13 @@ int vqa_gru_last_state(const vqa_gru_args* args, void* stream) {
   if (int rc = require_sm100()) return rc;
   VQA_REQUIRE(args, "vqa_gru_last_state: NULL args");
   return gru_last_state(*args, (cudaStream_t)stream);
+}
+
+size_t vqa_lstm_workspace_bytes(int B, int T, int H, int dtype) { return carve_lstm(nullptr, B, T, H, dtype).bytes; }
+int vqa_lstm_sequence(const vqa_lstm_args* args, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  VQA_REQUIRE(args, "vqa_lstm_sequence: NULL args");
+  return lstm_sequence(*args, (cudaStream_t)stream);
 }
 
 int vqa_attention_pool(const float* d_logit_parts, int n_parts, float logit_bias, const void* d_x, int B,

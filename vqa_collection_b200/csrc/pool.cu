@@ -380,6 +380,42 @@ int gru_gate(const float* gi, const float* gh, int B, int H, int T, int t, const
 }
 
 // ---------------------------------------------------------------------------
+// LSTM gate update (torch LSTM semantics, modules.py:123-130 with rnn_type='LSTM'), gate order [i; f; g; o]:
+//   c' = σ(f) ⊙ c + σ(i) ⊙ tanh(g),  h' = σ(o) ⊙ tanh(c')     (gates = W_ih x + b_ih + W_hh h + b_hh, all four summed
+//   before this kernel: the input half enters the recurrent GEMM as its additive epilogue operand)
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+lstm_gate_kernel(const float* __restrict__ gates, int B, int H, float* c, float* h_out, T* __restrict__ h_lp, int ld_lp) {
+  const int total = B * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / H, j = i - b * H;
+    const float* g = gates + (size_t)b * 4 * H;
+    const float ig = 1.f / (1.f + expf(-g[j]));
+    const float fg = 1.f / (1.f + expf(-g[H + j]));
+    const float gg = tanhf(g[2 * H + j]);
+    const float og = 1.f / (1.f + expf(-g[3 * H + j]));
+    const float cn = fg * c[i] + ig * gg;
+    const float hn = og * tanhf(cn);
+    c[i] = cn;
+    if (h_out) h_out[i] = hn;
+    h_lp[(size_t)b * ld_lp + j] = Elem<T>::from_f(hn);
+  }
+}
+
+int lstm_gate(const float* gates, int B, int H, float* c, float* h_out, void* h_lp, int ld_lp, int dtype, cudaStream_t s) {
+  const int total = B * H;
+  int grid = (total + 255) / 256;
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  if (dtype == VQA_BF16)
+    lstm_gate_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(gates, B, H, c, h_out, (__nv_bfloat16*)h_lp, ld_lp);
+  else
+    lstm_gate_kernel<float><<<grid, 256, 0, s>>>(gates, B, H, c, h_out, (float*)h_lp, ld_lp);
+  VQA_LAUNCH_CHECK();
+  return VQA_OK;
+}
+
+// ---------------------------------------------------------------------------
 // a14 / f4: VQA soft score of the chosen answers (wrapper.py:16-22: one_hot(label) ⊙ target) without the
 // zeros → scatter → multiply round trips: one block per question writes its dense row (optional) and
 // score_row[b] = target[b, label[b]]; a single warp then sums the rows in a fixed order (deterministic).

@@ -172,60 +172,91 @@ class DotProduct(nn.Module):
 
 
 class SentenceEmbedding(nn.Module):
-    """nn.GRU wrapper returning the last time step (modules.py:98-163).  Only the
-    configuration on the hot path is built: GRU, 1 layer, unidirectional."""
+    """nn.GRU / nn.LSTM wrapper returning the last time step (modules.py:98-163), unidirectional.
+    1-layer GRU (the main.py defaults) runs the persistent fused tcgen05 kernel; stacked layers run one sequence
+    kernel per layer (each layer reads the full output sequence of the one below); LSTM layers take the per-step
+    path of vqa_lstm_sequence."""
 
     def __init__(self, in_dim: int, hidden_dim: int, device: str, rnn_layer: int = 1, dropout: float = 0.0,
                  rnn_type: str = 'LSTM', bidirect: bool = False):
         super().__init__()
         assert rnn_type == 'LSTM' or rnn_type == 'GRU'
-        if rnn_type != 'GRU' or rnn_layer != 1 or bidirect:
-            raise NotImplementedError("vqa_collection_b200: only rnn_type='GRU', rnn_layer=1, unidirectional "
-                                      "is on the accelerated path (main.py:75-76 defaults)")
-        self.rnn = nn.GRU(input_size=in_dim, hidden_size=hidden_dim, num_layers=1, dropout=dropout,
-                          bidirectional=False, batch_first=True)
+        if bidirect:
+            raise NotImplementedError("vqa_collection_b200: bidirectional sentence encoders are never built by the "
+                                      "reference's models (encoder.py:131-138) and are not on the accelerated path")
+        rnn_cls = nn.LSTM if rnn_type == 'LSTM' else nn.GRU
+        self.rnn = rnn_cls(input_size=in_dim, hidden_size=hidden_dim, num_layers=rnn_layer, dropout=dropout,
+                           bidirectional=False, batch_first=True)
         self.in_dim, self.hidden_dim, self.rnn_layer = in_dim, hidden_dim, rnn_layer
         self.rnn_type, self.ndirections, self.device = rnn_type, 1, device
         self._cache = PreparedCache()
 
-    def prepared(self, dtype):
+    def prepared(self, dtype, layer=0):
         r = self.rnn
+        w_ih_p, w_hh_p = getattr(r, f"weight_ih_l{layer}"), getattr(r, f"weight_hh_l{layer}")
+        b_ih_p, b_hh_p = getattr(r, f"bias_ih_l{layer}"), getattr(r, f"bias_hh_l{layer}")
 
         def build():
-            E = r.weight_ih_l0.shape[1]
+            E = w_ih_p.shape[1]
             E_pad = (E + 63) // 64 * 64
-            w_ih = torch.zeros((r.weight_ih_l0.shape[0], E_pad), dtype=dtype, device=r.weight_ih_l0.device)
-            w_ih[:, :E] = r.weight_ih_l0.detach().to(dtype)
-            b_ih, b_hh = r.bias_ih_l0.detach().float().contiguous(), r.bias_hh_l0.detach().float().contiguous()
-            w_hh = r.weight_hh_l0.detach().to(dtype).contiguous()
-            packed = pack_gru(w_ih, w_hh, b_ih, b_hh) if dtype == torch.bfloat16 else None
+            w_ih = torch.zeros((w_ih_p.shape[0], E_pad), dtype=dtype, device=w_ih_p.device)
+            w_ih[:, :E] = w_ih_p.detach().to(dtype)
+            b_ih, b_hh = b_ih_p.detach().float().contiguous(), b_hh_p.detach().float().contiguous()
+            w_hh = w_hh_p.detach().to(dtype).contiguous()
+            packed = pack_gru(w_ih, w_hh, b_ih, b_hh) if (dtype == torch.bfloat16 and self.rnn_type == 'GRU') else None
             return (w_ih, b_ih, w_hh, b_hh, E_pad, packed)
-        return self._cache.get(("gru", dtype), (r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0), build)
+        return self._cache.get(("rnn", dtype, layer), (w_ih_p, w_hh_p, b_ih_p, b_hh_p), build)
+
+    def _simple(self):
+        return self.rnn_type == 'GRU' and self.rnn_layer == 1
+
+    def _pad_input(self, batch, E_pad, dtype):
+        B, T, E = batch.shape
+        if E == E_pad and batch.dtype == dtype and batch.is_contiguous():
+            return batch
+        x = torch.zeros((B, T, E_pad), dtype=dtype, device=batch.device)
+        x[:, :, :E] = batch.to(dtype)
+        return x
+
+    def _layer(self, x, dtype, layer, want_all, want_last):
+        """one layer over [B,T,E_pad] → (all states [B,T,H] or None, f32 last state or None)"""
+        w_ih, b_ih, w_hh, b_hh, E_pad, packed = self.prepared(dtype, layer)
+        x = self._pad_input(x, E_pad, dtype)
+        if self.rnn_type == 'LSTM':
+            return ops.lstm_sequence(x, w_ih, b_ih, w_hh, b_hh, want_all=want_all, want_last=want_last)
+        if want_last:
+            out, h = ops.gru_sequence(x, w_ih, b_ih, w_hh, b_hh, packed=packed, want_last=True)
+            return (out if want_all else None), h
+        return ops.gru_sequence(x, w_ih, b_ih, w_hh, b_hh, packed=packed), None
 
     def forward_tokens(self, tokens, embedding_weight):
-        """fused embedding gather + GRU (encoder.py:159-160) → f32 [B,H]"""
+        """embedding gather + RNN (encoder.py:159-160) → f32 [B,H]; fused in one kernel for the 1-layer GRU"""
+        if not self._simple():
+            return self.forward(torch.nn.functional.embedding(tokens, embedding_weight.detach()))
         dtype = compute_dtype()
         w_ih, b_ih, w_hh, b_hh, E_pad, packed = self.prepared(dtype)
         emb = self._cache.get(("emb", dtype), (embedding_weight,), lambda: _pad_emb(embedding_weight, E_pad, dtype))
         return ops.gru_last_state(tokens.contiguous(), emb, w_ih, b_ih, w_hh, b_hh, packed=packed)
 
     def forward_all(self, batch):
-        """batch: [B,T,in_dim] → every hidden state [B,T,H] in the compute dtype (modules.py:147-152)"""
+        """batch: [B,T,in_dim] → every hidden state of the top layer [B,T,H] in the compute dtype (modules.py:147-152)"""
         _no_training(self)
         dtype = compute_dtype()
-        w_ih, b_ih, w_hh, b_hh, E_pad, packed = self.prepared(dtype)
-        B, T, E = batch.shape
-        if E == E_pad and batch.dtype == dtype and batch.is_contiguous():
-            x = batch
-        else:
-            x = torch.zeros((B, T, E_pad), dtype=dtype, device=batch.device)
-            x[:, :, :E] = batch.to(dtype)
-        return ops.gru_sequence(x, w_ih, b_ih, w_hh, b_hh, packed=packed)
+        x = batch
+        for layer in range(self.rnn_layer):
+            x, _ = self._layer(x, dtype, layer, True, False)
+        return x
 
     def forward(self, batch):
-        """batch: already-embedded [B,T,in_dim] (modules.py:155-159) → last step [B,H] f32"""
+        """batch: already-embedded [B,T,in_dim] (modules.py:155-159) → last step of the top layer, [B,H] f32"""
         _no_training(self)
         dtype = compute_dtype()
+        if not self._simple():
+            x = batch
+            for layer in range(self.rnn_layer - 1):
+                x, _ = self._layer(x, dtype, layer, True, False)
+            _, h = self._layer(x, dtype, self.rnn_layer - 1, False, True)
+            return h
         w_ih, b_ih, w_hh, b_hh, E_pad, packed = self.prepared(dtype)
         B, T, E = batch.shape
         table = torch.zeros((B * T, E_pad), dtype=dtype, device=batch.device)

@@ -83,6 +83,8 @@ class Wrapper(nn.Module):
         key = (get_precision(),) + tuple((p._version, p.data_ptr()) for p in params)
         if self._engine is None or self._engine_key != key:
             relation = isinstance(self.encoder, RelationEncoder)
+            if not self.encoder.q_rnn._simple():
+                return None                                  # LSTM / stacked question encoders: module-level path
             if relation and len(self.encoder.spatial_encoder.gcn) != 1:
                 return None                                  # multi-layer GCN: module-level path
             if len(self.predictor.classifier.linears()) != 2:
@@ -106,7 +108,7 @@ class Wrapper(nn.Module):
         from .encoder import BaseEncoder
         return (type(self.encoder) is BaseEncoder and isinstance(self.encoder.attention, MultiplyAttention)
                 and type(self.predictor) is BasePredictor and len(self.predictor.classifier.linears()) == 2
-                and self.generator is None)
+                and self.generator is None and self.encoder.q_rnn._simple())
 
     def get_loss(self, batch):
         """wrapper.py:76-105.  One C call runs forward + loss + backward (vqa_updown_train_step); the returned

@@ -236,6 +236,35 @@ def gru_sequence(x, w_ih, b_ih, w_hh, b_hh, packed=None, want_last=False):
     return (out, h) if want_last else out
 
 
+def lstm_sequence(x, w_ih, b_ih, w_hh, b_hh, want_all=True, want_last=False):
+    """1-layer LSTM over dense inputs, h0 = c0 = 0 (SentenceEmbedding with rnn_type='LSTM', modules.py:121-159).
+
+    x [B,T,E_pad] (E_pad = w_ih.shape[1], zero padded); w_ih [4H,E_pad], w_hh [4H,H] in x.dtype; biases f32 [4H].
+    Returns (every hidden state [B,T,H] in x.dtype or None, f32 last state [B,H] or None)."""
+    lib = L.load()
+    _require(x, None, "x")
+    _require(w_ih, x.dtype, "w_ih")
+    _require(w_hh, x.dtype, "w_hh")
+    _require(b_ih, torch.float32, "b_ih")
+    _require(b_hh, torch.float32, "b_hh")
+    B, T, E_pad = x.shape
+    H = w_hh.shape[1]
+    if w_ih.shape != (4 * H, E_pad) or w_hh.shape != (4 * H, H) or not (want_all or want_last):
+        raise ValueError("lstm_sequence: weight shapes do not match")
+    code = dtype_code(x.dtype)
+    ws_bytes = lib.vqa_lstm_workspace_bytes(B, T, H, code)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=x.device)
+    out = torch.empty((B, T, H), dtype=x.dtype, device=x.device) if want_all else None
+    h = torch.empty((B, H), dtype=torch.float32, device=x.device) if want_last else None
+    a = L.LstmArgs()
+    a.B, a.T, a.H, a.E_pad, a.dtype = B, T, H, E_pad, code
+    a.d_x, a.d_w_ih, a.d_b_ih, a.d_w_hh, a.d_b_hh = x.data_ptr(), w_ih.data_ptr(), b_ih.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr()
+    a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+    a.d_h_last, a.d_out_all = _ptr(h), _ptr(out)
+    L.check(lib.vqa_lstm_sequence(C.byref(a), _stream()))
+    return out, h
+
+
 def caption_gate_scale(out_w, p, r, want_a=False):
     """a = σ(h_w⊙p + h_w⊙r), h_w = out_w[:, -1]; returns a[:, None, :] ⊙ out_w (modules.py:225-243,294-295)."""
     lib = L.load()
