@@ -150,3 +150,61 @@ def test_dropout_is_deterministic_and_unbiased():
     assert float(l0) != float(l2)
     clean, _, _ = run_step(cfg, W, batch, "fp32")
     assert abs(float(l0) - float(clean)) < 0.5 * abs(float(clean))       # same ballpark as the dropout-free loss
+
+
+def test_train_loop_with_fused_optimizer_and_gradient_accumulation():
+    """(1) train.py:99-113 with the library's one-launch Adamax / clip_grad_norm_ follows the same loss trajectory as with
+    torch's own; (2) the flat gradient buffer is never reused while something still depends on it: two get_loss calls
+    before one backward, and a backward without zero_grad (accumulation), give the gradients torch semantics demand."""
+    import vqa_collection_b200 as pkg
+    from vqa_collection_b200 import optim as fused
+    from vqa_collection_b200.modules.wrapper import set_model
+    cfg = O.SMALL
+    W = O.make_weights(cfg, 1111)
+    pkg.set_precision("fp32")
+    try:
+        def build():
+            m = set_model(encoder_type="base", predictor_type="base", decoder_type="none", ntoken=cfg.ntoken, v_dim=cfg.v_dim,
+                          embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2,
+                          c_len=20, device="cuda", dropout=0.0, rnn_type="GRU", att_type="new", conv_layer=1, conv_type="corr")
+            m.load_state_dict(W, strict=True)
+            m.encoder.attention.dropout.p = 0.0
+            return m.train()
+        batch, batch2 = O.make_batch(cfg, 32, 77), O.make_batch(cfg, 32, 78)
+        runs = []
+        for Adamax, clip in ((fused.Adamax, fused.clip_grad_norm_), (torch.optim.Adamax, torch.nn.utils.clip_grad_norm_)):
+            m = build()
+            opt = Adamax([{'params': m.encoder.parameters()}, {'params': m.predictor.parameters(), 'lr': 0.004}], lr=0.002)
+            losses = []
+            for _ in range(5):
+                loss, _ = m.get_loss(batch)
+                loss.backward()
+                clip(m.parameters(), 0.25)
+                opt.step()
+                opt.zero_grad()
+                losses.append(loss.item())
+            runs.append(losses)
+        assert np.allclose(runs[0], runs[1], rtol=1e-4), runs
+        # (2) reference gradients of each batch alone
+        m = build()
+        def grads_of(b):
+            m.zero_grad()
+            l, _ = m.get_loss(b)
+            l.backward()
+            return {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+        g1, g2 = grads_of(batch), grads_of(batch2)
+        m.zero_grad()
+        l1, _ = m.get_loss(batch)
+        l2, _ = m.get_loss(batch2)                                  # second forward before the first backward
+        (l1 + l2).backward()
+        for n, p in m.named_parameters():
+            assert torch.allclose(p.grad, g1[n] + g2[n], rtol=1e-5, atol=1e-7), n
+        m.zero_grad()
+        la, _ = m.get_loss(batch)
+        la.backward()
+        lb, _ = m.get_loss(batch2)                                  # no zero_grad in between: .grad accumulates
+        lb.backward()
+        for n, p in m.named_parameters():
+            assert torch.allclose(p.grad, g1[n] + g2[n], rtol=1e-5, atol=1e-7), n
+    finally:
+        pkg.set_precision("bf16")

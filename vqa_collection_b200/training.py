@@ -91,8 +91,10 @@ class UpDownTrainStep(torch.autograd.Function):
         # autograd without copies): reuse the buffer only when no parameter's .grad aliases it (i.e. after zero_grad)
         alias = fg is not None and any(p.grad is not None and p.grad.untyped_storage().data_ptr() ==
                                        fg.flat.untyped_storage().data_ptr() for p in ctx_params)
-        if fg is None or alias or not fg.matches(shapes, dev):
+        # ... and only when no earlier get_loss still waits for its backward() (two losses summed before one backward)
+        if fg is None or alias or getattr(fg, "pending", False) or not fg.matches(shapes, dev):
             fg = _FLAT[dev] = FlatGradients(shapes, dev)
+        fg.pending = True
         grads = fg.views
         a.p_emb, a.p_w_ih, a.p_w_hh, a.p_b_ih, a.p_b_hh = (p.data_ptr() for p in params[:5])
         a.g_emb, a.g_w_ih, a.g_w_hh, a.g_b_ih, a.g_b_hh = (g.data_ptr() for g in grads[:5])
@@ -116,6 +118,7 @@ class UpDownTrainStep(torch.autograd.Function):
     def backward(ctx, g_loss, _g_logits):
         fg = ctx.fg
         ctx.fg = None
+        fg.pending = False
         if ctx.work is not None:
             ctx.work.wait()
         # ONE pass scales the whole flat buffer by the incoming gradient (1 after loss.backward()); the parameters then
