@@ -79,3 +79,24 @@ big = torch.from_numpy(O.make_boxes(1 << 18, 36, 4)).to(dev)
 timeit("relation_labels B=262144", lambda: ops.relation_labels(big, 640, 480), reps=10, bytes_=(1 << 18) * 1872)
 xf = torch.rand((B, 36, 2048), device=dev)
 timeit("cast f32->bf16 (B*36*2048)", lambda: ops.cast_to_bf16(xf), bytes_=B * 36 * 2048 * 6)
+
+# ---- optimizer side of the training step (csrc/optim.cu): all 26 parameter tensors of the Up-Down model in one launch
+from vqa_collection_b200 import optim as fused
+Wf = O.make_weights(O.FULL, 1111)
+params = [torch.nn.Parameter(v.clone().float().to(dev)) for v in Wf.values()]
+n_par = sum(p.numel() for p in params)
+for p in params:
+    p.grad = torch.randn_like(p) * 1e-3
+opt = fused.Adamax(params, lr=0.002)
+opt.step()
+timeit(f"adamax, {len(params)} tensors / {n_par / 1e6:.1f} M parameters", lambda: opt.step(), bytes_=n_par * 28)
+timeit("clip_grad_norm_ (norm + finalize + scale)", lambda: fused.clip_grad_norm_(params, 0.25), bytes_=n_par * 12)
+opt2 = torch.optim.Adamax(params, lr=0.002)
+opt2.step()
+timeit("torch.optim.Adamax (same tensors)", lambda: opt2.step(), bytes_=n_par * 28)
+timeit("torch clip_grad_norm_ (same tensors)", lambda: torch.nn.utils.clip_grad_norm_(params, 0.25), bytes_=n_par * 12)
+# caption head: one step's attention logits from the stored projection (B=128 captions, Hd=512)
+proj = torch.rand((1024 * 36, 512), device=dev).to(torch.bfloat16)
+qd = torch.rand((1024, 512), device=dev)
+wd_ = torch.rand((512,), device=dev)
+timeit("attention_logits B=1024 Hd=512", lambda: ops.attention_logits(proj, qd, wd_, 36, 0), bytes_=1024 * 36 * 512 * 2)
