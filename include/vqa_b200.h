@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 6
+#define VQA_B200_ABI_VERSION 7
 
 typedef enum {
   VQA_OK = 0,
@@ -291,6 +291,10 @@ int vqa_attention_logits(const void* d_proj, int ldp, const float* d_q, int ldq,
                          int Hd, int mode, int dtype, float* d_logits, void* stream);
 int vqa_gru_cell(const float* d_gi, const float* d_gh, const float* d_h_prev, int B, int H, int dtype,
                  float* d_h_out, void* d_h_lp, int ld_lp, void* stream);
+/*  vqa_lstm_cell         nn.LSTMCell's gate update: gates f32 [B,4H] = W_ih x + b_ih + W_hh h + b_hh ([i;f;g;o]);
+ *      c f32 [B,H] updated in place; h_out f32 [B,H] (optional); h_lp [B, ld_lp] (dtype). */
+int vqa_lstm_cell(const float* d_gates, int B, int H, int dtype, float* d_c, float* d_h_out, void* d_h_lp, int ld_lp,
+                  void* stream);
 
 /*  vqa_caption_decode_steps  replaces the time loop of DecoderModule.forward (generator.py:99-111) around
  *      BaseDecoder.decode (:168-181) in ONE call: T teacher-forced steps, step t on the first h_batches[t]
@@ -314,6 +318,9 @@ typedef struct {
   const void* d_w_att; const void* d_w_hh; const float* d_b_hh;
   void* d_h_all; float* d_h; const void* d_h0_lp;
   void* d_workspace; size_t workspace_bytes;
+  /* rnn_type: 0 = nn.GRUCell (gate blocks of 3Hd: gi_prev [B, T*3Hd], w_att [3Hd,V], w_hh [3Hd,Hd]);
+   *           1 = nn.LSTMCell (4Hd everywhere, gate order [i;f;g;o]); d_c f32 [B,Hd]: cell state, in/out */
+  int cell; float* d_c;
 } vqa_caption_decode_args;
 size_t vqa_caption_decode_workspace_bytes(int B, int K, int V, int Hd, int dtype);
 int vqa_caption_decode_steps(const vqa_caption_decode_args* args, void* stream);

@@ -83,6 +83,8 @@ FULL_BASECAP = Config(predictor="base-cap")
 SMALL_DECODER = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, decoder="base",
                        decoder_hidden_dim=64)
 FULL_DECODER = Config(decoder="base")
+SMALL_DECODER_LSTM = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, decoder="base",
+                            decoder_hidden_dim=64, rnn_type="LSTM")
 
 
 def _uniform(gen, shape, bound):
@@ -187,10 +189,10 @@ def make_weights(cfg: Config, seed: int = 1111, sharpen_att: float = 100.0,
         # Drawn last so that every earlier tensor is the same with and without the caption head.
         Hd = cfg.decoder_hidden_dim
         kd = 1.0 / math.sqrt(Hd)
-        w["generator.rnn.weight_ih"] = _uniform(g, (3 * Hd, E + V), kd)
-        w["generator.rnn.weight_hh"] = _uniform(g, (3 * Hd, Hd), kd)
-        w["generator.rnn.bias_ih"] = _uniform(g, (3 * Hd,), kd)
-        w["generator.rnn.bias_hh"] = _uniform(g, (3 * Hd,), kd)
+        w["generator.rnn.weight_ih"] = _uniform(g, (ng * Hd, E + V), kd)       # nn.GRUCell / nn.LSTMCell (rnn_type)
+        w["generator.rnn.weight_hh"] = _uniform(g, (ng * Hd, Hd), kd)
+        w["generator.rnn.bias_ih"] = _uniform(g, (ng * Hd,), kd)
+        w["generator.rnn.bias_hh"] = _uniform(g, (ng * Hd,), kd)
         if cfg.att_type == "new":
             wn_linear("generator.attention.W_v.main.0", Hd, V)
             wn_linear("generator.attention.W_q.main.0", Hd, Hd)
@@ -528,12 +530,26 @@ def gru_cell(x, h, W, prefix):
     return (1.0 - z) * n + z * h
 
 
-def base_decoder_step(v, prev, h, W, prefix="generator"):
-    """BaseDecoder.decode (generator.py:168-181), rnn_type='GRU', dropout = identity (eval):
-    att = attention(v, h); att_v = Σ_K att·v; h' = GRUCell([prev; att_v], h); word = Linear(h')."""
+def lstm_cell(x, h, c, W, prefix):
+    """nn.LSTMCell: gate order [i; f; g; o]; c' = σ(f)c + σ(i)tanh(g); h' = σ(o)tanh(c')."""
+    Hd = h.shape[1]
+    gates = F.linear(x, W[prefix + ".weight_ih"], W[prefix + ".bias_ih"]) + F.linear(h, W[prefix + ".weight_hh"], W[prefix + ".bias_hh"])
+    i, f, g, o = gates[:, :Hd], gates[:, Hd:2 * Hd], gates[:, 2 * Hd:3 * Hd], gates[:, 3 * Hd:]
+    c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+    return torch.sigmoid(o) * torch.tanh(c), c
+
+
+def base_decoder_step(v, prev, h, W, prefix="generator", c=None):
+    """BaseDecoder.decode (generator.py:168-181), dropout = identity (eval):
+    att = attention(v, h); att_v = Σ_K att·v; h' = GRUCell([prev; att_v], h); word = Linear(h').
+    With ``c`` (rnn_type='LSTM'): (h', c') = LSTMCell([prev; att_v], (h, c)) and the return value is ((h', c'), word, att)."""
     att = torch.softmax(attention_logits(v, h, W, prefix + ".attention"), dim=1)
     att_v = (att * v).sum(1)
-    h = gru_cell(torch.cat([prev, att_v], dim=1), h, W, prefix + ".rnn")
+    x = torch.cat([prev, att_v], dim=1)
+    if c is not None:
+        h, c = lstm_cell(x, h, c, W, prefix + ".rnn")
+        return (h, c), F.linear(h, W[prefix + ".fcnet.weight"], W[prefix + ".fcnet.bias"]), att
+    h = gru_cell(x, h, W, prefix + ".rnn")
     return h, F.linear(h, W[prefix + ".fcnet.weight"], W[prefix + ".fcnet.bias"]), att
 
 
@@ -547,10 +563,14 @@ def base_decoder_forward(enc, W, cfg: Config, prefix="generator"):
     v, caption, target = enc["v"][sort_id], enc["c"][sort_id], enc["c_target"][sort_id]
     decode_len = (cap_len - 1).tolist()
     h = torch.zeros((v.shape[0], cfg.decoder_hidden_dim), dtype=v.dtype)
+    c = torch.zeros_like(h) if cfg.rnn_type == "LSTM" else None
     predict, tgt, atts = [], [], []
     for t in range(max(decode_len)):
         bt = sum(l > t for l in decode_len)
-        h, word, att = base_decoder_step(v[:bt], caption[:bt, t], h[:bt], W, prefix)
+        if c is not None:
+            (h, c), word, att = base_decoder_step(v[:bt], caption[:bt, t], h[:bt], W, prefix, c=c[:bt])
+        else:
+            h, word, att = base_decoder_step(v[:bt], caption[:bt, t], h[:bt], W, prefix)
         predict.append(word)
         tgt.append(target[:bt, t + 1])                     # targets are the words after <start> (generator.py:115)
         atts.append(att)

@@ -154,13 +154,17 @@ def run_decoder(name, cfg, B, wseed, bseed, col_stride):
         loss_cap = torch.nn.functional.cross_entropy(cap["predict"], cap["target"])
         enc = m.encoder(ref_batch)
         h0 = [torch.rand((B, cfg.decoder_hidden_dim), generator=torch.Generator().manual_seed(bseed)) - 0.5]
+        if cfg.rnn_type == "LSTM":                          # nn.LSTMCell state is the pair (h, c)
+            h0 = [(h0[0], torch.rand((B, cfg.decoder_hidden_dim), generator=torch.Generator().manual_seed(bseed + 1)) - 0.5)]
         h1, word, att = m.generator.decode(v=enc["v"], v_mean=enc["v"].mean(1), prev=enc["c"][:, 3], h=h0)
     out = {"logits": predict.numpy(), "cap_predict_sub": cap["predict"].numpy()[:, ::col_stride].copy(),
            "cap_argmax": cap["predict"].argmax(1).numpy(), "cap_lse": torch.logsumexp(cap["predict"], 1).numpy(),
            "cap_target": cap["target"].numpy(), "cap_loss": np.array(loss_cap.item(), dtype=np.float64),
            "cap_len": batch["cap_len"].numpy(),
-           "step_h": h1[0].numpy(), "step_word_sub": word.numpy()[:, ::col_stride].copy(),
+           "step_h": (h1[0][0] if cfg.rnn_type == "LSTM" else h1[0]).numpy(), "step_word_sub": word.numpy()[:, ::col_stride].copy(),
            "step_word_argmax": word.argmax(1).numpy(), "step_att": att.numpy()[:, :, 0]}
+    if cfg.rnn_type == "LSTM":
+        out["step_c"] = h1[0][1].numpy()
     meta = dict(cfg=cfg.as_dict(), B=B, wseed=wseed, bseed=bseed, col_stride=col_stride)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array(repr(meta)), **out)
     print(name, {k: v.shape for k, v in out.items()}, float(loss_cap))
@@ -207,6 +211,9 @@ if __name__ == "__main__":
         run_model("basecap_small", O.SMALL_BASECAP, 8, 1111, 8001)
         run_model("basecap_full", O.FULL_BASECAP, 4, 1111, 8002)
         sys.exit(0)
+    if "--decoder-lstm-only" in sys.argv:
+        run_decoder("decoder_lstm_small", O.SMALL_DECODER_LSTM, 8, 1111, 7003, 1)
+        sys.exit(0)
     if "--decoder-only" in sys.argv:
         run_decoder("decoder_small", O.SMALL_DECODER, 8, 1111, 7001, 1)
         run_decoder("decoder_full", O.FULL_DECODER, 5, 1111, 7002, 16)
@@ -228,6 +235,7 @@ if __name__ == "__main__":
     run_qcap("qcap_full", O.FULL_QCAP, 4, 1111, 6002)
     run_decoder("decoder_small", O.SMALL_DECODER, 8, 1111, 7001, 1)
     run_decoder("decoder_full", O.FULL_DECODER, 5, 1111, 7002, 16)
+    run_decoder("decoder_lstm_small", O.SMALL_DECODER_LSTM, 8, 1111, 7003, 1)
     run_model("basecap_small", O.SMALL_BASECAP, 8, 1111, 8001)
     run_model("basecap_full", O.FULL_BASECAP, 4, 1111, 8002)
     run_model("gru2_small", O.SMALL_GRU2, 8, 1111, 9001)

@@ -23,8 +23,8 @@ def build_model(cfg, W, device="cuda"):
     from vqa_collection_b200.modules.wrapper import set_model
     m = set_model(encoder_type="base", predictor_type="base", decoder_type=cfg.decoder, ntoken=cfg.ntoken, v_dim=cfg.v_dim,
                   embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim, decoder_hidden_dim=cfg.decoder_hidden_dim,
-                  rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2, c_len=cfg.c_len, device=device, dropout=0.2,
-                  rnn_type="GRU", att_type=cfg.att_type)
+                  rnn_layer=cfg.rnn_layer, ans_dim=cfg.ans_dim, cls_layer=2, c_len=cfg.c_len, device=device, dropout=0.2,
+                  rnn_type=cfg.rnn_type, att_type=cfg.att_type)
     m.load_state_dict(W, strict=True)
     return m.eval()
 
@@ -36,7 +36,7 @@ def _need_gpu():
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("name", ["decoder_small", "decoder_full"])
+@pytest.mark.parametrize("name", ["decoder_small", "decoder_full", "decoder_lstm_small"])
 def test_caption_head_matches_reference(golden_dir, name, precision):
     import vqa_collection_b200 as pkg
     pkg.set_precision(precision)
@@ -54,7 +54,13 @@ def test_caption_head_matches_reference(golden_dir, name, precision):
             cap2 = m.forward_cap(batch)
             enc = m.encoder(batch)
             h0 = torch.rand((meta["B"], cfg.decoder_hidden_dim), generator=torch.Generator().manual_seed(meta["bseed"])) - 0.5
-            h1, word, att = m.generator.decode(v=enc["v"], v_mean=None, prev=enc["c"][:, 3], h=[h0.cuda()])
+            if cfg.rnn_type == "LSTM":                                # nn.LSTMCell: the state is the pair (h, c)
+                c0 = torch.rand((meta["B"], cfg.decoder_hidden_dim), generator=torch.Generator().manual_seed(meta["bseed"] + 1)) - 0.5
+                h1, word, att = m.generator.decode(v=enc["v"], v_mean=None, prev=enc["c"][:, 3], h=[(h0.cuda(), c0.cuda())])
+                assert relerr(h1[0][1], z["step_c"]) < tol
+                h1 = [h1[0][0]]
+            else:
+                h1, word, att = m.generator.decode(v=enc["v"], v_mean=None, prev=enc["c"][:, 3], h=[h0.cuda()])
         assert relerr(predict, z["logits"]) < tol
         assert cap["predict"].dtype == torch.float32 and cap["predict"].shape == (int((z["cap_len"] - 1).sum()), cfg.ntoken)
         assert torch.equal(cap["predict"], cap2["predict"])                              # deterministic
@@ -73,15 +79,16 @@ def test_caption_head_matches_reference(golden_dir, name, precision):
         pkg.set_precision("bf16")
 
 
+@pytest.mark.parametrize("rnn_type", ["GRU", "LSTM"])
 @pytest.mark.parametrize("att_type", ["new", "base"])
-def test_caption_head_ties_and_concat_attention_vs_oracle(att_type):
+def test_caption_head_ties_and_concat_attention_vs_oracle(att_type, rnn_type):
     """B = 40 > c_len - 1: equal caption lengths occur (stable order), batch_t shrinks step by step;
     att_type='base' runs the decoder's ConcatAttention (mode 1 of vqa_attention_logits)"""
     import vqa_collection_b200 as pkg
     from dataclasses import replace
     pkg.set_precision("fp32")
     try:
-        cfg = replace(O.SMALL_DECODER, att_type=att_type)
+        cfg = replace(O.SMALL_DECODER, att_type=att_type, rnn_type=rnn_type)
         W = O.make_weights(cfg, 2222)
         batch = O.make_decoder_batch(cfg, 40, 7003)
         assert len(set(batch["cap_len"].tolist())) < 40

@@ -119,8 +119,10 @@ def test_unsupported_configurations_raise():
               decoder_hidden_dim=8, rnn_layer=1, ans_dim=4, cls_layer=2, c_len=5, device="cpu", att_type="new")
     with pytest.raises(NotImplementedError):                     # BUTDDecoder.decode returns None in the reference
         set_model(decoder_type="butd", **kw)
-    with pytest.raises(NotImplementedError):                     # the caption head's cell is the GRUCell only
-        set_model(decoder_type="base", rnn_type="LSTM", **kw)
+    m = set_model(decoder_type="base", rnn_type="LSTM", **kw)    # nn.LSTMCell caption head: 4 gate blocks, (h, c) state
+    assert m.state_dict()["generator.rnn.weight_ih"].shape == (32, 16)
+    (h0, c0), = m.generator.init_hidden(3)
+    assert h0.shape == c0.shape == (3, 8)
     # LSTM / stacked question encoders (main.py:66,72): the reference's parameter names, never on the fused engine / train step
     m = set_model(decoder_type="none", rnn_type="LSTM", **{**kw, "rnn_layer": 2})
     names = [k for k in m.state_dict() if k.startswith("encoder.q_rnn.rnn.")]

@@ -150,7 +150,7 @@ def test_relation_known_answers(golden_dir):
     assert [tuple(x) for x in z["ka_labels"][16:].tolist()] == rest
 
 
-@pytest.mark.parametrize("name", ["decoder_small", "decoder_full"])
+@pytest.mark.parametrize("name", ["decoder_small", "decoder_full", "decoder_lstm_small"])
 def test_caption_decoder_matches_reference(golden_dir, name):
     """SURVEY §8f f3 (second half): the teacher-forced BaseDecoder forward and one decode() step of the real
     reference (decoder_type='base', the main.py default) — ragged caption lengths, packed output order."""
@@ -164,7 +164,12 @@ def test_caption_decoder_matches_reference(golden_dir, name):
         logits, enc = O.forward(batch, W, cfg)
         cap = O.base_decoder_forward(enc, W, cfg)
         h0 = torch.rand((meta["B"], cfg.decoder_hidden_dim), generator=torch.Generator().manual_seed(meta["bseed"])) - 0.5
-        h1, word, att = O.base_decoder_step(enc["v"], enc["c"][:, 3], h0, W)
+        if cfg.rnn_type == "LSTM":
+            c0 = torch.rand((meta["B"], cfg.decoder_hidden_dim), generator=torch.Generator().manual_seed(meta["bseed"] + 1)) - 0.5
+            (h1, c1), word, att = O.base_decoder_step(enc["v"], enc["c"][:, 3], h0, W, c=c0)
+            assert _relerr(c1.numpy(), z["step_c"]) < 1e-5
+        else:
+            h1, word, att = O.base_decoder_step(enc["v"], enc["c"][:, 3], h0, W)
     assert _relerr(logits.numpy(), z["logits"]) < 1e-5                       # the VQA head is unchanged by the caption head
     assert cap["predict"].shape[0] == int((z["cap_len"] - 1).sum())
     assert np.array_equal(cap["target"].numpy(), z["cap_target"])

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
 
 VQA_F32, VQA_BF16 = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -146,6 +146,7 @@ class CaptionDecodeArgs(C.Structure):
         ("d_w_att", c_void_p), ("d_w_hh", c_void_p), ("d_b_hh", c_void_p),
         ("d_h_all", c_void_p), ("d_h", c_void_p), ("d_h0_lp", c_void_p),
         ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("cell", c_int), ("d_c", c_void_p),
     ]
 
 
@@ -175,6 +176,7 @@ SYMBOLS = {
     "vqa_softmax_mul": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vqa_attention_logits": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p]),
+    "vqa_lstm_cell": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "vqa_gru_cell": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "vqa_caption_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vqa_caption_decode_steps": (c_int, [C.POINTER(CaptionDecodeArgs), c_void_p]),

@@ -372,6 +372,14 @@ int vqa_attention_logits(const void* d_proj, int ldp, const float* d_q, int ldq,
   if (int rc = require_sm100()) return rc;
   return attention_logits(d_proj, ldp, d_q, ldq, d_w, B, K, Hd, mode, dtype, d_logits, (cudaStream_t)stream);
 }
+int vqa_lstm_cell(const float* d_gates, int B, int H, int dtype, float* d_c, float* d_h_out, void* d_h_lp, int ld_lp,
+                  void* stream) {
+  if (int rc = require_sm100()) return rc;
+  VQA_REQUIRE(B >= 0 && H >= 1 && ld_lp >= H, "lstm_cell: bad dims B=%d H=%d ld_lp=%d", B, H, ld_lp);
+  if (B == 0) return VQA_OK;
+  VQA_REQUIRE(d_gates && d_c && d_h_lp, "lstm_cell: NULL pointer");
+  return lstm_gate(d_gates, B, H, d_c, d_h_out, d_h_lp, ld_lp, dtype, (cudaStream_t)stream);
+}
 int vqa_gru_cell(const float* d_gi, const float* d_gh, const float* d_h_prev, int B, int H, int dtype, float* d_h_out,
                  void* d_h_lp, int ld_lp, void* stream) {
   if (int rc = require_sm100()) return rc;
@@ -385,14 +393,14 @@ int vqa_gru_cell(const float* d_gi, const float* d_gh, const float* d_h_prev, in
 // per step W_q GEMM -> attention_logits -> attention_pool -> W_ih[:, E:] GEMM (+ the hoisted previous-word half) ->
 // W_hh GEMM -> gate update; step t runs on the first batch_t samples (captions sorted by decreasing length).
 struct DecWs { float* q; float* parts; void* att_v; float* gi; float* gh; size_t bytes; };
-static DecWs carve_dec(char* base, int B, int K, int V, int Hd, int dtype) {
+static DecWs carve_dec(char* base, int B, int K, int V, int Hd, int dtype, int ng = 4) {
   DecWs w{}; size_t off = 0;
   auto take = [&](size_t n) { char* p = base ? base + off : nullptr; off += align_up(n, 256); return p; };
   w.q = (float*)take((size_t)B * Hd * 4);
   w.parts = (float*)take((size_t)B * K * 4);
   w.att_v = take((size_t)B * V * elem_size(dtype));
-  w.gi = (float*)take((size_t)B * 3 * Hd * 4);
-  w.gh = (float*)take((size_t)B * 3 * Hd * 4);
+  w.gi = (float*)take((size_t)B * ng * Hd * 4);           // sized for the LSTM cell's 4 gates (GRU uses 3)
+  w.gh = (float*)take((size_t)B * ng * Hd * 4);
   w.bytes = off;
   return w;
 }
@@ -409,6 +417,8 @@ int vqa_caption_decode_steps(const vqa_caption_decode_args* args, void* stream) 
   if (a.B == 0 || a.T == 0) return VQA_OK;
   VQA_REQUIRE(a.h_batches && a.d_x && a.d_proj && a.d_wq && a.d_logit_w && a.d_gi_prev && a.d_w_att && a.d_w_hh &&
               a.d_b_hh && a.d_h_all && a.d_h && a.d_h0_lp && a.d_workspace, "caption_decode: NULL pointer");
+  VQA_REQUIRE(a.cell == 0 || (a.cell == 1 && a.d_c), "caption_decode: cell=%d (0 = GRUCell, 1 = LSTMCell with d_c)", a.cell);
+  const int ng = a.cell == 1 ? 4 : 3;                      // gates per cell
   const DecWs w = carve_dec((char*)a.d_workspace, a.B, a.K, a.V, a.Hd, a.dtype);
   VQA_REQUIRE(a.workspace_bytes >= w.bytes, "caption_decode: workspace %zu < %zu bytes", a.workspace_bytes, w.bytes);
   const size_t es = elem_size(a.dtype);
@@ -427,16 +437,19 @@ int vqa_caption_decode_steps(const vqa_caption_decode_args* args, void* stream) 
     if ((rc = attention_logits(a.d_proj, a.Hd, w.q, a.Hd, a.d_logit_w, bt, a.K, a.Hd, a.att_mode, a.dtype, w.parts, s))) return rc;
     if ((rc = attention_pool(w.parts, 1, a.logit_bias, a.d_x, bt, a.K, a.V, a.dtype, nullptr, w.att_v, nullptr, s))) return rc;
     vqa_linear_args gi{};                      // W_ih[:, E:] att_v + (W_ih[:, :E] prev + b_ih)
-    gi.d_A = w.att_v; gi.lda = a.V; gi.d_W = a.d_w_att; gi.ldw = a.V; gi.M = bt; gi.N = 3 * a.Hd; gi.K = a.V; gi.dtype = a.dtype;
-    gi.d_add = a.d_gi_prev + (size_t)t * 3 * a.Hd; gi.ld_add = a.T * 3 * a.Hd; gi.add_row_div = 1;
-    gi.d_out = w.gi; gi.ldo = 3 * a.Hd; gi.out_dtype = VQA_F32; gi.mul_row_div = 1;
+    gi.d_A = w.att_v; gi.lda = a.V; gi.d_W = a.d_w_att; gi.ldw = a.V; gi.M = bt; gi.N = ng * a.Hd; gi.K = a.V; gi.dtype = a.dtype;
+    gi.d_add = a.d_gi_prev + (size_t)t * ng * a.Hd; gi.ld_add = a.T * ng * a.Hd; gi.add_row_div = 1;
+    gi.d_out = w.gi; gi.ldo = ng * a.Hd; gi.out_dtype = VQA_F32; gi.mul_row_div = 1;
     if ((rc = linear_dispatch(gi, s))) return rc;
     vqa_linear_args gh{};
-    gh.d_A = h_in; gh.lda = a.Hd; gh.d_W = a.d_w_hh; gh.ldw = a.Hd; gh.M = bt; gh.N = 3 * a.Hd; gh.K = a.Hd; gh.dtype = a.dtype;
-    gh.d_bias = a.d_b_hh; gh.d_out = w.gh; gh.ldo = 3 * a.Hd; gh.out_dtype = VQA_F32; gh.mul_row_div = 1; gh.add_row_div = 1;
+    gh.d_A = h_in; gh.lda = a.Hd; gh.d_W = a.d_w_hh; gh.ldw = a.Hd; gh.M = bt; gh.N = ng * a.Hd; gh.K = a.Hd; gh.dtype = a.dtype;
+    gh.d_bias = a.d_b_hh; gh.d_out = w.gh; gh.ldo = ng * a.Hd; gh.out_dtype = VQA_F32; gh.mul_row_div = 1; gh.add_row_div = 1;
+    if (a.cell == 1) { gh.d_add = w.gi; gh.ld_add = ng * a.Hd; }        // LSTM: all four gate pre-activations summed here
     if ((rc = linear_dispatch(gh, s))) return rc;
     void* h_out_lp = (char*)a.d_h_all + row * a.Hd * es;
-    if ((rc = gru_gate(w.gi, w.gh, bt, a.Hd, 1, 0, a.d_h, a.d_h, h_out_lp, a.Hd, a.dtype, s))) return rc;
+    if (a.cell == 1) {
+      if ((rc = lstm_gate(w.gh, bt, a.Hd, a.d_c, a.d_h, h_out_lp, a.Hd, a.dtype, s))) return rc;
+    } else if ((rc = gru_gate(w.gi, w.gh, bt, a.Hd, 1, 0, a.d_h, a.d_h, h_out_lp, a.Hd, a.dtype, s))) return rc;
     h_in = h_out_lp;
     row += (size_t)bt;
   }

@@ -1,7 +1,7 @@
 """Caption head — mirror of modules/generator.py (set_decoder :12-37, DecoderModule :40-120,
 BaseDecoder :123-181) on the C-ABI kernels.
 
-Only what the reference can run is built: decoder_type='base' with rnn_type='GRU'.
+Only what the reference can run is built: decoder_type='base' (nn.GRUCell or nn.LSTMCell).
 ``BUTDDecoder.decode`` has no return statement in the reference (generator.py:240-266), so
 ``DecoderModule.forward`` raises a TypeError on it; decoder_type='butd' raises here as well.
 
@@ -42,11 +42,16 @@ class DecoderModule(nn.Module):
     def init_hidden(self, batch_size):
         """Initialize hidden states (generator.py:45-49)."""
         init = torch.zeros((batch_size, self.hidden_dim), device=self.device)
+        if self.rnn_type == 'LSTM':
+            return [(init, init)] * self.h_num
         return [init] * self.h_num
 
     def select_hidden(self, h, batch_size):
         for i in range(len(h)):
-            h[i] = h[i][:batch_size]
+            if self.rnn_type == 'LSTM':
+                h[i] = (h[i][0][:batch_size], h[i][1][:batch_size])
+            else:
+                h[i] = h[i][:batch_size]
         return h
 
     def decode(self, v, v_mean, prev, h):
@@ -54,7 +59,8 @@ class DecoderModule(nn.Module):
 
 
 class BaseDecoder(DecoderModule):
-    """Base generator based on "Show, Attend and Tell" (generator.py:123-181), rnn_type='GRU'."""
+    """Base generator based on "Show, Attend and Tell" (generator.py:123-181); rnn_type 'GRU' (nn.GRUCell) or 'LSTM'
+    (nn.LSTMCell: the hidden state is the pair (h, c), attention and word logits read h)."""
 
     step_loop_in_python = False          # True: compose the per-step ops from Python (same kernels; tests run both)
 
@@ -62,12 +68,11 @@ class BaseDecoder(DecoderModule):
                  dropout: float = 0.5, rnn_type: str = 'GRU', att_type: str = 'base'):
         super().__init__()
         assert rnn_type == 'LSTM' or rnn_type == 'GRU'
-        if rnn_type != 'GRU':
-            raise NotImplementedError("vqa_collection_b200: the caption head is built for rnn_type='GRU' (main.py:66 default)")
         self.rnn_type, self.hidden_dim, self.max_len, self.ntoken, self.device = rnn_type, hidden_dim, max_len, ntoken, device
         self.embed_dim, self.v_dim = embed_dim, v_dim
         self.h_num = 1
-        self.rnn = nn.GRUCell(input_size=embed_dim + v_dim, hidden_size=hidden_dim)      # parameters only
+        rnn_cls = nn.LSTMCell if rnn_type == 'LSTM' else nn.GRUCell
+        self.rnn = rnn_cls(input_size=embed_dim + v_dim, hidden_size=hidden_dim)         # parameters only
         self.attention = set_att(att_type)(v_dim=v_dim, q_dim=hidden_dim, hidden_dim=hidden_dim)
         self.fcnet = nn.Linear(hidden_dim, ntoken)
         self.dropout = nn.Dropout(dropout)                                              # identity in eval
@@ -107,19 +112,26 @@ class BaseDecoder(DecoderModule):
         _no_training(self)
         dtype = compute_dtype()
         P = self.prepared(dtype)
-        h0 = h[0].to(self.device).float().contiguous()
+        lstm = self.rnn_type == 'LSTM'
+        state = h[0]
+        h0 = (state[0] if lstm else state).to(self.device).float().contiguous()
         v = v.to(self.device)
         parts, x = self.attention.logit_parts(v, h0)
         att, att_v, _ = ops.attention_pool(parts, float(self.attention.linear.bias.detach()), x, True, True, False)
         gi = ops.linear(self._pad_prev(prev.to(self.device), P["E_pad"], dtype), P["w_prev"], bias=P["b_ih"],
                         out_dtype=torch.float32)
         gi = ops.linear(att_v, P["w_att"], add=gi, out_dtype=torch.float32)
-        gh = ops.linear(as_compute(h0, dtype), P["w_hh"], bias=P["b_hh"], out_dtype=torch.float32)
         h_new = h0.clone()
         h_lp = torch.empty(h0.shape, dtype=dtype, device=h0.device)
-        ops.gru_cell(gi, gh, h_new, h_lp)
+        if lstm:
+            gates = ops.linear(as_compute(h0, dtype), P["w_hh"], bias=P["b_hh"], add=gi, out_dtype=torch.float32)
+            c_new = state[1].to(self.device).float().clone().contiguous()
+            ops.lstm_cell(gates, c_new, h_new, h_lp)
+        else:
+            gh = ops.linear(as_compute(h0, dtype), P["w_hh"], bias=P["b_hh"], out_dtype=torch.float32)
+            ops.gru_cell(gi, gh, h_new, h_lp)
         output = ops.linear(h_lp, P["w_fc"], bias=P["b_fc"], out_dtype=torch.float32)
-        return [h_new], output, att.unsqueeze(2)
+        return [(h_new, c_new) if lstm else h_new], output, att.unsqueeze(2)
 
     def forward(self, batch):
         """Teacher-forced pass (generator.py:66-120) → {'predict': [Σ_t batch_t, ntoken] f32, 'target': [Σ_t batch_t]}
@@ -147,10 +159,13 @@ class BaseDecoder(DecoderModule):
         # hoisted out of the time loop (see the module docstring)
         proj, x = self.attention.project(v)                                             # [B*K,Hd]
         prev_all = self._pad_prev(caption[:, :T].reshape(B * T, E), P["E_pad"], dtype)
-        gi_prev = ops.linear(prev_all, P["w_prev"], bias=P["b_ih"], out_dtype=torch.float32).view(B, T * 3 * Hd)
+        lstm = self.rnn_type == 'LSTM'
+        ng = 4 if lstm else 3
+        gi_prev = ops.linear(prev_all, P["w_prev"], bias=P["b_ih"], out_dtype=torch.float32).view(B, T * ng * Hd)
         att_bias = float(self.attention.linear.bias.detach())
 
         h = torch.zeros((B, Hd), dtype=torch.float32, device=dev)
+        c = torch.zeros((B, Hd), dtype=torch.float32, device=dev) if lstm else None
         h_in = torch.zeros((B, Hd), dtype=dtype, device=dev)
         if self.step_loop_in_python:
             h_all = torch.empty((offs[-1], Hd), dtype=dtype, device=dev)                 # every h_t, packed order
@@ -158,14 +173,17 @@ class BaseDecoder(DecoderModule):
                 h_in = h_in[:bt]
                 parts = self.attention.step_parts(proj, h_in, K)
                 _, att_v, _ = ops.attention_pool(parts, att_bias, x[:bt], False, True, False)
-                gi = ops.linear(att_v, P["w_att"], add=gi_prev[:bt, t * 3 * Hd:(t + 1) * 3 * Hd], out_dtype=torch.float32)
-                gh = ops.linear(h_in, P["w_hh"], bias=P["b_hh"], out_dtype=torch.float32)
+                gi = ops.linear(att_v, P["w_att"], add=gi_prev[:bt, t * ng * Hd:(t + 1) * ng * Hd], out_dtype=torch.float32)
+                gh = ops.linear(h_in, P["w_hh"], bias=P["b_hh"], add=gi if lstm else None, out_dtype=torch.float32)
                 h_in = h_all[offs[t]:offs[t + 1]]
-                ops.gru_cell(gi, gh, h[:bt], h_in)
+                if lstm:
+                    ops.lstm_cell(gh, c[:bt], h[:bt], h_in)
+                else:
+                    ops.gru_cell(gi, gh, h[:bt], h_in)
         else:                                                                            # the same steps in one C call
             mode, w_q, q_scale, q_bias, logit_w = self.attention.step_weights(dtype)
             h_all = ops.caption_decode_steps(x, proj, batches, mode, w_q, q_scale, q_bias, logit_w, att_bias, gi_prev,
-                                             P["w_att"], P["w_hh"], P["b_hh"], h, h_in)
+                                             P["w_att"], P["w_hh"], P["b_hh"], h, h_in, c=c)
         predict = ops.linear(h_all, P["w_fc"], bias=P["b_fc"], out_dtype=torch.float32)
         # the targets are the words after <start> (generator.py:115), packed like the predictions
         tgt = torch.cat([target[:bt, t + 1] for t, bt in enumerate(batches)])

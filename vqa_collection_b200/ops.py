@@ -338,15 +338,36 @@ def gru_cell(gi, gh, h, h_lp):
     return h
 
 
+def lstm_cell(gates, c, h, h_lp):
+    """nn.LSTMCell gate update (generator.py:158-159 with rnn_type='LSTM'): gates f32 [B,4H] = W_ih x + b_ih + W_hh h + b_hh
+    ([i;f;g;o]); ``c`` and ``h`` f32 [B,H] are updated IN PLACE, ``h_lp`` [B,H] (compute dtype) receives the operand copy."""
+    lib = L.load()
+    _require(gates, torch.float32, "gates")
+    _require(c, torch.float32, "c")
+    _require(h, torch.float32, "h")
+    _require(h_lp, None, "h_lp")
+    B, H = h.shape
+    if gates.shape != (B, 4 * H) or c.shape != (B, H) or h_lp.shape != (B, H) or not (gates.is_contiguous() and
+                                                                                      c.is_contiguous() and h.is_contiguous()):
+        raise ValueError("lstm_cell: shape mismatch")
+    L.check(lib.vqa_lstm_cell(gates.data_ptr(), B, H, dtype_code(h_lp.dtype), c.data_ptr(), h.data_ptr(), h_lp.data_ptr(),
+                              h_lp.stride(0), _stream()))
+    return h, c
+
+
 def caption_decode_steps(x, proj, batches, att_mode, w_q, q_scale, q_bias, logit_w, logit_bias, gi_prev, w_att, w_hh, b_hh,
-                         h, h0_lp):
+                         h, h0_lp, c=None):
     """The teacher-forced time loop of the caption head in one C call (vqa_caption_decode_steps;
     generator.py:99-111 + :168-181).  ``batches``: python list, batch_t per step (non-increasing).
     x [B,K,V], proj [B*K,Hd], gi_prev f32 [B, T*3Hd], h f32 [B,Hd] (updated in place), h0_lp [B,Hd].
+    ``c`` f32 [B,Hd] (updated in place) selects the LSTMCell form: gate blocks are then 4Hd wide instead of 3Hd.
     Returns h_all [Σ batch_t, Hd] in the compute dtype (every new state, pack_padded_sequence order)."""
     lib = L.load()
     _require(x, None, "x")
     dt = x.dtype
+    ng = 3 if c is None else 4
+    if c is not None:
+        _require(c, torch.float32, "c")
     for nm, t in (("proj", proj), ("w_q", w_q), ("w_att", w_att), ("w_hh", w_hh), ("h0_lp", h0_lp)):
         _require(t, dt, nm)
     for nm, t in (("q_scale", q_scale), ("q_bias", q_bias), ("logit_w", logit_w), ("gi_prev", gi_prev), ("b_hh", b_hh),
@@ -355,8 +376,9 @@ def caption_decode_steps(x, proj, batches, att_mode, w_q, q_scale, q_bias, logit
             _require(t, torch.float32, nm)
     B, K, V = x.shape
     Hd, T = h.shape[1], len(batches)
-    if (proj.shape != (B * K, Hd) or gi_prev.shape != (B, T * 3 * Hd) or w_att.shape != (3 * Hd, V) or
-            w_hh.shape != (3 * Hd, Hd) or w_q.shape != (Hd, Hd) or h.shape != (B, Hd) or h0_lp.shape != (B, Hd) or
+    if (proj.shape != (B * K, Hd) or gi_prev.shape != (B, T * ng * Hd) or w_att.shape != (ng * Hd, V) or
+            w_hh.shape != (ng * Hd, Hd) or w_q.shape != (Hd, Hd) or h.shape != (B, Hd) or h0_lp.shape != (B, Hd) or
+            (c is not None and (c.shape != (B, Hd) or not c.is_contiguous())) or
             not all(t.is_contiguous() for t in (x, proj, gi_prev, w_att, w_hh, w_q, h, h0_lp))):
         raise ValueError("caption_decode_steps: shape mismatch")
     code = dtype_code(dt)
@@ -373,6 +395,7 @@ def caption_decode_steps(x, proj, batches, att_mode, w_q, q_scale, q_bias, logit
     a.d_w_att, a.d_w_hh, a.d_b_hh = w_att.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr()
     a.d_h_all, a.d_h, a.d_h0_lp = h_all.data_ptr(), h.data_ptr(), h0_lp.data_ptr()
     a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+    a.cell, a.d_c = (0, None) if c is None else (1, c.data_ptr())
     L.check(lib.vqa_caption_decode_steps(C.byref(a), _stream()))
     return h_all
 
