@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 7
+#define VQA_B200_ABI_VERSION 8
 
 typedef enum {
   VQA_OK = 0,
@@ -126,10 +126,16 @@ typedef struct {
   float leaky_slope;         /* negative-side slope of the activation when relu != 0 */
   int add_after_act;         /* apply `add` after the activation instead of before   */
   int sigmoid;               /* logistic function applied last                       */
+  /* fused answer selection (wrapper.py:14, torch.max(predict, 1)[1]: lowest index among equal maxima) over the N
+   * outputs of each row, store form only: d_argmax_label int64 [M]; d_argmax_ws = vqa_linear_argmax_workspace_bytes(M)
+   * bytes that are ZERO on entry (the call leaves them dirty).  NULL = off. */
+  int64_t* d_argmax_label;
+  void* d_argmax_ws;
 } vqa_linear_args;
 
 int vqa_linear(const vqa_linear_args* args, void* stream);
 int vqa_linear_part_width(int dtype);
+size_t vqa_linear_argmax_workspace_bytes(int M);
 
 /* ------------------------------------------------------------------------
  * a6/a7  question encoder: embedding gather + 1-layer GRU, last state

@@ -224,6 +224,33 @@ def test_gru_persistent_shapes(ops, B, T):
     assert relerr(h[idx.cuda()], want) < 1e-2
 
 
+# ---------------------------------------------------------------------------- fused answer selection
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(1024, 3129, 2048), (37, 3129, 256), (300, 200, 128), (5, 64, 64)])
+def test_linear_fused_argmax(ops, dtype, M, N, K):
+    """lowest-index argmax of every output row selected in the GEMM's epilogue (wrapper.py:14, torch.max's tie rule):
+    many N tiles per row block, row tails, ties inside a tile and across tiles, an all-zero (post-ReLU) row"""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.rand((M, K), generator=g) - 0.3).to(dtype)
+    W = (torch.randn((N, K), generator=g) / K ** 0.5).to(dtype)
+    bias = torch.randn((N,), generator=g) * 0.1
+    # duplicated weight rows give exactly equal logits far apart (different N tiles) and next to each other
+    W[N - 1] = W[3]
+    W[5] = W[3]
+    bias[N - 1] = bias[5] = bias[3] = 2.0                      # ... and large enough to be the maximum of many rows
+    A[0] = 0                                                   # row 0: logits = bias only
+    out, label = ops.linear(A.cuda(), W.cuda(), None, bias.cuda(), relu=True, out_dtype=torch.float32, want_argmax=True)
+    assert label.dtype == torch.int64 and label.shape == (M,)
+    assert torch.equal(label, torch.max(out, 1)[1])            # the rule, on the kernel's own logits
+    assert int(label[0]) == 3                                  # first of the three equal maxima
+    ties = (out[:, 3] == out.max(1)[0]).sum().item()
+    assert ties >= 1
+    bias0 = torch.full((N,), -1.0)
+    out0, label0 = ops.linear(torch.zeros((M, K)).to(dtype).cuda(), W.cuda(), None, bias0.cuda(), relu=True,
+                              out_dtype=torch.float32, want_argmax=True)
+    assert float(out0.abs().max()) == 0.0 and int(label0.abs().max()) == 0       # all-zero rows -> index 0
+
+
 # ---------------------------------------------------------------------------- attention pooling
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,K,V,P", [(3, 36, 2048, 4), (1, 36, 256, 1), (5, 10, 64, 2), (2, 64, 512, 8)])

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
 
 VQA_F32, VQA_BF16 = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -31,6 +31,7 @@ class LinearArgs(C.Structure):
         ("trans_a", c_int), ("trans_w", c_int),
         ("d_mask", c_void_p), ("ld_mask", c_int), ("mask_dtype", c_int),
         ("leaky_slope", c_float), ("add_after_act", c_int), ("sigmoid", c_int),
+        ("d_argmax_label", c_void_p), ("d_argmax_ws", c_void_p),
     ]
 
 
@@ -162,6 +163,7 @@ SYMBOLS = {
     "vqa_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vqa_linear": (c_int, [C.POINTER(LinearArgs), c_void_p]),
     "vqa_linear_part_width": (c_int, [c_int]),
+    "vqa_linear_argmax_workspace_bytes": (c_size_t, [c_int]),
     "vqa_gru_last_state": (c_int, [C.POINTER(GruArgs), c_void_p]),
     "vqa_gru_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "vqa_lstm_sequence": (c_int, [C.POINTER(LstmArgs), c_void_p]),

@@ -100,9 +100,14 @@ static int linear_dispatch(const vqa_linear_args& a, cudaStream_t s) {
   VQA_REQUIRE(a.dtype == VQA_F32 || a.dtype == VQA_BF16, "vqa_linear: dtype=%d", a.dtype);
   VQA_REQUIRE(a.d_mul == nullptr || a.mul_row_div >= 1, "vqa_linear: mul_row_div must be >= 1");
   VQA_REQUIRE(a.d_add == nullptr || a.add_row_div >= 1, "vqa_linear: add_row_div must be >= 1");
-  if (a.dtype == VQA_BF16 && !force_simt()) return linear_tc(a, s);
-  return linear_simt(a, s);
+  VQA_REQUIRE(!a.d_argmax_label || (a.d_argmax_ws && !a.d_logit_w && a.out_dtype == VQA_F32),
+              "vqa_linear: fused argmax needs its workspace, the store form and an f32 output");
+  if (a.dtype == VQA_BF16 && !force_simt()) return linear_tc(a, s);      // argmax in the epilogue
+  if (int rc = linear_simt(a, s)) return rc;
+  if (a.d_argmax_label) return argmax_rows((const float*)a.d_out, a.M, a.N, a.ldo, a.d_argmax_label, s);
+  return VQA_OK;
 }
+static size_t argmax_ws_bytes(int M) { return align_up((size_t)(M > 0 ? M : 1) * 8, 256) + align_up((size_t)((M + 127) / 128 + 1) * 4, 256); }
 
 static int part_width(int dtype) {
   return (dtype == VQA_BF16 && !force_simt()) ? linear_tc_part_width() : 128;
@@ -310,6 +315,7 @@ int vqa_linear(const vqa_linear_args* args, void* stream) {
   return linear_dispatch(*args, (cudaStream_t)stream);
 }
 int vqa_linear_part_width(int dtype) { return part_width(dtype); }
+size_t vqa_linear_argmax_workspace_bytes(int M) { return argmax_ws_bytes(M); }
 
 size_t vqa_gru_workspace_bytes(int B, int T, int H, int E_pad, int dtype) {
   return carve_gru(nullptr, B, T, H, E_pad, dtype).bytes;
@@ -473,6 +479,7 @@ int vqa_adamax_step(const vqa_optim_tensor* h_tensors, int n_tensors, float beta
 struct FwdWs {
   void* gru; size_t gru_bytes;
   float* h; void* h_lp; float* qq; float* parts; void* vsum; void* Y; void* joint; void* hid;
+  void* amax; size_t amax_bytes;             // fused answer selection of the last classifier layer
   size_t bytes;
 };
 static FwdWs carve_fwd(const vqa_forward_args& a, void* base) {
@@ -492,6 +499,8 @@ static FwdWs carve_fwd(const vqa_forward_args& a, void* base) {
   w.Y = a.relation ? take((size_t)a.B * a.K * (a.d_Wg3 ? 3 : 4) * a.V * es) : nullptr;
   w.joint = take((size_t)a.B * a.H * es);
   w.hid = take((size_t)a.B * 2 * a.H * es);
+  w.amax_bytes = argmax_ws_bytes(a.B);
+  w.amax = take(w.amax_bytes);
   w.bytes = off;
   return w;
 }
@@ -534,6 +543,8 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
     }
     VQA_REQUIRE(labels, "vqa_forward: relation path needs d_labels or d_bbox");
   }
+  // the fused answer selection of step 8 needs its keys / counters zeroed: first node of the chain, off the critical path
+  if (a.d_label && a.dtype == VQA_BF16 && !force_simt()) VQA_CUDA_CHECK(cudaMemsetAsync(w.amax, 0, w.amax_bytes, s));
   // 1. question encoder (encoder.py:159-160)
   vqa_gru_args g{};
   g.d_tokens = a.d_tokens; g.B = a.B; g.T = a.T; g.H = a.H; g.E_pad = a.E_pad; g.ntoken_rows = a.ntoken_rows;
@@ -612,9 +623,9 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
   l.d_A = w.hid; l.lda = 2 * a.H; l.d_W = a.d_Wc1; l.ldw = 2 * a.H; l.M = a.B; l.N = a.A; l.K = 2 * a.H; l.dtype = a.dtype;
   l.d_scale = a.d_sc1; l.d_bias = a.d_bc1; l.relu = 1; l.mul_row_div = 1;
   l.d_out = a.d_logits; l.ldo = a.A; l.out_dtype = VQA_F32;
+  // 8. answers (wrapper.py:14): selected in this GEMM's epilogue (bf16 path) or by argmax_rows after it (fp32 path)
+  l.d_argmax_label = a.d_label; l.d_argmax_ws = a.d_label ? w.amax : nullptr;
   if ((rc = linear_dispatch(l, s))) return rc;
-  // 8. answers (wrapper.py:14)
-  if (a.d_label) if ((rc = argmax_rows(a.d_logits, a.B, a.A, a.A, a.d_label, s))) return rc;
   if (a.d_q) VQA_CUDA_CHECK(cudaMemcpy2DAsync(a.d_q, (size_t)a.H * 4, w.qq + a.H, (size_t)2 * a.H * 4, (size_t)a.H * 4, a.B,
                                               cudaMemcpyDeviceToDevice, s));
   g_last_forward_launches = launch_count() - before;

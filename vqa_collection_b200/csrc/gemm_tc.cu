@@ -58,6 +58,9 @@ struct Params {
   void* out; int ldo; int out_bf16; int n_parts;
   int tiles_m, tiles_n;
   float leaky_slope; int add_after_act; int sigmoid;
+  // fused lowest-index argmax over n (wrapper.py:14): keys u64 [M] (value order bits << 32 | ~n), per-row-block tile
+  // counters [tiles_m] — both zero on entry — and the int64 labels written by the LAST tile of each row block
+  unsigned long long* amax_keys; int* amax_cnt; long long* amax_label;
 };
 
 // ---- the kernel ----------------------------------------------------------------
@@ -209,6 +212,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float* add_row = p.add ? p.add + (size_t)((row_ok ? row : 0) / p.add_row_div) * p.ld_add : nullptr;
       const bool add_vec = p.add && ((p.ld_add & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.add) & 15) == 0);
       float part = 0.f;
+      float best = 0.f; int bidx = -1;                 // fused argmax: first maximum of this row within the tile
       const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -282,6 +286,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) y[j] = __fdividef(1.f, 1.f + __expf(-y[j]));
         }
+        if (p.amax_keys) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nbase + j < p.N && (bidx < 0 || y[j] > best)) { best = y[j]; bidx = nbase + j; }
+        }
         if (p.logit_w) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) part = fmaf(y[j], ps[2 * BN + c0 + j], part);   // logit_w = 0 beyond N
@@ -321,6 +330,30 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       if (p.logit_w && row_ok) reinterpret_cast<float*>(p.out)[(size_t)row * p.n_parts + n_blk] = part;
+      if constexpr (!PAIR) {
+        if (p.amax_keys) {
+          // Row maxima of the tiles of one row block meet in a 64-bit atomicMax: the high word orders like the float
+          // (+0 = -0), the low word is ~n, so among equal values the LOWEST column wins (torch.max's rule).  The tile
+          // that arrives last at the row block's counter turns the keys into int64 labels.
+          if (row_ok && bidx >= 0) {
+            uint32_t b = __float_as_uint(best + 0.f);
+            b ^= (b >> 31) ? 0xFFFFFFFFu : 0x80000000u;
+            atomicMax(p.amax_keys + row, ((unsigned long long)b << 32) | (0xFFFFFFFFu - (uint32_t)bidx));
+          }
+          __threadfence();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          volatile int* last_flag = reinterpret_cast<volatile int*>(base_ptr + C::STAGES * C::STAGE_BYTES + 8 * (2 * C::STAGES + 5));
+          if (et == 0) *last_flag = (atomicAdd(p.amax_cnt + m_blk, 1) == p.tiles_n - 1);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (*last_flag) {
+            __threadfence();
+            if (row_ok) {
+              const unsigned long long key = *reinterpret_cast<volatile unsigned long long*>(p.amax_keys + row);
+              p.amax_label[row] = (long long)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull));
+            }
+          }
+        }
+      }
       // release the accumulator stage
       tcgen05_fence_before();
       if constexpr (PAIR) {
@@ -399,6 +432,13 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
   p.logit_w = a.d_logit_w; p.out = a.d_out; p.ldo = a.ldo; p.out_bf16 = (a.out_dtype == VQA_BF16);
   p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
   p.leaky_slope = a.leaky_slope; p.add_after_act = a.add_after_act; p.sigmoid = a.sigmoid;
+  p.amax_keys = nullptr; p.amax_cnt = nullptr; p.amax_label = nullptr;
+  if (a.d_argmax_label) {
+    VQA_REQUIRE(a.d_argmax_ws && !a.d_logit_w, "vqa_linear: fused argmax needs its zeroed workspace and the store form");
+    p.amax_keys = (unsigned long long*)a.d_argmax_ws;
+    p.amax_cnt = (int*)((char*)a.d_argmax_ws + align_up((size_t)a.M * 8, 256));
+    p.amax_label = (long long*)a.d_argmax_label;
+  }
   auto kern = linear_tc_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -448,6 +488,7 @@ static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
   p.logit_w = a.d_logit_w; p.out = a.d_out; p.ldo = a.ldo; p.out_bf16 = (a.out_dtype == VQA_BF16);
   p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
   p.leaky_slope = a.leaky_slope; p.add_after_act = a.add_after_act; p.sigmoid = a.sigmoid;
+  p.amax_keys = nullptr; p.amax_cnt = nullptr; p.amax_label = nullptr;
   const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
   const int pairs = pair_tiles < pairs_resident ? pair_tiles : pairs_resident;
   cudaLaunchConfig_t cfg = {};
@@ -475,7 +516,7 @@ static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
       // many tiles per SM: CTA pairs pay.  Only whole 256-wide N tiles (the shapes of the path: N = 1024, 6144).  Pairs on
       // narrower tiles for the small-M layers were tried and measured: no gain (365 vs 368 us per Up-Down step) — those
       // layers are bound by launch / fill / drain latency, not by operand ingest.
-      if (tiles_m * ((a.N + 255) / 256) >= 2 * sms && a.N % 256 == 0) {
+      if (tiles_m * ((a.N + 255) / 256) >= 2 * sms && a.N % 256 == 0 && !a.d_argmax_label) {
         const int rc = launch_pair(a, s);
         if (rc != VQA_ERR_UNSUPPORTED) return rc;
       }

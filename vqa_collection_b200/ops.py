@@ -105,7 +105,7 @@ def linear_part_width(dtype: torch.dtype) -> int:
 
 def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, logit_w=None,
            out_dtype=None, N=None, add=None, add_row_div=1, trans_a=False, trans_w=False, mask=None, out=None,
-           leaky_slope=0.0, add_after_act=False, sigmoid=False):
+           leaky_slope=0.0, add_after_act=False, sigmoid=False, want_argmax=False):
     """Fused weight-normed linear layer (modules.py:13-60), see vqa_linear in the header.
 
     A [M,K], W [N_rows,K] (same dtype); returns [M,N] (out_dtype) or, with ``logit_w``,
@@ -113,7 +113,8 @@ def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, log
     rows of W (row-padded weights).  Backward forms: ``trans_w`` → W is [K,N] (y = A·W),
     ``trans_a`` (with trans_w) → A is [K,M] (y = Aᵀ·W); ``mask`` [M,N] zeroes y where mask ≤ 0.
     ``leaky_slope`` turns the ReLU into LeakyReLU (LReLUNet, modules.py:62-78); ``add_after_act`` applies ``add``
-    after the activation; ``sigmoid`` applies the logistic function last.
+    after the activation; ``sigmoid`` applies the logistic function last.  ``want_argmax`` (f32 store form): also returns the
+    lowest-index argmax of every output row (int64 [M]; wrapper.py:14), selected in the GEMM's epilogue → (out, label).
     """
     lib = L.load()
     _require(A, None, "A")
@@ -163,8 +164,15 @@ def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, log
             out = torch.empty((M, N), dtype=out_dtype, device=A.device)
         a.ldo, a.out_dtype = out.stride(0), dtype_code(out.dtype)
     a.d_out = out.data_ptr()
+    label = None
+    if want_argmax:
+        if logit_w is not None or out.dtype != torch.float32:
+            raise ValueError("linear: want_argmax needs the f32 store form")
+        label = torch.empty((M,), dtype=torch.int64, device=A.device)
+        amax_ws = torch.zeros((lib.vqa_linear_argmax_workspace_bytes(M),), dtype=torch.uint8, device=A.device)
+        a.d_argmax_label, a.d_argmax_ws = label.data_ptr(), amax_ws.data_ptr()
     L.check(lib.vqa_linear(C.byref(a), _stream()))
-    return out
+    return (out, label) if want_argmax else out
 
 
 def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False, packed=None):
