@@ -143,7 +143,8 @@ size_t vqa_linear_argmax_workspace_bytes(int M);
  * h0 = 0, output[:, -1], gate order [r;z;n]).
  *   tokens int64 [B,T]; emb [ntoken+1, ld_emb] (dtype); w_ih [3H, ld_emb]
  *   (zero padded to ld_emb), w_hh [3H,H] (dtype); biases f32 [3H].
- *   workspace: vqa_gru_workspace_bytes(B,T,H,ld_emb,dtype) bytes.
+ *   workspace: vqa_gru_workspace_bytes(B,T,H,ld_emb,dtype) bytes; whatever the caller passes BEYOND that many
+ *   bytes is zero-filled by the call (vqa_forward parks the must-be-zero scratch of its fused answer selection there).
  *   out: h_last f32 [B,H]; if d_h_last_lp != NULL also written in `dtype`.
  * Sequence form (config 5, replaces modules.py:147-152 SentenceEmbedding.forward_all):
  *   d_x != NULL      : dense inputs [B*T, E_pad] (dtype) instead of tokens + embedding gather

@@ -58,7 +58,8 @@ int softmax_mul(const float*, const void*, int, int, int, void*, cudaStream_t);
 int attention_logits(const void*, int, const float*, int, const float*, int, int, int, int, int, float*, cudaStream_t);
 int attention_pool(const float*, int, float, const void*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int argmax_rows(const float*, int, int, int, int64_t*, cudaStream_t);
-int embedding_gather(const int64_t*, int, int, int, int, const void*, void*, cudaStream_t);
+int embedding_gather(const int64_t*, int, int, int, int, const void*, void*, cudaStream_t, void* zero_ptr = nullptr,
+                     size_t zero_bytes = 0);
 int gru_gate(const float*, const float*, int, int, int, int, const float*, float*, void*, int, int, cudaStream_t);
 int lstm_gate(const float*, int, int, float*, float*, void*, int, int, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
@@ -142,8 +143,14 @@ static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
   const GruWs w = carve_gru(a.d_workspace, a.B, a.T, a.H, a.E_pad, a.dtype);
   int rc;
   const void* X = a.d_x;
+  // bytes of the workspace beyond what the GRU needs are zero-filled by the call (vqa_b200.h): by the gather kernel when
+  // there is one, else by a memset
+  void* tail = (char*)a.d_workspace + need.bytes;
+  const size_t tail_bytes = (a.workspace_bytes - need.bytes) / 16 * 16;
+  if (X && tail_bytes) VQA_CUDA_CHECK(cudaMemsetAsync(tail, 0, tail_bytes, s));
   if (!X) {
-    if ((rc = embedding_gather(a.d_tokens, a.B * a.T, a.E_pad, a.ntoken_rows, a.dtype, a.d_emb, w.X, s))) return rc;
+    if ((rc = embedding_gather(a.d_tokens, a.B * a.T, a.E_pad, a.ntoken_rows, a.dtype, a.d_emb, w.X, s, tail, tail_bytes)))
+      return rc;
     X = w.X;
   }
   if (a.dtype == VQA_BF16 && a.d_wx_packed && a.d_wh_packed && a.d_bias_packed && !force_simt() && a.H % 64 == 0 &&
@@ -488,8 +495,11 @@ static FwdWs carve_fwd(const vqa_forward_args& a, void* base) {
   char* p = (char*)base;
   auto take = [&](size_t n) { void* r = p ? p + off : nullptr; off += align_up(n, 256); return r; };
   const size_t es = elem_size(a.dtype);
+  // [GRU workspace | keys + counters of the fused answer selection]: the GRU call zero-fills whatever follows its own part
   w.gru_bytes = carve_gru(nullptr, a.B, a.T, a.H, a.E_pad, a.dtype).bytes;
-  w.gru = take(w.gru_bytes);
+  w.amax_bytes = argmax_ws_bytes(a.B);
+  w.gru = take(w.gru_bytes + w.amax_bytes);
+  w.amax = p ? (char*)w.gru + w.gru_bytes : nullptr;
   w.h = (float*)take((size_t)a.B * a.H * 4);
   w.h_lp = take((size_t)a.B * a.H * es);
   w.qq = (float*)take((size_t)a.B * 2 * a.H * 4);
@@ -499,8 +509,6 @@ static FwdWs carve_fwd(const vqa_forward_args& a, void* base) {
   w.Y = a.relation ? take((size_t)a.B * a.K * (a.d_Wg3 ? 3 : 4) * a.V * es) : nullptr;
   w.joint = take((size_t)a.B * a.H * es);
   w.hid = take((size_t)a.B * 2 * a.H * es);
-  w.amax_bytes = argmax_ws_bytes(a.B);
-  w.amax = take(w.amax_bytes);
   w.bytes = off;
   return w;
 }
@@ -543,14 +551,13 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
     }
     VQA_REQUIRE(labels, "vqa_forward: relation path needs d_labels or d_bbox");
   }
-  // the fused answer selection of step 8 needs its keys / counters zeroed: first node of the chain, off the critical path
-  if (a.d_label && a.dtype == VQA_BF16 && !force_simt()) VQA_CUDA_CHECK(cudaMemsetAsync(w.amax, 0, w.amax_bytes, s));
   // 1. question encoder (encoder.py:159-160)
   vqa_gru_args g{};
   g.d_tokens = a.d_tokens; g.B = a.B; g.T = a.T; g.H = a.H; g.E_pad = a.E_pad; g.ntoken_rows = a.ntoken_rows;
   g.dtype = a.dtype; g.d_emb = a.d_emb; g.d_w_ih = a.d_w_ih; g.d_b_ih = a.d_b_ih; g.d_w_hh = a.d_w_hh;
   g.d_b_hh = a.d_b_hh; g.d_wx_packed = a.d_wx_packed; g.d_wh_packed = a.d_wh_packed; g.d_bias_packed = a.d_bias_packed;
-  g.d_workspace = w.gru; g.workspace_bytes = w.gru_bytes; g.d_h_last = w.h; g.d_h_last_lp = w.h_lp;
+  g.d_workspace = w.gru; g.workspace_bytes = w.gru_bytes + w.amax_bytes;     // the tail (w.amax) comes back zeroed
+  g.d_h_last = w.h; g.d_h_last_lp = w.h_lp;
   if ((rc = gru_last_state(g, s))) return rc;
   // 2. [W_q ; q_net] (attention.py:71, encoder.py:169): qq = ReLU(h Wqqᵀ s + b) f32 [B,2H]
   vqa_linear_args l{};

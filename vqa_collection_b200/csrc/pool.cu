@@ -313,7 +313,10 @@ int argmax_rows(const float* logits, int B, int A, int ld, int64_t* out, cudaStr
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 embedding_gather_kernel(const int64_t* __restrict__ tokens, int n_rows, int row_vec16, int ntoken_rows,
-                        const uint4* __restrict__ emb, uint4* __restrict__ out) {
+                        const uint4* __restrict__ emb, uint4* __restrict__ out, uint4* __restrict__ zero, int zero_vec16) {
+  // first kernel of the forward chain: it also clears the small must-be-zero scratch parked behind the GRU workspace
+  // (keys / counters of the fused answer selection) instead of a memset node of its own
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_vec16; i += gridDim.x * blockDim.x) zero[i] = make_uint4(0, 0, 0, 0);
   const int total = n_rows * row_vec16;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / row_vec16, c = i - r * row_vec16;
@@ -324,7 +327,7 @@ embedding_gather_kernel(const int64_t* __restrict__ tokens, int n_rows, int row_
 }
 
 int embedding_gather(const int64_t* tokens, int n_rows, int E_pad, int ntoken_rows, int dtype,
-                     const void* emb, void* out, cudaStream_t s) {
+                     const void* emb, void* out, cudaStream_t s, void* zero_ptr, size_t zero_bytes) {
   const size_t row_bytes = (size_t)E_pad * elem_size(dtype);
   VQA_REQUIRE(row_bytes % 16 == 0, "embedding_gather: padded row of %zu bytes is not 16-byte aligned",
               row_bytes);
@@ -333,8 +336,9 @@ int embedding_gather(const int64_t* tokens, int n_rows, int E_pad, int ntoken_ro
   const int total = n_rows * row_vec16;
   int grid = (total + 255) / 256;
   if (grid > sm_count() * 8) grid = sm_count() * 8;
+  VQA_REQUIRE(zero_bytes % 16 == 0 && ((uintptr_t)zero_ptr & 15) == 0, "embedding_gather: zero region must be 16-byte aligned");
   embedding_gather_kernel<<<grid, 256, 0, s>>>(tokens, n_rows, row_vec16, ntoken_rows,
-                                               (const uint4*)emb, (uint4*)out);
+                                               (const uint4*)emb, (uint4*)out, (uint4*)zero_ptr, (int)(zero_bytes / 16));
   VQA_LAUNCH_CHECK();
   return VQA_OK;
 }
