@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 8
+#define VQA_B200_ABI_VERSION 9
 
 typedef enum {
   VQA_OK = 0,
@@ -248,6 +248,9 @@ typedef struct {
 } vqa_graph_attention_args;
 
 int vqa_graph_attention(const vqa_graph_attention_args* args, void* stream);
+/* dst += src, n elements of `dtype` (n % 8 == 0, 16-byte aligned): the sum of the implicit and the spatial relation
+ * branch, encoder.py:257,264 (RelationEncoder with use_imp=True) */
+int vqa_add_inplace(void* d_dst, const void* d_src, size_t n, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------
  * a14  answer selection: lowest-index argmax over the A logits

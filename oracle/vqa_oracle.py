@@ -52,6 +52,8 @@ class Config:
     num_labels: int = 12
     conv_layer: int = 1
     relation: bool = False          # encoder_type 'relation' vs 'base'
+    use_imp: bool = False           # RelationEncoder(use_imp=True): + the implicit (fully connected) branch, encoder.py:202,252-257
+    use_spa: bool = True            # the spatial branch (encoder.py:203,260-264)
     att_type: str = "new"           # 'new' = MultiplyAttention (CLI default main.py:67), 'base' = ConcatAttention
     predictor: str = "base"         # 'base' = BasePredictor, 'q-cap' = PredictorwithCaption (config 5)
     neg_slope: float = 0.01         # LeakyReLU slope of the q-cap predictor's own LReLUNets (predictor.py:159)
@@ -71,6 +73,9 @@ SMALL = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200,
                relation=False)
 SMALL_REGAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200,
                      relation=True)
+SMALL_REGAT_IMP = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, relation=True, use_imp=True)
+SMALL_IMP_ONLY = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, relation=True, use_imp=True,
+                        use_spa=False)
 SMALL_CONCAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, att_type="base")
 FULL_CONCAT = Config(att_type="base")
 SMALL_QCAP = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, predictor="q-cap")
@@ -202,6 +207,18 @@ def make_weights(cfg: Config, seed: int = 1111, sharpen_att: float = 100.0,
             wn_linear("generator.attention.sequence.2", 1, Hd, 0.1 * sharpen_att)
         w["generator.fcnet.weight"] = _uniform(g, (cfg.ntoken, Hd), 0.1 * sharpen_cls)     # generator.py:165 (±0.1)
         w["generator.fcnet.bias"] = _uniform(g, (cfg.ntoken,), 0.1)
+
+    if cfg.relation and cfg.use_imp:
+        # the implicit branch's own GCN (encoder.py:211-219), unregistered tensors like the spatial one: gcn_imp.{i}.*
+        for i in range(cfg.conv_layer):
+            p = f"gcn_imp.{i}."
+            bv = 1.0 / math.sqrt(V)
+            w[p + "bias"] = _uniform(g, (cfg.num_labels, V), bv)
+            for d in range(3):
+                w[p + f"weight.{d}.weight"] = _uniform(g, (V, V), bv)
+            for nm in ("wa", "wb"):
+                w[p + f"dot_product.{nm}.weight"] = _uniform(g, (V, V), bv) * sharpen_gcn
+                w[p + f"dot_product.{nm}.bias"] = _uniform(g, (V,), bv)
     return w
 
 
@@ -438,22 +455,32 @@ def corr_graph_conv(feature, graph, W, p):
     return torch.bmm(alpha, conv), alpha
 
 
-def gcn(feature, graph, W, n_layer=1):
+def gcn(feature, graph, W, n_layer=1, prefix="gcn"):
     """GCN.forward (gcn.py:199-215): per layer conv → dropout(identity) → ReLU."""
     alphas = []
     for i in range(n_layer):
-        feature, alpha = corr_graph_conv(feature, graph, W, f"gcn.{i}.")
+        feature, alpha = corr_graph_conv(feature, graph, W, f"{prefix}.{i}.")
         alphas.append(alpha)
         feature = torch.relu(feature)
     return feature, alphas
 
 
-def relation_encoder(batch, W, n_layer=1):
-    """RelationEncoder.forward, spatial branch only (encoder.py:236-272)."""
+def relation_encoder(batch, W, n_layer=1, use_imp=False, use_spa=True):
+    """RelationEncoder.forward (encoder.py:236-272): the implicit branch (fully connected graph, ones - eye, its own GCN)
+    and / or the spatial branch (batch['graph']), outputs summed; ``alpha`` = the last branch's (encoder.py:256,263)."""
     out = base_encoder(batch, W)
-    graph = batch["graph"].to(out["v"].dtype)
-    new_v, alphas = gcn(out["v"], graph, W, n_layer)
-    out["v"] = torch.zeros_like(out["v"]) + new_v
+    v = out["v"]
+    output_v = torch.zeros_like(v)
+    alphas = []
+    if use_imp:
+        K = v.shape[1]
+        g_imp = (torch.ones(K, K) - torch.eye(K)).to(v.dtype).repeat(v.shape[0], 1, 1)       # encoder.py:231-234,255
+        new_v, alphas = gcn(v, g_imp, W, n_layer, prefix="gcn_imp")
+        output_v = output_v + new_v
+    if use_spa:
+        new_v, alphas = gcn(v, batch["graph"].to(v.dtype), W, n_layer)
+        output_v = output_v + new_v
+    out["v"] = output_v
     out["alpha"] = alphas
     return out
 
@@ -587,7 +614,8 @@ def compute_score(predict, target):
 
 def forward(batch, W, cfg: Config):
     """Wrapper.forward / get_att composition (wrapper.py:64-74,107-110)."""
-    enc = relation_encoder(batch, W, cfg.conv_layer) if cfg.relation else base_encoder(batch, W)
+    enc = (relation_encoder(batch, W, cfg.conv_layer, cfg.use_imp, cfg.use_spa) if cfg.relation
+           else base_encoder(batch, W))
     if cfg.predictor == "q-cap":
         logits = qcap_predictor(enc, W, cfg.neg_slope)
     elif cfg.predictor == "base-cap":

@@ -36,12 +36,23 @@ def build_reference(cfg: O.Config, W: dict):
                   decoder_hidden_dim=cfg.decoder_hidden_dim, rnn_layer=cfg.rnn_layer, ans_dim=cfg.ans_dim, cls_layer=2,
                   c_len=cfg.c_len, device="cpu", dropout=0.2, neg_slope=cfg.neg_slope, rnn_type=cfg.rnn_type,
                   att_type=cfg.att_type, conv_layer=cfg.conv_layer, conv_type="corr")
-    sd = {k: v for k, v in W.items() if not k.startswith("gcn.")}
+    if cfg.relation and (cfg.use_imp or not cfg.use_spa):
+        # set_model cannot reach use_imp / use_spa (encoder.py:36-48 does not pass them): build the reference's own
+        # RelationEncoder directly and put it in the Wrapper
+        from modules.encoder import RelationEncoder as RefRelationEncoder
+        m.encoder = RefRelationEncoder(ntoken=cfg.ntoken, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim,
+                                       rnn_layer=cfg.rnn_layer, v_dim=cfg.v_dim, device="cpu", dropout=0.2,
+                                       rnn_type=cfg.rnn_type, att_type=cfg.att_type, conv_layer=cfg.conv_layer,
+                                       conv_type="corr", use_imp=cfg.use_imp, use_spa=cfg.use_spa)
+    sd = {k: v for k, v in W.items() if not k.startswith("gcn")}
     m.load_state_dict(sd, strict=True)
     if cfg.relation:
-        for i, layer in enumerate(m.encoder.spatial_encoder.gcn):
-            lsd = {k[len(f"gcn.{i}."):]: v for k, v in W.items() if k.startswith(f"gcn.{i}.")}
-            layer.load_state_dict(lsd, strict=True)
+        for name, enc in (("gcn", m.encoder.spatial_encoder), ("gcn_imp", m.encoder.implicit_encoder)):
+            if enc is None:
+                continue
+            for i, layer in enumerate(enc.gcn):
+                lsd = {k[len(f"{name}.{i}."):]: v for k, v in W.items() if k.startswith(f"{name}.{i}.")}
+                layer.load_state_dict(lsd, strict=True)
     return m.eval()
 
 
@@ -202,6 +213,10 @@ def run_relation():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--imp-only" in sys.argv:
+        run_model("regat_imp_small", O.SMALL_REGAT_IMP, 8, 1111, 3003)
+        run_model("imp_only_small", O.SMALL_IMP_ONLY, 8, 1111, 3004)
+        sys.exit(0)
     if "--rnn-only" in sys.argv:
         run_model("gru2_small", O.SMALL_GRU2, 8, 1111, 9001)
         run_model("lstm2_small", O.SMALL_LSTM2, 8, 1111, 9002)
@@ -241,3 +256,5 @@ if __name__ == "__main__":
     run_model("gru2_small", O.SMALL_GRU2, 8, 1111, 9001)
     run_model("lstm2_small", O.SMALL_LSTM2, 8, 1111, 9002)
     run_model("lstm_full", O.FULL_LSTM, 4, 1111, 9003)
+    run_model("regat_imp_small", O.SMALL_REGAT_IMP, 8, 1111, 3003)
+    run_model("imp_only_small", O.SMALL_IMP_ONLY, 8, 1111, 3004)

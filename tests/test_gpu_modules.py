@@ -25,10 +25,20 @@ def build_model(cfg, W, device="cuda"):
                   ntoken=cfg.ntoken, v_dim=cfg.v_dim, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim,
                   decoder_hidden_dim=0, rnn_layer=cfg.rnn_layer, ans_dim=cfg.ans_dim, cls_layer=2, c_len=cfg.c_len, device=device,
                   dropout=0.2, rnn_type=cfg.rnn_type, att_type=cfg.att_type, conv_layer=cfg.conv_layer, conv_type="corr")
-    m.load_state_dict({k: v for k, v in W.items() if not k.startswith("gcn.")}, strict=True)
+    if cfg.relation and (cfg.use_imp or not cfg.use_spa):
+        # like the reference, set_model does not reach use_imp / use_spa: the encoder is built directly
+        from vqa_collection_b200.modules.encoder import RelationEncoder
+        m.encoder = RelationEncoder(ntoken=cfg.ntoken, embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim,
+                                    rnn_layer=cfg.rnn_layer, v_dim=cfg.v_dim, device=device, dropout=0.2, rnn_type=cfg.rnn_type,
+                                    att_type=cfg.att_type, conv_layer=cfg.conv_layer, conv_type="corr", use_imp=cfg.use_imp,
+                                    use_spa=cfg.use_spa).to(device)
+    m.load_state_dict({k: v for k, v in W.items() if not k.startswith("gcn")}, strict=True)
     if cfg.relation:
-        for i, layer in enumerate(m.encoder.spatial_encoder.gcn):
-            layer.load_state_dict({k[len(f"gcn.{i}."):]: v for k, v in W.items() if k.startswith(f"gcn.{i}.")})
+        for name, enc in (("gcn", m.encoder.spatial_encoder), ("gcn_imp", m.encoder.implicit_encoder)):
+            if enc is None:
+                continue
+            for i, layer in enumerate(enc.gcn):
+                layer.load_state_dict({k[len(f"{name}.{i}."):]: v for k, v in W.items() if k.startswith(f"{name}.{i}.")})
     return m.eval()
 
 
@@ -40,7 +50,8 @@ def _need_gpu():
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["updown_small", "regat_small", "updown_full", "regat_full", "concat_small",
-                                  "concat_full", "basecap_small", "basecap_full", "gru2_small", "lstm2_small", "lstm_full"])
+                                  "concat_full", "basecap_small", "basecap_full", "gru2_small", "lstm2_small", "lstm_full",
+                                  "regat_imp_small", "imp_only_small"])
 def test_wrapper_api_matches_reference(golden_dir, name, precision):
     import vqa_collection_b200 as pkg
     pkg.set_precision(precision)

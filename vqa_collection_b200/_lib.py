@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
 
 VQA_F32, VQA_BF16 = 0, 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -171,6 +171,7 @@ SYMBOLS = {
     "vqa_attention_pool": (c_int, [c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "vqa_graph_attention": (c_int, [C.POINTER(GraphAttentionArgs), c_void_p]),
+    "vqa_add_inplace": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "vqa_answer_scores": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vqa_caption_gate_scale": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                        c_void_p]),

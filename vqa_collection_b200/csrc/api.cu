@@ -56,6 +56,7 @@ int caption_gate_scale(const void*, const float*, const float*, int, int, int, i
 int seq_max(const void*, int, int, int, int, void*, cudaStream_t);
 int softmax_mul(const float*, const void*, int, int, int, void*, cudaStream_t);
 int attention_logits(const void*, int, const float*, int, const float*, int, int, int, int, int, float*, cudaStream_t);
+int add_inplace(void*, const void*, size_t, int, cudaStream_t);
 int attention_pool(const float*, int, float, const void*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int argmax_rows(const float*, int, int, int, int64_t*, cudaStream_t);
 int embedding_gather(const int64_t*, int, int, int, int, const void*, void*, cudaStream_t, void* zero_ptr = nullptr,
@@ -380,6 +381,10 @@ int vqa_softmax_mul(const float* d_z, const void* d_v, int B, int H, int dtype, 
   return softmax_mul(d_z, d_v, B, H, dtype, d_out, (cudaStream_t)stream);
 }
 
+int vqa_add_inplace(void* d_dst, const void* d_src, size_t n, int dtype, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return add_inplace(d_dst, d_src, n, dtype, (cudaStream_t)stream);
+}
 int vqa_attention_logits(const void* d_proj, int ldp, const float* d_q, int ldq, const float* d_w, int B, int K, int Hd,
                          int mode, int dtype, float* d_logits, void* stream) {
   if (int rc = require_sm100()) return rc;

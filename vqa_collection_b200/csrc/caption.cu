@@ -131,6 +131,30 @@ static int grid_for(size_t total) {
   return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
+// dst += src (the sum of the relation branches, encoder.py:257,264)
+template <typename T>
+__global__ void __launch_bounds__(256) add_inplace_kernel(T* __restrict__ dst, const T* __restrict__ src, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    float a[8], b[8];
+    load8(dst + i * 8, a);
+    load8(src + i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    store8(dst + i * 8, a);
+  }
+}
+
+int add_inplace(void* dst, const void* src, size_t n, int dtype, cudaStream_t s) {
+  VQA_REQUIRE(n % 8 == 0, "add_inplace: n=%zu must be a multiple of 8", n);
+  if (n == 0) return VQA_OK;
+  VQA_REQUIRE(dst && src, "add_inplace: NULL pointer");
+  const int grid = grid_for(n / 8);
+  if (dtype == VQA_BF16) add_inplace_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, n / 8);
+  else add_inplace_kernel<float><<<grid, 256, 0, s>>>((float*)dst, (const float*)src, n / 8);
+  VQA_LAUNCH_CHECK();
+  return VQA_OK;
+}
+
 int attention_logits(const void* proj, int ldp, const float* q, int ldq, const float* w, int B, int K, int Hd, int mode,
                      int dtype, float* out, cudaStream_t s) {
   VQA_REQUIRE(B >= 0 && K >= 1 && Hd >= 8 && Hd % 8 == 0 && ldp % 8 == 0 && ldq % 8 == 0 && (mode == 0 || mode == 1),

@@ -73,7 +73,9 @@ class BaseEncoder(nn.Module):
 
 
 class RelationEncoder(BaseEncoder):
-    """BaseEncoder + spatial-relation GCN over batch['graph']   (encoder.py:186-272).
+    """BaseEncoder + relation GCNs over the attended regions (encoder.py:186-272): the spatial branch over
+    batch['graph'] (default) and/or the implicit branch over the fully connected graph (``use_imp``; labels 1 off the
+    diagonal, 0 on it — encoder.py:231-234,255).  Their outputs are summed (encoder.py:257,264).
     Extension: when batch has 'bbox' (+'wh') and no 'graph', the labels are computed on device."""
 
     def __init__(self, ntoken: int, embed_dim: int, hidden_dim: int, rnn_layer: int, v_dim: int, device: str,
@@ -82,11 +84,14 @@ class RelationEncoder(BaseEncoder):
                  num_objs: int = 36):
         super().__init__(ntoken, embed_dim, hidden_dim, rnn_layer, v_dim, device, dropout, rnn_type, att_type)
         assert use_imp or use_spa or use_sem, 'Should use at least one relation'
-        if use_imp or use_sem:
-            raise NotImplementedError("only the spatial relation branch is built (reference default, encoder.py:202-204)")
-        self.implicit_encoder = None
-        self.spatial_encoder = GCN(in_dim=v_dim, out_dim=v_dim, num_labels=12, device=device, conv_layer=conv_layer,
-                                   conv_type=conv_type, dropout=dropout)
+
+        def make():
+            return GCN(in_dim=v_dim, out_dim=v_dim, num_labels=12, device=device, conv_layer=conv_layer,
+                       conv_type=conv_type, dropout=dropout)
+        self.implicit_encoder = make() if use_imp else None
+        self.spatial_encoder = make() if use_spa else None
+        self.num_objs = num_objs
+        self._imp_labels = None
 
     def graph_labels(self, batch):
         if 'graph' in batch:
@@ -96,12 +101,34 @@ class RelationEncoder(BaseEncoder):
         w, h = batch['wh']
         return ops.relation_labels(bbox, float(w), float(h))
 
+    def implicit_labels(self, B, K, device):
+        """the fully connected graph of encoder.py:231-234 as labels [B,K,K] u8 (1 off the diagonal)"""
+        if self._imp_labels is None or self._imp_labels.shape[:2] != (B, K) or self._imp_labels.device != device:
+            g = (torch.ones(K, K) - torch.eye(K)).to(torch.uint8)
+            self._imp_labels = g.unsqueeze(0).repeat(B, 1, 1).contiguous().to(device)
+        return self._imp_labels
+
     def forward(self, batch, graph_alpha=False):
         x, q_emb, att, _, _ = self._attend(batch, False, False)
-        labels = self.graph_labels(batch)
-        new_v, vsum, alphas = self.spatial_encoder(x, labels, graph_alpha, att=att, want_vsum=True)
+        B, K, V = x.shape
+        new_v = vsum = alphas = None
+        branches = []
+        if self.implicit_encoder is not None:
+            branches.append((self.implicit_encoder, self.implicit_labels(B, K, x.device)))
+        if self.spatial_encoder is not None:
+            branches.append((self.spatial_encoder, self.graph_labels(batch)))
+        for gcn, labels in branches:
+            v_b, vsum_b, alphas = gcn(x, labels, graph_alpha, att=att, want_vsum=True)   # like the reference, the LAST branch's α
+            if new_v is None:
+                new_v, vsum = v_b, vsum_b
+            else:
+                ops.add_(new_v, v_b)
+                ops.add_(vsum, vsum_b)
         if graph_alpha:
-            return alphas
+            return alphas if alphas is not None else []
+        if new_v is None:                              # use_sem only: no encoder exists for it (encoder.py:247 zeros)
+            new_v = torch.zeros((B, K, V), dtype=x.dtype, device=x.device)
+            vsum = torch.zeros((B, V), dtype=x.dtype, device=x.device)
         out = {'v': new_v, 'q': self.q_net(q_emb, out_dtype=torch.float32), 'v_att': att.unsqueeze(2), 'v_sum': vsum}
         if 'c' in batch:
             c_target = batch['c'].to(self.device)

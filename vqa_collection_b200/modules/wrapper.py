@@ -68,7 +68,7 @@ class Wrapper(nn.Module):
         """state_dict + the unregistered GCN tensors as gcn.{i}.* """
         W = {k: v for k, v in self.state_dict().items()}
         W.setdefault("encoder.embedding.weight", self.encoder.embedding.weight)      # PretrainedWordEmbedding: not a parameter
-        if isinstance(self.encoder, RelationEncoder):
+        if isinstance(self.encoder, RelationEncoder) and self.encoder.spatial_encoder is not None:
             for i, layer in enumerate(self.encoder.spatial_encoder.gcn):
                 for k, v in layer.state_dict().items():
                     W[f"gcn.{i}.{k}"] = v
@@ -78,6 +78,8 @@ class Wrapper(nn.Module):
         from ..engine import VQAEngine
         params = list(self.parameters())
         if isinstance(self.encoder, RelationEncoder):
+            if self.encoder.implicit_encoder is not None or self.encoder.spatial_encoder is None:
+                return None                                  # implicit / no spatial branch: module-level path
             for layer in self.encoder.spatial_encoder.gcn:
                 params += list(layer.parameters())
         key = (get_precision(),) + tuple((p._version, p.data_ptr()) for p in params)

@@ -481,6 +481,17 @@ def graph_attention_merged(Y, x, att, labels, wvec, c0, label_bias_lp, num_label
     return out, vsum, alpha
 
 
+def add_(dst, src):
+    """dst += src in place (same shape and dtype, numel % 8 == 0): the sum of the relation branches (encoder.py:257,264)."""
+    lib = L.load()
+    _require(dst, None, "dst")
+    _require(src, dst.dtype, "src")
+    if dst.shape != src.shape or not (dst.is_contiguous() and src.is_contiguous()):
+        raise ValueError("add_: shape mismatch")
+    L.check(lib.vqa_add_inplace(dst.data_ptr(), src.data_ptr(), dst.numel(), dtype_code(dst.dtype), _stream()))
+    return dst
+
+
 def answer_scores(label, target, want_dense=True, want_sum=False):
     """one_hot(label) ⊙ target (wrapper.py:16-22) → (dense [B,A] or None, per-question score [B], sum [1] or None)."""
     lib = L.load()
