@@ -73,6 +73,7 @@ SMALL = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200,
                relation=False)
 SMALL_REGAT = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200,
                      relation=True)
+SMALL_REGAT2 = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, relation=True, conv_layer=2)
 SMALL_REGAT_IMP = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, relation=True, use_imp=True)
 SMALL_IMP_ONLY = Config(ntoken=100, v_dim=256, embed_dim=64, hidden_dim=128, ans_dim=200, relation=True, use_imp=True,
                         use_spa=False)

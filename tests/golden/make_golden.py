@@ -213,6 +213,9 @@ def run_relation():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if "--regat2-only" in sys.argv:
+        run_model("regat2_small", O.SMALL_REGAT2, 8, 1111, 3005)
+        sys.exit(0)
     if "--imp-only" in sys.argv:
         run_model("regat_imp_small", O.SMALL_REGAT_IMP, 8, 1111, 3003)
         run_model("imp_only_small", O.SMALL_IMP_ONLY, 8, 1111, 3004)
@@ -258,3 +261,4 @@ if __name__ == "__main__":
     run_model("lstm_full", O.FULL_LSTM, 4, 1111, 9003)
     run_model("regat_imp_small", O.SMALL_REGAT_IMP, 8, 1111, 3003)
     run_model("imp_only_small", O.SMALL_IMP_ONLY, 8, 1111, 3004)
+    run_model("regat2_small", O.SMALL_REGAT2, 8, 1111, 3005)

@@ -24,7 +24,7 @@ def _relerr(a, b):
 
 @pytest.mark.parametrize("name", ["updown_small", "regat_small", "updown_full", "regat_full", "concat_small",
                                   "concat_full", "basecap_small", "basecap_full", "gru2_small", "lstm2_small", "lstm_full",
-                                  "regat_imp_small", "imp_only_small"])
+                                  "regat_imp_small", "imp_only_small", "regat2_small"])
 def test_forward_matches_reference(golden_dir, name):
     z, meta = _load(golden_dir, name)
     cfg = O.Config(**meta["cfg"])
