@@ -51,7 +51,7 @@ def _need_gpu():
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["updown_small", "regat_small", "updown_full", "regat_full", "concat_small",
                                   "concat_full", "basecap_small", "basecap_full", "gru2_small", "lstm2_small", "lstm_full",
-                                  "regat_imp_small", "imp_only_small"])
+                                  "regat_imp_small", "imp_only_small", "regat2_small"])
 def test_wrapper_api_matches_reference(golden_dir, name, precision):
     import vqa_collection_b200 as pkg
     pkg.set_precision(precision)
