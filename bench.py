@@ -239,7 +239,7 @@ def main():
     # the host cores this rank may count on (all cores / ranks on the box); 0 = pack everything, 1 = everything raw.
     # Which split wins depends on the box (cores and memory bandwidth per GPU, ranks sharing them), so the candidates are
     # timed for a few steps first (all ranks agree on the one with the best worst-rank time), then the winner is measured.
-    from vqa_collection_b200.engine import host_cores_per_rank, host_raw_chunk_period, host_pack_threads
+    from vqa_collection_b200.engine import host_cores_per_rank, host_pack_threads
 
     def time_host(period, steps):
         pack = args.precision == "bf16" and period != 1

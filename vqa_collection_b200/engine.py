@@ -11,7 +11,6 @@ Weights arrive under the reference's parameter names, e.g. from
 ``Wrapper.state_dict()`` plus the unregistered GCN tensors as ``gcn.{i}.*``.
 """
 import ctypes as C
-import math
 
 import torch
 

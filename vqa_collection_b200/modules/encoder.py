@@ -2,10 +2,10 @@
 import torch
 import torch.nn as nn
 
-from .. import compute_dtype, ops
+from .. import ops
 from .attention import set_att
 from .gcn import GCN
-from .modules import FCNet, SentenceEmbedding, PretrainedWordEmbedding, PreparedCache, as_compute, _no_training
+from .modules import FCNet, SentenceEmbedding, PretrainedWordEmbedding, PreparedCache, _no_training
 
 
 def set_encoder(encoder_type: str, ntoken: int, v_dim: int, embed_dim: int, hidden_dim: int, device: str,
