@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 9
+#define VQA_B200_ABI_VERSION 10
 
 typedef enum {
   VQA_OK = 0,
@@ -131,10 +131,18 @@ typedef struct {
    * bytes that are ZERO on entry (the call leaves them dirty).  NULL = off. */
   int64_t* d_argmax_label;
   void* d_argmax_ws;
+  /* launch shaping (bf16 tensor-core path; all 0 = the whole GEMM on the whole device): the call computes only the
+   * output tiles [tile_begin, tile_end) of the kernel's tile order (vqa_linear_tile_count gives the total) on at most
+   * cta_limit SMs, so that two calls on different streams can split one GEMM between two sets of SMs. */
+  int tile_begin, tile_end;
+  int cta_limit;
 } vqa_linear_args;
 
 int vqa_linear(const vqa_linear_args* args, void* stream);
 int vqa_linear_part_width(int dtype);
+/* number of output tiles (the unit of tile_begin / tile_end) the call would walk over; 0 when the shape takes a path
+ * without tile ranges (fp32) */
+int vqa_linear_tile_count(const vqa_linear_args* args);
 size_t vqa_linear_argmax_workspace_bytes(int M);
 
 /* ------------------------------------------------------------------------
@@ -416,6 +424,16 @@ typedef struct {
   void* d_v;                 /* [B,K,V] encoder output 'v', optional         */
   float* d_alpha;            /* [B,K,K], optional (relation)                 */
   uint8_t* d_labels_out;     /* [B,K,K], optional (relation + bbox)          */
+  /* Two-stream schedule (bf16 tensor-core path, B >= 512; 0 = every kernel on `stream`, in order).
+   * overlap = 1: the question encoder (gather, GRU on side_sms SMs with two interleaved row blocks per CTA pair,
+   * [W_q ; q_net]) runs on a library-owned side stream WHILE the question-independent projection of the region
+   * features runs on `stream` on the other SMs — ReGAT: x·[W0+W1; W2; WbᵀWa]ᵀ; Up-Down: ReLU(W_v x) stored as
+   * bf16 [B·K,H] (the ⊙q logit reduction then is its own streaming kernel).  When the encoder is done, its SMs
+   * compute the last side_tile_permille / 1000 of the projection's tiles.  The streams are joined before the
+   * attention; the call can be captured in a CUDA graph (the first, uncaptured call creates the side stream). */
+  int overlap;
+  int side_sms;              /* SMs of the side stream, even (0 = 64)                                        */
+  int side_tile_permille;    /* 0 = automatic (from the shapes); -1 = none                                   */
 } vqa_forward_args;
 
 size_t vqa_forward_workspace_bytes(const vqa_forward_args* args);

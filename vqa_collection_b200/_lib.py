@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
 
 VQA_F32, VQA_BF16 = 0, 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -32,6 +32,7 @@ class LinearArgs(C.Structure):
         ("d_mask", c_void_p), ("ld_mask", c_int), ("mask_dtype", c_int),
         ("leaky_slope", c_float), ("add_after_act", c_int), ("sigmoid", c_int),
         ("d_argmax_label", c_void_p), ("d_argmax_ws", c_void_p),
+        ("tile_begin", c_int), ("tile_end", c_int), ("cta_limit", c_int),
     ]
 
 
@@ -86,6 +87,7 @@ class ForwardArgs(C.Structure):
         ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("d_logits", c_void_p), ("d_label", c_void_p), ("d_att", c_void_p), ("d_q", c_void_p),
         ("d_v", c_void_p), ("d_alpha", c_void_p), ("d_labels_out", c_void_p),
+        ("overlap", c_int), ("side_sms", c_int), ("side_tile_permille", c_int),
     ]
 
 
@@ -163,6 +165,7 @@ SYMBOLS = {
     "vqa_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vqa_linear": (c_int, [C.POINTER(LinearArgs), c_void_p]),
     "vqa_linear_part_width": (c_int, [c_int]),
+    "vqa_linear_tile_count": (c_int, [C.POINTER(LinearArgs)]),
     "vqa_linear_argmax_workspace_bytes": (c_size_t, [c_int]),
     "vqa_gru_last_state": (c_int, [C.POINTER(GruArgs), c_void_p]),
     "vqa_gru_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

@@ -39,6 +39,7 @@ static const DevInfo& device() {
   return cache;
 }
 int sm_count() { const int n = device().sms; return n > 0 ? n : 148; }
+int current_device() { return device().dev; }
 int require_sm100() {
   const DevInfo& d = device();
   if (d.dev < 0) return fail(VQA_ERR_CUDA, "no CUDA device available (%s)", cudaGetErrorString(cudaGetLastError()));
@@ -75,7 +76,7 @@ int updown_train_step(const vqa_train_args&, cudaStream_t);
 int gru_persistent(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
                    void*, cudaStream_t);
 int gru_pair(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
-             void*, const GruTrainSave*, cudaStream_t);
+             void*, const GruTrainSave*, int sm_limit, cudaStream_t);
 
 bool pdl_enabled() {
   static int v = -1;
@@ -133,7 +134,8 @@ static GruWs carve_gru(void* base, int B, int T, int H, int E_pad, int dtype) {
   return w;
 }
 
-static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
+// sm_limit > 0: the persistent kernel may use at most that many SMs (vqa_forward's overlap mode)
+static int gru_last_state(const vqa_gru_args& a, cudaStream_t s, int sm_limit = 0) {
   VQA_REQUIRE(((a.d_tokens && a.d_emb) || a.d_x) && a.d_w_ih && a.d_w_hh && a.d_b_ih && a.d_b_hh &&
               (a.d_h_last || a.d_out_all), "vqa_gru_last_state: NULL pointer");
   VQA_REQUIRE(a.B >= 0 && a.T >= 1 && a.H >= 1 && a.E_pad >= 1, "vqa_gru_last_state: bad dims");
@@ -169,7 +171,7 @@ static int gru_last_state(const vqa_gru_args& a, cudaStream_t s) {
     }
     if (pair) {
       rc = gru_pair(X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
-                    a.d_h_last, a.d_h_last_lp, a.d_out_all, nullptr, s);
+                    a.d_h_last, a.d_h_last_lp, a.d_out_all, nullptr, sm_limit, s);
       if (rc != VQA_ERR_UNSUPPORTED) return rc;
     }
     return gru_persistent(X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
@@ -323,6 +325,10 @@ int vqa_linear(const vqa_linear_args* args, void* stream) {
   return linear_dispatch(*args, (cudaStream_t)stream);
 }
 int vqa_linear_part_width(int dtype) { return part_width(dtype); }
+int vqa_linear_tile_count(const vqa_linear_args* args) {
+  if (!args || args->dtype != VQA_BF16 || force_simt()) return 0;
+  return linear_tc_tile_count(*args);
+}
 size_t vqa_linear_argmax_workspace_bytes(int M) { return argmax_ws_bytes(M); }
 
 size_t vqa_gru_workspace_bytes(int B, int T, int H, int E_pad, int dtype) {
@@ -488,9 +494,14 @@ int vqa_adamax_step(const vqa_optim_tensor* h_tensors, int n_tensors, float beta
 }
 
 // ---- whole path --------------------------------------------------------------
+static bool overlap_mode(const vqa_forward_args& a) {
+  return a.overlap && a.dtype == VQA_BF16 && !force_simt() && a.d_wx_packed && a.d_wh_packed && a.d_bias_packed &&
+         a.B >= 512 && a.H % 64 == 0 && a.E_pad % 64 == 0 && a.H % 8 == 0;
+}
+
 struct FwdWs {
   void* gru; size_t gru_bytes;
-  float* h; void* h_lp; float* qq; float* parts; void* vsum; void* Y; void* joint; void* hid;
+  float* h; void* h_lp; float* qq; float* parts; void* vsum; void* Y; void* proj; void* joint; void* hid;
   void* amax; size_t amax_bytes;             // fused answer selection of the last classifier layer
   size_t bytes;
 };
@@ -512,6 +523,7 @@ static FwdWs carve_fwd(const vqa_forward_args& a, void* base) {
   w.parts = (float*)take((size_t)a.B * a.K * n_parts * 4);
   w.vsum = take((size_t)a.B * a.V * es);
   w.Y = a.relation ? take((size_t)a.B * a.K * (a.d_Wg3 ? 3 : 4) * a.V * es) : nullptr;
+  w.proj = (!a.relation && overlap_mode(a)) ? take((size_t)a.B * a.K * a.H * es) : nullptr;   // stored W_v projection
   w.joint = take((size_t)a.B * a.H * es);
   w.hid = take((size_t)a.B * 2 * a.H * es);
   w.bytes = off;
@@ -525,6 +537,42 @@ size_t vqa_forward_workspace_bytes(const vqa_forward_args* args) {
 
 static thread_local int g_last_forward_launches = 0;
 int vqa_forward_last_launch_count(void) { return g_last_forward_launches; }
+
+// side stream + fork / join events of the two-stream schedule, one set per (thread, device); created by the first
+// uncaptured call (stream creation is not a capturable operation)
+struct SideCtx { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; bool tried = false; };
+static SideCtx* side_ctx() {
+  static thread_local SideCtx ctx[64];
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) return nullptr;
+  SideCtx& c = ctx[dev];
+  if (!c.tried) {
+    c.tried = true;
+    // highest priority: when SMs free up, the block scheduler places the (latency-bound) encoder's CTAs first
+    int prio_lo = 0, prio_hi = 0;
+    (void)cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&c.s, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) != cudaSuccess) {
+      (void)cudaGetLastError();
+      c.s = nullptr;
+    }
+  }
+  return c.s ? &c : nullptr;
+}
+
+// Share (per mille) of the projection's tiles that the side SMs take once the question encoder is done: both sets of
+// SMs should finish together.  tile time ~ 12.5 us per 256 x 256 x 2048 pair tile, encoder ~ 10.5 us per GRU step + 30 us
+// (measured at H = 1024, profiles/); the engine can override the estimate (side_tile_permille).
+static int auto_side_permille(int tiles, int K, int T, int main_sms, int side_sms) {
+  const double tau = 12.5 * K / 2048.0, G = 10.5 * T + 30.0;
+  const double pt = main_sms / 2, ps = side_sms / 2;
+  const double t_end = (tiles * tau + ps * G) / (pt + ps);
+  double share = ps * (t_end - G) / tau / tiles;
+  if (share < 0.02) return 0;
+  if (share > 0.5) share = 0.5;
+  return (int)(share * 1000.0);
+}
 
 int vqa_forward(const vqa_forward_args* args, void* stream) {
   if (int rc = require_sm100()) return rc;
@@ -555,7 +603,56 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
       labels = a.d_labels_out;
     }
     VQA_REQUIRE(labels, "vqa_forward: relation path needs d_labels or d_bbox");
+    VQA_REQUIRE(a.d_att, "vqa_forward: relation path needs d_att");
   }
+  if (a.att_concat) VQA_REQUIRE(a.d_W1q && a.d_b1, "vqa_forward: att_concat needs d_W1q and d_b1");
+
+  // ---- schedule: everything on `s` in order, or (overlap) question encoder on the side stream `sq` while the
+  //      question-independent projection of the region features runs on `s` on the other SMs
+  SideCtx* side = overlap_mode(a) ? side_ctx() : nullptr;
+  const bool overlap = side != nullptr;
+  VQA_REQUIRE(overlap || !overlap_mode(a), "vqa_forward: overlap requested but the side stream could not be created");
+  const int sms = sm_count();
+  int side_sms = overlap ? ((a.side_sms > 0 ? a.side_sms : 64) & ~1) : 0;
+  if (overlap && (side_sms < 2 || side_sms > sms - 2)) side_sms = (sms / 2) & ~1;
+  const int main_sms = (sms - side_sms) & ~1;
+  cudaStream_t sq = overlap ? side->s : s;
+  if (overlap) {
+    VQA_CUDA_CHECK(cudaEventRecord(side->fork, s));
+    VQA_CUDA_CHECK(cudaStreamWaitEvent(sq, side->fork, 0));
+  }
+  const int pw = overlap && !a.relation ? a.H : part_width(a.dtype);   // unfused logits come as ONE part per region
+  const int n_parts = (a.H + pw - 1) / pw;
+  const int maps = a.d_Wg3 ? 3 : 4;
+
+  // the question-independent projection: the wide ReGAT GEMM on the raw features (x = a·v enters the graph attention
+  // through its coefficients, graph_attn_tc.cu), or — overlap only — the stored W_v projection of the Up-Down path
+  vqa_linear_args proj{};
+  if (a.relation) {
+    proj.d_A = a.d_img; proj.lda = a.V; proj.d_W = a.d_Wg3 ? a.d_Wg3 : a.d_Wg; proj.ldw = a.V; proj.M = a.B * a.K;
+    proj.N = maps * a.V; proj.K = a.V; proj.dtype = a.dtype; proj.mul_row_div = 1; proj.d_out = w.Y; proj.ldo = maps * a.V;
+    proj.out_dtype = a.dtype;
+  } else if (overlap) {
+    // 'new' attention: ReLU(s·W_v v + b) (attention.py:70); 'base': the bare v-half s·W1v v of the concat layer — its bias,
+    // the q-half and the ReLU follow in the logit kernel (attention.py:38-40)
+    proj.d_A = a.d_img; proj.lda = a.V; proj.d_W = a.d_Wv; proj.ldw = a.V; proj.M = a.B * a.K; proj.N = a.H; proj.K = a.V;
+    proj.dtype = a.dtype; proj.d_scale = a.d_sv; proj.mul_row_div = 1;
+    if (!a.att_concat) { proj.d_bias = a.d_bv; proj.relu = 1; }
+    proj.d_out = w.proj; proj.ldo = a.H; proj.out_dtype = a.dtype;
+  }
+  int split_tile = 0;                            // tiles [split_tile, end) go to the side SMs after the encoder
+  if (overlap) {
+    const int tiles = linear_tc_tile_count(proj);
+    int permille = a.side_tile_permille;
+    if (permille == 0) permille = auto_side_permille(tiles, a.V, a.T, main_sms, side_sms);
+    if (permille < 0) permille = 0;
+    if (permille > 900) permille = 900;
+    split_tile = tiles - (int)((long long)tiles * permille / 1000);
+    vqa_linear_args main_part = proj;
+    main_part.tile_begin = 0; main_part.tile_end = split_tile; main_part.cta_limit = main_sms;
+    if ((rc = linear_dispatch(main_part, s))) return rc;
+  }
+
   // 1. question encoder (encoder.py:159-160)
   vqa_gru_args g{};
   g.d_tokens = a.d_tokens; g.B = a.B; g.T = a.T; g.H = a.H; g.E_pad = a.E_pad; g.ntoken_rows = a.ntoken_rows;
@@ -563,52 +660,60 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
   g.d_b_hh = a.d_b_hh; g.d_wx_packed = a.d_wx_packed; g.d_wh_packed = a.d_wh_packed; g.d_bias_packed = a.d_bias_packed;
   g.d_workspace = w.gru; g.workspace_bytes = w.gru_bytes + w.amax_bytes;     // the tail (w.amax) comes back zeroed
   g.d_h_last = w.h; g.d_h_last_lp = w.h_lp;
-  if ((rc = gru_last_state(g, s))) return rc;
+  if ((rc = gru_last_state(g, sq, side_sms))) return rc;
   // 2. [W_q ; q_net] (attention.py:71, encoder.py:169): qq = ReLU(h Wqqᵀ s + b) f32 [B,2H]
   vqa_linear_args l{};
   if (!a.att_concat) {
     l.d_A = w.h_lp; l.lda = a.H; l.d_W = a.d_Wqq; l.ldw = a.H; l.M = a.B; l.N = 2 * a.H; l.K = a.H; l.dtype = a.dtype;
     l.d_scale = a.d_sqq; l.d_bias = a.d_bqq; l.relu = 1; l.mul_row_div = 1;
-    l.d_out = w.qq; l.ldo = 2 * a.H; l.out_dtype = VQA_F32;
-    if ((rc = linear_dispatch(l, s))) return rc;
+    l.d_out = w.qq; l.ldo = 2 * a.H; l.out_dtype = VQA_F32; l.cta_limit = side_sms;
+    if ((rc = linear_dispatch(l, sq))) return rc;
   } else {
     // ConcatAttention (attention.py:38-42): W1[v;q] = W1v v + W1q q, so the q-half is one [B,H] GEMM
     // (no ReLU) that enters the W_v GEMM as an additive row-broadcast operand; q_net separately.
-    VQA_REQUIRE(a.d_W1q && a.d_b1, "vqa_forward: att_concat needs d_W1q and d_b1");
     l.d_A = w.h_lp; l.lda = a.H; l.d_W = a.d_W1q; l.ldw = a.H; l.M = a.B; l.N = a.H; l.K = a.H; l.dtype = a.dtype;
     l.d_scale = a.d_sv; l.d_bias = a.d_b1; l.relu = 0; l.mul_row_div = 1;
-    l.d_out = w.qq; l.ldo = 2 * a.H; l.out_dtype = VQA_F32;
-    if ((rc = linear_dispatch(l, s))) return rc;
+    l.d_out = w.qq; l.ldo = 2 * a.H; l.out_dtype = VQA_F32; l.cta_limit = side_sms;
+    if ((rc = linear_dispatch(l, sq))) return rc;
     l = vqa_linear_args{};
     l.d_A = w.h_lp; l.lda = a.H; l.d_W = a.d_Wqq; l.ldw = a.H; l.M = a.B; l.N = a.H; l.K = a.H; l.dtype = a.dtype;
     l.d_scale = a.d_sqq; l.d_bias = a.d_bqq; l.relu = 1; l.mul_row_div = 1;
-    l.d_out = w.qq + a.H; l.ldo = 2 * a.H; l.out_dtype = VQA_F32;
+    l.d_out = w.qq + a.H; l.ldo = 2 * a.H; l.out_dtype = VQA_F32; l.cta_limit = side_sms;
+    if ((rc = linear_dispatch(l, sq))) return rc;
+  }
+  if (overlap) {
+    // the encoder's SMs take the tail of the projection, then the streams join
+    vqa_linear_args side_part = proj;
+    side_part.tile_begin = split_tile; side_part.tile_end = 0; side_part.cta_limit = side_sms;
+    if ((rc = linear_dispatch(side_part, sq))) return rc;
+    VQA_CUDA_CHECK(cudaEventRecord(side->join, sq));
+    VQA_CUDA_CHECK(cudaStreamWaitEvent(s, side->join, 0));
+  }
+  // 3. attention logits (attention.py:70-75 / :38-42)
+  if (overlap && !a.relation) {
+    // the projection is stored: reduce it against the question half, one warp per region row
+    if ((rc = attention_logits(w.proj, a.H, w.qq, 2 * a.H, a.d_wlin, a.B, a.K, a.H, a.att_concat ? 1 : 0, a.dtype, w.parts, s)))
+      return rc;
+  } else {
+    // W_v projection fused with ⊙Qp (or + the q-half) and the 1-wide logit layer: the [B·K,H] projection never
+    // reaches HBM
+    l = vqa_linear_args{};
+    l.d_A = a.d_img; l.lda = a.V; l.d_W = a.d_Wv; l.ldw = a.V; l.M = a.B * a.K; l.N = a.H; l.K = a.V; l.dtype = a.dtype;
+    l.d_scale = a.d_sv; l.relu = 1; l.mul_row_div = 1;
+    if (!a.att_concat) { l.d_bias = a.d_bv; l.d_mul = w.qq; l.ld_mul = 2 * a.H; l.mul_row_div = a.K; }
+    else { l.d_add = w.qq; l.ld_add = 2 * a.H; l.add_row_div = a.K; }
+    l.d_logit_w = a.d_wlin; l.d_out = w.parts; l.ldo = n_parts; l.out_dtype = VQA_F32;
     if ((rc = linear_dispatch(l, s))) return rc;
   }
-  // 3. W_v projection fused with ⊙Qp (or + the q-half) and the 1-wide logit layer (attention.py:70-75 / :38-42)
-  const int pw = part_width(a.dtype);
-  const int n_parts = (a.H + pw - 1) / pw;
-  l = vqa_linear_args{};
-  l.d_A = a.d_img; l.lda = a.V; l.d_W = a.d_Wv; l.ldw = a.V; l.M = a.B * a.K; l.N = a.H; l.K = a.V; l.dtype = a.dtype;
-  l.d_scale = a.d_sv; l.relu = 1; l.mul_row_div = 1;
-  if (!a.att_concat) { l.d_bias = a.d_bv; l.d_mul = w.qq; l.ld_mul = 2 * a.H; l.mul_row_div = a.K; }
-  else { l.d_add = w.qq; l.ld_add = 2 * a.H; l.add_row_div = a.K; }
-  l.d_logit_w = a.d_wlin; l.d_out = w.parts; l.ldo = n_parts; l.out_dtype = VQA_F32;
-  if ((rc = linear_dispatch(l, s))) return rc;
   // 4. softmax over K + weighted sum (attention.py:86, encoder.py:166, predictor.py:85)
   if (!a.relation) {
     if ((rc = attention_pool(w.parts, n_parts, a.b_lin, a.d_img, a.B, a.K, a.V, a.dtype, a.d_att ? a.d_att : nullptr,
                              w.vsum, a.d_v, s))) return rc;
   } else {
     float* att = a.d_att;
-    VQA_REQUIRE(att, "vqa_forward: relation path needs d_att");
     if ((rc = attention_pool(w.parts, n_parts, a.b_lin, a.d_img, a.B, a.K, a.V, a.dtype, att, nullptr, nullptr, s))) return rc;
-    // 5. wide projection of the raw features + relation-masked graph attention (gcn.py)
-    const int maps = a.d_Wg3 ? 3 : 4;
-    l = vqa_linear_args{};
-    l.d_A = a.d_img; l.lda = a.V; l.d_W = a.d_Wg3 ? a.d_Wg3 : a.d_Wg; l.ldw = a.V; l.M = a.B * a.K; l.N = maps * a.V; l.K = a.V;
-    l.dtype = a.dtype; l.mul_row_div = 1; l.d_out = w.Y; l.ldo = maps * a.V; l.out_dtype = a.dtype;
-    if ((rc = linear_dispatch(l, s))) return rc;
+    // 5. wide projection of the raw features (already done in overlap mode) + relation-masked graph attention (gcn.py)
+    if (!overlap && (rc = linear_dispatch(proj, s))) return rc;
     vqa_graph_attention_args ga{};
     ga.d_Y = w.Y; ga.ldy = maps * a.V; ga.d_att = att; ga.d_labels = labels; ga.d_label_bias = a.d_label_bias;
     ga.num_labels = a.num_labels; ga.d_ba = a.d_ba; ga.d_bb = a.d_bb; ga.B = a.B; ga.K = a.K; ga.V = a.V; ga.dtype = a.dtype;

@@ -42,6 +42,22 @@ void reset_launch_count();
 
 int require_sm100();          // VQA_OK or VQA_ERR_UNSUPPORTED
 int sm_count();
+int current_device();         // cudaGetDevice, -1 when there is none
+
+// cudaFuncSetAttribute / occupancy answers are per DEVICE, not per process: one of these per call site remembers which
+// devices have been set up (a second device in one process — the reference's `decoder_device`, main.py:88 — would
+// otherwise launch with the 48 KB default and fail).  Devices >= 64 are simply set up on every call.
+struct DeviceOnce {
+  unsigned long long done = 0;
+  bool need(int dev) const { return dev < 0 || dev >= 64 || !((done >> dev) & 1ull); }
+  void mark(int dev) { if (dev >= 0 && dev < 64) done |= 1ull << dev; }
+};
+// a small per-device integer cache (-1 = not computed yet)
+struct DeviceInt {
+  int v[64];
+  DeviceInt() { for (int i = 0; i < 64; ++i) v[i] = -1; }
+  int& at(int dev) { return v[(dev >= 0 && dev < 64) ? dev : 0]; }
+};
 
 inline size_t elem_size(int dtype) { return dtype == VQA_BF16 ? 2 : 4; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -129,5 +145,6 @@ struct GruTrainSave { float *R, *Z, *N, *HN, *Hs; };      // f32 [T,B,H] each; H
 int linear_simt(const vqa_linear_args& a, cudaStream_t s);
 int linear_tc(const vqa_linear_args& a, cudaStream_t s);
 int linear_tc_part_width();
+int linear_tc_tile_count(const vqa_linear_args& a);
 
 }  // namespace vqa

@@ -57,6 +57,7 @@ struct Params {
   const float* logit_w;
   void* out; int ldo; int out_bf16; int n_parts;
   int tiles_m, tiles_n;
+  int tile_begin, tile_end;                  // this launch walks tiles [tile_begin, tile_end) of the tile order
   float leaky_slope; int add_after_act; int sigmoid;
   // fused lowest-index argmax over n (wrapper.py:14): keys u64 [M] (value order bits << 32 | ~n), per-row-block tile
   // counters [tiles_m] — both zero on entry — and the int64 labels written by the LAST tile of each row block
@@ -87,8 +88,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // PAIR: the pair walks over (row-block pair, n_blk) tiles; this CTA owns row block 2*mp + rank of each
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   const bool lead = crank == 0;
-  const int num_tiles = PAIR ? ((p.tiles_m + 1) / 2) * p.tiles_n : p.tiles_m * p.tiles_n;
-  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_tiles = p.tile_end;
+  const int tile0 = p.tile_begin + (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   auto tile_m = [&](int tile) { return PAIR ? 2 * (tile / p.tiles_n) + (int)crank : tile / p.tiles_n; };
   const int num_kb = (p.K + BK - 1) / BK;      // K tail: TMA zero-fills both operands
@@ -414,6 +415,14 @@ static int make_tensor_map_mn(CUtensorMap* map, const void* ptr, long long k_row
   return make_tensor_map_bf16(map, ptr, k_rows, mn_cols, ld, BK);
 }
 
+// [tile_begin, tile_end) of the call clamped to the kernel's tile count
+static void tile_range(const vqa_linear_args& a, int total, int* begin, int* end) {
+  int b = a.tile_begin > 0 ? a.tile_begin : 0;
+  int e = (a.tile_end > 0 && a.tile_end < total) ? a.tile_end : total;
+  if (b > e) b = e;
+  *begin = b; *end = e;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int launch(const vqa_linear_args& a, cudaStream_t s) {
   using C = Cfg<BN>;
@@ -440,13 +449,17 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
     p.amax_label = (long long*)a.d_argmax_label;
   }
   auto kern = linear_tc_kernel<BN, A_MN, B_MN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr;                            // per device, not per process
+  const int dev = current_device();
+  if (attr.need(dev)) {
     VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr.mark(dev);
   }
-  const int tiles = p.tiles_m * p.tiles_n;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  tile_range(a, p.tiles_m * p.tiles_n, &p.tile_begin, &p.tile_end);
+  const int tiles = p.tile_end - p.tile_begin;
+  if (tiles <= 0) return VQA_OK;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  if (a.cta_limit > 0 && a.cta_limit < grid) grid = a.cta_limit;
   VQA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)C::SMEM_BYTES, s, tmA, tmW, p));
   VQA_LAUNCH_CHECK();
   return VQA_OK;
@@ -454,11 +467,13 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
 
 // 256 x 256 tiles on CTA pairs (tcgen05 cta_group::2) for the large K-major GEMMs.  VQA_ERR_UNSUPPORTED = the device cannot
 // hold the pairs (or VQA_B200_GEMM_PAIR=0): the caller falls back to one CTA per tile.
-static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
+// how many CTA pairs of the 256 x 256 kernel the current device holds at once (0 = pairs unusable)
+static int pairs_resident_on_device() {
   constexpr int BN = 256;
   using C = Cfg<BN, true>;
   auto kern = linear_tc_kernel<BN, false, false, true>;
-  static int pairs_resident = -1;
+  static DeviceInt cache;
+  int& pairs_resident = cache.at(current_device());
   if (pairs_resident < 0) {
     const char* e = getenv("VQA_B200_GEMM_PAIR");
     pairs_resident = 0;
@@ -474,6 +489,14 @@ static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
     }
     (void)cudaGetLastError();
   }
+  return pairs_resident;
+}
+
+static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
+  constexpr int BN = 256;
+  using C = Cfg<BN, true>;
+  auto kern = linear_tc_kernel<BN, false, false, true>;
+  const int pairs_resident = pairs_resident_on_device();
   if (pairs_resident <= 0) return VQA_ERR_UNSUPPORTED;
   CUtensorMap tmA, tmW;
   int rc;
@@ -489,8 +512,11 @@ static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
   p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
   p.leaky_slope = a.leaky_slope; p.add_after_act = a.add_after_act; p.sigmoid = a.sigmoid;
   p.amax_keys = nullptr; p.amax_cnt = nullptr; p.amax_label = nullptr;
-  const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
-  const int pairs = pair_tiles < pairs_resident ? pair_tiles : pairs_resident;
+  tile_range(a, ((p.tiles_m + 1) / 2) * p.tiles_n, &p.tile_begin, &p.tile_end);
+  const int pair_tiles = p.tile_end - p.tile_begin;
+  if (pair_tiles <= 0) return VQA_OK;
+  int pairs = pair_tiles < pairs_resident ? pair_tiles : pairs_resident;
+  if (a.cta_limit > 0 && a.cta_limit / 2 < pairs) pairs = a.cta_limit / 2 > 0 ? a.cta_limit / 2 : 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
   cudaLaunchAttribute at[2];
@@ -502,35 +528,45 @@ static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
   return VQA_OK;
 }
 
-template <bool A_MN, bool B_MN>
-static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
-  // Large GEMMs (a tile for every SM at BN = 256) are tensor-bound: widest tile.  Small-M layers are bound by
-  // what one SM can pull in per tile — (BM + BN)·K operand bytes — times the number of waves, so pick the BN
-  // that minimises waves x (BM + BN); ties go to the wider tile (fewer operand bytes in total).
-  // Measured on the 3129-way classifier (M = 1024, K = 2048): BN = 128 -> 200 tiles = 2 waves, 30 us;
-  // BN = 192 -> 136 tiles = 1 wave.
+// Tile shape of a call.  Large GEMMs (a tile for every SM at BN = 256) are tensor-bound: widest tile, on CTA pairs when
+// there are at least two 256-wide tiles per SM (only whole 256-wide N tiles — the shapes of the path: N = 1024, 6144;
+// pairs on narrower tiles for the small-M layers were measured: no gain, those layers are bound by launch / fill / drain
+// latency, not by operand ingest).  Small-M layers are bound by what one SM can pull in per tile — (BM + BN)·K operand
+// bytes — times the number of waves, so pick the BN that minimises waves x (BM + BN); ties go to the wider tile.
+// Measured on the 3129-way classifier (M = 1024, K = 2048): BN = 128 -> 200 tiles = 2 waves, 30 us; BN = 192 -> 136
+// tiles = 1 wave.
+struct Plan { int bn; bool pair; int tiles; };
+static Plan plan_tiles(const vqa_linear_args& a, bool mn_major) {
   const int tiles_m = (a.M + BM - 1) / BM;
   const int sms = sm_count();
+  Plan pl{256, false, 0};
   if (a.d_logit_w || tiles_m * ((a.N + 255) / 256) >= sms) {
-    if constexpr (!A_MN && !B_MN) {
-      // many tiles per SM: CTA pairs pay.  Only whole 256-wide N tiles (the shapes of the path: N = 1024, 6144).  Pairs on
-      // narrower tiles for the small-M layers were tried and measured: no gain (365 vs 368 us per Up-Down step) — those
-      // layers are bound by launch / fill / drain latency, not by operand ingest.
-      if (tiles_m * ((a.N + 255) / 256) >= 2 * sms && a.N % 256 == 0 && !a.d_argmax_label) {
-        const int rc = launch_pair(a, s);
-        if (rc != VQA_ERR_UNSUPPORTED) return rc;
-      }
+    if (!mn_major && tiles_m * ((a.N + 255) / 256) >= 2 * sms && a.N % 256 == 0 && !a.d_argmax_label &&
+        pairs_resident_on_device() > 0)
+      pl.pair = true;
+  } else {
+    int best_cost = 1 << 30;
+    for (int bn : {256, 192, 128, 64}) {
+      if (bn == 192 && mn_major) continue;           // MN-major operand tiles come in 64-wide atoms: 256 / 128 / 64 only
+      const int tiles = tiles_m * ((a.N + bn - 1) / bn);
+      const int cost = ((tiles + sms - 1) / sms) * (BM + bn);
+      if (cost < best_cost) { best_cost = cost; pl.bn = bn; }
     }
-    return launch<256, A_MN, B_MN>(a, s);
   }
-  int best_bn = 256, best_cost = 1 << 30;
-  for (int bn : {256, 192, 128, 64}) {
-    if (bn == 192 && (A_MN || B_MN)) continue;       // MN-major operand tiles come in 64-wide atoms: 256 / 128 / 64 only
-    const int tiles = tiles_m * ((a.N + bn - 1) / bn);
-    const int cost = ((tiles + sms - 1) / sms) * (BM + bn);
-    if (cost < best_cost) { best_cost = cost; best_bn = bn; }
+  pl.tiles = (pl.pair ? (tiles_m + 1) / 2 : tiles_m) * ((a.N + pl.bn - 1) / pl.bn);
+  return pl;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
+  const Plan pl = plan_tiles(a, A_MN || B_MN);
+  if constexpr (!A_MN && !B_MN) {
+    if (pl.pair) {
+      const int rc = launch_pair(a, s);
+      if (rc != VQA_ERR_UNSUPPORTED) return rc;
+    }
   }
-  switch (best_bn) {
+  switch (pl.bn) {
     case 256: return launch<256, A_MN, B_MN>(a, s);
     case 192:
       if constexpr (!A_MN && !B_MN) return launch<192, A_MN, B_MN>(a, s);
@@ -543,6 +579,11 @@ static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
 }  // namespace tc
 
 int linear_tc_part_width() { return 256; }
+
+int linear_tc_tile_count(const vqa_linear_args& a) {
+  if (a.M <= 0) return 0;
+  return tc::plan_tiles(a, a.trans_a || a.trans_w).tiles;
+}
 
 int linear_tc(const vqa_linear_args& a, cudaStream_t s) {
   VQA_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0 && (uintptr_t)a.d_A % 16 == 0 && (uintptr_t)a.d_W % 16 == 0,

@@ -457,10 +457,10 @@ int graph_attention_tc(const vqa_graph_attention_args& a, cudaStream_t s) {
   static int rev = -1;
   if (rev < 0) { const char* e = getenv("VQA_B200_GAT_REVERSE"); rev = (e && e[0] == '1') ? 1 : 0; }
   p.rev = rev;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr;                            // per device, not per process
+  if (attr.need(current_device())) {
     VQA_CUDA_CHECK(cudaFuncSetAttribute(graph_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    attr.mark(current_device());
   }
   const int grid = a.B < sm_count() ? a.B : sm_count();
   VQA_CUDA_CHECK(launch_pdl(graph_attention_tc_kernel, dim3(grid), dim3(THREADS), (size_t)SMEM_BYTES, s, tmQ, tmX, tmW, tmPS,

@@ -16,6 +16,14 @@
 // Barriers: TMA of both CTAs counts bytes on the LEADER's full barrier (cp.async.bulk.tensor
 // .cta_group::2); tcgen05.commit multicasts the stage release and "accumulator ready" to both CTAs;
 // the epilogue warps of both CTAs release the accumulator on the leader's barrier (mapa + remote arrive).
+//
+// ROW-BLOCK INTERLEAVING (RB = 2): a step of one row block is a serial chain — publish h_t -> acquire ->
+// TMA -> MMA -> gates — of which only a third is tensor work, so with one row block per pair the tensor
+// core idles for two thirds of every step (ncu: tensor pipe 48 %).  With RB = 2 a pair owns TWO independent
+// 256-row blocks and works on them alternately ("jobs" j = t·RB + b, accumulator j mod NACC): while block
+// 0 waits for its neighbours' h_t, the tensor core runs block 1.  Same step latency, HALF the SMs — the
+// other half of the device is free for question-independent work (the wide ReGAT projection / the W_v
+// projection run there at the same time, api.cu `overlap`).
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -33,11 +41,12 @@ constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;   // 640
 constexpr int W_PREFETCH = 4;
 constexpr int A_BYTES = BM * BK * 2;              // 16 KB
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_STRIDE = 256;
 
 // UNITS = hidden units per CTA pair: 64 normally; 32 when the batch is so small that 64-unit tiles would leave
 // half of the SMs idle (B <= 512 at H = 1024) — twice the CTAs, half the W tile and half the gate math per CTA.
 template <int UNITS> struct Cfg {
+  static constexpr int ACC_STRIDE = 4 * UNITS;             // columns of one accumulator: [r|z|n] x 2 halves, then n_x
+  static constexpr int NACC = TMEM_COLS / ACC_STRIDE;      // accumulators in flight: 2 (64 units) / 4 (32 units)
   static constexpr int HALF_UNITS = UNITS / 2;             // units whose W rows one CTA holds
   static constexpr int UPT = UNITS / (EPI_WARPS / 4);      // units per epilogue thread (16 / 8)
   static constexpr int W_BYTES = 3 * HALF_UNITS * BK * 2;  // this CTA's half of the W tile (12 KB / 6 KB)
@@ -54,7 +63,7 @@ struct Params {
   float* h_last;                // [B,H] f32 or NULL
   __nv_bfloat16* h_last_lp;     // [B,H] bf16 or NULL
   __nv_bfloat16* h_all;         // every state, or NULL: [B,T,H] (sequence form, see gru_tc.cu) or, time-major, [T,Bfull,H]
-  int* counter;                 // per-row-block arrival counters, zero on entry
+  int* counter;                 // per-row-block (128 rows) arrival counters, zero on entry
   // training form (train.cu): states time-major, gates saved for the backward pass (f32 [T,Bfull,H] each, chunk offset applied)
   int time_major, Bfull, b0;
   float *save_r, *save_z, *save_n, *save_hn, *save_h;   // save_h: slot t = state AFTER step t
@@ -63,13 +72,14 @@ struct Params {
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
-template <int UNITS>
+template <int UNITS, int RB>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH0,
                 const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmWx,
                 const __grid_constant__ CUtensorMap tmWh, const Params p) {
   using C = Cfg<UNITS>;
   constexpr int HALF_UNITS = C::HALF_UNITS, UPT = C::UPT, STAGE_BYTES = C::STAGE_BYTES, STAGES = C::STAGES, COL_NI = C::COL_NI;
+  constexpr int ACC_STRIDE = C::ACC_STRIDE, NACC = C::NACC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -78,18 +88,21 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + NACC + a); };
+  static_assert(8 * (2 * STAGES + 2 * NACC + 1) <= 256, "barrier block");
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * NACC);
   volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * NACC));
   float* bias_s = reinterpret_cast<float*>(base_ptr + STAGES * STAGE_BYTES + 256);   // [4][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();          // 0 = leader of the pair
   const bool lead = crank == 0;
   const int pid = blockIdx.x >> 1;
-  const int m_blk = 2 * (pid / p.tiles_n) + (int)crank, n_blk = pid % p.tiles_n;
-  const int m0 = m_blk * BM, u0 = n_blk * UNITS;
+  const int grp = pid / p.tiles_n, n_blk = pid % p.tiles_n;
+  // the pair owns RB blocks of 256 rows; this CTA's 128 rows of block b are row block m_blk_of(b)
+  auto m_blk_of = [&](int b) { return 2 * (grp * RB + b) + (int)crank; };
+  const int u0 = n_blk * UNITS;
   const int kb_x = p.E_pad / BK, kb_h = p.H / BK;
 
   if (warp == 0 && lane == 0) {
@@ -98,7 +111,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
+    for (int a = 0; a < NACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
@@ -125,6 +138,8 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = 0; t < p.T; ++t) {
+       for (int b = 0; b < RB; ++b) {
+        const int m_blk = m_blk_of(b), m0 = m_blk * BM;
         for (int kb = 0; kb < kb_x; ++kb) {                       // x-part: no dependence on h
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
@@ -161,6 +176,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
+       }
       }
     }
   } else if (warp == 1) {
@@ -170,9 +186,11 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       constexpr uint32_t idesc_n = make_idesc_bf16(2 * BM, UNITS);         // M = 256, N = 64 (32): n rows of both halves
       constexpr uint32_t N_ROW_OFF = (2 * HALF_UNITS * BK * 2) >> 4;       // the n rows of a half tile
       int stage = 0; uint32_t phase = 0;
+      uint32_t job = 0;                                  // j = t·RB + b: accumulator j mod NACC, its (j / NACC)-th use
       for (int t = 0; t < p.T; ++t) {
-        const int acc = t & 1;
-        const uint32_t acc_phase = (uint32_t)(t >> 1) & 1u;
+       for (int b = 0; b < RB; ++b, ++job) {
+        const uint32_t acc = job % NACC;
+        const uint32_t acc_phase = (job / NACC) & 1u;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d = tmem_base + acc * ACC_STRIDE;
@@ -202,31 +220,38 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
         }
         umma_commit_2cta(tfull_bar(acc), 0b11);
+       }
       }
     }
   } else if (warp >= EPI_WARP0) {
-    // ===== gate epilogue (both CTAs, own 128 rows): thread = (batch row, 16 units), fp32 state in registers =====
+    // ===== gate epilogue (both CTAs, own 128 rows of every block): thread = (batch row, 16 units), fp32 state in registers =====
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int uh = (warp - EPI_WARP0) >> 2;          // which 16-unit slice of the 64 units
     const int et = threadIdx.x - EPI_WARP0 * 32;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.B;
     const int ub = uh * UPT;                         // first unit (within the tile) of this thread
     const int colb = (ub / HALF_UNITS) * (3 * HALF_UNITS) + (ub % HALF_UNITS);   // column of r for unit ub
-    float h[UPT];
+    float h[RB][UPT];
 #pragma unroll
-    for (int j = 0; j < UPT; ++j) h[j] = 0.f;
+    for (int b = 0; b < RB; ++b)
+#pragma unroll
+      for (int j = 0; j < UPT; ++j) h[b][j] = 0.f;
+    uint32_t job = 0;
     for (int t = 0; t < p.T; ++t) {
-      const int acc = t & 1;
-      const uint32_t acc_phase = (uint32_t)(t >> 1) & 1u;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
-      const uint32_t trow = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
       const bool last = (t == p.T - 1);
       const size_t slot = (size_t)t * p.Bfull * p.H;             // time-major slot of this step
       __nv_bfloat16* hdst = p.h_all ? p.h_all + (p.time_major ? slot : (size_t)t * p.H)
                                     : ((last && p.h_last_lp) ? p.h_last_lp : p.h_op[t & 1]);
       const size_t h_ld = (p.h_all && !p.time_major) ? (size_t)p.T * p.H : (size_t)p.H;
+#pragma unroll
+      for (int b = 0; b < RB; ++b, ++job) {
+      const int m_blk = m_blk_of(b);
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.B;
+      const uint32_t acc = job % NACC;
+      const uint32_t acc_phase = (job / NACC) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t trow = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int c = 0; c < UPT; c += 8) {
         uint32_t vr[8], vz[8], vni[8], vnh[8];
@@ -243,8 +268,8 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const float nh = (__uint_as_float(vnh[j]) - __uint_as_float(vni[j])) + bias_s[3 * UNITS + ub + c + j];
           const float pn = __uint_as_float(vni[j]) + bias_s[2 * UNITS + ub + c + j] + r * nh;
           const float n = tanh_fast(pn);
-          const float hn = (1.f - z) * n + z * h[c + j];
-          h[c + j] = hn;
+          const float hn = (1.f - z) * n + z * h[b][c + j];
+          h[b][c + j] = hn;
           o[j] = hn;
         }
         if (row_ok) {
@@ -272,7 +297,8 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (saving) {
         // Training form: what the backward pass needs (train.cu) is written AFTER h_t has been published, so the
         // 20 extra 16-byte stores per thread stay out of the step-to-step dependency chain; the gates are
-        // recomputed from the accumulators, which are released only now (the next step uses the other buffer).
+        // recomputed from the accumulators, which are released only now (the block's next job uses another buffer
+        // or, with NACC == RB, waits for this release).
 #pragma unroll
         for (int c = 0; c < UPT; c += 8) {
           uint32_t vr[8], vz[8], vni[8], vnh[8];
@@ -288,7 +314,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             gz[j] = sigmoid_fast(__uint_as_float(vz[j]) + bias_s[UNITS + ub + c + j]);
             ghn[j] = (__uint_as_float(vnh[j]) - __uint_as_float(vni[j])) + bias_s[3 * UNITS + ub + c + j];
             gn[j] = tanh_fast(__uint_as_float(vni[j]) + bias_s[2 * UNITS + ub + c + j] + gr[j] * ghn[j]);
-            hs[j] = h[c + j];
+            hs[j] = h[b][c + j];
           }
           if (row_ok) {
             const size_t off = slot + (size_t)row * p.H + u0 + ub + c;
@@ -300,12 +326,17 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
       }
+      }
     }
-    if (row_ok && p.h_last) {
-      float* dst = p.h_last + (size_t)row * p.H + u0 + ub;
 #pragma unroll
-      for (int j = 0; j < UPT; j += 4)
-        *reinterpret_cast<float4*>(dst + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+    for (int b = 0; b < RB; ++b) {
+      const int row = m_blk_of(b) * BM + q * 32 + lane;
+      if (row < p.B && p.h_last) {
+        float* dst = p.h_last + (size_t)row * p.H + u0 + ub;
+#pragma unroll
+        for (int j = 0; j < UPT; j += 4)
+          *reinterpret_cast<float4*>(dst + j) = make_float4(h[b][j], h[b][j + 1], h[b][j + 2], h[b][j + 3]);
+      }
     }
   }
 
@@ -321,45 +352,52 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // Same contract as gru_persistent (gru_tc.cu).  With `save` (training form): h_all is time-major [T,B,H] (slot t = state
 // after step t) and the gates r, z, n, W_hn·h + b_hn and the f32 states are stored per step for the backward pass.  Returns VQA_ERR_UNSUPPORTED (without setting the error text as a
 // failure of the call) when the pair launch is not possible; the caller then uses the single-CTA kernel.
-template <int UNITS>
+// sm_limit > 0: use at most that many SMs (the caller runs something else on the rest at the same time).
+template <int UNITS, int RB>
 static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void* wx_p, const void* wh_p,
                       const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
-                      const GruTrainSave* save, cudaStream_t s) {
+                      const GruTrainSave* save, int sm_limit, cudaStream_t s) {
   using namespace grup;
   using C = Cfg<UNITS>;
   constexpr int HALF_UNITS = C::HALF_UNITS, SMEM_BYTES = C::SMEM_BYTES;
-  auto kernel = gru_pair_kernel<UNITS>;
+  auto kernel = gru_pair_kernel<UNITS, RB>;
   if (H % PACK_UNITS != 0 || E_pad % tc::BK != 0) return VQA_ERR_UNSUPPORTED;
   const int tiles_n = H / UNITS;
-  const int sms = sm_count();
-  int max_tiles_m = (sms / tiles_n) & ~1;            // pairs: an even number of 128-row blocks per launch
-  if (max_tiles_m < 2) return VQA_ERR_UNSUPPORTED;
-  static int usable = -1;                            // can max_tiles_m * tiles_n CTAs run as co-resident pairs?
+  const int dev = current_device();
+  static DeviceInt usable_dev;                       // number of pairs the device can hold at once (0 = pairs unusable)
+  int& usable = usable_dev.at(dev);
   if (usable < 0) {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
       (void)cudaGetLastError();
       usable = 0;
     } else {
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(max_tiles_m * tiles_n); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES;
+      cfg.gridDim = dim3(2 * (sm_count() / 2)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int clusters = 0;
       if (cudaOccupancyMaxActiveClusters(&clusters, (const void*)kernel, &cfg) != cudaSuccess) { (void)cudaGetLastError(); clusters = 0; }
-      usable = clusters > 0 ? clusters : 0;          // number of pairs the device can hold at once
+      usable = clusters > 0 ? clusters : 0;
     }
   }
-  if (usable <= 0) return VQA_ERR_UNSUPPORTED;
-  while (max_tiles_m >= 2 && (max_tiles_m * tiles_n) / 2 > usable) max_tiles_m -= 2;
-  if (max_tiles_m < 2) return VQA_ERR_UNSUPPORTED;
+  int pairs_max = usable;
+  if (sm_limit > 0 && sm_limit / 2 < pairs_max) pairs_max = sm_limit / 2;
+  const int max_groups = pairs_max / tiles_n;        // groups of RB x 256 rows that can be co-resident
+  if (max_groups < 1) return VQA_ERR_UNSUPPORTED;
+  const int rows_per_group = 2 * RB * tc::BM;
+  // cooperative launch = the runtime checks co-residency of the whole grid; VQA_B200_GRU_COOP=0 launches plainly (the
+  // grid is sized to fit either way)
+  static int coop = -1;
+  if (coop < 0) { const char* e = getenv("VQA_B200_GRU_COOP"); coop = (e && e[0] == '0') ? 0 : 1; }
   CUtensorMap tmWx, tmWh;
   int rc;
   if ((rc = tc::make_tensor_map_bf16(&tmWx, wx_p, 3LL * H, E_pad, E_pad, HALF_UNITS))) return rc;
   if ((rc = tc::make_tensor_map_bf16(&tmWh, wh_p, 3LL * H, H, H, HALF_UNITS))) return rc;
-  for (int b0 = 0; b0 < B; b0 += max_tiles_m * tc::BM) {
-    const int Bc = (B - b0 < max_tiles_m * tc::BM) ? B - b0 : max_tiles_m * tc::BM;
-    const int tiles_m = ((Bc + tc::BM - 1) / tc::BM + 1) & ~1;      // padded to whole pairs; extra rows are masked
+  for (int b0 = 0; b0 < B; b0 += max_groups * rows_per_group) {
+    const int Bc = (B - b0 < max_groups * rows_per_group) ? B - b0 : max_groups * rows_per_group;
+    const int groups = (Bc + rows_per_group - 1) / rows_per_group;   // padded to whole groups; extra rows are masked
+    const int tiles_m = groups * 2 * RB;
     const __nv_bfloat16* Xc = (const __nv_bfloat16*)X + (size_t)b0 * T * E_pad;
     __nv_bfloat16* h0 = (__nv_bfloat16*)h_op + (size_t)b0 * H;
     __nv_bfloat16* h1 = (__nv_bfloat16*)h_op + (size_t)B * H + (size_t)b0 * H;
@@ -378,7 +416,7 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
       if ((rc = tc::make_tensor_map_bf16(&tmH1, h1, Bc, H, H, tc::BM))) return rc;
     }
     Params p;
-    p.B = Bc; p.T = T; p.H = H; p.E_pad = E_pad; p.tiles_n = tiles_n; p.num_ctas = tiles_m * tiles_n;
+    p.B = Bc; p.T = T; p.H = H; p.E_pad = E_pad; p.tiles_n = tiles_n; p.num_ctas = 2 * groups * tiles_n;
     p.bias = bias_p; p.h_op[0] = h0; p.h_op[1] = h1;
     p.h_last = h_last ? h_last + (size_t)b0 * H : nullptr;
     p.h_all = hall;
@@ -389,6 +427,7 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
     p.save_r = tmajor ? save->R + so : nullptr; p.save_z = tmajor ? save->Z + so : nullptr;
     p.save_n = tmajor ? save->N + so : nullptr; p.save_hn = tmajor ? save->HN + so : nullptr;
     p.save_h = tmajor ? save->Hs + so : nullptr;
+    if (tiles_m > 64) return fail(VQA_ERR_INVALID, "gru_pair: %d row blocks per launch exceed the counter block", tiles_m);
     VQA_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int) * tiles_m, s));
     void* args[] = {(void*)&tmX, (void*)&tmH0, (void*)&tmH1, (void*)&tmWx, (void*)&tmWh, (void*)&p};
     cudaLaunchConfig_t cfg = {};
@@ -396,24 +435,50 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
     cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 2;
+    cfg.attrs = at; cfg.numAttrs = coop ? 2 : 1;
     VQA_CUDA_CHECK(cudaLaunchKernelExC(&cfg, (const void*)kernel, args));
     count_launch();
   }
   return VQA_OK;
 }
 
+// Tile choice.  One 256-row block per pair (RB = 1): 64-unit tiles, or 32-unit tiles when 64-unit tiles would use at most
+// half of the SMs (B <= 512 at H = 1024).  Two interleaved row blocks per pair (RB = 2, see the header): when the caller
+// gives the GRU only a share of the device (sm_limit > 0: the other SMs run question-independent GEMM tiles at the same
+// time) and the batch has at least two 256-row blocks.  VQA_B200_GRU_CFG = "64x1" | "32x1" | "64x2" | "32x2" forces one.
 int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, const void* wh_p,
              const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
-             const GruTrainSave* save, cudaStream_t s) {
-  // 32-unit tiles when 64-unit tiles would use at most half of the SMs (VQA_B200_GRU_UNITS=64 forces the wide tile)
-  static int force64 = -1;
-  if (force64 < 0) { const char* e = getenv("VQA_B200_GRU_UNITS"); force64 = (e && atoi(e) == 64) ? 1 : 0; }
+             const GruTrainSave* save, int sm_limit, cudaStream_t s) {
+  static int forced = -1;                            // 0 = automatic, else 10 * units + rb
+  if (forced < 0) {
+    forced = 0;
+    const char* e = getenv("VQA_B200_GRU_CFG");
+    if (e) {
+      int u = 0, r = 0;
+      if (sscanf(e, "%dx%d", &u, &r) == 2 && (u == 32 || u == 64) && (r == 1 || r == 2)) forced = 10 * u + r;
+    }
+    const char* e64 = getenv("VQA_B200_GRU_UNITS");  // older switch: 64 forces the wide tile
+    if (!forced && e64 && atoi(e64) == 64) forced = 641;
+  }
+  if (H % grup::PACK_UNITS != 0) return VQA_ERR_UNSUPPORTED;
+  const int sms = sm_count();
+  const int budget = (sm_limit > 0 && sm_limit < sms) ? sm_limit : sms;
   const int row_pairs = (B + 2 * tc::BM - 1) / (2 * tc::BM);
-  const int ctas64 = 2 * row_pairs * (H / grup::PACK_UNITS);
-  if (!force64 && H % grup::PACK_UNITS == 0 && 2 * ctas64 <= sm_count())
-    return gru_pair_t<32>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, s);
-  return gru_pair_t<64>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, s);
+  auto ctas = [&](int units, int rb) { return 2 * ((row_pairs + rb - 1) / rb) * (H / units); };
+  int cfg = forced;
+  if (!cfg) {
+    if (sm_limit > 0 && !save && row_pairs >= 2 && ctas(64, 2) <= budget) cfg = 642;
+    else if (2 * ctas(64, 1) <= budget) cfg = 321;
+    else cfg = 641;
+  }
+#define VQA_GRU_CALL(U, R) gru_pair_t<U, R>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, sm_limit, s)
+  switch (cfg) {
+    case 321: return VQA_GRU_CALL(32, 1);
+    case 322: return VQA_GRU_CALL(32, 2);
+    case 642: return VQA_GRU_CALL(64, 2);
+    default: return VQA_GRU_CALL(64, 1);
+  }
+#undef VQA_GRU_CALL
 }
 
 }  // namespace vqa

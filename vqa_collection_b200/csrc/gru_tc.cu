@@ -302,10 +302,10 @@ int gru_persistent(const void* X, int B, int T, int H, int E_pad, const void* wx
   const int sms = sm_count();
   VQA_REQUIRE(tiles_n <= sms, "gru(bf16): H=%d needs more CTAs than the device has SMs", H);
   const int max_tiles_m = sms / tiles_n;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr;                            // per device, not per process
+  if (attr.need(current_device())) {
     VQA_CUDA_CHECK(cudaFuncSetAttribute(gru_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    attr.mark(current_device());
   }
   CUtensorMap tmWx, tmWh;
   int rc;

@@ -227,11 +227,12 @@ static int launch_pool_stream(const float* parts, int n_parts, float bias, const
   const size_t smem = (size_t)S * R * row_bytes + 128 + 2 * kPoolMaxK * sizeof(float);
   const int grid = B < sm_count() ? B : sm_count();
   (void)chunks;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[sizeof(T) == 2]) {
+  static DeviceOnce attr_done[2];                    // per device, not per process
+  const int dev = current_device();
+  if (attr_done[sizeof(T) == 2].need(dev)) {
     VQA_CUDA_CHECK(cudaFuncSetAttribute(attention_pool_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kStreamMaxStages * kStreamChunkBytes + 1024));
-    attr_done[sizeof(T) == 2] = true;
+    attr_done[sizeof(T) == 2].mark(dev);
   }
   VQA_CUDA_CHECK(launch_pdl(attention_pool_stream_kernel<T>, dim3(grid), dim3(kStreamThreads), smem, s, parts, n_parts, bias,
                             x, B, K, V, rev, S, R, att, vsum));

@@ -182,9 +182,18 @@ class VQAEngine:
     """B200 forward engine for the Up-Down (+ReGAT) VQA path."""
 
     def __init__(self, weights: dict, relation: bool = False, precision: str = "bf16",
-                 device="cuda", num_objs: int = 36):
+                 device="cuda", num_objs: int = 36, overlap=None, side_sms: int = 0, side_tile_permille: int = 0):
+        """``overlap`` (bf16, B >= 512): run the question encoder on a side stream on ``side_sms`` SMs while the
+        question-independent projection of the region features runs on the other SMs (vqa_forward_args.overlap);
+        None = on unless VQA_B200_OVERLAP=0."""
+        import os
         self.lib = L.load()
         self.device = torch.device(device)
+        if self.device.index is None and self.device.type == "cuda":
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        if overlap is None:
+            overlap = os.environ.get("VQA_B200_OVERLAP", "1") != "0"
+        self.overlap, self.side_sms, self.side_tile_permille = bool(overlap), int(side_sms), int(side_tile_permille)
         self.dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[precision]
         self.precision = precision
         self.relation = bool(relation)
@@ -201,6 +210,7 @@ class VQAEngine:
         a.E_pad, a.ntoken_rows = P["E_pad"], P["ntoken_rows"]
         a.num_labels = P.get("num_labels", 0)
         a.dtype, a.relation = ops.dtype_code(self.dtype), int(self.relation)
+        a.overlap, a.side_sms, a.side_tile_permille = int(self.overlap), self.side_sms, self.side_tile_permille
         for name in ("emb", "w_ih", "b_ih", "w_hh", "b_hh", "Wv", "sv", "bv", "Wqq", "sqq", "bqq", "wlin",
                      "Wvn", "svn", "bvn", "Wc0", "sc0", "bc0", "Wc1", "sc1", "bc1"):
             setattr(a, "d_" + name, P[name].data_ptr())
@@ -290,9 +300,31 @@ class VQAEngine:
         if B == 0:                                   # empty shard: nothing to launch, empty outputs
             self.last_launches = 0
             return out
-        L.check(self.lib.vqa_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        self.last_launches = self.lib.vqa_forward_last_launch_count() + n_cast
+        # the library launches on the CURRENT device: make that the engine's device, and use ITS current stream
+        with torch.cuda.device(self.device):
+            L.check(self.lib.vqa_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+            self.last_launches = self.lib.vqa_forward_last_launch_count() + n_cast
         return out
+
+    def capture(self, img, tokens, labels=None, bbox=None, wh=None, warmup: int = 2, **want):
+        """Capture ``forward`` on fixed (resident) inputs into a CUDA graph: returns ``(graph, out)``; every
+        ``graph.replay()`` recomputes ``out`` from the CURRENT contents of ``img`` / ``tokens`` / ``labels``.  One
+        graph launch instead of 8-12 kernel launches + tensor-map encodes per step: the steady-state form for a
+        serving loop over resident batches (all pointers of the path are fixed, tensor maps are by-value parameters)."""
+        if img.dtype != self.dtype:
+            raise TypeError("capture() needs inputs already in the engine dtype (use resident())")
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):          # the first, uncaptured calls set attributes / create the side stream
+                    self.forward(img, tokens, labels=labels, bbox=bbox, wh=wh, **want)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                out = self.forward(img, tokens, labels=labels, bbox=bbox, wh=wh, **want)
+        return g, out
 
     # -- host-buffer forward (the e2e path) ----------------------------------------
     def _next_host_ctx(self):
@@ -338,6 +370,8 @@ class VQAEngine:
         if K != self.K or V != self.P["V"]:
             raise ValueError(f"img must be [B,{self.K},{self.P['V']}], got {tuple(img_h.shape)}")
         ctx = self._next_host_ctx()
+        if not hasattr(self, "_host_keep"):
+            self._host_keep = {}
         a = self._args(B, tokens_h.shape[1])
         ws, need = self._workspace(a)
         dev = self.device
@@ -366,12 +400,18 @@ class VQAEngine:
                 raise ValueError("relation engine needs labels_h or bbox_h")
         label_h = torch.empty((B,), dtype=torch.int64)
         ha.fwd, ha.h_label = a, label_h.data_ptr()
+        if int(raw_chunk_period) == 1:                   # "everything raw" (host_raw_chunk_period on a small core slice)
+            pack_on_host, raw_chunk_period = False, 0
         ha.chunk_rows, ha.pack_on_host = int(chunk), int(bool(pack_on_host) and self.dtype == torch.bfloat16)
         ha.raw_chunk_period = int(raw_chunk_period) if ha.pack_on_host else 0
         ha.img_is_bf16 = int(wire_bf16)
         L.check(self.lib.vqa_forward_host_wait(ctx))             # a context carries one batch at a time
+        # everything the C context points into (it keeps raw pointers to the host buffers and to h_label until
+        # vqa_forward_host_wait) lives on the ENGINE, keyed by context, until the next wait on that context returns —
+        # a caller that drops the handle without result() cannot free memory that is still being read or written
+        self._host_keep[ctx.value] = (label_h, keep, img_h, tokens_h, ha, logits, att, ws)
         with torch.cuda.device(self.device):
-            L.check(self.lib.vqa_forward_host_submit(ctx, C.byref(ha), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            L.check(self.lib.vqa_forward_host_submit(ctx, C.byref(ha), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         n_chunks = (B + chunk - 1) // chunk
         self.last_launches = self.lib.vqa_forward_last_launch_count() + (
             (n_chunks if not ha.pack_on_host else (n_chunks // ha.raw_chunk_period if ha.raw_chunk_period else 0))
@@ -382,14 +422,15 @@ class VQAEngine:
         class _Pending:
             def result(self_inner):
                 L.check(eng.lib.vqa_forward_host_wait(ctx))
-                _ = keep, img_h, tokens_h                    # host buffers must outlive the transfer
                 return label_h, int(ha.h2d_bytes), int(ha.d2h_bytes)
         return _Pending()
 
     def __del__(self):
         for ctx in getattr(self, "_host_ctxs", None) or []:
             try:
+                self.lib.vqa_forward_host_wait(ctx)      # a submitted batch still reads / writes the kept host buffers
                 self.lib.vqa_host_ctx_destroy(ctx)
             except Exception:
                 pass
         self._host_ctxs = None
+        self._host_keep = None

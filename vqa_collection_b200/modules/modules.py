@@ -162,13 +162,13 @@ class DotProduct(nn.Module):
                        bias=self.wa.bias.detach().float().contiguous(), out_dtype=dtype)
         Bm = ops.linear(as_compute(b.reshape(-1, b.shape[-1]), dtype), self.wb.weight.detach().to(dtype).contiguous(),
                         bias=self.wb.bias.detach().float().contiguous(), out_dtype=dtype)
-        outs = []
+        # Stand-alone use only (the ReGAT layer never calls this: its DotProduct is merged into the wide projection and
+        # contracted inside vqa_graph_attention): one small GEMM per image, written into one output tensor.
+        out = torch.empty((a.shape[0], a.shape[1], b.shape[1]), dtype=torch.float32, device=A.device)
         for i in range(a.shape[0]):                       # per-image [a_len,out]x[out,b_len]
-            Ai = A[i * a.shape[1]:(i + 1) * a.shape[1]]
-            Bi = Bm[i * b.shape[1]:(i + 1) * b.shape[1]]
-            pad = (-Bi.shape[0]) % 8
-            outs.append(ops.linear(Ai, Bi, out_dtype=torch.float32))
-        return torch.stack(outs)
+            out[i] = ops.linear(A[i * a.shape[1]:(i + 1) * a.shape[1]], Bm[i * b.shape[1]:(i + 1) * b.shape[1]],
+                                out_dtype=torch.float32)
+        return out
 
 
 class SentenceEmbedding(nn.Module):

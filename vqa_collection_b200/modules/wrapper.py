@@ -147,6 +147,13 @@ class Wrapper(nn.Module):
             predict = self.predictor(enc)
             score, label = compute_score(predict, target, self.device, True)
             return score, label, target
+        if not batch['img'].is_cuda:
+            # A DataLoader batch (host tensors, dataset.py:96-104): the pipelined host path — features packed to bf16 by
+            # the host cores chunk by chunk while the previous chunk's DMA is in flight, forward, answers back — instead
+            # of one pageable .to(device) of the whole batch (encoder.py:153-156).  This is the path bench.py reports as e2e.
+            label = self._forward_vqa_host(eng, batch).to(self.device)
+            score, _, _ = ops.answer_scores(label, target.contiguous())
+            return score, label, target
         img = batch['img'].to(self.device)
         tokens = batch['q'].to(self.device)
         kw = {}
@@ -159,6 +166,24 @@ class Wrapper(nn.Module):
         label = out['label']
         score, _, _ = ops.answer_scores(label, target.contiguous())
         return score, label, target
+
+    def _forward_vqa_host(self, eng, batch):
+        """host batch → host answers (int64 [B]) through VQAEngine.forward_host (vqa_forward_host_submit / _wait)"""
+        from ..engine import host_raw_chunk_period
+        img_h = batch['img']
+        if img_h.dtype != torch.bfloat16:                 # bf16 = a feature cache kept in the resident format
+            img_h = img_h.float()
+        img_h = img_h.contiguous()
+        tokens_h = batch['q'].long().contiguous()
+        kw = {}
+        if eng.relation:
+            if 'graph' in batch:
+                g = batch['graph']
+                kw['labels_h'] = (g if g.dtype == torch.uint8 else g.to(torch.uint8)).contiguous()
+            else:
+                kw['bbox_h'], kw['wh'] = batch['bbox'].float().contiguous(), batch['wh']
+        label_h, _, _ = eng.forward_host(img_h, tokens_h, raw_chunk_period=host_raw_chunk_period(), **kw)
+        return label_h
 
     def forward_cap(self, batch):
         batch = self.encoder(batch)

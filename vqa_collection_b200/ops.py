@@ -514,3 +514,40 @@ def argmax_rows(logits):
     out = torch.empty((B,), dtype=torch.int64, device=logits.device)
     L.check(lib.vqa_argmax_rows(_ptr(logits), B, A, logits.stride(0), _ptr(out), _stream()))
     return out
+
+
+# ---- device guard -----------------------------------------------------------------------------------------------
+# The library launches on the CURRENT device and the wrappers above take torch.cuda.current_stream() of the current
+# device.  A model built on another device than the current one (the reference's --device / --decoder_device,
+# main.py:88, wrapper.py:148-150) would otherwise launch on device A's stream with device B's pointers.  Every
+# tensor-taking wrapper therefore runs under the device of its first CUDA tensor argument.
+def _on_tensor_device(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for v in list(args) + list(kwargs.values()):
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                dev = v.device
+                break
+            if isinstance(v, (tuple, list, dict)):
+                for u in (v.values() if isinstance(v, dict) else v):
+                    if isinstance(u, torch.Tensor) and u.is_cuda:
+                        dev = u.device
+                        break
+                if dev is not None:
+                    break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
+for _name in ("relation_labels", "cast_to_bf16", "cast_to_f32", "linear", "gru_last_state", "gru_sequence",
+              "lstm_sequence", "caption_gate_scale", "seq_max", "softmax_mul", "attention_logits", "gru_cell",
+              "lstm_cell", "caption_decode_steps", "attention_pool", "graph_attention", "graph_attention_merged",
+              "add_", "answer_scores", "argmax_rows"):
+    globals()[_name] = _on_tensor_device(globals()[_name])
+del _name

@@ -65,8 +65,10 @@ def clip_grad_norm_(parameters, max_norm, norm_type=2.0):
     if ws is None:
         ws = _CLIP_WS[dev] = torch.empty((lib.vqa_grad_clip_workspace_bytes() // 4 + 2,), dtype=torch.float32, device=dev)
     out = torch.empty((2,), dtype=torch.float32, device=dev)          # [total_norm, scale]
-    L.check(lib.vqa_grad_clip(_table(entries), len(entries), float(max_norm), 1, ws.data_ptr(), out.data_ptr(),
-                              out.data_ptr() + 4, _stream()))
+    with torch.cuda.device(dev):                                      # the library launches on the current device
+        L.check(lib.vqa_grad_clip(_table(entries), len(entries), float(max_norm), 1, ws.data_ptr(), out.data_ptr(),
+                                  out.data_ptr() + 4, _stream()))
+    torch._C._increment_version(grads)                                # scaled in place behind autograd's back
     return out[0]
 
 
@@ -129,5 +131,10 @@ class Adamax(torch.optim.Optimizer):
             for i, e in enumerate(entries):
                 a = arr[i]
                 a.d_p, a.d_g, a.d_m, a.d_u, a.n, a.lr = e
-            L.check(lib.vqa_adamax_step(arr, len(entries), b1, b2, eps, wd, step, gs, _stream()))
+            with torch.cuda.device(live[0][1].device):                # the library launches on the current device
+                L.check(lib.vqa_adamax_step(arr, len(entries), b1, b2, eps, wd, step, gs, _stream()))
+        # The kernel wrote the parameters through raw pointers: tell autograd.  The weight caches of the forward path
+        # (Wrapper.engine(), PreparedCache) key on Tensor._version — without the bump, evaluate() after a training epoch
+        # would keep serving the bf16 copies and weight-norm scales of the OLD weights.
+        torch._C._increment_version([p for _, p in live])
         return loss

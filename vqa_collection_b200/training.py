@@ -106,17 +106,27 @@ class UpDownTrainStep(torch.autograd.Function):
         a.d_loss, a.d_logits = loss.data_ptr(), logits.data_ptr()
         ws, need = _workspace(lib, a, dev)
         a.d_workspace, a.workspace_bytes = ws.data_ptr(), need
-        L.check(lib.vqa_updown_train_step(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        with torch.cuda.device(dev):                 # the library launches on the current device
+            L.check(lib.vqa_updown_train_step(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        # Called under no_grad / with frozen parameters (evaluation through get_loss): nobody will run backward(), so the
+        # gradients are dropped here — no all-reduce is started (ranks that skip differently must not desynchronise) and
+        # the flat buffer is free for the next step.
+        wants_grad = any(ctx.needs_input_grad)
+        if not wants_grad:
+            fg.pending = False
         # the exchange step of the data-parallel training path: average the shard gradients over ranks
         # (async on NCCL's stream; backward() waits for it, so clip_grad_norm_ sees the global gradient)
-        ctx.work = average_gradients_(fg.flat, _GROUP, async_op=True) if _dp_active() else None
-        ctx.fg = fg
+        ctx.work = average_gradients_(fg.flat, _GROUP, async_op=True) if (_dp_active() and wants_grad) else None
+        ctx.fg = fg if wants_grad else None
         ctx.mark_non_differentiable(logits)
         return loss.reshape(()), logits
 
     @staticmethod
     def backward(ctx, g_loss, _g_logits):
         fg = ctx.fg
+        if fg is None:
+            raise RuntimeError("UpDownTrainStep.backward ran twice (retain_graph / a second backward): the fused step "
+                               "keeps ONE set of gradients per forward; call get_loss again")
         ctx.fg = None
         fg.pending = False
         if ctx.work is not None:
