@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """bench.py — VQA forward questions/sec on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload updown|regat]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workloads updown,regat]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference ...      # the reference's own CPU path on the box's host cores
 
 A step = one forward pass (question encoder → top-down attention → [ReGAT] → classifier →
 answers) over one batch of 1024 synthetic questions per GPU (36x2048 region features, 14
-tokens, 3129 answers), inputs resident in HBM as bf16.  Batch is sharded data-parallel
-(weak scaling: 1024 questions per GPU, no forward collective).  One JSON line on rank 0.
+tokens, 3129 answers), inputs resident in HBM as bf16.  The batch is sharded data-parallel
+(weak scaling: 1024 questions per GPU, no forward collective).  Rank 0 prints ONE JSON line:
+
+  * ``value`` ...            Up-Down forward (BASELINE configs[1], the configuration the metric is quoted on)
+  * ``regat`` {...}          the same keys for Up-Down + ReGAT (configs[2], the north-star workload): value,
+                             ms_per_step, e2e, roofline(s), parity, per-rank times — at EVERY N
+  * ``roofline``             the LONGEST kernel of the Up-Down step, ``roofline_kernels`` every hot kernel timed alone
+  * ``parity``               answers / logits of batch 0 against the CPU oracle at the full batch (N = 1)
+
+Every timed step is one CUDA-graph launch (the whole forward incl. its side stream is captured once per resident
+batch); 4 resident batches of 151 MB rotate, so no step finds its features in the 126 MB L2.
 """
 import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -25,6 +33,20 @@ import torch  # noqa: E402
 METRIC = "VQA forward questions/sec (36x2048 regions, bs=1024)"
 UNIT = "questions/s"
 FLOPS_PER_Q = {"updown": 290_500_608, "regat": 1_214_553_216}       # SURVEY.md §8d (minimal algebra)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")                    # git-ignored copy of the reference (build())
+WORKLOAD_NAME = {
+    "updown": "Up-Down VQA forward bf16 batch 1024 on 1xB200 (tcgen05 projections + fused attention/softmax)",
+    "regat": "ReGAT spatial-relation VQA forward (11 relation labels, KxK masked graph attention) batch 1024",
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 1024 from the `ncu --set full` captures committed
+# under profiles/ (bytes, file); scaled by B / 1024 below.  None = no capture of this kernel in this round.
+NCU_TRAFFIC = {
+    "wv": (166.2e6, "profiles/r01e_ncu_wv.md"),
+    "wide": (594.07e6, "profiles/r01e_ncu_wide.md"),
+    "gat": (606.0e6, "profiles/r01e_ncu_gat.md"),
+    "pool": (155.6e6, "profiles/r01f_ncu_pool.md"),
+    "gru": (None, "profiles/r01e_ncu_gru.md (single-CTA variant; the pair kernel cannot run under ncu)"),
+}
 
 
 def parse():
@@ -33,11 +55,21 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="updown", choices=["updown", "regat"])
+    ap.add_argument("--workloads", default="updown,regat", help="comma list; the first one is the line's `value`")
+    ap.add_argument("--workload", default=None, help="(compat) a single workload")
     ap.add_argument("--batch", type=int, default=1024, help="questions per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-graph", action="store_true", help="direct launches instead of CUDA graph replays")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--overlap", type=int, default=None, help="force the two-stream schedule on (1) / off (0)")
+    a = ap.parse_args()
+    a.workloads = [a.workload] if a.workload else [w for w in a.workloads.split(",") if w]
+    for w in a.workloads:
+        if w not in WORKLOAD_NAME:
+            ap.error(f"unknown workload {w}")
+    return a
 
 
 def peaks():
@@ -51,10 +83,11 @@ def peaks():
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """samples SM clock / throttle reasons with NVML while the timed region runs"""
+    """SM clock / throttle reasons through NVML, sampled by the MAIN thread while it waits for the timed region's end
+    event (no polling thread: 8 ranks x a 5 ms poller on a shared 32-vCPU box is measurable jitter in a 7 ms window)"""
 
     def __init__(self, index):
-        self.samples, self.reasons, self._stop, self.ok = [], set(), threading.Event(), False
+        self.samples, self.reasons, self.ok = [], set(), False
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -82,19 +115,12 @@ class ClockSampler:
         except Exception:
             pass
 
-    def _run(self):
-        while not self._stop.is_set():
+    def wait_for(self, event):
+        """sample until `event` has completed (at least once, during the region)"""
+        self.sample()
+        while not event.query():
             self.sample()
-            time.sleep(0.005)
-
-    def __enter__(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
-        return self
-
-    def __exit__(self, *a):
-        self._stop.set()
-        self.t.join()
+            time.sleep(0.0005)
 
     def summary(self):
         s = sorted(self.samples)
@@ -113,193 +139,307 @@ def cpu_model():
     return "unknown"
 
 
-def cpu_forward_qps(workload, sample_b, iters, warmup=1, threads=None):
-    """the reference's CPU path (oracle port: same torch-CPU ops, op for op) on all host cores"""
-    from oracle import vqa_oracle as O
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
+def build_reference_model(workload):
+    """the UNMODIFIED reference (baseline/_ref, copied there from /root/reference by __graft_entry__.build()):
+    set_model(...) exactly as BASELINE.md §3 states, default initialisers, eval mode.  None when the copy is absent."""
+    if not os.path.isdir(os.path.join(REF_DIR, "modules")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    import contextlib
+    import io
+    import warnings
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):     # the reference prints while it builds
+        warnings.simplefilter("ignore")
+        from modules.wrapper import set_model              # the reference's own module tree
+        torch.manual_seed(1111)
+        m = set_model(encoder_type="relation" if workload == "regat" else "base", predictor_type="base",
+                      decoder_type="none", ntoken=20000, v_dim=2048, embed_dim=300, hidden_dim=1024,
+                      decoder_hidden_dim=512, rnn_layer=1, ans_dim=3129, cls_layer=2, c_len=20, device="cpu",
+                      dropout=0.5, neg_slope=0.5, rnn_type="GRU", att_type="new", conv_layer=1, conv_type="corr",
+                      pretrained_embed_path="")
+    return m.eval()
+
+
+def cpu_forward_qps(workload, B, iters, warmup=1, threads=None):
+    """The reference's CPU path on the host cores: Wrapper.forward_vqa(batch) (wrapper.py:113-118) of the real
+    reference when baseline/_ref is present (kind "reference"), else the oracle port (kind "port").  A step is the
+    WHOLE batch of B questions; the ReGAT batch goes through forward_vqa in chunks of 128 questions (the reference
+    gathers a [B,36,36,2048] f32 label-bias tensor, gcn.py:107: 11 GB at B = 1024)."""
+    from oracle import vqa_oracle as O                       # synthetic inputs (+ the port when the reference is absent)
     cfg = O.FULL_REGAT if workload == "regat" else O.FULL
-    cores = threads or os.cpu_count() or 1
+    cores = threads or host_cores()
     torch.set_num_threads(cores)
-    W = O.make_weights(cfg, 1111)
-    batch = O.make_batch(cfg, sample_b, 2000)
+    batch = O.make_batch(cfg, B, 2000)
+    batch = {k: v for k, v in batch.items() if k not in ("bbox", "wh")}
+    chunk = 128 if workload == "regat" else B
+    model = build_reference_model(workload)
+    if model is None:
+        W = O.make_weights(cfg, 1111)
+        run = lambda b: O.forward_vqa(b, W, cfg)
+        kind = "port"
+    else:
+        run = model.forward_vqa
+        kind = "reference"
     times = []
     with torch.no_grad():
         for i in range(warmup + iters):
             t0 = time.perf_counter()
-            O.forward_vqa(batch, W, cfg)
+            for c0 in range(0, B, chunk):
+                run({k: (v[c0:c0 + chunk] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == B else v)
+                     for k, v in batch.items()})
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return sample_b / (sum(times) / len(times)), times, cores
+    sample = (f"{B} questions per step ({'in chunks of %d' % chunk if chunk < B else 'one call'}), fp32, "
+              f"{'the reference Wrapper.forward_vqa from baseline/_ref' if kind == 'reference' else 'torch-CPU oracle port of Wrapper.forward_vqa'}, "
+              f"{cores} threads, {len(times)} timed passes")
+    return {"qps": B / (sum(times) / len(times)), "best": B / min(times), "times": times, "cores": cores,
+            "kind": kind, "sample": sample, "B": B}
+
+
+def workload_config(args, workload, extra=None):
+    cfg = {"workload": WORKLOAD_NAME[workload], "batch_per_gpu": args.batch, "regions": 36, "v_dim": 2048, "hidden": 1024,
+           "tokens": 14, "answers": 3129, "ntoken": 20000, "parallelism": f"dp{args.gpus}",
+           "l2": "4 rotating resident batches (151 MB bf16 features each > 126 MB L2)"}
+    cfg.update(extra or {})
+    return cfg
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's CPU path, full batch per step, rank 0 only"""
     if rank != 0:
         return
-    sample_b = 128 if args.workload == "updown" else 32
-    qps, times, cores = cpu_forward_qps(args.workload, sample_b, max(args.steps, 1), max(args.warmup, 1))
-    ms = 1e3 * sum(times) / len(times)
-    sample = (f"{sample_b} of the {args.batch} questions per step, fp32, torch-CPU oracle port of "
-              f"Wrapper.forward_vqa, {cores} threads")
-    line = {
-        "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, sample_b),
-        "cpu_baseline": {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    blocks = {}
+    for wl in args.workloads:
+        # bounded: the driver's K/W apply to the first workload; the others get 2 timed passes
+        iters = max(args.steps, 1) if wl == args.workloads[0] else min(max(args.steps, 1), 2)
+        warm = max(args.warmup, 1) if wl == args.workloads[0] else 1
+        if wl == "regat":
+            iters, warm = min(iters, 3), 1            # ~3-8 s per 1024-question step
+        r = cpu_forward_qps(wl, args.batch, iters, warm)
+        blocks[wl] = {"value": r["qps"], "unit": UNIT, "ms_per_step": 1e3 * sum(r["times"]) / len(r["times"]),
+                      "steps": len(r["times"]), "best_of": r["best"],
+                      "cpu_baseline": {"value": r["qps"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                       "sample": r["sample"], "cpu_model": cpu_model()},
+                      "e2e": {"value": r["qps"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "config": workload_config(args, wl)}
+    first = blocks[args.workloads[0]]
+    line = {"impl": "reference", "metric": METRIC, "value": first["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": first["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": first["config"],
+            "cpu_baseline": first["cpu_baseline"], "e2e": first["e2e"], "gpu_launches": 0, "same_config": True}
+    for wl in args.workloads[1:]:
+        line[wl] = blocks[wl]
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, per_step_b=None):
-    name = ("Up-Down VQA forward bf16 batch 1024 on 1xB200 (tcgen05 projections + fused attention/softmax)"
-            if args.workload == "updown" else
-            "ReGAT spatial-relation VQA forward (11 relation labels, KxK masked graph attention) batch 1024")
-    return {"workload": name, "batch_per_gpu": args.batch, "regions": 36, "v_dim": 2048, "hidden": 1024,
-            "tokens": 14, "answers": 3129, "ntoken": 20000, "parallelism": f"dp{args.gpus}",
-            "l2": "4 rotating resident batches (151 MB bf16 features each > 126 MB L2)",
-            **({"sample_per_step": per_step_b} if per_step_b else {})}
-
-
 # ----------------------------------------------------------------------------- B200 arm
-def main():
-    args = parse()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+class Ctx:
+    pass
 
-    from oracle import vqa_oracle as O          # only for synthetic weights/inputs + the cpu_baseline leg
-    from vqa_collection_b200.engine import VQAEngine
-    from vqa_collection_b200 import ops
 
-    relation = args.workload == "regat"
+def all_max(ctx, ms):
+    """max over ranks + the per-rank list (device-timed, NCCL all_gather of one double)"""
+    if ctx.dist is None:
+        return ms, [ms]
+    t = torch.tensor([ms], device=ctx.dev, dtype=torch.float64)
+    out = [torch.zeros_like(t) for _ in range(ctx.world)]
+    ctx.dist.all_gather(out, t)
+    per = [float(x.item()) for x in out]
+    return max(per), per
+
+
+def barrier(ctx):
+    torch.cuda.synchronize()
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+    torch.cuda.synchronize()
+
+
+def parity_block(O, cfg, W, eng, batch_cpu, out, relation):
+    """answers / logits / attention of one full batch against the CPU oracle (the checker, rank 0 only).
+    margin-ok rows = rows whose reference top-2 margin exceeds 4x the largest logit error of the run (SURVEY H1:
+    a bf16 path cannot be asked to reproduce an fp32 near-tie)."""
+    B = batch_cpu["img"].shape[0]
+    chunk = 128 if relation else 256
+    ref_logits, ref_att = [], []
+    with torch.no_grad():
+        for c0 in range(0, B, chunk):
+            sub = {k: (v[c0:c0 + chunk] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == B else v)
+                   for k, v in batch_cpu.items()}
+            lg, enc = O.forward(sub, W, cfg)
+            ref_logits.append(lg)
+            ref_att.append(enc["v_att"][:, :, 0])
+    ref_logits, ref_att = torch.cat(ref_logits), torch.cat(ref_att)
+    logits, att, label = out["logits"].float().cpu(), out["att"].float().cpu(), out["label"].cpu()
+    ref_label = ref_logits.max(1)[1]
+    err = float((logits - ref_logits).abs().max())
+    top2 = ref_logits.topk(2, dim=1)[0]
+    margin_ok = (top2[:, 0] - top2[:, 1]) > 4.0 * err
+    equal = label == ref_label
+    return {"n": int(B), "n_equal": int(equal.sum()), "n_margin_ok": int(margin_ok.sum()),
+            "n_equal_margin_ok": int((equal & margin_ok).sum()),
+            "n_equal_outside_margin": int((equal & ~margin_ok).sum()),
+            "max_rel_logit_err": err / float(ref_logits.abs().max()),
+            "max_rel_att_err": float((att - ref_att).abs().max() / ref_att.abs().max()),
+            "oracle": "oracle/vqa_oracle.py forward() fp32 on the same seeded batch (pinned to the real reference's goldens)"}
+
+
+def run_workload(ctx, args, wl):
+    O, ops = ctx.O, ctx.ops
+    from vqa_collection_b200.engine import VQAEngine, host_cores_per_rank, host_pack_threads
+    relation = wl == "regat"
     cfg = O.FULL_REGAT if relation else O.FULL
     W = O.make_weights(cfg, 1111)
-    eng = VQAEngine(W, relation=relation, precision=args.precision, device=dev)
-    B, NB = args.batch, 4
+    kw = {} if args.overlap is None else {"overlap": bool(args.overlap)}
+    eng = VQAEngine(W, relation=relation, precision=args.precision, device=ctx.dev, **kw)
+    B, NB, dev, rank = args.batch, 4, ctx.dev, ctx.rank
+    batch0 = O.make_batch(cfg, B, 3000 + rank)                 # batch 0 is a full oracle batch (parity below)
     g = torch.Generator(device="cpu").manual_seed(1000 * 2 + rank)
     imgs, toks, labs = [], [], []
     for i in range(NB):
-        img = torch.rand((B, 36, 2048), generator=g, dtype=torch.float32)
+        if i == 0:
+            img, tok = batch0["img"], batch0["q"]
+        else:
+            img = torch.rand((B, 36, 2048), generator=g, dtype=torch.float32)
+            tok = torch.randint(0, cfg.ntoken, (B, 14), generator=g)
         imgs.append(eng.resident(img.to(dev)))
-        toks.append(torch.randint(0, cfg.ntoken, (B, 14), generator=g).to(dev))
+        toks.append(tok.to(dev))
         if relation:
-            boxes = torch.from_numpy(O.make_boxes(B, 36, 50 + i + 10 * rank)).to(dev)
-            labs.append(ops.relation_labels(boxes, 640, 480))
+            if i == 0:
+                labs.append(batch0["graph"].to(torch.uint8).to(dev))
+            else:
+                boxes = torch.from_numpy(O.make_boxes(B, 36, 50 + i + 10 * rank)).to(dev)
+                labs.append(ops.relation_labels(boxes, 640, 480))
     host_img = torch.rand((B, 36, 2048), generator=g, dtype=torch.float32).pin_memory()
     host_tok = torch.randint(0, cfg.ntoken, (B, 14), generator=g).pin_memory()
-    host_lab = labs[0].cpu().pin_memory() if relation else None
+    host_lab = labs[1].cpu().pin_memory() if relation else None
 
-    def step(i):
+    def direct(i):
         return eng.forward(imgs[i % NB], toks[i % NB], labels=labs[i % NB] if relation else None)
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---- one CUDA graph per resident batch: a step is ONE graph launch (no per-step tensor-map encodes, argument
+    # structs, output allocations or 8-12 launches from Python)
+    graphs, outs, mode = [], [], "direct"
+    out0 = direct(0)
+    launches_per_step = eng.last_launches
+    if not args.no_graph:
+        try:
+            for i in range(NB):
+                gph, o = eng.capture(imgs[i], toks[i], labels=labs[i] if relation else None)
+                graphs.append(gph)
+                outs.append(o)
+            mode = "cuda_graph"
+        except Exception as e:                              # keep measuring: the direct launches are the same kernels
+            graphs, outs, mode = [], [], f"direct (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            torch.cuda.synchronize()
+
+    def step(i):
+        if graphs:
+            graphs[i % NB].replay()
+        else:
+            direct(i)
 
     for i in range(max(args.warmup, 3)):
         step(i)
-    barrier()
-    sampler = ClockSampler(local_rank)
+    barrier(ctx)
+    sampler = ClockSampler(ctx.local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with sampler:
-        e0.record()
-        for i in range(args.steps):
-            step(i)
-        e1.record()
-        sampler.sample()
-        barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = eng.last_launches * args.steps
-    if dist is not None:
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    value = B * world * args.steps / (ms_total / 1e3)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    sampler.wait_for(e1)
+    barrier(ctx)
+    ms_rank = e0.elapsed_time(e1)
+    ms_total, per_rank = all_max(ctx, ms_rank)
+    value = B * ctx.world * args.steps / (ms_total / 1e3)
+    res = {"value": value, "unit": UNIT, "ms_per_step": ms_total / args.steps, "steps": args.steps,
+           "per_rank_ms_total": [round(x, 4) for x in per_rank], "launch_mode": mode,
+           "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+           "schedule": ("two streams: question encoder beside the question-independent projection" if eng.overlap and
+                        args.precision == "bf16" and B >= 512 else "one stream"),
+           "clocks": sampler.summary(), "config": workload_config(args, wl)}
+
+    # ---- parity of batch 0 at the full batch size (rank 0, N = 1: the oracle takes seconds)
+    if ctx.world == 1 and not args.no_parity:
+        o = outs[0] if outs else out0
+        if graphs:
+            graphs[0].replay()
+        else:
+            o = direct(0)
+        torch.cuda.synchronize()
+        res["parity"] = parity_block(O, cfg, W, eng, batch0, o, relation)
 
     # ---- e2e: host buffers in the reference wire format (pinned f32 features) through the C-ABI host entry
-    # point vqa_forward_host: host cores pack f32→bf16 chunk by chunk while the previous chunk's DMA is in
-    # flight → H2D → forward → answers D2H, all inside the timed region
-    e2e_steps = max(3, min(args.steps, 20))
+    # point: host cores pack f32→bf16 chunk by chunk while the previous chunk's DMA is in flight → H2D → forward →
+    # answers D2H, all inside the timed region.  Hybrid staging: of every `period` chunks one crosses PCIe as raw f32
+    # (device cast), the others are packed; which split wins depends on the box, so the candidates are timed for a few
+    # steps first (all ranks agree on the one with the best worst-rank time), then the winner is measured.
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 20))
 
-    # hybrid staging: of every `period` chunks one crosses PCIe as raw f32 (device cast), the others are packed to bf16 by
-    # the host cores this rank may count on (all cores / ranks on the box); 0 = pack everything, 1 = everything raw.
-    # Which split wins depends on the box (cores and memory bandwidth per GPU, ranks sharing them), so the candidates are
-    # timed for a few steps first (all ranks agree on the one with the best worst-rank time), then the winner is measured.
-    from vqa_collection_b200.engine import host_cores_per_rank, host_pack_threads
+        def time_host(img_h, period, steps):
+            pack = args.precision == "bf16" and period != 1
+            kwh = dict(labels_h=host_lab, pack_on_host=pack, raw_chunk_period=period if pack else 0)
+            for _ in range(2):
+                eng.forward_host(img_h, host_tok, **kwh)
+            barrier(ctx)
+            e0.record()
+            pending = None
+            for _ in range(steps):                        # two batches in flight: stage n+1 while n computes
+                nxt = eng.forward_host_async(img_h, host_tok, **kwh)
+                if pending is not None:
+                    pending.result()
+                pending = nxt
+            _, h2d_, d2h_ = pending.result()
+            e1.record()
+            barrier(ctx)
+            ms, _ = all_max(ctx, e0.elapsed_time(e1))
+            return ms, h2d_, d2h_
 
-    def time_host(period, steps):
-        pack = args.precision == "bf16" and period != 1
-        kw = dict(labels_h=host_lab, pack_on_host=pack, raw_chunk_period=period if pack else 0)
-        for _ in range(2):
-            eng.forward_host(host_img, host_tok, **kw)
-        barrier()
-        e0.record()
-        pending = None
-        for _ in range(steps):                        # two batches in flight: stage n+1 while n computes
-            nxt = eng.forward_host_async(host_img, host_tok, **kw)
-            if pending is not None:
-                pending.result()
-            pending = nxt
-        _, h2d_, d2h_ = pending.result()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, h2d_, d2h_
+        candidates = [0, 4, 3, 2, 1] if args.precision == "bf16" else [1]
+        trials = {c: time_host(host_img, c, 6)[0] / 6 for c in candidates}
+        period = min(trials, key=trials.get)
+        ms_e2e, h2d, d2h = time_host(host_img, period, e2e_steps)
+        res["e2e"] = {"value": B * ctx.world * e2e_steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
+                      "host_pack_threads": host_pack_threads(), "host_cores_per_rank": host_cores_per_rank(),
+                      "raw_chunk_period": period, "raw_chunk_period_trials_ms": {str(k): round(v, 3) for k, v in trials.items()},
+                      "batches_in_flight": 2,
+                      "note": "vqa_forward_host_submit/_wait (the call Wrapper.forward_vqa makes for a host batch): pinned f32 "
+                              "host features (reference wire format) -> 64-image chunks, one in raw_chunk_period sent as f32 and "
+                              "cast on the device, the others packed to bf16 by this rank's share of the host cores (0 = all "
+                              "packed, 1 = all raw; picked by a short trial of every candidate), pipelined with H2D -> forward "
+                              "-> answers D2H; batch n+1 is staged while batch n computes"}
+        if args.precision == "bf16":
+            ms_b, h2d_b, _ = time_host(host_img.to(torch.bfloat16).pin_memory(), 1, e2e_steps)
+            res["e2e_bf16_host_cache"] = {"value": B * ctx.world * e2e_steps / (ms_b / 1e3), "unit": UNIT,
+                                          "h2d_bytes_per_step": h2d_b, "ms_per_step": ms_b / e2e_steps,
+                                          "note": "bf16 host feature cache -> H2D -> forward -> answers D2H"}
 
-    candidates = [0, 4, 3, 2, 1] if args.precision == "bf16" else [1]
-    trials = {c: time_host(c, 6)[0] / 6 for c in candidates}
-    RAW_PERIOD = min(trials, key=trials.get)
-    ms_e2e, h2d, d2h = time_host(RAW_PERIOD, e2e_steps)
-    e2e_value = B * world * e2e_steps / (ms_e2e / 1e3)
-    e2e_alt = None
+    # ---- rooflines: every hot kernel of the step timed ALONE with CUDA events on its launch stream (rotating inputs)
     if args.precision == "bf16":
-        ms_alt, h2d_alt, _ = time_host(1, e2e_steps)
-        e2e_alt = {"value": B * world * e2e_steps / (ms_alt / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_alt,
-                   "ms_per_step": ms_alt / e2e_steps, "note": "f32 features over PCIe + device cast (no host packing)"}
+        res["roofline_kernels"] = kernel_rooflines(ctx, args, eng, imgs, toks, labs, relation)
+        res["roofline"] = max(res["roofline_kernels"], key=lambda r: r["launch_ms"])
+    res["path_tflops_per_gpu"] = value / ctx.world * FLOPS_PER_Q[wl] / 1e12
+    res["path_frac_of_sustained_bf16"] = res["path_tflops_per_gpu"] / peaks()["bf16_tflops_sustained"]
+    del graphs, outs
+    return res
 
-    # a host-side feature cache kept in the resident bf16 format (SURVEY §8f f2): what the same call does when the
-    # caller stores its features as bf16 — reported next to the headline, which keeps the reference's f32 wire format
-    e2e_bf16 = None
-    if args.precision == "bf16":
-        host_img_bf16 = host_img.to(torch.bfloat16).pin_memory()
-        saved = host_img
-        host_img = host_img_bf16
-        ms_b, h2d_b, _ = time_host(1, e2e_steps)
-        host_img = saved
-        e2e_bf16 = {"value": B * world * e2e_steps / (ms_b / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_b,
-                    "ms_per_step": ms_b / e2e_steps, "note": "bf16 host feature cache -> H2D -> forward -> answers D2H"}
 
-    # ---- roofline of the dominant kernel (W_v projection fused with the attention logits),
-    # timed alone with CUDA events on its launch stream
-    P = eng.P
+def kernel_rooflines(ctx, args, eng, imgs, toks, labs, relation):
+    ops, P, B, NB, dev = ctx.ops, eng.P, args.batch, len(imgs), ctx.dev
     pk = peaks()
-    reps = max(10, min(args.steps, 100))
-    qq = torch.rand((B, 2 * P["H"]), device=dev)
-
-    def wv(i):
-        return ops.linear(imgs[i % NB].view(B * 36, 2048), P["Wv"], P["sv"], P["bv"], relu=True, mul=qq,
-                          mul_row_div=36, logit_w=P["wlin"])
-
-    def wide(i):
-        return ops.linear(imgs[i % NB].view(B * 36, 2048), P["Wg3"])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(10, min(args.steps, 50))
 
     def time_kernel(fn, n):
         for i in range(3):
@@ -312,69 +452,108 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
 
-    roof = None
-    if args.precision == "bf16":
-        # dominant kernel of the workload: Up-Down = the W_v projection fused with the attention logits; ReGAT = the wide
-        # projection x·[W0+W1; W2; WbᵀWa]ᵀ (55 % of the step).  traffic = dram__bytes_read.sum + dram__bytes_write.sum per
-        # launch from `ncu --set full` (profiles/r01e_ncu_wv.md: 159.48 + 6.71 MB, algorithmic 159.0 MB;
-        # profiles/r01e_ncu_wide.md: 181.17 + 412.90 MB, algorithmic 151 + 25 + 453 MB — part of Y is still in L2 at kernel end)
-        if relation and "Wg3" in P:
-            k_ms = time_kernel(wide, max(5, reps // 5))
-            flops = 2.0 * B * 36 * P["V"] * P["Wg3"].shape[0]
-            name, traffic, src = ("linear_tc_kernel<256,pair> (wide ReGAT projection [B*36,2048]x[6144,2048]^T, tcgen05 cta_group::2)",
-                                  594.07e6, "profiles/r01e_ncu_wide.md")
-        else:
-            k_ms = time_kernel(wv, reps)
-            flops = 2.0 * B * 36 * P["H"] * P["V"]
-            name, traffic, src = ("linear_tc_kernel<256,pair> (W_v projection + logit reduction, tcgen05 cta_group::2)",
-                                  166.2e6, "profiles/r01e_ncu_wv.md")
-        achieved = flops / (k_ms / 1e3) / 1e12
-        roof = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_tflops"], "traffic": traffic * B / 1024, "traffic_source": src,
-                "peak_source": pk["src"] + " burst (kernel timed alone)", "launch_ms": k_ms, "flops_per_launch": flops}
-    path_tflops = value / world * FLOPS_PER_Q[args.workload] / 1e12
+    def entry(key, name, bound, ms, work, unit_scale):
+        peak = pk["bf16_tflops"] if bound == "tensor" else pk["hbm_gbs"]
+        achieved = work / (ms / 1e3) / unit_scale
+        traffic, src = NCU_TRAFFIC.get(key, (None, None))
+        return {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s" if bound == "tensor" else "GB/s", "frac": achieved / peak,
+                "traffic": (traffic * B / 1024 if traffic else None), "traffic_source": src,
+                "peak_source": pk["src"] + " burst (kernel timed alone)", "launch_ms": ms,
+                ("flops_per_launch" if bound == "tensor" else "bytes_per_launch"): work}
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+    H, V, K, T, E = P["H"], P["V"], 36, toks[0].shape[1], P["E_pad"]
+    qq = torch.rand((B, 2 * H), device=dev)
+    out = []
+    # question GRU: T steps of [B,E_pad+H] x [3H, E_pad+H] (the embedding gather and the counter memset are separate launches)
+    ms = time_kernel(lambda i: ops.gru_last_state(toks[i % NB], P["emb"], P["w_ih"], P["b_ih"], P["w_hh"], P["b_hh"],
+                                                  packed=(P["wx_packed"], P["wh_packed"], P["bias_packed"])), reps)
+    out.append(entry("gru", "gru_pair_kernel (persistent GRU, 14 steps, tcgen05 cta_group::2; + gather + memset launches)",
+                     "tensor", ms, 2.0 * B * T * 3 * H * (E + H) - 2.0 * B * 3 * H * H, 1e12))
+    ms = time_kernel(lambda i: ops.linear(imgs[i % NB].view(B * K, V), P["Wv"], P["sv"], P["bv"], relu=True, mul=qq,
+                                          mul_row_div=K, logit_w=P["wlin"]), reps)
+    out.append(entry("wv", "linear_tc_kernel<256,pair> (W_v projection + x Qp + logit reduction, tcgen05 cta_group::2)",
+                     "tensor", ms, 2.0 * B * K * H * V, 1e12))
+    parts = torch.rand((B * K, 4), device=dev)
+    ms = time_kernel(lambda i: ops.attention_pool(parts, 0.0, imgs[i % NB], want_att=True, want_vsum=True), reps)
+    out.append(entry("pool", "attention_pool_stream_kernel (softmax over 36 regions + attention-weighted feature sum)",
+                     "hbm", ms, float(B * K * V * 2 + B * V * 2 + B * K * 4 * 5), 1e9))
+    if relation and "Wg3" in P:
+        Y = None
+
+        def wide(i):
+            nonlocal Y
+            Y = ops.linear(imgs[i % NB].view(B * K, V), P["Wg3"])
+        ms = time_kernel(wide, max(5, reps // 4))
+        out.append(entry("wide", "linear_tc_kernel<256,pair> (wide ReGAT projection [B*36,2048]x[6144,2048]^T, tcgen05 cta_group::2)",
+                         "tensor", ms, 2.0 * B * K * V * P["Wg3"].shape[0], 1e12))
+        att = torch.rand((B, K), device=dev)
+        ms = time_kernel(lambda i: ops.graph_attention_merged(Y, imgs[i % NB].view(B * K, V), att, labs[i % NB], P["wvec"],
+                                                              P["gat_c0"], P["label_bias_lp"], P["num_labels"], K,
+                                                              want_out=False, want_vsum=True), max(5, reps // 2))
+        out.append(entry("gat", "graph_attention_tc_kernel (relation-masked KxK graph attention, tcgen05; reads Y and x)",
+                         "hbm", ms, float(B * K * V * 2 * 4 + B * V * 2), 1e9))
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
         return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    ctx = Ctx()
+    ctx.rank, ctx.local_rank, ctx.world = rank, local_rank, world
+    ctx.dev = torch.device("cuda", local_rank)
+    ctx.dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=ctx.dev)
+        ctx.dist = dist
+
+    from oracle import vqa_oracle as O          # synthetic weights/inputs, the parity checker and the cpu_baseline leg only
+    from vqa_collection_b200 import ops
+    ctx.O, ctx.ops = O, ops
+
+    results = {wl: run_workload(ctx, args, wl) for wl in args.workloads}
+    if rank != 0:
+        if ctx.dist is not None:
+            ctx.dist.destroy_process_group()
+        return
+    first = args.workloads[0]
+    r = results[first]
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        sample_b = 64 if not relation else 16
-        qps, times, cores = cpu_forward_qps(args.workload, sample_b, 5 if not relation else 3)
-        best = sample_b / min(times)
-        qps1, _, _ = cpu_forward_qps(args.workload, sample_b if not relation else 8, 1, warmup=1, threads=1)
-        torch.set_num_threads(cores)
-        cpu = {"value": qps, "unit": UNIT, "cores": cores, "kind": "port", "best_of": best, "value_1_thread": qps1,
-               "cpu_model": cpu_model(),
-               "sample": f"{sample_b} questions x {len(times)} passes (mean; best_of = fastest pass), fp32 torch-CPU oracle "
-                         f"port of Wrapper.forward_vqa, {cores} threads"}
+        # the same function, model and full batch as `--impl reference`, bounded to ~10-30 s of CPU work
+        cpu = {}
+        for wl in args.workloads:
+            c = cpu_forward_qps(wl, args.batch, 3 if wl == "updown" else 1, warmup=1)
+            cpu[wl] = {"value": c["qps"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"], "best_of": c["best"],
+                       "cpu_model": cpu_model(), "sample": c["sample"]}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision if args.precision == "bf16" else "f32",
-        "data": "synthetic", "config": workload_config(args),
-        "clocks": sampler.summary(),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                "host_pack_threads": host_pack_threads(), "host_cores_per_rank": host_cores_per_rank(),
-                "raw_chunk_period": RAW_PERIOD, "raw_chunk_period_trials_ms": {str(k): round(v, 3) for k, v in trials.items()},
-                "batches_in_flight": 2,
-                "note": "vqa_forward_host_submit/_wait: pinned f32 host features (reference wire format) -> 64-image chunks, "
-                        "one in raw_chunk_period sent as f32 and cast on the device, the others packed to bf16 by this rank's "
-                        "share of the host cores (0 = all packed, 1 = all raw; the split is picked by a short trial run of every "
-                        "candidate), all pipelined with H2D -> forward -> answers D2H; batch n+1 is staged while batch n computes"},
-        "e2e_f32_over_pcie": e2e_alt,
-        "e2e_bf16_host_cache": e2e_bf16,
-        "gpu_launches": launches,
-        "roofline": roof,
-        "path_tflops_per_gpu": path_tflops,
-        "path_frac_of_sustained_bf16": path_tflops / pk["bf16_tflops_sustained"],
-        "cpu_baseline": cpu,
+        "data": "synthetic", "config": r["config"],
     }
+    for k in ("clocks", "e2e", "e2e_bf16_host_cache", "gpu_launches", "launches_per_step", "launch_mode", "schedule",
+              "per_rank_ms_total", "parity", "roofline", "roofline_kernels", "path_tflops_per_gpu",
+              "path_frac_of_sustained_bf16"):
+        if k in r:
+            line[k] = r[k]
+    line["cpu_baseline"] = cpu[first] if cpu else None
+    for wl in args.workloads[1:]:
+        blk = dict(results[wl])
+        blk["cpu_baseline"] = cpu[wl] if cpu else None
+        line[wl] = blk
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -494,19 +494,25 @@ def test_fused_optimizer_host_side():
 
 
 def test_bench_reference_arm_json_contract():
-    """`bench.py --impl reference` needs no GPU: the reference's CPU path (oracle port) on a bounded sample, one JSON line with
-    the keys the driver reads (metric / value / unit / config of the b200 arm, impl, cpu_baseline, e2e with zero copy bytes)"""
+    """`bench.py --impl reference` needs no GPU: the reference's own CPU path (baseline/_ref, staged by build(); the oracle
+    port only when that copy is absent) on the full 1024-question batch, ONE JSON line on stdout with the keys the driver
+    reads (metric / value / unit / config of the b200 arm, impl, cpu_baseline, e2e with zero copy bytes) and the ReGAT block"""
     import json
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
+    assert len(out.stdout.strip().splitlines()) == 1, out.stdout[:500]          # nothing but the JSON line on stdout
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "questions/s" and line["higher_is_better"] is True
     assert line["metric"].startswith("VQA forward questions/sec") and line["n_gpus"] == 1 and line["steps"] == 1
     assert line["value"] > 0 and line["vs_baseline"] is None and line["data"] == "synthetic"
     assert line["config"]["workload"].startswith("Up-Down VQA forward") and line["config"]["batch_per_gpu"] == 1024
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    staged = os.path.isdir(os.path.join(root, "baseline", "_ref", "modules"))
+    assert cb["kind"] == ("reference" if staged else "port") and cb["cores"] >= 1 and cb["value"] == line["value"]
+    assert "1024 questions per step" in cb["sample"] and line["same_config"] is True
+    rg = line["regat"]
+    assert rg["value"] > 0 and rg["config"]["workload"].startswith("ReGAT") and rg["cpu_baseline"]["kind"] == cb["kind"]
     assert line["e2e"] == {"value": line["value"], "unit": "questions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
