@@ -55,7 +55,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workloads", default="updown,regat", help="comma list; the first one is the line's `value`")
+    ap.add_argument("--workloads", default="updown,regat,train",
+                    help="comma list; the first one is the line's `value`; `train` = the config-4 training-step block")
     ap.add_argument("--workload", default=None, help="(compat) a single workload")
     ap.add_argument("--batch", type=int, default=1024, help="questions per GPU per step")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -63,12 +64,17 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="direct launches instead of CUDA graph replays")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--overlap", type=int, default=None, help="force the two-stream schedule on (1) / off (0)")
+    ap.add_argument("--overlap", type=int, default=None, help="force the encoder-beside-projection schedule on (1) / off (0)")
+    ap.add_argument("--chase", type=int, default=None, help="SMs of the graph attention chasing the wide projection (0 = serial)")
     a = ap.parse_args()
     a.workloads = [a.workload] if a.workload else [w for w in a.workloads.split(",") if w]
+    a.train_block = "train" in a.workloads
+    a.workloads = [w for w in a.workloads if w != "train"]
     for w in a.workloads:
         if w not in WORKLOAD_NAME:
             ap.error(f"unknown workload {w}")
+    if not a.workloads:
+        ap.error("need at least one forward workload")
     return a
 
 
@@ -299,6 +305,8 @@ def run_workload(ctx, args, wl):
     cfg = O.FULL_REGAT if relation else O.FULL
     W = O.make_weights(cfg, 1111)
     kw = {} if args.overlap is None else {"overlap": bool(args.overlap)}
+    if args.chase is not None:
+        kw["gat_chase_sms"] = args.chase
     eng = VQAEngine(W, relation=relation, precision=args.precision, device=ctx.dev, **kw)
     B, NB, dev, rank = args.batch, 4, ctx.dev, ctx.rank
     batch0 = O.make_batch(cfg, B, 3000 + rank)                 # batch 0 is a full oracle batch (parity below)
@@ -364,7 +372,9 @@ def run_workload(ctx, args, wl):
     res = {"value": value, "unit": UNIT, "ms_per_step": ms_total / args.steps, "steps": args.steps,
            "per_rank_ms_total": [round(x, 4) for x in per_rank], "launch_mode": mode,
            "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-           "schedule": ("two streams: question encoder beside the question-independent projection" if eng.overlap and
+           "schedule": (f"two streams: graph attention on {eng.gat_chase_sms} SMs chasing the wide projection (reads Y from L2)"
+                        if relation and eng.gat_chase_sms > 0 and args.precision == "bf16" else
+                        "two streams: question encoder beside the question-independent projection" if eng.overlap and
                         args.precision == "bf16" and B >= 512 else "one stream"),
            "clocks": sampler.summary(), "config": workload_config(args, wl)}
 
@@ -496,6 +506,82 @@ def kernel_rooflines(ctx, args, eng, imgs, toks, labs, relation):
     return out
 
 
+def run_train_block(ctx, args, global_batch=512, steps=20, warmup=5):
+    """BASELINE config 4: Up-Down training step at a FIXED global batch of 512 (strong scaling: 512 / N questions per GPU),
+    one step = train.py:103-111 (get_loss -> backward -> clip_grad_norm_ -> Adamax.step -> zero_grad) with the NCCL gradient
+    all-reduce in two buckets (training.py).  Also times the fused forward+backward call alone and the all-reduce of the
+    flat gradient buffer alone, so the record says what bounds the step at every N."""
+    import vqa_collection_b200 as pkg
+    from vqa_collection_b200 import optim as fused, training
+    from vqa_collection_b200.modules.wrapper import set_model
+    from vqa_collection_b200.parallel import shard_batch, average_gradients_
+    O, dev, world, rank = ctx.O, ctx.dev, ctx.world, ctx.rank
+    cfg = O.FULL
+    prev = pkg.get_precision()
+    pkg.set_precision(args.precision)
+    try:
+        m = set_model(encoder_type="base", predictor_type="base", decoder_type="none", ntoken=cfg.ntoken, v_dim=cfg.v_dim,
+                      embed_dim=cfg.embed_dim, hidden_dim=cfg.hidden_dim, rnn_layer=1, ans_dim=cfg.ans_dim, cls_layer=2, c_len=20,
+                      device=str(dev), dropout=0.2, rnn_type="GRU", att_type="new", conv_layer=1, conv_type="corr")
+        m.load_state_dict(O.make_weights(cfg, 1111), strict=True)
+        opt = fused.Adamax([{'params': m.encoder.parameters()}, {'params': m.predictor.parameters(), 'lr': 0.002}], lr=0.002)
+        b = shard_batch(O.make_batch(cfg, global_batch, 7), world, rank)
+        dt = torch.bfloat16 if args.precision == "bf16" else torch.float32
+        batch = {"img": b["img"].to(dt).to(dev), "q": b["q"].to(dev), "a": b["a"].float().to(dev)}
+        m.train()
+
+        def step():
+            loss, _ = m.get_loss(batch)
+            loss.backward()
+            fused.clip_grad_norm_(m.parameters(), 0.25)
+            opt.step()
+            opt.zero_grad()
+            return loss
+
+        for _ in range(warmup):
+            step()
+        barrier(ctx)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        barrier(ctx)
+        ms, per_rank = all_max(ctx, e0.elapsed_time(e1) / steps)
+        # the fused forward + loss + backward call (+ its all-reduce buckets when N > 1), no optimizer, no host reads
+        e0.record()
+        for _ in range(steps):
+            l, _ = training.updown_loss(m, batch["img"], batch["q"], batch["a"], seed=1)
+            l.backward()
+            opt.zero_grad()
+        e1.record()
+        barrier(ctx)
+        ms_core, _ = all_max(ctx, e0.elapsed_time(e1) / steps)
+        n_grad = sum(p.numel() for p in m.parameters())
+        ar_ms = None
+        if ctx.dist is not None:
+            flat = torch.zeros((n_grad,), dtype=torch.float32, device=dev)
+            for _ in range(3):
+                average_gradients_(flat)
+            barrier(ctx)
+            e0.record()
+            for _ in range(10):
+                average_gradients_(flat)
+            e1.record()
+            barrier(ctx)
+            ar_ms, _ = all_max(ctx, e0.elapsed_time(e1) / 10)
+        return {"metric": "Up-Down VQA training questions/sec (global batch %d)" % global_batch,
+                "value": global_batch / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "per_rank_ms_per_step": [round(x, 4) for x in per_rank],
+                "ms_fwd_loss_bwd_allreduce": ms_core, "allreduce_alone_ms": ar_ms, "allreduce_bytes": 4 * n_grad,
+                "allreduce": "ncclAllReduce AVG over NVLink, two buckets: the 7 weight-normed layers under the BPTT, then GRU + embedding",
+                "scaling": "strong", "steps": steps, "loss": float(loss), "dtype": args.precision,
+                "config": {"workload": "Up-Down VQA training step batch 512 with NCCL gradient allreduce",
+                           "global_batch": global_batch, "per_gpu_batch": int(batch["img"].shape[0]), "parallelism": f"dp{world}",
+                           "optimizer": "vqa_collection_b200.optim.Adamax + clip_grad_norm_(0.25), one launch each (train.py:108-111)"}}
+    finally:
+        pkg.set_precision(prev)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -521,6 +607,12 @@ def main():
     ctx.O, ctx.ops = O, ops
 
     results = {wl: run_workload(ctx, args, wl) for wl in args.workloads}
+    train = None
+    if args.train_block:
+        try:
+            train = run_train_block(ctx, args)
+        except Exception as e:                              # never lose the forward line to the training block
+            train = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if rank != 0:
         if ctx.dist is not None:
             ctx.dist.destroy_process_group()
@@ -551,6 +643,8 @@ def main():
         blk = dict(results[wl])
         blk["cpu_baseline"] = cpu[wl] if cpu else None
         line[wl] = blk
+    if train is not None:
+        line["train"] = train
     print(json.dumps(line), flush=True)
     if ctx.dist is not None:
         ctx.dist.destroy_process_group()

@@ -136,6 +136,11 @@ typedef struct {
    * cta_limit SMs, so that two calls on different streams can split one GEMM between two sets of SMs. */
   int tile_begin, tile_end;
   int cta_limit;
+  /* optional progress counters int32 [2*ceil(M/256)], ZERO on entry (bf16 tensor-core path, store form): every finished
+   * output tile adds 1 (release, gpu scope) to the counter of its 128-row block; a row block is complete when its
+   * counter reaches ceil(N / tile width) (vqa_linear_tiles_n).  Lets a consumer kernel on another stream start on
+   * finished row blocks while the GEMM is still running (vqa_graph_attention_args.d_progress). */
+  int* d_progress;
 } vqa_linear_args;
 
 int vqa_linear(const vqa_linear_args* args, void* stream);
@@ -143,6 +148,8 @@ int vqa_linear_part_width(int dtype);
 /* number of output tiles (the unit of tile_begin / tile_end) the call would walk over; 0 when the shape takes a path
  * without tile ranges (fp32) */
 int vqa_linear_tile_count(const vqa_linear_args* args);
+/* tiles per 128-row block along N (the value a d_progress counter reaches when its row block is complete) */
+int vqa_linear_tiles_n(const vqa_linear_args* args);
 size_t vqa_linear_argmax_workspace_bytes(int M);
 
 /* ------------------------------------------------------------------------
@@ -253,6 +260,13 @@ typedef struct {
   const void* d_wvec;
   float c0;
   const void* d_label_bias_lp;
+  /* layout 1 only, optional: the kernel runs BESIDE the GEMM that produces Y (another stream, grid capped at cta_limit
+   * SMs) and starts on an image as soon as the 128-row blocks of Y that hold its K rows are complete: d_progress are
+   * that GEMM's counters (vqa_linear_args.d_progress), progress_target = vqa_linear_tiles_n of it.  Images are taken
+   * in ascending order, the order in which the GEMM finishes them, so Y is read while it is still in L2.
+   * The producer GEMM must be running (or done): a wait of more than ~2 s traps instead of hanging. */
+  const int* d_progress; int progress_target;
+  int cta_limit;             /* 0 = one CTA per SM */
 } vqa_graph_attention_args;
 
 int vqa_graph_attention(const vqa_graph_attention_args* args, void* stream);
@@ -434,6 +448,13 @@ typedef struct {
   int overlap;
   int side_sms;              /* SMs of the side stream, even (0 = 64)                                        */
   int side_tile_permille;    /* 0 = automatic (from the shapes); -1 = none                                   */
+  /* ReGAT, bf16 merged form: gat_chase_sms = G > 0 runs the graph attention on G SMs of the side stream BESIDE the wide
+   * projection (which keeps the other SMs): the GEMM publishes every finished 128-row block of Y (vqa_linear_args
+   * .d_progress) and the graph attention works on an image as soon as its rows are complete, i.e. while they are still in
+   * L2 — Y's HBM read and most of the HBM-bound kernel's SM time disappear behind the tensor-bound one.  Takes
+   * precedence over `overlap`.  Falls back to the serial order under a profiler / CUDA_LAUNCH_BLOCKING (kernels of the
+   * two streams must be able to run at the same time). */
+  int gat_chase_sms;
 } vqa_forward_args;
 
 size_t vqa_forward_workspace_bytes(const vqa_forward_args* args);
@@ -524,6 +545,10 @@ typedef struct {
   float* d_loss;                      /* [1]                                   */
   float* d_logits;                    /* [B,A] f32 predictions                 */
   void* d_workspace; size_t workspace_bytes;
+  /* optional cudaEvent_t, recorded on `stream` when the gradients of the seven weight-normed layers (g_v / g_g / g_b:
+   * 59 of the 75.5 MB) are final — before the back-propagation through time — so that a data-parallel caller can
+   * all-reduce that bucket on another stream while the GRU / embedding gradients are still being computed */
+  void* ev_head_done;
 } vqa_train_args;
 
 size_t vqa_train_workspace_bytes(const vqa_train_args* args);

@@ -33,6 +33,7 @@ class LinearArgs(C.Structure):
         ("leaky_slope", c_float), ("add_after_act", c_int), ("sigmoid", c_int),
         ("d_argmax_label", c_void_p), ("d_argmax_ws", c_void_p),
         ("tile_begin", c_int), ("tile_end", c_int), ("cta_limit", c_int),
+        ("d_progress", c_void_p),
     ]
 
 
@@ -62,6 +63,7 @@ class GraphAttentionArgs(C.Structure):
         ("d_out", c_void_p), ("d_vsum", c_void_p), ("d_alpha", c_void_p),
         ("layout", c_int), ("d_x", c_void_p), ("ldx", c_int), ("d_wvec", c_void_p), ("c0", c_float),
         ("d_label_bias_lp", c_void_p),
+        ("d_progress", c_void_p), ("progress_target", c_int), ("cta_limit", c_int),
     ]
 
 
@@ -87,7 +89,7 @@ class ForwardArgs(C.Structure):
         ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("d_logits", c_void_p), ("d_label", c_void_p), ("d_att", c_void_p), ("d_q", c_void_p),
         ("d_v", c_void_p), ("d_alpha", c_void_p), ("d_labels_out", c_void_p),
-        ("overlap", c_int), ("side_sms", c_int), ("side_tile_permille", c_int),
+        ("overlap", c_int), ("side_sms", c_int), ("side_tile_permille", c_int), ("gat_chase_sms", c_int),
     ]
 
 
@@ -118,6 +120,7 @@ class TrainArgs(C.Structure):
         ("g_v", _fp), ("g_g", _fp), ("g_b", _fp),
         ("d_loss", c_void_p), ("d_logits", c_void_p),
         ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("ev_head_done", c_void_p),
     ]
 
 
@@ -166,6 +169,7 @@ SYMBOLS = {
     "vqa_linear": (c_int, [C.POINTER(LinearArgs), c_void_p]),
     "vqa_linear_part_width": (c_int, [c_int]),
     "vqa_linear_tile_count": (c_int, [C.POINTER(LinearArgs)]),
+    "vqa_linear_tiles_n": (c_int, [C.POINTER(LinearArgs)]),
     "vqa_linear_argmax_workspace_bytes": (c_size_t, [c_int]),
     "vqa_gru_last_state": (c_int, [C.POINTER(GruArgs), c_void_p]),
     "vqa_gru_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

@@ -329,6 +329,10 @@ int vqa_linear_tile_count(const vqa_linear_args* args) {
   if (!args || args->dtype != VQA_BF16 || force_simt()) return 0;
   return linear_tc_tile_count(*args);
 }
+int vqa_linear_tiles_n(const vqa_linear_args* args) {
+  if (!args || args->dtype != VQA_BF16 || force_simt()) return 0;
+  return linear_tc_tiles_n(*args);
+}
 size_t vqa_linear_argmax_workspace_bytes(int M) { return argmax_ws_bytes(M); }
 
 size_t vqa_gru_workspace_bytes(int B, int T, int H, int E_pad, int dtype) {
@@ -494,14 +498,29 @@ int vqa_adamax_step(const vqa_optim_tensor* h_tensors, int n_tensors, float beta
 }
 
 // ---- whole path --------------------------------------------------------------
+// kernels of two streams can run at the same time only outside profilers that serialise launches
+static bool concurrent_kernels_ok() {
+  static int v = -1;
+  if (v < 0) {
+    const char* b = getenv("CUDA_LAUNCH_BLOCKING");
+    v = (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || (b && b[0] == '1')) ? 0 : 1;
+  }
+  return v == 1;
+}
+// ReGAT: the graph attention runs beside the wide projection and chases it (vqa_forward_args.gat_chase_sms)
+static bool chase_mode(const vqa_forward_args& a) {
+  return a.relation && a.gat_chase_sms > 0 && a.d_Wg3 && a.dtype == VQA_BF16 && !force_simt() && a.K == 36 &&
+         a.B >= 128 && concurrent_kernels_ok();
+}
 static bool overlap_mode(const vqa_forward_args& a) {
-  return a.overlap && a.dtype == VQA_BF16 && !force_simt() && a.d_wx_packed && a.d_wh_packed && a.d_bias_packed &&
+  return !chase_mode(a) && a.overlap && a.dtype == VQA_BF16 && !force_simt() && a.d_wx_packed && a.d_wh_packed && a.d_bias_packed &&
          a.B >= 512 && a.H % 64 == 0 && a.E_pad % 64 == 0 && a.H % 8 == 0;
 }
 
 struct FwdWs {
   void* gru; size_t gru_bytes;
   float* h; void* h_lp; float* qq; float* parts; void* vsum; void* Y; void* proj; void* joint; void* hid;
+  int* progress;                             // row-block counters of the wide projection (chase mode)
   void* amax; size_t amax_bytes;             // fused answer selection of the last classifier layer
   size_t bytes;
 };
@@ -524,6 +543,7 @@ static FwdWs carve_fwd(const vqa_forward_args& a, void* base) {
   w.vsum = take((size_t)a.B * a.V * es);
   w.Y = a.relation ? take((size_t)a.B * a.K * (a.d_Wg3 ? 3 : 4) * a.V * es) : nullptr;
   w.proj = (!a.relation && overlap_mode(a)) ? take((size_t)a.B * a.K * a.H * es) : nullptr;   // stored W_v projection
+  w.progress = chase_mode(a) ? (int*)take(((size_t)(a.B * a.K + 255) / 256 * 2 + 1) * 4) : nullptr;
   w.joint = take((size_t)a.B * a.H * es);
   w.hid = take((size_t)a.B * 2 * a.H * es);
   w.bytes = off;
@@ -609,9 +629,10 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
 
   // ---- schedule: everything on `s` in order, or (overlap) question encoder on the side stream `sq` while the
   //      question-independent projection of the region features runs on `s` on the other SMs
-  SideCtx* side = overlap_mode(a) ? side_ctx() : nullptr;
-  const bool overlap = side != nullptr;
-  VQA_REQUIRE(overlap || !overlap_mode(a), "vqa_forward: overlap requested but the side stream could not be created");
+  const bool chase = chase_mode(a);
+  SideCtx* side = (overlap_mode(a) || chase) ? side_ctx() : nullptr;
+  const bool overlap = side != nullptr && !chase;
+  VQA_REQUIRE(side || !(overlap_mode(a) || chase), "vqa_forward: a two-stream schedule was requested but the side stream could not be created");
   const int sms = sm_count();
   int side_sms = overlap ? ((a.side_sms > 0 ? a.side_sms : 64) & ~1) : 0;
   if (overlap && (side_sms < 2 || side_sms > sms - 2)) side_sms = (sms / 2) & ~1;
@@ -713,16 +734,34 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
     float* att = a.d_att;
     if ((rc = attention_pool(w.parts, n_parts, a.b_lin, a.d_img, a.B, a.K, a.V, a.dtype, att, nullptr, nullptr, s))) return rc;
     // 5. wide projection of the raw features (already done in overlap mode) + relation-masked graph attention (gcn.py)
+    cudaStream_t sg = s;                         // stream of the graph attention
+    int chase_sms = 0;
+    if (chase) {
+      // the graph attention chases the projection: GEMM on `s` (all SMs but chase_sms) publishes finished row blocks,
+      // the graph attention on the side stream consumes them while they are still in L2
+      chase_sms = a.gat_chase_sms < sms - 8 ? a.gat_chase_sms : sms - 8;
+      VQA_CUDA_CHECK(cudaMemsetAsync(w.progress, 0, ((size_t)(a.B * a.K + 255) / 256 * 2 + 1) * 4, s));
+      VQA_CUDA_CHECK(cudaEventRecord(side->fork, s));
+      VQA_CUDA_CHECK(cudaStreamWaitEvent(side->s, side->fork, 0));
+      proj.d_progress = w.progress;
+      proj.cta_limit = (sms - chase_sms) & ~1;
+      sg = side->s;
+    }
     if (!overlap && (rc = linear_dispatch(proj, s))) return rc;
     vqa_graph_attention_args ga{};
+    if (chase) { ga.d_progress = w.progress; ga.progress_target = linear_tc_tiles_n(proj); ga.cta_limit = chase_sms; }
     ga.d_Y = w.Y; ga.ldy = maps * a.V; ga.d_att = att; ga.d_labels = labels; ga.d_label_bias = a.d_label_bias;
     ga.num_labels = a.num_labels; ga.d_ba = a.d_ba; ga.d_bb = a.d_bb; ga.B = a.B; ga.K = a.K; ga.V = a.V; ga.dtype = a.dtype;
     ga.d_out = a.d_v; ga.d_vsum = w.vsum; ga.d_alpha = a.d_alpha;
     if (a.d_Wg3) {
       ga.layout = 1; ga.d_x = a.d_img; ga.ldx = a.V; ga.d_wvec = a.d_wvec; ga.c0 = a.gat_c0;
       ga.d_label_bias_lp = a.d_label_bias_lp;
-      if ((rc = graph_attention_tc(ga, s))) return rc;
+      if ((rc = graph_attention_tc(ga, sg))) return rc;
     } else if ((rc = graph_attention(ga, s))) return rc;
+    if (chase) {
+      VQA_CUDA_CHECK(cudaEventRecord(side->join, sg));
+      VQA_CUDA_CHECK(cudaStreamWaitEvent(s, side->join, 0));
+    }
   }
   // 6. v_net ⊙ q_net (predictor.py:88-91)
   l = vqa_linear_args{};

@@ -146,5 +146,6 @@ int linear_simt(const vqa_linear_args& a, cudaStream_t s);
 int linear_tc(const vqa_linear_args& a, cudaStream_t s);
 int linear_tc_part_width();
 int linear_tc_tile_count(const vqa_linear_args& a);
+int linear_tc_tiles_n(const vqa_linear_args& a);
 
 }  // namespace vqa

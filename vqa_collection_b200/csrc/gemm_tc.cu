@@ -62,6 +62,10 @@ struct Params {
   // fused lowest-index argmax over n (wrapper.py:14): keys u64 [M] (value order bits << 32 | ~n), per-row-block tile
   // counters [tiles_m] — both zero on entry — and the int64 labels written by the LAST tile of each row block
   unsigned long long* amax_keys; int* amax_cnt; long long* amax_label;
+  // optional progress counters [tiles_m], zero on entry: every finished tile adds 1 to the counter of its 128-row block
+  // (release), so a consumer kernel running BESIDE this one can start on a row block as soon as all tiles_n tiles of it
+  // are in memory (graph_attn_tc.cu chases the wide projection this way)
+  int* progress;
 };
 
 // ---- the kernel ----------------------------------------------------------------
@@ -363,6 +367,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         mbar_arrive(tempty_bar(acc));
       }
+      if (p.progress) {
+        // this CTA's 128 x BN block of the output is written: publish it (all 128 epilogue threads stored rows of it)
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) red_release_gpu_add(p.progress + m_blk, 1);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -442,6 +452,7 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
   p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
   p.leaky_slope = a.leaky_slope; p.add_after_act = a.add_after_act; p.sigmoid = a.sigmoid;
   p.amax_keys = nullptr; p.amax_cnt = nullptr; p.amax_label = nullptr;
+  p.progress = a.d_progress;
   if (a.d_argmax_label) {
     VQA_REQUIRE(a.d_argmax_ws && !a.d_logit_w, "vqa_linear: fused argmax needs its zeroed workspace and the store form");
     p.amax_keys = (unsigned long long*)a.d_argmax_ws;
@@ -512,6 +523,7 @@ static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
   p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
   p.leaky_slope = a.leaky_slope; p.add_after_act = a.add_after_act; p.sigmoid = a.sigmoid;
   p.amax_keys = nullptr; p.amax_cnt = nullptr; p.amax_label = nullptr;
+  p.progress = a.d_progress;
   tile_range(a, ((p.tiles_m + 1) / 2) * p.tiles_n, &p.tile_begin, &p.tile_end);
   const int pair_tiles = p.tile_end - p.tile_begin;
   if (pair_tiles <= 0) return VQA_OK;
@@ -583,6 +595,11 @@ int linear_tc_part_width() { return 256; }
 int linear_tc_tile_count(const vqa_linear_args& a) {
   if (a.M <= 0) return 0;
   return tc::plan_tiles(a, a.trans_a || a.trans_w).tiles;
+}
+int linear_tc_tiles_n(const vqa_linear_args& a) {
+  if (a.M <= 0) return 0;
+  const int bn = tc::plan_tiles(a, a.trans_a || a.trans_w).bn;
+  return (a.N + bn - 1) / bn;
 }
 
 int linear_tc(const vqa_linear_args& a, cudaStream_t s) {

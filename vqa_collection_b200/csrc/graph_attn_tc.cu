@@ -79,7 +79,16 @@ struct Params {
   int rev;                     // walk the images in descending order (the tail of Y is what the GEMM left in L2)
   const float* att; const uint8_t* labels; int num_labels; float c0;
   __nv_bfloat16* out; __nv_bfloat16* vsum; float* alpha;
+  // chase mode: Y is being produced by a GEMM running beside this kernel; counter m of `progress` reaches
+  // `progress_target` when rows [128m, 128m + 128) of Y are complete (gemm_tc.cu)
+  const int* progress; int progress_target;
 };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(P2_THREADS) : "memory"); }
 
@@ -142,6 +151,27 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       int stage = 0; uint32_t phase = 0;
       auto load_g = [&](int img) {                   // phase-1 operands of one image
         const int row0 = (p.rev ? p.B - 1 - img : img) * GK;
+        if (p.progress) {
+          // first touch of this image's rows of Y: wait until the producer GEMM has finished the (one or two) 128-row
+          // blocks that hold them, then make its generic-proxy stores visible to the TMA loads (async proxy)
+          // (the 40-row TMA boxes reach 4 rows into the next image: those rows meet zero coefficients in phase 3, but
+          // they must be finished — finite — data, so their row block is waited for as well)
+          const int m_last = (p.B * GK - 1) / BM;
+          const int m_lo = row0 / BM, m_hi = min((row0 + GROWS - 1) / BM, m_last);
+          unsigned long long t0 = 0;
+          for (int m = m_lo; m <= m_hi; ++m) {
+            unsigned int polls = 0;
+            while (ld_acquire_gpu(p.progress + m) < p.progress_target) {
+              if ((++polls & 0x3FFu) == 0) {           // a producer that never runs must not hang the device
+                const unsigned long long now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 2000000000ull) __trap();
+              }
+              __nanosleep(64);
+            }
+          }
+          fence_proxy_async_all();
+        }
         for (int kb = 0; kb < kb_g; kb += 2) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t slot = base + stage * SLOT_BYTES;
@@ -453,16 +483,19 @@ int graph_attention_tc(const vqa_graph_attention_args& a, cudaStream_t s) {
   Params p;
   p.B = a.B; p.V = a.V; p.att = a.d_att; p.labels = a.d_labels; p.num_labels = a.num_labels; p.c0 = a.c0;
   p.out = (__nv_bfloat16*)a.d_out; p.vsum = (__nv_bfloat16*)a.d_vsum; p.alpha = a.d_alpha;
+  p.progress = a.d_progress; p.progress_target = a.progress_target;
+  VQA_REQUIRE(!a.d_progress || a.progress_target > 0, "graph_attention(layout 1): d_progress needs progress_target > 0");
   // measured: no gain here (1089 vs 1085 us per ReGAT step) — Y is 3.6x the L2, the tail that survives is small
   static int rev = -1;
   if (rev < 0) { const char* e = getenv("VQA_B200_GAT_REVERSE"); rev = (e && e[0] == '1') ? 1 : 0; }
-  p.rev = rev;
+  p.rev = a.d_progress ? 0 : rev;                    // chase mode walks the images in the order the GEMM finishes them
   static DeviceOnce attr;                            // per device, not per process
   if (attr.need(current_device())) {
     VQA_CUDA_CHECK(cudaFuncSetAttribute(graph_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr.mark(current_device());
   }
-  const int grid = a.B < sm_count() ? a.B : sm_count();
+  int grid = a.B < sm_count() ? a.B : sm_count();
+  if (a.cta_limit > 0 && a.cta_limit < grid) grid = a.cta_limit;
   VQA_CUDA_CHECK(launch_pdl(graph_attention_tc_kernel, dim3(grid), dim3(THREADS), (size_t)SMEM_BYTES, s, tmQ, tmX, tmW, tmPS,
                             tmLB, p));
   VQA_LAUNCH_CHECK();

@@ -702,6 +702,16 @@ static int train_step_t(const vqa_train_args& a, const TrainWs& w, cudaStream_t 
   if ((rc = gemm_dW(dqq + H, 2 * H, hT, H, B, H, H, a.g_v[L_QNET], H))) return rc;
   if ((rc = gemm_dX(dqq, 2 * H, w.Wqq, H, B, H, H, svec(L_WQ), nullptr, nullptr, 0, 0, w.dh1, H, VQA_F32))) return rc;
   if ((rc = gemm_dX(dqq + H, 2 * H, (T*)w.Wqq + (size_t)H * H, H, B, H, H, svec(L_QNET), w.dh1, nullptr, 0, 0, w.dh0, H, VQA_F32))) return rc;
+  // weight-norm chain rule for the 7 layers, in place over the raw dW_eff.  All seven weight-normed layers are "head" layers:
+  // their gradients are final HERE, before the back-propagation through time — the caller's event marks that point, so a
+  // data-parallel job can all-reduce this bucket (59 of the 75.5 MB) on a side stream under the BPTT (training.py).
+  wn_dot_partials_kernel<<<dim3(PARTS, NL), 256, 0, s>>>(tb, 1, w.part);
+  VQA_LAUNCH_CHECK();
+  wn_backward_finalize_kernel<<<NL, 32, 0, s>>>(tb, w.part, w.scal, w.coef);
+  VQA_LAUNCH_CHECK();
+  wn_backward_apply_kernel<<<dim3(PARTS * 4, NL), 256, 0, s>>>(tb, w.scal, w.coef);
+  VQA_LAUNCH_CHECK();
+  if (a.ev_head_done) VQA_CUDA_CHECK(cudaEventRecord((cudaEvent_t)a.ev_head_done, s));
   // GRU, back-propagation through time
   float* dh_cur = w.dh0;
   float* dh_nxt = w.dh1;
@@ -724,13 +734,6 @@ static int train_step_t(const vqa_train_args& a, const TrainWs& w, cudaStream_t 
   if ((rc = gemm_dX(w.dGI, 3 * H, w.w_ih, Ep, B * Tn, 3 * H, Ep, nullptr, nullptr, nullptr, 0, 0, w.dX, Ep, VQA_F32))) return rc;
   VQA_CUDA_CHECK(cudaMemsetAsync(a.g_emb, 0, (size_t)a.ntoken_rows * E * 4, s));
   scatter_add_kernel<<<grid_for((size_t)B * Tn * E), 256, 0, s>>>(a.d_tokens, B * Tn, E, Ep, a.ntoken_rows, w.dX, a.g_emb);
-  VQA_LAUNCH_CHECK();
-  // weight-norm chain rule for the 7 layers, in place over the raw dW_eff
-  wn_dot_partials_kernel<<<dim3(PARTS, NL), 256, 0, s>>>(tb, 1, w.part);
-  VQA_LAUNCH_CHECK();
-  wn_backward_finalize_kernel<<<NL, 32, 0, s>>>(tb, w.part, w.scal, w.coef);
-  VQA_LAUNCH_CHECK();
-  wn_backward_apply_kernel<<<dim3(PARTS * 4, NL), 256, 0, s>>>(tb, w.scal, w.coef);
   VQA_LAUNCH_CHECK();
   (void)bf16;
   return VQA_OK;

@@ -182,18 +182,25 @@ class VQAEngine:
     """B200 forward engine for the Up-Down (+ReGAT) VQA path."""
 
     def __init__(self, weights: dict, relation: bool = False, precision: str = "bf16",
-                 device="cuda", num_objs: int = 36, overlap=None, side_sms: int = 0, side_tile_permille: int = 0):
-        """``overlap`` (bf16, B >= 512): run the question encoder on a side stream on ``side_sms`` SMs while the
-        question-independent projection of the region features runs on the other SMs (vqa_forward_args.overlap);
-        None = on unless VQA_B200_OVERLAP=0."""
+                 device="cuda", num_objs: int = 36, overlap=None, side_sms: int = 0, side_tile_permille: int = 0,
+                 gat_chase_sms=None):
+        """Two-stream schedules of ``vqa_forward`` (bf16 only, see include/vqa_b200.h):
+        ``gat_chase_sms`` (ReGAT): the graph attention runs on that many SMs BESIDE the wide projection and consumes Y
+        row block by row block while it is still in L2; None = 16 unless VQA_B200_GAT_CHASE says otherwise (0 = off).
+        ``overlap`` (B >= 512): the question encoder on a side stream on ``side_sms`` SMs while the question-independent
+        projection of the region features runs on the other SMs; measured no better than the serial order on a B200
+        (the GRU's L2-latency-bound step slows down beside a GEMM), so None = off unless VQA_B200_OVERLAP=1."""
         import os
         self.lib = L.load()
         self.device = torch.device(device)
         if self.device.index is None and self.device.type == "cuda":
             self.device = torch.device("cuda", torch.cuda.current_device())
         if overlap is None:
-            overlap = os.environ.get("VQA_B200_OVERLAP", "1") != "0"
+            overlap = os.environ.get("VQA_B200_OVERLAP", "0") == "1"
+        if gat_chase_sms is None:
+            gat_chase_sms = int(os.environ.get("VQA_B200_GAT_CHASE", "16") or 0)
         self.overlap, self.side_sms, self.side_tile_permille = bool(overlap), int(side_sms), int(side_tile_permille)
+        self.gat_chase_sms = int(gat_chase_sms) if relation else 0
         self.dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[precision]
         self.precision = precision
         self.relation = bool(relation)
@@ -211,6 +218,7 @@ class VQAEngine:
         a.num_labels = P.get("num_labels", 0)
         a.dtype, a.relation = ops.dtype_code(self.dtype), int(self.relation)
         a.overlap, a.side_sms, a.side_tile_permille = int(self.overlap), self.side_sms, self.side_tile_permille
+        a.gat_chase_sms = self.gat_chase_sms
         for name in ("emb", "w_ih", "b_ih", "w_hh", "b_hh", "Wv", "sv", "bv", "Wqq", "sqq", "bqq", "wlin",
                      "Wvn", "svn", "bvn", "Wc0", "sc0", "bc0", "Wc1", "sc1", "bc1"):
             setattr(a, "d_" + name, P[name].data_ptr())

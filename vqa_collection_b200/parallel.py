@@ -78,6 +78,10 @@ class FlatGradients:
         self._layout = list(zip(offs, sizes, shapes))
         self.views = [self.flat[o:o + n].view(s) for o, n, s in self._layout]
 
+    def offset_of(self, i: int) -> int:
+        """element offset of tensor i in the flat buffer (buckets are contiguous ranges of it)"""
+        return self._layout[i][0] if i < len(self._layout) else self.flat.numel()
+
     def fresh_views(self):
         """new tensor objects over the same memory (nobody else holds them, so autograd may adopt them as .grad)"""
         return [self.flat[o:o + n].view(s) for o, n, s in self._layout]

@@ -59,6 +59,21 @@ def _workspace(lib, a, device):
     return ws, need
 
 
+_BUCKET = {}
+
+
+def _bucket_event(dev):
+    """(head-done event, side stream) of a device; the event object exists in the driver (it has been recorded once), so
+    its raw handle can be handed to the C call"""
+    hit = _BUCKET.get(dev)
+    if hit is None:
+        with torch.cuda.device(dev):
+            ev = torch.cuda.Event()
+            ev.record()
+            hit = _BUCKET[dev] = (ev, torch.cuda.Stream(dev))
+    return hit
+
+
 class UpDownTrainStep(torch.autograd.Function):
     """(img [B,K,V] compute dtype, tokens int64 [B,T], target f32 [B,A], p_att, p_cls, seed, *26 params)
     → (loss 0-d f32, logits f32 [B,A])"""
@@ -106,17 +121,32 @@ class UpDownTrainStep(torch.autograd.Function):
         a.d_loss, a.d_logits = loss.data_ptr(), logits.data_ptr()
         ws, need = _workspace(lib, a, dev)
         a.d_workspace, a.workspace_bytes = ws.data_ptr(), need
-        with torch.cuda.device(dev):                 # the library launches on the current device
-            L.check(lib.vqa_updown_train_step(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         # Called under no_grad / with frozen parameters (evaluation through get_loss): nobody will run backward(), so the
-        # gradients are dropped here — no all-reduce is started (ranks that skip differently must not desynchronise) and
+        # gradients are dropped — no all-reduce is started (ranks that skip differently must not desynchronise) and
         # the flat buffer is free for the next step.
         wants_grad = any(ctx.needs_input_grad)
+        dp = _dp_active() and wants_grad
+        ev = side = None
+        if dp:
+            ev, side = _bucket_event(dev)
+            a.ev_head_done = ev.cuda_event
+        with torch.cuda.device(dev):                 # the library launches on the current device
+            L.check(lib.vqa_updown_train_step(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
         if not wants_grad:
             fg.pending = False
-        # the exchange step of the data-parallel training path: average the shard gradients over ranks
-        # (async on NCCL's stream; backward() waits for it, so clip_grad_norm_ sees the global gradient)
-        ctx.work = average_gradients_(fg.flat, _GROUP, async_op=True) if (_dp_active() and wants_grad) else None
+        # The exchange step of the data-parallel training path: average the shard gradients over ranks, in TWO buckets in
+        # the order the backward pass finishes them.  Bucket 1 = the seven weight-normed layers (59 of 75.5 MB), final
+        # before the back-propagation through time: its all-reduce is issued from a side stream that only waits for the
+        # step's head-done event, so NCCL moves it over NVLink while the BPTT still runs.  Bucket 2 = GRU + embedding, after
+        # the whole step.  backward() waits for both, so clip_grad_norm_ (train.py:109) sees the global gradient.
+        ctx.work = None
+        if dp:
+            head_off = fg.offset_of(len(GRU_PARAMS))
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                w1 = average_gradients_(fg.flat[head_off:], _GROUP, async_op=True)
+            w2 = average_gradients_(fg.flat[:head_off], _GROUP, async_op=True)
+            ctx.work = (w1, w2)
         ctx.fg = fg if wants_grad else None
         ctx.mark_non_differentiable(logits)
         return loss.reshape(()), logits
@@ -129,8 +159,9 @@ class UpDownTrainStep(torch.autograd.Function):
                                "keeps ONE set of gradients per forward; call get_loss again")
         ctx.fg = None
         fg.pending = False
-        if ctx.work is not None:
-            ctx.work.wait()
+        for work in (ctx.work or ()):
+            if work is not None:
+                work.wait()
         # ONE pass scales the whole flat buffer by the incoming gradient (1 after loss.backward()); the parameters then
         # receive FRESH views of it, which autograd adopts as .grad without copying (26 multiplies + 26 copies less)
         fg.flat.mul_(g_loss)
