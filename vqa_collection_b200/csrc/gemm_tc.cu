@@ -420,6 +420,22 @@ int make_tensor_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long
   return VQA_OK;
 }
 
+int make_tensor_map_bf16_nd(CUtensorMap* map, const void* ptr, int rank, const long long* dims,
+                            const long long* strides_bytes, const int* box) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(VQA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if (rank < 2 || rank > 4 || box[0] != BK) return fail(VQA_ERR_INVALID, "make_tensor_map_bf16_nd: rank=%d box0=%d", rank, box[0]);
+  cuuint64_t d[4]; cuuint64_t st[3]; cuuint32_t bx[4]; cuuint32_t es[4];
+  for (int i = 0; i < rank; ++i) { d[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = (cuuint64_t)strides_bytes[i];
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, st, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(VQA_ERR_CUDA, "cuTensorMapEncodeTiled (rank %d) failed with CUresult %d", rank, (int)r);
+  return VQA_OK;
+}
+
 // MN-major operand: the tensor is [K rows, MN cols] row-major; box = {64 mn, 64 k-rows}
 static int make_tensor_map_mn(CUtensorMap* map, const void* ptr, long long k_rows, long long mn_cols, long long ld) {
   return make_tensor_map_bf16(map, ptr, k_rows, mn_cols, ld, BK);

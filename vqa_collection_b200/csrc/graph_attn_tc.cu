@@ -48,9 +48,17 @@ constexpr int SLOT_BYTES = 2 * ATOM_BYTES;   // 24 KB
 // bytes in flight / HBM latency: 7 slots x 17 KB / 2.8 us = 43 GB/s per SM, 0.68 of HBM.)  The MMAs read 48 x-rows (N = 48):
 // rows 40..47 are the first rows of the wvec tile — finite garbage that only reaches the unused columns 40..47 of D1.
 constexpr int GROWS = 40;
-constexpr int G_Q_OFF = 0, G_X_OFF = GROWS * 128, G_W_OFF = 2 * GROWS * 128;
 constexpr int G_BYTES = 2 * GROWS * 128 + 16 * 128;       // 12 KB per k-block
 static_assert(2 * G_BYTES == 2 * 12 * 1024, "two phase-1 k-blocks fill one ring slot");
+// Slot layouts (one TMA instruction per operand, 3-D / 4-D boxes over the 64-column atoms — the producer was bound by
+// TMA instructions per image, 192 small boxes, not by bytes):
+//   phase 1: [Q k-block 0 | Q k-block 1 | x k-block 0 | x k-block 1 | wvec k-block 0 | wvec k-block 1]   (5+5+5+5+2+2 KB)
+//   phase 3: [atom 0: P 40 rows, S 40 rows | atom 1: P, S | bias atom 0 | bias atom 1]                   (10+10+2+2 KB)
+constexpr int G_TILE = GROWS * 128;                       // one 40-row k-block tile (5 KB)
+constexpr int G_Q_OFF = 0, G_X_OFF = 2 * G_TILE, G_W_OFF = 4 * G_TILE, G_W_TILE = 16 * 128;
+constexpr int PS_ATOM_BYTES = (P_ROWS + S_ROWS) * 128;    // 10 KB: the P and S rows of one 64-channel atom
+constexpr int LB_SLOT_OFF = 2 * PS_ATOM_BYTES, LB_ATOM_BYTES = LB_ROWS * 128;
+static_assert(LB_SLOT_OFF + 2 * LB_ATOM_BYTES == 2 * ATOM_BYTES, "phase-3 slot");
 constexpr int STAGES = 7;
 constexpr int BT_CHUNK = NPAD * 128;         // one 64-k chunk of the coefficient tile (6 KB)
 constexpr int BT_BYTES = 2 * BT_CHUNK;
@@ -176,13 +184,9 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t slot = base + stage * SLOT_BYTES;
           mbar_arrive_expect_tx(full_bar(stage), 2 * G_BYTES);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t sk = slot + h * G_BYTES;
-            tma_load_2d(sk + G_Q_OFF, &tmQ, full_bar(stage), 2 * V + (kb + h) * BK, row0);
-            tma_load_2d(sk + G_X_OFF, &tmX, full_bar(stage), (kb + h) * BK, row0);
-            tma_load_2d(sk + G_W_OFF, &tmW, full_bar(stage), (kb + h) * BK, 0);
-          }
+          tma_load_3d(slot + G_Q_OFF, &tmQ, full_bar(stage), 0, row0, (2 * V) / BK + kb);     // Q, two k-blocks
+          tma_load_3d(slot + G_X_OFF, &tmX, full_bar(stage), 0, row0, kb);                    // x
+          tma_load_3d(slot + G_W_OFF, &tmW, full_bar(stage), 0, 0, kb);                       // [Waᵀbb, Wbᵀba]
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       };
@@ -194,14 +198,8 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t slot = base + stage * SLOT_BYTES;
           mbar_arrive_expect_tx(full_bar(stage), SLOT_BYTES);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int c = cc * CH + h * 64;
-            const uint32_t atom = slot + h * ATOM_BYTES;
-            tma_load_2d(atom, &tmPS, full_bar(stage), c, row0);                          // P rows (k 0..39)
-            tma_load_2d(atom + S_OFF * 128, &tmPS, full_bar(stage), V + c, row0);        // S rows (k 40..79)
-            tma_load_2d(atom + LB_OFF * 128, &tmLB, full_bar(stage), c, 0);              // bias rows (k 80..95)
-          }
+          tma_load_4d(slot, &tmPS, full_bar(stage), 0, row0, 0, cc * (CH / 64));          // P and S rows of both atoms
+          tma_load_3d(slot + LB_SLOT_OFF, &tmLB, full_bar(stage), 0, 0, cc * (CH / 64));  // bias rows of both atoms
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -222,9 +220,9 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           const uint32_t slot = base + stage * SLOT_BYTES;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const uint32_t sk = slot + h * G_BYTES;
-            const uint64_t qd = make_sw128_kmajor_desc(sk + G_Q_OFF), xd = make_sw128_kmajor_desc(sk + G_X_OFF),
-                           wd = make_sw128_kmajor_desc(sk + G_W_OFF);
+            const uint64_t qd = make_sw128_kmajor_desc(slot + G_Q_OFF + h * G_TILE),
+                           xd = make_sw128_kmajor_desc(slot + G_X_OFF + h * G_TILE),
+                           wd = make_sw128_kmajor_desc(slot + G_W_OFF + h * G_W_TILE);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               umma_bf16(dg + COL_G, qd + 2 * k, xd + 2 * k, idesc_g, (kb | h | k) != 0);
@@ -257,7 +255,10 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           const uint32_t d = tmem_base + COL_OUT + buf * OUT_STRIDE;
 #pragma unroll
           for (int ks = 0; ks < KROWS / UMMA_K; ++ks) {
-            const uint64_t ad = make_sw128_mnmajor_desc(slot + ks * 2048, ATOM_BYTES, 1024);
+            // k rows 0..79 = the P and S rows (atoms 10 KB apart), k rows 80..95 = the bias rows (atoms 2 KB apart)
+            const uint64_t ad = ks < (P_ROWS + S_ROWS) / UMMA_K
+                                    ? make_sw128_mnmajor_desc(slot + ks * 2048, PS_ATOM_BYTES, 1024)
+                                    : make_sw128_mnmajor_desc(slot + LB_SLOT_OFF, LB_ATOM_BYTES, 1024);
             const uint64_t bd = make_sw128_kmajor_desc(btb + (ks >> 2) * BT_CHUNK) + (uint64_t)(2 * (ks & 3));
             umma_bf16(d, ad, bd, idesc_o, ks != 0);
           }
@@ -475,11 +476,21 @@ int graph_attention_tc(const vqa_graph_attention_args& a, cudaStream_t s) {
   CUtensorMap tmQ, tmX, tmW, tmPS, tmLB;
   int rc;
   const long long rows = (long long)a.B * GK;
-  if ((rc = tc::make_tensor_map_bf16(&tmQ, a.d_Y, rows, a.ldy, a.ldy, GROWS))) return rc;
-  if ((rc = tc::make_tensor_map_bf16(&tmX, a.d_x, rows, a.V, a.ldx, GROWS))) return rc;
-  if ((rc = tc::make_tensor_map_bf16(&tmW, a.d_wvec, 16, a.V, a.V, 16))) return rc;
-  if ((rc = tc::make_tensor_map_bf16(&tmPS, a.d_Y, rows, a.ldy, a.ldy, P_ROWS))) return rc;
-  if ((rc = tc::make_tensor_map_bf16(&tmLB, a.d_label_bias_lp, LB_ROWS, a.V, a.V, LB_ROWS))) return rc;
+  {
+    // every operand is a row-major matrix viewed as [64-column atoms][rows][64 cols]: one box = several atoms
+    const int bq[3] = {BK, GROWS, 2}, bw[3] = {BK, 16, 2}, bps[4] = {BK, P_ROWS, 2, 2};
+    const long long dq[3] = {BK, rows, a.ldy / BK}, sq[2] = {2LL * a.ldy, 2LL * BK};
+    const long long dx[3] = {BK, rows, a.V / BK}, sx[2] = {2LL * a.ldx, 2LL * BK};
+    const long long dw[3] = {BK, 16, a.V / BK}, sw[2] = {2LL * a.V, 2LL * BK};
+    // P / S: [atoms][map: P = 0, S = 1 (V columns further)][rows][64 cols]
+    const long long dps[4] = {BK, rows, 2, a.V / BK}, sps[3] = {2LL * a.ldy, 2LL * a.V, 2LL * BK};
+    VQA_REQUIRE(a.ldy % BK == 0 && a.V % BK == 0, "graph_attention(layout 1): ldy and V must be multiples of %d", BK);
+    if ((rc = tc::make_tensor_map_bf16_nd(&tmQ, a.d_Y, 3, dq, sq, bq))) return rc;
+    if ((rc = tc::make_tensor_map_bf16_nd(&tmX, a.d_x, 3, dx, sx, bq))) return rc;
+    if ((rc = tc::make_tensor_map_bf16_nd(&tmW, a.d_wvec, 3, dw, sw, bw))) return rc;
+    if ((rc = tc::make_tensor_map_bf16_nd(&tmPS, a.d_Y, 4, dps, sps, bps))) return rc;
+    if ((rc = tc::make_tensor_map_bf16_nd(&tmLB, a.d_label_bias_lp, 3, dw, sw, bw))) return rc;
+  }
   Params p;
   p.B = a.B; p.V = a.V; p.att = a.d_att; p.labels = a.d_labels; p.num_labels = a.num_labels; p.c0 = a.c0;
   p.out = (__nv_bfloat16*)a.d_out; p.vsum = (__nv_bfloat16*)a.d_vsum; p.alpha = a.d_alpha;

@@ -125,12 +125,12 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_ptr;
   griddep_launch();
 
-  // this CTA's half of the pair's W rows: [r | z | n] rows of units [u0 + HALF·crank, u0 + HALF·crank + HALF)
+  // this CTA's half of the pair's W rows: [r | z | n] rows of units [u0 + HALF·crank, u0 + HALF·crank + HALF) — ONE 3-D box
+  // {64 cols, HALF rows, 3 gates} out of the gate-interleaved packing (the packed matrix viewed as [3H/64 gate blocks][64
+  // rows][K]); it lands as three consecutive HALF-row tiles, the layout the MMAs read.  (Three 2-D boxes per stage before:
+  // the producer is bound by TMA instructions per step, not by bytes.)
   auto load_w = [&](uint32_t sw, const CUtensorMap* map, uint32_t bar, int col) {
-#pragma unroll
-    for (int g = 0; g < 3; ++g)
-      tma_load_2d_2cta(sw + g * (HALF_UNITS * 128), map, bar, col,
-                       (u0 / PACK_UNITS) * (3 * PACK_UNITS) + g * PACK_UNITS + (u0 % PACK_UNITS) + (int)crank * HALF_UNITS);
+    tma_load_3d_2cta(sw, map, bar, col, (u0 % PACK_UNITS) + (int)crank * HALF_UNITS, (u0 / PACK_UNITS) * 3);
   };
 
   if (warp == 0) {
@@ -392,8 +392,14 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
   if (coop < 0) { const char* e = getenv("VQA_B200_GRU_COOP"); coop = (e && e[0] == '0') ? 0 : 1; }
   CUtensorMap tmWx, tmWh;
   int rc;
-  if ((rc = tc::make_tensor_map_bf16(&tmWx, wx_p, 3LL * H, E_pad, E_pad, HALF_UNITS))) return rc;
-  if ((rc = tc::make_tensor_map_bf16(&tmWh, wh_p, 3LL * H, H, H, HALF_UNITS))) return rc;
+  {
+    // packed W [3H, K] viewed as [3H/64 gate blocks][64 rows][K]: box = {64 cols, HALF_UNITS rows, 3 gate blocks}
+    const int box[3] = {tc::BK, HALF_UNITS, 3};
+    const long long dx[3] = {E_pad, PACK_UNITS, 3LL * H / PACK_UNITS}, sx[2] = {2LL * E_pad, 2LL * E_pad * PACK_UNITS};
+    const long long dh[3] = {H, PACK_UNITS, 3LL * H / PACK_UNITS}, sh[2] = {2LL * H, 2LL * H * PACK_UNITS};
+    if ((rc = tc::make_tensor_map_bf16_nd(&tmWx, wx_p, 3, dx, sx, box))) return rc;
+    if ((rc = tc::make_tensor_map_bf16_nd(&tmWh, wh_p, 3, dh, sh, box))) return rc;
+  }
   for (int b0 = 0; b0 < B; b0 += max_groups * rows_per_group) {
     const int Bc = (B - b0 < max_groups * rows_per_group) ? B - b0 : max_groups * rows_per_group;
     const int groups = (Bc + rows_per_group - 1) / rows_per_group;   // padded to whole groups; extra rows are masked

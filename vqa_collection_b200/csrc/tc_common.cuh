@@ -131,6 +131,24 @@ __device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
 }
+// 3-D / 4-D boxes: ONE instruction fetches several 64-column atoms (k-blocks, gate blocks, maps) of a row-major matrix.
+// The TMA unit's cost per instruction is what bounds kernels that move many small boxes (measured: the GRU step and the
+// graph attention ran at one box per ~100-190 clk per SM whatever the bytes), so fewer, larger boxes it is.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 // arrive on the mbarrier at the same offset in CTA `rank` of this cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
   asm volatile(
@@ -221,6 +239,10 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
 // box = [box_rows, 64 cols], 128-byte swizzle, OOB reads return zero
 int make_tensor_map_bf16(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld,
                          int box_rows);
+// host: general bf16 tensor map of rank 2..4, 128-byte swizzle; dims[0] is the contiguous one (box[0] must be 64),
+// strides_bytes[i] = byte stride of dims[i + 1] (multiples of 16)
+int make_tensor_map_bf16_nd(CUtensorMap* map, const void* ptr, int rank, const long long* dims,
+                            const long long* strides_bytes, const int* box);
 
 }  // namespace tc
 }  // namespace vqa
