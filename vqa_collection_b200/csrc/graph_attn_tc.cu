@@ -63,16 +63,21 @@ constexpr int STAGES = 7;
 constexpr int BT_CHUNK = NPAD * 128;         // one 64-k chunk of the coefficient tile (6 KB)
 constexpr int BT_BYTES = 2 * BT_CHUNK;
 constexpr int BT_BUFS = 2;                   // coefficient tile double buffered over images
-constexpr int P2_THREADS = 128;              // warps 4..7: phase 0/2;  warps 8..11: phase-3 epilogue
-constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, EPI_THREADS = EPI_WARPS * 32;
-constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;      // 384
+// warps 4..11: phase 0/2 (the K×K stage);  warps 12..15: phase-3 epilogue.  The K×K stage is the per-image critical
+// path of a CTA (36 k warp-instructions of dependent shared-memory arithmetic per image): with 4 warps — one per
+// scheduler, IPC 0.25 — it took ≈ 19 us per image whatever the memory system did (the kernel ran at the same 31-34 GB/s
+// per SM from HBM on 148 SMs and from L2 on 16); 8 warps halve the work per thread and give every scheduler two warps.
+constexpr int P2_WARPS = 8, P2_THREADS = P2_WARPS * 32;
+constexpr int EPI_WARP0 = 4, EPI3_WARP0 = EPI_WARP0 + P2_WARPS, EPI_WARPS = P2_WARPS + 4, EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;      // 512
 constexpr int TMEM_COLS = 512;
 constexpr int COL_G = 0, COL_U = 48, G_STRIDE = 64, COL_OUT = 128, OUT_STRIDE = 64, OUT_BUFS = 4;
 
+constexpr int GP = GK + 4;                   // row pitch of A0 / Al: 16-byte aligned rows for float4 access
 struct P2 {
   float G[GK][GK + 1];                       // Q·xᵀ
-  float A0[GK][GK + 1];                      // ReLU(dot)
-  float Al[GK][GK + 1];                      // adj·A0 → α
+  alignas(16) float A0[GK][GP];              // ReLU(dot)
+  alignas(16) float Al[GK][GP];              // adj·A0 → α
   float hist[GK][MAXL];
   float a[GK], ua[GK], ub[GK];
   unsigned long long adj[GK], adjT[GK];      // row masks (bit k: label_ik≠0), column masks (bit j: label_jk≠0)
@@ -271,31 +276,40 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     }
   } else if (warp >= EPI_WARP0) {
     const int q = warp & 3;                          // TMEM lane quarter of this warp
-    const int hf = (warp - EPI_WARP0) >> 2;          // 0: phase 0/2 warps (4..7), 1: phase-3 epilogue warps (8..11)
-    const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127 within the phase-2 group
+    const int hf = warp >= EPI3_WARP0 ? 1 : 0;       // 0: phase 0/2 warps, 1: phase-3 epilogue warps
+    const int et = threadIdx.x - EPI_WARP0 * 32;     // index within the phase-2 group
     // ---- phase 0: attention scalars, row adjacency masks, label histogram of one image
     auto phase0 = [&](int img_it) {
       const int img = p.rev ? p.B - 1 - img_it : img_it;
-      if (et < GK) {
-        sm.a[et] = p.att ? __ldg(p.att + (size_t)img * GK + et) : 1.f;
-        const uint32_t* lr = reinterpret_cast<const uint32_t*>(p.labels + ((size_t)img * GK + et) * GK);
-        uint32_t w[GK / 4];
+      // 4 threads per region row, 9 labels each (whole warps take part in the shuffles): adjacency bits and a packed
+      // 8-bit-per-label histogram, combined over the 4 neighbouring lanes
+      if (et < 160) {
+        const bool valid = et < 4 * GK;
+        const int r = valid ? (et >> 2) : 0, part = et & 3;
+        const uint8_t* lr = p.labels + ((size_t)img * GK + r) * GK + part * (GK / 4);
+        unsigned long long m = 0ull, h0 = 0ull, h1 = 0ull;
 #pragma unroll
-        for (int k4 = 0; k4 < GK / 4; ++k4) w[k4] = __ldg(lr + k4);
-        unsigned long long m = 0ull;
-        float h[MAXL];
-#pragma unroll
-        for (int l = 0; l < MAXL; ++l) h[l] = 0.f;
-#pragma unroll
-        for (int k = 0; k < GK; ++k) {
-          const int l = (w[k >> 2] >> (8 * (k & 3))) & 0xff;
-          if (l != 0) m |= (1ull << k);
-#pragma unroll
-          for (int t = 0; t < MAXL; ++t) h[t] += (t == l) ? 1.f : 0.f;
+        for (int k = 0; k < GK / 4; ++k) {
+          const unsigned l = valid ? (unsigned)__ldg(lr + k) : 0u;
+          if (l != 0) m |= 1ull << (part * (GK / 4) + k);
+          if (l < 8) h0 += 1ull << (8 * l);
+          else if (l < MAXL) h1 += 1ull << (8 * (l - 8));
         }
-        sm.adj[et] = m;
 #pragma unroll
-        for (int l = 0; l < MAXL; ++l) sm.hist[et][l] = (l < p.num_labels) ? h[l] : 0.f;
+        for (int o = 1; o <= 2; o <<= 1) {
+          m |= __shfl_xor_sync(0xffffffffu, m, o);
+          h0 += __shfl_xor_sync(0xffffffffu, h0, o);
+          h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+        }
+        if (valid && part == 0) {
+          sm.a[r] = p.att ? __ldg(p.att + (size_t)img * GK + r) : 1.f;
+          sm.adj[r] = m;
+#pragma unroll
+          for (int l = 0; l < MAXL; ++l) {
+            const unsigned cnt = (unsigned)(((l < 8 ? h0 >> (8 * l) : h1 >> (8 * (l - 8)))) & 0xffull);
+            sm.hist[r][l] = (l < p.num_labels) ? (float)cnt : 0.f;
+          }
+        }
       }
     };
     uint32_t it = 0;
@@ -307,7 +321,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       const uint32_t gbuf = it & 1u;
       mbar_wait(gfull_bar(gbuf), (it >> 1) & 1u);
       tcgen05_fence_after();
-      if (q < 2) {
+      if (q < 2 && warp < EPI_WARP0 + 4) {          // rows 0..63 of D1 / D2: one warp per TMEM lane quarter
         uint32_t v[32], w16[16], u16[16];
         const uint32_t t_row = tmem_base + gbuf * G_STRIDE + ((uint32_t)(q * 32) << 16);
         tmem_ld_32x32(t_row + COL_G, v);
@@ -342,13 +356,17 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
       epi_bar();
       // ---- 2c: α1 = adj·α0
-      for (int e = et; e < GK * GK; e += P2_THREADS) {
-        const int i = e / GK, j = e - i * GK;
+      for (int e = et; e < GK * (GK / 4); e += P2_THREADS) {          // thread = (row i, 4 columns): one LDS.128 per k
+        const int i = e / (GK / 4), j4 = (e - i * (GK / 4)) * 4;
         const unsigned long long m = sm.adj[i];
-        float s = 0.f;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < GK; ++k) s += ((m >> k) & 1ull) ? sm.A0[k][j] : 0.f;
-        sm.Al[i][j] = s;
+        for (int k = 0; k < GK; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(&sm.A0[k][j4]);
+          const bool on = (m >> k) & 1ull;
+          s.x += on ? v.x : 0.f; s.y += on ? v.y : 0.f; s.z += on ? v.z : 0.f; s.w += on ? v.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(&sm.Al[i][j4]) = s;
       }
       epi_bar();
       // ---- 2d: softmax over the row index i for every column j (4 threads per column, 9 rows each)
