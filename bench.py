@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--overlap", type=int, default=None, help="force the encoder-beside-projection schedule on (1) / off (0)")
+    ap.add_argument("--side-sms", type=int, default=0)
+    ap.add_argument("--side-permille", type=int, default=0)
     ap.add_argument("--chase", type=int, default=None, help="SMs of the graph attention chasing the wide projection (0 = serial)")
     a = ap.parse_args()
     a.workloads = [a.workload] if a.workload else [w for w in a.workloads.split(",") if w]
@@ -307,6 +309,10 @@ def run_workload(ctx, args, wl):
     kw = {} if args.overlap is None else {"overlap": bool(args.overlap)}
     if args.chase is not None:
         kw["gat_chase_sms"] = args.chase
+    if args.side_sms:
+        kw["side_sms"] = args.side_sms
+    if args.side_permille:
+        kw["side_tile_permille"] = args.side_permille
     eng = VQAEngine(W, relation=relation, precision=args.precision, device=ctx.dev, **kw)
     B, NB, dev, rank = args.batch, 4, ctx.dev, ctx.rank
     batch0 = O.make_batch(cfg, B, 3000 + rank)                 # batch 0 is a full oracle batch (parity below)

@@ -582,10 +582,12 @@ static SideCtx* side_ctx() {
 }
 
 // Share (per mille) of the projection's tiles that the side SMs take once the question encoder is done: both sets of
-// SMs should finish together.  tile time ~ 12.5 us per 256 x 256 x 2048 pair tile, encoder ~ 10.5 us per GRU step + 30 us
-// (measured at H = 1024, profiles/); the engine can override the estimate (side_tile_permille).
+// SMs should finish together.  tile time ~ 12.5 us per 256 x 256 x 2048 pair tile; encoder beside a running GEMM ~ 15.7 us
+// per GRU step (two interleaved row blocks on 64 SMs) + 70 us (fork, gather, [W_q;q_net] on 64 SMs) — measured at H = 1024:
+// 300 per mille is the best split of the wide ReGAT projection at B = 1024 (profiles/r02_overlap_split.md); the engine
+// can override the estimate (side_tile_permille).
 static int auto_side_permille(int tiles, int K, int T, int main_sms, int side_sms) {
-  const double tau = 12.5 * K / 2048.0, G = 10.5 * T + 30.0;
+  const double tau = 12.5 * K / 2048.0, G = 15.7 * T + 70.0;
   const double pt = main_sms / 2, ps = side_sms / 2;
   const double t_end = (tiles * tau + ps * G) / (pt + ps);
   double share = ps * (t_end - G) / tau / tiles;

@@ -95,6 +95,8 @@ struct Params {
   // chase mode: Y is being produced by a GEMM running beside this kernel; counter m of `progress` reaches
   // `progress_target` when rows [128m, 128m + 128) of Y are complete (gemm_tc.cu)
   const int* progress; int progress_target;
+  int debug;                   // VQA_B200_GAT_DEBUG bits (timing experiments only, results are wrong): 1 = no D2 MMAs,
+                               // 2 = no phase-1 MMAs, 4 = no phase-3 MMAs, 8 = no K×K arithmetic
 };
 
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -230,8 +232,8 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
                            wd = make_sw128_kmajor_desc(slot + G_W_OFF + h * G_W_TILE);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              umma_bf16(dg + COL_G, qd + 2 * k, xd + 2 * k, idesc_g, (kb | h | k) != 0);
-              umma_bf16(dg + COL_U, xd + 2 * k, wd + 2 * k, idesc_u, (kb | h | k) != 0);
+              if (!(p.debug & 2)) umma_bf16(dg + COL_G, qd + 2 * k, xd + 2 * k, idesc_g, (kb | h | k) != 0);
+              if (!(p.debug & 3)) umma_bf16(dg + COL_U, xd + 2 * k, wd + 2 * k, idesc_u, (kb | h | k) != 0);
             }
           }
           umma_commit(empty_bar(stage));
@@ -265,7 +267,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
                                     ? make_sw128_mnmajor_desc(slot + ks * 2048, PS_ATOM_BYTES, 1024)
                                     : make_sw128_mnmajor_desc(slot + LB_SLOT_OFF, LB_ATOM_BYTES, 1024);
             const uint64_t bd = make_sw128_kmajor_desc(btb + (ks >> 2) * BT_CHUNK) + (uint64_t)(2 * (ks & 3));
-            umma_bf16(d, ad, bd, idesc_o, ks != 0);
+            if (!(p.debug & 4)) umma_bf16(d, ad, bd, idesc_o, ks != 0);
           }
           umma_commit(empty_bar(stage));
           umma_commit(ofull_bar(buf));
@@ -340,6 +342,13 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
       tcgen05_fence_before();
       epi_bar();
+      if (p.debug & 8) {                                 // timing experiment: hand the (stale) coefficient tile over at once
+        const uint32_t cbd = it & 1u;
+        if (it >= 2) mbar_wait(cempty_bar(cbd), ((it >> 1) - 1u) & 1u);
+        epi_bar();
+        if (et == 0) mbar_arrive(cfull_bar(cbd));
+        continue;
+      }
       // ---- 2b: α0 = ReLU(dot); column masks adjT from the row masks
       for (int e = et; e < GK * GK; e += P2_THREADS) {
         const int i = e / GK, j = e - i * GK;
@@ -513,6 +522,9 @@ int graph_attention_tc(const vqa_graph_attention_args& a, cudaStream_t s) {
   p.B = a.B; p.V = a.V; p.att = a.d_att; p.labels = a.d_labels; p.num_labels = a.num_labels; p.c0 = a.c0;
   p.out = (__nv_bfloat16*)a.d_out; p.vsum = (__nv_bfloat16*)a.d_vsum; p.alpha = a.d_alpha;
   p.progress = a.d_progress; p.progress_target = a.progress_target;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("VQA_B200_GAT_DEBUG"); dbg = e ? atoi(e) : 0; }
+  p.debug = dbg;
   VQA_REQUIRE(!a.d_progress || a.progress_target > 0, "graph_attention(layout 1): d_progress needs progress_target > 0");
   // measured: no gain here (1089 vs 1085 us per ReGAT step) — Y is 3.6x the L2, the tail that survives is small
   static int rev = -1;

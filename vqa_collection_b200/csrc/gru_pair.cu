@@ -66,6 +66,7 @@ struct Params {
   int* counter;                 // per-row-block (128 rows) arrival counters, zero on entry
   // training form (train.cu): states time-major, gates saved for the backward pass (f32 [T,Bfull,H] each, chunk offset applied)
   int time_major, Bfull, b0;
+  int thread_fences;            // 1 = every epilogue thread fences before the publish barrier (VQA_B200_GRU_FENCE=1)
   float *save_r, *save_z, *save_n, *save_hn, *save_h;   // save_h: slot t = state AFTER step t
 };
 
@@ -287,9 +288,13 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
       }
       if (!last) {
-        __threadfence();
+        // publish h_t: the state stores of all epilogue threads are ordered before the barrier; the release at gpu scope of
+        // the ONE thread that then bumps the counter is cumulative over what it has observed through the barrier (PTX
+        // memory model), so the other 511 threads need no fence of their own (each cost a round trip to L2 in the chain)
+        if (p.thread_fences) __threadfence();
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
         if (et == 0) {
+          __threadfence();
           fence_proxy_async_all();
           red_release_gpu_add(p.counter + m_blk, 1);
         }
@@ -429,6 +434,9 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
     p.h_last_lp = h_last_lp ? (__nv_bfloat16*)h_last_lp + (size_t)b0 * H : nullptr;
     p.counter = counter;
     p.time_major = tmajor ? 1 : 0; p.Bfull = B; p.b0 = b0;
+    static int fences = -1;
+    if (fences < 0) { const char* e = getenv("VQA_B200_GRU_FENCE"); fences = (e && e[0] == '1') ? 1 : 0; }
+    p.thread_fences = fences;
     const size_t so = (size_t)b0 * H;
     p.save_r = tmajor ? save->R + so : nullptr; p.save_z = tmajor ? save->Z + so : nullptr;
     p.save_n = tmajor ? save->N + so : nullptr; p.save_hn = tmajor ? save->HN + so : nullptr;
@@ -473,9 +481,10 @@ int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, co
   auto ctas = [&](int units, int rb) { return 2 * ((row_pairs + rb - 1) / rb) * (H / units); };
   int cfg = forced;
   if (!cfg) {
-    if (sm_limit > 0 && !save && row_pairs >= 2 && ctas(64, 2) <= budget) cfg = 642;
-    else if (2 * ctas(64, 1) <= budget) cfg = 321;
-    else cfg = 641;
+    if (2 * ctas(64, 1) <= budget) cfg = 321;                 // small batch: narrower tiles fill the SMs
+    else if (ctas(64, 1) <= budget) cfg = 641;                // one row block per pair fits: lowest latency
+    else if (!save && row_pairs >= 2 && ctas(64, 2) <= budget) cfg = 642;   // half the SMs: two interleaved row blocks
+    else cfg = 641;                                           // several launches
   }
 #define VQA_GRU_CALL(U, R) gru_pair_t<U, R>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, sm_limit, s)
   switch (cfg) {

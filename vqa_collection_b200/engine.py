@@ -184,21 +184,24 @@ class VQAEngine:
     def __init__(self, weights: dict, relation: bool = False, precision: str = "bf16",
                  device="cuda", num_objs: int = 36, overlap=None, side_sms: int = 0, side_tile_permille: int = 0,
                  gat_chase_sms=None):
-        """Two-stream schedules of ``vqa_forward`` (bf16 only, see include/vqa_b200.h):
-        ``gat_chase_sms`` (ReGAT): the graph attention runs on that many SMs BESIDE the wide projection and consumes Y
-        row block by row block while it is still in L2; None = 16 unless VQA_B200_GAT_CHASE says otherwise (0 = off).
+        """Two-stream schedules of ``vqa_forward`` (bf16 only, see include/vqa_b200.h; measurements in DESIGN.md §3.6):
         ``overlap`` (B >= 512): the question encoder on a side stream on ``side_sms`` SMs while the question-independent
-        projection of the region features runs on the other SMs; measured no better than the serial order on a B200
-        (the GRU's L2-latency-bound step slows down beside a GEMM), so None = off unless VQA_B200_OVERLAP=1."""
+        projection of the region features runs on the other SMs.  ReGAT: 2 % faster than the serial order (the wide
+        projection keeps 84 SMs busy while the latency-bound GRU runs) -> None = on; Up-Down: 5 % slower (the W_v projection
+        must then be stored and reduced by a second kernel) -> None = off.  VQA_B200_OVERLAP=0/1 overrides both.
+        ``gat_chase_sms`` (ReGAT): the graph attention on that many SMs BESIDE the wide projection, consuming Y row block
+        by row block.  Correct but not faster (one SM of the graph attention moves 33 GB/s whatever the memory system
+        does, so it needs > 32 SMs to keep up with the GEMM): None = off unless VQA_B200_GAT_CHASE=n."""
         import os
         self.lib = L.load()
         self.device = torch.device(device)
         if self.device.index is None and self.device.type == "cuda":
             self.device = torch.device("cuda", torch.cuda.current_device())
         if overlap is None:
-            overlap = os.environ.get("VQA_B200_OVERLAP", "0") == "1"
+            env = os.environ.get("VQA_B200_OVERLAP", "")
+            overlap = (env == "1") if env in ("0", "1") else bool(relation)
         if gat_chase_sms is None:
-            gat_chase_sms = int(os.environ.get("VQA_B200_GAT_CHASE", "16") or 0)
+            gat_chase_sms = int(os.environ.get("VQA_B200_GAT_CHASE", "0") or 0)
         self.overlap, self.side_sms, self.side_tile_permille = bool(overlap), int(side_sms), int(side_tile_permille)
         self.gat_chase_sms = int(gat_chase_sms) if relation else 0
         self.dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[precision]
