@@ -50,12 +50,18 @@ constexpr int SLOT_BYTES = 2 * ATOM_BYTES;   // 24 KB
 constexpr int GROWS = 40;
 constexpr int G_BYTES = 2 * GROWS * 128 + 16 * 128;       // 12 KB per k-block
 static_assert(2 * G_BYTES == 2 * 12 * 1024, "two phase-1 k-blocks fill one ring slot");
-// Slot layouts (one TMA instruction per operand, 3-D / 4-D boxes over the 64-column atoms — the producer was bound by
-// TMA instructions per image, 192 small boxes, not by bytes):
-//   phase 1: [Q k-block 0 | Q k-block 1 | x k-block 0 | x k-block 1 | wvec k-block 0 | wvec k-block 1]   (5+5+5+5+2+2 KB)
-//   phase 3: [atom 0: P 40 rows, S 40 rows | atom 1: P, S | bias atom 0 | bias atom 1]                   (10+10+2+2 KB)
+// Slot layouts:
+//   phase 1: two k-blocks, each [Q 40 rows | x 40 rows | wvec 16 rows] (5+5+2 KB) — ONE tcgen05.mma per k-step reads the
+//            128 rows from Q on as A and the 64 rows from x on as B: D[0..39][0..39] = Q·xᵀ and D[40..79][40..55] =
+//            x·[Waᵀbb, Wbᵀba]ᵀ land in one 64-column accumulator (two MMAs per k-step before; the kernel pays ≈ 50 ns per
+//            MMA instruction whatever its N, measured by switching them off: 135.6 -> 122.1 us without the second one).
+//            Rows 96..127 of A / 56..63 of B are whatever follows in shared memory — finite, and they only reach rows /
+//            columns of D that nobody reads.
+//   phase 3: [atom 0: P 40 rows, S 40 rows | atom 1: P, S | bias atom 0 | bias atom 1] (10+10+2+2 KB), one 4-D box for
+//            the P and S rows of both 64-channel atoms, one 3-D box for the bias rows
 constexpr int G_TILE = GROWS * 128;                       // one 40-row k-block tile (5 KB)
-constexpr int G_Q_OFF = 0, G_X_OFF = 2 * G_TILE, G_W_OFF = 4 * G_TILE, G_W_TILE = 16 * 128;
+constexpr int G_Q_OFF = 0, G_X_OFF = G_TILE, G_W_OFF = 2 * G_TILE;
+constexpr int U_ROW0 = 40, U_COL0 = 40;                   // D rows / columns of the x·wvec block
 constexpr int PS_ATOM_BYTES = (P_ROWS + S_ROWS) * 128;    // 10 KB: the P and S rows of one 64-channel atom
 constexpr int LB_SLOT_OFF = 2 * PS_ATOM_BYTES, LB_ATOM_BYTES = LB_ROWS * 128;
 static_assert(LB_SLOT_OFF + 2 * LB_ATOM_BYTES == 2 * ATOM_BYTES, "phase-3 slot");
@@ -71,7 +77,7 @@ constexpr int P2_WARPS = 8, P2_THREADS = P2_WARPS * 32;
 constexpr int EPI_WARP0 = 4, EPI3_WARP0 = EPI_WARP0 + P2_WARPS, EPI_WARPS = P2_WARPS + 4, EPI_THREADS = EPI_WARPS * 32;
 constexpr int THREADS = EPI_WARP0 * 32 + EPI_THREADS;      // 512
 constexpr int TMEM_COLS = 512;
-constexpr int COL_G = 0, COL_U = 48, G_STRIDE = 64, COL_OUT = 128, OUT_STRIDE = 64, OUT_BUFS = 4;
+constexpr int COL_G = 0, G_STRIDE = 64, COL_OUT = 128, OUT_STRIDE = 64, OUT_BUFS = 4;
 
 constexpr int GP = GK + 4;                   // row pitch of A0 / Al: 16-byte aligned rows for float4 access
 struct P2 {
@@ -95,7 +101,7 @@ struct Params {
   // chase mode: Y is being produced by a GEMM running beside this kernel; counter m of `progress` reaches
   // `progress_target` when rows [128m, 128m + 128) of Y are complete (gemm_tc.cu)
   const int* progress; int progress_target;
-  int debug;                   // VQA_B200_GAT_DEBUG bits (timing experiments only, results are wrong): 1 = no D2 MMAs,
+  int debug;                   // VQA_B200_GAT_DEBUG bits (timing experiments only, results are wrong):
                                // 2 = no phase-1 MMAs, 4 = no phase-3 MMAs, 8 = no K×K arithmetic
 };
 
@@ -191,9 +197,13 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t slot = base + stage * SLOT_BYTES;
           mbar_arrive_expect_tx(full_bar(stage), 2 * G_BYTES);
-          tma_load_3d(slot + G_Q_OFF, &tmQ, full_bar(stage), 0, row0, (2 * V) / BK + kb);     // Q, two k-blocks
-          tma_load_3d(slot + G_X_OFF, &tmX, full_bar(stage), 0, row0, kb);                    // x
-          tma_load_3d(slot + G_W_OFF, &tmW, full_bar(stage), 0, 0, kb);                       // [Waᵀbb, Wbᵀba]
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t sk = slot + h * G_BYTES;
+            tma_load_3d(sk + G_Q_OFF, &tmQ, full_bar(stage), 0, row0, (2 * V) / BK + kb + h);
+            tma_load_3d(sk + G_X_OFF, &tmX, full_bar(stage), 0, row0, kb + h);
+            tma_load_3d(sk + G_W_OFF, &tmW, full_bar(stage), 0, 0, kb + h);                  // [Waᵀbb, Wbᵀba]
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       };
@@ -214,8 +224,7 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc_g = make_idesc_bf16(128, NPAD);
-      constexpr uint32_t idesc_u = make_idesc_bf16(128, 16);
+      constexpr uint32_t idesc_g = make_idesc_bf16(128, 64);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, NPAD) | IDESC_A_MN_MAJOR;
       int stage = 0; uint32_t phase = 0;
       auto mma_g = [&](uint32_t gbuf) {
@@ -227,14 +236,11 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           const uint32_t slot = base + stage * SLOT_BYTES;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const uint64_t qd = make_sw128_kmajor_desc(slot + G_Q_OFF + h * G_TILE),
-                           xd = make_sw128_kmajor_desc(slot + G_X_OFF + h * G_TILE),
-                           wd = make_sw128_kmajor_desc(slot + G_W_OFF + h * G_W_TILE);
+            const uint32_t sk = slot + h * G_BYTES;
+            const uint64_t ad = make_sw128_kmajor_desc(sk + G_Q_OFF), bd = make_sw128_kmajor_desc(sk + G_X_OFF);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
-              if (!(p.debug & 2)) umma_bf16(dg + COL_G, qd + 2 * k, xd + 2 * k, idesc_g, (kb | h | k) != 0);
-              if (!(p.debug & 3)) umma_bf16(dg + COL_U, xd + 2 * k, wd + 2 * k, idesc_u, (kb | h | k) != 0);
-            }
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              if (!(p.debug & 2)) umma_bf16(dg + COL_G, ad + 2 * k, bd + 2 * k, idesc_g, (kb | h | k) != 0);
           }
           umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -323,12 +329,12 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       const uint32_t gbuf = it & 1u;
       mbar_wait(gfull_bar(gbuf), (it >> 1) & 1u);
       tcgen05_fence_after();
-      if (q < 2 && warp < EPI_WARP0 + 4) {          // rows 0..63 of D1 / D2: one warp per TMEM lane quarter
-        uint32_t v[32], w16[16], u16[16];
+      if (q < 3 && warp < EPI_WARP0 + 4) {          // D rows 0..35 = Q·xᵀ, rows 40..75 = x·wvecᵀ: one warp per lane quarter
+        uint32_t v[32], w16[16], u8[8];
         const uint32_t t_row = tmem_base + gbuf * G_STRIDE + ((uint32_t)(q * 32) << 16);
         tmem_ld_32x32(t_row + COL_G, v);
         tmem_ld_32x16(t_row + COL_G + 32, w16);
-        tmem_ld_32x16(t_row + COL_U, u16);
+        tmem_ld_32x8(t_row + COL_G + U_COL0, u8);
         tmem_ld_wait();
         const int r = q * 32 + lane;
         if (r < GK) {
@@ -336,8 +342,10 @@ graph_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           for (int j = 0; j < 32; ++j) sm.G[r][j] = __uint_as_float(v[j]);
 #pragma unroll
           for (int j = 0; j < GK - 32; ++j) sm.G[r][32 + j] = __uint_as_float(w16[j]);
-          sm.ua[r] = __uint_as_float(u16[0]);
-          sm.ub[r] = __uint_as_float(u16[1]);
+        }
+        if (r >= U_ROW0 && r < U_ROW0 + GK) {
+          sm.ua[r - U_ROW0] = __uint_as_float(u8[0]);
+          sm.ub[r - U_ROW0] = __uint_as_float(u8[1]);
         }
       }
       tcgen05_fence_before();
@@ -505,7 +513,7 @@ int graph_attention_tc(const vqa_graph_attention_args& a, cudaStream_t s) {
   const long long rows = (long long)a.B * GK;
   {
     // every operand is a row-major matrix viewed as [64-column atoms][rows][64 cols]: one box = several atoms
-    const int bq[3] = {BK, GROWS, 2}, bw[3] = {BK, 16, 2}, bps[4] = {BK, P_ROWS, 2, 2};
+    const int bq[3] = {BK, GROWS, 1}, bw1[3] = {BK, 16, 1}, bw[3] = {BK, 16, 2}, bps[4] = {BK, P_ROWS, 2, 2};
     const long long dq[3] = {BK, rows, a.ldy / BK}, sq[2] = {2LL * a.ldy, 2LL * BK};
     const long long dx[3] = {BK, rows, a.V / BK}, sx[2] = {2LL * a.ldx, 2LL * BK};
     const long long dw[3] = {BK, 16, a.V / BK}, sw[2] = {2LL * a.V, 2LL * BK};
@@ -514,7 +522,7 @@ int graph_attention_tc(const vqa_graph_attention_args& a, cudaStream_t s) {
     VQA_REQUIRE(a.ldy % BK == 0 && a.V % BK == 0, "graph_attention(layout 1): ldy and V must be multiples of %d", BK);
     if ((rc = tc::make_tensor_map_bf16_nd(&tmQ, a.d_Y, 3, dq, sq, bq))) return rc;
     if ((rc = tc::make_tensor_map_bf16_nd(&tmX, a.d_x, 3, dx, sx, bq))) return rc;
-    if ((rc = tc::make_tensor_map_bf16_nd(&tmW, a.d_wvec, 3, dw, sw, bw))) return rc;
+    if ((rc = tc::make_tensor_map_bf16_nd(&tmW, a.d_wvec, 3, dw, sw, bw1))) return rc;
     if ((rc = tc::make_tensor_map_bf16_nd(&tmPS, a.d_Y, 4, dps, sps, bps))) return rc;
     if ((rc = tc::make_tensor_map_bf16_nd(&tmLB, a.d_label_bias_lp, 3, dw, sw, bw))) return rc;
   }

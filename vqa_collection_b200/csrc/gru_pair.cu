@@ -10,9 +10,15 @@
 //     (three 32-row TMA boxes out of the same gate-interleaved packing) — half the W fill per SM;
 //   * ONE thread of the pair's leader CTA issues tcgen05.mma.cta_group::2 (M = 256, N = 192): each
 //     SM's tensor core reads its own A tile and both B halves, so the B operand reads per SM halve too.
-// Accumulator columns (per CTA, N = 192 ordered as the two B halves):
-//   unit u = 32·hf + uu:  r at 96·hf + uu,  z at 96·hf + 32 + uu,  n_x + W_hn·h at 96·hf + 64 + uu;
-//   n_x alone (second x-part MMA, N = 64) at 192 + u.   Double buffered over steps (2 × 256 columns).
+// Accumulator columns of a tile of U units (4U columns, e.g. 256 for U = 64):
+//   [0,U) W_in·x   [U,2U) r = W_ir·x + W_hr·h   [2U,3U) z   [3U,4U) W_hn·h
+// The x-part MMA writes columns [0,4U): its B rows are the tile's gate rows in the order [n | r | z] followed by U
+// zero rows (a TMA box placed past the end of the packed matrix: out-of-bounds rows arrive as zeros), so it also CLEARS
+// the W_hn·h columns; the h-part MMA then accumulates the gate rows [r | z | n] onto columns [U,4U).  One MMA per
+// k-step and part — the kernel pays for every tcgen05.mma instruction, and the earlier layout (n_x + W_hn·h together,
+// n_x again by a second N = U MMA per x k-step) spent 20 of its 104 MMAs per step on keeping n_x apart.
+// With cta_group::2 CTA c supplies rows [c·N/2, (c+1)·N/2) of the B operand: chunk q = (N/U)·c + i of U/2 rows is
+// rows [half·U/2, +U/2) of gate order[q / 2], half = q % 2 — three (x-part: + one zero) boxes per CTA and stage.
 // Barriers: TMA of both CTAs counts bytes on the LEADER's full barrier (cp.async.bulk.tensor
 // .cta_group::2); tcgen05.commit multicasts the stage release and "accumulator ready" to both CTAs;
 // the epilogue warps of both CTAs release the accumulator on the leader's barrier (mapa + remote arrive).
@@ -49,11 +55,13 @@ template <int UNITS> struct Cfg {
   static constexpr int NACC = TMEM_COLS / ACC_STRIDE;      // accumulators in flight: 2 (64 units) / 4 (32 units)
   static constexpr int HALF_UNITS = UNITS / 2;             // units whose W rows one CTA holds
   static constexpr int UPT = UNITS / (EPI_WARPS / 4);      // units per epilogue thread (16 / 8)
-  static constexpr int W_BYTES = 3 * HALF_UNITS * BK * 2;  // this CTA's half of the W tile (12 KB / 6 KB)
-  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;    // 28 KB / 22 KB
-  static constexpr int STAGES = UNITS == 64 ? 7 : 9;
-  static constexpr int COL_NI = 3 * UNITS;
+  static constexpr int CHUNK_BYTES = HALF_UNITS * BK * 2;  // one box of U/2 gate rows (4 KB / 2 KB)
+  static constexpr int W_BYTES = 4 * CHUNK_BYTES;          // this CTA's half of the widest (x-part, N = 4U) B tile
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;    // 32 KB / 24 KB
+  static constexpr int STAGES = UNITS == 64 ? 7 : 9;         // 224 KB / 216 KB of ring
+  static constexpr int COL_NH = 3 * UNITS;                 // W_hn·h
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + 4 * UNITS * 4;
+  static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
 };
 
 struct Params {
@@ -79,7 +87,8 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmWx,
                 const __grid_constant__ CUtensorMap tmWh, const Params p) {
   using C = Cfg<UNITS>;
-  constexpr int HALF_UNITS = C::HALF_UNITS, UPT = C::UPT, STAGE_BYTES = C::STAGE_BYTES, STAGES = C::STAGES, COL_NI = C::COL_NI;
+  constexpr int HALF_UNITS = C::HALF_UNITS, UPT = C::UPT, STAGE_BYTES = C::STAGE_BYTES, STAGES = C::STAGES, COL_NH = C::COL_NH;
+  constexpr int CHUNK_BYTES = C::CHUNK_BYTES;
   constexpr int ACC_STRIDE = C::ACC_STRIDE, NACC = C::NACC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -126,13 +135,24 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot_ptr;
   griddep_launch();
 
-  // this CTA's half of the pair's W rows: [r | z | n] rows of units [u0 + HALF·crank, u0 + HALF·crank + HALF) — ONE 3-D box
-  // {64 cols, HALF rows, 3 gates} out of the gate-interleaved packing (the packed matrix viewed as [3H/64 gate blocks][64
-  // rows][K]); it lands as three consecutive HALF-row tiles, the layout the MMAs read.  (Three 2-D boxes per stage before:
-  // the producer is bound by TMA instructions per step, not by bytes.)
-  auto load_w = [&](uint32_t sw, const CUtensorMap* map, uint32_t bar, int col) {
-    tma_load_3d_2cta(sw, map, bar, col, (u0 % PACK_UNITS) + (int)crank * HALF_UNITS, (u0 / PACK_UNITS) * 3);
+  // this CTA's half of the B tile: chunks q = n_chunks·crank + i of HALF_UNITS rows, chunk q = rows [half·HALF, +HALF) of
+  // gate order[q / 2] of the tile's units (packed matrix viewed as [3H/64 gate blocks r,z,n][64 rows][K]); x-part: gate
+  // order n, r, z and a fourth, all-zero chunk per CTA pair half (out-of-bounds box); h-part: r, z, n.  The bytes the
+  // stage's barrier expects are the CTA pair's: x_part ? 2·(A + 4 chunks) : 2·(A + 3 chunks).
+  const int gate_blk0 = (u0 / PACK_UNITS) * 3, unit_row0 = u0 % PACK_UNITS, oob_blk = 3 * p.H / PACK_UNITS;
+  auto load_w = [&](uint32_t sw, const CUtensorMap* map, uint32_t bar, int col, bool x_part) {
+    const int n_chunks = x_part ? 4 : 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i >= n_chunks) break;
+      const int q = n_chunks * (int)crank + i;             // 0..7 (x) / 0..5 (h) over the pair
+      const int pos = q >> 1, half = q & 1;
+      const int gate = x_part ? (pos == 0 ? 2 : pos - 1) : pos;          // x: n, r, z, (zeros)   h: r, z, n
+      const int blk = (x_part && pos == 3) ? oob_blk : gate_blk0 + gate;
+      tma_load_3d_2cta(sw + i * CHUNK_BYTES, map, bar, col, unit_row0 + half * HALF_UNITS, blk);
+    }
   };
+  constexpr uint32_t X_STAGE_TX = 2 * (A_BYTES + 4 * CHUNK_BYTES), H_STAGE_TX = 2 * (A_BYTES + 3 * CHUNK_BYTES);
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs; bytes are counted on the leader's full barrier) =====
@@ -144,9 +164,9 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int kb = 0; kb < kb_x; ++kb) {                       // x-part: no dependence on h
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
-          if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+          if (lead) mbar_arrive_expect_tx(full_bar(stage), X_STAGE_TX);
           tma_load_2d_2cta(sa, &tmX, full_bar(stage), t * p.E_pad + kb * BK, m0);
-          load_w(sw, &tmWx, full_bar(stage), kb * BK);
+          load_w(sw, &tmWx, full_bar(stage), kb * BK, true);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (t > 0) {
@@ -154,8 +174,8 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           int pre_stage[W_PREFETCH];
           for (int kb = 0; kb < npre; ++kb) {                     // W_h tiles do not depend on h: start them early
             mbar_wait(empty_bar(stage), phase ^ 1);
-            if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
-            load_w(base + stage * STAGE_BYTES + A_BYTES, &tmWh, full_bar(stage), kb * BK);
+            if (lead) mbar_arrive_expect_tx(full_bar(stage), H_STAGE_TX);
+            load_w(base + stage * STAGE_BYTES + A_BYTES, &tmWh, full_bar(stage), kb * BK, false);
             pre_stage[kb] = stage;
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -171,9 +191,9 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int kb = npre; kb < kb_h; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
-            if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+            if (lead) mbar_arrive_expect_tx(full_bar(stage), H_STAGE_TX);
             tma_load_2d_2cta(sa, tmH, full_bar(stage), hcol + kb * BK, hrow);
-            load_w(sw, &tmWh, full_bar(stage), kb * BK);
+            load_w(sw, &tmWh, full_bar(stage), kb * BK, false);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -183,9 +203,8 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the LEADER CTA drives both tensor cores =====
     if (lane == 0 && lead) {
-      constexpr uint32_t idesc_rzn = make_idesc_bf16(2 * BM, 3 * UNITS);   // M = 256, N = 192 (96)
-      constexpr uint32_t idesc_n = make_idesc_bf16(2 * BM, UNITS);         // M = 256, N = 64 (32): n rows of both halves
-      constexpr uint32_t N_ROW_OFF = (2 * HALF_UNITS * BK * 2) >> 4;       // the n rows of a half tile
+      constexpr uint32_t idesc_x = make_idesc_bf16(2 * BM, 4 * UNITS);     // M = 256, N = 256 (128): [n | r | z | zeros]
+      constexpr uint32_t idesc_h = make_idesc_bf16(2 * BM, 3 * UNITS);     // M = 256, N = 192 (96):  [r | z | n]
       int stage = 0; uint32_t phase = 0;
       uint32_t job = 0;                                  // j = t·RB + b: accumulator j mod NACC, its (j / NACC)-th use
       for (int t = 0; t < p.T; ++t) {
@@ -201,10 +220,8 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
           const uint64_t adesc = make_sw128_kmajor_desc(sa), wdesc = make_sw128_kmajor_desc(sw);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16_2cta(d, adesc + 2 * k, wdesc + 2 * k, idesc_rzn, (kb | k) != 0);                      // [r|z|n_x] x 2 halves
-            umma_bf16_2cta(d + COL_NI, adesc + 2 * k, wdesc + N_ROW_OFF + 2 * k, idesc_n, (kb | k) != 0);   // n_x kept apart
-          }
+          for (int k = 0; k < BK / UMMA_K; ++k)                  // columns [0,4U): the first one also clears W_hn·h
+            umma_bf16_2cta(d, adesc + 2 * k, wdesc + 2 * k, idesc_x, (kb | k) != 0);
           umma_commit_2cta(empty_bar(stage), 0b11);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -215,7 +232,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
             const uint64_t adesc = make_sw128_kmajor_desc(sa), wdesc = make_sw128_kmajor_desc(sw);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_2cta(d, adesc + 2 * k, wdesc + 2 * k, idesc_rzn, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_2cta(d + UNITS, adesc + 2 * k, wdesc + 2 * k, idesc_h, 1u);
             umma_commit_2cta(empty_bar(stage), 0b11);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -229,8 +246,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int uh = (warp - EPI_WARP0) >> 2;          // which 16-unit slice of the 64 units
     const int et = threadIdx.x - EPI_WARP0 * 32;
-    const int ub = uh * UPT;                         // first unit (within the tile) of this thread
-    const int colb = (ub / HALF_UNITS) * (3 * HALF_UNITS) + (ub % HALF_UNITS);   // column of r for unit ub
+    const int ub = uh * UPT;                         // first unit (within the tile) of this thread = its W_in·x column
     float h[RB][UPT];
 #pragma unroll
     for (int b = 0; b < RB; ++b)
@@ -256,17 +272,17 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
       for (int c = 0; c < UPT; c += 8) {
         uint32_t vr[8], vz[8], vni[8], vnh[8];
-        tmem_ld_32x8(trow + colb + c, vr);
-        tmem_ld_32x8(trow + colb + HALF_UNITS + c, vz);
-        tmem_ld_32x8(trow + colb + 2 * HALF_UNITS + c, vnh);
-        tmem_ld_32x8(trow + COL_NI + ub + c, vni);
+        tmem_ld_32x8(trow + UNITS + ub + c, vr);
+        tmem_ld_32x8(trow + 2 * UNITS + ub + c, vz);
+        tmem_ld_32x8(trow + COL_NH + ub + c, vnh);
+        tmem_ld_32x8(trow + ub + c, vni);
         tmem_ld_wait();
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float pr = __uint_as_float(vr[j]) + bias_s[ub + c + j], pz = __uint_as_float(vz[j]) + bias_s[UNITS + ub + c + j];
           const float r = sigmoid_fast(pr), z = sigmoid_fast(pz);
-          const float nh = (__uint_as_float(vnh[j]) - __uint_as_float(vni[j])) + bias_s[3 * UNITS + ub + c + j];
+          const float nh = __uint_as_float(vnh[j]) + bias_s[3 * UNITS + ub + c + j];
           const float pn = __uint_as_float(vni[j]) + bias_s[2 * UNITS + ub + c + j] + r * nh;
           const float n = tanh_fast(pn);
           const float hn = (1.f - z) * n + z * h[b][c + j];
@@ -307,17 +323,17 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
         for (int c = 0; c < UPT; c += 8) {
           uint32_t vr[8], vz[8], vni[8], vnh[8];
-          tmem_ld_32x8(trow + colb + c, vr);
-          tmem_ld_32x8(trow + colb + HALF_UNITS + c, vz);
-          tmem_ld_32x8(trow + colb + 2 * HALF_UNITS + c, vnh);
-          tmem_ld_32x8(trow + COL_NI + ub + c, vni);
+          tmem_ld_32x8(trow + UNITS + ub + c, vr);
+          tmem_ld_32x8(trow + 2 * UNITS + ub + c, vz);
+          tmem_ld_32x8(trow + COL_NH + ub + c, vnh);
+          tmem_ld_32x8(trow + ub + c, vni);
           tmem_ld_wait();
           float gr[8], gz[8], gn[8], ghn[8], hs[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             gr[j] = sigmoid_fast(__uint_as_float(vr[j]) + bias_s[ub + c + j]);
             gz[j] = sigmoid_fast(__uint_as_float(vz[j]) + bias_s[UNITS + ub + c + j]);
-            ghn[j] = (__uint_as_float(vnh[j]) - __uint_as_float(vni[j])) + bias_s[3 * UNITS + ub + c + j];
+            ghn[j] = __uint_as_float(vnh[j]) + bias_s[3 * UNITS + ub + c + j];
             gn[j] = tanh_fast(__uint_as_float(vni[j]) + bias_s[2 * UNITS + ub + c + j] + gr[j] * ghn[j]);
             hs[j] = h[b][c + j];
           }
@@ -398,8 +414,8 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
   CUtensorMap tmWx, tmWh;
   int rc;
   {
-    // packed W [3H, K] viewed as [3H/64 gate blocks][64 rows][K]: box = {64 cols, HALF_UNITS rows, 3 gate blocks}
-    const int box[3] = {tc::BK, HALF_UNITS, 3};
+    // packed W [3H, K] viewed as [3H/64 gate blocks][64 rows][K]: box = {64 cols, HALF_UNITS rows of one gate block}
+    const int box[3] = {tc::BK, HALF_UNITS, 1};
     const long long dx[3] = {E_pad, PACK_UNITS, 3LL * H / PACK_UNITS}, sx[2] = {2LL * E_pad, 2LL * E_pad * PACK_UNITS};
     const long long dh[3] = {H, PACK_UNITS, 3LL * H / PACK_UNITS}, sh[2] = {2LL * H, 2LL * H * PACK_UNITS};
     if ((rc = tc::make_tensor_map_bf16_nd(&tmWx, wx_p, 3, dx, sx, box))) return rc;
