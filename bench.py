@@ -41,11 +41,12 @@ WORKLOAD_NAME = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at B = 1024 from the `ncu --set full` captures committed
 # under profiles/ (bytes, file); scaled by B / 1024 below.  None = no capture of this kernel in this round.
 NCU_TRAFFIC = {
-    "wv": (166.2e6, "profiles/r01e_ncu_wv.md"),
-    "wide": (594.07e6, "profiles/r01e_ncu_wide.md"),
-    "gat": (606.0e6, "profiles/r01e_ncu_gat.md"),
-    "pool": (155.6e6, "profiles/r01f_ncu_pool.md"),
-    "gru": (None, "profiles/r01e_ncu_gru.md (single-CTA variant; the pair kernel cannot run under ncu)"),
+    "wv": (163.7e6, "profiles/r02_ncu_wv.md"),        # 159.47 read + 4.21 written; algorithmic 151.0 + 4.2 + 0.6
+    "wide": (588.8e6, "profiles/r02_ncu_wide.md"),    # 178.8 read + 410.0 written; algorithmic 151 + 25 + 453 (part of Y is still in L2 at kernel end)
+    "gat": (613.3e6, "profiles/r02_ncu_gat.md"),      # 606.3 read + 7.1 written; algorithmic 604 + 4.2
+    "pool": (156.8e6, "profiles/r02_ncu_pool.md"),    # 151.6 read + 5.2 written; algorithmic 151.0 + 4.3
+    "gru": (18.0e6, "profiles/r02_ncu_gru.md (gru_persistent_kernel, the single-CTA variant: ncu cannot launch the "
+                    "cooperative cluster kernel; operands are L2-resident)"),
 }
 
 

@@ -75,6 +75,8 @@ struct Params {
   // training form (train.cu): states time-major, gates saved for the backward pass (f32 [T,Bfull,H] each, chunk offset applied)
   int time_major, Bfull, b0;
   int thread_fences;            // 1 = every epilogue thread fences before the publish barrier (VQA_B200_GRU_FENCE=1)
+  int debug;                    // VQA_B200_GRU_DEBUG bits, timing experiments only (results are wrong): 1 = no MMAs,
+                                // 2 = no TMA loads, 4 = no wait for the other CTAs' h_t, 8 = no gate arithmetic / stores
   float *save_r, *save_z, *save_n, *save_hn, *save_h;   // save_h: slot t = state AFTER step t
 };
 
@@ -158,15 +160,18 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // ===== TMA producer (both CTAs; bytes are counted on the leader's full barrier) =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      const bool noload = (p.debug & 2) != 0;
       for (int t = 0; t < p.T; ++t) {
        for (int b = 0; b < RB; ++b) {
         const int m_blk = m_blk_of(b), m0 = m_blk * BM;
         for (int kb = 0; kb < kb_x; ++kb) {                       // x-part: no dependence on h
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
-          if (lead) mbar_arrive_expect_tx(full_bar(stage), X_STAGE_TX);
-          tma_load_2d_2cta(sa, &tmX, full_bar(stage), t * p.E_pad + kb * BK, m0);
-          load_w(sw, &tmWx, full_bar(stage), kb * BK, true);
+          if (lead) mbar_arrive_expect_tx(full_bar(stage), noload ? 0u : X_STAGE_TX);
+          if (!noload) {
+            tma_load_2d_2cta(sa, &tmX, full_bar(stage), t * p.E_pad + kb * BK, m0);
+            load_w(sw, &tmWx, full_bar(stage), kb * BK, true);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (t > 0) {
@@ -174,26 +179,28 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           int pre_stage[W_PREFETCH];
           for (int kb = 0; kb < npre; ++kb) {                     // W_h tiles do not depend on h: start them early
             mbar_wait(empty_bar(stage), phase ^ 1);
-            if (lead) mbar_arrive_expect_tx(full_bar(stage), H_STAGE_TX);
-            load_w(base + stage * STAGE_BYTES + A_BYTES, &tmWh, full_bar(stage), kb * BK, false);
+            if (lead) mbar_arrive_expect_tx(full_bar(stage), noload ? 0u : H_STAGE_TX);
+            if (!noload) load_w(base + stage * STAGE_BYTES + A_BYTES, &tmWh, full_bar(stage), kb * BK, false);
             pre_stage[kb] = stage;
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           // h_{t-1}[rows of this CTA, :] is published by the tiles_n CTAs that own these rows
           const int target = t * p.tiles_n;
-          while (ld_acquire_gpu(p.counter + m_blk) < target) { }
+          if (!(p.debug & 4)) while (ld_acquire_gpu(p.counter + m_blk) < target) { }
           fence_proxy_async_all();
           const CUtensorMap* tmH = ((t - 1) & 1) ? &tmH1 : &tmH0;
           const int hcol = (p.h_all && !p.time_major) ? (t - 1) * p.H : 0;
           const int hrow = p.time_major ? (t - 1) * p.Bfull + p.b0 + m0 : m0;
           for (int kb = 0; kb < npre; ++kb)
-            tma_load_2d_2cta(base + pre_stage[kb] * STAGE_BYTES, tmH, full_bar(pre_stage[kb]), hcol + kb * BK, hrow);
+            if (!noload) tma_load_2d_2cta(base + pre_stage[kb] * STAGE_BYTES, tmH, full_bar(pre_stage[kb]), hcol + kb * BK, hrow);
           for (int kb = npre; kb < kb_h; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
             const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
-            if (lead) mbar_arrive_expect_tx(full_bar(stage), H_STAGE_TX);
-            tma_load_2d_2cta(sa, tmH, full_bar(stage), hcol + kb * BK, hrow);
-            load_w(sw, &tmWh, full_bar(stage), kb * BK, false);
+            if (lead) mbar_arrive_expect_tx(full_bar(stage), noload ? 0u : H_STAGE_TX);
+            if (!noload) {
+              tma_load_2d_2cta(sa, tmH, full_bar(stage), hcol + kb * BK, hrow);
+              load_w(sw, &tmWh, full_bar(stage), kb * BK, false);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -221,7 +228,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint64_t adesc = make_sw128_kmajor_desc(sa), wdesc = make_sw128_kmajor_desc(sw);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)                  // columns [0,4U): the first one also clears W_hn·h
-            umma_bf16_2cta(d, adesc + 2 * k, wdesc + 2 * k, idesc_x, (kb | k) != 0);
+            if (!(p.debug & 1)) umma_bf16_2cta(d, adesc + 2 * k, wdesc + 2 * k, idesc_x, (kb | k) != 0);
           umma_commit_2cta(empty_bar(stage), 0b11);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -232,7 +239,8 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
             const uint64_t adesc = make_sw128_kmajor_desc(sa), wdesc = make_sw128_kmajor_desc(sw);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16_2cta(d + UNITS, adesc + 2 * k, wdesc + 2 * k, idesc_h, 1u);
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              if (!(p.debug & 1)) umma_bf16_2cta(d + UNITS, adesc + 2 * k, wdesc + 2 * k, idesc_h, 1u);
             umma_commit_2cta(empty_bar(stage), 0b11);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -271,6 +279,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const uint32_t trow = tmem_base + acc * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 #pragma unroll
       for (int c = 0; c < UPT; c += 8) {
+        if (p.debug & 8) break;
         uint32_t vr[8], vz[8], vni[8], vnh[8];
         tmem_ld_32x8(trow + UNITS + ub + c, vr);
         tmem_ld_32x8(trow + 2 * UNITS + ub + c, vz);
@@ -453,6 +462,9 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
     static int fences = -1;
     if (fences < 0) { const char* e = getenv("VQA_B200_GRU_FENCE"); fences = (e && e[0] == '1') ? 1 : 0; }
     p.thread_fences = fences;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("VQA_B200_GRU_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
     const size_t so = (size_t)b0 * H;
     p.save_r = tmajor ? save->R + so : nullptr; p.save_z = tmajor ? save->Z + so : nullptr;
     p.save_n = tmajor ? save->N + so : nullptr; p.save_hn = tmajor ? save->HN + so : nullptr;
