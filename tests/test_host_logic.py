@@ -366,7 +366,7 @@ import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
 from oracle import vqa_oracle as O
 from vqa_collection_b200.parallel import shard_batch, FlatGradients, average_gradients_
-from vqa_collection_b200.training import param_names
+from vqa_collection_b200.training import param_names, GRU_PARAMS
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 cfg = O.SMALL
@@ -378,7 +378,13 @@ names = param_names()
 fg = FlatGradients([tuple(W[n].shape) for n in names], "cpu")
 for v, n in zip(fg.views, names):
     v.copy_(local[n])
-average_gradients_(fg.flat)                         # the exchange step (SUM + divide under gloo, AVG under NCCL)
+# the exchange step (SUM + divide under gloo, AVG under NCCL) in the TWO buckets of training.py: the weight-normed layers
+# (final before the BPTT) and then GRU + embedding — contiguous ranges of the flat buffer that together cover it
+head_off = fg.offset_of(len(GRU_PARAMS))
+assert 0 < head_off < fg.flat.numel() and fg.offset_of(len(names)) == fg.flat.numel()
+assert fg.views[len(GRU_PARAMS)].data_ptr() == fg.flat[head_off:].data_ptr()
+average_gradients_(fg.flat[head_off:])
+average_gradients_(fg.flat[:head_off])
 gmax = max(float(full[n].abs().max()) for n in names)
 for v, n in zip(fg.views, names):
     ref = full[n]
