@@ -74,3 +74,33 @@ def test_two_gpu_sharded_forward_and_gradient_allreduce(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == n
+
+
+def test_model_on_a_device_other_than_the_current_one():
+    """the reference's --device / --decoder_device (main.py:88, wrapper.py:148-150): a model built on cuda:1 while the
+    current device is 0 must launch on cuda:1's stream with cuda:1's kernel attributes — same answers as on cuda:0"""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    sys.path.insert(0, ROOT)
+    from oracle import vqa_oracle as O
+    from vqa_collection_b200.engine import VQAEngine
+    from vqa_collection_b200 import ops
+    torch.cuda.set_device(0)
+    for relation, B in ((False, 600), (True, 130)):
+        cfg = O.FULL_REGAT if relation else O.FULL
+        W = O.make_weights(cfg, 1111)
+        batch = O.make_batch(cfg, B, 77)
+        outs = []
+        for dev in ("cuda:0", "cuda:1"):
+            eng = VQAEngine(W, relation=relation, precision="bf16", device=dev)
+            kw = dict(labels=batch["graph"].to(torch.uint8).to(dev)) if relation else {}
+            out = eng.forward(batch["img"].to(dev), batch["q"].to(dev), **kw)
+            assert out["logits"].device == torch.device(dev)
+            outs.append((out["logits"].cpu(), out["label"].cpu()))
+        assert torch.cuda.current_device() == 0
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    # tensor-level wrappers follow their tensors' device too
+    boxes = torch.from_numpy(O.make_boxes(8, 36, 1)).to("cuda:1")
+    lab1 = ops.relation_labels(boxes, 640, 480)
+    assert lab1.device == torch.device("cuda:1")
+    assert torch.equal(lab1.cpu(), ops.relation_labels(boxes.to("cuda:0"), 640, 480).cpu())
