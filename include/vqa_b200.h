@@ -182,6 +182,11 @@ typedef struct {
   void* d_workspace;   size_t workspace_bytes;
   float* d_h_last;     void* d_h_last_lp;
   const void* d_x;     void* d_out_all;
+  /* optional token table (fp16 [ntoken_rows, 3H], gate order r|z|n): row v = W_ih·emb[v] + (b_ir+b_hr | b_iz+b_hz | b_in),
+   * the input half of the gates, which depends on the token only (modules.py:153 evaluates it per (sample, step)).
+   * With the packed weights and tokens (no d_x / d_out_all) it selects the token-table form of the fused kernel: no
+   * embedding gather, no x-part GEMM — the kernel reads row tokens[b,t] of the table instead.  NULL = off.       */
+  const void* d_gi_table;
 } vqa_gru_args;
 
 int vqa_gru_last_state(const vqa_gru_args* args, void* stream);
@@ -455,6 +460,8 @@ typedef struct {
    * precedence over `overlap`.  Falls back to the serial order under a profiler / CUDA_LAUNCH_BLOCKING (kernels of the
    * two streams must be able to run at the same time). */
   int gat_chase_sms;
+  /* question encoder, token-table form: see vqa_gru_args.d_gi_table (NULL = gather + x-part GEMM) */
+  const void* d_gi_table;
 } vqa_forward_args;
 
 size_t vqa_forward_workspace_bytes(const vqa_forward_args* args);

@@ -13,11 +13,12 @@ g = torch.Generator().manual_seed(0)
 packed = (P["wx_packed"], P["wh_packed"], P["bias_packed"])
 for T in (1, 2, 14):
     q = torch.randint(0, cfg.ntoken, (B, T), generator=g).to(dev)
-    f = lambda: ops.gru_last_state(q, P["emb"], P["w_ih"], P["b_ih"], P["w_hh"], P["b_hh"], packed=packed)
+    tab = P.get("gi_table") if os.environ.get("TABLE", "1") != "0" else None
+    f = lambda: ops.gru_last_state(q, P["emb"], P["w_ih"], P["b_ih"], P["w_hh"], P["b_hh"], packed=packed, gi_table=tab)
     for _ in range(3): f()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(30): f()
     e1.record(); torch.cuda.synchronize()
-    print(f"debug={os.environ.get('VQA_B200_GRU_DEBUG','0')} B={B} T={T}: {e0.elapsed_time(e1)/30*1e3:.1f} us", flush=True)
+    print(f"table={tab is not None} debug={os.environ.get('VQA_B200_GRU_DEBUG','0')} B={B} T={T}: {e0.elapsed_time(e1)/30*1e3:.1f} us", flush=True)

@@ -224,6 +224,49 @@ def test_gru_persistent_shapes(ops, B, T):
     assert relerr(h[idx.cuda()], want) < 1e-2
 
 
+@pytest.mark.parametrize("B,T", [(1, 1), (5, 2), (130, 3), (1024, 14), (1300, 14)])
+def test_gru_token_table(ops, B, T):
+    """token-table form of the fused GRU (vqa_gru_args.d_gi_table): no gather, no x-part GEMM; against the oracle, against the
+    x-part form, deterministic; every tile choice (one / two row blocks per CTA pair, 32 / 64 units)"""
+    from vqa_collection_b200.engine import prepare_weights
+    cfg = O.FULL
+    W = O.make_weights(cfg, 1111)
+    P = prepare_weights(W, torch.bfloat16, "cuda", False)
+    assert P["gi_table"].dtype == torch.float16 and P["gi_table"].shape == (P["emb"].shape[0], 3 * cfg.hidden_dim)
+    g = torch.Generator().manual_seed(B + T)
+    q = torch.randint(0, cfg.ntoken + 1, (B, T), generator=g)           # includes the padding row
+    packed = (P["wx_packed"], P["wh_packed"], P["bias_packed"])
+    args = (q.cuda(), P["emb"], P["w_ih"], P["b_ih"], P["w_hh"], P["b_hh"])
+    h_x = ops.gru_last_state(*args, packed=packed)
+    h, h_lp = ops.gru_last_state(*args, packed=packed, gi_table=P["gi_table"], want_lp=True)
+    idx = torch.arange(0, B, max(1, B // 64))
+    with torch.no_grad():
+        want = O.question_embedding(q[idx], W)
+    e_tab, e_x = relerr(h[idx.cuda()], want), relerr(h_x[idx.cuda()], want)
+    print(f"token table: err {e_tab:.2e} (x-part form {e_x:.2e})")
+    assert e_tab < 1e-2
+    assert relerr(h_lp[idx.cuda()], want) < 1e-2
+    assert relerr(h, h_x) < 1e-2
+    assert torch.equal(h, ops.gru_last_state(*args, packed=packed, gi_table=P["gi_table"]))
+    for forced in ("64x1", "32x1", "64x2", "32x2"):
+        import subprocess, sys, os
+        code = (
+            "import torch, sys; sys.path.insert(0, '.');\n"
+            "from oracle import vqa_oracle as O; from vqa_collection_b200 import ops; from vqa_collection_b200.engine import prepare_weights\n"
+            f"W = O.make_weights(O.FULL, 1111); P = prepare_weights(W, torch.bfloat16, 'cuda', False)\n"
+            f"g = torch.Generator().manual_seed({B + T}); q = torch.randint(0, O.FULL.ntoken + 1, ({B}, {T}), generator=g)\n"
+            "h = ops.gru_last_state(q.cuda(), P['emb'], P['w_ih'], P['b_ih'], P['w_hh'], P['b_hh'], packed=(P['wx_packed'], P['wh_packed'], P['bias_packed']), gi_table=P['gi_table'])\n"
+            "torch.save(h.cpu(), sys.argv[1])\n")
+        if B != 1024:
+            continue                                                    # the forced tiles: at the full batch only
+        out = f"/tmp/gru_tab_{forced}_{B}.pt"
+        env = dict(os.environ, VQA_B200_GRU_CFG=forced)
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        hf = torch.load(out)
+        assert relerr(hf[idx], want) < 1e-2, forced
+        assert relerr(hf, h.cpu()) < 2e-3, forced                      # same arithmetic, other tile shapes
+
+
 # ---------------------------------------------------------------------------- fused answer selection
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,N,K", [(1024, 3129, 2048), (37, 3129, 256), (300, 200, 128), (5, 64, 64)])

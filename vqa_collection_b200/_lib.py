@@ -49,6 +49,7 @@ class GruArgs(C.Structure):
         ("d_workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("d_h_last", c_void_p), ("d_h_last_lp", c_void_p),
         ("d_x", c_void_p), ("d_out_all", c_void_p),
+        ("d_gi_table", c_void_p),
     ]
 
 
@@ -90,6 +91,7 @@ class ForwardArgs(C.Structure):
         ("d_logits", c_void_p), ("d_label", c_void_p), ("d_att", c_void_p), ("d_q", c_void_p),
         ("d_v", c_void_p), ("d_alpha", c_void_p), ("d_labels_out", c_void_p),
         ("overlap", c_int), ("side_sms", c_int), ("side_tile_permille", c_int), ("gat_chase_sms", c_int),
+        ("d_gi_table", c_void_p),
     ]
 
 

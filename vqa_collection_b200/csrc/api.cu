@@ -76,7 +76,7 @@ int updown_train_step(const vqa_train_args&, cudaStream_t);
 int gru_persistent(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
                    void*, cudaStream_t);
 int gru_pair(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
-             void*, const GruTrainSave*, int sm_limit, cudaStream_t);
+             void*, const GruTrainSave*, int sm_limit, const GruTokenTable*, cudaStream_t);
 
 bool pdl_enabled() {
   static int v = -1;
@@ -134,6 +134,21 @@ static GruWs carve_gru(void* base, int B, int T, int H, int E_pad, int dtype) {
   return w;
 }
 
+// CTA pairs (tcgen05 cta_group::2, gru_pair.cu: 138 vs 144 us at B=1024, T=14) when the device can hold the pairs,
+// else one CTA per tile; VQA_B200_GRU_PAIR=0 forces the single-CTA kernel.
+// Nsight Compute cannot launch a cooperative CLUSTER kernel ("LaunchFailed" under the profiler and the target process is
+// torn down): when its injection environment is present the single-CTA kernel runs instead, so `ncu python bench.py` works
+// (VQA_B200_GRU_PAIR=1 overrides).
+static bool gru_pair_enabled() {
+  static int pair = -1;
+  if (pair < 0) {
+    const char* e = getenv("VQA_B200_GRU_PAIR");
+    if (e) pair = (e[0] == '0') ? 0 : 1;
+    else pair = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ? 0 : 1;
+  }
+  return pair != 0;
+}
+
 // sm_limit > 0: the persistent kernel may use at most that many SMs (vqa_forward's overlap mode)
 static int gru_last_state(const vqa_gru_args& a, cudaStream_t s, int sm_limit = 0) {
   VQA_REQUIRE(((a.d_tokens && a.d_emb) || a.d_x) && a.d_w_ih && a.d_w_hh && a.d_b_ih && a.d_b_hh &&
@@ -150,28 +165,28 @@ static int gru_last_state(const vqa_gru_args& a, cudaStream_t s, int sm_limit = 
   // there is one, else by a memset
   void* tail = (char*)a.d_workspace + need.bytes;
   const size_t tail_bytes = (a.workspace_bytes - need.bytes) / 16 * 16;
+  const bool fused_ok = a.dtype == VQA_BF16 && a.d_wx_packed && a.d_wh_packed && a.d_bias_packed && !force_simt() &&
+                        a.H % 64 == 0 && a.E_pad % 64 == 0;
+  // token-table form (d_gi_table): no gather, no x-part; pair kernel only (VQA_B200_GRU_TABLE=0 ignores the table)
+  static int use_table = -1;
+  if (use_table < 0) { const char* e = getenv("VQA_B200_GRU_TABLE"); use_table = (e && e[0] == '0') ? 0 : 1; }
+  if (use_table && fused_ok && a.d_gi_table && a.d_tokens && !a.d_x && !a.d_out_all && gru_pair_enabled()) {
+    // the counter block is the last 256 bytes of the GRU's own workspace: one memset clears it and the caller's tail
+    const GruTokenTable tab{a.d_gi_table, a.d_tokens, a.ntoken_rows, tail_bytes};
+    rc = gru_pair(nullptr, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
+                  a.d_h_last, a.d_h_last_lp, nullptr, nullptr, sm_limit, &tab, s);
+    if (rc != VQA_ERR_UNSUPPORTED) return rc;
+  }
   if (X && tail_bytes) VQA_CUDA_CHECK(cudaMemsetAsync(tail, 0, tail_bytes, s));
   if (!X) {
     if ((rc = embedding_gather(a.d_tokens, a.B * a.T, a.E_pad, a.ntoken_rows, a.dtype, a.d_emb, w.X, s, tail, tail_bytes)))
       return rc;
     X = w.X;
   }
-  if (a.dtype == VQA_BF16 && a.d_wx_packed && a.d_wh_packed && a.d_bias_packed && !force_simt() && a.H % 64 == 0 &&
-      a.E_pad % 64 == 0) {
-    // CTA pairs (tcgen05 cta_group::2, gru_pair.cu: 138 vs 144 us at B=1024, T=14) when the device can hold the pairs,
-    // else one CTA per tile; VQA_B200_GRU_PAIR=0 forces the single-CTA kernel
-    // Nsight Compute cannot launch a cooperative CLUSTER kernel ("LaunchFailed" under the profiler and the target process is
-    // torn down): when its injection environment is present the single-CTA kernel runs instead, so `ncu python bench.py` works
-    // (VQA_B200_GRU_PAIR=1 overrides).
-    static int pair = -1;
-    if (pair < 0) {
-      const char* e = getenv("VQA_B200_GRU_PAIR");
-      if (e) pair = (e[0] == '0') ? 0 : 1;
-      else pair = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ? 0 : 1;
-    }
-    if (pair) {
+  if (fused_ok) {
+    if (gru_pair_enabled()) {
       rc = gru_pair(X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
-                    a.d_h_last, a.d_h_last_lp, a.d_out_all, nullptr, sm_limit, s);
+                    a.d_h_last, a.d_h_last_lp, a.d_out_all, nullptr, sm_limit, nullptr, s);
       if (rc != VQA_ERR_UNSUPPORTED) return rc;
     }
     return gru_persistent(X, a.B, a.T, a.H, a.E_pad, a.d_wx_packed, a.d_wh_packed, a.d_bias_packed, w.h_op, w.counter,
@@ -682,7 +697,7 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
   g.dtype = a.dtype; g.d_emb = a.d_emb; g.d_w_ih = a.d_w_ih; g.d_b_ih = a.d_b_ih; g.d_w_hh = a.d_w_hh;
   g.d_b_hh = a.d_b_hh; g.d_wx_packed = a.d_wx_packed; g.d_wh_packed = a.d_wh_packed; g.d_bias_packed = a.d_bias_packed;
   g.d_workspace = w.gru; g.workspace_bytes = w.gru_bytes + w.amax_bytes;     // the tail (w.amax) comes back zeroed
-  g.d_h_last = w.h; g.d_h_last_lp = w.h_lp;
+  g.d_h_last = w.h; g.d_h_last_lp = w.h_lp; g.d_gi_table = a.d_gi_table;
   if ((rc = gru_last_state(g, sq, side_sms))) return rc;
   // 2. [W_q ; q_net] (attention.py:71, encoder.py:169): qq = ReLU(h Wqqᵀ s + b) f32 [B,2H]
   vqa_linear_args l{};

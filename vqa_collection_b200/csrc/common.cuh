@@ -141,6 +141,9 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---- internal launchers shared between api.cu and the kernels --------------
+// token-table form of the question encoder (gru_pair.cu): gi_table fp16 [ntoken_rows, 3H]; zero_after_counter = bytes
+// behind the GRU's 256-byte counter block that the call clears together with the counters
+struct GruTokenTable { const void* gi_table; const int64_t* tokens; int ntoken_rows; size_t zero_after_counter; };
 struct GruTrainSave { float *R, *Z, *N, *HN, *Hs; };      // f32 [T,B,H] each; Hs slot t = state after step t
 int linear_simt(const vqa_linear_args& a, cudaStream_t s);
 int linear_tc(const vqa_linear_args& a, cudaStream_t s);

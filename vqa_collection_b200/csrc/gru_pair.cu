@@ -30,7 +30,16 @@
 // 0 waits for its neighbours' h_t, the tensor core runs block 1.  Same step latency, HALF the SMs — the
 // other half of the device is free for question-independent work (the wide ReGAT projection / the W_v
 // projection run there at the same time, api.cu `overlap`).
+//
+// TOKEN-TABLE FORM (TABLE = true; question encoder of the forward path): the input half of the gates depends on the
+// token only, gi(v) = W_ih·emb[v] + b — a [vocabulary, 3H] table that engine.prepare_weights builds once per weight
+// version (fp16, r/z/n biases folded in).  The x-part (embedding gather kernel, 24 % of the MMAs, 25 % of the operand
+// bytes a CTA pulls out of L2 every step) disappears: the epilogue threads, who own the accumulator rows anyway, WRITE
+// gi[token(row, t)] (and b_hn) into the accumulator of a later job with tcgen05.st while the tensor core works on the
+// other accumulator — after h_t has been published, so the table reads stay out of the step-to-step chain — and the
+// h-part MMAs accumulate on top.  "accumulator drained" (tempty) then also means "re-initialised".
 #include <stdlib.h>
+#include <cuda_fp16.h>
 
 #include "tc_common.cuh"
 
@@ -78,12 +87,25 @@ struct Params {
   int debug;                    // VQA_B200_GRU_DEBUG bits, timing experiments only (results are wrong): 1 = no MMAs,
                                 // 2 = no TMA loads, 4 = no wait for the other CTAs' h_t, 8 = no gate arithmetic / stores
   float *save_r, *save_z, *save_n, *save_hn, *save_h;   // save_h: slot t = state AFTER step t
+  // token-table form: gi_table fp16 [ntoken_rows, 3H] (gate order r|z|n, biases b_ir+b_hr | b_iz+b_hz | b_in folded in)
+  const __half* gi_table;
+  const int64_t* tokens;        // [B,T]
+  int ntoken_rows;
 };
+
+__device__ __forceinline__ void half8_to_f32(const uint4& v, uint32_t (&o)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    o[2 * i] = __float_as_uint(f.x); o[2 * i + 1] = __float_as_uint(f.y);
+  }
+}
 
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
-template <int UNITS, int RB>
+template <int UNITS, int RB, bool TABLE>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH0,
                 const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmWx,
@@ -164,7 +186,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int t = 0; t < p.T; ++t) {
        for (int b = 0; b < RB; ++b) {
         const int m_blk = m_blk_of(b), m0 = m_blk * BM;
-        for (int kb = 0; kb < kb_x; ++kb) {                       // x-part: no dependence on h
+        for (int kb = 0; kb < (TABLE ? 0 : kb_x); ++kb) {         // x-part: no dependence on h
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
           if (lead) mbar_arrive_expect_tx(full_bar(stage), noload ? 0u : X_STAGE_TX);
@@ -218,10 +240,11 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
        for (int b = 0; b < RB; ++b, ++job) {
         const uint32_t acc = job % NACC;
         const uint32_t acc_phase = (job / NACC) & 1u;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        // TABLE: every use of an accumulator, the first one too, waits for the epilogue threads' initialisation
+        mbar_wait(tempty_bar(acc), TABLE ? acc_phase : (acc_phase ^ 1));
         tcgen05_fence_after();
         const uint32_t d = tmem_base + acc * ACC_STRIDE;
-        for (int kb = 0; kb < kb_x; ++kb) {
+        for (int kb = 0; kb < (TABLE ? 0 : kb_x); ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = base + stage * STAGE_BYTES, sw = sa + A_BYTES;
@@ -260,6 +283,41 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     for (int b = 0; b < RB; ++b)
 #pragma unroll
       for (int j = 0; j < UPT; ++j) h[b][j] = 0.f;
+    // bias of gate row i of the tile; the token-table form has them in the accumulator already
+    auto bs = [&](int i) { return TABLE ? 0.f : bias_s[i]; };
+    // TABLE: write gi[token(row, step)] + biases and b_hn into the accumulator of job jn (step jn / RB, block jn % RB)
+    const uint32_t total_jobs = (uint32_t)p.T * RB;
+    auto init_acc = [&](uint32_t jn) {
+      const int tn = (int)(jn / RB), bn = (int)(jn % RB);
+      const int rown = m_blk_of(bn) * BM + q * 32 + lane;
+      const uint32_t tr = tmem_base + (jn % NACC) * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+      const bool ok = rown < p.B;
+      long long tok = ok ? (long long)p.tokens[(size_t)rown * p.T + tn] : 0;
+      tok = tok < 0 ? 0 : (tok >= p.ntoken_rows ? p.ntoken_rows - 1 : tok);
+      const __half* g = p.gi_table + (size_t)tok * 3 * p.H + u0 + ub;
+#pragma unroll
+      for (int c = 0; c < UPT; c += 8) {
+        const uint4 gr = __ldg(reinterpret_cast<const uint4*>(g + c));
+        const uint4 gz = __ldg(reinterpret_cast<const uint4*>(g + p.H + c));
+        const uint4 gn = __ldg(reinterpret_cast<const uint4*>(g + 2 * p.H + c));
+        uint32_t v[8];
+        half8_to_f32(gn, v); tmem_st_32x8(tr + ub + c, v);
+        half8_to_f32(gr, v); tmem_st_32x8(tr + UNITS + ub + c, v);
+        half8_to_f32(gz, v); tmem_st_32x8(tr + 2 * UNITS + ub + c, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(bias_s[3 * UNITS + ub + c + j]);
+        tmem_st_32x8(tr + COL_NH + ub + c, v);
+      }
+      tmem_st_wait();
+    };
+    if (TABLE) {
+      for (uint32_t jn = 0; jn < (uint32_t)NACC && jn < total_jobs; ++jn) {
+        init_acc(jn);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(jn), 0);
+      }
+    }
     uint32_t job = 0;
     for (int t = 0; t < p.T; ++t) {
       const bool last = (t == p.T - 1);
@@ -289,10 +347,10 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float pr = __uint_as_float(vr[j]) + bias_s[ub + c + j], pz = __uint_as_float(vz[j]) + bias_s[UNITS + ub + c + j];
+          const float pr = __uint_as_float(vr[j]) + bs(ub + c + j), pz = __uint_as_float(vz[j]) + bs(UNITS + ub + c + j);
           const float r = sigmoid_fast(pr), z = sigmoid_fast(pz);
-          const float nh = __uint_as_float(vnh[j]) + bias_s[3 * UNITS + ub + c + j];
-          const float pn = __uint_as_float(vni[j]) + bias_s[2 * UNITS + ub + c + j] + r * nh;
+          const float nh = __uint_as_float(vnh[j]) + bs(3 * UNITS + ub + c + j);
+          const float pn = __uint_as_float(vni[j]) + bs(2 * UNITS + ub + c + j) + r * nh;
           const float n = tanh_fast(pn);
           const float hn = (1.f - z) * n + z * h[b][c + j];
           h[b][c + j] = hn;
@@ -305,8 +363,8 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           *reinterpret_cast<uint4*>(hdst + (size_t)row * h_ld + u0 + ub + c) = w0;
         }
       }
-      const bool saving = p.save_r != nullptr;
-      if (!saving) {
+      const bool saving = !TABLE && p.save_r != nullptr;
+      if (!saving && !TABLE) {
         // accumulator buffer drained: one arrive per warp on the LEADER's barrier (2 CTAs x 16 warps)
         tcgen05_fence_before();
         __syncwarp();
@@ -323,6 +381,14 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           fence_proxy_async_all();
           red_release_gpu_add(p.counter + m_blk, 1);
         }
+      }
+      if (TABLE) {
+        // h_t is on its way to the other CTAs: now (off the chain) prepare this accumulator for its next job and hand it
+        // back to the MMA thread
+        if (job + NACC < total_jobs) init_acc(job + NACC);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
       }
       if (saving) {
         // Training form: what the backward pass needs (train.cu) is written AFTER h_t has been published, so the
@@ -383,14 +449,14 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // after step t) and the gates r, z, n, W_hn·h + b_hn and the f32 states are stored per step for the backward pass.  Returns VQA_ERR_UNSUPPORTED (without setting the error text as a
 // failure of the call) when the pair launch is not possible; the caller then uses the single-CTA kernel.
 // sm_limit > 0: use at most that many SMs (the caller runs something else on the rest at the same time).
-template <int UNITS, int RB>
+template <int UNITS, int RB, bool TABLE>
 static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void* wx_p, const void* wh_p,
                       const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
-                      const GruTrainSave* save, int sm_limit, cudaStream_t s) {
+                      const GruTrainSave* save, int sm_limit, const GruTokenTable* tab, cudaStream_t s) {
   using namespace grup;
   using C = Cfg<UNITS>;
   constexpr int HALF_UNITS = C::HALF_UNITS, SMEM_BYTES = C::SMEM_BYTES;
-  auto kernel = gru_pair_kernel<UNITS, RB>;
+  auto kernel = gru_pair_kernel<UNITS, RB, TABLE>;
   if (H % PACK_UNITS != 0 || E_pad % tc::BK != 0) return VQA_ERR_UNSUPPORTED;
   const int tiles_n = H / UNITS;
   const int dev = current_device();
@@ -427,8 +493,9 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
     const int box[3] = {tc::BK, HALF_UNITS, 1};
     const long long dx[3] = {E_pad, PACK_UNITS, 3LL * H / PACK_UNITS}, sx[2] = {2LL * E_pad, 2LL * E_pad * PACK_UNITS};
     const long long dh[3] = {H, PACK_UNITS, 3LL * H / PACK_UNITS}, sh[2] = {2LL * H, 2LL * H * PACK_UNITS};
-    if ((rc = tc::make_tensor_map_bf16_nd(&tmWx, wx_p, 3, dx, sx, box))) return rc;
     if ((rc = tc::make_tensor_map_bf16_nd(&tmWh, wh_p, 3, dh, sh, box))) return rc;
+    if (TABLE) tmWx = tmWh;                            // never used
+    else if ((rc = tc::make_tensor_map_bf16_nd(&tmWx, wx_p, 3, dx, sx, box))) return rc;
   }
   for (int b0 = 0; b0 < B; b0 += max_groups * rows_per_group) {
     const int Bc = (B - b0 < max_groups * rows_per_group) ? B - b0 : max_groups * rows_per_group;
@@ -438,7 +505,7 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
     __nv_bfloat16* h0 = (__nv_bfloat16*)h_op + (size_t)b0 * H;
     __nv_bfloat16* h1 = (__nv_bfloat16*)h_op + (size_t)B * H + (size_t)b0 * H;
     CUtensorMap tmX, tmH0, tmH1;
-    if ((rc = tc::make_tensor_map_bf16(&tmX, Xc, Bc, (long long)T * E_pad, (long long)T * E_pad, tc::BM))) return rc;
+    if (!TABLE && (rc = tc::make_tensor_map_bf16(&tmX, Xc, Bc, (long long)T * E_pad, (long long)T * E_pad, tc::BM))) return rc;
     const bool tmajor = save != nullptr;
     __nv_bfloat16* hall = h_all ? (__nv_bfloat16*)h_all + (tmajor ? (size_t)b0 * H : (size_t)b0 * T * H) : nullptr;
     if (hall && tmajor) {                               // [T*B rows, H]: step t reads rows (t-1)*B + b0 + m0 ..
@@ -451,7 +518,11 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
       if ((rc = tc::make_tensor_map_bf16(&tmH0, h0, Bc, H, H, tc::BM))) return rc;
       if ((rc = tc::make_tensor_map_bf16(&tmH1, h1, Bc, H, H, tc::BM))) return rc;
     }
+    if (TABLE) tmX = tmH0;                             // never used
     Params p;
+    p.gi_table = TABLE ? (const __half*)tab->gi_table : nullptr;
+    p.tokens = TABLE ? tab->tokens + (size_t)b0 * T : nullptr;
+    p.ntoken_rows = TABLE ? tab->ntoken_rows : 0;
     p.B = Bc; p.T = T; p.H = H; p.E_pad = E_pad; p.tiles_n = tiles_n; p.num_ctas = 2 * groups * tiles_n;
     p.bias = bias_p; p.h_op[0] = h0; p.h_op[1] = h1;
     p.h_last = h_last ? h_last + (size_t)b0 * H : nullptr;
@@ -470,7 +541,10 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
     p.save_n = tmajor ? save->N + so : nullptr; p.save_hn = tmajor ? save->HN + so : nullptr;
     p.save_h = tmajor ? save->Hs + so : nullptr;
     if (tiles_m > 64) return fail(VQA_ERR_INVALID, "gru_pair: %d row blocks per launch exceed the counter block", tiles_m);
-    VQA_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(int) * tiles_m, s));
+    // the counters; the first launch of a token-table call also clears what the caller parked right behind the 256-byte
+    // counter block (the gather kernel that used to do it is gone)
+    const size_t zero_bytes = (TABLE && b0 == 0 && tab->zero_after_counter) ? 256 + tab->zero_after_counter : sizeof(int) * tiles_m;
+    VQA_CUDA_CHECK(cudaMemsetAsync(counter, 0, zero_bytes, s));
     void* args[] = {(void*)&tmX, (void*)&tmH0, (void*)&tmH1, (void*)&tmWx, (void*)&tmWh, (void*)&p};
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(p.num_ctas); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
@@ -490,7 +564,8 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
 // time) and the batch has at least two 256-row blocks.  VQA_B200_GRU_CFG = "64x1" | "32x1" | "64x2" | "32x2" forces one.
 int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, const void* wh_p,
              const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
-             const GruTrainSave* save, int sm_limit, cudaStream_t s) {
+             const GruTrainSave* save, int sm_limit, const GruTokenTable* tab, cudaStream_t s) {
+  if (tab && (save || h_all || !tab->gi_table || !tab->tokens)) return fail(VQA_ERR_INVALID, "gru_pair: the token-table form has no sequence / training variant");
   static int forced = -1;                            // 0 = automatic, else 10 * units + rb
   if (forced < 0) {
     forced = 0;
@@ -514,7 +589,8 @@ int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, co
     else if (!save && row_pairs >= 2 && ctas(64, 2) <= budget) cfg = 642;   // half the SMs: two interleaved row blocks
     else cfg = 641;                                           // several launches
   }
-#define VQA_GRU_CALL(U, R) gru_pair_t<U, R>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, sm_limit, s)
+#define VQA_GRU_CALL(U, R) (tab ? gru_pair_t<U, R, true>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, sm_limit, tab, s) \
+                                : gru_pair_t<U, R, false>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, sm_limit, tab, s))
   switch (cfg) {
     case 321: return VQA_GRU_CALL(32, 1);
     case 322: return VQA_GRU_CALL(32, 2);

@@ -23,7 +23,7 @@
 namespace vqa {
 
 int gru_pair(const void*, int, int, int, int, const void*, const void*, const float*, void*, int*, float*, void*,
-             void*, const GruTrainSave*, int sm_limit, cudaStream_t);
+             void*, const GruTrainSave*, int sm_limit, const GruTokenTable*, cudaStream_t);
 
 int attention_pool(const float*, int, float, const void*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
@@ -575,7 +575,7 @@ static int train_step_t(const vqa_train_args& a, const TrainWs& w, cudaStream_t 
     VQA_LAUNCH_CHECK();
     const GruTrainSave save{w.R, w.Z, w.N, w.HN, w.Hs + BH};
     gru_rc = gru_pair(w.X, B, Tn, H, Ep, w.wx_packed, w.wh_packed, w.bias_packed, nullptr, w.gru_counter, nullptr, nullptr,
-                      (T*)w.Hlp + BH, &save, 0, s);
+                      (T*)w.Hlp + BH, &save, 0, nullptr, s);
     if (gru_rc != VQA_OK && gru_rc != VQA_ERR_UNSUPPORTED) return gru_rc;
   }
   if (gru_rc == VQA_ERR_UNSUPPORTED) {

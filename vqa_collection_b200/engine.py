@@ -85,6 +85,26 @@ def pack_gru(w_ih, w_hh, b_ih, b_hh, units: int = 64):
     return w_ih[perm].contiguous(), w_hh[perm].contiguous(), bias.float().contiguous()
 
 
+GI_TABLE_MAX_BYTES = 1 << 30          # vocabulary x 3H fp16 entries; beyond this the x-part GEMM stays
+
+
+def gru_token_table(emb, w_ih, b_ih, b_hh, device):
+    """Input half of the GRU gates per TOKEN (vqa_gru_args.d_gi_table): row v = W_ih·emb[v] + (b_ir+b_hr | b_iz+b_hz |
+    b_in), fp16 [rows, 3H].  modules.py:153 evaluates W_ih·x_t for every (sample, step); x_t = emb[token] takes one of
+    `rows` values, so the product is a property of the weights.  Built from the f32 master weights (f32 matmul), i.e. it is
+    closer to the reference than the bf16 x-part GEMM it replaces.  None when the table would be too large or an entry
+    does not fit fp16."""
+    H = w_ih.shape[0] // 3
+    if emb.shape[0] * 3 * H * 2 > GI_TABLE_MAX_BYTES:
+        return None
+    bias = b_ih.clone()
+    bias[:2 * H] += b_hh[:2 * H]
+    gi = torch.addmm(bias.to(device), emb.to(device), w_ih.to(device).t())
+    if not bool(torch.isfinite(gi).all()) or float(gi.abs().max()) > 6.0e4:
+        return None
+    return gi.to(torch.float16).contiguous()
+
+
 def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_layer: int = 0, K: int = 36) -> dict:
     """Reference-named tensors → device tensors in kernel layout."""
     f32 = lambda t: t.detach().to("cpu", torch.float32)
@@ -105,6 +125,9 @@ def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_lay
         packed = pack_gru(P["w_ih"], P["w_hh"], P["b_ih"], P["b_hh"])
         if packed is not None:
             P["wx_packed"], P["wh_packed"], P["bias_packed"] = packed
+            tab = gru_token_table(emb, f32(W[r + "weight_ih_l0"]), f32(W[r + "bias_ih_l0"]), f32(W[r + "bias_hh_l0"]), device)
+            if tab is not None:
+                P["gi_table"] = tab
 
     def wn(prefix):
         v, g, b = f32(W[prefix + ".weight_v"]), f32(W[prefix + ".weight_g"]), f32(W[prefix + ".bias"])
@@ -231,6 +254,8 @@ class VQAEngine:
         if "wx_packed" in P:
             a.d_wx_packed, a.d_wh_packed, a.d_bias_packed = (P["wx_packed"].data_ptr(), P["wh_packed"].data_ptr(),
                                                              P["bias_packed"].data_ptr())
+        if "gi_table" in P:
+            a.d_gi_table = P["gi_table"].data_ptr()
         if self.relation:
             if "Wg3" in P:
                 for name in ("Wg3", "wvec", "label_bias_lp"):

@@ -175,7 +175,7 @@ def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, log
     return (out, label) if want_argmax else out
 
 
-def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False, packed=None):
+def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False, packed=None, gi_table=None):
     """Embedding gather + GRU last state (encoder.py:159-160, modules.py:139-159).
 
     tokens int64 [B,T]; emb [rows,E_pad]; w_ih [3H,E_pad]; w_hh [3H,H] (all one dtype);
@@ -205,6 +205,11 @@ def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False, packed=No
     if packed is not None:                 # (wx_packed, wh_packed, bias_packed) from engine.pack_gru
         a.d_wx_packed, a.d_wh_packed, a.d_bias_packed = (packed[0].data_ptr(), packed[1].data_ptr(),
                                                          packed[2].data_ptr())
+    if gi_table is not None:               # engine.gru_token_table: the token-table form of the fused kernel
+        _require(gi_table, torch.float16, "gi_table")
+        if gi_table.shape != (emb.shape[0], 3 * H):
+            raise ValueError("gru_last_state: gi_table must be [rows of emb, 3H]")
+        a.d_gi_table = gi_table.data_ptr()
     a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
     a.d_h_last, a.d_h_last_lp = h.data_ptr(), (h_lp.data_ptr() if want_lp else None)
     L.check(lib.vqa_gru_last_state(C.byref(a), _stream()))
