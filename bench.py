@@ -60,7 +60,9 @@ def parse():
                     help="comma list; the first one is the line's `value`; `train` = the config-4 training-step block")
     ap.add_argument("--workload", default=None, help="(compat) a single workload")
     ap.add_argument("--batch", type=int, default=1024, help="questions per GPU per step")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp32tc"])
+    ap.add_argument("--no-exact-block", action="store_true",
+                    help="skip the fp32tc block (fp32-class arithmetic on the tensor cores: exact answers, 1e-5 logits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="direct launches instead of CUDA graph replays")
     ap.add_argument("--no-e2e", action="store_true")
@@ -614,6 +616,20 @@ def main():
     ctx.O, ctx.ops = O, ops
 
     results = {wl: run_workload(ctx, args, wl) for wl in args.workloads}
+    # the same workloads in the fp32-class tensor-core mode (precision 'fp32tc'): the mode whose answers are bit-exact
+    exact = None
+    if args.precision == "bf16" and not args.no_exact_block:
+        import copy
+        a2 = copy.copy(args)
+        a2.precision, a2.no_e2e, a2.steps = "fp32tc", True, max(3, min(args.steps, 20))
+        exact = {}
+        for wl in args.workloads:
+            try:
+                r2 = run_workload(ctx, a2, wl)
+                exact[wl] = {k: r2[k] for k in ("value", "unit", "ms_per_step", "steps", "per_rank_ms_total", "launch_mode",
+                                                "launches_per_step", "parity", "clocks") if k in r2}
+            except Exception as e:                          # never lose the bf16 line to this block
+                exact[wl] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     train = None
     if args.train_block:
         try:
@@ -650,6 +666,11 @@ def main():
         blk = dict(results[wl])
         blk["cpu_baseline"] = cpu[wl] if cpu else None
         line[wl] = blk
+    if exact is not None:
+        exact["note"] = ("precision 'fp32tc': every GEMM operand as an fp16 plane pair (hi + lo'·2^-11), three tcgen05.mma per "
+                         "k-step, fp32 accumulators in TMEM; device-resident inputs (plane pairs), CUDA-graph steps, same "
+                         "batches and timing rules as `value`; parity = the fp32 gates (1e-5 logits / attention, answers bit-exact)")
+        line["fp32tc"] = exact
     if train is not None:
         line["train"] = train
     print(json.dumps(line), flush=True)

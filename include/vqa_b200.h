@@ -41,7 +41,11 @@ typedef enum {
 
 typedef enum {
   VQA_F32 = 0,               /* fp32 operands, fp32 FFMA accumulate          */
-  VQA_BF16 = 1               /* bf16 operands, fp32 accumulate (tcgen05/TMEM)*/
+  VQA_BF16 = 1,              /* bf16 operands, fp32 accumulate (tcgen05/TMEM)*/
+  /* fp32-class on tensor cores: a tensor of R rows and leading dimension ld is a PAIR OF fp16 PLANES [2][R][ld],
+   * x = hi + lo'·2^-11 with hi = fp16(x), lo' = fp16((x - hi)·2^11) (22 significant bits; vqa_split_f32 makes them).
+   * vqa_linear then issues three tcgen05.mma per k-step (hi·hi + 2^-11·(hi·lo' + lo'·hi), fp32 accumulators in TMEM). */
+  VQA_F16X2 = 2
 } vqa_dtype;
 
 int vqa_abi_version(void);
@@ -73,6 +77,8 @@ int vqa_relation_labels_host(const float* h_bbox, int B, int K, float img_w, flo
  * ---------------------------------------------------------------------- */
 int vqa_cast_f32_to_bf16(const float* d_src, void* d_dst, size_t n, void* stream);
 int vqa_cast_bf16_to_f32(const void* d_src, float* d_dst, size_t n, void* stream);
+/* f32 -> the fp16 plane pair of VQA_F16X2 (hi, lo' = residual·2^11): n contiguous elements into each plane */
+int vqa_split_f32(const float* d_src, void* d_hi, void* d_lo, size_t n, void* stream);
 
 /* ------------------------------------------------------------------------
  * k4/k5/k8/k11  fused weight-normed linear layer
@@ -141,6 +147,9 @@ typedef struct {
    * counter reaches ceil(N / tile width) (vqa_linear_tiles_n).  Lets a consumer kernel on another stream start on
    * finished row blocks while the GEMM is still running (vqa_graph_attention_args.d_progress). */
   int* d_progress;
+  /* dtype / out_dtype VQA_F16X2: byte offset of the lo' plane behind the hi plane that d_A / d_W / d_out point to;
+   * 0 = the planes are adjacent (M·lda·2, N·ldw·2, M·ldo·2 bytes) */
+  size_t a_plane, w_plane, out_plane;
 } vqa_linear_args;
 
 int vqa_linear(const vqa_linear_args* args, void* stream);
@@ -182,10 +191,13 @@ typedef struct {
   void* d_workspace;   size_t workspace_bytes;
   float* d_h_last;     void* d_h_last_lp;
   const void* d_x;     void* d_out_all;
-  /* optional token table (fp16 [ntoken_rows, 3H], gate order r|z|n): row v = W_ih·emb[v] + (b_ir+b_hr | b_iz+b_hz | b_in),
-   * the input half of the gates, which depends on the token only (modules.py:153 evaluates it per (sample, step)).
-   * With the packed weights and tokens (no d_x / d_out_all) it selects the token-table form of the fused kernel: no
-   * embedding gather, no x-part GEMM — the kernel reads row tokens[b,t] of the table instead.  NULL = off.       */
+  /* optional token table: row v = W_ih·emb[v] + bias, the input half of the gates, which depends on the token only
+   * (modules.py:153 evaluates it per (sample, step)).
+   *   dtype VQA_BF16: fp16 [ntoken_rows, H/32, 3, 32] — per 32-unit block the gates r | z | n, biases b_ir+b_hr |
+   *     b_iz+b_hz | b_in folded in.  With the packed weights and tokens (no d_x / d_out_all) it selects the token-table
+   *     form of the fused kernel: no embedding gather, no x-part GEMM — the kernel stages row tokens[b,t] of the table
+   *     in shared memory (one bulk copy per row and step) and starts the accumulators from it.  NULL = off.
+   *   dtype VQA_F16X2: f32 [ntoken_rows, 3H] in torch's gate order, b_ih folded in; required (this mode has no x-part). */
   const void* d_gi_table;
 } vqa_gru_args;
 

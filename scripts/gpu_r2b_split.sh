@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export PYTHONDONTWRITEBYTECODE=1
+timeout 600 python -m pytest -q --timeout=300 --timeout-method=thread -p no:cacheprovider tests/test_gpu_ops.py -m gpu -k "split or gru" -s > gpurun_out/tests_split.log 2>&1
+echo "tests rc=$?"; grep -E "linear_split|token table|passed|failed|Error|error|assert" gpurun_out/tests_split.log | tail -30
+for d in 0 16; do VQA_B200_GRU_DEBUG=$d TABLE=1 timeout 120 python scripts/time_gru.py 2>&1 | tail -1; done
+TABLE=0 timeout 120 python scripts/time_gru.py 2>&1 | tail -1
+for c in 32x1 64x2 32x2; do VQA_B200_GRU_CFG=$c TABLE=1 timeout 120 python scripts/time_gru.py 2>&1 | tail -1; VQA_B200_GRU_CFG=$c TABLE=0 timeout 120 python scripts/time_gru.py 2>&1 | tail -1; done

@@ -13,7 +13,7 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "updown"
 relation = wl == "regat"
 cfg = O.FULL_REGAT if relation else O.FULL
 B = int(os.environ.get("B", 1024))
-eng = VQAEngine(O.make_weights(cfg, 1111), relation=relation, precision="bf16", device=torch.device("cuda"))
+eng = VQAEngine(O.make_weights(cfg, 1111), relation=relation, precision=os.environ.get("PRECISION", "bf16"), device=torch.device("cuda"))
 g = torch.Generator().manual_seed(3)
 img = eng.resident(torch.rand((B, 36, 2048), generator=g).cuda())
 tok = torch.randint(0, cfg.ntoken, (B, 14), generator=g).cuda()

@@ -99,6 +99,32 @@ def test_fp32_matches_oracle_at_baseline_batch(relation):
     assert torch.equal(label, ref_logits.max(1)[1])
 
 
+@pytest.mark.parametrize("relation", [False, True])
+def test_fp32tc_matches_oracle_at_baseline_batch(relation):
+    """B = 1024, fp32-class arithmetic ON THE TENSOR CORES (precision 'fp32tc': fp16 plane pairs, three tcgen05.mma per
+    k-step, fp32 accumulators): the fp32 gates — 1e-5 on logits / attention and bit-exact answers — in a mode that runs
+    at tensor-core speed; also through the host path and deterministic"""
+    from vqa_collection_b200.engine import VQAEngine
+    cfg, W, batch, ref_logits, ref_att = oracle_at_1024(relation)
+    eng = VQAEngine(W, relation=relation, precision="fp32tc")
+    kw = dict(labels=batch["graph"].to(torch.uint8).cuda()) if relation else {}
+    out = eng.forward(batch["img"].cuda(), batch["q"].cuda(), **kw)
+    logits, att, label = out["logits"].cpu(), out["att"].cpu(), out["label"].cpu()
+    e_log = float((logits - ref_logits).abs().max() / ref_logits.abs().max())
+    e_att = float((att - ref_att).abs().max() / ref_att.abs().max())
+    n_eq = int((label == ref_logits.max(1)[1]).sum())
+    print("fp32tc parity at B=1024", "regat" if relation else "updown", {"logit_err": e_log, "att_err": e_att, "n_equal": n_eq})
+    assert e_log < 1e-5 and e_att < 1e-5
+    assert n_eq == 1024
+    assert torch.equal(label, logits.max(1)[1])
+    planes = eng.resident(batch["img"].cuda())                       # resident format: the plane pair
+    out2 = eng.forward(planes, batch["q"].cuda(), **kw)
+    assert torch.equal(out2["logits"].cpu(), logits)
+    hkw = dict(labels_h=batch["graph"].to(torch.uint8)) if relation else {}
+    label_h, h2d, _ = eng.forward_host(batch["img"].contiguous(), batch["q"].contiguous(), **hkw)
+    assert torch.equal(label_h, label) and h2d >= batch["img"].numel() * 4
+
+
 def test_two_stream_schedule_matches_serial():
     """ReGAT: the two-stream schedule computes exactly what the serial one does (same kernels, same per-element
     arithmetic; only where and when the tiles run changes) -> bit-identical.  Up-Down: the W_v projection is stored as

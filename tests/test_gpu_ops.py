@@ -444,3 +444,46 @@ def test_answer_scores(ops):
     assert torch.equal(row.cpu(), ref_score.sum(1)) and abs(float(total) - float(ref_score.sum())) < 1e-4
     _, row2, _ = ops.answer_scores(label, target.cuda(), want_dense=False)
     assert torch.equal(row2, row)
+
+
+# ---------------------------------------------------------------------------- fp32-class tensor-core mode (VQA_F16X2)
+def test_split_f32_planes(ops):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((38, 100), generator=g) * torch.logspace(-6, 3, 100)          # element count % 8 == 0 (16-byte planes)
+    x[0, :4] = torch.tensor([0.0, 1.0, -65504.0, 6.0e-8])
+    p = ops.split_f32(x.cuda()).cpu()
+    hi = x.to(torch.float16)
+    lo = ((x - hi.float()) * 2048.0).to(torch.float16)
+    assert torch.equal(p[0], hi) and torch.equal(p[1], lo)
+    back = p[0].double() + p[1].double() / 2048.0
+    ok = x.abs() > 1e-4
+    assert float(((back - x.double()).abs() / x.double().abs())[ok].max()) < 2.0 ** -21
+
+
+@pytest.mark.parametrize("M,N,K", [(36864, 1024, 2048), (1024, 3129, 2048), (1024, 2048, 1024), (300, 200, 128), (5, 64, 64)])
+def test_linear_split(ops, M, N, K):
+    """three-product fp16 split GEMM against float64: an order of magnitude inside the fp32 gate (1e-5), every tile shape
+    (CTA pairs, 256 / 192 / 128 / 64 wide), row / column tails, fused epilogues, plane-pair output, fused argmax"""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.rand((M, K), generator=g) * 4.0                    # post-ReLU features
+    A[A < 1.0] = 0.0
+    W = torch.randn((N, K), generator=g) / K ** 0.5
+    bias = torch.randn((N,), generator=g) * 0.1
+    scale = torch.rand((N,), generator=g) + 0.5
+    A2, W2 = ops.split_f32(A.cuda()), ops.split_f32(W.cuda())
+    rows = torch.arange(0, M, max(1, M // 256))
+    ref = torch.relu((A[rows].double() @ W.double().t()) * scale.double() + bias.double())
+    out, label = ops.linear_split(A2, W2, scale.cuda(), bias.cuda(), relu=True, want_argmax=True)
+    err = relerr(out[rows.cuda()], ref)
+    f32 = relerr(torch.relu((A[rows] @ W.t()) * scale + bias), ref)
+    print(f"linear_split {M}x{N}x{K}: err {err:.2e} (cpu fp32 {f32:.2e})")
+    assert err < 5e-6
+    assert torch.equal(label, torch.max(out, 1)[1])
+    planes = ops.linear_split(A2, W2, scale.cuda(), bias.cuda(), relu=True, out_split=True)
+    assert torch.equal(planes, ops.split_f32(out))
+    if N % 256 == 0:
+        lw = torch.randn((N,), generator=g)
+        mul = torch.rand(((M + 35) // 36, N), generator=g)
+        parts = ops.linear_split(A2, W2, scale.cuda(), bias.cuda(), relu=True, mul=mul.cuda(), mul_row_div=36, logit_w=lw.cuda())
+        want = ((ref * mul[rows // 36].double()) * lw.double()).sum(1)
+        assert relerr(parts.sum(1)[rows.cuda()], want) < 5e-6

@@ -13,10 +13,12 @@ _PRECISION = "bf16"
 
 
 def set_precision(p: str):
-    """'bf16' (tcgen05 tensor cores, default) or 'fp32' (FFMA, 1e-5 parity mode)."""
+    """'bf16' (tcgen05 tensor cores, default), 'fp32' (FFMA, 1e-5 parity mode) or 'fp32tc' (fp32-class arithmetic on the
+    tensor cores for the whole-forward engine — fp16 plane pairs, three tcgen05.mma per k-step; module-level calls outside
+    the engine run the 'fp32' kernels)."""
     global _PRECISION
-    if p not in ("bf16", "fp32"):
-        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if p not in ("bf16", "fp32", "fp32tc"):
+        raise ValueError("precision must be 'bf16', 'fp32' or 'fp32tc'")
     _PRECISION = p
 
 

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvqa_b200.so")
 
-VQA_F32, VQA_BF16 = 0, 1
+VQA_F32, VQA_BF16, VQA_F16X2 = 0, 1, 2
 ABI_VERSION = 10
 
 c_void_p, c_int, c_float, c_size_t = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -34,6 +34,7 @@ class LinearArgs(C.Structure):
         ("d_argmax_label", c_void_p), ("d_argmax_ws", c_void_p),
         ("tile_begin", c_int), ("tile_end", c_int), ("cta_limit", c_int),
         ("d_progress", c_void_p),
+        ("a_plane", c_size_t), ("w_plane", c_size_t), ("out_plane", c_size_t),
     ]
 
 
@@ -167,6 +168,7 @@ SYMBOLS = {
     "vqa_relation_labels_host": (c_int, [c_void_p, c_int, c_int, c_float, c_float, c_void_p]),
     "vqa_relation_near_threshold": (c_float, [c_float, c_float]),
     "vqa_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vqa_split_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vqa_cast_bf16_to_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "vqa_linear": (c_int, [C.POINTER(LinearArgs), c_void_p]),
     "vqa_linear_part_width": (c_int, [c_int]),

@@ -60,6 +60,9 @@ int attention_logits(const void*, int, const float*, int, const float*, int, int
 int add_inplace(void*, const void*, size_t, int, cudaStream_t);
 int attention_pool(const float*, int, float, const void*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int argmax_rows(const float*, int, int, int, int64_t*, cudaStream_t);
+int split_f32(const float*, void*, void*, size_t, cudaStream_t);
+int gru_gate_table(const float*, const int64_t*, int, const float*, const float*, int, int, int, int, const float*, float*, void*,
+                   cudaStream_t);
 int embedding_gather(const int64_t*, int, int, int, int, const void*, void*, cudaStream_t, void* zero_ptr = nullptr,
                      size_t zero_bytes = 0);
 int gru_gate(const float*, const float*, int, int, int, int, const float*, float*, void*, int, int, cudaStream_t);
@@ -100,11 +103,13 @@ static int linear_dispatch(const vqa_linear_args& a, cudaStream_t s) {
   VQA_REQUIRE(a.M >= 0 && a.N >= 1 && a.K >= 1, "vqa_linear: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
   if (a.M == 0) return VQA_OK;
   VQA_REQUIRE(a.d_A && a.d_W && a.d_out, "vqa_linear: NULL pointer");
-  VQA_REQUIRE(a.dtype == VQA_F32 || a.dtype == VQA_BF16, "vqa_linear: dtype=%d", a.dtype);
+  VQA_REQUIRE(a.dtype == VQA_F32 || a.dtype == VQA_BF16 || a.dtype == VQA_F16X2, "vqa_linear: dtype=%d", a.dtype);
+  VQA_REQUIRE(a.out_dtype != VQA_F16X2 || a.dtype == VQA_F16X2, "vqa_linear: a split (f16x2) output needs split operands");
   VQA_REQUIRE(a.d_mul == nullptr || a.mul_row_div >= 1, "vqa_linear: mul_row_div must be >= 1");
   VQA_REQUIRE(a.d_add == nullptr || a.add_row_div >= 1, "vqa_linear: add_row_div must be >= 1");
   VQA_REQUIRE(!a.d_argmax_label || (a.d_argmax_ws && !a.d_logit_w && a.out_dtype == VQA_F32),
               "vqa_linear: fused argmax needs its workspace, the store form and an f32 output");
+  if (a.dtype == VQA_F16X2) return linear_tc(a, s);                      // fp32-class: tensor cores or nothing
   if (a.dtype == VQA_BF16 && !force_simt()) return linear_tc(a, s);      // argmax in the epilogue
   if (int rc = linear_simt(a, s)) return rc;
   if (a.d_argmax_label) return argmax_rows((const float*)a.d_out, a.M, a.N, a.ldo, a.d_argmax_label, s);
@@ -113,7 +118,7 @@ static int linear_dispatch(const vqa_linear_args& a, cudaStream_t s) {
 static size_t argmax_ws_bytes(int M) { return align_up((size_t)(M > 0 ? M : 1) * 8, 256) + align_up((size_t)((M + 127) / 128 + 1) * 4, 256); }
 
 static int part_width(int dtype) {
-  return (dtype == VQA_BF16 && !force_simt()) ? linear_tc_part_width() : 128;
+  return (dtype == VQA_F16X2 || (dtype == VQA_BF16 && !force_simt())) ? linear_tc_part_width() : 128;
 }
 
 // ---- GRU --------------------------------------------------------------------
@@ -150,7 +155,40 @@ static bool gru_pair_enabled() {
 }
 
 // sm_limit > 0: the persistent kernel may use at most that many SMs (vqa_forward's overlap mode)
+// fp32-class mode (VQA_F16X2): token table for the input half (f32 [rows, 3H] = W_ih·emb[v] + b_ih), per step one split
+// GEMM h·W_hhᵀ + b_hh (three tcgen05.mma per k-step) and the gate kernel, which writes the state as f32 and as the fp16
+// plane pair that is the next GEMM's operand.  h_0 = 0: the first step has no GEMM.
+static int gru_last_state_split(const vqa_gru_args& a, cudaStream_t s) {
+  VQA_REQUIRE(a.d_tokens && a.d_gi_table && a.d_w_hh && a.d_b_hh && a.d_h_last && !a.d_x && !a.d_out_all,
+              "vqa_gru_last_state(f16x2): needs tokens, the f32 token table, W_hh planes, b_hh and d_h_last (no sequence form)");
+  VQA_REQUIRE(a.B >= 0 && a.T >= 1 && a.H >= 1 && a.H % 8 == 0, "vqa_gru_last_state(f16x2): bad dims");
+  const GruWs need = carve_gru(nullptr, a.B, a.T, a.H, a.E_pad, a.dtype);
+  VQA_REQUIRE(a.d_workspace && a.workspace_bytes >= need.bytes,
+              "vqa_gru_last_state: workspace %zu < %zu bytes", a.workspace_bytes, need.bytes);
+  if (a.B == 0) return VQA_OK;
+  const GruWs w = carve_gru(a.d_workspace, a.B, a.T, a.H, a.E_pad, a.dtype);
+  void* tail = (char*)a.d_workspace + need.bytes;
+  const size_t tail_bytes = (a.workspace_bytes - need.bytes) / 16 * 16;
+  if (tail_bytes) VQA_CUDA_CHECK(cudaMemsetAsync(tail, 0, tail_bytes, s));
+  int rc;
+  for (int t = 0; t < a.T; ++t) {
+    const bool last = (t == a.T - 1);
+    if (t > 0) {
+      vqa_linear_args gh{};
+      gh.d_A = w.h_lp; gh.lda = a.H; gh.d_W = a.d_w_hh; gh.ldw = a.H;
+      gh.M = a.B; gh.N = 3 * a.H; gh.K = a.H; gh.dtype = VQA_F16X2;
+      gh.d_bias = a.d_b_hh; gh.d_out = w.gh; gh.ldo = 3 * a.H; gh.out_dtype = VQA_F32; gh.mul_row_div = 1;
+      if ((rc = linear_dispatch(gh, s))) return rc;
+    }
+    void* planes = (last && a.d_h_last_lp) ? a.d_h_last_lp : w.h_lp;
+    if ((rc = gru_gate_table((const float*)a.d_gi_table, a.d_tokens, a.ntoken_rows, t > 0 ? w.gh : nullptr, a.d_b_hh, a.B, a.H,
+                             a.T, t, t > 0 ? w.h : nullptr, last ? a.d_h_last : w.h, planes, s))) return rc;
+  }
+  return VQA_OK;
+}
+
 static int gru_last_state(const vqa_gru_args& a, cudaStream_t s, int sm_limit = 0) {
+  if (a.dtype == VQA_F16X2) return gru_last_state_split(a, s);
   VQA_REQUIRE(((a.d_tokens && a.d_emb) || a.d_x) && a.d_w_ih && a.d_w_hh && a.d_b_ih && a.d_b_hh &&
               (a.d_h_last || a.d_out_all), "vqa_gru_last_state: NULL pointer");
   VQA_REQUIRE(a.B >= 0 && a.T >= 1 && a.H >= 1 && a.E_pad >= 1, "vqa_gru_last_state: bad dims");
@@ -328,6 +366,10 @@ int vqa_relation_labels_host(const float* h_bbox, int B, int K, float img_w, flo
 int vqa_cast_f32_to_bf16(const float* d_src, void* d_dst, size_t n, void* stream) {
   if (int rc = require_sm100()) return rc;
   return cast_f32_to_bf16(d_src, d_dst, n, (cudaStream_t)stream);
+}
+int vqa_split_f32(const float* d_src, void* d_hi, void* d_lo, size_t n, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  return split_f32(d_src, d_hi, d_lo, n, (cudaStream_t)stream);
 }
 int vqa_cast_bf16_to_f32(const void* d_src, float* d_dst, size_t n, void* stream) {
   if (int rc = require_sm100()) return rc;
@@ -535,6 +577,7 @@ static bool overlap_mode(const vqa_forward_args& a) {
 struct FwdWs {
   void* gru; size_t gru_bytes;
   float* h; void* h_lp; float* qq; float* parts; void* vsum; void* Y; void* proj; void* joint; void* hid;
+  float* vsum_f32;                           // f16x2 + relation: the fp32 graph attention's output before it is split
   int* progress;                             // row-block counters of the wide projection (chase mode)
   void* amax; size_t amax_bytes;             // fused answer selection of the last classifier layer
   size_t bytes;
@@ -556,6 +599,7 @@ static FwdWs carve_fwd(const vqa_forward_args& a, void* base) {
   const int n_parts = (a.H + part_width(a.dtype) - 1) / part_width(a.dtype);
   w.parts = (float*)take((size_t)a.B * a.K * n_parts * 4);
   w.vsum = take((size_t)a.B * a.V * es);
+  w.vsum_f32 = (a.relation && a.dtype == VQA_F16X2) ? (float*)take((size_t)a.B * a.V * 4) : nullptr;
   w.Y = a.relation ? take((size_t)a.B * a.K * (a.d_Wg3 ? 3 : 4) * a.V * es) : nullptr;
   w.proj = (!a.relation && overlap_mode(a)) ? take((size_t)a.B * a.K * a.H * es) : nullptr;   // stored W_v projection
   w.progress = chase_mode(a) ? (int*)take(((size_t)(a.B * a.K + 255) / 256 * 2 + 1) * 4) : nullptr;
@@ -643,6 +687,9 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
     VQA_REQUIRE(a.d_att, "vqa_forward: relation path needs d_att");
   }
   if (a.att_concat) VQA_REQUIRE(a.d_W1q && a.d_b1, "vqa_forward: att_concat needs d_W1q and d_b1");
+  if (a.dtype == VQA_F16X2)
+    VQA_REQUIRE(a.d_gi_table && !a.d_Wg3 && a.V % 8 == 0 && a.H % 8 == 0 && (a.B * a.K * a.V) % 8 == 0,
+                "vqa_forward(f16x2): needs the f32 token table, 16-byte aligned planes and the unmerged ReGAT weights");
 
   // ---- schedule: everything on `s` in order, or (overlap) question encoder on the side stream `sq` while the
   //      question-independent projection of the region features runs on `s` on the other SMs
@@ -669,7 +716,7 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
   if (a.relation) {
     proj.d_A = a.d_img; proj.lda = a.V; proj.d_W = a.d_Wg3 ? a.d_Wg3 : a.d_Wg; proj.ldw = a.V; proj.M = a.B * a.K;
     proj.N = maps * a.V; proj.K = a.V; proj.dtype = a.dtype; proj.mul_row_div = 1; proj.d_out = w.Y; proj.ldo = maps * a.V;
-    proj.out_dtype = a.dtype;
+    proj.out_dtype = a.dtype == VQA_F16X2 ? VQA_F32 : a.dtype;        // fp32-class: Y feeds the fp32 graph attention
   } else if (overlap) {
     // 'new' attention: ReLU(s·W_v v + b) (attention.py:70); 'base': the bare v-half s·W1v v of the concat layer — its bias,
     // the q-half and the ReLU follow in the logit kernel (attention.py:38-40)
@@ -770,6 +817,10 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
     ga.d_Y = w.Y; ga.ldy = maps * a.V; ga.d_att = att; ga.d_labels = labels; ga.d_label_bias = a.d_label_bias;
     ga.num_labels = a.num_labels; ga.d_ba = a.d_ba; ga.d_bb = a.d_bb; ga.B = a.B; ga.K = a.K; ga.V = a.V; ga.dtype = a.dtype;
     ga.d_out = a.d_v; ga.d_vsum = w.vsum; ga.d_alpha = a.d_alpha;
+    if (a.dtype == VQA_F16X2) {
+      VQA_REQUIRE(!a.d_v, "vqa_forward(f16x2): the encoder output 'v' is not produced in this mode");
+      ga.dtype = VQA_F32; ga.d_vsum = w.vsum_f32;
+    }
     if (a.d_Wg3) {
       ga.layout = 1; ga.d_x = a.d_img; ga.ldx = a.V; ga.d_wvec = a.d_wvec; ga.c0 = a.gat_c0;
       ga.d_label_bias_lp = a.d_label_bias_lp;
@@ -779,6 +830,8 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
       VQA_CUDA_CHECK(cudaEventRecord(side->join, sg));
       VQA_CUDA_CHECK(cudaStreamWaitEvent(s, side->join, 0));
     }
+    if (a.dtype == VQA_F16X2 &&
+        (rc = split_f32(w.vsum_f32, w.vsum, (char*)w.vsum + (size_t)a.B * a.V * 2, (size_t)a.B * a.V, s))) return rc;
   }
   // 6. v_net ⊙ q_net (predictor.py:88-91)
   l = vqa_linear_args{};

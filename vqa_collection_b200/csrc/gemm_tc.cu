@@ -35,13 +35,23 @@ constexpr int EPI_WARP0 = 4;           // warps 4..7 (warp_id % 4 selects the TM
 // PAIR: two CTAs on one TPC work on a 256 x BN tile with tcgen05.mma.cta_group::2 — each CTA loads its own 128 rows of A
 // and HALF of the W tile (the tensor cores of both SMs read both halves), so the shared-memory fill and the B-operand
 // reads per SM shrink by a third / a half; one thread of the leader CTA issues the MMAs (see gru_pair.cu for the protocol).
-template <int BN, bool PAIR = false> struct Cfg {
-  static constexpr int A_BYTES = BM * BK * 2;
+// SPLIT (dtype VQA_F16X2, the fp32-class mode): every operand is a pair of fp16 planes, x = hi + lo'·2^-11 with
+// hi = fp16(x), lo' = fp16((x - hi)·2^11) (22 significant bits, no subnormal loss of the residual: Ootomo & Yokota,
+// "Recovering single precision accuracy from Tensor Cores while surpassing the FP32 theoretical peak performance").  A stage
+// holds [A_hi | A_lo | W_hi | W_lo]; per k-step THREE MMAs: hi·hi into the main accumulator, hi·lo' and lo'·hi into a second one
+// that the epilogue adds scaled by 2^-11 (the lo'·lo' term, 2^-22 relative, is dropped).  A tile therefore owns 2·BN TMEM
+// columns, and the accumulators are double buffered only where 4·BN columns fit (BN <= 128).
+template <int BN, bool PAIR = false, bool SPLIT = false> struct Cfg {
+  static constexpr int PLANES = SPLIT ? 2 : 1;
+  static constexpr int A_BYTES = BM * BK * 2;                // one plane
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = PAIR ? 6 : (BN >= 256 ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8)));
-  static constexpr int TMEM_COLS = pow2_ge(2 * BN);
-  static constexpr int ACC_STRIDE = TMEM_COLS / 2;
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = SPLIT ? (PAIR ? 3 : (BN >= 192 ? 2 : (BN >= 128 ? 3 : 4)))
+                                      : (PAIR ? 6 : (BN >= 256 ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8))));
+  static constexpr int TILE_COLS = PLANES * BN;              // TMEM columns of one tile: [main | correction]
+  static constexpr int NACC = (2 * TILE_COLS <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = pow2_ge(NACC * TILE_COLS);
+  static constexpr int ACC_STRIDE = TMEM_COLS / NACC;
   static constexpr int PARAM_FLOATS = 2 * 3 * BN;            // 2 acc stages x (scale,bias,logit_w)
   static constexpr int STAGE_OUT_FLOATS = 4 * 32 * 33;       // per epilogue warp: 32 rows x 32 cols (+1 pad) f32
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 256 /*barriers*/ +
@@ -56,6 +66,7 @@ struct Params {
   const void* mask; int ld_mask; int mask_bf16;
   const float* logit_w;
   void* out; int ldo; int out_bf16; int n_parts;
+  int out_split; size_t out_plane;            // fp16 plane pair: lo' plane out_plane bytes behind the hi plane
   int tiles_m, tiles_n;
   int tile_begin, tile_end;                  // this launch walks tiles [tile_begin, tile_end) of the tile order
   float leaky_slope; int add_after_act; int sigmoid;
@@ -69,11 +80,13 @@ struct Params {
 };
 
 // ---- the kernel ----------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, bool PAIR = false>
+template <int BN, bool A_MN, bool B_MN, bool PAIR = false, bool SPLIT = false>
 __global__ void __launch_bounds__(THREADS, 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Params p) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const Params p) {
   static_assert(!PAIR || (!A_MN && !B_MN), "CTA pairs are built for the K-major forward form");
-  using C = Cfg<BN, PAIR>;
+  static_assert(!SPLIT || (!A_MN && !B_MN), "the split form is built for the K-major forward form");
+  using C = Cfg<BN, PAIR, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B needs 1024-byte alignment
@@ -101,6 +114,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
+    if constexpr (SPLIT) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmW2); }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -125,15 +139,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m_blk = tile_m(tile), n_blk = tile % p.tiles_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::PLANES * C::A_BYTES;
           if constexpr (PAIR) {                      // both CTAs fill their own slots; bytes are counted on the leader's barrier
             if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
             tma_load_2d_2cta(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
             tma_load_2d_2cta(sb, &tmW, full_bar(stage), kb * BK, n_blk * BN + (int)crank * (BN / 2));
+            if constexpr (SPLIT) {
+              tma_load_2d_2cta(sa + C::A_BYTES, &tmA2, full_bar(stage), kb * BK, m_blk * BM);
+              tma_load_2d_2cta(sb + C::B_BYTES, &tmW2, full_bar(stage), kb * BK, n_blk * BN + (int)crank * (BN / 2));
+            }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
           mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          if constexpr (SPLIT) {
+            tma_load_2d(sa + C::A_BYTES, &tmA2, full_bar(stage), kb * BK, m_blk * BM);
+            tma_load_2d(sb + C::B_BYTES, &tmW2, full_bar(stage), kb * BK, n_blk * BN);
+          }
           if constexpr (!A_MN) {
             tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
           } else {                                   // tensor [K rows, M cols]: 64-wide atoms of 64 k-rows
@@ -155,7 +177,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0 && lead) {
-      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN) | (A_MN ? IDESC_A_MN_MAJOR : 0u) | (B_MN ? IDESC_B_MN_MAJOR : 0u);
+      constexpr uint32_t idesc = (SPLIT ? make_idesc_f16(PAIR ? 2 * BM : BM, BN) : make_idesc_bf16(PAIR ? 2 * BM : BM, BN)) |
+                                 (A_MN ? IDESC_A_MN_MAJOR : 0u) | (B_MN ? IDESC_B_MN_MAJOR : 0u);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -165,9 +188,27 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::A_BYTES;
+          const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::PLANES * C::A_BYTES;
+          if constexpr (SPLIT) {
+            // main += A_hi·W_hi ; correction += A_hi·W_lo' + A_lo'·W_hi   (columns [BN, 2BN) of the tile)
+            const uint64_t ah = make_sw128_kmajor_desc(sa), al = make_sw128_kmajor_desc(sa + C::A_BYTES);
+            const uint64_t wh = make_sw128_kmajor_desc(sb), wl = make_sw128_kmajor_desc(sb + C::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t first = (kb | k) != 0;
+              if constexpr (PAIR) {
+                umma_bf16_2cta(d_tmem, ah + 2 * k, wh + 2 * k, idesc, first);
+                umma_bf16_2cta(d_tmem + BN, ah + 2 * k, wl + 2 * k, idesc, first);
+                umma_bf16_2cta(d_tmem + BN, al + 2 * k, wh + 2 * k, idesc, 1u);
+              } else {
+                umma_bf16(d_tmem, ah + 2 * k, wh + 2 * k, idesc, first);
+                umma_bf16(d_tmem + BN, ah + 2 * k, wl + 2 * k, idesc, first);
+                umma_bf16(d_tmem + BN, al + 2 * k, wh + 2 * k, idesc, 1u);
+              }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < (SPLIT ? 0 : BK / UMMA_K); ++k) {
             // K-major: advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom (+2 in the addr>>4 field);
             // MN-major: advance 16 k-rows = 2048 bytes, atoms BK*128 bytes apart
             const uint64_t adesc = A_MN ? make_sw128_mnmajor_desc(sa + k * 2048, BK * 128, 1024)
@@ -186,7 +227,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == C::NACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -194,11 +235,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp - EPI_WARP0;                  // == warp % 4: TMEM lane quarter
     const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+    int pbuf = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, pbuf ^= 1) {
       const int m_blk = tile_m(tile), n_blk = tile % p.tiles_n;
       const int n0 = n_blk * BN;
-      // stage this tile's per-column parameters (double buffered with the accumulator)
-      float* ps = params_smem + acc * 3 * BN;
+      // stage this tile's per-column parameters; double buffered by tile parity (not by accumulator: a single-buffered
+      // accumulator would let a fast warp overwrite what a slow one still reads; the barrier below orders buffer reuse)
+      float* ps = params_smem + pbuf * 3 * BN;
       for (int c = et; c < BN; c += 128) {
         const int n = n0 + c;
         const bool ok = n < p.N;
@@ -223,7 +266,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld_32x32(t_row + c0, v);
-        tmem_ld_wait();
+        if constexpr (SPLIT) {
+          uint32_t vc[32];
+          tmem_ld_32x32(t_row + BN + c0, vc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(vc[j]), 0x1p-11f, __uint_as_float(v[j])));
+        } else {
+          tmem_ld_wait();
+        }
         const int nbase = n0 + c0;
         if (nbase >= p.N) continue;
         float y[32];
@@ -300,7 +351,29 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) part = fmaf(y[j], ps[2 * BN + c0 + j], part);   // logit_w = 0 beyond N
         } else if (row_ok) {
-          if (p.out_bf16) {
+          if (p.out_split) {
+            // fp16 plane pair for the next layer's A operand
+            __half* oh = reinterpret_cast<__half*>(p.out) + (size_t)row * p.ldo + nbase;
+            __half* ol = reinterpret_cast<__half*>(reinterpret_cast<char*>(p.out) + p.out_plane) + (size_t)row * p.ldo + nbase;
+            if (full && ((p.ldo & 7) == 0) && (((reinterpret_cast<uintptr_t>(p.out) | p.out_plane) & 15) == 0)) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                uint4 rh, rl;
+                uint32_t* ph = reinterpret_cast<uint32_t*>(&rh); uint32_t* pl = reinterpret_cast<uint32_t*>(&rl);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_f16x2_pair(y[8 * j8 + 2 * e], y[8 * j8 + 2 * e + 1], ph[e], pl[e]);
+                reinterpret_cast<uint4*>(oh)[j8] = rh;
+                reinterpret_cast<uint4*>(ol)[j8] = rl;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nbase + j < p.N) {
+                  const __half h = __float2half_rn(y[j]);
+                  oh[j] = h; ol[j] = __float2half_rn((y[j] - __half2float(h)) * 2048.f);
+                }
+            }
+          } else if (p.out_bf16) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)row * p.ldo + nbase;
             if (full && ((p.ldo & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) {
 #pragma unroll
@@ -316,7 +389,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        if (!p.logit_w && !p.out_bf16) {
+        if (!p.logit_w && !p.out_bf16 && !p.out_split) {
           // f32 output: thread = row would scatter 4-byte stores over 32 rows per instruction; transpose the
           // 32x32 chunk through shared memory so that every store instruction writes one 128-byte row segment
           float* st = stage_out + q * (32 * 33);
@@ -373,7 +446,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) red_release_gpu_add(p.progress + m_blk, 1);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == C::NACC) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -449,15 +522,23 @@ static void tile_range(const vqa_linear_args& a, int total, int* begin, int* end
   *begin = b; *end = e;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// lo' planes of a split (VQA_F16X2) operand / output: explicit byte offset, or right behind the hi plane of `rows` rows
+static size_t plane_offset(size_t given, long long rows, long long ld) { return given ? given : (size_t)rows * ld * 2; }
+
+template <int BN, bool A_MN, bool B_MN, bool SPLIT = false>
 static int launch(const vqa_linear_args& a, cudaStream_t s) {
-  using C = Cfg<BN>;
-  CUtensorMap tmA, tmW;
+  using C = Cfg<BN, false, SPLIT>;
+  CUtensorMap tmA, tmW, tmA2, tmW2;
   int rc;
   if (A_MN) { if ((rc = make_tensor_map_mn(&tmA, a.d_A, a.K, a.M, a.lda))) return rc; }
   else if ((rc = make_tensor_map_bf16(&tmA, a.d_A, a.M, a.K, a.lda, BM))) return rc;
   if (B_MN) { if ((rc = make_tensor_map_mn(&tmW, a.d_W, a.K, a.N, a.ldw))) return rc; }
   else if ((rc = make_tensor_map_bf16(&tmW, a.d_W, a.N, a.K, a.ldw, BN))) return rc;
+  tmA2 = tmA; tmW2 = tmW;
+  if (SPLIT) {                                         // 2-byte elements: the bf16 maps serve fp16 planes as well
+    if ((rc = make_tensor_map_bf16(&tmA2, (const char*)a.d_A + plane_offset(a.a_plane, a.M, a.lda), a.M, a.K, a.lda, BM))) return rc;
+    if ((rc = make_tensor_map_bf16(&tmW2, (const char*)a.d_W + plane_offset(a.w_plane, a.N, a.ldw), a.N, a.K, a.ldw, BN))) return rc;
+  }
   Params p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.scale = a.d_scale; p.bias = a.d_bias; p.relu = a.relu;
@@ -465,6 +546,7 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
   p.add = a.d_add; p.ld_add = a.ld_add; p.add_row_div = a.add_row_div > 0 ? a.add_row_div : 1;
   p.mask = a.d_mask; p.ld_mask = a.ld_mask; p.mask_bf16 = (a.mask_dtype == VQA_BF16);
   p.logit_w = a.d_logit_w; p.out = a.d_out; p.ldo = a.ldo; p.out_bf16 = (a.out_dtype == VQA_BF16);
+  p.out_split = (a.out_dtype == VQA_F16X2); p.out_plane = plane_offset(a.out_plane, a.M, a.ldo);
   p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
   p.leaky_slope = a.leaky_slope; p.add_after_act = a.add_after_act; p.sigmoid = a.sigmoid;
   p.amax_keys = nullptr; p.amax_cnt = nullptr; p.amax_label = nullptr;
@@ -475,7 +557,7 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
     p.amax_cnt = (int*)((char*)a.d_argmax_ws + align_up((size_t)a.M * 8, 256));
     p.amax_label = (long long*)a.d_argmax_label;
   }
-  auto kern = linear_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = linear_tc_kernel<BN, A_MN, B_MN, false, SPLIT>;
   static DeviceOnce attr;                            // per device, not per process
   const int dev = current_device();
   if (attr.need(dev)) {
@@ -487,7 +569,7 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
   if (tiles <= 0) return VQA_OK;
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (a.cta_limit > 0 && a.cta_limit < grid) grid = a.cta_limit;
-  VQA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)C::SMEM_BYTES, s, tmA, tmW, p));
+  VQA_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(THREADS), (size_t)C::SMEM_BYTES, s, tmA, tmW, tmA2, tmW2, p));
   VQA_LAUNCH_CHECK();
   return VQA_OK;
 }
@@ -495,10 +577,11 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
 // 256 x 256 tiles on CTA pairs (tcgen05 cta_group::2) for the large K-major GEMMs.  VQA_ERR_UNSUPPORTED = the device cannot
 // hold the pairs (or VQA_B200_GEMM_PAIR=0): the caller falls back to one CTA per tile.
 // how many CTA pairs of the 256 x 256 kernel the current device holds at once (0 = pairs unusable)
+template <bool SPLIT>
 static int pairs_resident_on_device() {
   constexpr int BN = 256;
-  using C = Cfg<BN, true>;
-  auto kern = linear_tc_kernel<BN, false, false, true>;
+  using C = Cfg<BN, true, SPLIT>;
+  auto kern = linear_tc_kernel<BN, false, false, true, SPLIT>;
   static DeviceInt cache;
   int& pairs_resident = cache.at(current_device());
   if (pairs_resident < 0) {
@@ -519,16 +602,22 @@ static int pairs_resident_on_device() {
   return pairs_resident;
 }
 
+template <bool SPLIT>
 static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
   constexpr int BN = 256;
-  using C = Cfg<BN, true>;
-  auto kern = linear_tc_kernel<BN, false, false, true>;
-  const int pairs_resident = pairs_resident_on_device();
+  using C = Cfg<BN, true, SPLIT>;
+  auto kern = linear_tc_kernel<BN, false, false, true, SPLIT>;
+  const int pairs_resident = pairs_resident_on_device<SPLIT>();
   if (pairs_resident <= 0) return VQA_ERR_UNSUPPORTED;
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmA2, tmW2;
   int rc;
   if ((rc = make_tensor_map_bf16(&tmA, a.d_A, a.M, a.K, a.lda, BM))) return rc;
   if ((rc = make_tensor_map_bf16(&tmW, a.d_W, a.N, a.K, a.ldw, BN / 2))) return rc;
+  tmA2 = tmA; tmW2 = tmW;
+  if (SPLIT) {
+    if ((rc = make_tensor_map_bf16(&tmA2, (const char*)a.d_A + plane_offset(a.a_plane, a.M, a.lda), a.M, a.K, a.lda, BM))) return rc;
+    if ((rc = make_tensor_map_bf16(&tmW2, (const char*)a.d_W + plane_offset(a.w_plane, a.N, a.ldw), a.N, a.K, a.ldw, BN / 2))) return rc;
+  }
   Params p;
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.scale = a.d_scale; p.bias = a.d_bias; p.relu = a.relu;
@@ -536,6 +625,7 @@ static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
   p.add = a.d_add; p.ld_add = a.ld_add; p.add_row_div = a.add_row_div > 0 ? a.add_row_div : 1;
   p.mask = a.d_mask; p.ld_mask = a.ld_mask; p.mask_bf16 = (a.mask_dtype == VQA_BF16);
   p.logit_w = a.d_logit_w; p.out = a.d_out; p.ldo = a.ldo; p.out_bf16 = (a.out_dtype == VQA_BF16);
+  p.out_split = (a.out_dtype == VQA_F16X2); p.out_plane = plane_offset(a.out_plane, a.M, a.ldo);
   p.tiles_m = (a.M + BM - 1) / BM; p.tiles_n = (a.N + BN - 1) / BN; p.n_parts = p.tiles_n;
   p.leaky_slope = a.leaky_slope; p.add_after_act = a.add_after_act; p.sigmoid = a.sigmoid;
   p.amax_keys = nullptr; p.amax_cnt = nullptr; p.amax_label = nullptr;
@@ -551,7 +641,7 @@ static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  VQA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, p));
+  VQA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmA2, tmW2, p));
   VQA_LAUNCH_CHECK();
   return VQA_OK;
 }
@@ -570,7 +660,7 @@ static Plan plan_tiles(const vqa_linear_args& a, bool mn_major) {
   Plan pl{256, false, 0};
   if (a.d_logit_w || tiles_m * ((a.N + 255) / 256) >= sms) {
     if (!mn_major && tiles_m * ((a.N + 255) / 256) >= 2 * sms && a.N % 256 == 0 && !a.d_argmax_label &&
-        pairs_resident_on_device() > 0)
+        (a.dtype == VQA_F16X2 ? pairs_resident_on_device<true>() : pairs_resident_on_device<false>()) > 0)
       pl.pair = true;
   } else {
     int best_cost = 1 << 30;
@@ -585,12 +675,27 @@ static Plan plan_tiles(const vqa_linear_args& a, bool mn_major) {
   return pl;
 }
 
+// split (fp32-class) form: K-major only
+static int launch_split(const vqa_linear_args& a, cudaStream_t s) {
+  const Plan pl = plan_tiles(a, false);
+  if (pl.pair) {
+    const int rc = launch_pair<true>(a, s);
+    if (rc != VQA_ERR_UNSUPPORTED) return rc;
+  }
+  switch (pl.bn) {
+    case 256: return launch<256, false, false, true>(a, s);
+    case 192: return launch<192, false, false, true>(a, s);
+    case 128: return launch<128, false, false, true>(a, s);
+    default: return launch<64, false, false, true>(a, s);
+  }
+}
+
 template <bool A_MN, bool B_MN>
 static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
   const Plan pl = plan_tiles(a, A_MN || B_MN);
   if constexpr (!A_MN && !B_MN) {
     if (pl.pair) {
-      const int rc = launch_pair(a, s);
+      const int rc = launch_pair<false>(a, s);
       if (rc != VQA_ERR_UNSUPPORTED) return rc;
     }
   }
@@ -623,6 +728,10 @@ int linear_tc(const vqa_linear_args& a, cudaStream_t s) {
               "vqa_linear(bf16): TMA needs 16-byte aligned rows (lda=%d ldw=%d)", a.lda, a.ldw);
   VQA_REQUIRE(!(a.trans_a && !a.trans_w), "vqa_linear(bf16): trans_a without trans_w is not built");
   if (a.M == 0) return VQA_OK;
+  if (a.dtype == VQA_F16X2) {
+    VQA_REQUIRE(!a.trans_a && !a.trans_w && !a.d_mask, "vqa_linear(f16x2): forward (K-major) form only");
+    return tc::launch_split(a, s);
+  }
   if (a.trans_a) return tc::launch_bn<true, true>(a, s);       // dW = dYᵀ·X
   if (a.trans_w) return tc::launch_bn<false, true>(a, s);      // dX = dY·W
   return tc::launch_bn<false, false>(a, s);

@@ -59,18 +59,24 @@ constexpr int TMEM_COLS = 512;
 
 // UNITS = hidden units per CTA pair: 64 normally; 32 when the batch is so small that 64-unit tiles would leave
 // half of the SMs idle (B <= 512 at H = 1024) — twice the CTAs, half the W tile and half the gate math per CTA.
-template <int UNITS> struct Cfg {
+template <int UNITS, bool TABLE = false> struct Cfg {
   static constexpr int ACC_STRIDE = 4 * UNITS;             // columns of one accumulator: [r|z|n] x 2 halves, then n_x
   static constexpr int NACC = TMEM_COLS / ACC_STRIDE;      // accumulators in flight: 2 (64 units) / 4 (32 units)
   static constexpr int HALF_UNITS = UNITS / 2;             // units whose W rows one CTA holds
   static constexpr int UPT = UNITS / (EPI_WARPS / 4);      // units per epilogue thread (16 / 8)
   static constexpr int CHUNK_BYTES = HALF_UNITS * BK * 2;  // one box of U/2 gate rows (4 KB / 2 KB)
-  static constexpr int W_BYTES = 4 * CHUNK_BYTES;          // this CTA's half of the widest (x-part, N = 4U) B tile
-  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;    // 32 KB / 24 KB
-  static constexpr int STAGES = UNITS == 64 ? 7 : 9;         // 224 KB / 216 KB of ring
+  static constexpr int W_BYTES = (TABLE ? 3 : 4) * CHUNK_BYTES;   // this CTA's half of the widest B tile (x-part: N = 4U)
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;    // 32 KB / 24 KB (token-table form: 28 KB / 22 KB)
+  static constexpr int STAGES = TABLE ? (UNITS == 64 ? 6 : 8) : (UNITS == 64 ? 7 : 9);
   static constexpr int COL_NH = 3 * UNITS;                 // W_hn·h
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + 4 * UNITS * 4;
+  // token-table form: the 128 table rows of the next job, [r | z | n] x 32 units per 32-unit block; the row stride is an
+  // ODD number of 16-byte words so that 8 consecutive rows (lanes) hit 8 different 16-byte bank groups (LDS.128)
+  static constexpr int GI_ROW_BYTES = 3 * UNITS * 2;
+  static constexpr int GI_STRIDE = GI_ROW_BYTES + 16;
+  static constexpr int GI_BYTES = TABLE ? BM * GI_STRIDE : 0;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + GI_BYTES + 256 + 4 * UNITS * 4;
   static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
+  static_assert((GI_STRIDE / 16) % 2 == 1, "row stride of the table tile");
 };
 
 struct Params {
@@ -87,7 +93,8 @@ struct Params {
   int debug;                    // VQA_B200_GRU_DEBUG bits, timing experiments only (results are wrong): 1 = no MMAs,
                                 // 2 = no TMA loads, 4 = no wait for the other CTAs' h_t, 8 = no gate arithmetic / stores
   float *save_r, *save_z, *save_n, *save_hn, *save_h;   // save_h: slot t = state AFTER step t
-  // token-table form: gi_table fp16 [ntoken_rows, 3H] (gate order r|z|n, biases b_ir+b_hr | b_iz+b_hz | b_in folded in)
+  // token-table form: gi_table fp16 [ntoken_rows, H/32, 3, 32] (per 32-unit block the gates r|z|n; biases b_ir+b_hr |
+  // b_iz+b_hz | b_in folded in)
   const __half* gi_table;
   const int64_t* tokens;        // [B,T]
   int ntoken_rows;
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH0,
                 const __grid_constant__ CUtensorMap tmH1, const __grid_constant__ CUtensorMap tmWx,
                 const __grid_constant__ CUtensorMap tmWh, const Params p) {
-  using C = Cfg<UNITS>;
+  using C = Cfg<UNITS, TABLE>;
   constexpr int HALF_UNITS = C::HALF_UNITS, UPT = C::UPT, STAGE_BYTES = C::STAGE_BYTES, STAGES = C::STAGES, COL_NH = C::COL_NH;
   constexpr int CHUNK_BYTES = C::CHUNK_BYTES;
   constexpr int ACC_STRIDE = C::ACC_STRIDE, NACC = C::NACC;
@@ -123,11 +130,14 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + NACC + a); };
-  static_assert(8 * (2 * STAGES + 2 * NACC + 1) <= 256, "barrier block");
+  static_assert(8 * (2 * STAGES + 2 * NACC + 3) <= 256, "barrier block");
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2 * NACC);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 2 * NACC));
+  const uint32_t gi_full = bars + 8u * (2 * STAGES + 2 * NACC + 1), gi_empty = gi_full + 8u;   // token-table tile
   float* bias_s = reinterpret_cast<float*>(base_ptr + STAGES * STAGE_BYTES + 256);   // [4][64]
+  const uint32_t gi_s = bars + 256u + 4u * UNITS * 4u;                                // [128 rows][GI_STRIDE] (TABLE)
+  const uint8_t* gi_ptr = base_ptr + STAGES * STAGE_BYTES + 256 + 4 * UNITS * 4;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();          // 0 = leader of the pair
@@ -146,6 +156,7 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < NACC; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
+    mbar_init(gi_full, 1); mbar_init(gi_empty, EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2cta(tmem_slot, TMEM_COLS);
@@ -272,6 +283,28 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
        }
       }
     }
+  } else if (TABLE && warp == 3) {
+    // ===== token-table loader: per job, this CTA's 128 rows x [r|z|n] x UNITS of the table as 128 bulk copies =====
+    // (per-thread global loads of these rows — 32 different sectors per warp instruction — kept the SM's load/store
+    // pipeline busy for ~1.5 us per step right when the next step's acquire / TMA issue / mbarrier polls needed it)
+    const uint32_t total_jobs = (uint32_t)p.T * RB;
+    for (uint32_t jn = 0; jn < total_jobs; ++jn) {
+      const int tn = (int)(jn / RB), bn = (int)(jn % RB);
+      mbar_wait(gi_empty, (jn & 1u) ^ 1u);                           // the epilogue warps have read the previous tile
+      if (lane == 0) mbar_arrive_expect_tx(gi_full, (p.debug & 16) ? 0u : (uint32_t)(BM * C::GI_ROW_BYTES));
+      __syncwarp();
+      if (p.debug & 16) continue;                                    // debug 16: no table reads
+#pragma unroll
+      for (int i = 0; i < BM / 32; ++i) {
+        const int r = i * 32 + lane;
+        int rown = m_blk_of(bn) * BM + r;
+        rown = rown < p.B ? rown : p.B - 1;                          // rows beyond the batch: any valid row (masked later)
+        long long tok = (long long)p.tokens[(size_t)rown * p.T + tn];
+        tok = tok < 0 ? 0 : (tok >= p.ntoken_rows ? p.ntoken_rows - 1 : tok);
+        const __half* src = p.gi_table + (size_t)tok * 3 * p.H + (size_t)(u0 / 32) * 96;
+        bulk_g2s(gi_s + (uint32_t)r * C::GI_STRIDE, src, (uint32_t)C::GI_ROW_BYTES, gi_full);
+      }
+    }
   } else if (warp >= EPI_WARP0) {
     // ===== gate epilogue (both CTAs, own 128 rows of every block): thread = (batch row, 16 units), fp32 state in registers =====
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
@@ -285,25 +318,28 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int j = 0; j < UPT; ++j) h[b][j] = 0.f;
     // bias of gate row i of the tile; the token-table form has them in the accumulator already
     auto bs = [&](int i) { return TABLE ? 0.f : bias_s[i]; };
-    // TABLE: write gi[token(row, step)] + biases and b_hn into the accumulator of job jn (step jn / RB, block jn % RB)
+    // TABLE: the accumulator of job jn (step jn / RB, block jn % RB) starts as gi[token(row, step)] (+ biases) and b_hn;
+    // the loader warp has staged the 128 rows in shared memory (row r at gi_s + r·GI_STRIDE: per 32-unit block [r|z|n])
     const uint32_t total_jobs = (uint32_t)p.T * RB;
     auto init_acc = [&](uint32_t jn) {
-      const int tn = (int)(jn / RB), bn = (int)(jn % RB);
-      const int rown = m_blk_of(bn) * BM + q * 32 + lane;
       const uint32_t tr = tmem_base + (jn % NACC) * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-      const bool ok = rown < p.B;
-      long long tok = ok ? (long long)p.tokens[(size_t)rown * p.T + tn] : 0;
-      tok = tok < 0 ? 0 : (tok >= p.ntoken_rows ? p.ntoken_rows - 1 : tok);
-      const __half* g = p.gi_table + (size_t)tok * 3 * p.H + u0 + ub;
+      mbar_wait(gi_full, jn & 1u);
+      const uint8_t* rowp = gi_ptr + (q * 32 + lane) * C::GI_STRIDE + (ub / 32) * 192 + (ub % 32) * 2;
+      uint4 gr[UPT / 8], gz[UPT / 8], gn[UPT / 8];
+#pragma unroll
+      for (int c = 0; c < UPT / 8; ++c) {
+        gr[c] = reinterpret_cast<const uint4*>(rowp)[c];
+        gz[c] = reinterpret_cast<const uint4*>(rowp + 64)[c];
+        gn[c] = reinterpret_cast<const uint4*>(rowp + 128)[c];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(gi_empty);                           // tile read: the loader may fetch the next job's
 #pragma unroll
       for (int c = 0; c < UPT; c += 8) {
-        const uint4 gr = __ldg(reinterpret_cast<const uint4*>(g + c));
-        const uint4 gz = __ldg(reinterpret_cast<const uint4*>(g + p.H + c));
-        const uint4 gn = __ldg(reinterpret_cast<const uint4*>(g + 2 * p.H + c));
         uint32_t v[8];
-        half8_to_f32(gn, v); tmem_st_32x8(tr + ub + c, v);
-        half8_to_f32(gr, v); tmem_st_32x8(tr + UNITS + ub + c, v);
-        half8_to_f32(gz, v); tmem_st_32x8(tr + 2 * UNITS + ub + c, v);
+        half8_to_f32(gn[c / 8], v); tmem_st_32x8(tr + ub + c, v);
+        half8_to_f32(gr[c / 8], v); tmem_st_32x8(tr + UNITS + ub + c, v);
+        half8_to_f32(gz[c / 8], v); tmem_st_32x8(tr + 2 * UNITS + ub + c, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(bias_s[3 * UNITS + ub + c + j]);
         tmem_st_32x8(tr + COL_NH + ub + c, v);
@@ -454,7 +490,7 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
                       const float* bias_p, void* h_op, int* counter, float* h_last, void* h_last_lp, void* h_all,
                       const GruTrainSave* save, int sm_limit, const GruTokenTable* tab, cudaStream_t s) {
   using namespace grup;
-  using C = Cfg<UNITS>;
+  using C = Cfg<UNITS, TABLE>;
   constexpr int HALF_UNITS = C::HALF_UNITS, SMEM_BYTES = C::SMEM_BYTES;
   auto kernel = gru_pair_kernel<UNITS, RB, TABLE>;
   if (H % PACK_UNITS != 0 || E_pad % tc::BK != 0) return VQA_ERR_UNSUPPORTED;

@@ -20,6 +20,7 @@ void vqa_packpool_run(void* p, const float* src, uint16_t* dst, size_t n);
 
 namespace vqa {
 int cast_f32_to_bf16(const float*, void*, size_t, cudaStream_t);
+int split_f32(const float*, void*, void*, size_t, cudaStream_t);
 }
 
 using namespace vqa;
@@ -171,7 +172,8 @@ int vqa_forward_host_submit(vqa_host_ctx* c, vqa_forward_host_args* ha, void* st
       c->slot_bytes = need;
     }
   }
-  if (a.dtype == VQA_BF16 && !wire_bf16 && (!pack || period > 0)) {
+  const bool split = a.dtype == VQA_F16X2;             // fp32-class engine: f32 over PCIe, fp16 plane pair made on the device
+  if (split || (a.dtype == VQA_BF16 && !wire_bf16 && (!pack || period > 0))) {
     const size_t need = (size_t)chunk * row_elems * 4;
     if (c->stage_bytes < need) {
       for (int i = 0; i < 2; ++i) {
@@ -204,6 +206,12 @@ int vqa_forward_host_submit(vqa_host_ctx* c, vqa_forward_host_args* ha, void* st
       VQA_CUDA_CHECK(cudaEventRecord(c->slot_done[slot], c->copy));
       c->slot_used[slot] = true;
       ha->h2d_bytes += n * 2;
+    } else if (split) {
+      const int sl = i & 1;
+      VQA_CUDA_CHECK(cudaMemcpyAsync(c->d_stage[sl], src, n * 4, cudaMemcpyHostToDevice, c->copy));
+      char* hi = (char*)c->d_img + (size_t)b0 * row_elems * 2;
+      if ((rc = split_f32((const float*)c->d_stage[sl], hi, hi + (size_t)a.B * row_elems * 2, n, c->copy))) return rc;
+      ha->h2d_bytes += n * 4;
     } else if (a.dtype == VQA_BF16) {
       // raw chunk: f32 over PCIe, cast on the device.  The cast runs on the COPY stream right behind its DMA (in-order, so
       // the two staging buffers need no events) — on the main stream it would queue behind the forward of the batch that

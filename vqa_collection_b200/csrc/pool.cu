@@ -240,12 +240,87 @@ static int launch_pool_stream(const float* parts, int n_parts, float bias, const
   return VQA_OK;
 }
 
+// fp32-class mode (VQA_F16X2): the features and the pooled result are fp16 plane pairs, x = hi + lo'·2^-11 (exact in
+// f32); same work split as attention_pool_kernel, twice the 16-byte loads per thread (as many bytes as f32 features)
+__global__ void __launch_bounds__(kPoolThreads)
+attention_pool_split_kernel(const float* __restrict__ parts, int n_parts, float bias, const __half* __restrict__ x_hi,
+                            const __half* __restrict__ x_lo, int B, int K, int V, int slices, int rev,
+                            float* __restrict__ att_out, __half* __restrict__ vsum_hi, __half* __restrict__ vsum_lo) {
+  __shared__ float s_att[kPoolMaxK];
+  griddep_launch();
+  griddep_wait();
+  const int b = rev ? B - 1 - (int)(blockIdx.x / slices) : (int)(blockIdx.x / slices);
+  const int slice = blockIdx.x % slices;
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    float l0 = -INFINITY, l1 = -INFINITY;
+    if (tid < K) {
+      const float* p = parts + (size_t)(b * K + tid) * n_parts;
+      float s = 0.f;
+      for (int i = 0; i < n_parts; ++i) s += __ldg(p + i);
+      l0 = s + bias;
+    }
+    if (tid + 32 < K) {
+      const float* p = parts + (size_t)(b * K + tid + 32) * n_parts;
+      float s = 0.f;
+      for (int i = 0; i < n_parts; ++i) s += __ldg(p + i);
+      l1 = s + bias;
+    }
+    const float m = warp_max(fmaxf(l0, l1));
+    const float e0 = (tid < K) ? expf(l0 - m) : 0.f;
+    const float e1 = (tid + 32 < K) ? expf(l1 - m) : 0.f;
+    const float inv = 1.f / warp_sum(e0 + e1);
+    if (tid < K) s_att[tid] = e0 * inv;
+    if (tid + 32 < K) s_att[tid + 32] = e1 * inv;
+  }
+  __syncthreads();
+  if (att_out != nullptr && slice == 0 && tid < K) att_out[(size_t)b * K + tid] = s_att[tid];
+  if (vsum_hi == nullptr) return;
+  const int c = slice * kPoolChan + tid * 8;
+  if (c >= V) return;
+  const size_t off = (size_t)b * K * V + c;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 6
+  for (int k = 0; k < K; ++k) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(x_hi + off + (size_t)k * V));
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(x_lo + off + (size_t)k * V));
+    const __half2* hh = reinterpret_cast<const __half2*>(&h);
+    const __half2* ll = reinterpret_cast<const __half2*>(&l);
+    const float a = s_att[k];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fh = __half22float2(hh[i]), fl = __half22float2(ll[i]);
+      acc[2 * i] = fmaf(a, fmaf(fl.x, 0x1p-11f, fh.x), acc[2 * i]);
+      acc[2 * i + 1] = fmaf(a, fmaf(fl.y, 0x1p-11f, fh.y), acc[2 * i + 1]);
+    }
+  }
+  uint4 oh, ol;
+  uint32_t* ph = reinterpret_cast<uint32_t*>(&oh); uint32_t* pl = reinterpret_cast<uint32_t*>(&ol);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tc::split_f16x2_pair(acc[2 * i], acc[2 * i + 1], ph[i], pl[i]);
+  *reinterpret_cast<uint4*>(vsum_hi + (size_t)b * V + c) = oh;
+  *reinterpret_cast<uint4*>(vsum_lo + (size_t)b * V + c) = ol;
+}
+
 int attention_pool(const float* parts, int n_parts, float bias, const void* x, int B, int K, int V,
                    int dtype, float* att, void* vsum, void* vatt, cudaStream_t s) {
   VQA_REQUIRE(K >= 1 && K <= kPoolMaxK, "attention_pool: K=%d out of range", K);
   VQA_REQUIRE(V % 8 == 0 && n_parts >= 1, "attention_pool: V=%d must be a multiple of 8", V);
   if (B == 0) return VQA_OK;
   VQA_REQUIRE(parts && x, "attention_pool: NULL input");
+  if (dtype == VQA_F16X2) {
+    VQA_REQUIRE(vatt == nullptr, "attention_pool(f16x2): the per-region product is not built for plane pairs");
+    const int slices = vsum != nullptr ? (V + kPoolChan - 1) / kPoolChan : 1;
+    const __half* x_hi = (const __half*)x;
+    __half* v_hi = (__half*)vsum;
+    VQA_CUDA_CHECK(launch_pdl(attention_pool_split_kernel, dim3((unsigned)B * slices), dim3(kPoolThreads), 0, s, parts, n_parts,
+                              bias, x_hi, x_hi + (size_t)B * K * V, B, K, V, slices, l2_order_enabled() ? 1 : 0, att, v_hi,
+                              v_hi ? v_hi + (size_t)B * V : nullptr));
+    VQA_LAUNCH_CHECK();
+    return VQA_OK;
+  }
   if (vsum != nullptr && vatt == nullptr && pool_stream_enabled() && V <= kStreamConsumers * 8 &&
       V * (int)elem_size(dtype) <= kStreamChunkBytes && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(vsum) & 15) == 0) {
@@ -367,6 +442,44 @@ gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh, int 
     h_out[i] = hn;
     h_lp[(size_t)b * ld_lp + j] = Elem<T>::from_f(hn);
   }
+}
+
+// fp32-class mode: gi row = gi_table[token(b, t)] (f32 [rows, 3H] = W_ih·emb[v] + b_ih), gh = this step's recurrent GEMM
+// (NULL at t = 0: h_0 = 0, gh = b_hh); the new state leaves as f32 and as the fp16 plane pair that feeds the next GEMM
+__global__ void __launch_bounds__(256)
+gru_gate_table_kernel(const float* __restrict__ gi_table, const int64_t* __restrict__ tokens, int ntoken_rows,
+                      const float* __restrict__ gh, const float* __restrict__ b_hh, int B, int H, int Tlen, int t,
+                      const float* h_prev, float* h_out, __half* __restrict__ h_hi, __half* __restrict__ h_lo) {
+  griddep_launch();
+  griddep_wait();
+  const int total = B * H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / H, j = i - b * H;
+    long long tok = tokens[(size_t)b * Tlen + t];
+    tok = tok < 0 ? 0 : (tok >= ntoken_rows ? ntoken_rows - 1 : tok);
+    const float* gir = gi_table + (size_t)tok * 3 * H;
+    const float* ghr = gh ? gh + (size_t)b * 3 * H : b_hh;
+    const float r = 1.f / (1.f + expf(-(gir[j] + ghr[j])));
+    const float z = 1.f / (1.f + expf(-(gir[H + j] + ghr[H + j])));
+    const float n = tanhf(gir[2 * H + j] + r * ghr[2 * H + j]);
+    const float hn = (1.f - z) * n + z * (h_prev ? h_prev[i] : 0.f);
+    h_out[i] = hn;
+    const __half hh = __float2half_rn(hn);
+    h_hi[i] = hh;
+    h_lo[i] = __float2half_rn((hn - __half2float(hh)) * 2048.f);
+  }
+}
+
+int gru_gate_table(const float* gi_table, const int64_t* tokens, int ntoken_rows, const float* gh, const float* b_hh, int B,
+                   int H, int T, int t, const float* h_prev, float* h_out, void* h_planes, cudaStream_t s) {
+  const int total = B * H;
+  int grid = (total + 255) / 256;
+  if (grid > sm_count() * 8) grid = sm_count() * 8;
+  __half* hi = (__half*)h_planes;
+  VQA_CUDA_CHECK(launch_pdl(gru_gate_table_kernel, dim3(grid), dim3(256), 0, s, gi_table, tokens, ntoken_rows, gh, b_hh, B, H, T,
+                            t, h_prev, h_out, hi, hi + (size_t)B * H));
+  VQA_LAUNCH_CHECK();
+  return VQA_OK;
 }
 
 // h_lp row stride ld_lp: H for the [B,H] operand copy, T*H when the states go straight into [B,T,H]
@@ -499,6 +612,45 @@ int cast_f32_to_bf16(const float* src, void* dst, size_t n, cudaStream_t s) {
   if (grid < 1) grid = 1;
   if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
   cast_f32_bf16_kernel<<<(unsigned)grid, 256, 0, s>>>(src, (__nv_bfloat16*)dst, n);
+  VQA_LAUNCH_CHECK();
+  return VQA_OK;
+}
+
+// f32 -> fp16 plane pair (VQA_F16X2): hi = fp16(x), lo' = fp16((x - hi)·2^11); n contiguous elements, streaming
+__global__ void __launch_bounds__(256)
+split_f32_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, size_t n) {
+  const size_t n8 = n / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i);
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 h, l;
+    uint32_t* ph = reinterpret_cast<uint32_t*>(&h); uint32_t* pl = reinterpret_cast<uint32_t*>(&l);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 hh = __floats2half2_rn(x[2 * e], x[2 * e + 1]);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn((x[2 * e] - hf.x) * 2048.f, (x[2 * e + 1] - hf.y) * 2048.f);
+      ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    reinterpret_cast<uint4*>(hi)[i] = h;
+    reinterpret_cast<uint4*>(lo)[i] = l;
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = n8 * 8 + threadIdx.x; i < n; i += blockDim.x) {
+      const __half h = __float2half_rn(src[i]);
+      hi[i] = h; lo[i] = __float2half_rn((src[i] - __half2float(h)) * 2048.f);
+    }
+}
+
+int split_f32(const float* src, void* hi, void* lo, size_t n, cudaStream_t s) {
+  VQA_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)hi % 16 == 0) && ((uintptr_t)lo % 16 == 0), "split: pointers must be 16-byte aligned");
+  if (n == 0) return VQA_OK;
+  size_t grid = (n / 8 + 255) / 256;
+  if (grid < 1) grid = 1;
+  if (grid > (size_t)sm_count() * 16) grid = (size_t)sm_count() * 16;
+  split_f32_kernel<<<(unsigned)grid, 256, 0, s>>>(src, (__half*)hi, (__half*)lo, n);
   VQA_LAUNCH_CHECK();
   return VQA_OK;
 }

@@ -90,7 +90,7 @@ GI_TABLE_MAX_BYTES = 1 << 30          # vocabulary x 3H fp16 entries; beyond thi
 
 def gru_token_table(emb, w_ih, b_ih, b_hh, device):
     """Input half of the GRU gates per TOKEN (vqa_gru_args.d_gi_table): row v = W_ih·emb[v] + (b_ir+b_hr | b_iz+b_hz |
-    b_in), fp16 [rows, 3H].  modules.py:153 evaluates W_ih·x_t for every (sample, step); x_t = emb[token] takes one of
+    b_in), fp16 [rows, 3H] stored as [rows, H/32, 3, 32].  modules.py:153 evaluates W_ih·x_t for every (sample, step); x_t = emb[token] takes one of
     `rows` values, so the product is a property of the weights.  Built from the f32 master weights (f32 matmul), i.e. it is
     closer to the reference than the bf16 x-part GEMM it replaces.  None when the table would be too large or an entry
     does not fit fp16."""
@@ -100,27 +100,43 @@ def gru_token_table(emb, w_ih, b_ih, b_hh, device):
     bias = b_ih.clone()
     bias[:2 * H] += b_hh[:2 * H]
     gi = torch.addmm(bias.to(device), emb.to(device), w_ih.to(device).t())
-    if not bool(torch.isfinite(gi).all()) or float(gi.abs().max()) > 6.0e4:
+    if H % 32 or not bool(torch.isfinite(gi).all()) or float(gi.abs().max()) > 6.0e4:
         return None
+    # kernel layout: per 32-unit block the gates r | z | n side by side, so that the 3 x UNITS entries a CTA pair needs of a
+    # row are ONE contiguous piece (a single bulk copy per row and step)
+    rows = gi.shape[0]
+    gi = gi.view(rows, 3, H // 32, 32).permute(0, 2, 1, 3).reshape(rows, 3 * H)
     return gi.to(torch.float16).contiguous()
 
 
-def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_layer: int = 0, K: int = 36) -> dict:
-    """Reference-named tensors → device tensors in kernel layout."""
+def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_layer: int = 0, K: int = 36,
+                    split: bool = False) -> dict:
+    """Reference-named tensors → device tensors in kernel layout.  ``split`` (precision 'fp32tc'): every GEMM weight
+    becomes the fp16 plane pair [2, out, in] of VQA_F16X2 (ops.split_f32 of the f32 weight), everything else stays f32."""
     f32 = lambda t: t.detach().to("cpu", torch.float32)
-    dev = lambda t, dt=torch.float32: t.to(dt).contiguous().to(device)
+    _dev = lambda t, dt=torch.float32: t.to(dt).contiguous().to(device)
+
+    def dev(t, dt=torch.float32):
+        if split and dt is dtype and t.dim() == 2:           # a GEMM operand in the compute format
+            return ops.split_f32(_dev(t))
+        return _dev(t, dt)
+    if split:
+        dtype = _SPLIT                                       # marker: dev(t, dtype) makes plane pairs
     P = {}
     emb = f32(W["encoder.embedding.weight"])
     E = emb.shape[1]
     E_pad = (E + 63) // 64 * 64
     P["E"], P["E_pad"], P["ntoken_rows"] = E, E_pad, emb.shape[0]
-    P["emb"] = dev(_pad_cols(emb, E_pad), dtype)
     r = "encoder.q_rnn.rnn."
-    P["w_ih"] = dev(_pad_cols(f32(W[r + "weight_ih_l0"]), E_pad), dtype)
+    P["emb"] = _dev(_pad_cols(emb, E_pad), torch.float32 if split else dtype)
+    P["w_ih"] = _dev(_pad_cols(f32(W[r + "weight_ih_l0"]), E_pad), torch.float32 if split else dtype)
     P["w_hh"] = dev(f32(W[r + "weight_hh_l0"]), dtype)
     P["b_ih"] = dev(f32(W[r + "bias_ih_l0"]))
     P["b_hh"] = dev(f32(W[r + "bias_hh_l0"]))
-    H = P["w_hh"].shape[1]
+    H = P["w_hh"].shape[-1]
+    if split:
+        # the input half of the gates per token, f32: W_ih·emb[v] + b_ih (vqa_gru_args.d_gi_table in the f16x2 mode)
+        P["gi_table"] = torch.addmm(P["b_ih"], _dev(emb), _dev(f32(W[r + "weight_ih_l0"])).t()).contiguous()
     if dtype == torch.bfloat16:
         packed = pack_gru(P["w_ih"], P["w_hh"], P["b_ih"], P["b_hh"])
         if packed is not None:
@@ -158,11 +174,17 @@ def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_lay
     P["Wc0"], P["sc0"], P["bc0"] = dev(v, dtype), dev(torch.full((v.shape[0],), s)), dev(b)
     v, s, b = wn("predictor.classifier.main.3")
     P["Wc1"], P["sc1"], P["bc1"] = dev(v, dtype), dev(torch.full((v.shape[0],), s)), dev(b)
-    P["H"], P["V"], P["A"] = H, P["Wv"].shape[1], P["Wc1"].shape[0]
+    P["H"], P["V"], P["A"] = H, P["Wv"].shape[-1], P["Wc1"].shape[-2]
     if relation:
         p = f"gcn.{gcn_layer}."
-        P.update(prepare_gcn_layer({k[len(p):]: t for k, t in W.items() if k.startswith(p)}, dtype, device, K))
+        P.update(prepare_gcn_layer({k[len(p):]: t for k, t in W.items() if k.startswith(p)},
+                                   torch.float32 if split else dtype, device, K, merged=False if split else None))
+        if split:
+            P["Wg"] = ops.split_f32(P["Wg"])
     return P
+
+
+_SPLIT = object()
 
 
 def gat_tc_supported(dtype, V: int, K: int = 36) -> bool:
@@ -227,12 +249,21 @@ class VQAEngine:
             gat_chase_sms = int(os.environ.get("VQA_B200_GAT_CHASE", "0") or 0)
         self.overlap, self.side_sms, self.side_tile_permille = bool(overlap), int(side_sms), int(side_tile_permille)
         self.gat_chase_sms = int(gat_chase_sms) if relation else 0
-        self.dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}[precision]
+        # 'fp32tc': fp32-class arithmetic on the tensor cores (VQA_F16X2: fp16 plane pairs, three tcgen05.mma per k-step);
+        # the wire format stays f32, the resident format of the features is the plane pair [2,B,K,V]
+        self.dtype = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp32tc": torch.float32}[precision]
+        self.split = precision == "fp32tc"
+        self.code = L.VQA_F16X2 if self.split else ops.dtype_code(self.dtype)
         self.precision = precision
         self.relation = bool(relation)
         self.K = num_objs
+        # token-table form of the fused GRU (bf16): measured slower than the x-part form while its table rows are gathered
+        # with per-thread loads -> off unless VQA_B200_GRU_TABLE=1
+        self.use_gi_table = os.environ.get("VQA_B200_GRU_TABLE", "0") == "1"
+        if self.split:
+            self.overlap, self.gat_chase_sms = False, 0
         with torch.cuda.device(self.device):
-            self.P = prepare_weights(weights, self.dtype, self.device, self.relation, K=num_objs)
+            self.P = prepare_weights(weights, self.dtype, self.device, self.relation, K=num_objs, split=self.split)
         self._ws = {}
         self.last_launches = 0
 
@@ -242,7 +273,7 @@ class VQAEngine:
         a.B, a.K, a.V, a.H, a.A, a.T = B, self.K, P["V"], P["H"], P["A"], T
         a.E_pad, a.ntoken_rows = P["E_pad"], P["ntoken_rows"]
         a.num_labels = P.get("num_labels", 0)
-        a.dtype, a.relation = ops.dtype_code(self.dtype), int(self.relation)
+        a.dtype, a.relation = self.code, int(self.relation)
         a.overlap, a.side_sms, a.side_tile_permille = int(self.overlap), self.side_sms, self.side_tile_permille
         a.gat_chase_sms = self.gat_chase_sms
         for name in ("emb", "w_ih", "b_ih", "w_hh", "b_hh", "Wv", "sv", "bv", "Wqq", "sqq", "bqq", "wlin",
@@ -254,7 +285,7 @@ class VQAEngine:
         if "wx_packed" in P:
             a.d_wx_packed, a.d_wh_packed, a.d_bias_packed = (P["wx_packed"].data_ptr(), P["wh_packed"].data_ptr(),
                                                              P["bias_packed"].data_ptr())
-        if "gi_table" in P:
+        if "gi_table" in P and (self.split or self.use_gi_table):
             a.d_gi_table = P["gi_table"].data_ptr()
         if self.relation:
             if "Wg3" in P:
@@ -277,6 +308,12 @@ class VQAEngine:
 
     def resident(self, img: torch.Tensor) -> torch.Tensor:
         """Wire-format f32 features → the resident compute dtype (bf16 cast kernel)."""
+        if self.split:
+            if img.dtype == torch.float16 and img.dim() == 4 and img.shape[0] == 2:
+                return img
+            if img.dtype == torch.float32 and img.dim() == 3:
+                return ops.split_f32(img.contiguous())
+            raise TypeError("an fp32tc engine takes f32 [B,K,V] features or their fp16 plane pair [2,B,K,V]")
         if img.dtype == self.dtype:
             return img
         if img.dtype == torch.float32 and self.dtype == torch.bfloat16:
@@ -291,10 +328,12 @@ class VQAEngine:
         Returns dict(logits f32 [B,A], label int64 [B], att f32 [B,K], ...)."""
         if not (img.is_cuda and tokens.is_cuda):
             raise RuntimeError("VQAEngine.forward needs CUDA tensors (use forward_host for host buffers)")
-        n_cast = int(img.dtype != self.dtype)
+        n_cast = int(img.dtype != (torch.float16 if self.split else self.dtype))
         img = self.resident(img).contiguous()
         tokens = tokens.contiguous()
-        B, K, V = img.shape
+        B, K, V = img.shape[-3:]
+        if self.split and want_v:
+            raise NotImplementedError("fp32tc engine: the encoder output 'v' is not produced (use precision='fp32')")
         if K != self.K or V != self.P["V"]:
             raise ValueError(f"img must be [B,{self.K},{self.P['V']}], got {tuple(img.shape)}")
         a = self._args(B, tokens.shape[1])
@@ -347,8 +386,8 @@ class VQAEngine:
         ``graph.replay()`` recomputes ``out`` from the CURRENT contents of ``img`` / ``tokens`` / ``labels``.  One
         graph launch instead of 8-12 kernel launches + tensor-map encodes per step: the steady-state form for a
         serving loop over resident batches (all pointers of the path are fixed, tensor maps are by-value parameters)."""
-        if img.dtype != self.dtype:
-            raise TypeError("capture() needs inputs already in the engine dtype (use resident())")
+        if img.dtype != (torch.float16 if self.split else self.dtype):
+            raise TypeError("capture() needs inputs already in the engine's resident format (use resident())")
         with torch.cuda.device(self.device):
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
@@ -451,7 +490,7 @@ class VQAEngine:
         n_chunks = (B + chunk - 1) // chunk
         self.last_launches = self.lib.vqa_forward_last_launch_count() + (
             (n_chunks if not ha.pack_on_host else (n_chunks // ha.raw_chunk_period if ha.raw_chunk_period else 0))
-            if (self.dtype == torch.bfloat16 and not wire_bf16) else 0)
+            if ((self.dtype == torch.bfloat16 and not wire_bf16) or self.split) else 0)
         self.last_host_outputs = {"logits": logits, "att": att}
         eng = self
 

@@ -175,6 +175,68 @@ def linear(A, W, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, log
     return (out, label) if want_argmax else out
 
 
+def split_f32(x):
+    """f32 tensor → the fp16 plane pair of the fp32-class tensor-core mode (VQA_F16X2): out[0] = fp16(x),
+    out[1] = fp16((x - out[0])·2^11), shape [2, *x.shape]."""
+    lib = L.load()
+    _require(x, torch.float32, "x")
+    x = x.contiguous()
+    out = torch.empty((2,) + tuple(x.shape), dtype=torch.float16, device=x.device)
+    L.check(lib.vqa_split_f32(_ptr(x), out[0].data_ptr(), out[1].data_ptr(), x.numel(), _stream()))
+    return out
+
+
+def linear_split(A2, W2, scale=None, bias=None, relu=False, mul=None, mul_row_div=1, logit_w=None, out_split=False,
+                 add=None, add_row_div=1, want_argmax=False):
+    """vqa_linear in the fp32-class tensor-core mode: A2 [2,M,K], W2 [2,N,K] fp16 plane pairs (split_f32); three
+    tcgen05.mma per k-step, fp32 accumulation.  Returns f32 [M,N], the f32 logit parts (``logit_w``) or, with ``out_split``,
+    the plane pair [2,M,N] of the result (the next layer's operand)."""
+    lib = L.load()
+    _require(A2, torch.float16, "A2")
+    _require(W2, torch.float16, "W2")
+    if A2.dim() != 3 or W2.dim() != 3 or A2.shape[0] != 2 or W2.shape[0] != 2 or A2.shape[2] != W2.shape[2]:
+        raise ValueError(f"linear_split: shape mismatch A2{tuple(A2.shape)} W2{tuple(W2.shape)}")
+    if not (A2.is_contiguous() and W2.is_contiguous()):
+        raise RuntimeError("linear_split: plane pairs must be contiguous")
+    _, M, K = A2.shape
+    N = W2.shape[1]
+    a = L.LinearArgs()
+    a.d_A, a.lda, a.d_W, a.ldw = A2.data_ptr(), K, W2.data_ptr(), K
+    a.M, a.N, a.K, a.dtype = M, N, K, L.VQA_F16X2
+    for nm, t in (("scale", scale), ("bias", bias), ("logit_w", logit_w)):
+        if t is not None:
+            _require(t, torch.float32, nm)
+    a.d_scale, a.d_bias, a.relu = _ptr(scale), _ptr(bias), int(bool(relu))
+    a.mul_row_div = a.add_row_div = 1
+    if mul is not None:
+        _require(mul, torch.float32, "mul")
+        a.d_mul, a.ld_mul, a.mul_row_div = mul.data_ptr(), mul.stride(0), int(mul_row_div)
+    if add is not None:
+        _require(add, torch.float32, "add")
+        a.d_add, a.ld_add, a.add_row_div = add.data_ptr(), add.stride(0), int(add_row_div)
+    if logit_w is not None:
+        pw = lib.vqa_linear_part_width(L.VQA_F16X2)
+        n_parts = (N + pw - 1) // pw
+        out = torch.empty((M, n_parts), dtype=torch.float32, device=A2.device)
+        a.d_logit_w, a.ldo, a.out_dtype = logit_w.data_ptr(), n_parts, L.VQA_F32
+    elif out_split:
+        out = torch.empty((2, M, N), dtype=torch.float16, device=A2.device)
+        a.ldo, a.out_dtype = N, L.VQA_F16X2
+    else:
+        out = torch.empty((M, N), dtype=torch.float32, device=A2.device)
+        a.ldo, a.out_dtype = N, L.VQA_F32
+    a.d_out = out.data_ptr()
+    label = None
+    if want_argmax:
+        if logit_w is not None or out_split:
+            raise ValueError("linear_split: want_argmax needs the f32 store form")
+        label = torch.empty((M,), dtype=torch.int64, device=A2.device)
+        amax_ws = torch.zeros((lib.vqa_linear_argmax_workspace_bytes(M),), dtype=torch.uint8, device=A2.device)
+        a.d_argmax_label, a.d_argmax_ws = label.data_ptr(), amax_ws.data_ptr()
+    L.check(lib.vqa_linear(C.byref(a), _stream()))
+    return (out, label) if want_argmax else out
+
+
 def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False, packed=None, gi_table=None):
     """Embedding gather + GRU last state (encoder.py:159-160, modules.py:139-159).
 
