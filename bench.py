@@ -486,8 +486,11 @@ def kernel_rooflines(ctx, args, eng, imgs, toks, labs, relation):
     out = []
     # question GRU: T steps of [B,E_pad+H] x [3H, E_pad+H] (the embedding gather and the counter memset are separate launches)
     ms = time_kernel(lambda i: ops.gru_last_state(toks[i % NB], P["emb"], P["w_ih"], P["b_ih"], P["w_hh"], P["b_hh"],
-                                                  packed=(P["wx_packed"], P["wh_packed"], P["bias_packed"])), reps)
-    out.append(entry("gru", "gru_pair_kernel (persistent GRU, 14 steps, tcgen05 cta_group::2; + gather + memset launches)",
+                                                  packed=(P["wx_packed"], P["wh_packed"], P["bias_packed"]),
+                                                  gi_table=P.get("gi_table") if eng.use_gi_table else None), reps)
+    out.append(entry("gru", "gru_pair_kernel (persistent GRU, 14 steps, tcgen05 cta_group::2, token-table form; + memset)"
+                     if (eng.use_gi_table and "gi_table" in P) else
+                     "gru_pair_kernel (persistent GRU, 14 steps, tcgen05 cta_group::2; + gather + memset launches)",
                      "tensor", ms, 2.0 * B * T * 3 * H * (E + H) - 2.0 * B * 3 * H * H, 1e12))
     ms = time_kernel(lambda i: ops.linear(imgs[i % NB].view(B * K, V), P["Wv"], P["sv"], P["bv"], relu=True, mul=qq,
                                           mul_row_div=K, logit_w=P["wlin"]), reps)

@@ -61,6 +61,7 @@ int add_inplace(void*, const void*, size_t, int, cudaStream_t);
 int attention_pool(const float*, int, float, const void*, int, int, int, int, float*, void*, void*, cudaStream_t);
 int argmax_rows(const float*, int, int, int, int64_t*, cudaStream_t);
 int split_f32(const float*, void*, void*, size_t, cudaStream_t);
+int linear_tc_gru_step(const GruStepSplit&, cudaStream_t);
 int gru_gate_table(const float*, const int64_t*, int, const float*, const float*, int, int, int, int, const float*, float*, void*,
                    cudaStream_t);
 int embedding_gather(const int64_t*, int, int, int, int, const void*, void*, cudaStream_t, void* zero_ptr = nullptr,
@@ -154,7 +155,6 @@ static bool gru_pair_enabled() {
   return pair != 0;
 }
 
-// sm_limit > 0: the persistent kernel may use at most that many SMs (vqa_forward's overlap mode)
 // fp32-class mode (VQA_F16X2): token table for the input half (f32 [rows, 3H] = W_ih·emb[v] + b_ih), per step one split
 // GEMM h·W_hhᵀ + b_hh (three tcgen05.mma per k-step) and the gate kernel, which writes the state as f32 and as the fp16
 // plane pair that is the next GEMM's operand.  h_0 = 0: the first step has no GEMM.
@@ -171,22 +171,43 @@ static int gru_last_state_split(const vqa_gru_args& a, cudaStream_t s) {
   const size_t tail_bytes = (a.workspace_bytes - need.bytes) / 16 * 16;
   if (tail_bytes) VQA_CUDA_CHECK(cudaMemsetAsync(tail, 0, tail_bytes, s));
   int rc;
-  for (int t = 0; t < a.T; ++t) {
+  // the state's plane pair ping-pongs between two buffers ([2][2][B][H]: h_lp and h_op are adjacent in the workspace): a
+  // step's CTAs read ALL units of their rows as the A operand while other CTAs already write the new state of theirs
+  char* planes4 = (char*)w.h_lp;
+  const size_t pair_bytes = (size_t)a.B * a.H * 4;
+  VQA_REQUIRE((char*)w.h_op == planes4 + pair_bytes, "vqa_gru_last_state(f16x2): workspace layout");
+  auto planes_of = [&](int t) { return (void*)(planes4 + (size_t)(t & 1) * pair_bytes); };
+  // step 0: h_0 = 0, no GEMM
+  {
+    const bool last = a.T == 1;
+    if ((rc = gru_gate_table((const float*)a.d_gi_table, a.d_tokens, a.ntoken_rows, nullptr, a.d_b_hh, a.B, a.H, a.T, 0, nullptr,
+                             last ? a.d_h_last : w.h, (last && a.d_h_last_lp) ? a.d_h_last_lp : planes_of(0), s))) return rc;
+    if (last) return VQA_OK;
+  }
+  if (a.d_wh_packed != nullptr && a.H % 64 == 0) {
+    // packed W_hh planes: GEMM + gates in one kernel, all steps in one launch when every tile has its own CTA pair
+    GruStepSplit g{};
+    g.B = a.B; g.T = a.T; g.t = 1; g.t_end = a.T; g.H = a.H; g.ntoken_rows = a.ntoken_rows;
+    g.tokens = a.d_tokens; g.gi_table = (const float*)a.d_gi_table; g.b_hh = a.d_b_hh;
+    g.wh_packed_planes = a.d_wh_packed; g.h_planes = planes4; g.h_planes_last = a.d_h_last_lp;
+    g.h = w.h; g.h_out_last = a.d_h_last; g.counter = w.counter;
+    rc = linear_tc_gru_step(g, s);
+    if (rc != VQA_ERR_UNSUPPORTED) return rc;
+  }
+  for (int t = 1; t < a.T; ++t) {                                   // no CTA pairs on this device: two kernels per step
     const bool last = (t == a.T - 1);
-    if (t > 0) {
-      vqa_linear_args gh{};
-      gh.d_A = w.h_lp; gh.lda = a.H; gh.d_W = a.d_w_hh; gh.ldw = a.H;
-      gh.M = a.B; gh.N = 3 * a.H; gh.K = a.H; gh.dtype = VQA_F16X2;
-      gh.d_bias = a.d_b_hh; gh.d_out = w.gh; gh.ldo = 3 * a.H; gh.out_dtype = VQA_F32; gh.mul_row_div = 1;
-      if ((rc = linear_dispatch(gh, s))) return rc;
-    }
-    void* planes = (last && a.d_h_last_lp) ? a.d_h_last_lp : w.h_lp;
-    if ((rc = gru_gate_table((const float*)a.d_gi_table, a.d_tokens, a.ntoken_rows, t > 0 ? w.gh : nullptr, a.d_b_hh, a.B, a.H,
-                             a.T, t, t > 0 ? w.h : nullptr, last ? a.d_h_last : w.h, planes, s))) return rc;
+    vqa_linear_args gh{};
+    gh.d_A = planes_of(t - 1); gh.lda = a.H; gh.d_W = a.d_w_hh; gh.ldw = a.H;
+    gh.M = a.B; gh.N = 3 * a.H; gh.K = a.H; gh.dtype = VQA_F16X2;
+    gh.d_bias = a.d_b_hh; gh.d_out = w.gh; gh.ldo = 3 * a.H; gh.out_dtype = VQA_F32; gh.mul_row_div = 1;
+    if ((rc = linear_dispatch(gh, s))) return rc;
+    if ((rc = gru_gate_table((const float*)a.d_gi_table, a.d_tokens, a.ntoken_rows, w.gh, a.d_b_hh, a.B, a.H, a.T, t, w.h,
+                             last ? a.d_h_last : w.h, (last && a.d_h_last_lp) ? a.d_h_last_lp : planes_of(t), s))) return rc;
   }
   return VQA_OK;
 }
 
+// sm_limit > 0: the persistent kernel may use at most that many SMs (vqa_forward's overlap mode)
 static int gru_last_state(const vqa_gru_args& a, cudaStream_t s, int sm_limit = 0) {
   if (a.dtype == VQA_F16X2) return gru_last_state_split(a, s);
   VQA_REQUIRE(((a.d_tokens && a.d_emb) || a.d_x) && a.d_w_ih && a.d_w_hh && a.d_b_ih && a.d_b_hh &&

@@ -145,6 +145,17 @@ __device__ __forceinline__ float warp_max(float v) {
 // token-table form of the question encoder (gru_pair.cu): gi_table fp16 [ntoken_rows, 3H]; zero_after_counter = bytes
 // behind the GRU's 256-byte counter block that the call clears together with the counters
 struct GruTokenTable { const void* gi_table; const int64_t* tokens; int ntoken_rows; size_t zero_after_counter; };
+// steps [t, t_end) of the fp32-class (VQA_F16X2) GRU, GEMM + gate update fused (gemm_tc.cu)
+struct GruStepSplit {
+  int B, T, t, t_end, H, ntoken_rows;
+  const int64_t* tokens; const float* gi_table; const float* b_hh;
+  const void* wh_packed_planes;             // [2][3H][H] fp16, gate-interleaved 192-row blocks (engine.pack_gru)
+  void* h_planes;                           // [2 buffers][2 planes][B][H] fp16: step t reads buffer (t-1)&1, writes t&1
+  void* h_planes_last;                      // where step T-1 writes its plane pair instead (or NULL)
+  float* h;                                 // f32 [B,H], updated in place
+  float* h_out_last;                        // where step T-1 writes the f32 state instead (or NULL)
+  int* counter;                             // >= ceil(B/128) ints (one launch for all steps) or NULL
+};
 struct GruTrainSave { float *R, *Z, *N, *HN, *Hs; };      // f32 [T,B,H] each; Hs slot t = state after step t
 int linear_simt(const vqa_linear_args& a, cudaStream_t s);
 int linear_tc(const vqa_linear_args& a, cudaStream_t s);

@@ -46,7 +46,7 @@ template <int BN, bool PAIR = false, bool SPLIT = false> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;                // one plane
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = SPLIT ? (PAIR ? 3 : (BN >= 192 ? 2 : (BN >= 128 ? 3 : 4)))
+  static constexpr int STAGES = SPLIT ? (PAIR ? (BN >= 192 ? 3 : (BN >= 128 ? 4 : 5)) : (BN >= 192 ? 2 : (BN >= 128 ? 3 : 4)))
                                       : (PAIR ? 6 : (BN >= 256 ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8))));
   static constexpr int TILE_COLS = PLANES * BN;              // TMEM columns of one tile: [main | correction]
   static constexpr int NACC = (2 * TILE_COLS <= 512) ? 2 : 1;
@@ -67,6 +67,16 @@ struct Params {
   const float* logit_w;
   void* out; int ldo; int out_bf16; int n_parts;
   int out_split; size_t out_plane;            // fp16 plane pair: lo' plane out_plane bytes behind the hi plane
+  // GRU step epilogue (template GRU; fp32-class mode): the tile's 192 columns are [r | z | n] x 64 units of h·W_hhᵀ
+  // (gate-interleaved packed W_hh); gi = gru_table[token(row, t)] (f32 [rows, 3H], b_ih folded in), torch gate order
+  // One launch runs steps [gru_t, gru_t_end): step t reads the state's plane pair from buffer (t-1)&1 of the 3-D map tmA
+  // ([2 buffers x 2 planes][B][H]) and writes buffer t&1 (the last step of the sequence: gru_planes_last / gru_hout_last
+  // when given); the f32 state gru_h is updated in place.  With more than one step per launch every CTA is co-resident and
+  // a finished tile bumps gru_counter[its 128-row block] (zero on entry); a step's loads wait until all tiles of the
+  // previous step of their row block have arrived (release / acquire + fence.proxy.async, as in gru_pair.cu).
+  const long long* gru_tokens; const float* gru_table; const float* gru_bhh;
+  float* gru_h; float* gru_hout_last; void* gru_planes; void* gru_planes_last; int* gru_counter;
+  int gru_T, gru_t, gru_t_end, gru_H, gru_rows;
   int tiles_m, tiles_n;
   int tile_begin, tile_end;                  // this launch walks tiles [tile_begin, tile_end) of the tile order
   float leaky_slope; int add_after_act; int sigmoid;
@@ -80,7 +90,7 @@ struct Params {
 };
 
 // ---- the kernel ----------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, bool PAIR = false, bool SPLIT = false>
+template <int BN, bool A_MN, bool B_MN, bool PAIR = false, bool SPLIT = false, bool GRU = false>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const Params p) {
@@ -135,19 +145,32 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      for (int gt = GRU ? p.gru_t : 0; gt < (GRU ? p.gru_t_end : 1); ++gt)
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile_m(tile), n_blk = tile % p.tiles_n;
+        if constexpr (GRU) {
+          if (p.gru_counter != nullptr && gt > p.gru_t) {      // h_{t-1}[rows of this CTA, :] comes from tiles_n CTAs
+            const int target = (gt - p.gru_t) * p.tiles_n;
+            while (ld_acquire_gpu(p.gru_counter + m_blk) < target) { }
+            fence_proxy_async_all();
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::PLANES * C::A_BYTES;
           if constexpr (PAIR) {                      // both CTAs fill their own slots; bytes are counted on the leader's barrier
             if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-            tma_load_2d_2cta(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
-            tma_load_2d_2cta(sb, &tmW, full_bar(stage), kb * BK, n_blk * BN + (int)crank * (BN / 2));
-            if constexpr (SPLIT) {
-              tma_load_2d_2cta(sa + C::A_BYTES, &tmA2, full_bar(stage), kb * BK, m_blk * BM);
-              tma_load_2d_2cta(sb + C::B_BYTES, &tmW2, full_bar(stage), kb * BK, n_blk * BN + (int)crank * (BN / 2));
+            if constexpr (GRU) {                     // tmA: [2 buffers x 2 planes][B][H]
+              const int z = ((gt - 1) & 1) * 2;
+              tma_load_3d_2cta(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, z);
+              tma_load_3d_2cta(sa + C::A_BYTES, &tmA, full_bar(stage), kb * BK, m_blk * BM, z + 1);
+            } else {
+              tma_load_2d_2cta(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM);
+              if constexpr (SPLIT) tma_load_2d_2cta(sa + C::A_BYTES, &tmA2, full_bar(stage), kb * BK, m_blk * BM);
             }
+            tma_load_2d_2cta(sb, &tmW, full_bar(stage), kb * BK, n_blk * BN + (int)crank * (BN / 2));
+            if constexpr (SPLIT)
+              tma_load_2d_2cta(sb + C::B_BYTES, &tmW2, full_bar(stage), kb * BK, n_blk * BN + (int)crank * (BN / 2));
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -181,6 +204,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                  (A_MN ? IDESC_A_MN_MAJOR : 0u) | (B_MN ? IDESC_B_MN_MAJOR : 0u);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      for (int gt = GRU ? p.gru_t : 0; gt < (GRU ? p.gru_t_end : 1); ++gt)
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tcgen05_fence_after();
@@ -236,6 +260,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127
     int acc = 0; uint32_t acc_phase = 0;
     int pbuf = 0;
+    for (int gt = GRU ? p.gru_t : 0; gt < (GRU ? p.gru_t_end : 1); ++gt)
     for (int tile = tile0; tile < num_tiles; tile += tile_step, pbuf ^= 1) {
       const int m_blk = tile_m(tile), n_blk = tile % p.tiles_n;
       const int n0 = n_blk * BN;
@@ -246,7 +271,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n = n0 + c;
         const bool ok = n < p.N;
         ps[c] = (ok && p.scale) ? p.scale[n] : 1.f;
-        ps[BN + c] = (ok && p.bias) ? p.bias[n] : 0.f;
+        if constexpr (GRU) ps[BN + c] = p.gru_bhh[(c / 64) * p.gru_H + n_blk * 64 + (c % 64)];   // column c = gate c/64, unit c%64
+        else ps[BN + c] = (ok && p.bias) ? p.bias[n] : 0.f;
         ps[2 * BN + c] = (ok && p.logit_w) ? p.logit_w[n] : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -255,6 +281,85 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       const int row = m_blk * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
+      if constexpr (GRU) {
+        // ---- GRU step (modules.py:153, torch GRU semantics): r = σ(gi_r + gh_r), z = σ(gi_z + gh_z),
+        //      n = tanh(gi_n + r·gh_n), h' = (1 - z)·n + z·h; gh = this tile's accumulators + b_hh
+        static_assert(SPLIT && BN == 192, "GRU step: 64 units x [r|z|n] per tile, fp32-class mode");
+        const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+        const int H = p.gru_H, u0 = n_blk * 64;
+        long long tok = row_ok ? p.gru_tokens[(size_t)row * p.gru_T + gt] : 0;
+        tok = tok < 0 ? 0 : (tok >= p.gru_rows ? p.gru_rows - 1 : tok);
+        const float* gi = p.gru_table + (size_t)tok * 3 * H + u0;
+        const float* hp = p.gru_h + (size_t)(row_ok ? row : 0) * H + u0;
+        const bool final_step = gt == p.gru_T - 1;
+        float* h_dst = (final_step && p.gru_hout_last) ? p.gru_hout_last : p.gru_h;
+        char* pl_dst = (final_step && p.gru_planes_last) ? reinterpret_cast<char*>(p.gru_planes_last)
+                                                         : reinterpret_cast<char*>(p.gru_planes) + (size_t)(gt & 1) * 2 * p.out_plane;
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t mr[16], cr[16], mz[16], cz[16], mn[16], cn[16];
+          tmem_ld_32x16(t_row + c, mr);        tmem_ld_32x16(t_row + BN + c, cr);
+          tmem_ld_32x16(t_row + 64 + c, mz);   tmem_ld_32x16(t_row + BN + 64 + c, cz);
+          tmem_ld_32x16(t_row + 128 + c, mn);  tmem_ld_32x16(t_row + BN + 128 + c, cn);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          float hn[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 gr4 = __ldg(reinterpret_cast<const float4*>(gi + c) + j4);
+            const float4 gz4 = __ldg(reinterpret_cast<const float4*>(gi + H + c) + j4);
+            const float4 gn4 = __ldg(reinterpret_cast<const float4*>(gi + 2 * H + c) + j4);
+            const float4 hp4 = *(reinterpret_cast<const float4*>(hp + c) + j4);
+            const float gir[4] = {gr4.x, gr4.y, gr4.z, gr4.w}, giz[4] = {gz4.x, gz4.y, gz4.z, gz4.w};
+            const float gin[4] = {gn4.x, gn4.y, gn4.z, gn4.w}, hpv[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * j4 + e;
+              const float ghr = fmaf(__uint_as_float(cr[j]), 0x1p-11f, __uint_as_float(mr[j])) + ps[BN + c + j];
+              const float ghz = fmaf(__uint_as_float(cz[j]), 0x1p-11f, __uint_as_float(mz[j])) + ps[BN + 64 + c + j];
+              const float ghn = fmaf(__uint_as_float(cn[j]), 0x1p-11f, __uint_as_float(mn[j])) + ps[BN + 128 + c + j];
+              const float r = 1.f / (1.f + expf(-(gir[e] + ghr)));
+              const float z = 1.f / (1.f + expf(-(giz[e] + ghz)));
+              const float n = tanhf(gin[e] + r * ghn);
+              hn[j] = (1.f - z) * n + z * hpv[e];
+            }
+          }
+          float* ho = h_dst + (size_t)row * H + u0 + c;
+          __half* oh = reinterpret_cast<__half*>(pl_dst) + (size_t)row * H + u0 + c;
+          __half* ol = reinterpret_cast<__half*>(pl_dst + p.out_plane) + (size_t)row * H + u0 + c;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4)
+            reinterpret_cast<float4*>(ho)[j4] = make_float4(hn[4 * j4], hn[4 * j4 + 1], hn[4 * j4 + 2], hn[4 * j4 + 3]);
+#pragma unroll
+          for (int j8 = 0; j8 < 2; ++j8) {
+            uint4 rh, rl;
+            uint32_t* ph = reinterpret_cast<uint32_t*>(&rh); uint32_t* pl = reinterpret_cast<uint32_t*>(&rl);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_f16x2_pair(hn[8 * j8 + 2 * e], hn[8 * j8 + 2 * e + 1], ph[e], pl[e]);
+            reinterpret_cast<uint4*>(oh)[j8] = rh;
+            reinterpret_cast<uint4*>(ol)[j8] = rl;
+          }
+        }
+        tcgen05_fence_before();
+        if constexpr (PAIR) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+        } else {
+          mbar_arrive(tempty_bar(acc));
+        }
+        if (p.gru_counter != nullptr && gt + 1 < p.gru_t_end) {
+          // publish this tile's part of h_t (see gru_pair.cu: the release of the one thread that bumps the counter is
+          // cumulative over the stores it observed through the barrier; TMA reads the planes, hence the proxy fence)
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            __threadfence();
+            fence_proxy_async_all();
+            red_release_gpu_add(p.gru_counter + m_blk, 1);
+          }
+        }
+        if (++acc == C::NACC) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       const float* mul_row = p.mul ? p.mul + (size_t)((row_ok ? row : 0) / p.mul_row_div) * p.ld_mul : nullptr;
       const bool mul_vec = p.mul && ((p.ld_mul & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mul) & 15) == 0);
       const float* add_row = p.add ? p.add + (size_t)((row_ok ? row : 0) / p.add_row_div) * p.ld_add : nullptr;
@@ -408,7 +513,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       if (p.logit_w && row_ok) reinterpret_cast<float*>(p.out)[(size_t)row * p.n_parts + n_blk] = part;
-      if constexpr (!PAIR) {
+      {
         if (p.amax_keys) {
           // Row maxima of the tiles of one row block meet in a 64-bit atomicMax: the high word orders like the float
           // (+0 = -0), the low word is ~n, so among equal values the LOWEST column wins (torch.max's rule).  The tile
@@ -577,9 +682,8 @@ static int launch(const vqa_linear_args& a, cudaStream_t s) {
 // 256 x 256 tiles on CTA pairs (tcgen05 cta_group::2) for the large K-major GEMMs.  VQA_ERR_UNSUPPORTED = the device cannot
 // hold the pairs (or VQA_B200_GEMM_PAIR=0): the caller falls back to one CTA per tile.
 // how many CTA pairs of the 256 x 256 kernel the current device holds at once (0 = pairs unusable)
-template <bool SPLIT>
+template <bool SPLIT, int BN = 256>
 static int pairs_resident_on_device() {
-  constexpr int BN = 256;
   using C = Cfg<BN, true, SPLIT>;
   auto kern = linear_tc_kernel<BN, false, false, true, SPLIT>;
   static DeviceInt cache;
@@ -602,12 +706,11 @@ static int pairs_resident_on_device() {
   return pairs_resident;
 }
 
-template <bool SPLIT>
+template <bool SPLIT, int BN = 256>
 static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
-  constexpr int BN = 256;
   using C = Cfg<BN, true, SPLIT>;
   auto kern = linear_tc_kernel<BN, false, false, true, SPLIT>;
-  const int pairs_resident = pairs_resident_on_device<SPLIT>();
+  const int pairs_resident = pairs_resident_on_device<SPLIT, BN>();
   if (pairs_resident <= 0) return VQA_ERR_UNSUPPORTED;
   CUtensorMap tmA, tmW, tmA2, tmW2;
   int rc;
@@ -630,6 +733,12 @@ static int launch_pair(const vqa_linear_args& a, cudaStream_t s) {
   p.leaky_slope = a.leaky_slope; p.add_after_act = a.add_after_act; p.sigmoid = a.sigmoid;
   p.amax_keys = nullptr; p.amax_cnt = nullptr; p.amax_label = nullptr;
   p.progress = a.d_progress;
+  if (a.d_argmax_label) {
+    VQA_REQUIRE(a.d_argmax_ws && !a.d_logit_w, "vqa_linear: fused argmax needs its zeroed workspace and the store form");
+    p.amax_keys = (unsigned long long*)a.d_argmax_ws;
+    p.amax_cnt = (int*)((char*)a.d_argmax_ws + align_up((size_t)a.M * 8, 256));
+    p.amax_label = (long long*)a.d_argmax_label;
+  }
   tile_range(a, ((p.tiles_m + 1) / 2) * p.tiles_n, &p.tile_begin, &p.tile_end);
   const int pair_tiles = p.tile_end - p.tile_begin;
   if (pair_tiles <= 0) return VQA_OK;
@@ -682,6 +791,25 @@ static int launch_split(const vqa_linear_args& a, cudaStream_t s) {
     const int rc = launch_pair<true>(a, s);
     if (rc != VQA_ERR_UNSUPPORTED) return rc;
   }
+  // Small-M layers (one wave): a stage of the split form is two planes of both operands, so a single CTA holds only 2-4
+  // stages and the MMAs wait for TMA (measured: the 3129-way classifier at 49 us against 19 us of MMA time).  On CTA pairs
+  // a CTA stages half of the W tile — 3 to 5 stages — at the same number of busy SMs: the narrowest tile whose pair tiles
+  // still fit the device in one wave.
+  static int small_pairs = -1;
+  if (small_pairs < 0) { const char* e = getenv("VQA_B200_SPLIT_SMALL_PAIR"); small_pairs = (e && e[0] == '0') ? 0 : 1; }
+  const int tiles_m = (a.M + BM - 1) / BM;
+  if (small_pairs && !pl.pair && tiles_m >= 2 && !a.d_progress && !a.d_logit_w &&      // (logit parts are 256 columns wide) a.tile_begin == 0 && a.tile_end == 0 && a.cta_limit == 0) {
+    const int mp = (tiles_m + 1) / 2;
+    const int cap = pairs_resident_on_device<true, 64>();
+    int rc = VQA_ERR_UNSUPPORTED;
+    if (cap > 0) {
+      if (mp * ((a.N + 63) / 64) <= cap) rc = launch_pair<true, 64>(a, s);
+      else if (mp * ((a.N + 127) / 128) <= cap) rc = launch_pair<true, 128>(a, s);
+      else if (mp * ((a.N + 191) / 192) <= cap) rc = launch_pair<true, 192>(a, s);
+      else if (mp * ((a.N + 255) / 256) <= cap) rc = launch_pair<true, 256>(a, s);
+    }
+    if (rc != VQA_ERR_UNSUPPORTED) return rc;
+  }
   switch (pl.bn) {
     case 256: return launch<256, false, false, true>(a, s);
     case 192: return launch<192, false, false, true>(a, s);
@@ -709,7 +837,84 @@ static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
   }
 }
 
+// One step of the fp32-class GRU as ONE kernel: h_{t-1}·W_hhᵀ on CTA pairs (256 x 192 tiles of the gate-interleaved
+// packed W_hh: 64 units x [r|z|n]) with the gate update as the epilogue.  VQA_ERR_UNSUPPORTED when the device cannot hold
+// the pairs (the caller then runs the GEMM and the gate kernel separately).
+static int gru_step_split(const GruStepSplit& g, cudaStream_t s) {
+  constexpr int BN = 192;
+  using C = Cfg<BN, true, true>;
+  auto kern = linear_tc_kernel<BN, false, false, true, true, true>;
+  static DeviceInt cache;
+  int& pairs_resident = cache.at(current_device());
+  if (pairs_resident < 0) {
+    pairs_resident = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * (sm_count() / 2)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, (const void*)kern, &cfg) == cudaSuccess) pairs_resident = n;
+    }
+    (void)cudaGetLastError();
+  }
+  if (pairs_resident <= 0 || g.H % 64 != 0) return VQA_ERR_UNSUPPORTED;
+  CUtensorMap tmA, tmW, tmW2;
+  int rc;
+  const size_t a_plane = (size_t)g.B * g.H * 2, w_plane = (size_t)3 * g.H * g.H * 2;
+  {
+    const long long dims[3] = {g.H, g.B, 4}, strides[2] = {2LL * g.H, 2LL * g.H * g.B};
+    const int box[3] = {BK, BM, 1};
+    if ((rc = make_tensor_map_bf16_nd(&tmA, g.h_planes, 3, dims, strides, box))) return rc;
+  }
+  if ((rc = make_tensor_map_bf16(&tmW, g.wh_packed_planes, 3 * g.H, g.H, g.H, BN / 2))) return rc;
+  if ((rc = make_tensor_map_bf16(&tmW2, (const char*)g.wh_packed_planes + w_plane, 3 * g.H, g.H, g.H, BN / 2))) return rc;
+  Params p{};
+  p.M = g.B; p.N = 3 * g.H; p.K = g.H;
+  p.mul_row_div = 1; p.add_row_div = 1;
+  p.ldo = g.H; p.out_split = 1; p.out_plane = a_plane;
+  p.tiles_m = (g.B + BM - 1) / BM; p.tiles_n = 3 * g.H / BN; p.n_parts = p.tiles_n;
+  p.gru_tokens = (const long long*)g.tokens; p.gru_table = g.gi_table; p.gru_bhh = g.b_hh; p.gru_h = g.h;
+  p.gru_hout_last = g.h_out_last; p.gru_planes = g.h_planes; p.gru_planes_last = g.h_planes_last;
+  p.gru_T = g.T; p.gru_H = g.H; p.gru_rows = g.ntoken_rows;
+  p.tile_begin = 0; p.tile_end = ((p.tiles_m + 1) / 2) * p.tiles_n;
+  // every tile on its own CTA pair, all of them resident: ONE launch for all steps, steps chained by the row-block
+  // counters (VQA_B200_GRU_SPLIT_PERSIST=0: one launch per step).  Otherwise one launch per step.
+  static int persist_env = -1;
+  if (persist_env < 0) {                     // Nsight Compute cannot launch a cooperative cluster kernel: per-step launches there
+    const char* e = getenv("VQA_B200_GRU_SPLIT_PERSIST");
+    persist_env = e ? ((e[0] == '0') ? 0 : 1) : (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ? 0 : 1);
+  }
+  const bool persist = persist_env && p.tile_end <= pairs_resident && g.counter != nullptr && p.tiles_m <= 64 && g.t_end - g.t > 1;
+  const int pairs = p.tile_end < pairs_resident ? p.tile_end : pairs_resident;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  if (persist) {
+    VQA_CUDA_CHECK(cudaMemsetAsync(g.counter, 0, sizeof(int) * p.tiles_m, s));
+    p.gru_counter = g.counter; p.gru_t = g.t; p.gru_t_end = g.t_end;
+    at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;      // the runtime checks co-residency
+    cfg.numAttrs = 2;
+    VQA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmA, tmW2, p));
+    VQA_LAUNCH_CHECK();
+    return VQA_OK;
+  }
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  for (int t = g.t; t < g.t_end; ++t) {
+    p.gru_counter = nullptr; p.gru_t = t; p.gru_t_end = t + 1;
+    VQA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, tmA, tmW2, p));
+    VQA_LAUNCH_CHECK();
+  }
+  return VQA_OK;
+}
+
 }  // namespace tc
+
+int linear_tc_gru_step(const GruStepSplit& g, cudaStream_t s) { return tc::gru_step_split(g, s); }
 
 int linear_tc_part_width() { return 256; }
 

@@ -135,6 +135,11 @@ def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_lay
     P["b_hh"] = dev(f32(W[r + "bias_hh_l0"]))
     H = P["w_hh"].shape[-1]
     if split:
+        # gate-interleaved W_hh planes: 192-row block j = [r | z | n] rows of units [64j, 64j+64), one GEMM tile per block, so
+        # the gate update can be the step GEMM's epilogue
+        if H % 64 == 0:
+            w_hh32 = f32(W[r + "weight_hh_l0"])
+            P["wh_packed"] = ops.split_f32(_dev(pack_gru(w_hh32, w_hh32, P["b_ih"].cpu(), P["b_hh"].cpu())[1]))
         # the input half of the gates per token, f32: W_ih·emb[v] + b_ih (vqa_gru_args.d_gi_table in the f16x2 mode)
         P["gi_table"] = torch.addmm(P["b_ih"], _dev(emb), _dev(f32(W[r + "weight_ih_l0"])).t()).contiguous()
     if dtype == torch.bfloat16:
@@ -257,9 +262,8 @@ class VQAEngine:
         self.precision = precision
         self.relation = bool(relation)
         self.K = num_objs
-        # token-table form of the fused GRU (bf16): measured slower than the x-part form while its table rows are gathered
-        # with per-thread loads -> off unless VQA_B200_GRU_TABLE=1
-        self.use_gi_table = os.environ.get("VQA_B200_GRU_TABLE", "0") == "1"
+        # token-table form of the fused GRU (bf16): on unless VQA_B200_GRU_TABLE=0
+        self.use_gi_table = os.environ.get("VQA_B200_GRU_TABLE", "1") != "0"
         if self.split:
             self.overlap, self.gat_chase_sms = False, 0
         with torch.cuda.device(self.device):
@@ -282,9 +286,9 @@ class VQAEngine:
         a.b_lin = P["b_lin"]
         if P["att_concat"]:
             a.att_concat, a.d_W1q, a.d_b1 = 1, P["W1q"].data_ptr(), P["b1"].data_ptr()
-        if "wx_packed" in P:
-            a.d_wx_packed, a.d_wh_packed, a.d_bias_packed = (P["wx_packed"].data_ptr(), P["wh_packed"].data_ptr(),
-                                                             P["bias_packed"].data_ptr())
+        for name in ("wx_packed", "wh_packed", "bias_packed"):
+            if name in P:
+                setattr(a, "d_" + name, P[name].data_ptr())
         if "gi_table" in P and (self.split or self.use_gi_table):
             a.d_gi_table = P["gi_table"].data_ptr()
         if self.relation:
