@@ -798,7 +798,7 @@ static int launch_split(const vqa_linear_args& a, cudaStream_t s) {
   static int small_pairs = -1;
   if (small_pairs < 0) { const char* e = getenv("VQA_B200_SPLIT_SMALL_PAIR"); small_pairs = (e && e[0] == '0') ? 0 : 1; }
   const int tiles_m = (a.M + BM - 1) / BM;
-  if (small_pairs && !pl.pair && tiles_m >= 2 && !a.d_progress && !a.d_logit_w &&      // (logit parts are 256 columns wide) a.tile_begin == 0 && a.tile_end == 0 && a.cta_limit == 0) {
+  if (small_pairs && !pl.pair && tiles_m >= 2 && !a.d_progress && !a.d_logit_w /* logit parts are 256 wide */ && a.tile_begin == 0 && a.tile_end == 0 && a.cta_limit == 0) {
     const int mp = (tiles_m + 1) / 2;
     const int cap = pairs_resident_on_device<true, 64>();
     int rc = VQA_ERR_UNSUPPORTED;
