@@ -294,6 +294,32 @@ def test_wrapper_forward_vqa_routes_host_batches_through_host_path():
         pkg.set_precision("fp32")
 
 
+def test_wrapper_forward_vqa_fp32tc_gives_the_reference_answers():
+    """set_precision('fp32tc'): Wrapper.forward_vqa (device and host batches) on the tensor-core fp32-class engine returns
+    exactly the fp32 oracle's answers and scores; module-level calls outside the engine run the fp32 kernels"""
+    import vqa_collection_b200 as pkg
+    from test_gpu_modules import build_model
+    pkg.set_precision("fp32tc")
+    try:
+        for cfg, B in ((O.FULL, 200), (O.FULL_REGAT, 70)):
+            W = O.make_weights(cfg, 1111)
+            batch = O.make_batch(cfg, B, 56)
+            with torch.no_grad():
+                ref_logits, _ = O.forward(batch, W, cfg)
+            ref_label = ref_logits.max(1)[1]
+            m = build_model(cfg, W)
+            assert m.engine().split
+            with torch.no_grad():
+                s_dev, l_dev, _ = m.forward_vqa({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()})
+                s_h, l_h, _ = m.forward_vqa(batch)
+                predict, v_att = m.get_att({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in batch.items()})
+            assert torch.equal(l_dev.cpu(), ref_label) and torch.equal(l_h.cpu(), ref_label)
+            assert torch.equal(s_dev, s_h)
+            assert float((predict.float().cpu() - ref_logits).abs().max() / ref_logits.abs().max()) < 1e-5
+    finally:
+        pkg.set_precision("fp32")
+
+
 def test_fused_adamax_invalidates_the_forward_weight_caches():
     """The fused Adamax writes parameters through raw pointers; it must bump their versions, or forward_vqa keeps serving
     the bf16 copies of the OLD weights after a training epoch (train.py:63-80 evaluates every epoch)."""

@@ -53,7 +53,8 @@ def test_single_cta_and_no_pdl_paths_match_default(tmp_path):
         assert np.abs(got["logits"] - oracle_logits.numpy()).max() / scale < 1e-2, name
         # same arithmetic in the same order: the variants differ in who loads what, not in what is summed — except the
         # single-CTA GRU, which keeps W_in·x + W_hn·h in one accumulator column and recovers W_hn·h as a difference (the
-        # pair kernel accumulates it in a column of its own): bf16-class differences in the question state
+        # pair kernel accumulates it in a column of its own) and has no token-table form (bf16 x-part GEMM instead of the
+        # fp16 table of W_ih·emb[v]): bf16-class differences in the question state
         tol = 1e-2 if name == "gru_single" else 1e-3
         assert np.abs(got["logits"] - ref["logits"]).max() / scale < tol, name
         assert np.abs(got["att"] - ref["att"]).max() < tol, name

@@ -666,8 +666,9 @@ static SideCtx* side_ctx() {
 // per GRU step (two interleaved row blocks on 64 SMs) + 70 us (fork, gather, [W_q;q_net] on 64 SMs) — measured at H = 1024:
 // 300 per mille is the best split of the wide ReGAT projection at B = 1024 (profiles/r02_overlap_split.md); the engine
 // can override the estimate (side_tile_permille).
-static int auto_side_permille(int tiles, int K, int T, int main_sms, int side_sms) {
-  const double tau = 12.5 * K / 2048.0, G = 15.7 * T + 70.0;
+static int auto_side_permille(int tiles, int K, int T, int main_sms, int side_sms, bool token_table) {
+  // token-table GRU (no gather, no x-part): 186 instead of 232 us beside the GEMM at T = 14
+  const double tau = 12.5 * K / 2048.0, G = token_table ? 13.3 * T + 64.0 : 15.7 * T + 70.0;
   const double pt = main_sms / 2, ps = side_sms / 2;
   const double t_end = (tiles * tau + ps * G) / (pt + ps);
   double share = ps * (t_end - G) / tau / tiles;
@@ -750,7 +751,7 @@ int vqa_forward(const vqa_forward_args* args, void* stream) {
   if (overlap) {
     const int tiles = linear_tc_tile_count(proj);
     int permille = a.side_tile_permille;
-    if (permille == 0) permille = auto_side_permille(tiles, a.V, a.T, main_sms, side_sms);
+    if (permille == 0) permille = auto_side_permille(tiles, a.V, a.T, main_sms, side_sms, a.d_gi_table != nullptr);
     if (permille < 0) permille = 0;
     if (permille > 900) permille = 900;
     split_tile = tiles - (int)((long long)tiles * permille / 1000);

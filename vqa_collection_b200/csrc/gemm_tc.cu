@@ -90,8 +90,13 @@ struct Params {
 };
 
 // ---- the kernel ----------------------------------------------------------------
+// GRU step form: 8 epilogue warps (the gate update with its table gathers and precise exp / tanh is 3-4x the work of a
+// linear epilogue): warp w handles TMEM lane quarter w % 4 and units [32·((w-4)/4), +32) of the tile
+constexpr int GRU_EPI_WARPS = 8;
+constexpr int GRU_THREADS = EPI_WARP0 * 32 + GRU_EPI_WARPS * 32;
+
 template <int BN, bool A_MN, bool B_MN, bool PAIR = false, bool SPLIT = false, bool GRU = false>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(GRU ? GRU_THREADS : THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmW2, const Params p) {
   static_assert(!PAIR || (!A_MN && !B_MN), "CTA pairs are built for the K-major forward form");
@@ -129,7 +134,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     // accumulator release: 128 epilogue threads, or (PAIR) one arrive per epilogue warp of both CTAs on the leader's barrier
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 8 : 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), GRU ? 2 * GRU_EPI_WARPS : (PAIR ? 8 : 128)); }
     fence_barrier_init();
   }
   if (warp == 2) { if constexpr (PAIR) tmem_alloc_2cta(tmem_slot, C::TMEM_COLS); else tmem_alloc(tmem_slot, C::TMEM_COLS); }
@@ -256,8 +261,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= EPI_WARP0) {
     // ===== epilogue =====
-    const int q = warp - EPI_WARP0;                  // == warp % 4: TMEM lane quarter
-    const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127
+    constexpr int EPI_THREADS_K = GRU ? GRU_EPI_WARPS * 32 : 128;
+    const int q = (warp - EPI_WARP0) & 3;            // == warp % 4: TMEM lane quarter
+    const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127 (GRU: 0..255)
     int acc = 0; uint32_t acc_phase = 0;
     int pbuf = 0;
     for (int gt = GRU ? p.gru_t : 0; gt < (GRU ? p.gru_t_end : 1); ++gt)
@@ -267,7 +273,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // stage this tile's per-column parameters; double buffered by tile parity (not by accumulator: a single-buffered
       // accumulator would let a fast warp overwrite what a slow one still reads; the barrier below orders buffer reuse)
       float* ps = params_smem + pbuf * 3 * BN;
-      for (int c = et; c < BN; c += 128) {
+      for (int c = et; c < BN; c += EPI_THREADS_K) {
         const int n = n0 + c;
         const bool ok = n < p.N;
         ps[c] = (ok && p.scale) ? p.scale[n] : 1.f;
@@ -275,7 +281,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         else ps[BN + c] = (ok && p.bias) ? p.bias[n] : 0.f;
         ps[2 * BN + c] = (ok && p.logit_w) ? p.logit_w[n] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if constexpr (GRU) {
+        // the table row of this step does not depend on the GEMM: pull this thread's 3 x 32 entries into L2 while the
+        // main loop runs (the table is hundreds of MB, its rows are scattered: an HBM round trip per chunk otherwise)
+        const int prow = m_blk * BM + ((warp - EPI_WARP0) & 3) * 32 + lane;
+        if (prow < p.M) {
+          long long ptok = p.gru_tokens[(size_t)prow * p.gru_T + gt];
+          ptok = ptok < 0 ? 0 : (ptok >= p.gru_rows ? p.gru_rows - 1 : ptok);
+          const float* pg = p.gru_table + (size_t)ptok * 3 * p.gru_H + n_blk * 64 + ((warp - EPI_WARP0) >> 2) * 32;
+#pragma unroll
+          for (int gate = 0; gate < 3; ++gate)
+#pragma unroll
+            for (int sct = 0; sct < 4; ++sct) asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + gate * p.gru_H + sct * 8));
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS_K) : "memory");
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 
@@ -295,8 +315,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float* h_dst = (final_step && p.gru_hout_last) ? p.gru_hout_last : p.gru_h;
         char* pl_dst = (final_step && p.gru_planes_last) ? reinterpret_cast<char*>(p.gru_planes_last)
                                                          : reinterpret_cast<char*>(p.gru_planes) + (size_t)(gt & 1) * 2 * p.out_plane;
+        const int c_begin = ((warp - EPI_WARP0) >> 2) * (64 / (GRU_EPI_WARPS / 4));
 #pragma unroll 1
-        for (int c = 0; c < 64; c += 16) {
+        for (int c = c_begin; c < c_begin + 64 / (GRU_EPI_WARPS / 4); c += 16) {
           uint32_t mr[16], cr[16], mz[16], cz[16], mn[16], cn[16];
           tmem_ld_32x16(t_row + c, mr);        tmem_ld_32x16(t_row + BN + c, cr);
           tmem_ld_32x16(t_row + 64 + c, mz);   tmem_ld_32x16(t_row + BN + 64 + c, cz);
@@ -350,7 +371,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.gru_counter != nullptr && gt + 1 < p.gru_t_end) {
           // publish this tile's part of h_t (see gru_pair.cu: the release of the one thread that bumps the counter is
           // cumulative over the stores it observed through the barrier; TMA reads the planes, hence the proxy fence)
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS_K) : "memory");
           if (et == 0) {
             __threadfence();
             fence_proxy_async_all();
@@ -850,7 +871,7 @@ static int gru_step_split(const GruStepSplit& g, cudaStream_t s) {
     pairs_resident = 0;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) == cudaSuccess) {
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(2 * (sm_count() / 2)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES;
+      cfg.gridDim = dim3(2 * (sm_count() / 2)); cfg.blockDim = dim3(GRU_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
@@ -889,7 +910,7 @@ static int gru_step_split(const GruStepSplit& g, cudaStream_t s) {
   const bool persist = persist_env && p.tile_end <= pairs_resident && g.counter != nullptr && p.tiles_m <= 64 && g.t_end - g.t > 1;
   const int pairs = p.tile_end < pairs_resident ? p.tile_end : pairs_resident;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
+  cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GRU_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;

@@ -625,9 +625,8 @@ int gru_pair(const void* X, int B, int T, int H, int E_pad, const void* wx_p, co
     else if (!save && row_pairs >= 2 && ctas(64, 2) <= budget) cfg = 642;   // half the SMs: two interleaved row blocks
     else cfg = 641;                                           // several launches
   }
-  // token-table form: 64-unit tiles only (measured: 137 vs 143 us at 64x1, slower than the x-part form at 32 units, where
-  // a CTA issues as many bulk copies per step for half the work) — otherwise the caller gathers and takes the x-part form
-  if (tab && cfg / 10 != 64) return VQA_ERR_UNSUPPORTED;
+  // (the token-table form runs on every tile shape: a 128-question shard of an 8-GPU job takes 32-unit tiles and must
+  // reproduce its rows of the unsharded batch bit for bit, so the arithmetic may not depend on the tile choice)
 #define VQA_GRU_CALL(U, R) (tab ? gru_pair_t<U, R, true>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, sm_limit, tab, s) \
                                 : gru_pair_t<U, R, false>(X, B, T, H, E_pad, wx_p, wh_p, bias_p, h_op, counter, h_last, h_last_lp, h_all, save, sm_limit, tab, s))
   switch (cfg) {

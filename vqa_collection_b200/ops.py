@@ -237,6 +237,46 @@ def linear_split(A2, W2, scale=None, bias=None, relu=False, mul=None, mul_row_di
     return (out, label) if want_argmax else out
 
 
+def attention_pool_split(parts, bias, x2, want_att=True):
+    """softmax over the K regions + attention-weighted feature sum in the fp32-class mode: x2 = fp16 plane pair [2,B,K,V];
+    returns (att f32 [B,K] or None, the pooled features as a plane pair [2,B,V])"""
+    lib = L.load()
+    _require(parts, torch.float32, "parts")
+    _require(x2, torch.float16, "x2")
+    _, B, K, V = x2.shape
+    att = torch.empty((B, K), dtype=torch.float32, device=x2.device) if want_att else None
+    vsum = torch.empty((2, B, V), dtype=torch.float16, device=x2.device)
+    L.check(lib.vqa_attention_pool(_ptr(parts), parts.shape[1], float(bias), x2.data_ptr(), B, K, V, L.VQA_F16X2,
+                                   _ptr(att), vsum.data_ptr(), None, _stream()))
+    return att, vsum
+
+
+def gru_last_state_split(tokens, gi_table, w_hh2, b_hh, wh_packed2=None):
+    """Question encoder in the fp32-class mode (VQA_F16X2): tokens int64 [B,T]; gi_table f32 [rows, 3H] = W_ih·emb[v] + b_ih;
+    w_hh2 the plane pair [2,3H,H] of W_hh (wh_packed2: the same in the gate-interleaved packing -> GEMM + gate update in
+    one kernel, all steps in one launch).  Returns the last state, f32 [B,H]."""
+    lib = L.load()
+    _require(tokens, torch.int64, "tokens")
+    _require(gi_table, torch.float32, "gi_table")
+    _require(w_hh2, torch.float16, "w_hh2")
+    _require(b_hh, torch.float32, "b_hh")
+    B, T = tokens.shape
+    H = w_hh2.shape[-1]
+    ws_bytes = lib.vqa_gru_workspace_bytes(B, T, H, 64, L.VQA_F16X2)
+    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=tokens.device)
+    h = torch.empty((B, H), dtype=torch.float32, device=tokens.device)
+    a = L.GruArgs()
+    a.d_tokens, a.B, a.T, a.H, a.E_pad, a.ntoken_rows, a.dtype = tokens.data_ptr(), B, T, H, 64, gi_table.shape[0], L.VQA_F16X2
+    a.d_gi_table, a.d_w_hh, a.d_b_hh = gi_table.data_ptr(), w_hh2.data_ptr(), b_hh.data_ptr()
+    if wh_packed2 is not None:
+        _require(wh_packed2, torch.float16, "wh_packed2")
+        a.d_wh_packed = wh_packed2.data_ptr()
+    a.d_workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+    a.d_h_last = h.data_ptr()
+    L.check(lib.vqa_gru_last_state(C.byref(a), _stream()))
+    return h
+
+
 def gru_last_state(tokens, emb, w_ih, b_ih, w_hh, b_hh, want_lp=False, packed=None, gi_table=None):
     """Embedding gather + GRU last state (encoder.py:159-160, modules.py:139-159).
 
