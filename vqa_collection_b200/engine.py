@@ -88,6 +88,13 @@ def pack_gru(w_ih, w_hh, b_ih, b_hh, units: int = 64):
 GI_TABLE_MAX_BYTES = 1 << 30          # vocabulary x 3H fp16 entries; beyond this the x-part GEMM stays
 
 
+def _token_table_f32(emb, w_ih, bias, device):
+    """emb [rows,E] · w_ih[3H,E]ᵀ + bias in f32 on the device, with the library's own fp32 GEMM (vqa_linear, FFMA)"""
+    E_pad = (emb.shape[1] + 15) // 16 * 16
+    to = lambda t: _pad_cols(t.detach().float().cpu(), E_pad).contiguous().to(device)
+    return ops.linear(to(emb), to(w_ih), None, bias.detach().float().contiguous().to(device), out_dtype=torch.float32)
+
+
 def gru_token_table(emb, w_ih, b_ih, b_hh, device):
     """Input half of the GRU gates per TOKEN (vqa_gru_args.d_gi_table): row v = W_ih·emb[v] + (b_ir+b_hr | b_iz+b_hz |
     b_in), fp16 [rows, 3H] stored as [rows, H/32, 3, 32].  modules.py:153 evaluates W_ih·x_t for every (sample, step); x_t = emb[token] takes one of
@@ -95,11 +102,11 @@ def gru_token_table(emb, w_ih, b_ih, b_hh, device):
     closer to the reference than the bf16 x-part GEMM it replaces.  None when the table would be too large or an entry
     does not fit fp16."""
     H = w_ih.shape[0] // 3
-    if emb.shape[0] * 3 * H * 2 > GI_TABLE_MAX_BYTES:
-        return None
+    if emb.shape[0] * 3 * H * 2 > GI_TABLE_MAX_BYTES or torch.device(device).type != "cuda":
+        return None                                          # (host-side layout checks prepare weights on the CPU)
     bias = b_ih.clone()
     bias[:2 * H] += b_hh[:2 * H]
-    gi = torch.addmm(bias.to(device), emb.to(device), w_ih.to(device).t())
+    gi = _token_table_f32(emb, w_ih, bias, device)
     if H % 32 or not bool(torch.isfinite(gi).all()) or float(gi.abs().max()) > 6.0e4:
         return None
     # kernel layout: per 32-unit block the gates r | z | n side by side, so that the 3 x UNITS entries a CTA pair needs of a
@@ -141,7 +148,7 @@ def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_lay
             w_hh32 = f32(W[r + "weight_hh_l0"])
             P["wh_packed"] = ops.split_f32(_dev(pack_gru(w_hh32, w_hh32, P["b_ih"].cpu(), P["b_hh"].cpu())[1]))
         # the input half of the gates per token, f32: W_ih·emb[v] + b_ih (vqa_gru_args.d_gi_table in the f16x2 mode)
-        P["gi_table"] = torch.addmm(P["b_ih"], _dev(emb), _dev(f32(W[r + "weight_ih_l0"])).t()).contiguous()
+        P["gi_table"] = _token_table_f32(emb, f32(W[r + "weight_ih_l0"]), P["b_ih"], device)
     if dtype == torch.bfloat16:
         packed = pack_gru(P["w_ih"], P["w_hh"], P["b_ih"], P["b_hh"])
         if packed is not None:
