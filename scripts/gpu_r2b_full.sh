@@ -2,7 +2,7 @@
 # full GPU suite + smoke + bench (1 GPU)
 mkdir -p gpurun_out
 export PYTHONDONTWRITEBYTECODE=1
-timeout 1500 python -m pytest -q --timeout=600 --timeout-method=thread -p no:cacheprovider tests -m gpu -x > gpurun_out/tests_full.log 2>&1
+timeout 1500 python -m pytest -q --timeout=600 --timeout-method=thread -p no:cacheprovider tests -m gpu > gpurun_out/tests_full.log 2>&1
 echo "tests rc=$?"; tail -8 gpurun_out/tests_full.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 900 python bench.py --steps 100 --warmup 10 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench rc=$?"

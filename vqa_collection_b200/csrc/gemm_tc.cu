@@ -156,7 +156,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (GRU) {
           if (p.gru_counter != nullptr && gt > p.gru_t) {      // h_{t-1}[rows of this CTA, :] comes from tiles_n CTAs
             const int target = (gt - p.gru_t) * p.tiles_n;
-            while (ld_acquire_gpu(p.gru_counter + m_blk) < target) { }
+            unsigned int polls = 0;
+            unsigned long long t0 = 0;
+            while (ld_acquire_gpu(p.gru_counter + m_blk) < target) {
+              if ((++polls & 0xFFFu) == 0) {             // a counter that never arrives must not hang the device: trap after 2 s
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 2000000000ull) __trap();
+              }
+            }
             fence_proxy_async_all();
           }
         }
@@ -907,7 +916,7 @@ static int gru_step_split(const GruStepSplit& g, cudaStream_t s) {
     const char* e = getenv("VQA_B200_GRU_SPLIT_PERSIST");
     persist_env = e ? ((e[0] == '0') ? 0 : 1) : (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ? 0 : 1);
   }
-  const bool persist = persist_env && p.tile_end <= pairs_resident && g.counter != nullptr && p.tiles_m <= 64 && g.t_end - g.t > 1;
+  const bool persist = persist_env && p.tile_end <= pairs_resident && g.counter != nullptr && p.tiles_m <= 62 && g.t_end - g.t > 1;
   const int pairs = p.tile_end < pairs_resident ? p.tile_end : pairs_resident;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GRU_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
@@ -915,7 +924,9 @@ static int gru_step_split(const GruStepSplit& g, cudaStream_t s) {
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   if (persist) {
-    VQA_CUDA_CHECK(cudaMemsetAsync(g.counter, 0, sizeof(int) * p.tiles_m, s));
+    // one counter per 128-row block of every PAIR: with an odd number of row blocks the last pair's second CTA has no
+    // rows of its own but still polls and bumps its counter
+    VQA_CUDA_CHECK(cudaMemsetAsync(g.counter, 0, sizeof(int) * 2 * ((p.tiles_m + 1) / 2), s));
     p.gru_counter = g.counter; p.gru_t = g.t; p.gru_t_end = g.t_end;
     at[1].id = cudaLaunchAttributeCooperative; at[1].val.cooperative = 1;      // the runtime checks co-residency
     cfg.numAttrs = 2;
