@@ -548,7 +548,9 @@ def kernel_rooflines_split(ctx, args, eng, imgs, toks):
     alg = 2.0 * B * K * H * V
     out.append({"kernel": "linear_tc_kernel<256,pair,split> (W_v projection on fp16 plane pairs + x Qp + logit reduction)",
                 "bound": "tensor", "achieved": 3 * alg / (ms / 1e3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": 3 * alg / (ms / 1e3) / 1e12 / pk["bf16_tflops"], "traffic": None,
+                "frac": 3 * alg / (ms / 1e3) / 1e12 / pk["bf16_tflops"], "traffic": 321.9e6 * B / 1024,
+                "traffic_source": "profiles/r02b_ncu_wv_split.md (315.8 MB read + 6.1 MB written at B = 1024; algorithmic: 302 MB of "
+                                  "feature planes + 8 MB of weight planes)",
                 "peak_source": pk["src"] + " burst, f16 = bf16 rate (kernel timed alone)", "launch_ms": ms,
                 "flops_per_launch": 3 * alg, "algorithmic_flops_per_launch": alg,
                 "note": "achieved counts the three MMAs per k-step that the split arithmetic issues"})
@@ -556,7 +558,8 @@ def kernel_rooflines_split(ctx, args, eng, imgs, toks):
     alg = 2.0 * B * (T - 1) * 3 * H * H
     out.append({"kernel": "gru_gate_table_kernel + linear_tc_kernel<192,pair,split,gru> (13 recurrent steps in one cooperative launch)",
                 "bound": "tensor", "achieved": 3 * alg / (ms / 1e3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": 3 * alg / (ms / 1e3) / 1e12 / pk["bf16_tflops"], "traffic": None,
+                "frac": 3 * alg / (ms / 1e3) / 1e12 / pk["bf16_tflops"], "traffic": 13 * 33.5e6 * B / 1024,
+                "traffic_source": "profiles/r02b_ncu_gru_split.md (33.5 MB per step: token-table rows, W_hh planes, state; 13 steps)",
                 "peak_source": pk["src"] + " burst (kernels timed alone)", "launch_ms": ms,
                 "flops_per_launch": 3 * alg, "algorithmic_flops_per_launch": alg})
     parts = torch.rand((B * K, 4), device=dev)
@@ -564,7 +567,8 @@ def kernel_rooflines_split(ctx, args, eng, imgs, toks):
     byts = float(B * K * V * 4 + B * V * 4 + B * K * 4 * 5)
     out.append({"kernel": "attention_pool_split_kernel (softmax over 36 regions + attention-weighted sum of the plane pair)",
                 "bound": "hbm", "achieved": byts / (ms / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": byts / (ms / 1e3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                "frac": byts / (ms / 1e3) / 1e9 / pk["hbm_gbs"], "traffic": 308.6e6 * B / 1024,
+                "traffic_source": "profiles/r02b_ncu_pool_split.md",
                 "peak_source": pk["src"] + " burst (kernel timed alone)", "launch_ms": ms, "bytes_per_launch": byts})
     return out
 
