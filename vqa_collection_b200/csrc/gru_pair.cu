@@ -98,6 +98,7 @@ struct Params {
   const __half* gi_table;
   const int64_t* tokens;        // [B,T]
   int ntoken_rows;
+  unsigned gi_pause_ns;         // pause between the loader warp's bursts of 32 row copies (VQA_B200_GRU_GI_PAUSE, ns)
 };
 
 __device__ __forceinline__ void half8_to_f32(const uint4& v, uint32_t (&o)[8]) {
@@ -296,6 +297,9 @@ gru_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (p.debug & 16) continue;                                    // debug 16: no table reads
 #pragma unroll
       for (int i = 0; i < BM / 32; ++i) {
+        // the copies are needed a whole step from now: issue them in 4 bursts of 32 with pauses in between, so that the
+        // TMA unit takes the next step's h / W tile loads (the critical path) between the bursts instead of behind all 128
+        if (i > 0 && p.gi_pause_ns > 0) __nanosleep(p.gi_pause_ns);
         const int r = i * 32 + lane;
         int rown = m_blk_of(bn) * BM + r;
         rown = rown < p.B ? rown : p.B - 1;                          // rows beyond the batch: any valid row (masked later)
@@ -559,6 +563,9 @@ static int gru_pair_t(const void* X, int B, int T, int H, int E_pad, const void*
     p.gi_table = TABLE ? (const __half*)tab->gi_table : nullptr;
     p.tokens = TABLE ? tab->tokens + (size_t)b0 * T : nullptr;
     p.ntoken_rows = TABLE ? tab->ntoken_rows : 0;
+    static int pause = -1;
+    if (pause < 0) { const char* e = getenv("VQA_B200_GRU_GI_PAUSE"); pause = e ? atoi(e) : 0; }
+    p.gi_pause_ns = (unsigned)pause;
     p.B = Bc; p.T = T; p.H = H; p.E_pad = E_pad; p.tiles_n = tiles_n; p.num_ctas = 2 * groups * tiles_n;
     p.bias = bias_p; p.h_op[0] = h0; p.h_op[1] = h1;
     p.h_last = h_last ? h_last + (size_t)b0 * H : nullptr;
