@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VQA_B200_ABI_VERSION 10
+#define VQA_B200_ABI_VERSION 11
 
 typedef enum {
   VQA_OK = 0,
