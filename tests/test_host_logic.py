@@ -522,3 +522,49 @@ def test_bench_reference_arm_json_contract():
     rg = line["regat"]
     assert rg["value"] > 0 and rg["config"]["workload"].startswith("ReGAT") and rg["cpu_baseline"]["kind"] == cb["kind"]
     assert line["e2e"] == {"value": line["value"], "unit": "questions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_fp16_plane_pair_format_and_three_product_rule():
+    """The number format of precision 'fp32tc' (VQA_F16X2), restated in numpy: x = hi + lo'·2^-11 with hi = fp16(x),
+    lo' = fp16((x - hi)·2^11).  (1) the pair carries >= 21 significant bits wherever hi is a normal fp16 number, and never
+    loses the residual to fp16's subnormals (which an unscaled residual does); (2) the three products the kernels issue —
+    hi·hi + 2^-11 (hi·lo' + lo'·hi), summed in fp32 — match a float64 dot product to fp32-sum accuracy, two orders of
+    magnitude closer than the bf16 operands of the default mode; (3) the token table of the GRU is an exact regrouping of
+    W_ih·x_t + b_ih (gather of a GEMM == GEMM of a gather)."""
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(200000) * np.logspace(-4, 3, 200000)).astype(np.float32)
+    hi = x.astype(np.float16)
+    lo = ((x - hi.astype(np.float32)) * np.float32(2048.0)).astype(np.float16)
+    back = hi.astype(np.float64) + lo.astype(np.float64) / 2048.0
+    normal = np.abs(x) > 6.2e-5
+    rel = np.abs(back - x.astype(np.float64))[normal] / np.abs(x.astype(np.float64))[normal]
+    assert rel.max() < 2.0 ** -21
+    lo_unscaled = (x - hi.astype(np.float32)).astype(np.float16)                 # what the scale factor avoids
+    back_u = hi.astype(np.float64) + lo_unscaled.astype(np.float64)
+    small = normal & (np.abs(x) < 1e-2)
+    assert (np.abs(back_u - x)[small] / np.abs(x)[small]).max() > 16 * rel[np.abs(x[normal]) < 1e-2].max()
+    # three-product rule on a GEMM of the path's depth
+    K, M, N = 2048, 64, 48
+    A = np.maximum(rng.standard_normal((M, K)), 0).astype(np.float32)           # post-ReLU activations
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+
+    def split(t):
+        h = t.astype(np.float16)
+        return h.astype(np.float32), ((t - h.astype(np.float32)) * np.float32(2048.0)).astype(np.float16).astype(np.float32)
+    ah, al = split(A)
+    wh, wl = split(W)
+    got = (ah @ wh.T) + (ah @ wl.T + al @ wh.T) * np.float32(2.0 ** -11)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T
+    scale = np.abs(ref).max()
+    e_split = np.abs(got - ref).max() / scale
+    e_f32 = np.abs(A @ W.T - ref).max() / scale
+    bf = lambda t: torch.from_numpy(t).to(torch.bfloat16).float().numpy()
+    e_bf16 = np.abs(bf(A) @ bf(W).T - ref).max() / scale
+    assert e_split < 4 * max(e_f32, 2e-7) and e_split < 1e-6 and e_bf16 > 100 * e_split
+    # token table: W_ih·emb[token] + b == (emb·W_ihᵀ + b)[token]
+    emb = rng.standard_normal((50, 24)).astype(np.float32)
+    w_ih = rng.standard_normal((36, 24)).astype(np.float32)
+    b = rng.standard_normal(36).astype(np.float32)
+    tok = rng.integers(0, 50, (7, 5))
+    table = emb @ w_ih.T + b
+    assert np.array_equal(table[tok], (emb[tok].reshape(-1, 24) @ w_ih.T + b).reshape(7, 5, 36))
