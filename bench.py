@@ -711,7 +711,7 @@ def main():
     line = {
         "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.precision if args.precision == "bf16" else "f32",
+        "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "fp32": "f32", "fp32tc": "f16x2 (fp16 plane pairs, fp32-class)"}[args.precision],
         "data": "synthetic", "config": r["config"],
     }
     for k in ("clocks", "e2e", "e2e_bf16_host_cache", "gpu_launches", "launches_per_step", "launch_mode", "schedule",

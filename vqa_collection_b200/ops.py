@@ -655,6 +655,7 @@ def _on_tensor_device(fn):
 for _name in ("relation_labels", "cast_to_bf16", "cast_to_f32", "linear", "gru_last_state", "gru_sequence",
               "lstm_sequence", "caption_gate_scale", "seq_max", "softmax_mul", "attention_logits", "gru_cell",
               "lstm_cell", "caption_decode_steps", "attention_pool", "graph_attention", "graph_attention_merged",
-              "add_", "answer_scores", "argmax_rows"):
+              "add_", "answer_scores", "argmax_rows", "split_f32", "linear_split", "attention_pool_split",
+              "gru_last_state_split"):
     globals()[_name] = _on_tensor_device(globals()[_name])
 del _name
