@@ -184,8 +184,8 @@ static int gru_last_state_split(const vqa_gru_args& a, cudaStream_t s) {
                              last ? a.d_h_last : w.h, (last && a.d_h_last_lp) ? a.d_h_last_lp : planes_of(0), s))) return rc;
     if (last) return VQA_OK;
   }
-  if (a.d_wh_packed != nullptr && a.H % 64 == 0) {
-    // packed W_hh planes: GEMM + gates in one kernel, all steps in one launch when every tile has its own CTA pair
+  if (a.d_wh_packed != nullptr && a.H % 32 == 0) {
+    // packed W_hh planes (32-unit blocks): GEMM + gates in one kernel, all steps in one launch when the tiles fit the device
     GruStepSplit g{};
     g.B = a.B; g.T = a.T; g.t = 1; g.t_end = a.T; g.H = a.H; g.ntoken_rows = a.ntoken_rows;
     g.tokens = a.d_tokens; g.gi_table = (const float*)a.d_gi_table; g.b_hh = a.d_b_hh;

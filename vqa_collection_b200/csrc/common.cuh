@@ -149,7 +149,7 @@ struct GruTokenTable { const void* gi_table; const int64_t* tokens; int ntoken_r
 struct GruStepSplit {
   int B, T, t, t_end, H, ntoken_rows;
   const int64_t* tokens; const float* gi_table; const float* b_hh;
-  const void* wh_packed_planes;             // [2][3H][H] fp16, gate-interleaved 192-row blocks (engine.pack_gru)
+  const void* wh_packed_planes;             // [2][3H][H] fp16, gate-interleaved 96-row blocks: [r|z|n] x 32 units (engine.pack_gru(units=32))
   void* h_planes;                           // [2 buffers][2 planes][B][H] fp16: step t reads buffer (t-1)&1, writes t&1
   void* h_planes_last;                      // where step T-1 writes its plane pair instead (or NULL)
   float* h;                                 // f32 [B,H], updated in place

@@ -46,7 +46,7 @@ template <int BN, bool PAIR = false, bool SPLIT = false> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;                // one plane
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = SPLIT ? (PAIR ? (BN >= 192 ? 3 : (BN >= 128 ? 4 : 5)) : (BN >= 192 ? 2 : (BN >= 128 ? 3 : 4)))
+  static constexpr int STAGES = SPLIT ? (PAIR ? (BN >= 192 ? 3 : (BN >= 96 ? 4 : 5)) : (BN >= 192 ? 2 : (BN >= 128 ? 3 : 4)))
                                       : (PAIR ? 6 : (BN >= 256 ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8))));
   static constexpr int TILE_COLS = PLANES * BN;              // TMEM columns of one tile: [main | correction]
   static constexpr int NACC = (2 * TILE_COLS <= 512) ? 2 : 1;
@@ -77,6 +77,8 @@ struct Params {
   const long long* gru_tokens; const float* gru_table; const float* gru_bhh;
   float* gru_h; float* gru_hout_last; void* gru_planes; void* gru_planes_last; int* gru_counter;
   int gru_T, gru_t, gru_t_end, gru_H, gru_rows;
+  int gru_debug;   // VQA_B200_GRUS_DEBUG, timing experiments only (results wrong): 1 = no MMAs, 2 = no wait for h_{t-1},
+                   // 4 = no gate arithmetic / table reads / stores, 8 = no TMA loads
   int tiles_m, tiles_n;
   int tile_begin, tile_end;                  // this launch walks tiles [tile_begin, tile_end) of the tile order
   float leaky_slope; int add_after_act; int sigmoid;
@@ -154,7 +156,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile_m(tile), n_blk = tile % p.tiles_n;
         if constexpr (GRU) {
-          if (p.gru_counter != nullptr && gt > p.gru_t) {      // h_{t-1}[rows of this CTA, :] comes from tiles_n CTAs
+          if (p.gru_counter != nullptr && gt > p.gru_t && !(p.gru_debug & 2)) {      // h_{t-1}[rows of this CTA, :] comes from tiles_n CTAs
             const int target = (gt - p.gru_t) * p.tiles_n;
             unsigned int polls = 0;
             unsigned long long t0 = 0;
@@ -173,6 +175,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = base + stage * C::STAGE_BYTES, sb = sa + C::PLANES * C::A_BYTES;
           if constexpr (PAIR) {                      // both CTAs fill their own slots; bytes are counted on the leader's barrier
+            if constexpr (GRU) {
+              if (p.gru_debug & 8) {                 // timing experiment: no loads
+                if (lead) mbar_arrive_expect_tx(full_bar(stage), 0u);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                continue;
+              }
+            }
             if (lead) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
             if constexpr (GRU) {                     // tmA: [2 buffers x 2 planes][B][H]
               const int z = ((gt - 1) & 1) * 2;
@@ -234,6 +243,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint32_t first = (kb | k) != 0;
+              if constexpr (GRU) { if (p.gru_debug & 1) continue; }
               if constexpr (PAIR) {
                 umma_bf16_2cta(d_tmem, ah + 2 * k, wh + 2 * k, idesc, first);
                 umma_bf16_2cta(d_tmem + BN, ah + 2 * k, wl + 2 * k, idesc, first);
@@ -275,107 +285,108 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127 (GRU: 0..255)
     int acc = 0; uint32_t acc_phase = 0;
     int pbuf = 0;
-    for (int gt = GRU ? p.gru_t : 0; gt < (GRU ? p.gru_t_end : 1); ++gt)
-    for (int tile = tile0; tile < num_tiles; tile += tile_step, pbuf ^= 1) {
-      const int m_blk = tile_m(tile), n_blk = tile % p.tiles_n;
-      const int n0 = n_blk * BN;
-      // stage this tile's per-column parameters; double buffered by tile parity (not by accumulator: a single-buffered
-      // accumulator would let a fast warp overwrite what a slow one still reads; the barrier below orders buffer reuse)
-      float* ps = params_smem + pbuf * 3 * BN;
-      for (int c = et; c < BN; c += EPI_THREADS_K) {
-        const int n = n0 + c;
-        const bool ok = n < p.N;
-        ps[c] = (ok && p.scale) ? p.scale[n] : 1.f;
-        if constexpr (GRU) ps[BN + c] = p.gru_bhh[(c / 64) * p.gru_H + n_blk * 64 + (c % 64)];   // column c = gate c/64, unit c%64
-        else ps[BN + c] = (ok && p.bias) ? p.bias[n] : 0.f;
-        ps[2 * BN + c] = (ok && p.logit_w) ? p.logit_w[n] : 0.f;
-      }
-      if constexpr (GRU) {
-        // the table row of this step does not depend on the GEMM: pull this thread's 3 x 32 entries into L2 while the
-        // main loop runs (the table is hundreds of MB, its rows are scattered: an HBM round trip per chunk otherwise)
-        const int prow = m_blk * BM + ((warp - EPI_WARP0) & 3) * 32 + lane;
-        if (prow < p.M) {
-          long long ptok = p.gru_tokens[(size_t)prow * p.gru_T + gt];
-          ptok = ptok < 0 ? 0 : (ptok >= p.gru_rows ? p.gru_rows - 1 : ptok);
-          const float* pg = p.gru_table + (size_t)ptok * 3 * p.gru_H + n_blk * 64 + ((warp - EPI_WARP0) >> 2) * 32;
+    if constexpr (GRU) {
+      // ===== GRU step epilogue (modules.py:153, torch GRU semantics): r = σ(gi_r + gh_r), z = σ(gi_z + gh_z),
+      //       n = tanh(gi_n + r·gh_n), h' = (1 - z)·n + z·h; gh = the tile's accumulators + b_hh, gi = the token's table row.
+      // Thread = (row, UT units of the tile).  One launch for all steps: the thread owns the same rows / units in every step
+      // (at most two tiles per pair and step), so the fp32 state stays in registers between steps.
+      static_assert(SPLIT && BN == 96 && PAIR, "GRU step: 32 units x [r|z|n] per pair tile, fp32-class mode");
+      constexpr int U = BN / 3, UT = U / (GRU_EPI_WARPS / 4);        // 16 units per thread
+      static_assert(UT == 16, "one 16-column TMEM load per gate");
+      const int H = p.gru_H;
+      const int c = ((warp - EPI_WARP0) >> 2) * UT;                   // this thread's first unit within the tile
+      auto process_tile = [&](int gt, int tile, float (&h)[UT], bool load_h, bool store_h) {
+        const int m_blk = tile_m(tile), n_blk = tile % p.tiles_n;
+        const int u0 = n_blk * U;
+        const int row = m_blk * BM + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        float* ps = params_smem + pbuf * 3 * BN;
+        for (int i = et; i < BN; i += EPI_THREADS_K) ps[BN + i] = p.gru_bhh[(i / U) * H + u0 + (i % U)];   // column = gate·U + unit
+        long long tok = row_ok ? p.gru_tokens[(size_t)row * p.gru_T + gt] : 0;
+        tok = tok < 0 ? 0 : (tok >= p.gru_rows ? p.gru_rows - 1 : tok);
+        const float* gi = p.gru_table + (size_t)tok * 3 * H + u0 + c;
+        if (row_ok) {
+          // the table row does not depend on the GEMM: pull this thread's entries into L2 while the main loop runs
 #pragma unroll
           for (int gate = 0; gate < 3; ++gate)
 #pragma unroll
-            for (int sct = 0; sct < 4; ++sct) asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + gate * p.gru_H + sct * 8));
-        }
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS_K) : "memory");
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
-
-      const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      if constexpr (GRU) {
-        // ---- GRU step (modules.py:153, torch GRU semantics): r = σ(gi_r + gh_r), z = σ(gi_z + gh_z),
-        //      n = tanh(gi_n + r·gh_n), h' = (1 - z)·n + z·h; gh = this tile's accumulators + b_hh
-        static_assert(SPLIT && BN == 192, "GRU step: 64 units x [r|z|n] per tile, fp32-class mode");
-        const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
-        const int H = p.gru_H, u0 = n_blk * 64;
-        long long tok = row_ok ? p.gru_tokens[(size_t)row * p.gru_T + gt] : 0;
-        tok = tok < 0 ? 0 : (tok >= p.gru_rows ? p.gru_rows - 1 : tok);
-        const float* gi = p.gru_table + (size_t)tok * 3 * H + u0;
-        const float* hp = p.gru_h + (size_t)(row_ok ? row : 0) * H + u0;
-        const bool final_step = gt == p.gru_T - 1;
-        float* h_dst = (final_step && p.gru_hout_last) ? p.gru_hout_last : p.gru_h;
-        char* pl_dst = (final_step && p.gru_planes_last) ? reinterpret_cast<char*>(p.gru_planes_last)
-                                                         : reinterpret_cast<char*>(p.gru_planes) + (size_t)(gt & 1) * 2 * p.out_plane;
-        const int c_begin = ((warp - EPI_WARP0) >> 2) * (64 / (GRU_EPI_WARPS / 4));
-#pragma unroll 1
-        for (int c = c_begin; c < c_begin + 64 / (GRU_EPI_WARPS / 4); c += 16) {
-          uint32_t mr[16], cr[16], mz[16], cz[16], mn[16], cn[16];
-          tmem_ld_32x16(t_row + c, mr);        tmem_ld_32x16(t_row + BN + c, cr);
-          tmem_ld_32x16(t_row + 64 + c, mz);   tmem_ld_32x16(t_row + BN + 64 + c, cz);
-          tmem_ld_32x16(t_row + 128 + c, mn);  tmem_ld_32x16(t_row + BN + 128 + c, cn);
-          tmem_ld_wait();
-          if (!row_ok) continue;
-          float hn[16];
+            for (int sct = 0; sct < UT / 8; ++sct) asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + gate * H + sct * 8));
+          if (load_h) {
+            const float* hp = p.gru_h + (size_t)row * H + u0 + c;
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 gr4 = __ldg(reinterpret_cast<const float4*>(gi + c) + j4);
-            const float4 gz4 = __ldg(reinterpret_cast<const float4*>(gi + H + c) + j4);
-            const float4 gn4 = __ldg(reinterpret_cast<const float4*>(gi + 2 * H + c) + j4);
-            const float4 hp4 = *(reinterpret_cast<const float4*>(hp + c) + j4);
-            const float gir[4] = {gr4.x, gr4.y, gr4.z, gr4.w}, giz[4] = {gz4.x, gz4.y, gz4.z, gz4.w};
-            const float gin[4] = {gn4.x, gn4.y, gn4.z, gn4.w}, hpv[4] = {hp4.x, hp4.y, hp4.z, hp4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = 4 * j4 + e;
-              const float ghr = fmaf(__uint_as_float(cr[j]), 0x1p-11f, __uint_as_float(mr[j])) + ps[BN + c + j];
-              const float ghz = fmaf(__uint_as_float(cz[j]), 0x1p-11f, __uint_as_float(mz[j])) + ps[BN + 64 + c + j];
-              const float ghn = fmaf(__uint_as_float(cn[j]), 0x1p-11f, __uint_as_float(mn[j])) + ps[BN + 128 + c + j];
-              const float r = 1.f / (1.f + expf(-(gir[e] + ghr)));
-              const float z = 1.f / (1.f + expf(-(giz[e] + ghz)));
-              const float n = tanhf(gin[e] + r * ghn);
-              hn[j] = (1.f - z) * n + z * hpv[e];
+            for (int j4 = 0; j4 < UT / 4; ++j4) {
+              const float4 v = *(reinterpret_cast<const float4*>(hp) + j4);
+              h[4 * j4] = v.x; h[4 * j4 + 1] = v.y; h[4 * j4 + 2] = v.z; h[4 * j4 + 3] = v.w;
             }
           }
-          float* ho = h_dst + (size_t)row * H + u0 + c;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS_K) : "memory");
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        const uint32_t t_row = tmem_base + acc * C::ACC_STRIDE + ((uint32_t)(q * 32) << 16);
+        const bool live = row_ok && !(p.gru_debug & 4);
+        float4 g4[2][UT / 4];                                       // gi_r, gi_z: in flight together with the TMEM loads
+        if (live) {
+#pragma unroll
+          for (int gate = 0; gate < 2; ++gate)
+#pragma unroll
+            for (int j4 = 0; j4 < UT / 4; ++j4) g4[gate][j4] = __ldg(reinterpret_cast<const float4*>(gi + gate * H) + j4);
+        }
+        float ghr[UT], ghz[UT], ghn[UT];
+        {
+          uint32_t mr[16], cr[16], mz[16], cz[16], mn[16], cn[16];
+          tmem_ld_32x16(t_row + c, mr);          tmem_ld_32x16(t_row + BN + c, cr);
+          tmem_ld_32x16(t_row + U + c, mz);      tmem_ld_32x16(t_row + BN + U + c, cz);
+          tmem_ld_32x16(t_row + 2 * U + c, mn);  tmem_ld_32x16(t_row + BN + 2 * U + c, cn);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < UT; ++j) {
+            ghr[j] = fmaf(__uint_as_float(cr[j]), 0x1p-11f, __uint_as_float(mr[j])) + ps[BN + c + j];
+            ghz[j] = fmaf(__uint_as_float(cz[j]), 0x1p-11f, __uint_as_float(mz[j])) + ps[BN + U + c + j];
+            ghn[j] = fmaf(__uint_as_float(cn[j]), 0x1p-11f, __uint_as_float(mn[j])) + ps[BN + 2 * U + c + j];
+          }
+        }
+        tcgen05_fence_before();                                     // accumulator in registers: hand it back to the MMA thread
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+        if (live) {
+          float4 gn4[UT / 4];                                       // gi_n: an L2 hit, in flight under the r / z arithmetic
+#pragma unroll
+          for (int j4 = 0; j4 < UT / 4; ++j4) gn4[j4] = __ldg(reinterpret_cast<const float4*>(gi + 2 * H) + j4);
+          const float* gr = reinterpret_cast<const float*>(g4[0]);
+          const float* gz = reinterpret_cast<const float*>(g4[1]);
+          const float* gn = reinterpret_cast<const float*>(gn4);
+#pragma unroll
+          for (int j = 0; j < UT; ++j) {
+            const float r = 1.f / (1.f + expf(-(gr[j] + ghr[j])));
+            const float z = 1.f / (1.f + expf(-(gz[j] + ghz[j])));
+            ghr[j] = r; ghz[j] = z;
+          }
+#pragma unroll
+          for (int j = 0; j < UT; ++j) {
+            const float n = tanhf(gn[j] + ghr[j] * ghn[j]);
+            h[j] = (1.f - ghz[j]) * n + ghz[j] * h[j];
+          }
+          const bool final_step = gt == p.gru_T - 1;
+          char* pl_dst = (final_step && p.gru_planes_last) ? reinterpret_cast<char*>(p.gru_planes_last)
+                                                           : reinterpret_cast<char*>(p.gru_planes) + (size_t)(gt & 1) * 2 * p.out_plane;
           __half* oh = reinterpret_cast<__half*>(pl_dst) + (size_t)row * H + u0 + c;
           __half* ol = reinterpret_cast<__half*>(pl_dst + p.out_plane) + (size_t)row * H + u0 + c;
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4)
-            reinterpret_cast<float4*>(ho)[j4] = make_float4(hn[4 * j4], hn[4 * j4 + 1], hn[4 * j4 + 2], hn[4 * j4 + 3]);
-#pragma unroll
-          for (int j8 = 0; j8 < 2; ++j8) {
+          for (int j8 = 0; j8 < UT / 8; ++j8) {
             uint4 rh, rl;
             uint32_t* ph = reinterpret_cast<uint32_t*>(&rh); uint32_t* pl = reinterpret_cast<uint32_t*>(&rl);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_f16x2_pair(hn[8 * j8 + 2 * e], hn[8 * j8 + 2 * e + 1], ph[e], pl[e]);
+            for (int e = 0; e < 4; ++e) split_f16x2_pair(h[8 * j8 + 2 * e], h[8 * j8 + 2 * e + 1], ph[e], pl[e]);
             reinterpret_cast<uint4*>(oh)[j8] = rh;
             reinterpret_cast<uint4*>(ol)[j8] = rl;
           }
-        }
-        tcgen05_fence_before();
-        if constexpr (PAIR) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
-        } else {
-          mbar_arrive(tempty_bar(acc));
+          if (store_h) {
+            float* ho = ((final_step && p.gru_hout_last) ? p.gru_hout_last : p.gru_h) + (size_t)row * H + u0 + c;
+#pragma unroll
+            for (int j4 = 0; j4 < UT / 4; ++j4)
+              reinterpret_cast<float4*>(ho)[j4] = make_float4(h[4 * j4], h[4 * j4 + 1], h[4 * j4 + 2], h[4 * j4 + 3]);
+          }
         }
         if (p.gru_counter != nullptr && gt + 1 < p.gru_t_end) {
           // publish this tile's part of h_t (see gru_pair.cu: the release of the one thread that bumps the counter is
@@ -388,8 +399,49 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (++acc == C::NACC) { acc = 0; acc_phase ^= 1; }
-        continue;
+        pbuf ^= 1;
+      };
+      if (p.gru_counter != nullptr) {
+        // all steps in this launch, at most two tiles per pair and step: state in registers
+        float h0[UT], h1[UT];
+#pragma unroll
+        for (int j = 0; j < UT; ++j) h0[j] = h1[j] = 0.f;
+        for (int gt = p.gru_t; gt < p.gru_t_end; ++gt) {
+          const bool first = gt == p.gru_t, last = gt + 1 == p.gru_t_end;
+          if (tile0 < num_tiles) process_tile(gt, tile0, h0, first, last);
+          if (tile0 + tile_step < num_tiles) process_tile(gt, tile0 + tile_step, h1, first, last);
+        }
+      } else {
+        // one step per launch (any number of tiles per pair): state through global memory
+        for (int gt = p.gru_t; gt < p.gru_t_end; ++gt)
+          for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+            float h[UT];
+#pragma unroll
+            for (int j = 0; j < UT; ++j) h[j] = 0.f;
+            process_tile(gt, tile, h, true, true);
+          }
       }
+    }
+    for (int gt = GRU ? p.gru_t : 0; gt < (GRU ? 0 : 1); ++gt)
+    for (int tile = tile0; tile < num_tiles; tile += tile_step, pbuf ^= 1) {
+      const int m_blk = tile_m(tile), n_blk = tile % p.tiles_n;
+      const int n0 = n_blk * BN;
+      // stage this tile's per-column parameters; double buffered by tile parity (not by accumulator: a single-buffered
+      // accumulator would let a fast warp overwrite what a slow one still reads; the barrier below orders buffer reuse)
+      float* ps = params_smem + pbuf * 3 * BN;
+      for (int c = et; c < BN; c += EPI_THREADS_K) {
+        const int n = n0 + c;
+        const bool ok = n < p.N;
+        ps[c] = (ok && p.scale) ? p.scale[n] : 1.f;
+        ps[BN + c] = (ok && p.bias) ? p.bias[n] : 0.f;
+        ps[2 * BN + c] = (ok && p.logit_w) ? p.logit_w[n] : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS_K) : "memory");
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
       const float* mul_row = p.mul ? p.mul + (size_t)((row_ok ? row : 0) / p.mul_row_div) * p.ld_mul : nullptr;
       const bool mul_vec = p.mul && ((p.ld_mul & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mul) & 15) == 0);
       const float* add_row = p.add ? p.add + (size_t)((row_ok ? row : 0) / p.add_row_div) * p.ld_add : nullptr;
@@ -871,7 +923,10 @@ static int launch_bn(const vqa_linear_args& a, cudaStream_t s) {
 // packed W_hh: 64 units x [r|z|n]) with the gate update as the epilogue.  VQA_ERR_UNSUPPORTED when the device cannot hold
 // the pairs (the caller then runs the GEMM and the gate kernel separately).
 static int gru_step_split(const GruStepSplit& g, cudaStream_t s) {
-  constexpr int BN = 192;
+  // 32 units x [r|z|n] per tile: at B = 1024 every CTA pair owns TWO tiles of a step (two different row blocks), so the
+  // tensor core runs one tile's MMAs while the 8 epilogue warps do the other tile's gate update (measured by switching
+  // pieces off, 64-unit tiles: the gate update was 11 of a step's 28 us, the MMAs 7, and they ran one after the other)
+  constexpr int BN = 96;
   using C = Cfg<BN, true, true>;
   auto kern = linear_tc_kernel<BN, false, false, true, true, true>;
   static DeviceInt cache;
@@ -889,7 +944,7 @@ static int gru_step_split(const GruStepSplit& g, cudaStream_t s) {
     }
     (void)cudaGetLastError();
   }
-  if (pairs_resident <= 0 || g.H % 64 != 0) return VQA_ERR_UNSUPPORTED;
+  if (pairs_resident <= 0 || g.H % 32 != 0) return VQA_ERR_UNSUPPORTED;
   CUtensorMap tmA, tmW, tmW2;
   int rc;
   const size_t a_plane = (size_t)g.B * g.H * 2, w_plane = (size_t)3 * g.H * g.H * 2;
@@ -908,6 +963,9 @@ static int gru_step_split(const GruStepSplit& g, cudaStream_t s) {
   p.gru_tokens = (const long long*)g.tokens; p.gru_table = g.gi_table; p.gru_bhh = g.b_hh; p.gru_h = g.h;
   p.gru_hout_last = g.h_out_last; p.gru_planes = g.h_planes; p.gru_planes_last = g.h_planes_last;
   p.gru_T = g.T; p.gru_H = g.H; p.gru_rows = g.ntoken_rows;
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("VQA_B200_GRUS_DEBUG"); dbg = e ? atoi(e) : 0; }
+  p.gru_debug = dbg;
   p.tile_begin = 0; p.tile_end = ((p.tiles_m + 1) / 2) * p.tiles_n;
   // every tile on its own CTA pair, all of them resident: ONE launch for all steps, steps chained by the row-block
   // counters (VQA_B200_GRU_SPLIT_PERSIST=0: one launch per step).  Otherwise one launch per step.
@@ -916,8 +974,10 @@ static int gru_step_split(const GruStepSplit& g, cudaStream_t s) {
     const char* e = getenv("VQA_B200_GRU_SPLIT_PERSIST");
     persist_env = e ? ((e[0] == '0') ? 0 : 1) : (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") ? 0 : 1);
   }
-  const bool persist = persist_env && p.tile_end <= pairs_resident && g.counter != nullptr && p.tiles_m <= 62 && g.t_end - g.t > 1;
-  const int pairs = p.tile_end < pairs_resident ? p.tile_end : pairs_resident;
+  // one launch for all steps when every CTA pair (all of them resident) owns at most two tiles of a step
+  int pairs = p.tile_end <= pairs_resident ? p.tile_end : (p.tile_end + 1) / 2;
+  const bool persist = persist_env && pairs <= pairs_resident && g.counter != nullptr && p.tiles_m <= 62 && g.t_end - g.t > 1;
+  if (!persist) pairs = p.tile_end < pairs_resident ? p.tile_end : pairs_resident;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(GRU_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = s;
   cudaLaunchAttribute at[2];

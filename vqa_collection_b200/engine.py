@@ -142,11 +142,11 @@ def prepare_weights(W: dict, dtype: torch.dtype, device, relation: bool, gcn_lay
     P["b_hh"] = dev(f32(W[r + "bias_hh_l0"]))
     H = P["w_hh"].shape[-1]
     if split:
-        # gate-interleaved W_hh planes: 192-row block j = [r | z | n] rows of units [64j, 64j+64), one GEMM tile per block, so
+        # gate-interleaved W_hh planes: 96-row block j = [r | z | n] rows of units [32j, 32j+32), one GEMM tile per block, so
         # the gate update can be the step GEMM's epilogue
-        if H % 64 == 0:
+        if H % 32 == 0:
             w_hh32 = f32(W[r + "weight_hh_l0"])
-            P["wh_packed"] = ops.split_f32(_dev(pack_gru(w_hh32, w_hh32, P["b_ih"].cpu(), P["b_hh"].cpu())[1]))
+            P["wh_packed"] = ops.split_f32(_dev(pack_gru(w_hh32, w_hh32, P["b_ih"].cpu(), P["b_hh"].cpu(), units=32)[1]))
         # the input half of the gates per token, f32: W_ih·emb[v] + b_ih (vqa_gru_args.d_gi_table in the f16x2 mode)
         P["gi_table"] = _token_table_f32(emb, f32(W[r + "weight_ih_l0"]), P["b_ih"], device)
     if dtype == torch.bfloat16:
