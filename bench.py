@@ -556,7 +556,7 @@ def kernel_rooflines_split(ctx, args, eng, imgs, toks):
                 "note": "achieved counts the three MMAs per k-step that the split arithmetic issues"})
     ms = time_kernel(lambda i: ops.gru_last_state_split(toks[i % NB], P["gi_table"], P["w_hh"], P["b_hh"], P.get("wh_packed")), reps)
     alg = 2.0 * B * (T - 1) * 3 * H * H
-    out.append({"kernel": "gru_gate_table_kernel + linear_tc_kernel<192,pair,split,gru> (13 recurrent steps in one cooperative launch)",
+    out.append({"kernel": "gru_gate_table_kernel + linear_tc_kernel<96,pair,split,gru> (13 recurrent steps in one cooperative launch)",
                 "bound": "tensor", "achieved": 3 * alg / (ms / 1e3) / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": 3 * alg / (ms / 1e3) / 1e12 / pk["bf16_tflops"], "traffic": 13 * 33.5e6 * B / 1024,
                 "traffic_source": "profiles/r02b_ncu_gru_split.md (33.5 MB per step: token-table rows, W_hh planes, state; 13 steps)",

@@ -667,8 +667,9 @@ static SideCtx* side_ctx() {
 // 300 per mille is the best split of the wide ReGAT projection at B = 1024 (profiles/r02_overlap_split.md); the engine
 // can override the estimate (side_tile_permille).
 static int auto_side_permille(int tiles, int K, int T, int main_sms, int side_sms, bool token_table) {
-  // token-table GRU (no gather, no x-part): 186 instead of 232 us beside the GEMM at T = 14
-  const double tau = 12.5 * K / 2048.0, G = token_table ? 13.3 * T + 64.0 : 15.7 * T + 70.0;
+  // (the token-table GRU saves the gather launch; beside a running GEMM its steps take as long as the x-part form's —
+  // 216 us at T = 14 in both timelines — because the step is bound by the L2 -> SM stream it shares with the GEMM)
+  const double tau = 12.5 * K / 2048.0, G = 15.7 * T + (token_table ? 64.0 : 70.0);
   const double pt = main_sms / 2, ps = side_sms / 2;
   const double t_end = (tiles * tau + ps * G) / (pt + ps);
   double share = ps * (t_end - G) / tau / tiles;
