@@ -1,5 +1,6 @@
-"""compute-sanitizer target: the kernels added in round 2's second session on small shapes (fp32tc forward incl. the
-cooperative GRU-step kernel, split GEMM tile shapes, token-table bf16 GRU, relation labels for several K)."""
+"""Small-shape run of the kernels added in round 2's second session (fp32tc forward incl. the cooperative GRU-step kernel,
+split GEMM tile shapes, token-table bf16 GRU, relation labels for several K) with their errors against the oracle.  Written as
+a compute-sanitizer target; the tool is closed on this pool, so scripts/gpu_r2b_san.sh's plain run is what there is."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
